@@ -1,0 +1,286 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see vlo_util.h header).  C API consumed through ctypes by tests/, smoke() and
+// bench.py's cpu_baseline / --impl reference legs.
+#include "vlo_block.h"
+#include "vlo_gen.h"
+#include <thread>
+#include <atomic>
+#include <chrono>
+
+using namespace vlo;
+
+namespace {
+thread_local std::string g_err;
+struct FilterHandle { FP f; };
+struct BlockHandle { Block b; };
+
+// Packed string list: blob + (n+1) u64 offsets
+std::vector<sv> unpack(const uint8_t* blob, const uint64_t* offs, uint64_t n) {
+    std::vector<sv> v(n);
+    for (uint64_t i = 0; i < n; i++) v[i] = sv((const char*)blob + offs[i], offs[i + 1] - offs[i]);
+    return v;
+}
+template <class F> int guard(F&& f) {
+    try { f(); return 0; } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+}  // namespace
+
+extern "C" {
+
+const char* vlo_last_error() { return g_err.c_str(); }
+
+uint64_t vlo_xxh64(const void* p, uint64_t n) { return xxh64(p, n); }
+
+// tokenizeStrings: out blob gets tokens joined by '\n' (tokens never contain '\n'); returns length or -1
+int64_t vlo_tokenize_strings(const uint8_t* blob, const uint64_t* offs, uint64_t n, char* out, uint64_t cap) {
+    auto toks = tokenize_strings(unpack(blob, offs, n));
+    std::string s;
+    for (size_t i = 0; i < toks.size(); i++) { if (i) s.push_back('\n'); s += toks[i]; }
+    if (s.size() > cap) return -1;
+    memcpy(out, s.data(), s.size());
+    return (int64_t)s.size();
+}
+int64_t vlo_tokenize_hashes(const uint8_t* blob, const uint64_t* offs, uint64_t n, uint64_t* out, uint64_t cap) {
+    auto h = tokenize_hashes(unpack(blob, offs, n));
+    if (h.size() > cap) return -1;
+    memcpy(out, h.data(), h.size() * 8);
+    return (int64_t)h.size();
+}
+// appendTokensHashes for one token: 6 hashes
+void vlo_token_hashes(const void* tok, uint64_t n, uint64_t* out6) {
+    std::vector<uint64_t> v; append_hashes_hashes(v, xxh64(tok, n)); memcpy(out6, v.data(), 48);
+}
+// bloomFilterMarshalTokens bloomfilter.go:22-28 (tokens are NOT deduplicated here, like the reference)
+int64_t vlo_bloom_marshal_tokens(const uint8_t* blob, const uint64_t* offs, uint64_t n, uint8_t* out, uint64_t cap) {
+    auto toks = unpack(blob, offs, n);
+    std::vector<uint64_t> hashes;
+    for (auto t : toks) hashes.push_back(xxh64(t));
+    BloomFilter bf; bf.init_hashes(hashes);
+    std::string m = bf.marshal();
+    if (m.size() > cap) return -1;
+    memcpy(out, m.data(), m.size());
+    return (int64_t)m.size();
+}
+int vlo_bloom_contains_all_tokens(const uint8_t* bloom, uint64_t bloom_len, const uint8_t* blob, const uint64_t* offs, uint64_t n) {
+    BloomFilter bf; if (!bf.unmarshal(sv((const char*)bloom, bloom_len))) return -1;
+    std::vector<std::string> toks; for (auto t : unpack(blob, offs, n)) toks.emplace_back(t);
+    return bf.contains_all(tokens_hashes(toks)) ? 1 : 0;
+}
+
+int vlo_match_phrase(const void* s, uint64_t sl, const void* p, uint64_t pl) { return match_phrase(sv((const char*)s, sl), sv((const char*)p, pl)); }
+int vlo_match_prefix(const void* s, uint64_t sl, const void* p, uint64_t pl) { return match_prefix(sv((const char*)s, sl), sv((const char*)p, pl)); }
+int64_t vlo_skip_first_last_token(const void* s, uint64_t sl, char* out, uint64_t cap) {
+    std::string r = skip_first_last_token(sv((const char*)s, sl));
+    if (r.size() > cap) return -1;
+    memcpy(out, r.data(), r.size()); return (int64_t)r.size();
+}
+// returns 1/0, or -1 on regex compile error
+int vlo_regex_match(const void* expr, uint64_t el, const void* s, uint64_t sl) {
+    int r = -1;
+    if (guard([&] { Regex re(sv((const char*)expr, el)); r = re.match_string(sv((const char*)s, sl)) ? 1 : 0; })) return -1;
+    return r;
+}
+// Describe regexutil.Regex fields as text (for tests / debugging)
+int64_t vlo_regex_describe(const void* expr, uint64_t el, char* out, uint64_t cap) {
+    std::string d;
+    if (guard([&] {
+            Regex re(sv((const char*)expr, el));
+            d = "prefix=" + re.prefix + "\nisOnlyPrefix=" + std::to_string(re.isOnlyPrefix) + "\nisSuffixDotStar=" + std::to_string(re.isSuffixDotStar) +
+                "\nisSuffixDotPlus=" + std::to_string(re.isSuffixDotPlus) + "\nsubstrDotStar=" + re.substrDotStar + "\nsubstrDotPlus=" + re.substrDotPlus + "\norValues=";
+            for (auto& v : re.orValues) d += "[" + v + "]";
+            d += "\nliterals=";
+            for (auto& v : re.get_literals()) d += "[" + v + "]";
+        })) return -1;
+    if (d.size() > cap) return -1;
+    memcpy(out, d.data(), d.size()); return (int64_t)d.size();
+}
+
+// parse helpers: return 1 ok / 0 fail
+int vlo_try_parse_uint64(const void* s, uint64_t n, uint64_t* out) { return try_parse_uint64(sv((const char*)s, n), out); }
+int vlo_try_parse_int64(const void* s, uint64_t n, int64_t* out) { return try_parse_int64(sv((const char*)s, n), out); }
+int vlo_try_parse_float64(const void* s, uint64_t n, double* out) { return try_parse_float64_exact(sv((const char*)s, n), out); }
+int vlo_try_parse_ipv4(const void* s, uint64_t n, uint32_t* out) { return try_parse_ipv4(sv((const char*)s, n), out); }
+int vlo_try_parse_iso8601(const void* s, uint64_t n, int64_t* out) { return try_parse_timestamp_iso8601(sv((const char*)s, n), out); }
+int64_t vlo_encoded_to_string(int vt, const void* v, uint64_t n, char* out, uint64_t cap) {
+    std::string r;
+    if (guard([&] { r = encoded_to_string((uint8_t)vt, sv((const char*)v, n)); })) return -1;
+    if (r.size() > cap) return -1;
+    memcpy(out, r.data(), r.size()); return (int64_t)r.size();
+}
+
+// strings block codec
+int64_t vlo_marshal_strings_block(const uint8_t* blob, const uint64_t* offs, uint64_t n, uint8_t* out, uint64_t cap) {
+    std::string r;
+    if (guard([&] { r = marshal_strings_block(unpack(blob, offs, n)); })) return -1;
+    if (r.size() > cap) return -1;
+    memcpy(out, r.data(), r.size()); return (int64_t)r.size();
+}
+// decodes to the post-zstd stage; lens_items/data buffers; returns 0 ok
+int vlo_decode_values_block(const uint8_t* src, uint64_t n, uint8_t* lens_out, uint64_t* lens_len, uint8_t* data_out, uint64_t* data_len) {
+    return guard([&] {
+        DecodedStringsBlock d = decode_values_block_stage(sv((const char*)src, n));
+        if (d.lens_items.size() > *lens_len || d.data.size() > *data_len) throw std::runtime_error("output buffer too small");
+        memcpy(lens_out, d.lens_items.data(), d.lens_items.size()); *lens_len = d.lens_items.size();
+        memcpy(data_out, d.data.data(), d.data.size()); *data_len = d.data.size();
+    });
+}
+// full unmarshal into packed strings: out_offs has items+1 entries
+int vlo_unmarshal_strings_block(const uint8_t* src, uint64_t n, uint64_t items, uint8_t* out, uint64_t cap, uint64_t* out_offs) {
+    return guard([&] {
+        DecodedStringsBlock d = decode_values_block_stage(sv((const char*)src, n));
+        auto vals = unmarshal_strings(d, items);
+        uint64_t off = 0;
+        for (uint64_t i = 0; i < items; i++) {
+            if (off + vals[i].size() > cap) throw std::runtime_error("output buffer too small");
+            memcpy(out + off, vals[i].data(), vals[i].size()); out_offs[i] = off; off += vals[i].size();
+        }
+        out_offs[items] = off;
+    });
+}
+
+// ---- blocks ------------------------------------------------------------------------------------------------------
+// names: packed list of ncols names; values: packed list of ncols*rows strings, column-major
+void* vlo_block_build(const uint8_t* names_blob, const uint64_t* names_offs, uint64_t ncols, const uint8_t* vals_blob, const uint64_t* vals_offs, uint64_t rows) {
+    BlockHandle* h = nullptr;
+    if (guard([&] {
+            auto names = unpack(names_blob, names_offs, ncols);
+            auto vals = unpack(vals_blob, vals_offs, ncols * rows);
+            std::vector<std::string> nm; std::vector<std::vector<sv>> cols(ncols);
+            for (uint64_t c = 0; c < ncols; c++) { nm.emplace_back(names[c]); cols[c].assign(vals.begin() + c * rows, vals.begin() + (c + 1) * rows); }
+            h = new BlockHandle{build_block(nm, cols, rows)};
+        })) return nullptr;
+    return h;
+}
+void vlo_block_free(void* h) { delete (BlockHandle*)h; }
+uint64_t vlo_block_rows(void* h) { return ((BlockHandle*)h)->b.rows; }
+uint64_t vlo_block_ncolumns(void* h) { return ((BlockHandle*)h)->b.columns.size(); }
+uint64_t vlo_block_nconsts(void* h) { return ((BlockHandle*)h)->b.consts.size(); }
+// column accessors: pointers stay valid while the block lives
+struct vlo_column_view {
+    const char* name; uint64_t name_len;
+    uint32_t value_type; uint32_t dict_len;
+    uint64_t min_value, max_value;
+    const char* dict_ptr[8]; uint64_t dict_lens[8];
+    const uint8_t* values_block; uint64_t values_block_len;
+    const uint8_t* bloom; uint64_t bloom_len;
+};
+void vlo_block_column(void* h, uint64_t i, vlo_column_view* v) {
+    const Column& c = ((BlockHandle*)h)->b.columns[i];
+    memset(v, 0, sizeof *v);
+    v->name = c.name.data(); v->name_len = c.name.size(); v->value_type = c.valueType; v->dict_len = (uint32_t)c.dict.size();
+    v->min_value = c.minValue; v->max_value = c.maxValue;
+    for (size_t k = 0; k < c.dict.size(); k++) { v->dict_ptr[k] = c.dict[k].data(); v->dict_lens[k] = c.dict[k].size(); }
+    v->values_block = (const uint8_t*)c.valuesBlock.data(); v->values_block_len = c.valuesBlock.size();
+    v->bloom = (const uint8_t*)c.bloom.data(); v->bloom_len = c.bloom.size();
+}
+void vlo_block_const(void* h, uint64_t i, const char** name, uint64_t* name_len, const char** value, uint64_t* value_len) {
+    const ConstColumn& c = ((BlockHandle*)h)->b.consts[i];
+    *name = c.name.data(); *name_len = c.name.size(); *value = c.value.data(); *value_len = c.value.size();
+}
+
+// ---- filters -----------------------------------------------------------------------------------------------------
+void* vlo_filter_phrase(const void* f, uint64_t fl, const void* p, uint64_t pl) { return new FilterHandle{std::make_shared<FilterPhrase>(sv((const char*)f, fl), sv((const char*)p, pl))}; }
+void* vlo_filter_prefix(const void* f, uint64_t fl, const void* p, uint64_t pl) { return new FilterHandle{std::make_shared<FilterPrefix>(sv((const char*)f, fl), sv((const char*)p, pl))}; }
+void* vlo_filter_exact(const void* f, uint64_t fl, const void* p, uint64_t pl) { return new FilterHandle{std::make_shared<FilterExact>(sv((const char*)f, fl), sv((const char*)p, pl))}; }
+void* vlo_filter_in(const void* f, uint64_t fl, const uint8_t* blob, const uint64_t* offs, uint64_t n) {
+    std::vector<std::string> vals; for (auto v : unpack(blob, offs, n)) vals.emplace_back(v);
+    return new FilterHandle{std::make_shared<FilterIn>(sv((const char*)f, fl), vals)};
+}
+void* vlo_filter_regexp(const void* f, uint64_t fl, const void* p, uint64_t pl) {
+    FilterHandle* h = nullptr;
+    if (guard([&] { h = new FilterHandle{std::make_shared<FilterRegexp>(sv((const char*)f, fl), sv((const char*)p, pl))}; })) return nullptr;
+    return h;
+}
+void* vlo_filter_noop() { return new FilterHandle{std::make_shared<FilterNoop>()}; }
+void* vlo_filter_and(void** hs, uint64_t n) { std::vector<FP> v; for (uint64_t i = 0; i < n; i++) v.push_back(((FilterHandle*)hs[i])->f); return new FilterHandle{std::make_shared<FilterAnd>(v)}; }
+void* vlo_filter_or(void** hs, uint64_t n) { std::vector<FP> v; for (uint64_t i = 0; i < n; i++) v.push_back(((FilterHandle*)hs[i])->f); return new FilterHandle{std::make_shared<FilterOr>(v)}; }
+void* vlo_filter_not(void* h) { return new FilterHandle{std::make_shared<FilterNot>(((FilterHandle*)h)->f)}; }
+void vlo_filter_free(void* h) { delete (FilterHandle*)h; }
+// tokens of a leaf filter joined by '\n' (for tests of getTokens())
+int64_t vlo_filter_tokens(void* h, char* out, uint64_t cap) {
+    std::string field; std::vector<std::string> toks;
+    if (!((FilterHandle*)h)->f->leaf_tokens(&field, &toks)) return -1;
+    std::string s; for (size_t i = 0; i < toks.size(); i++) { if (i) s.push_back('\n'); s += toks[i]; }
+    if (s.size() > cap) return -1;
+    memcpy(out, s.data(), s.size()); return (int64_t)s.size();
+}
+
+// blockSearch.search for one block: out_words must hold ceil(rows/64) u64. stats (6 u64, may be NULL) are ACCUMULATED.
+int vlo_block_search(void* block, void* filter, uint64_t* out_words, uint64_t* stats6) {
+    return guard([&] {
+        BlockSearch bs; Bitmap bm; ScanStats st;
+        block_search(bs, ((BlockHandle*)block)->b, *((FilterHandle*)filter)->f, bm, stats6 ? &st : nullptr);
+        memcpy(out_words, bm.a.data(), bm.a.size() * 8);
+        if (stats6) { stats6[0] += st.blocks; stats6[1] += st.rows; stats6[2] += st.bloom_probe_bytes; stats6[3] += st.values_bytes; stats6[4] += st.bitmap_bytes; stats6[5] += st.blocks_values_read; }
+    });
+}
+
+// ---- synthetic generator (CPU restatement of victorialogs_b200/csrc/gen.cuh; see vlo_gen.h) ---------------------------
+void* vlo_gen_block(const vlo_gen_config* cfg, uint64_t block_id) {
+    BlockHandle* h = nullptr;
+    if (guard([&] { h = new BlockHandle{gen_block(*cfg, block_id)}; })) return nullptr;
+    return h;
+}
+// raw generated rows of one column (before encoding), packed; for tests
+int vlo_gen_rows(const vlo_gen_config* cfg, uint64_t block_id, int column, uint8_t* out, uint64_t cap, uint64_t* out_offs) {
+    return guard([&] {
+        uint64_t rows = gen_block_rows(*cfg, block_id);
+        uint64_t off = 0;
+        for (uint64_t i = 0; i < rows; i++) {
+            std::string s = gen_value(*cfg, block_id, i, column);
+            if (off + s.size() > cap) throw std::runtime_error("output buffer too small");
+            memcpy(out + off, s.data(), s.size()); out_offs[i] = off; off += s.size();
+        }
+        out_offs[rows] = off;
+    });
+}
+
+// Multi-threaded scan over generated blocks [block_lo, block_hi): the CPU baseline ("port").
+// Blocks are statically sharded across threads like Storage.search workers (storage_search.go:1040-1067).
+// mode 0: build blocks outside the timed region, time only blockSearch over pre-built (zstd-compressed) blocks ("with-zstd");
+// Returns seconds spent scanning in *secs; accumulates stats; out_counts (may be NULL) gets per-block match counts;
+// out_digest gets xor of xxh64(bitmap words) keyed by block id.
+int vlo_scan_generated(const vlo_gen_config* cfg, void* filter, uint64_t block_lo, uint64_t block_hi, int threads, double* secs,
+                       uint64_t* stats6, uint32_t* out_counts, uint64_t* out_digest, uint64_t* total_matches) {
+    return guard([&] {
+        uint64_t nb = block_hi - block_lo;
+        std::vector<Block> blocks(nb);
+        {
+            std::vector<std::thread> th; std::atomic<uint64_t> next{0};
+            for (int t = 0; t < threads; t++) th.emplace_back([&] { for (;;) { uint64_t i = next++; if (i >= nb) break; blocks[i] = gen_block(*cfg, block_lo + i); } });
+            for (auto& t : th) t.join();
+        }
+        std::vector<ScanStats> sts(threads); std::vector<uint64_t> digs(threads, 0), tots(threads, 0);
+        std::vector<std::string> errs(threads);
+        // rebuild the filter per thread is unnecessary: filters are immutable after by_field_tokens() is initialised
+        Filter& f = *((FilterHandle*)filter)->f;
+        { BlockSearch bs; Bitmap bm; if (nb) block_search(bs, blocks[0], f, bm, nullptr); }   // warm lazily-initialised token caches
+        auto t0 = std::chrono::steady_clock::now();
+        std::vector<std::thread> th;
+        for (int t = 0; t < threads; t++) th.emplace_back([&, t] {
+            try {
+                BlockSearch bs; Bitmap bm;
+                uint64_t lo = nb * t / threads, hi = nb * (t + 1) / threads;
+                for (uint64_t i = lo; i < hi; i++) {
+                    block_search(bs, blocks[i], f, bm, &sts[t]);
+                    uint64_t ones = bm.ones();
+                    if (out_counts) out_counts[i] = (uint32_t)ones;
+                    tots[t] += ones;
+                    uint64_t key = block_lo + i;
+                    digs[t] ^= xxh64(bm.a.data(), bm.a.size() * 8) * (2 * key + 1);
+                }
+            } catch (const std::exception& e) { errs[t] = e.what(); }
+        });
+        for (auto& t : th) t.join();
+        *secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        for (auto& e : errs) if (!e.empty()) throw std::runtime_error(e);
+        uint64_t dig = 0, tot = 0;
+        for (int t = 0; t < threads; t++) {
+            dig ^= digs[t]; tot += tots[t];
+            if (stats6) { stats6[0] += sts[t].blocks; stats6[1] += sts[t].rows; stats6[2] += sts[t].bloom_probe_bytes; stats6[3] += sts[t].values_bytes; stats6[4] += sts[t].bitmap_bytes; stats6[5] += sts[t].blocks_values_read; }
+        }
+        if (out_digest) *out_digest = dig;
+        if (total_matches) *total_matches = tot;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,724 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see vlo_util.h header).
+//
+// Block builder (rows -> encoded column blocks + bloom filters), block search and the filter tree, restating
+//   lib/logstorage/block.go:107-175,202-320 (const-column detection, column.mustWriteTo)
+//   lib/logstorage/values_encoder.go:109-154,1141-1322 (valuesEncoder.encode order: dict,uint,int,float,ipv4,iso8601,string)
+//   lib/logstorage/block_search.go:207-226,232-324,411-474 (blockSearch.search / header + bloom + values access)
+//   lib/logstorage/bitmap.go:28-191
+//   lib/logstorage/filter_{phrase,prefix,exact,in,regexp,and,or,not,noop}.go, lib/logstorage/in_values.go
+#pragma once
+#include "vlo_util.h"
+#include "vlo_regex.h"
+#include <map>
+#include <memory>
+
+namespace vlo {
+
+enum ValueType : uint8_t { VT_UNKNOWN = 0, VT_STRING = 1, VT_DICT = 2, VT_UINT8 = 3, VT_UINT16 = 4, VT_UINT32 = 5, VT_UINT64 = 6,
+                           VT_FLOAT64 = 7, VT_IPV4 = 8, VT_ISO8601 = 9, VT_INT64 = 10 };
+static const size_t maxDictSizeBytes = 256, maxDictLen = 8, maxConstColumnValueSize = 256;
+
+struct Column {
+    std::string name;
+    uint8_t valueType = VT_STRING;
+    uint64_t minValue = 0, maxValue = 0;
+    std::vector<std::string> dict;
+    std::string valuesBlock;   // marshalStringsBlock(encoded values) == bytes at [valuesOffset, valuesOffset+valuesSize)
+    std::string bloom;         // bytes at [bloomFilterOffset, +bloomFilterSize): big-endian u64 words
+};
+struct ConstColumn { std::string name, value; };
+struct Block {
+    uint64_t rows = 0;
+    std::vector<Column> columns;
+    std::vector<ConstColumn> consts;
+};
+
+inline std::string canonical(sv name) { return name.empty() ? std::string("_msg") : std::string(name); }   // getCanonicalColumnName
+
+// ---- values encoder ---------------------------------------------------------------------------------------------
+struct EncodedValues { uint8_t vt; uint64_t minv = 0, maxv = 0; std::vector<std::string> values; std::vector<std::string> dict; };
+
+inline EncodedValues encode_values(const std::vector<sv>& values) {   // values_encoder.go:109-154
+    EncodedValues e; e.vt = VT_STRING;
+    if (values.empty()) return e;
+    // tryDictEncoding :1224-1241 + valuesDict.getOrAdd :1269-1288
+    {
+        std::vector<std::string> dict; bool ok = true;
+        std::vector<std::string> enc; enc.reserve(values.size());
+        for (sv v : values) {
+            if (v.size() > maxDictSizeBytes) { ok = false; break; }
+            size_t sz = 0; int id = -1;
+            for (size_t i = 0; i < dict.size(); i++) { if (dict[i] == v) { id = (int)i; break; } sz += dict[i].size(); }
+            if (id < 0) {
+                if (dict.size() >= maxDictLen || sz + v.size() > maxDictSizeBytes) { ok = false; break; }
+                dict.emplace_back(v); id = (int)dict.size() - 1;
+            }
+            enc.emplace_back(1, (char)id);
+        }
+        if (ok) { e.vt = VT_DICT; e.values = std::move(enc); e.dict = std::move(dict); return e; }
+    }
+    auto all = [&](auto parse, auto& arr) { arr.resize(values.size()); for (size_t i = 0; i < values.size(); i++) if (!parse(values[i], &arr[i])) return false; return true; };
+    {   // tryUintEncoding :1168-1222
+        std::vector<uint64_t> a;
+        if (all(try_parse_uint64, a)) {
+            uint64_t mn = a[0], mx = a[0];
+            for (uint64_t v : a) { mn = std::min(mn, v); mx = std::max(mx, v); }
+            int bits = mx ? 64 - __builtin_clzll(mx) : 0;
+            e.minv = mn; e.maxv = mx;
+            for (uint64_t v : a) {
+                std::string s;
+                if (bits <= 8) s.push_back((char)v); else if (bits <= 16) put_be16(s, (uint16_t)v); else if (bits <= 32) put_be32(s, (uint32_t)v); else put_be64(s, v);
+                e.values.push_back(std::move(s));
+            }
+            e.vt = bits <= 8 ? VT_UINT8 : bits <= 16 ? VT_UINT16 : bits <= 32 ? VT_UINT32 : VT_UINT64;
+            return e;
+        }
+    }
+    {   // tryIntEncoding :1141-1166
+        std::vector<int64_t> a;
+        if (all(try_parse_int64, a)) {
+            int64_t mn = a[0], mx = a[0];
+            for (int64_t v : a) { mn = std::min(mn, v); mx = std::max(mx, v); }
+            e.minv = (uint64_t)mn; e.maxv = (uint64_t)mx;
+            for (int64_t v : a) { std::string s; put_be64(s, zigzag(v)); e.values.push_back(std::move(s)); }
+            e.vt = VT_INT64; return e;
+        }
+    }
+    {   // tryFloat64Encoding :732-760
+        std::vector<double> a;
+        if (all(try_parse_float64_exact, a)) {
+            double mn = a[0], mx = a[0];
+            for (size_t i = 0; i < a.size(); i++) { if (i == 0 || a[i] < mn) mn = a[i]; if (i == 0 || a[i] > mx) mx = a[i]; }
+            memcpy(&e.minv, &mn, 8); memcpy(&e.maxv, &mx, 8);
+            for (double v : a) { uint64_t b; memcpy(&b, &v, 8); std::string s; put_be64(s, b); e.values.push_back(std::move(s)); }
+            e.vt = VT_FLOAT64; return e;
+        }
+    }
+    {   // tryIPv4Encoding :647-672
+        std::vector<uint32_t> a;
+        if (all(try_parse_ipv4, a)) {
+            uint32_t mn = a[0], mx = a[0];
+            for (uint32_t v : a) { mn = std::min(mn, v); mx = std::max(mx, v); }
+            e.minv = mn; e.maxv = mx;
+            for (uint32_t v : a) { std::string s; put_be32(s, v); e.values.push_back(std::move(s)); }
+            e.vt = VT_IPV4; return e;
+        }
+    }
+    {   // tryTimestampISO8601Encoding :308-333
+        std::vector<int64_t> a;
+        if (all(try_parse_timestamp_iso8601, a)) {
+            int64_t mn = a[0], mx = a[0];
+            for (int64_t v : a) { mn = std::min(mn, v); mx = std::max(mx, v); }
+            e.minv = (uint64_t)mn; e.maxv = (uint64_t)mx;
+            for (int64_t v : a) { std::string s; put_be64(s, (uint64_t)v); e.values.push_back(std::move(s)); }
+            e.vt = VT_ISO8601; return e;
+        }
+    }
+    e.vt = VT_STRING;
+    for (sv v : values) e.values.emplace_back(v);
+    return e;
+}
+
+// column.mustWriteTo block.go:134-175
+inline Column build_column(sv name, const std::vector<sv>& values) {
+    Column c; c.name = canonical(name);
+    EncodedValues e = encode_values(values);
+    c.valueType = e.vt; c.minValue = e.minv; c.maxValue = e.maxv; c.dict = e.dict;
+    c.valuesBlock = marshal_strings_block(e.values);
+    if (c.valueType != VT_DICT) {
+        BloomFilter bf; bf.init_hashes(tokenize_hashes(values));
+        c.bloom = bf.marshal();
+    }
+    return c;
+}
+
+// block.mustInitFromRows fast path (all rows have the same fields) block.go:232-253 + const detection :107-122.
+// Columns are given column-major: names[i], values[i][row]. Empty values mean "field missing in this row".
+inline Block build_block(const std::vector<std::string>& names, const std::vector<std::vector<sv>>& cols, uint64_t rows) {
+    Block b; b.rows = rows;
+    for (size_t i = 0; i < names.size(); i++) {
+        const auto& v = cols[i];
+        bool isconst = true;
+        if (!v.empty()) {
+            if (v[0].size() > maxConstColumnValueSize) isconst = false;
+            else for (size_t j = 1; j < v.size(); j++) if (v[j] != v[0]) { isconst = false; break; }
+        }
+        if (isconst) {
+            // a const column with an empty value is equivalent to a missing column (getConstColumnValue returns "")
+            if (!v.empty() && !v[0].empty()) b.consts.push_back({canonical(names[i]), std::string(v[0])});
+            continue;
+        }
+        b.columns.push_back(build_column(names[i], v));
+    }
+    return b;
+}
+
+// ---- bitmap bitmap.go:28-191 ---------------------------------------------------------------------------------------
+struct Bitmap {
+    std::vector<uint64_t> a; uint64_t bitsLen = 0;
+    void init(uint64_t n) { bitsLen = n; a.assign((n + 63) / 64, 0); }
+    void set_bits() {   // :62-72
+        for (auto& w : a) w = ~0ULL;
+        uint64_t tail = a.size() * 64 - bitsLen;
+        if (tail > 0) a.back() &= (~0ULL) >> tail;
+    }
+    void reset_bits() { for (auto& w : a) w = 0; }
+    bool is_zero() const { for (auto w : a) if (w) return false; return true; }
+    void and_not(const Bitmap& x) { for (size_t i = 0; i < a.size(); i++) a[i] &= ~x.a[i]; }
+    uint64_t ones() const { uint64_t n = 0; for (auto w : a) n += __builtin_popcountll(w); return n; }
+    template <class F> void for_each_set_bit(F&& f) {   // :128-153: f returns whether to keep the bit
+        for (size_t i = 0; i < a.size(); i++) {
+            uint64_t w = a[i]; if (!w) continue;
+            uint64_t keep = w;
+            for (int j = 0; j < 64; j++) {
+                if (!(w >> j & 1)) continue;
+                uint64_t idx = i * 64 + j;
+                if (idx >= bitsLen) break;
+                if (!f(idx)) keep &= ~(1ULL << j);
+            }
+            a[i] = keep;
+        }
+    }
+};
+
+// ---- predicates ----------------------------------------------------------------------------------------------------
+// getPhrasePos / matchPhrase filter_phrase.go:211-270
+inline bool match_phrase(sv s, sv phrase) {
+    if (phrase.empty()) return s.empty();
+    if (phrase.size() > s.size()) return false;
+    const uint8_t* sp = (const uint8_t*)s.data();
+    int sz;
+    int32_t r = (uint8_t)phrase[0];
+    if (r >= 0x80) r = decode_rune((const uint8_t*)phrase.data(), phrase.size(), &sz);
+    bool startsWithToken = is_token_rune(r);
+    r = (uint8_t)phrase.back();
+    if (r >= 0x80) r = decode_last_rune((const uint8_t*)phrase.data(), phrase.size(), &sz);
+    bool endsWithToken = is_token_rune(r);
+    size_t pos = 0;
+    for (;;) {
+        size_t n = s.find(phrase, pos);
+        if (n == sv::npos) return false;
+        pos = n;
+        if (startsWithToken && pos > 0) {
+            int32_t q = sp[pos - 1];
+            if (q >= 0x80) q = decode_last_rune(sp, pos, &sz);
+            if (q == RuneError || is_token_rune(q)) { pos++; continue; }
+        }
+        if (endsWithToken && pos + phrase.size() < s.size()) {
+            int32_t q = sp[pos + phrase.size()];
+            if (q >= 0x80) q = decode_rune(sp + pos + phrase.size(), s.size() - pos - phrase.size(), &sz);
+            if (q == RuneError || is_token_rune(q)) { pos++; continue; }
+        }
+        return true;
+    }
+}
+// matchPrefix filter_prefix.go:318-352
+inline bool match_prefix(sv s, sv prefix) {
+    if (prefix.empty()) return !s.empty();
+    if (prefix.size() > s.size()) return false;
+    const uint8_t* sp = (const uint8_t*)s.data();
+    int sz;
+    int32_t r = (uint8_t)prefix[0];
+    if (r >= 0x80) r = decode_rune((const uint8_t*)prefix.data(), prefix.size(), &sz);
+    bool startsWithToken = is_token_rune(r);
+    size_t off = 0;
+    for (;;) {
+        size_t n = s.find(prefix, off);
+        if (n == sv::npos) return false;
+        off = n;
+        if (startsWithToken && off > 0) {
+            int32_t q = sp[off - 1];
+            if (q >= 0x80) q = decode_last_rune(sp, off, &sz);
+            if (q == RuneError || is_token_rune(q)) { off++; continue; }
+        }
+        return true;
+    }
+}
+// getTokensSkipLast filter_prefix.go:354-363
+inline std::vector<std::string> tokens_skip_last(sv s) {
+    for (;;) { int sz; int32_t r = decode_last_rune((const uint8_t*)s.data(), s.size(), &sz); if (!is_token_rune(r)) break; s.remove_suffix(sz); }
+    return tokenize_string(s);
+}
+
+// ---- block search ----------------------------------------------------------------------------------------------------
+struct ScanStats {   // algorithmic-bytes accounting, block-granular, following the reference's short-circuit
+    uint64_t blocks = 0, rows = 0, bloom_probe_bytes = 0, values_bytes = 0, bitmap_bytes = 0, blocks_values_read = 0;
+};
+
+struct BlockSearch {
+    const Block* b = nullptr;
+    ScanStats* st = nullptr;
+    std::map<std::string, BloomFilter> bloomCache;
+    struct Vals { DecodedStringsBlock dec; std::vector<sv> values; };
+    std::map<std::string, std::unique_ptr<Vals>> valuesCache;
+
+    void reset(const Block* blk, ScanStats* s) { b = blk; st = s; bloomCache.clear(); valuesCache.clear(); }
+    sv const_value(sv name) const {   // getConstColumnValue block_search.go:232-276
+        std::string n = canonical(name);
+        for (auto& cc : b->consts) if (cc.name == n) return cc.value;
+        return sv();
+    }
+    const Column* column(sv name) const {   // getColumnHeader :278-324
+        std::string n = canonical(name);
+        for (auto& c : b->columns) if (c.name == n) return &c;
+        return nullptr;
+    }
+    const BloomFilter& bloom(const Column* ch) {   // getBloomFilterForColumn :411-439
+        auto it = bloomCache.find(ch->name);
+        if (it != bloomCache.end()) return it->second;
+        BloomFilter bf;
+        if (!bf.unmarshal(ch->bloom)) throw std::runtime_error("cannot unmarshal bloom filter");
+        return bloomCache.emplace(ch->name, std::move(bf)).first->second;
+    }
+    const std::vector<sv>& values(const Column* ch) {   // getValuesForColumn :444-474
+        auto it = valuesCache.find(ch->name);
+        if (it != valuesCache.end()) return it->second->values;
+        auto v = std::make_unique<Vals>();
+        v->dec = decode_values_block_stage(ch->valuesBlock);
+        v->values = unmarshal_strings(v->dec, b->rows);
+        if (st) { st->values_bytes += v->dec.lens_items.size() + v->dec.data.size(); st->blocks_values_read++; }
+        auto& ref = *v;
+        valuesCache.emplace(ch->name, std::move(v));
+        return ref.values;
+    }
+    bool bloom_all(const Column* ch, const std::vector<uint64_t>& hashes) {   // matchBloomFilterAllTokens filter_phrase.go:302-308
+        if (hashes.empty()) return true;
+        if (st) st->bloom_probe_bytes += 8 * hashes.size();
+        return bloom(ch).contains_all(hashes);
+    }
+    template <class F> void visit_values(const Column* ch, Bitmap& bm, F&& f) {   // visitValues :291-300
+        if (bm.is_zero()) return;
+        const auto& vals = values(ch);
+        bm.for_each_set_bit([&](uint64_t idx) { return f(vals[idx]); });
+    }
+    void match_encoded_dict(const Column* ch, Bitmap& bm, const std::vector<uint8_t>& lut) {   // matchEncodedValuesDict :272-289
+        bool any = false; for (uint8_t c : lut) any |= c == 1;
+        if (!any) { bm.reset_bits(); return; }
+        visit_values(ch, bm, [&](sv v) {
+            if (v.size() != 1) throw std::runtime_error("unexpected length for dict value");
+            uint8_t idx = (uint8_t)v[0];
+            if (idx >= lut.size()) throw std::runtime_error("too big index for dict value");
+            return lut[idx] == 1;
+        });
+    }
+};
+
+// value -> string for numeric columns (filter_phrase.go:310-346, filter_prefix.go:365-408)
+inline std::string encoded_to_string(uint8_t vt, sv v) {
+    std::string s;
+    const uint8_t* p = (const uint8_t*)v.data();
+    switch (vt) {
+    case VT_UINT8: if (v.size() != 1) throw std::runtime_error("bad uint8 len"); marshal_uint64_string(s, p[0]); break;
+    case VT_UINT16: if (v.size() != 2) throw std::runtime_error("bad uint16 len"); marshal_uint64_string(s, get_be16(p)); break;
+    case VT_UINT32: if (v.size() != 4) throw std::runtime_error("bad uint32 len"); marshal_uint64_string(s, get_be32(p)); break;
+    case VT_UINT64: if (v.size() != 8) throw std::runtime_error("bad uint64 len"); marshal_uint64_string(s, get_be64(p)); break;
+    case VT_INT64: if (v.size() != 8) throw std::runtime_error("bad int64 len"); marshal_int64_string(s, unzigzag(get_be64(p))); break;
+    case VT_FLOAT64: { if (v.size() != 8) throw std::runtime_error("bad float64 len"); uint64_t b = get_be64(p); double f; memcpy(&f, &b, 8); marshal_float64_string(s, f); break; }
+    case VT_IPV4: if (v.size() != 4) throw std::runtime_error("bad ipv4 len"); marshal_ipv4_string(s, get_be32(p)); break;
+    case VT_ISO8601: if (v.size() != 8) throw std::runtime_error("bad iso8601 len"); marshal_timestamp_iso8601_string(s, (int64_t)get_be64(p)); break;
+    default: s = std::string(v);
+    }
+    return s;
+}
+
+// ---- filters ---------------------------------------------------------------------------------------------------------
+struct FieldTokens { std::string field; std::vector<std::string> tokens; std::vector<uint64_t> hashes; };
+
+enum FilterKind { F_NOOP, F_PHRASE, F_PREFIX, F_EXACT, F_IN, F_REGEXP, F_AND, F_OR, F_NOT };
+
+struct Filter {
+    FilterKind kind;
+    virtual ~Filter() {}
+    virtual void apply(BlockSearch& bs, Bitmap& bm) = 0;   // applyToBlockSearch
+    // tokens contributed to the AND/OR bloom pre-pass (filter_and.go:131-165); has_tokens=false => "default:" branch
+    virtual bool leaf_tokens(std::string*, std::vector<std::string>*) { return false; }
+};
+using FP = std::shared_ptr<Filter>;
+
+// binary-equality over fixed-width encodings: matchBinaryValue filter_exact.go:356-364
+inline void match_binary_value(BlockSearch& bs, const Column* ch, Bitmap& bm, sv bin, const std::vector<uint64_t>& tokens) {
+    if (!bs.bloom_all(ch, tokens)) { bm.reset_bits(); return; }
+    bs.visit_values(ch, bm, [&](sv v) { return v == bin; });
+}
+
+// matchUintNByExactValue / matchInt64 / matchFloat64 / matchIPv4 / matchTimestampISO8601 ByExactValue filter_exact.go:237-354
+inline void match_numeric_exact(BlockSearch& bs, const Column* ch, Bitmap& bm, sv value, const std::vector<uint64_t>& tokens) {
+    std::string bin;
+    switch (ch->valueType) {
+    case VT_UINT8: case VT_UINT16: case VT_UINT32: case VT_UINT64: {
+        uint64_t n;
+        if (!try_parse_uint64(value, &n) || n < ch->minValue || n > ch->maxValue) { bm.reset_bits(); return; }
+        if (ch->valueType == VT_UINT8) bin.push_back((char)n); else if (ch->valueType == VT_UINT16) put_be16(bin, (uint16_t)n);
+        else if (ch->valueType == VT_UINT32) put_be32(bin, (uint32_t)n); else put_be64(bin, n);
+        break;
+    }
+    case VT_INT64: {
+        int64_t n;
+        if (!try_parse_int64(value, &n) || n < (int64_t)ch->minValue || n > (int64_t)ch->maxValue) { bm.reset_bits(); return; }
+        put_be64(bin, zigzag(n)); break;
+    }
+    case VT_FLOAT64: {
+        double f, mn, mx; memcpy(&mn, &ch->minValue, 8); memcpy(&mx, &ch->maxValue, 8);
+        if (!try_parse_float64_exact(value, &f) || f < mn || f > mx) { bm.reset_bits(); return; }
+        uint64_t b; memcpy(&b, &f, 8); put_be64(bin, b); break;
+    }
+    case VT_IPV4: {
+        uint32_t n;
+        if (!try_parse_ipv4(value, &n) || (uint64_t)n < ch->minValue || (uint64_t)n > ch->maxValue) { bm.reset_bits(); return; }
+        put_be32(bin, n); break;
+    }
+    case VT_ISO8601: {
+        int64_t n;
+        if (!try_parse_timestamp_iso8601(value, &n) || n < (int64_t)ch->minValue || n > (int64_t)ch->maxValue) { bm.reset_bits(); return; }
+        put_be64(bin, (uint64_t)n); break;
+    }
+    default: throw std::runtime_error("match_numeric_exact: bad type");
+    }
+    match_binary_value(bs, ch, bm, bin, tokens);
+}
+
+struct FilterNoop : Filter { FilterNoop() { kind = F_NOOP; } void apply(BlockSearch&, Bitmap&) override {} };
+
+struct FilterPhrase : Filter {   // filter_phrase.go:25-111
+    std::string field, phrase; std::vector<std::string> tokens; std::vector<uint64_t> hashes;
+    FilterPhrase(sv f, sv p) : field(f), phrase(p) { kind = F_PHRASE; tokens = tokenize_string(phrase); hashes = tokens_hashes(tokens); }
+    bool leaf_tokens(std::string* f, std::vector<std::string>* t) override { *f = field; *t = tokens; return true; }
+    void apply(BlockSearch& bs, Bitmap& bm) override {
+        sv v = bs.const_value(field);
+        if (!v.empty()) { if (!match_phrase(v, phrase)) bm.reset_bits(); return; }
+        const Column* ch = bs.column(field);
+        if (!ch) { if (!phrase.empty()) bm.reset_bits(); return; }
+        switch (ch->valueType) {
+        case VT_STRING:
+            if (!bs.bloom_all(ch, hashes)) { bm.reset_bits(); return; }
+            bs.visit_values(ch, bm, [&](sv x) { return match_phrase(x, phrase); });
+            break;
+        case VT_DICT: {
+            std::vector<uint8_t> lut; for (auto& d : ch->dict) lut.push_back(match_phrase(d, phrase) ? 1 : 0);
+            bs.match_encoded_dict(ch, bm, lut); break;
+        }
+        case VT_UINT8: case VT_UINT16: case VT_UINT32: case VT_UINT64: case VT_INT64:
+            match_numeric_exact(bs, ch, bm, phrase, hashes); break;
+        case VT_FLOAT64: {   // matchFloat64ByPhrase :159-186
+            double f;
+            if (!try_parse_float64_exact(phrase, &f) && phrase != "." && phrase != "+" && phrase != "-") { bm.reset_bits(); return; }
+            size_t n = phrase.find('.');
+            if (n != std::string::npos && n > 0 && n < phrase.size() - 1) { match_numeric_exact(bs, ch, bm, phrase, hashes); return; }
+            to_string_match(bs, ch, bm); break;
+        }
+        case VT_IPV4: { uint32_t ip; if (try_parse_ipv4(phrase, &ip)) { match_numeric_exact(bs, ch, bm, phrase, hashes); return; } to_string_match(bs, ch, bm); break; }
+        case VT_ISO8601: { int64_t t; if (try_parse_timestamp_iso8601(phrase, &t)) { match_numeric_exact(bs, ch, bm, phrase, hashes); return; } to_string_match(bs, ch, bm); break; }
+        default: throw std::runtime_error("unknown valueType");
+        }
+    }
+    void to_string_match(BlockSearch& bs, const Column* ch, Bitmap& bm) {
+        if (!bs.bloom_all(ch, hashes)) { bm.reset_bits(); return; }
+        bs.visit_values(ch, bm, [&](sv x) { return match_phrase(encoded_to_string(ch->valueType, x), phrase); });
+    }
+};
+
+struct FilterPrefix : Filter {   // filter_prefix.go:20-106
+    std::string field, prefix; std::vector<std::string> tokens; std::vector<uint64_t> hashes;
+    FilterPrefix(sv f, sv p) : field(f), prefix(p) { kind = F_PREFIX; tokens = tokens_skip_last(prefix); hashes = tokens_hashes(tokens); }
+    bool leaf_tokens(std::string* f, std::vector<std::string>* t) override { *f = field; *t = tokens; return true; }
+    void apply(BlockSearch& bs, Bitmap& bm) override {
+        sv v = bs.const_value(field);
+        if (!v.empty()) { if (!match_prefix(v, prefix)) bm.reset_bits(); return; }
+        const Column* ch = bs.column(field);
+        if (!ch) { bm.reset_bits(); return; }
+        switch (ch->valueType) {
+        case VT_STRING:
+            if (!bs.bloom_all(ch, hashes)) { bm.reset_bits(); return; }
+            bs.visit_values(ch, bm, [&](sv x) { return match_prefix(x, prefix); });
+            break;
+        case VT_DICT: {
+            std::vector<uint8_t> lut; for (auto& d : ch->dict) lut.push_back(match_prefix(d, prefix) ? 1 : 0);
+            bs.match_encoded_dict(ch, bm, lut); break;
+        }
+        case VT_UINT8: case VT_UINT16: case VT_UINT32: case VT_UINT64: {   // :201-291
+            if (prefix.empty()) return;
+            uint64_t n;
+            if (!try_parse_uint64(prefix, &n) || n > ch->maxValue) { bm.reset_bits(); return; }
+            bs.visit_values(ch, bm, [&](sv x) { return match_prefix(encoded_to_string(ch->valueType, x), prefix); });
+            break;
+        }
+        case VT_INT64: {   // :293-316
+            if (prefix.empty()) return;
+            if (prefix != "-") {
+                int64_t n;
+                if (!try_parse_int64(prefix, &n) || n < (int64_t)ch->minValue || n > (int64_t)ch->maxValue) { bm.reset_bits(); return; }
+            }
+            bs.visit_values(ch, bm, [&](sv x) { return match_prefix(encoded_to_string(ch->valueType, x), prefix); });
+            break;
+        }
+        case VT_FLOAT64: {   // :150-176
+            if (prefix.empty()) return;
+            double f;
+            if (!try_parse_float64_exact(prefix, &f) && prefix != "." && prefix != "+" && prefix != "-" && prefix[0] != 'e' && prefix[0] != 'E') { bm.reset_bits(); return; }
+            if (!bs.bloom_all(ch, hashes)) { bm.reset_bits(); return; }
+            bs.visit_values(ch, bm, [&](sv x) { return match_prefix(encoded_to_string(ch->valueType, x), prefix); });
+            break;
+        }
+        case VT_IPV4: case VT_ISO8601: {   // :108-148
+            if (prefix.empty()) return;
+            if (!bs.bloom_all(ch, hashes)) { bm.reset_bits(); return; }
+            bs.visit_values(ch, bm, [&](sv x) { return match_prefix(encoded_to_string(ch->valueType, x), prefix); });
+            break;
+        }
+        default: throw std::runtime_error("unknown valueType");
+        }
+    }
+};
+
+struct FilterExact : Filter {   // filter_exact.go:17-235
+    std::string field, value; std::vector<std::string> tokens; std::vector<uint64_t> hashes;
+    FilterExact(sv f, sv v) : field(f), value(v) { kind = F_EXACT; tokens = tokenize_string(value); hashes = tokens_hashes(tokens); }
+    bool leaf_tokens(std::string* f, std::vector<std::string>* t) override { *f = field; *t = tokens; return true; }
+    void apply(BlockSearch& bs, Bitmap& bm) override {
+        sv v = bs.const_value(field);
+        if (!v.empty()) { if (value != v) bm.reset_bits(); return; }
+        const Column* ch = bs.column(field);
+        if (!ch) { if (!value.empty()) bm.reset_bits(); return; }
+        switch (ch->valueType) {
+        case VT_STRING:
+            if (!bs.bloom_all(ch, hashes)) { bm.reset_bits(); return; }
+            bs.visit_values(ch, bm, [&](sv x) { return x == value; });
+            break;
+        case VT_DICT: {
+            std::vector<uint8_t> lut; for (auto& d : ch->dict) lut.push_back(d == value ? 1 : 0);
+            bs.match_encoded_dict(ch, bm, lut); break;
+        }
+        default: match_numeric_exact(bs, ch, bm, value, hashes);
+        }
+    }
+};
+
+struct FilterIn : Filter {   // filter_in.go:14-234 + in_values.go
+    std::string field; std::vector<std::string> values;
+    std::unordered_set<std::string> strset;
+    std::vector<uint64_t> commonHashes; std::vector<std::vector<uint64_t>> tokenSetsHashes;
+    FilterIn(sv f, const std::vector<std::string>& vals) : field(f), values(vals) {
+        kind = F_IN;
+        for (auto& v : values) strset.insert(v);
+        // getCommonTokensAndTokenSets in_values.go:317-346
+        std::vector<std::vector<std::string>> sets;
+        for (auto& v : values) sets.push_back(tokenize_string(v));
+        std::vector<std::string> common;
+        if (!sets.empty()) {
+            common = sets[0];
+            for (size_t i = 1; i < sets.size(); i++) {
+                if (common.empty()) break;
+                std::vector<std::string> d;
+                for (auto& t : common) if (std::find(sets[i].begin(), sets[i].end(), t) != sets[i].end()) d.push_back(t);
+                common = d;
+            }
+        }
+        if (!common.empty()) for (auto& s : sets) {
+            std::vector<std::string> d;
+            for (auto& t : s) if (std::find(common.begin(), common.end(), t) == common.end()) d.push_back(t);
+            s = d;
+        }
+        commonHashes = tokens_hashes(common);
+        for (auto& s : sets) tokenSetsHashes.push_back(tokens_hashes(s));
+    }
+    // typed sets in_values.go:141-315
+    std::unordered_set<std::string> bin_values(uint8_t vt) const {
+        std::unordered_set<std::string> m;
+        for (auto& v : values) {
+            std::string b;
+            switch (vt) {
+            case VT_UINT8: { uint64_t n; if (!try_parse_uint64(v, &n) || n >= (1ULL << 8)) continue; b.push_back((char)n); break; }
+            case VT_UINT16: { uint64_t n; if (!try_parse_uint64(v, &n) || n >= (1ULL << 16)) continue; put_be16(b, (uint16_t)n); break; }
+            case VT_UINT32: { uint64_t n; if (!try_parse_uint64(v, &n) || n >= (1ULL << 32)) continue; put_be32(b, (uint32_t)n); break; }
+            case VT_UINT64: { uint64_t n; if (!try_parse_uint64(v, &n)) continue; put_be64(b, n); break; }
+            case VT_INT64: { int64_t n; if (!try_parse_int64(v, &n)) continue; put_be64(b, zigzag(n)); break; }
+            case VT_FLOAT64: { double f; if (!try_parse_float64_exact(v, &f)) continue; uint64_t u; memcpy(&u, &f, 8); put_be64(b, u); break; }
+            case VT_IPV4: { uint32_t n; if (!try_parse_ipv4(v, &n)) continue; put_be32(b, n); break; }
+            case VT_ISO8601: { int64_t n; if (!try_parse_timestamp_iso8601(v, &n)) continue; put_be64(b, (uint64_t)n); break; }
+            default: b = v;
+            }
+            m.insert(b);
+        }
+        return m;
+    }
+    void apply(BlockSearch& bs, Bitmap& bm) override {
+        if (values.empty()) { bm.reset_bits(); return; }
+        sv v = bs.const_value(field);
+        if (!v.empty()) { if (!strset.count(std::string(v))) bm.reset_bits(); return; }
+        const Column* ch = bs.column(field);
+        if (!ch) { if (!strset.count("")) bm.reset_bits(); return; }
+        if (ch->valueType == VT_DICT) {
+            std::vector<uint8_t> lut; for (auto& d : ch->dict) lut.push_back(strset.count(d) ? 1 : 0);
+            bs.match_encoded_dict(ch, bm, lut); return;
+        }
+        std::unordered_set<std::string> bin = ch->valueType == VT_STRING ? strset : bin_values(ch->valueType);
+        // matchAnyValue :187-200
+        if (bin.empty()) { bm.reset_bits(); return; }
+        // matchBloomFilterAnyTokenSet :202-218
+        if (!bs.bloom_all(ch, commonHashes)) { bm.reset_bits(); return; }
+        if (!(tokenSetsHashes.size() > 1000 || tokenSetsHashes.size() > 10 * bs.b->rows)) {
+            bool any = false;
+            const BloomFilter& bf = bs.bloom(ch);
+            for (auto& t : tokenSetsHashes) { if (bs.st) bs.st->bloom_probe_bytes += 8 * t.size(); if (bf.contains_all(t)) { any = true; break; } }
+            if (!any) { bm.reset_bits(); return; }
+        }
+        bs.visit_values(ch, bm, [&](sv x) { return bin.count(std::string(x)) > 0; });
+    }
+};
+
+struct FilterRegexp : Filter {   // filter_regexp.go:17-254
+    std::string field; Regex re; std::vector<std::string> tokens; std::vector<uint64_t> hashes;
+    FilterRegexp(sv f, sv expr) : field(f), re(expr) {
+        kind = F_REGEXP;
+        std::vector<std::string> lits = re.get_literals();
+        std::vector<std::string> stripped; for (auto& l : lits) stripped.push_back(skip_first_last_token(l));
+        std::vector<sv> views(stripped.begin(), stripped.end());
+        tokens = tokenize_strings(views);
+        hashes = tokens_hashes(tokens);
+    }
+    bool leaf_tokens(std::string* f, std::vector<std::string>* t) override { *f = field; *t = tokens; return true; }
+    void apply(BlockSearch& bs, Bitmap& bm) override {
+        sv v = bs.const_value(field);
+        if (!v.empty()) { if (!re.match_string(v)) bm.reset_bits(); return; }
+        const Column* ch = bs.column(field);
+        if (!ch) { if (!re.match_string("")) bm.reset_bits(); return; }
+        if (ch->valueType == VT_DICT) {
+            std::vector<uint8_t> lut; for (auto& d : ch->dict) lut.push_back(re.match_string(d) ? 1 : 0);
+            bs.match_encoded_dict(ch, bm, lut); return;
+        }
+        if (!bs.bloom_all(ch, hashes)) { bm.reset_bits(); return; }
+        if (ch->valueType == VT_STRING) bs.visit_values(ch, bm, [&](sv x) { return re.match_string(x); });
+        else bs.visit_values(ch, bm, [&](sv x) { return re.match_string(encoded_to_string(ch->valueType, x)); });
+    }
+};
+
+inline bool match_string_by_all_tokens(sv v, const std::vector<std::string>& tokens) {   // filter_and.go:189-196
+    for (auto& t : tokens) if (!match_phrase(v, t)) return false;
+    return true;
+}
+inline bool match_dict_values_by_all_tokens(const std::vector<std::string>& dict, const std::vector<std::string>& tokens) {   // :198-208
+    std::string joined; for (auto& d : dict) { joined += d; joined.push_back(','); }
+    return match_string_by_all_tokens(joined, tokens);
+}
+
+struct FilterOr;
+struct FilterAnd : Filter {   // filter_and.go:15-187
+    std::vector<FP> filters; std::vector<FieldTokens> byField; bool inited = false;
+    explicit FilterAnd(std::vector<FP> f) : filters(std::move(f)) { kind = F_AND; }
+    const std::vector<FieldTokens>& by_field_tokens();
+    void apply(BlockSearch& bs, Bitmap& bm) override {
+        if (!match_bloom(bs)) { bm.reset_bits(); return; }
+        for (auto& f : filters) { f->apply(bs, bm); if (bm.is_zero()) return; }
+    }
+    bool match_bloom(BlockSearch& bs) {   // :76-111
+        for (auto& ft : by_field_tokens()) {
+            sv v = bs.const_value(ft.field);
+            if (!v.empty()) { if (match_string_by_all_tokens(v, ft.tokens)) continue; return false; }
+            const Column* ch = bs.column(ft.field);
+            if (!ch) return false;
+            if (ch->valueType == VT_DICT) { if (match_dict_values_by_all_tokens(ch->dict, ft.tokens)) continue; return false; }
+            if (!bs.bloom_all(ch, ft.hashes)) return false;
+        }
+        return true;
+    }
+};
+struct FilterOr : Filter {   // filter_or.go:36-193
+    std::vector<FP> filters; std::vector<FieldTokens> byField; bool inited = false;
+    explicit FilterOr(std::vector<FP> f) : filters(std::move(f)) { kind = F_OR; }
+    const std::vector<FieldTokens>& by_field_tokens();
+    void apply(BlockSearch& bs, Bitmap& bm) override {
+        if (!match_bloom(bs)) { bm.reset_bits(); return; }
+        Bitmap res = bm, tmp;
+        for (auto& f : filters) {
+            tmp = res;
+            f->apply(bs, tmp);
+            res.and_not(tmp);
+            if (res.is_zero()) return;
+        }
+        bm.and_not(res);
+    }
+    bool match_bloom(BlockSearch& bs) {   // :80-115
+        auto& bft = by_field_tokens();
+        if (bft.empty()) return true;
+        for (auto& ft : bft) {
+            sv v = bs.const_value(ft.field);
+            if (!v.empty()) { if (match_string_by_all_tokens(v, ft.tokens)) return true; continue; }
+            const Column* ch = bs.column(ft.field);
+            if (!ch) continue;
+            if (ch->valueType == VT_DICT) { if (match_dict_values_by_all_tokens(ch->dict, ft.tokens)) return true; continue; }
+            if (bs.bloom_all(ch, ft.hashes)) return true;
+        }
+        return false;
+    }
+};
+struct FilterNot : Filter {   // filter_not.go:11-46
+    FP f;
+    explicit FilterNot(FP x) : f(std::move(x)) { kind = F_NOT; }
+    void apply(BlockSearch& bs, Bitmap& bm) override { Bitmap tmp = bm; f->apply(bs, tmp); bm.and_not(tmp); }
+};
+
+inline std::vector<std::string> dedup_keep_order(const std::vector<std::string>& a) {
+    std::vector<std::string> o; std::unordered_set<std::string> seen;
+    for (auto& t : a) if (seen.insert(t).second) o.push_back(t);
+    return o;
+}
+inline const std::vector<FieldTokens>& FilterAnd::by_field_tokens() {   // getCommonTokensForAndFilters :122-187
+    if (inited) return byField;
+    inited = true;
+    std::map<std::string, std::vector<std::string>> m; std::vector<std::string> names;
+    auto merge = [&](const std::string& field, const std::vector<std::string>& tokens) {
+        if (tokens.empty()) return;
+        std::string fn = canonical(field);
+        if (!m.count(fn)) names.push_back(fn);
+        auto& v = m[fn]; v.insert(v.end(), tokens.begin(), tokens.end());
+    };
+    for (auto& f : filters) {
+        std::string field; std::vector<std::string> toks;
+        if (f->leaf_tokens(&field, &toks)) merge(field, toks);
+        else if (f->kind == F_OR) for (auto& bft : static_cast<FilterOr*>(f.get())->by_field_tokens()) merge(bft.field, bft.tokens);
+    }
+    for (auto& n : names) { FieldTokens ft; ft.field = n; ft.tokens = dedup_keep_order(m[n]); ft.hashes = tokens_hashes(ft.tokens); byField.push_back(ft); }
+    return byField;
+}
+inline const std::vector<FieldTokens>& FilterOr::by_field_tokens() {   // getCommonTokensForOrFilters :126-193
+    if (inited) return byField;
+    inited = true;
+    std::map<std::string, std::vector<std::vector<std::string>>> m; std::vector<std::string> names;
+    auto merge = [&](const std::string& field, const std::vector<std::string>& tokens) {
+        if (tokens.empty()) return;
+        std::string fn = canonical(field);
+        if (!m.count(fn)) names.push_back(fn);
+        m[fn].push_back(tokens);
+    };
+    for (auto& f : filters) {
+        std::string field; std::vector<std::string> toks;
+        if (f->leaf_tokens(&field, &toks)) merge(field, toks);
+        else if (f->kind == F_AND) for (auto& bft : static_cast<FilterAnd*>(f.get())->by_field_tokens()) merge(bft.field, bft.tokens);
+        else { byField.clear(); return byField; }   // default: cannot extract common tokens
+    }
+    for (auto& n : names) {
+        auto& tokenss = m[n];
+        if (tokenss.size() != filters.size()) continue;
+        std::vector<std::string> common = tokenss[0];
+        for (size_t i = 1; i < tokenss.size(); i++) {
+            if (common.empty()) break;
+            std::vector<std::string> d;
+            for (auto& t : common) if (std::find(tokenss[i].begin(), tokenss[i].end(), t) != tokenss[i].end()) d.push_back(t);
+            common = d;
+        }
+        if (common.empty()) continue;
+        FieldTokens ft; ft.field = n; ft.tokens = common; ft.hashes = tokens_hashes(common); byField.push_back(ft);
+    }
+    return byField;
+}
+
+// blockSearch.search block_search.go:207-226 (filter part)
+inline void block_search(BlockSearch& bs, const Block& b, Filter& f, Bitmap& bm, ScanStats* st) {
+    bs.reset(&b, st);
+    bm.init(b.rows);
+    bm.set_bits();
+    f.apply(bs, bm);
+    if (st) { st->blocks++; st->rows += b.rows; if (!bm.is_zero()) st->bitmap_bytes += 8 * bm.a.size(); }
+}
+
+}  // namespace vlo

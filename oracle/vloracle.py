@@ -1,0 +1,375 @@
+"""ctypes binding of the CPU oracle (oracle/liboracle.so).
+
+TEST INFRASTRUCTURE ONLY: import this from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs, never from victorialogs_b200/.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+VT_NAMES = {1: "string", 2: "dict", 3: "uint8", 4: "uint16", 5: "uint32", 6: "uint64", 7: "float64", 8: "ipv4", 9: "iso8601", 10: "int64"}
+
+
+class GenConfig(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("total_rows", C.c_uint64), ("rows_per_block", C.c_uint32),
+                ("hot_block_permille", C.c_uint32), ("hit_row_permille", C.c_uint32), ("columns_mask", C.c_uint32)]
+
+
+class ColumnView(C.Structure):
+    _fields_ = [("name", C.c_void_p), ("name_len", C.c_uint64), ("value_type", C.c_uint32), ("dict_len", C.c_uint32),
+                ("min_value", C.c_uint64), ("max_value", C.c_uint64), ("dict_ptr", C.c_void_p * 8), ("dict_lens", C.c_uint64 * 8),
+                ("values_block", C.c_void_p), ("values_block_len", C.c_uint64), ("bloom", C.c_void_p), ("bloom_len", C.c_uint64)]
+
+
+def build():
+    subprocess.check_call([os.path.join(_HERE, "build.sh")], stdout=subprocess.DEVNULL)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        L.vlo_last_error.restype = C.c_char_p
+        L.vlo_xxh64.restype = C.c_uint64
+        for name in ("vlo_tokenize_strings", "vlo_tokenize_hashes", "vlo_bloom_marshal_tokens", "vlo_skip_first_last_token",
+                     "vlo_regex_describe", "vlo_encoded_to_string", "vlo_marshal_strings_block", "vlo_filter_tokens"):
+            getattr(L, name).restype = C.c_int64
+        for name in ("vlo_block_build", "vlo_filter_phrase", "vlo_filter_prefix", "vlo_filter_exact", "vlo_filter_in", "vlo_filter_regexp",
+                     "vlo_filter_noop", "vlo_filter_and", "vlo_filter_or", "vlo_filter_not", "vlo_gen_block"):
+            getattr(L, name).restype = C.c_void_p
+        for name in ("vlo_block_rows", "vlo_block_ncolumns", "vlo_block_nconsts"):
+            getattr(L, name).restype = C.c_uint64
+        _LIB = L
+    return _LIB
+
+
+def _b(s):
+    return s.encode("utf-8", "surrogateescape") if isinstance(s, str) else bytes(s)
+
+
+def _pack(strings):
+    bs = [_b(s) for s in strings]
+    offs = np.zeros(len(bs) + 1, dtype=np.uint64)
+    if bs:
+        offs[1:] = np.cumsum([len(x) for x in bs], dtype=np.uint64)
+    blob = b"".join(bs)
+    return blob, offs
+
+
+def _err():
+    return RuntimeError(lib().vlo_last_error().decode())
+
+
+def xxh64(data):
+    data = _b(data)
+    return lib().vlo_xxh64(data, C.c_uint64(len(data)))
+
+
+def tokenize_strings(strings):
+    blob, offs = _pack(strings)
+    cap = len(blob) + len(strings) + 16
+    out = C.create_string_buffer(cap)
+    n = lib().vlo_tokenize_strings(blob, offs.ctypes.data_as(C.c_void_p), C.c_uint64(len(strings)), out, C.c_uint64(cap))
+    assert n >= 0
+    raw = out.raw[:n]
+    return [t for t in raw.split(b"\n")] if n else []
+
+
+def tokenize_hashes(strings):
+    blob, offs = _pack(strings)
+    cap = len(blob) + 16
+    out = np.zeros(cap, dtype=np.uint64)
+    n = lib().vlo_tokenize_hashes(blob, offs.ctypes.data_as(C.c_void_p), C.c_uint64(len(strings)), out.ctypes.data_as(C.c_void_p), C.c_uint64(cap))
+    assert n >= 0
+    return out[:n].copy()
+
+
+def token_hashes(token):
+    token = _b(token)
+    out = np.zeros(6, dtype=np.uint64)
+    lib().vlo_token_hashes(token, C.c_uint64(len(token)), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def bloom_marshal_tokens(tokens):
+    blob, offs = _pack(tokens)
+    cap = len(tokens) * 2 + 64
+    out = C.create_string_buffer(cap)
+    n = lib().vlo_bloom_marshal_tokens(blob, offs.ctypes.data_as(C.c_void_p), C.c_uint64(len(tokens)), out, C.c_uint64(cap))
+    assert n >= 0
+    return out.raw[:n]
+
+
+def bloom_contains_all(bloom, tokens):
+    blob, offs = _pack(tokens)
+    r = lib().vlo_bloom_contains_all_tokens(bloom, C.c_uint64(len(bloom)), blob, offs.ctypes.data_as(C.c_void_p), C.c_uint64(len(tokens)))
+    assert r >= 0
+    return bool(r)
+
+
+def match_phrase(s, phrase):
+    s, phrase = _b(s), _b(phrase)
+    return bool(lib().vlo_match_phrase(s, C.c_uint64(len(s)), phrase, C.c_uint64(len(phrase))))
+
+
+def match_prefix(s, prefix):
+    s, prefix = _b(s), _b(prefix)
+    return bool(lib().vlo_match_prefix(s, C.c_uint64(len(s)), prefix, C.c_uint64(len(prefix))))
+
+
+def skip_first_last_token(s):
+    s = _b(s)
+    out = C.create_string_buffer(len(s) + 1)
+    n = lib().vlo_skip_first_last_token(s, C.c_uint64(len(s)), out, C.c_uint64(len(s) + 1))
+    return out.raw[:n]
+
+
+def regex_match(expr, s):
+    expr, s = _b(expr), _b(s)
+    r = lib().vlo_regex_match(expr, C.c_uint64(len(expr)), s, C.c_uint64(len(s)))
+    if r < 0:
+        raise _err()
+    return bool(r)
+
+
+def regex_describe(expr):
+    expr = _b(expr)
+    out = C.create_string_buffer(65536)
+    n = lib().vlo_regex_describe(expr, C.c_uint64(len(expr)), out, C.c_uint64(65536))
+    if n < 0:
+        raise _err()
+    d = {}
+    for line in out.raw[:n].decode("utf-8", "replace").split("\n"):
+        k, _, v = line.partition("=")
+        d[k] = v
+    return d
+
+
+def _parse(fn, ctype, s):
+    s = _b(s)
+    out = ctype()
+    ok = fn(s, C.c_uint64(len(s)), C.byref(out))
+    return (out.value, bool(ok))
+
+
+def try_parse_uint64(s):
+    return _parse(lib().vlo_try_parse_uint64, C.c_uint64, s)
+
+
+def try_parse_int64(s):
+    return _parse(lib().vlo_try_parse_int64, C.c_int64, s)
+
+
+def try_parse_float64(s):
+    return _parse(lib().vlo_try_parse_float64, C.c_double, s)
+
+
+def try_parse_ipv4(s):
+    return _parse(lib().vlo_try_parse_ipv4, C.c_uint32, s)
+
+
+def try_parse_iso8601(s):
+    return _parse(lib().vlo_try_parse_iso8601, C.c_int64, s)
+
+
+def encoded_to_string(vt, v):
+    out = C.create_string_buffer(512)
+    n = lib().vlo_encoded_to_string(C.c_int(vt), v, C.c_uint64(len(v)), out, C.c_uint64(512))
+    if n < 0:
+        raise _err()
+    return out.raw[:n]
+
+
+def marshal_strings_block(strings):
+    blob, offs = _pack(strings)
+    cap = len(blob) + 9 * len(strings) + 1024
+    out = C.create_string_buffer(cap)
+    n = lib().vlo_marshal_strings_block(blob, offs.ctypes.data_as(C.c_void_p), C.c_uint64(len(strings)), out, C.c_uint64(cap))
+    if n < 0:
+        raise _err()
+    return out.raw[:n]
+
+
+def decode_values_block(src, cap=None):
+    """-> (lens_items bytes, data bytes): the post-ZSTD stage of a values block."""
+    cap = cap or (64 << 20)
+    lens = C.create_string_buffer(cap)
+    data = C.create_string_buffer(cap)
+    ll, dl = C.c_uint64(cap), C.c_uint64(cap)
+    if lib().vlo_decode_values_block(src, C.c_uint64(len(src)), lens, C.byref(ll), data, C.byref(dl)):
+        raise _err()
+    return lens.raw[:ll.value], data.raw[:dl.value]
+
+
+def unmarshal_strings_block(src, items, cap=None):
+    cap = cap or (64 << 20)
+    out = C.create_string_buffer(cap)
+    offs = np.zeros(items + 1, dtype=np.uint64)
+    if lib().vlo_unmarshal_strings_block(src, C.c_uint64(len(src)), C.c_uint64(items), out, C.c_uint64(cap), offs.ctypes.data_as(C.c_void_p)):
+        raise _err()
+    raw = out.raw
+    return [raw[int(offs[i]):int(offs[i + 1])] for i in range(items)]
+
+
+class Column:
+    __slots__ = ("name", "value_type", "min_value", "max_value", "dict", "values_block", "bloom")
+
+
+class Block:
+    """An encoded block as the reference writer would produce it (one column = header fields + values block + bloom)."""
+
+    def __init__(self, handle):
+        assert handle, _err()
+        self.h = C.c_void_p(handle)
+        L = lib()
+        self.rows = L.vlo_block_rows(self.h)
+        self.columns = []
+        for i in range(L.vlo_block_ncolumns(self.h)):
+            v = ColumnView()
+            L.vlo_block_column(self.h, C.c_uint64(i), C.byref(v))
+            c = Column()
+            c.name = C.string_at(v.name, v.name_len)
+            c.value_type = v.value_type
+            c.min_value, c.max_value = v.min_value, v.max_value
+            c.dict = [C.string_at(v.dict_ptr[k], v.dict_lens[k]) for k in range(v.dict_len)]
+            c.values_block = C.string_at(v.values_block, v.values_block_len)
+            c.bloom = C.string_at(v.bloom, v.bloom_len)
+            self.columns.append(c)
+        self.consts = []
+        for i in range(L.vlo_block_nconsts(self.h)):
+            n, nl, val, vl = C.c_void_p(), C.c_uint64(), C.c_void_p(), C.c_uint64()
+            L.vlo_block_const(self.h, C.c_uint64(i), C.byref(n), C.byref(nl), C.byref(val), C.byref(vl))
+            self.consts.append((C.string_at(n, nl.value), C.string_at(val, vl.value)))
+
+    def __del__(self):
+        try:
+            lib().vlo_block_free(self.h)
+        except Exception:
+            pass
+
+    @staticmethod
+    def from_columns(columns, rows=None):
+        """columns: list of (name, [values...]) column-major, like `[]column{{name, values}}` in filter_test.go."""
+        names = [c[0] for c in columns]
+        if rows is None:
+            rows = len(columns[0][1]) if columns else 0
+        vals = []
+        for _, v in columns:
+            assert len(v) == rows
+            vals.extend(v)
+        nb, no = _pack(names)
+        vb, vo = _pack(vals)
+        h = lib().vlo_block_build(nb, no.ctypes.data_as(C.c_void_p), C.c_uint64(len(names)), vb, vo.ctypes.data_as(C.c_void_p), C.c_uint64(rows))
+        if not h:
+            raise _err()
+        return Block(h)
+
+    @staticmethod
+    def generated(cfg, block_id):
+        h = lib().vlo_gen_block(C.byref(cfg), C.c_uint64(block_id))
+        if not h:
+            raise _err()
+        return Block(h)
+
+    def search(self, flt, stats=None):
+        words = np.zeros((self.rows + 63) // 64, dtype=np.uint64)
+        st = stats.ctypes.data_as(C.c_void_p) if stats is not None else None
+        if lib().vlo_block_search(self.h, flt.h, words.ctypes.data_as(C.c_void_p), st):
+            raise _err()
+        return words
+
+
+def bitmap_rows(words, rows):
+    bits = np.unpackbits(words.view(np.uint8), bitorder="little")[:rows]
+    return [int(i) for i in np.nonzero(bits)[0]]
+
+
+class Filter:
+    def __init__(self, handle, keep=()):
+        if not handle:
+            raise _err()
+        self.h = C.c_void_p(handle)
+        self._keep = keep
+
+    def tokens(self):
+        out = C.create_string_buffer(65536)
+        n = lib().vlo_filter_tokens(self.h, out, C.c_uint64(65536))
+        assert n >= 0
+        return out.raw[:n].split(b"\n") if n else []
+
+    @staticmethod
+    def phrase(field, phrase):
+        f, p = _b(field), _b(phrase)
+        return Filter(lib().vlo_filter_phrase(f, C.c_uint64(len(f)), p, C.c_uint64(len(p))))
+
+    @staticmethod
+    def prefix(field, prefix):
+        f, p = _b(field), _b(prefix)
+        return Filter(lib().vlo_filter_prefix(f, C.c_uint64(len(f)), p, C.c_uint64(len(p))))
+
+    @staticmethod
+    def exact(field, value):
+        f, p = _b(field), _b(value)
+        return Filter(lib().vlo_filter_exact(f, C.c_uint64(len(f)), p, C.c_uint64(len(p))))
+
+    @staticmethod
+    def in_(field, values):
+        f = _b(field)
+        blob, offs = _pack(values)
+        return Filter(lib().vlo_filter_in(f, C.c_uint64(len(f)), blob, offs.ctypes.data_as(C.c_void_p), C.c_uint64(len(values))))
+
+    @staticmethod
+    def regexp(field, expr):
+        f, p = _b(field), _b(expr)
+        return Filter(lib().vlo_filter_regexp(f, C.c_uint64(len(f)), p, C.c_uint64(len(p))))
+
+    @staticmethod
+    def noop():
+        return Filter(lib().vlo_filter_noop())
+
+    @staticmethod
+    def and_(filters):
+        arr = (C.c_void_p * len(filters))(*[f.h for f in filters])
+        return Filter(lib().vlo_filter_and(arr, C.c_uint64(len(filters))), keep=tuple(filters))
+
+    @staticmethod
+    def or_(filters):
+        arr = (C.c_void_p * len(filters))(*[f.h for f in filters])
+        return Filter(lib().vlo_filter_or(arr, C.c_uint64(len(filters))), keep=tuple(filters))
+
+    @staticmethod
+    def not_(f):
+        return Filter(lib().vlo_filter_not(f.h), keep=(f,))
+
+
+def gen_rows(cfg, block_id, column, cap=None):
+    rows = min(cfg.rows_per_block, cfg.total_rows - block_id * cfg.rows_per_block)
+    cap = cap or rows * 256 + 1024
+    out = C.create_string_buffer(cap)
+    offs = np.zeros(rows + 1, dtype=np.uint64)
+    if lib().vlo_gen_rows(C.byref(cfg), C.c_uint64(block_id), C.c_int(column), out, C.c_uint64(cap), offs.ctypes.data_as(C.c_void_p)):
+        raise _err()
+    raw = out.raw
+    return [raw[int(offs[i]):int(offs[i + 1])] for i in range(rows)]
+
+
+def scan_generated(cfg, flt, block_lo, block_hi, threads, want_counts=False):
+    """CPU baseline: multi-threaded blockSearch over generated blocks. -> dict(secs, stats, digest, matches, counts)"""
+    secs = C.c_double()
+    stats = np.zeros(6, dtype=np.uint64)
+    dig, tot = C.c_uint64(), C.c_uint64()
+    counts = np.zeros(block_hi - block_lo, dtype=np.uint32) if want_counts else None
+    r = lib().vlo_scan_generated(C.byref(cfg), flt.h, C.c_uint64(block_lo), C.c_uint64(block_hi), C.c_int(threads), C.byref(secs),
+                                 stats.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p) if want_counts else None,
+                                 C.byref(dig), C.byref(tot))
+    if r:
+        raise _err()
+    return dict(secs=secs.value, stats=stats, digest=dig.value, matches=tot.value, counts=counts)
