@@ -1,0 +1,192 @@
+/*
+ * vlscan.h -- C ABI of the B200-native LogsQL block-scan / filter engine (libvlscan.so).
+ *
+ * Drop-in boundary for lib/logstorage's query hot path.  The reference has no FFI seam; it is cut at the body of the
+ * search-worker loop over one blockSearchWorkBatch (lib/logstorage/storage_search.go:1044-1062): a batch of
+ * independent blocks sharing one searchOptions.filter goes in, one row bitmap per block comes out, and everything
+ * after it (blockResult.mustInit, initColumns, writeBlock) keeps working unchanged.  All file:line citations are
+ * relative to the VictoriaLogs reference tree.  INTEGRATION.md shows the cgo binding a maintainer would add.
+ *
+ * Conventions (mirroring the reference's only FFI precedent, vendor/github.com/valyala/gozstd/gozstd.go:14-38):
+ *   - plain pointers + sizes, no C++ / torch types; the library never retains caller pointers past return;
+ *   - int return: 0 OK, <0 malformed input (the Go side turns it into logger.Panicf("FATAL: ...") like
+ *     block_search.go:264,318,423,466), >0 CUDA error; text via vlscan_last_error();
+ *   - re-entrant across distinct vlscan_ctx; one ctx <-> one calling thread (= one search worker goroutine).
+ *   - there is NO CPU fallback: every entry point that computes fails with an error when no CUDA device is usable.
+ */
+#ifndef VLSCAN_H
+#define VLSCAN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vlscan_ctx vlscan_ctx;         /* per search-worker state: device, stream, staging buffers          */
+typedef struct vlscan_program vlscan_program; /* compiled filter tree (replaces so.filter, storage_search.go:1035)  */
+typedef struct vlscan_batch vlscan_batch;     /* a batch of blocks resident in HBM                                  */
+
+/* valueType, lib/logstorage/values_encoder.go:20-60 */
+enum {
+    VLSCAN_VT_STRING = 1, VLSCAN_VT_DICT = 2, VLSCAN_VT_UINT8 = 3, VLSCAN_VT_UINT16 = 4, VLSCAN_VT_UINT32 = 5,
+    VLSCAN_VT_UINT64 = 6, VLSCAN_VT_FLOAT64 = 7, VLSCAN_VT_IPV4 = 8, VLSCAN_VT_ISO8601 = 9, VLSCAN_VT_INT64 = 10
+};
+
+/* column kinds: what blockSearch.getConstColumnValue / getColumnHeader would find (block_search.go:232-324).
+ * A field that is absent from the block is simply not listed. */
+enum { VLSCAN_COL_CONST = 1, VLSCAN_COL_VALUES = 2 };
+
+/* stage of the values payload handed over */
+enum {
+    VLSCAN_STAGE_ONDISK = 0,  /* `values` = the bytes at [valuesOffset, +valuesSize) of the values file:
+                                 bytesBlock(uintBlock lens) ++ bytesBlock(data), plain or ZSTD
+                                 (lib/logstorage/encoding.go:16-50,343-426); ZSTD frames are decoded on the host with
+                                 libzstd at staging time, exactly where the reference calls cgo libzstd today       */
+    VLSCAN_STAGE_DECODED = 1  /* `lens_items` / `data` = what unmarshalBytesBlock yields for the two sub-blocks
+                                 (encoding.go:372-426): the uintBlock items incl. their type byte, and the data     */
+};
+
+/* One column of one block: the fields of columnHeader the scan needs (lib/logstorage/block_header.go:584-615) plus
+ * the payload bytes blockSearch would ReadAt (block_search.go:411-474). */
+typedef struct vlscan_column {
+    uint32_t field;         /* index into the batch's field-name table                                             */
+    uint8_t kind;           /* VLSCAN_COL_*                                                                        */
+    uint8_t value_type;     /* VLSCAN_VT_* (VALUES only)                                                           */
+    uint8_t stage;          /* VLSCAN_STAGE_* (VALUES only)                                                        */
+    uint8_t dict_len;       /* number of valuesDict entries (<= 8, values_encoder.go:1243-1322)                    */
+    uint64_t min_value;     /* columnHeader.minValue / maxValue (raw u64 bits; meaning depends on value_type)      */
+    uint64_t max_value;
+    const uint8_t* const_value; uint64_t const_len;      /* CONST: the value (<= 256 B, consts.go:41)              */
+    const uint8_t* dict_blob;   const uint32_t* dict_offsets; /* DICT: concatenated values + dict_len+1 offsets     */
+    const uint8_t* values;      uint64_t values_len;     /* STAGE_ONDISK                                           */
+    const uint8_t* lens_items;  uint64_t lens_items_len; /* STAGE_DECODED                                          */
+    const uint8_t* data;        uint64_t data_len;       /* STAGE_DECODED                                          */
+    const uint8_t* bloom;       uint64_t bloom_len;      /* big-endian u64 words as stored (bloomfilter.go:49-71)  */
+} vlscan_column;
+
+/* One block = blockSearchWork.bh.rowsCount + the columns the program references (block_search.go:64-77). */
+typedef struct vlscan_block {
+    uint64_t rows;
+    uint32_t ncols;
+    uint32_t reserved;
+    const vlscan_column* cols;
+} vlscan_block;
+
+/* Counters of one scan (block_stats-like accounting, lib/logstorage/pipe_block_stats.go:90-105). Algorithmic bytes
+ * are block-granular and follow the reference's short-circuit order (a column is charged when the reference would
+ * have called getValuesForColumn / getBloomFilterForColumn for it). */
+typedef struct vlscan_stats {
+    uint64_t blocks;              /* blocks submitted                                                              */
+    uint64_t rows;                /* rows submitted ("rows scanned")                                               */
+    uint64_t rows_matched;        /* sum of popcounts                                                              */
+    uint64_t blocks_matched;      /* blocks with a non-zero bitmap                                                 */
+    uint64_t values_bytes;        /* decoded payload (lens items + data) of every column read                      */
+    uint64_t bloom_probe_bytes;   /* 8 B x probes                                                                  */
+    uint64_t bitmap_bytes;        /* 8 B x words of non-zero result bitmaps                                        */
+    uint64_t columns_read;        /* (block, column) pairs whose values were read                                  */
+    uint64_t gpu_launches;        /* kernels launched by this call                                                 */
+    uint64_t h2d_bytes;           /* host->device bytes moved by this call                                         */
+    uint64_t d2h_bytes;           /* device->host bytes moved by this call                                         */
+    double gpu_ms;                /* device time of the scan kernels (CUDA events on the ctx stream)               */
+    double scan_kernel_ms;        /* device time of the dominant string-scan kernel launches only                  */
+    uint64_t scan_kernel_bytes;   /* algorithmic bytes processed by those launches                                 */
+} vlscan_stats;
+
+/* Synthetic data set description (benchmark / test infrastructure; row shape of app/vlogsgenerator/main.go:240-281). */
+typedef struct vlscan_gen_config {
+    uint64_t seed;
+    uint64_t total_rows;
+    uint32_t rows_per_block;
+    uint32_t hot_block_permille;
+    uint32_t hit_row_permille;
+    uint32_t columns_mask;       /* bit0 _msg, bit1 level, bit2 path, bit3 status */
+} vlscan_gen_config;
+
+/* ---- library / worker context ---------------------------------------------------------------------------------- */
+int vlscan_device_count(void);                               /* number of usable CUDA devices (0 => nothing works)  */
+vlscan_ctx* vlscan_ctx_create(int device);                   /* replaces getBlockSearch() per worker
+                                                                (storage_search.go:1041-1043); NULL on failure     */
+void vlscan_ctx_free(vlscan_ctx* ctx);
+const char* vlscan_last_error(const vlscan_ctx* ctx);        /* ctx may be NULL: last error of the calling thread   */
+void* vlscan_ctx_stream(const vlscan_ctx* ctx);              /* the cudaStream_t all work of this ctx is issued on  */
+int vlscan_ctx_sync(vlscan_ctx* ctx);                        /* cudaStreamSynchronize                               */
+
+/* ---- program: the filter tree ---------------------------------------------------------------------------------- */
+/* `tree` is the filter tree serialised depth-first (the Go shim walks `filter` values, lib/logstorage/filter.go:8-20):
+ *   node   := kind:u8 payload
+ *   bytes  := varuint(len) raw            (vm/encoding/int.go:506-527 MarshalBytes)
+ *   0 NOOP    (filter_noop.go)            -
+ *   1 PHRASE  (filter_phrase.go:25-32)    bytes(fieldName) bytes(phrase)
+ *   2 PREFIX  (filter_prefix.go:20-27)    bytes(fieldName) bytes(prefix)
+ *   3 EXACT   (filter_exact.go:17-24)     bytes(fieldName) bytes(value)
+ *   4 IN      (filter_in.go:14-18)        bytes(fieldName) varuint(n) n x bytes(value)
+ *   5 REGEXP  (filter_regexp.go:17-24)    bytes(fieldName) bytes(regexp source, regexutil.Regex.String())
+ *   6 AND     (filter_and.go:15-20)       varuint(n) n x node
+ *   7 OR      (filter_or.go:36-41)        varuint(n) n x node
+ *   8 NOT     (filter_not.go:11-13)       node
+ * Token hashes, merged AND/OR per-field tokens, typed needles and regex automata are derived here, like the
+ * sync.Once initialisers of the Go filters do on first use.  Returns <0 with an error text for malformed trees,
+ * regexps that do not compile and regexps outside the supported syntax. */
+enum { VLSCAN_F_NOOP = 0, VLSCAN_F_PHRASE, VLSCAN_F_PREFIX, VLSCAN_F_EXACT, VLSCAN_F_IN, VLSCAN_F_REGEXP, VLSCAN_F_AND, VLSCAN_F_OR, VLSCAN_F_NOT };
+int vlscan_program_create(const void* tree, size_t tree_len, vlscan_program** out);
+void vlscan_program_free(vlscan_program* prog);
+/* canonical names of the fields the tree references (so the caller lists only those columns per block) */
+uint32_t vlscan_program_nfields(const vlscan_program* prog);
+const char* vlscan_program_field(const vlscan_program* prog, uint32_t i, size_t* len);
+/* token strings of a leaf (tests; mirrors filterPhrase.getTokens() etc.), '\n'-joined into buf; returns length or -1 */
+int64_t vlscan_program_leaf_tokens(const vlscan_program* prog, uint32_t leaf, char* buf, size_t cap);
+
+/* ---- batches ---------------------------------------------------------------------------------------------------- */
+/* Stage `nblocks` blocks into HBM (host pointers in, pinned staging + cudaMemcpyAsync inside).  Field names are the
+ * canonical column names ("_msg" for the empty name, getCanonicalColumnName). */
+int vlscan_batch_upload(vlscan_ctx* ctx, const char* const* field_names, const size_t* field_name_lens, uint32_t nfields,
+                        const vlscan_block* blocks, uint64_t nblocks, vlscan_batch** out, vlscan_stats* stats /* may be NULL: h2d_bytes */);
+void vlscan_batch_free(vlscan_batch* batch);
+uint64_t vlscan_batch_nblocks(const vlscan_batch* batch);
+uint64_t vlscan_batch_rows(const vlscan_batch* batch);
+uint64_t vlscan_batch_words(const vlscan_batch* batch);      /* sum over blocks of ceil(rows/64)                    */
+uint64_t vlscan_batch_device_bytes(const vlscan_batch* batch);
+
+/* Generate blocks [block_lo, block_hi) of a synthetic data set directly in HBM (decoded stage + bloom filters, byte-
+ * identical to what the reference writer path would produce for the same rows; verified against the oracle). */
+int vlscan_batch_generate(vlscan_ctx* ctx, const vlscan_gen_config* cfg, uint64_t block_lo, uint64_t block_hi, vlscan_batch** out);
+
+/* Copy a resident batch back into caller-visible host memory as vlscan_block descriptors (decoded stage).  The
+ * descriptors and payloads live in one library-owned pinned host buffer that stays valid until vlscan_host_blocks_free. */
+typedef struct vlscan_host_blocks vlscan_host_blocks;
+int vlscan_batch_download(vlscan_ctx* ctx, const vlscan_batch* batch, vlscan_host_blocks** out);
+const vlscan_block* vlscan_host_blocks_get(const vlscan_host_blocks* hb, uint64_t* nblocks, uint32_t* nfields);
+const char* vlscan_host_blocks_field(const vlscan_host_blocks* hb, uint32_t i, size_t* len);
+uint64_t vlscan_host_blocks_bytes(const vlscan_host_blocks* hb);
+void vlscan_host_blocks_free(vlscan_host_blocks* hb);
+
+/* ---- the scan ---------------------------------------------------------------------------------------------------- */
+/* Scan a resident batch: equivalent of `for each block: bm.init(rows); bm.setBits(); filter.applyToBlockSearch(bs, bm)`
+ * (block_search.go:207-215).  Results stay on the device until fetched; the call only enqueues work on the ctx stream
+ * (no host synchronisation) unless `stats` is non-NULL, in which case it synchronises and fills the counters. */
+int vlscan_scan_resident(vlscan_ctx* ctx, const vlscan_program* prog, const vlscan_batch* batch, vlscan_stats* stats);
+
+/* Fetch the results of the last vlscan_scan_resident on this ctx.
+ *   out_bitmap_words : packed per-block bitmaps, block b at word offset sum_{i<b} ceil(rows_i/64); bit i%64 of word i/64
+ *                      = row i, tail bits zero (lib/logstorage/bitmap.go:28-31,62-72) so Go can alias it as bitmap.a
+ *   out_match_counts : per block onesCount() (bitmap.go:185-191) == blockResult.rowsLen (block_result.go:403-414)
+ * Either may be NULL. Synchronises the ctx stream. */
+int vlscan_fetch_results(vlscan_ctx* ctx, uint64_t* out_bitmap_words, uint32_t* out_match_counts, vlscan_stats* stats /* may be NULL: d2h_bytes */);
+/* Ascending hit-row indexes (u32 per hit, row index within its block) of the last scan, block after block; for callers
+ * that want to skip forEachSetBitReadonly (bitmap.go:156-183).  out_hit_offsets has nblocks+1 entries. */
+int vlscan_fetch_hits(vlscan_ctx* ctx, uint32_t* out_hit_rows, uint64_t cap, uint64_t* out_hit_offsets);
+/* Device pointers of the last scan's results (bench / multi-GPU reduce): bitmap words, per-block counts,
+ * and a 4 x u64 totals vector {rows, rows_matched, blocks_matched, values_bytes}. */
+int vlscan_result_device_ptrs(vlscan_ctx* ctx, void** bitmap_words, void** match_counts, void** totals4);
+
+/* End-to-end call on host buffers: upload + scan + fetch + free (what the cgo shim calls per work batch). */
+int vlscan_scan_batch(vlscan_ctx* ctx, const vlscan_program* prog, const char* const* field_names, const size_t* field_name_lens,
+                      uint32_t nfields, const vlscan_block* blocks, uint64_t nblocks, uint64_t* out_bitmap_words,
+                      uint32_t* out_match_counts, vlscan_stats* stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VLSCAN_H */

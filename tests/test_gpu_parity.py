@@ -1,0 +1,226 @@
+"""GPU parity tests: the CUDA path (through the C ABI, vlscan_scan_batch / vlscan_scan_resident) against the CPU oracle.
+
+Bar: bit-exact row bitmaps and match counts (integer / byte work; no tolerance).  Fixtures: every
+testFilterMatchForColumns(...) table of the reference's filter_{phrase,prefix,exact,in,regexp,not,and,or}_test.go
+(tests/golden/), seeded random differential cases, generated vlogsgenerator-shaped blocks, and the edge cases the
+reference tests cover (empty / single-row / const / dict / numeric / ragged / invalid UTF-8)."""
+import numpy as np
+import pytest
+
+from golden_util import load_filter_cases, build_filter, and_or_cases
+
+pytestmark = pytest.mark.gpu
+
+CASES = load_filter_cases()
+
+
+@pytest.fixture(scope="module")
+def env(oracle):
+    from victorialogs_b200 import scan as vs
+    import parity_util as pu
+    ctx = vs.Ctx(0)
+    yield oracle, vs, pu, ctx
+    ctx.close()
+
+
+def check(env, columns_or_blocks, spec_or_pair, stage="ondisk"):
+    oracle, vs, pu, ctx = env
+    blocks = columns_or_blocks if isinstance(columns_or_blocks[0], oracle.Block) else [oracle.Block.from_columns(columns_or_blocks)]
+    of, gf = spec_or_pair
+    want = [oracle.bitmap_rows(b.search(of), b.rows) for b in blocks]
+    got, counts, st = pu.gpu_rows(ctx, gf, blocks, stage)
+    assert got == want, (gf, [c.name for c in blocks[0].columns])
+    assert [int(c) for c in counts] == [len(w) for w in want]
+    assert st.rows == sum(b.rows for b in blocks) and st.rows_matched == sum(len(w) for w in want)
+    return want, st
+
+
+def test_reference_filter_tables_on_gpu(env):
+    """388 cases of filter_{phrase,prefix,exact,in,regexp,not}_test.go, on-disk stage (ZSTD decoded by the host stager)."""
+    oracle, vs, pu, ctx = env
+    unsupported = 0
+    for c in CASES:
+        b = oracle.Block.from_columns(c["columns"])
+        of, gf = build_filter(oracle.Filter, c["filter"]), build_filter(vs.Filter, c["filter"])
+        try:
+            got, counts, st = pu.gpu_rows(ctx, gf, [b])
+        except vs.VlscanError as e:
+            # declared limitation: phrase / prefix / regexp over float64 columns needs float -> text formatting on the device
+            assert "float64" in str(e), (c["src"], c["filter"], str(e))
+            unsupported += 1
+            continue
+        assert got[0] == c["expected"], (c["src"], c["filter"])
+        assert int(counts[0]) == len(c["expected"])
+    assert unsupported <= 40, unsupported
+
+
+def test_reference_filter_tables_decoded_stage(env):
+    oracle, vs, pu, ctx = env
+    for c in CASES[::7]:
+        b = oracle.Block.from_columns(c["columns"])
+        gf = build_filter(vs.Filter, c["filter"])
+        try:
+            got, counts, st = pu.gpu_rows(ctx, gf, [b], stage="decoded")
+        except vs.VlscanError as e:
+            assert "float64" in str(e)
+            continue
+        assert got[0] == c["expected"], (c["src"], c["filter"])
+
+
+def test_reference_and_or_tables_on_gpu(env):
+    oracle, vs, pu, ctx = env
+    for (q, cols, of, want), (_, _, gf, _) in zip(and_or_cases(oracle.Filter), and_or_cases(vs.Filter)):
+        b = oracle.Block.from_columns(cols)
+        got, counts, st = pu.gpu_rows(ctx, gf, [b])
+        assert got[0] == want, q
+
+
+def test_many_blocks_one_batch_and_resident_path(env):
+    """All golden blocks of one filter kind in ONE batch; resident scan == end-to-end scan; hit offsets == set bits."""
+    oracle, vs, pu, ctx = env
+    blocks = [oracle.Block.from_columns(c["columns"]) for c in CASES[:120]]
+    of, gf = oracle.Filter.phrase("foo", "abc"), vs.Filter.phrase("foo", "abc")
+    want = [oracle.bitmap_rows(b.search(of), b.rows) for b in blocks]
+    got, counts, st = pu.gpu_rows(ctx, gf, blocks)
+    assert got == want
+    hb = pu.host_blocks_from_oracle(blocks)
+    batch = ctx.upload(hb)
+    prog = vs.Program(gf)
+    st2 = ctx.scan_resident(prog, batch)
+    words, cnt = ctx.fetch()
+    per = vs.split_bitmaps(words, [b.rows for b in blocks])
+    assert [oracle.bitmap_rows(np.ascontiguousarray(w), b.rows) for w, b in zip(per, blocks)] == want
+    assert st2.rows_matched == sum(len(w) for w in want) and st2.gpu_launches > 0
+    hits, offs = ctx.fetch_hits()
+    flat = [r for w in want for r in w]
+    assert [int(h) for h in hits] == flat
+    assert [int(offs[i + 1] - offs[i]) for i in range(len(blocks))] == [len(w) for w in want]
+    batch.free()
+
+
+def _rand_text(rng, n, alphabet):
+    return "".join(rng.choice(alphabet, n))
+
+
+def test_random_differential_strings(env):
+    """Seeded random rows (ASCII, Cyrillic, CJK, invalid UTF-8, empty rows) x phrase / prefix / exact / in / regexp needles."""
+    oracle, vs, pu, ctx = env
+    rng = np.random.default_rng(20250718)
+    words = ["error", "errors", "timeout", "GET", "conn", "refused", "foo", "bar", "a", "ab", "abc", "теСТ", "тест", "日本", "x_y", "12", "3.4", "_"]
+    seps = [" ", "  ", ",", ".", "-", "/", ":", "=", "(", ")", "\n", "é", "€"]
+    def row():
+        k = int(rng.integers(0, 9))
+        s = "".join(str(rng.choice(words)) + str(rng.choice(seps)) for _ in range(k)).encode()
+        if rng.random() < 0.15:
+            pos = int(rng.integers(0, len(s) + 1))
+            s = s[:pos] + bytes([int(rng.integers(0x80, 0x100))]) + s[pos:]   # invalid / truncated UTF-8
+        if rng.random() < 0.1:
+            s = s[:int(rng.integers(0, len(s) + 1))]
+        return s
+    for trial in range(6):
+        nrows = int(rng.choice([1, 2, 63, 64, 65, 700, 3000]))
+        vals = [row() for _ in range(nrows)]
+        if len(set(vals)) <= 8:
+            vals += [b"pad %d" % i for i in range(9)]
+        cols = [("f", vals), ("id", [b"%d" % i for i in range(len(vals))])]
+        blk = oracle.Block.from_columns(cols)
+        assert any(c.name == b"f" and c.value_type == 1 for c in blk.columns)
+        needles = ["error", "err", "a", "ab", "GET", "теСТ", "ес", "日本", "x_y", "_", "12", "3.4", ".", " ", "", "conn", "é", "error,", "-foo", "o b", "refused)"]
+        for nd in needles:
+            for kind in ("phrase", "prefix", "exact"):
+                check(env, [blk], (getattr(oracle.Filter, kind)("f", nd), getattr(vs.Filter, kind)("f", nd)))
+        check(env, [blk], (oracle.Filter.in_("f", ["error ", "abc", "", vals[0]]), vs.Filter.in_("f", ["error ", "abc", "", vals[0]])))
+        for rx in ["err.*out", "conn.*refused", "foo|bar", "^error", "refused.$", "(?i)ERROR", "a+b", "[0-9]+\\.[0-9]", "GET.+", ".+GET.+", "error.", "x_y$", "^$",
+                   "тест|日本", "\\bfoo\\b", "o\\b", "e(rr|xx)or", "(foo|bar) (foo|bar)", "t.m.o", ".*", ".+", "", "foo.*", "[^a-z ]{3}"]:
+            check(env, [blk], (oracle.Filter.regexp("f", rx), vs.Filter.regexp("f", rx)))
+
+
+def test_numeric_and_special_columns(env):
+    oracle, vs, pu, ctx = env
+    n = 300
+    cols = [
+        ("u8", [b"%d" % (i % 200) for i in range(n)]),
+        ("u16", [b"%d" % (i * 37 % 60000) for i in range(n)]),
+        ("u32", [b"%d" % (i * 104729 % 4000000000) for i in range(n)]),
+        ("u64", [b"%d" % (i * 1234567890123 + 5000000000) for i in range(n)]),
+        ("i64", [b"%d" % ((i - 150) * 987654321) for i in range(n)]),
+        ("ip", [b"10.%d.%d.%d" % (i % 3, i % 251, (i * 7) % 256) for i in range(n)]),
+        ("ts", [b"2024-03-%02dT12:%02d:%02d.%03dZ" % (1 + i % 28, i % 60, (i * 7) % 60, i % 1000) for i in range(n)]),
+        ("lvl", [[b"info", b"warn", b"error", b"ERROR", b"debug"][i % 5] for i in range(n)]),
+        ("cst", [b"same value"] * n),
+        ("msg", [b"row %d has status %d" % (i, 200 + i % 5) for i in range(n)]),
+    ]
+    blk = oracle.Block.from_columns(cols)
+    vts = {c.name: c.value_type for c in blk.columns}
+    assert (vts[b"u8"], vts[b"u16"], vts[b"u32"], vts[b"u64"], vts[b"i64"], vts[b"ip"], vts[b"ts"], vts[b"lvl"]) == (3, 4, 5, 6, 10, 8, 9, 2)
+    F, G = oracle.Filter, vs.Filter
+    probes = [
+        ("phrase", "u8", "7"), ("phrase", "u8", "199"), ("phrase", "u8", "300"), ("phrase", "u8", "07"), ("exact", "u16", "37"), ("exact", "u16", "x"),
+        ("phrase", "u32", "104729"), ("phrase", "u64", "5000000000"), ("exact", "i64", "-987654321"), ("phrase", "i64", "0"), ("phrase", "i64", "-0"),
+        ("prefix", "u8", "1"), ("prefix", "u8", ""), ("prefix", "u16", "37"), ("prefix", "u32", "1047"), ("prefix", "u64", "12345"), ("prefix", "i64", "-"), ("prefix", "i64", "-98"),
+        ("prefix", "i64", "98"), ("phrase", "ip", "10.1.7.49"), ("phrase", "ip", "10.1"), ("phrase", "ip", "1"), ("prefix", "ip", "10.2"), ("prefix", "ip", "7"),
+        ("exact", "ip", "10.0.0.0"), ("phrase", "ts", "2024-03-05T12:04:28.004Z"), ("phrase", "ts", "2024-03-05"), ("prefix", "ts", "2024-03-1"), ("phrase", "ts", "12"),
+        ("phrase", "lvl", "error"), ("phrase", "lvl", "ERROR"), ("prefix", "lvl", "e"), ("exact", "lvl", "warn"), ("phrase", "lvl", "nope"),
+        ("phrase", "cst", "same"), ("phrase", "cst", "other"), ("prefix", "cst", "va"), ("exact", "cst", "same value"),
+        ("phrase", "missing", ""), ("phrase", "missing", "x"), ("prefix", "missing", ""), ("exact", "missing", ""),
+        ("phrase", "msg", "status"), ("phrase", "msg", "203"), ("prefix", "msg", "20"), ("exact", "msg", "row 7 has status 202"),
+    ]
+    for kind, field, arg in probes:
+        check(env, [blk], (getattr(F, kind)(field, arg), getattr(G, kind)(field, arg)))
+    for field, rx in [("u8", "^1.$"), ("u16", "37"), ("ip", "^10\\.1\\."), ("ts", "T12:0[0-3]"), ("lvl", "(?i)error"), ("cst", "val"), ("missing", "^$"), ("missing", "x"), ("i64", "^-")]:
+        check(env, [blk], (F.regexp(field, rx), G.regexp(field, rx)))
+    for field, vals in [("u8", ["7", "8", "x", "256"]), ("u16", ["37", "74"]), ("i64", ["-987654321", "0"]), ("ip", ["10.1.7.49", "1.1.1.1"]), ("lvl", ["warn", "ERROR"]),
+                        ("cst", ["same value"]), ("cst", ["other"]), ("missing", ["", "a"]), ("missing", ["a"]), ("msg", ["row 7 has status 202", "row 8 has status 203"]),
+                        ("u8", []), ("ts", ["2024-03-05T12:04:28.004Z"])]:
+        check(env, [blk], (F.in_(field, vals), G.in_(field, vals)))
+    # combinators across column kinds
+    tree_o = F.and_([F.phrase("msg", "status"), F.or_([F.phrase("lvl", "error"), F.in_("u8", ["7", "9"])]), F.not_(F.prefix("ip", "10.2"))])
+    tree_g = G.and_([G.phrase("msg", "status"), G.or_([G.phrase("lvl", "error"), G.in_("u8", ["7", "9"])]), G.not_(G.prefix("ip", "10.2"))])
+    check(env, [blk], (tree_o, tree_g))
+
+
+def test_block_shape_edge_cases(env):
+    oracle, vs, pu, ctx = env
+    F, G = oracle.Filter, vs.Filter
+    shapes = {
+        "single row": [("f", [b"only error row"]), ("g", [b"x"])],
+        "two equal-length rows (const lens)": [("f", [b"error aa", b"bb error"]), ("g", [b"1", b"2"])],
+        "rows of length 0 and 1": [("f", [b"", b"a", b"", b"b", b"error", b"", b"c", b"d", b"e", b"f"]), ("g", [b"%d" % i for i in range(10)])],
+        "long rows (u16 lens)": [("f", [b"x" * 300 + b" error " + b"y" * i for i in range(12)]), ("g", [b"%d" % i for i in range(12)])],
+        "very long row (u32 lens)": [("f", [b"z" * 70000 + b" error", b"short", b"error"] + [b"r%d" % i for i in range(9)]), ("g", [b"%d" % i for i in range(12)])],
+        "64k rows": [("f", [b"row %d %s" % (i, b"error" if i % 97 == 0 else b"fine") for i in range(65536)])],
+        "hit at the very end of the data": [("f", [b"aaa %d" % i for i in range(20)] + [b"tail error"])],
+        "needle straddles a row boundary": [("f", [b"xx err", b"or yy", b"error", b"er", b"ror"] + [b"q%d" % i for i in range(8)])],
+    }
+    for name, cols in shapes.items():
+        for kind, arg in [("phrase", "error"), ("prefix", "err"), ("exact", "error"), ("phrase", ""), ("prefix", ""), ("regexp", "err.*"), ("regexp", "^error$"), ("regexp", "r.w")]:
+            check(env, cols, (getattr(F, kind)("f", arg), getattr(G, kind)("f", arg)))
+    # an empty batch and a batch whose filter references no column at all
+    hb = vs.HostBlocks([b"_msg"], [])
+    words, counts, st = ctx.scan_batch(vs.Program(G.phrase("_msg", "x")), hb)
+    assert len(words) == 0 and st.rows == 0
+    check(env, shapes["single row"], (F.noop(), G.noop()))
+
+
+def test_malformed_blocks_are_rejected(env):
+    """Corrupt inputs return an error (the Go side turns it into logger.Panicf FATAL) instead of undefined behaviour."""
+    oracle, vs, pu, ctx = env
+    blk = oracle.Block.from_columns([("f", [b"row %d" % i for i in range(100)])])
+    d = pu.oracle_block_to_desc(blk, "decoded")
+    prog = vs.Program(vs.Filter.phrase("f", "row"))
+    bad = dict(d, columns=[dict(d["columns"][0], lens_items=d["columns"][0]["lens_items"][:-1])])
+    with pytest.raises(vs.VlscanError):
+        ctx.scan_batch(prog, vs.HostBlocks([b"f"], [bad]))
+    bad = dict(d, columns=[dict(d["columns"][0], data=d["columns"][0]["data"][:-3])])   # lens do not add up to the data length
+    with pytest.raises(vs.VlscanError):
+        ctx.scan_batch(prog, vs.HostBlocks([b"f"], [bad]))
+    bad = dict(d, columns=[dict(d["columns"][0], bloom=b"\x00" * 7)])
+    with pytest.raises(vs.VlscanError):
+        ctx.scan_batch(prog, vs.HostBlocks([b"f"], [bad]))
+    d2 = pu.oracle_block_to_desc(blk, "ondisk")
+    bad = dict(d2, columns=[dict(d2["columns"][0], values_block=d2["columns"][0]["values_block"][:-5])])
+    with pytest.raises(vs.VlscanError):
+        ctx.scan_batch(prog, vs.HostBlocks([b"f"], [bad]))
+    # the context stays usable afterwards
+    got, counts, st = pu.gpu_rows(ctx, vs.Filter.phrase("f", "row"), [blk])
+    assert len(got[0]) == 100

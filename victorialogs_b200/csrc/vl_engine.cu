@@ -1,0 +1,616 @@
+// libvlscan.so: staging of column blocks into HBM, the filter-tree interpreter that drives the CUDA kernels, and the
+// C ABI declared in include/vlscan.h.  There is no CPU code path for the scan itself: without a CUDA device every
+// computing entry point fails with an error.
+#include <dlfcn.h>
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include "vl_engine.h"
+#include "vl_program.h"
+
+using namespace vl;
+
+namespace vl {
+static thread_local std::string g_thread_err;
+void set_thread_error(const std::string& s) { g_thread_err = s; }
+}  // namespace vl
+
+struct vlscan_program {
+    Program p;
+    struct Image { DevBuf leaves, prepass, regexes, blob, u64s, u32s; DevProgram view; };
+    std::map<int, std::unique_ptr<Image>> images;
+    std::mutex mu;
+    const DevProgram& image(int device, cudaStream_t st) {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = images.find(device);
+        if (it != images.end()) return it->second->view;
+        auto im = std::make_unique<Image>();
+        auto up = [&](DevBuf& b, const void* src, size_t n) { b.ensure(std::max<size_t>(n, 16)); if (n) VL_CUDA(cudaMemcpyAsync(b.p, src, n, cudaMemcpyHostToDevice, st)); };
+        up(im->leaves, p.leaves.data(), p.leaves.size() * sizeof(DevLeaf));
+        up(im->prepass, p.prepass.data(), p.prepass.size() * sizeof(DevPrepass));
+        up(im->regexes, p.regexes.data(), p.regexes.size() * sizeof(DevRegex));
+        up(im->blob, p.blob.data(), p.blob.size());
+        up(im->u64s, p.u64s.data(), p.u64s.size() * 8);
+        up(im->u32s, p.u32s.data(), p.u32s.size() * 4);
+        VL_CUDA(cudaStreamSynchronize(st));
+        im->view = DevProgram{im->leaves.as<DevLeaf>(), im->prepass.as<DevPrepass>(), im->regexes.as<DevRegex>(), im->blob.as<uint8_t>(), im->u64s.as<uint64_t>(), im->u32s.as<uint32_t>()};
+        auto& ref = *im;
+        images[device] = std::move(im);
+        return ref.view;
+    }
+    ~vlscan_program() { for (auto& kv : images) { cudaSetDevice(kv.first); kv.second->leaves.release(); kv.second->prepass.release(); kv.second->regexes.release(); kv.second->blob.release(); kv.second->u64s.release(); kv.second->u32s.release(); } }
+};
+
+struct vlscan_host_blocks {
+    void* pinned = nullptr; size_t bytes = 0;
+    std::vector<vlscan_block> blocks;
+    std::vector<vlscan_column> cols;
+    std::vector<std::string> fields;
+    std::vector<std::vector<uint32_t>> dict_offsets;
+};
+
+void* vlscan_ctx::ensure_pinned(size_t n) {
+    if (n <= pinned_cap) return pinned;
+    if (pinned) cudaFreeHost(pinned);
+    pinned = nullptr; pinned_cap = 0;
+    VL_CUDA(cudaMallocHost(&pinned, n));
+    pinned_cap = n;
+    return pinned;
+}
+
+namespace {
+
+// ---- error plumbing --------------------------------------------------------------------------------------------------
+template <class F> int guarded(vlscan_ctx* ctx, F&& f) {
+    try { f(); return 0; }
+    catch (const CudaFail& e) { set_thread_error(e.msg); if (ctx) ctx->err = e.msg; return e.code > 0 ? e.code : 1; }
+    catch (const BadInput& e) { set_thread_error(e.msg); if (ctx) ctx->err = e.msg; return -1; }
+    catch (const ProgError& e) { set_thread_error(e.what()); if (ctx) ctx->err = e.what(); return -2; }
+    catch (const std::exception& e) { set_thread_error(e.what()); if (ctx) ctx->err = e.what(); return -3; }
+}
+
+// ---- libzstd (host staging of VLSCAN_STAGE_ONDISK payloads; the reference reaches the same library through cgo) -----------
+struct Zstd {
+    unsigned long long (*frame_size)(const void*, size_t) = nullptr;
+    size_t (*decompress)(void*, size_t, const void*, size_t) = nullptr;
+    unsigned (*is_error)(size_t) = nullptr;
+    bool ok = false;
+    Zstd() {
+        void* h = dlopen("libzstd.so.1", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return;
+        frame_size = (decltype(frame_size))dlsym(h, "ZSTD_getFrameContentSize");
+        decompress = (decltype(decompress))dlsym(h, "ZSTD_decompress");
+        is_error = (decltype(is_error))dlsym(h, "ZSTD_isError");
+        ok = frame_size && decompress && is_error;
+    }
+};
+Zstd& zstd() { static Zstd z; return z; }
+
+// unmarshalBytesBlock lib/logstorage/encoding.go:372-426; returns bytes consumed
+size_t host_unmarshal_bytes_block(std::vector<uint8_t>& dst, const uint8_t* src, size_t n) {
+    if (n < 1) throw BadInput("cannot unmarshal block type from empty src");
+    if (src[0] == 0) {
+        if (n < 2) throw BadInput("cannot unmarshal plain block size from empty src");
+        size_t len = src[1];
+        if (n - 2 < len) throw BadInput("cannot read plain block: not enough bytes");
+        dst.insert(dst.end(), src + 2, src + 2 + len);
+        return 2 + len;
+    }
+    if (src[0] == 1) {
+        uint64_t clen = 0; int sh = 0; size_t i = 1; bool done = false;
+        for (; i < n && i < 11; i++) { clen |= (uint64_t)(src[i] & 0x7F) << sh; sh += 7; if (src[i] < 0x80) { done = true; i++; break; } }
+        if (!done) throw BadInput("cannot unmarshal compressed block size");
+        if (n - i < clen) throw BadInput("cannot read compressed block: not enough bytes");
+        if (!zstd().ok) throw BadInput("libzstd.so.1 is not available for decoding a ZSTD values block");
+        unsigned long long dl = zstd().frame_size(src + i, clen);
+        if (dl == (unsigned long long)-1 || dl == (unsigned long long)-2 || dl > (64ull << 20)) throw BadInput("cannot decompress block: bad frame header");
+        size_t old = dst.size(); dst.resize(old + dl);
+        size_t got = zstd().decompress(dst.data() + old, dl, src + i, clen);
+        if (zstd().is_error(got) || got != dl) throw BadInput("cannot decompress block");
+        return i + clen;
+    }
+    throw BadInput("unexpected block type; supported types: 0, 1");
+}
+
+void launch_check(vlscan_ctx* ctx) { ctx->launches++; VL_CUDA(cudaGetLastError()); }
+inline unsigned cdiv(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
+
+}  // namespace
+
+// ---- batch layout shared with the generator ------------------------------------------------------------------------------
+namespace vl {
+void finish_batch_layout(vlscan_ctx* ctx, vlscan_batch* b, const std::vector<uint32_t>& rows) {
+    b->nblocks = rows.size();
+    b->h_rows = rows;
+    b->h_word_off.assign(rows.size() + 1, 0);
+    b->rows = 0;
+    for (size_t i = 0; i < rows.size(); i++) { b->h_word_off[i + 1] = b->h_word_off[i] + (rows[i] + 63) / 64; b->rows += rows[i]; }
+    b->nwords = b->h_word_off.back();
+    std::vector<uint32_t> wb(b->nwords);
+    std::vector<uint64_t> init(b->nwords);
+    for (size_t i = 0; i < rows.size(); i++) {
+        for (uint64_t w = b->h_word_off[i]; w < b->h_word_off[i + 1]; w++) { wb[w] = (uint32_t)i; init[w] = ~0ull; }
+        uint32_t tail = rows[i] & 63;   // bitmap.setBits: tail bits beyond bitsLen stay zero (bitmap.go:62-72)
+        if (tail) init[b->h_word_off[i + 1] - 1] = (~0ull) >> (64 - tail);
+    }
+    b->blk_rows.ensure(std::max<size_t>(rows.size() * 4, 16));
+    b->blk_word_off.ensure((rows.size() + 1) * 8);
+    b->word_block.ensure(std::max<size_t>(b->nwords * 4, 16));
+    b->init_bitmap.ensure(std::max<size_t>(b->nwords * 8, 16));
+    if (!rows.empty()) VL_CUDA(cudaMemcpyAsync(b->blk_rows.p, rows.data(), rows.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    VL_CUDA(cudaMemcpyAsync(b->blk_word_off.p, b->h_word_off.data(), (rows.size() + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (b->nwords) {
+        VL_CUDA(cudaMemcpyAsync(b->word_block.p, wb.data(), b->nwords * 4, cudaMemcpyHostToDevice, ctx->stream));
+        VL_CUDA(cudaMemcpyAsync(b->init_bitmap.p, init.data(), b->nwords * 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    VL_CUDA(cudaStreamSynchronize(ctx->stream));   // wb / init are stack-owned
+}
+}  // namespace vl
+
+// ---- upload --------------------------------------------------------------------------------------------------------------
+static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const size_t* field_name_lens, uint32_t nfields, const vlscan_block* blocks,
+                      uint64_t nblocks, vlscan_batch* out, vlscan_stats* stats) {
+    VL_CUDA(cudaSetDevice(ctx->device));
+    if (nblocks > 0xFFFFFFF0ull) throw BadInput("too many blocks in one batch");
+    out->device = ctx->device; out->nfields = nfields;
+    for (uint32_t f = 0; f < nfields; f++) out->field_names.emplace_back(field_names[f], field_name_lens[f]);
+    std::vector<DevColumn> cols((size_t)nblocks * std::max<uint32_t>(nfields, 1));
+    memset(cols.data(), 0, cols.size() * sizeof(DevColumn));
+    std::vector<uint32_t> rows(nblocks);
+    struct Piece { const uint8_t* src; uint64_t len; uint64_t dst; };
+    std::vector<Piece> pieces;
+    std::vector<std::unique_ptr<std::vector<uint8_t>>> owned;   // decoded ONDISK payloads, dict metadata
+    uint64_t cursor = 16;   // the first 16 bytes stay unused so that every payload has a readable byte in front of it
+    auto add_piece = [&](const uint8_t* src, uint64_t len) { uint64_t off = arena_reserve(cursor, len); if (len) pieces.push_back({src, len, off}); return off; };
+    for (uint64_t b = 0; b < nblocks; b++) {
+        const vlscan_block& blk = blocks[b];
+        if (blk.rows > (8u << 20)) throw BadInput("block rows exceed maxRowsPerBlock (8Mi)");   // consts.go:24
+        rows[b] = (uint32_t)blk.rows;
+        for (uint32_t k = 0; k < blk.ncols; k++) {
+            const vlscan_column& c = blk.cols[k];
+            if (c.field >= nfields) throw BadInput("column refers to a field outside the batch field table");
+            DevColumn& d = cols[(size_t)b * nfields + c.field];
+            if (d.kind != COL_MISSING) throw BadInput("duplicate column for one field in a block");
+            if (c.kind == VLSCAN_COL_CONST) {
+                d.kind = COL_CONST; d.meta_len = (uint32_t)c.const_len; d.meta_off = add_piece(c.const_value, c.const_len);
+                continue;
+            }
+            if (c.kind != VLSCAN_COL_VALUES) throw BadInput("unknown column kind");
+            if (c.value_type < VT_STRING || c.value_type >= VT_MAX) throw BadInput("unknown valueType");
+            d.kind = COL_VALUES; d.vt = c.value_type; d.min_value = c.min_value; d.max_value = c.max_value;
+            const uint8_t* lens_items; uint64_t lens_len; const uint8_t* data; uint64_t data_len;
+            if (c.stage == VLSCAN_STAGE_ONDISK) {
+                // stringsBlockUnmarshaler.unmarshal: bytesBlock(lens) ++ bytesBlock(data) (encoding.go:83-108)
+                auto lv = std::make_unique<std::vector<uint8_t>>(); auto dv = std::make_unique<std::vector<uint8_t>>();
+                size_t c1 = host_unmarshal_bytes_block(*lv, c.values, c.values_len);
+                size_t c2 = host_unmarshal_bytes_block(*dv, c.values + c1, c.values_len - c1);
+                if (c1 + c2 != c.values_len) throw BadInput("unexpected non-empty tail after reading bytes block with strings");
+                lens_items = lv->data(); lens_len = lv->size(); data = dv->data(); data_len = dv->size();
+                owned.push_back(std::move(lv)); owned.push_back(std::move(dv));
+            } else if (c.stage == VLSCAN_STAGE_DECODED) {
+                lens_items = c.lens_items; lens_len = c.lens_items_len; data = c.data; data_len = c.data_len;
+            } else throw BadInput("unknown values stage");
+            // unmarshalUint64Items header checks (encoding.go:246-336)
+            if (lens_len < 1) throw BadInput("cannot unmarshal uint64 block type from empty src");
+            uint8_t lt = lens_items[0];
+            if (lt > 7) throw BadInput("unexpected uint64 block type");
+            uint64_t want = lt < 4 ? (blk.rows << lt) : (1ull << (lt - 4));
+            if (lens_len - 1 != want) throw BadInput("unexpected block length for uint items");
+            d.lens_type = lt;
+            if (lt >= 4) { uint64_t v = 0; for (uint64_t i = 0; i < want; i++) v = (v << 8) | lens_items[1 + i]; if (v > 0xFFFFFFFFull) throw BadInput("row length does not fit 32 bits"); d.lens_const = (uint32_t)v; }
+            if (data_len > 0xFFFFFFFFull) throw BadInput("values block too large");
+            d.lens_off = add_piece(lens_items + 1, lens_len - 1);
+            d.data_off = add_piece(data, data_len); d.data_len = data_len;
+            // decode rule of encoding.go:113-120: rows >= 2, all lens equal, len(data) == lens[0] => every row = data
+            d.data_const = (blk.rows >= 2 && lt >= 4 && data_len == d.lens_const) ? 1 : 0;
+            if (c.bloom_len % 8) throw BadInput("cannot unmarshal bloomFilter from src with size not multiple by 8");   // bloomfilter.go:59-61
+            d.bloom_words = (uint32_t)(c.bloom_len / 8); d.bloom_off = add_piece(c.bloom, c.bloom_len);
+            if (c.value_type == VT_DICT) {
+                if (c.dict_len > 8) throw BadInput("valuesDict may contain max 8 items");
+                d.dict_len = c.dict_len;
+                auto meta = std::make_unique<std::vector<uint8_t>>();
+                uint32_t total = c.dict_len ? c.dict_offsets[c.dict_len] : 0;
+                meta->resize(4 * (c.dict_len + 1) + total);
+                if (c.dict_len) memcpy(meta->data(), c.dict_offsets, 4 * (c.dict_len + 1)); else memset(meta->data(), 0, 4);
+                if (total) memcpy(meta->data() + 4 * (c.dict_len + 1), c.dict_blob, total);
+                d.meta_len = total; d.meta_off = add_piece(meta->data(), meta->size());
+                owned.push_back(std::move(meta));
+            }
+        }
+    }
+    out->arena_bytes = cursor + kArenaPad;
+    out->arena.ensure(out->arena_bytes);
+    // copy pieces: runs that are contiguous on both sides (src stride == dst stride) and live in pinned host memory go out as one
+    // cudaMemcpyAsync; everything else is packed through a pinned staging ring.
+    uint64_t h2d = 0;
+    const size_t CH = 32u << 20;
+    uint8_t* stage = nullptr; cudaEvent_t evs[2] = {nullptr, nullptr}; int cur = 0; size_t fill = 0; uint64_t chunk_dst = 0; bool chunk_open = false;
+    auto flush = [&]() {
+        if (!chunk_open || !fill) { chunk_open = false; fill = 0; return; }
+        VL_CUDA(cudaMemcpyAsync(out->arena.as<uint8_t>() + chunk_dst, stage + (size_t)cur * CH, fill, cudaMemcpyHostToDevice, ctx->stream));
+        VL_CUDA(cudaEventRecord(evs[cur], ctx->stream));
+        h2d += fill; cur ^= 1; fill = 0; chunk_open = false;
+        VL_CUDA(cudaEventSynchronize(evs[cur]));
+    };
+    auto is_pinned = [&](const void* p) { cudaPointerAttributes a; if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; } return a.type == cudaMemoryTypeHost; };
+    VL_CUDA(cudaMemsetAsync(out->arena.p, 0, out->arena_bytes, ctx->stream));
+    size_t i = 0;
+    bool all_pinned = !pieces.empty() && is_pinned(pieces.front().src) && is_pinned(pieces.back().src);
+    if (!all_pinned && !pieces.empty()) { stage = (uint8_t*)ctx->ensure_pinned(2 * CH); VL_CUDA(cudaEventCreateWithFlags(&evs[0], cudaEventDisableTiming)); VL_CUDA(cudaEventCreateWithFlags(&evs[1], cudaEventDisableTiming)); VL_CUDA(cudaEventRecord(evs[0], ctx->stream)); VL_CUDA(cudaEventRecord(evs[1], ctx->stream)); }
+    while (i < pieces.size()) {
+        if (all_pinned) {
+            size_t j = i; uint64_t len = pieces[i].len;
+            while (j + 1 < pieces.size() && pieces[j + 1].src - pieces[i].src == (ptrdiff_t)(pieces[j + 1].dst - pieces[i].dst) && pieces[j + 1].src > pieces[j].src) { j++; len = (pieces[j].dst - pieces[i].dst) + pieces[j].len; }
+            VL_CUDA(cudaMemcpyAsync(out->arena.as<uint8_t>() + pieces[i].dst, pieces[i].src, len, cudaMemcpyHostToDevice, ctx->stream));
+            h2d += len; i = j + 1;
+            continue;
+        }
+        const Piece& pc = pieces[i];
+        uint64_t done = 0;
+        while (done < pc.len) {
+            if (chunk_open && (chunk_dst + fill != pc.dst + done || fill == CH)) flush();
+            if (!chunk_open) { chunk_open = true; chunk_dst = pc.dst + done; fill = 0; }
+            size_t take = (size_t)std::min<uint64_t>(pc.len - done, CH - fill);
+            memcpy(stage + (size_t)cur * CH + fill, pc.src + done, take);
+            fill += take; done += take;
+            // the gap up to the next piece (alignment + pad) is zero in the arena already; close the chunk at piece end unless adjacent
+        }
+        // allow packing of the inter-piece padding when the next piece follows within the pad distance
+        if (i + 1 < pieces.size()) {
+            uint64_t gap = pieces[i + 1].dst - (pc.dst + pc.len);
+            if (gap <= 64 && fill + gap < CH) { memset(stage + (size_t)cur * CH + fill, 0, gap); fill += gap; } else flush();
+        }
+        i++;
+    }
+    flush();
+    for (int k = 0; k < 2; k++) if (evs[k]) cudaEventDestroy(evs[k]);
+    out->cols.ensure(std::max<size_t>(cols.size() * sizeof(DevColumn), 16));
+    if (!cols.empty()) VL_CUDA(cudaMemcpyAsync(out->cols.p, cols.data(), cols.size() * sizeof(DevColumn), cudaMemcpyHostToDevice, ctx->stream));
+    h2d += cols.size() * sizeof(DevColumn);
+    finish_batch_layout(ctx, out, rows);   // synchronises the stream => `owned`, `cols`, staging are safe to drop
+    h2d += out->nwords * 12 + nblocks * 12;
+    if (stats) stats->h2d_bytes += h2d;
+}
+
+// ---- the filter-tree interpreter --------------------------------------------------------------------------------------------
+namespace {
+struct ScanRun {
+    vlscan_ctx* ctx; const vlscan_program* prog; const vlscan_batch* batch;
+    DevProgram P; BatchView B; std::vector<int> field_slot;   // program field -> batch field slot or -1
+    unsigned long long* stats;
+    size_t regs_used = 0;
+
+    uint64_t* new_reg() {
+        if (regs_used == ctx->regs.size()) ctx->regs.emplace_back();
+        DevBuf& r = ctx->regs[regs_used++];
+        r.ensure(std::max<size_t>(B.nwords * 8, 16));
+        return r.as<uint64_t>();
+    }
+    void free_reg() { regs_used--; }
+    void copy_reg(uint64_t* dst, const uint64_t* src) { if (B.nwords) VL_CUDA(cudaMemcpyAsync(dst, src, B.nwords * 8, cudaMemcpyDeviceToDevice, ctx->stream)); }
+    void andnot(uint64_t* a, const uint64_t* b) { if (!B.nwords) return; k_andnot<<<cdiv(B.nwords, 256), 256, 0, ctx->stream>>>(a, b, B.nwords); launch_check(ctx); }
+    void block_any(const uint64_t* reg) { k_block_any<<<cdiv((uint64_t)B.nblocks * 32, 256), 256, 0, ctx->stream>>>(reg, B, ctx->alive.as<uint8_t>()); launch_check(ctx); }
+
+    void prepass(const PNode& nd, uint64_t* reg) {
+        if (nd.prepass_count == 0) return;
+        std::vector<int> slots(nd.prepass_count);
+        for (int e = 0; e < nd.prepass_count; e++) slots[e] = field_slot[prog->p.prepass[nd.prepass_begin + e].field];
+        // slots live in a small device array; successive pre-passes use disjoint regions of it
+        size_t off = slots_cursor; slots_cursor += slots.size();
+        ctx->slots.ensure(std::max<size_t>(slots_total * 4, 16));
+        VL_CUDA(cudaMemcpyAsync(ctx->slots.as<int>() + off, slots.data(), slots.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        block_any(reg);
+        k_prepass<<<cdiv((uint64_t)B.nblocks * 32, 128), 128, 0, ctx->stream>>>(P, B, (uint32_t)nd.prepass_begin, (uint32_t)nd.prepass_count, ctx->slots.as<int>() + off,
+                                                                             nd.kind == F_OR, reg, ctx->alive.as<uint8_t>(), stats);
+        launch_check(ctx);
+    }
+    size_t slots_cursor = 0, slots_total = 0;
+
+    void leaf(int leaf_idx, uint64_t* reg) {
+        const DevLeaf& L = prog->p.leaves[leaf_idx];
+        if (L.kind == F_NOOP) return;
+        int slot = field_slot[L.field];
+        uint8_t* action = ctx->action.as<uint8_t>(); uint64_t* payload = ctx->payload.as<uint64_t>(); uint64_t* leaf_bm = ctx->leaf_bm.as<uint64_t>();
+        block_any(reg);
+        k_plan_leaf<<<cdiv((uint64_t)B.nblocks * 32, 128), 128, 0, ctx->stream>>>(P, B, (uint32_t)leaf_idx, slot, ctx->alive.as<uint8_t>(), action, payload, stats);
+        launch_check(ctx);
+        if (slot >= 0 && B.nwords) {
+            uint32_t* wb = ctx->work_blocks.as<uint32_t>(); uint32_t* tp = ctx->tile_prefix.as<uint32_t>(); uint32_t* wc = ctx->work_count.as<uint32_t>();
+            uint32_t* ro = ctx->row_off64[slot].as<uint32_t>(); uint8_t* ready = ctx->ready[slot].as<uint8_t>();
+            if (!ctx->ready_cleared[slot]) { VL_CUDA(cudaMemsetAsync(ready, 0, B.nblocks, ctx->stream)); ctx->ready_cleared[slot] = 1; }
+            const int persistent = ctx->sm_count * 8;
+            // row-agnostic substring scan
+            if (L.str_strategy == STR_SCAN) {
+                VL_CUDA(cudaMemsetAsync(leaf_bm, 0, B.nwords * 8, ctx->stream));
+                k_build_worklist<<<1, 1024, 0, ctx->stream>>>(B, slot, action, (uint8_t)ACT_SCAN, (uint32_t)VL_TILE_BYTES, wb, tp, wc, stats, 1); launch_check(ctx);
+                k_lens_offsets<<<persistent, 256, 0, ctx->stream>>>(B, slot, wb, wc, ro, ready, stats); launch_check(ctx);
+                ScanParams sp; memset(&sp, 0, sizeof sp);
+                sp.mode = L.scan_mode; sp.needle_off = L.scan_needle_off; sp.needle_len = L.scan_needle_len; sp.starts_tok = L.starts_tok; sp.ends_tok = L.ends_tok; sp.regex = L.regex;
+                const uint8_t* nd = prog->p.blob.data() + L.scan_needle_off;
+                uint32_t k = std::min<uint32_t>(4, L.scan_needle_len);
+                for (uint32_t i = 0; i < k; i++) { sp.n4 |= (uint32_t)nd[i] << (8 * i); sp.m4 |= 0xFFu << (8 * i); }
+                if (L.scan_mode == SCAN_CONTAINS || L.scan_mode >= SCAN_RX_DOTPLUS) { sp.starts_tok = sp.ends_tok = 0; }
+                auto& evp = next_scan_events();
+                VL_CUDA(cudaEventRecord(evp.first, ctx->stream));
+                k_substr_scan<<<persistent, VL_SCAN_THREADS, 0, ctx->stream>>>(P, B, slot, sp, wb, tp, wc, ro, leaf_bm); launch_check(ctx);
+                VL_CUDA(cudaEventRecord(evp.second, ctx->stream));
+            }
+            // per-row matcher (string exact / in / general regexp; numeric columns through text)
+            k_build_worklist<<<1, 1024, 0, ctx->stream>>>(B, slot, action, (uint8_t)ACT_ROW, (uint32_t)VL_TILE_BYTES, wb, tp, wc, stats, 0); launch_check(ctx);
+            k_lens_offsets<<<persistent, 256, 0, ctx->stream>>>(B, slot, wb, wc, ro, ready, stats); launch_check(ctx);
+            k_row_match<<<cdiv(B.nwords * 32, 256), 256, 0, ctx->stream>>>(P, B, (uint32_t)leaf_idx, slot, action, payload, ro, leaf_bm); launch_check(ctx);
+            k_word_match<<<cdiv(B.nwords, 128), 128, 0, ctx->stream>>>(P, B, (uint32_t)leaf_idx, slot, action, payload, leaf_bm, stats); launch_check(ctx);
+        }
+        if (B.nwords) { k_apply_leaf<<<cdiv(B.nwords, 256), 256, 0, ctx->stream>>>(B, action, leaf_bm, reg); launch_check(ctx); }
+    }
+    std::pair<cudaEvent_t, cudaEvent_t>& next_scan_events() {
+        if (ctx->scan_events_used == ctx->scan_events.size()) { cudaEvent_t a, b; VL_CUDA(cudaEventCreate(&a)); VL_CUDA(cudaEventCreate(&b)); ctx->scan_events.emplace_back(a, b); }
+        return ctx->scan_events[ctx->scan_events_used++];
+    }
+    // applyToBlockSearch of the combinators: filter_and.go:58-74, filter_or.go:55-78, filter_not.go:38-46
+    void node(int id, uint64_t* reg) {
+        const PNode& nd = prog->p.nodes[id];
+        switch (nd.kind) {
+        case F_NOOP: break;
+        case F_AND: prepass(nd, reg); for (int k : nd.kids) node(k, reg); break;
+        case F_OR: {
+            prepass(nd, reg);
+            uint64_t* res = new_reg(); uint64_t* tmp = new_reg();
+            copy_reg(res, reg);
+            for (int k : nd.kids) { copy_reg(tmp, res); node(k, tmp); andnot(res, tmp); }
+            andnot(reg, res);
+            free_reg(); free_reg();
+            break;
+        }
+        case F_NOT: { uint64_t* tmp = new_reg(); copy_reg(tmp, reg); node(nd.kids[0], tmp); andnot(reg, tmp); free_reg(); break; }
+        default: leaf(nd.leaf, reg);
+        }
+    }
+};
+}  // namespace
+
+static void read_stats(vlscan_ctx* ctx, vlscan_stats* st, bool check_error) {
+    unsigned long long h[ST_COUNT];
+    VL_CUDA(cudaMemcpyAsync(h, ctx->stats.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    VL_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (check_error && h[ST_ERROR]) {
+        static const char* const msg[] = {"", "cannot unmarshal strings: row lengths do not add up to the data length", "too big index for dict value",
+                                          "unexpected length for binary representation of a number", "phrase/prefix/regexp over a float64 column needs float->string formatting, which the GPU engine does not implement",
+                                          "unexpected uint64 block type"};
+        throw BadInput(msg[std::min<unsigned long long>(h[ST_ERROR], 5)]);
+    }
+    if (!st) return;
+    st->values_bytes += h[ST_VALUES_BYTES]; st->bloom_probe_bytes += h[ST_BLOOM_BYTES]; st->columns_read += h[ST_COLUMNS_READ];
+    st->bitmap_bytes += h[ST_BITMAP_BYTES]; st->rows_matched += h[ST_ROWS_MATCHED]; st->blocks_matched += h[ST_BLOCKS_MATCHED];
+    st->scan_kernel_bytes += h[ST_SCAN_BYTES];
+    float ms = 0;
+    VL_CUDA(cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end)); st->gpu_ms += ms;
+    for (size_t i = 0; i < ctx->scan_events_used; i++) { VL_CUDA(cudaEventElapsedTime(&ms, ctx->scan_events[i].first, ctx->scan_events[i].second)); st->scan_kernel_ms += ms; }
+}
+
+static void do_scan(vlscan_ctx* ctx, const vlscan_program* prog, const vlscan_batch* batch, vlscan_stats* stats) {
+    VL_CUDA(cudaSetDevice(ctx->device));
+    if (batch->device != ctx->device) throw BadInput("batch lives on another device than the ctx");
+    ScanRun run{ctx, prog, batch};
+    run.P = const_cast<vlscan_program*>(prog)->image(ctx->device, ctx->stream);
+    run.B = batch->view();
+    const Program& pr = prog->p;
+    run.field_slot.assign(pr.fields.size(), -1);
+    for (size_t f = 0; f < pr.fields.size(); f++) for (uint32_t s = 0; s < batch->nfields; s++) if (batch->field_names[s] == pr.fields[f]) run.field_slot[f] = (int)s;
+    for (auto& nd : pr.nodes) run.slots_total += nd.prepass_count;
+    uint64_t nb = std::max<uint64_t>(batch->nblocks, 1), nw = std::max<uint64_t>(batch->nwords, 1);
+    ctx->alive.ensure(nb); ctx->action.ensure(nb); ctx->payload.ensure(nb * 8); ctx->leaf_bm.ensure(nw * 8);
+    ctx->work_blocks.ensure(nb * 4); ctx->tile_prefix.ensure((nb + 1) * 4); ctx->work_count.ensure(16);
+    ctx->stats.ensure(ST_COUNT * 8); ctx->totals.ensure(32); ctx->counts.ensure(nb * 4);
+    if (ctx->row_off64.size() < batch->nfields) { ctx->row_off64.resize(batch->nfields); ctx->ready.resize(batch->nfields); }
+    ctx->ready_cleared.assign(batch->nfields, 0);
+    for (uint32_t s = 0; s < batch->nfields; s++) { ctx->row_off64[s].ensure(nw * 4); ctx->ready[s].ensure(nb); }
+    uint64_t launches0 = ctx->launches;
+    ctx->scan_events_used = 0;
+    run.stats = ctx->stats.as<unsigned long long>();
+    VL_CUDA(cudaEventRecord(ctx->ev_begin, ctx->stream));
+    VL_CUDA(cudaMemsetAsync(ctx->stats.p, 0, ST_COUNT * 8, ctx->stream));
+    VL_CUDA(cudaMemsetAsync(ctx->totals.p, 0, 32, ctx->stream));
+    VL_CUDA(cudaMemsetAsync(ctx->work_count.p, 0, 16, ctx->stream));
+    // bm.init(rows); bm.setBits()   (block_search.go:213-214)
+    uint64_t* reg = run.new_reg();
+    run.copy_reg(reg, batch->init_bitmap.as<uint64_t>());
+    if (batch->nblocks) {
+        run.node(pr.root, reg);
+        k_finalize<<<cdiv((uint64_t)batch->nblocks * 32, 256), 256, 0, ctx->stream>>>(run.B, reg, ctx->counts.as<uint32_t>(), run.stats, ctx->totals.as<unsigned long long>());
+        launch_check(ctx);
+    }
+    VL_CUDA(cudaEventRecord(ctx->ev_end, ctx->stream));
+    ctx->last_batch = batch; ctx->has_result = true;
+    if (stats) {
+        read_stats(ctx, stats, true);
+        stats->blocks += batch->nblocks; stats->rows += batch->rows; stats->gpu_launches += ctx->launches - launches0;
+    }
+}
+
+// ---- C ABI -------------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int vlscan_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+vlscan_ctx* vlscan_ctx_create(int device) {
+    vlscan_ctx* ctx = new vlscan_ctx();
+    int rc = guarded(nullptr, [&] {
+        int n = vlscan_device_count();
+        if (n <= 0) throw CudaFail("no CUDA device is available: libvlscan has no CPU fallback", 100);
+        ctx->device = ((device % n) + n) % n;
+        VL_CUDA(cudaSetDevice(ctx->device));
+        VL_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        VL_CUDA(cudaEventCreate(&ctx->ev_begin)); VL_CUDA(cudaEventCreate(&ctx->ev_end));
+        cudaDeviceProp prop; VL_CUDA(cudaGetDeviceProperties(&prop, ctx->device)); ctx->sm_count = prop.multiProcessorCount;
+    });
+    if (rc) { delete ctx; return nullptr; }
+    return ctx;
+}
+void vlscan_ctx_free(vlscan_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (DevBuf* b : {&ctx->alive, &ctx->action, &ctx->payload, &ctx->leaf_bm, &ctx->work_blocks, &ctx->tile_prefix, &ctx->work_count, &ctx->stats, &ctx->totals, &ctx->counts, &ctx->slots, &ctx->hit_offs, &ctx->hits}) b->release();
+    for (auto& r : ctx->regs) r.release();
+    for (auto& r : ctx->row_off64) r.release();
+    for (auto& r : ctx->ready) r.release();
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (auto& e : ctx->scan_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
+    if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+const char* vlscan_last_error(const vlscan_ctx* ctx) { return ctx ? ctx->err.c_str() : g_thread_err.c_str(); }
+void* vlscan_ctx_stream(const vlscan_ctx* ctx) { return (void*)ctx->stream; }
+int vlscan_ctx_sync(vlscan_ctx* ctx) { return guarded(ctx, [&] { VL_CUDA(cudaSetDevice(ctx->device)); VL_CUDA(cudaStreamSynchronize(ctx->stream)); }); }
+
+int vlscan_program_create(const void* tree, size_t tree_len, vlscan_program** out) {
+    *out = nullptr;
+    auto* pg = new vlscan_program();
+    int rc = guarded(nullptr, [&] { ProgramBuilder(tree, tree_len, pg->p).build(); });
+    if (rc) { delete pg; return rc; }
+    *out = pg;
+    return 0;
+}
+void vlscan_program_free(vlscan_program* prog) { delete prog; }
+uint32_t vlscan_program_nfields(const vlscan_program* prog) { return (uint32_t)prog->p.fields.size(); }
+const char* vlscan_program_field(const vlscan_program* prog, uint32_t i, size_t* len) { *len = prog->p.fields[i].size(); return prog->p.fields[i].data(); }
+int64_t vlscan_program_leaf_tokens(const vlscan_program* prog, uint32_t leaf, char* buf, size_t cap) {
+    if (leaf >= prog->p.leaf_tokens.size()) return -1;
+    std::string s; for (size_t i = 0; i < prog->p.leaf_tokens[leaf].size(); i++) { if (i) s.push_back('\n'); s += prog->p.leaf_tokens[leaf][i]; }
+    if (s.size() > cap) return -1;
+    memcpy(buf, s.data(), s.size());
+    return (int64_t)s.size();
+}
+
+int vlscan_batch_upload(vlscan_ctx* ctx, const char* const* field_names, const size_t* field_name_lens, uint32_t nfields, const vlscan_block* blocks,
+                        uint64_t nblocks, vlscan_batch** out, vlscan_stats* stats) {
+    *out = nullptr;
+    auto* b = new vlscan_batch();
+    int rc = guarded(ctx, [&] { do_upload(ctx, field_names, field_name_lens, nfields, blocks, nblocks, b, stats); });
+    if (rc) { delete b; return rc; }
+    *out = b;
+    return 0;
+}
+void vlscan_batch_free(vlscan_batch* batch) { delete batch; }
+uint64_t vlscan_batch_nblocks(const vlscan_batch* b) { return b->nblocks; }
+uint64_t vlscan_batch_rows(const vlscan_batch* b) { return b->rows; }
+uint64_t vlscan_batch_words(const vlscan_batch* b) { return b->nwords; }
+uint64_t vlscan_batch_device_bytes(const vlscan_batch* b) { return b->device_bytes(); }
+
+int vlscan_batch_download(vlscan_ctx* ctx, const vlscan_batch* batch, vlscan_host_blocks** out) {
+    *out = nullptr;
+    auto* hb = new vlscan_host_blocks();
+    int rc = guarded(ctx, [&] {
+        VL_CUDA(cudaSetDevice(ctx->device));
+        hb->bytes = batch->arena_bytes;
+        VL_CUDA(cudaMallocHost(&hb->pinned, std::max<size_t>(hb->bytes, 16)));
+        std::vector<DevColumn> cols((size_t)batch->nblocks * batch->nfields);
+        VL_CUDA(cudaMemcpyAsync(hb->pinned, batch->arena.p, hb->bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if (!cols.empty()) VL_CUDA(cudaMemcpyAsync(cols.data(), batch->cols.p, cols.size() * sizeof(DevColumn), cudaMemcpyDeviceToHost, ctx->stream));
+        VL_CUDA(cudaStreamSynchronize(ctx->stream));
+        hb->fields = batch->field_names;
+        const uint8_t* base = (const uint8_t*)hb->pinned;
+        hb->blocks.resize(batch->nblocks);
+        hb->cols.reserve(cols.size());
+        // the lens type byte is not stored in the arena: rebuild "type + items" views in a side buffer kept alive by dict_offsets storage
+        std::vector<size_t> first(batch->nblocks + 1, 0);
+        for (uint64_t b = 0; b < batch->nblocks; b++) {
+            first[b] = hb->cols.size();
+            for (uint32_t f = 0; f < batch->nfields; f++) {
+                const DevColumn& d = cols[(size_t)b * batch->nfields + f];
+                if (d.kind == COL_MISSING) continue;
+                vlscan_column c; memset(&c, 0, sizeof c);
+                c.field = f;
+                if (d.kind == COL_CONST) { c.kind = VLSCAN_COL_CONST; c.const_value = base + d.meta_off; c.const_len = d.meta_len; hb->cols.push_back(c); continue; }
+                c.kind = VLSCAN_COL_VALUES; c.value_type = d.vt; c.stage = VLSCAN_STAGE_DECODED; c.dict_len = d.dict_len; c.min_value = d.min_value; c.max_value = d.max_value;
+                uint64_t items = d.lens_type < 4 ? ((uint64_t)batch->h_rows[b] << d.lens_type) : (1ull << (d.lens_type - 4));
+                // lens items are preceded in the arena by alignment slack; the type byte is materialised in the byte right before them
+                uint8_t* tb = (uint8_t*)hb->pinned + d.lens_off - 1;
+                *tb = d.lens_type;
+                c.lens_items = tb; c.lens_items_len = items + 1;
+                c.data = base + d.data_off; c.data_len = d.data_len;
+                c.bloom = base + d.bloom_off; c.bloom_len = (uint64_t)d.bloom_words * 8;
+                if (d.vt == VT_DICT) { c.dict_offsets = (const uint32_t*)(base + d.meta_off); c.dict_blob = base + d.meta_off + 4 * (d.dict_len + 1); }
+                hb->cols.push_back(c);
+            }
+        }
+        first[batch->nblocks] = hb->cols.size();
+        for (uint64_t b = 0; b < batch->nblocks; b++) { hb->blocks[b].rows = batch->h_rows[b]; hb->blocks[b].ncols = (uint32_t)(first[b + 1] - first[b]); hb->blocks[b].cols = hb->cols.data() + first[b]; }
+    });
+    if (rc) { if (hb->pinned) cudaFreeHost(hb->pinned); delete hb; return rc; }
+    *out = hb;
+    return 0;
+}
+const vlscan_block* vlscan_host_blocks_get(const vlscan_host_blocks* hb, uint64_t* nblocks, uint32_t* nfields) { *nblocks = hb->blocks.size(); *nfields = (uint32_t)hb->fields.size(); return hb->blocks.data(); }
+const char* vlscan_host_blocks_field(const vlscan_host_blocks* hb, uint32_t i, size_t* len) { *len = hb->fields[i].size(); return hb->fields[i].data(); }
+uint64_t vlscan_host_blocks_bytes(const vlscan_host_blocks* hb) { return hb->bytes; }
+void vlscan_host_blocks_free(vlscan_host_blocks* hb) { if (!hb) return; if (hb->pinned) cudaFreeHost(hb->pinned); delete hb; }
+
+int vlscan_scan_resident(vlscan_ctx* ctx, const vlscan_program* prog, const vlscan_batch* batch, vlscan_stats* stats) {
+    return guarded(ctx, [&] { do_scan(ctx, prog, batch, stats); });
+}
+
+int vlscan_fetch_results(vlscan_ctx* ctx, uint64_t* out_bitmap_words, uint32_t* out_match_counts, vlscan_stats* stats) {
+    return guarded(ctx, [&] {
+        if (!ctx->has_result) throw BadInput("no scan result to fetch on this ctx");
+        VL_CUDA(cudaSetDevice(ctx->device));
+        const vlscan_batch* b = ctx->last_batch;
+        uint64_t d2h = 0;
+        if (out_bitmap_words && b->nwords) { VL_CUDA(cudaMemcpyAsync(out_bitmap_words, ctx->regs[0].p, b->nwords * 8, cudaMemcpyDeviceToHost, ctx->stream)); d2h += b->nwords * 8; }
+        if (out_match_counts && b->nblocks) { VL_CUDA(cudaMemcpyAsync(out_match_counts, ctx->counts.p, b->nblocks * 4, cudaMemcpyDeviceToHost, ctx->stream)); d2h += b->nblocks * 4; }
+        read_stats(ctx, nullptr, true);
+        if (stats) stats->d2h_bytes += d2h;
+    });
+}
+
+int vlscan_fetch_hits(vlscan_ctx* ctx, uint32_t* out_hit_rows, uint64_t cap, uint64_t* out_hit_offsets) {
+    return guarded(ctx, [&] {
+        if (!ctx->has_result) throw BadInput("no scan result to fetch on this ctx");
+        VL_CUDA(cudaSetDevice(ctx->device));
+        const vlscan_batch* b = ctx->last_batch;
+        BatchView B = b->view();
+        ctx->hit_offs.ensure((b->nblocks + 1) * 8); ctx->hits.ensure(std::max<uint64_t>(cap, 4) * 4);
+        k_scan_counts<<<1, 1024, 0, ctx->stream>>>(ctx->counts.as<uint32_t>(), (uint32_t)b->nblocks, ctx->hit_offs.as<uint64_t>()); launch_check(ctx);
+        if (b->nblocks) { k_hits_compact<<<cdiv((uint64_t)b->nblocks * 32, 256), 256, 0, ctx->stream>>>(B, ctx->regs[0].as<uint64_t>(), ctx->hit_offs.as<uint64_t>(), ctx->hits.as<uint32_t>(), cap); launch_check(ctx); }
+        VL_CUDA(cudaMemcpyAsync(out_hit_offsets, ctx->hit_offs.p, (b->nblocks + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        VL_CUDA(cudaStreamSynchronize(ctx->stream));
+        uint64_t total = out_hit_offsets[b->nblocks];
+        if (total > cap) throw BadInput("hit buffer too small");
+        if (total) VL_CUDA(cudaMemcpyAsync(out_hit_rows, ctx->hits.p, total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        VL_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+int vlscan_result_device_ptrs(vlscan_ctx* ctx, void** bitmap_words, void** match_counts, void** totals4) {
+    if (!ctx->has_result) { ctx->err = "no scan result on this ctx"; return -1; }
+    if (bitmap_words) *bitmap_words = ctx->regs[0].p;
+    if (match_counts) *match_counts = ctx->counts.p;
+    if (totals4) *totals4 = ctx->totals.p;
+    return 0;
+}
+
+int vlscan_scan_batch(vlscan_ctx* ctx, const vlscan_program* prog, const char* const* field_names, const size_t* field_name_lens, uint32_t nfields,
+                      const vlscan_block* blocks, uint64_t nblocks, uint64_t* out_bitmap_words, uint32_t* out_match_counts, vlscan_stats* stats) {
+    vlscan_batch* b = nullptr;
+    int rc = vlscan_batch_upload(ctx, field_names, field_name_lens, nfields, blocks, nblocks, &b, stats);
+    if (rc) return rc;
+    rc = vlscan_scan_resident(ctx, prog, b, nullptr);
+    if (!rc) rc = vlscan_fetch_results(ctx, out_bitmap_words, out_match_counts, stats);
+    if (!rc && stats) {
+        rc = guarded(ctx, [&] { read_stats(ctx, stats, true); stats->blocks += b->nblocks; stats->rows += b->rows; });
+    }
+    ctx->has_result = false; ctx->last_batch = nullptr;
+    vlscan_batch_free(b);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,90 @@
+// Internal structures of libvlscan.so shared by vl_engine.cu (staging, scan interpreter, C ABI) and vl_gen.cu
+// (synthetic batch generator).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/vlscan.h"
+#include "vl_kernels.cuh"
+
+namespace vl {
+
+void set_thread_error(const std::string& s);
+#define VL_CUDA(call)                                                                                                   \
+    do {                                                                                                                \
+        cudaError_t e__ = (call);                                                                                       \
+        if (e__ != cudaSuccess) throw CudaFail(std::string(#call) + ": " + cudaGetErrorString(e__), (int)e__);        \
+    } while (0)
+struct CudaFail { std::string msg; int code; CudaFail(std::string m, int c) : msg(std::move(m)), code(c) {} };
+struct BadInput { std::string msg; explicit BadInput(std::string m) : msg(std::move(m)) {} };
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    void ensure(size_t n) {
+        if (n <= cap) return;
+        if (p) VL_CUDA(cudaFree(p));
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 256;
+        VL_CUDA(cudaMalloc(&p, want)); cap = want;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+static const size_t kArenaAlign = 16;
+static const size_t kArenaPad = 32;   // readable slack after every payload (vector loads past the end, see k_substr_scan)
+inline uint64_t arena_reserve(uint64_t& cursor, uint64_t len) {
+    uint64_t off = (cursor + kArenaAlign - 1) / kArenaAlign * kArenaAlign;
+    cursor = off + len + kArenaPad;
+    return off;
+}
+
+}  // namespace vl
+
+// opaque C ABI types
+struct vlscan_batch {
+    int device = 0;
+    uint32_t nfields = 0;
+    std::vector<std::string> field_names;
+    uint64_t nblocks = 0, nwords = 0, rows = 0;
+    uint64_t arena_bytes = 0;
+    vl::DevBuf arena, cols, blk_rows, blk_word_off, word_block, init_bitmap;
+    std::vector<uint32_t> h_rows;
+    std::vector<uint64_t> h_word_off;
+    vl::BatchView view() const {
+        vl::BatchView v;
+        v.arena = arena.as<uint8_t>(); v.cols = cols.as<vl::DevColumn>(); v.blk_rows = blk_rows.as<uint32_t>();
+        v.blk_word_off = blk_word_off.as<uint64_t>(); v.word_block = word_block.as<uint32_t>();
+        v.nblocks = (uint32_t)nblocks; v.nfields = nfields; v.nwords = nwords;
+        return v;
+    }
+    uint64_t device_bytes() const { return arena.cap + cols.cap + blk_rows.cap + blk_word_off.cap + word_block.cap + init_bitmap.cap; }
+    ~vlscan_batch() { cudaSetDevice(device); arena.release(); cols.release(); blk_rows.release(); blk_word_off.release(); word_block.release(); init_bitmap.release(); }
+};
+
+struct vlscan_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    // scratch (grow-only)
+    vl::DevBuf alive, action, payload, leaf_bm, work_blocks, tile_prefix, work_count, stats, totals, counts, slots, hit_offs, hits;
+    std::vector<vl::DevBuf> regs;          // bitmap registers of the tree interpreter
+    std::vector<vl::DevBuf> row_off64;     // per batch field slot
+    std::vector<vl::DevBuf> ready;         // per batch field slot: row_off64 computed for block b in this scan
+    std::vector<char> ready_cleared;
+    void* pinned = nullptr; size_t pinned_cap = 0;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> scan_events; size_t scan_events_used = 0;
+    // last scan
+    const vlscan_batch* last_batch = nullptr;
+    bool has_result = false;
+    int sm_count = 148;
+    void* ensure_pinned(size_t n);
+};
+
+namespace vl {
+// fills word_block / init_bitmap / blk_* device arrays of a batch from host row counts (shared by upload + generate)
+void finish_batch_layout(vlscan_ctx* ctx, vlscan_batch* b, const std::vector<uint32_t>& rows);
+}

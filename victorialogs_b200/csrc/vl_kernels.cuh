@@ -1,0 +1,693 @@
+// CUDA kernels of the block-scan engine (sm_100a).  HBM-bound byte / bitmap work: coalesced 16-byte vector loads,
+// warp ballots / shuffles, no tensor cores.  Each kernel names the reference code it replaces.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "vl_hd.cuh"
+#include "vl_types.h"
+
+namespace vl {
+
+struct DevProgram {
+    const DevLeaf* leaves; const DevPrepass* prepass; const DevRegex* regexes;
+    const uint8_t* blob; const uint64_t* u64s; const uint32_t* u32s;
+};
+
+// stats slots (device u64 array)
+enum { ST_VALUES_BYTES = 0, ST_BLOOM_BYTES, ST_COLUMNS_READ, ST_BITMAP_BYTES, ST_ROWS_MATCHED, ST_BLOCKS_MATCHED, ST_ERROR, ST_SCAN_BYTES, ST_COUNT };
+enum { ERR_NONE = 0, ERR_LENS_MISMATCH = 1, ERR_DICT_INDEX = 2, ERR_BAD_WIDTH = 3, ERR_UNSUPPORTED_FLOAT_TOSTRING = 4, ERR_BAD_LENS_TYPE = 5 };
+
+struct BatchView {
+    const uint8_t* arena;
+    const DevColumn* cols;        // [nblocks * nfields]
+    const uint32_t* blk_rows;     // [nblocks]
+    const uint64_t* blk_word_off; // [nblocks + 1]
+    const uint32_t* word_block;   // [nwords] owning block of each bitmap word
+    uint32_t nblocks, nfields;
+    uint64_t nwords;
+};
+
+static __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+static __device__ __forceinline__ uint32_t width_of_vt(uint32_t vt) {
+    switch (vt) { case VT_DICT: case VT_UINT8: return 1; case VT_UINT16: return 2; case VT_UINT32: case VT_IPV4: return 4; case VT_UINT64: case VT_FLOAT64: case VT_ISO8601: case VT_INT64: return 8; }
+    return 0;
+}
+static __device__ __forceinline__ uint64_t lens_stored_bytes(const DevColumn& c, uint32_t rows) {
+    return 1 + (c.lens_type < 4 ? ((uint64_t)rows << c.lens_type) : (1ull << (c.lens_type - 4)));
+}
+// length of row r (unmarshalUint64Items lib/logstorage/encoding.go:246-336)
+static __device__ __forceinline__ uint32_t row_len(const DevColumn& c, const uint8_t* lens, uint32_t r) {
+    switch (c.lens_type) {
+    case 0: return lens[r];
+    case 1: return ld_be16(lens + 2 * (uint64_t)r);
+    case 2: return ld_be32(lens + 4 * (uint64_t)r);
+    case 3: return (uint32_t)ld_be64(lens + 8 * (uint64_t)r);
+    default: return c.lens_const;
+    }
+}
+static __device__ __forceinline__ uint64_t load_fixed_be(const uint8_t* p, uint32_t w) {
+    switch (w) { case 1: return p[0]; case 2: return ld_be16(p); case 4: return ld_be32(p); default: return ld_be64(p); }
+}
+static __device__ __forceinline__ int64_t unzigzag64(uint64_t u) { return (int64_t)(u >> 1) ^ -(int64_t)(u & 1); }
+
+// ---- regex on device (regexutil.Regex.MatchString, regex.go:86-212) -----------------------------------------------------------
+static __device__ __forceinline__ uint32_t rx_class(const DevRegex& R, const uint8_t* blob, int32_t r) {
+    if (r < 128) return blob[R.ascii_off + r];
+    const int32_t* b = (const int32_t*)(blob + R.bounds_off);
+    int lo = 0, hi = (int)R.nclasses - 1;
+    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (b[mid] <= r) lo = mid; else hi = mid - 1; }
+    return (uint32_t)lo;
+}
+static __device__ bool dfa_run(const DevRegex& R, const uint8_t* blob, const uint8_t* s, uint32_t n) {
+    const uint16_t* T = (const uint16_t*)(blob + R.trans_off);
+    uint32_t st = 0;
+    for (uint32_t i = 0; i < n;) {
+        int w; int32_t r = s[i];
+        if (r < 0x80) w = 1; else r = decode_rune(s + i, n - i, &w);
+        i += w;
+        uint32_t e = T[st * R.nclasses + rx_class(R, blob, r)];
+        if (e & 0x8000) return true;
+        st = e & 0x7FFF;
+        if (st == 0x7FFF) return false;
+    }
+    return blob[R.accept_off + st] != 0;
+}
+static __device__ bool regex_match(const DevRegex& R, const uint8_t* blob, const uint8_t* s, uint32_t n) {
+    const uint8_t* pre = blob + R.prefix_off; uint32_t pl = R.prefix_len;
+    const uint8_t* sub = blob + R.sub_off; uint32_t sl = R.sub_len;
+    if (R.only_prefix) return pl == 0 || find_bytes(s, n, pre, pl, 0) >= 0;
+    if (pl == 0) {
+        if (R.dot_star) return true;
+        if (R.dot_plus) return n > 0;
+        if (R.sub_kind == 1) return find_bytes(s, n, sub, sl, 0) >= 0;
+        if (R.sub_kind == 2) { int k = find_bytes(s, n, sub, sl, 0); return k > 0 && (uint32_t)k + sl < n; }
+        return dfa_run(R, blob, s, n);
+    }
+    int k = find_bytes(s, n, pre, pl, 0);
+    if (k < 0) return false;
+    uint32_t rem = (uint32_t)k + pl;
+    if (R.dot_star) return true;
+    if (R.dot_plus) return n > rem;
+    if (R.sub_kind == 1) return find_bytes(s + rem, n - rem, sub, sl, 0) >= 0;
+    if (R.sub_kind == 2) { int m = find_bytes(s + rem, n - rem, sub, sl, 0); return m > 0 && (uint32_t)m + sl < n - rem; }
+    for (;;) {
+        if (dfa_run(R, blob, s + rem, n - rem)) return true;
+        k = find_bytes(s, n, pre, pl, (uint32_t)k + 1);
+        if (k < 0) return false;
+        rem = (uint32_t)k + pl;
+    }
+}
+
+// in(): is the string one of the values (filter_in.go:187-200 for string columns / const / dict)
+static __device__ bool in_contains_string(const DevLeaf& L, const uint8_t* blob, const uint8_t* s, uint32_t n) {
+    const uint32_t* offs = (const uint32_t*)(blob + L.in_offs_off);
+    const uint8_t* base = blob + L.in_blob_off;
+    for (uint32_t i = 0; i < L.in_count; i++) { uint32_t a = offs[i], b = offs[i + 1]; if (b - a == n && bytes_equal(base + a, n, s, n)) return true; }
+    return false;
+}
+static __device__ __forceinline__ bool in_contains_typed(const DevLeaf& L, const uint64_t* u64s, uint32_t vt, uint64_t v) {
+    const uint64_t* set = u64s + L.in_typed_off[vt];
+    int lo = 0, hi = (int)L.in_typed_cnt[vt] - 1;
+    while (lo <= hi) { int mid = (lo + hi) >> 1; uint64_t x = set[mid]; if (x == v) return true; if (x < v) lo = mid + 1; else hi = mid - 1; }
+    return false;
+}
+
+// generic string predicate of a leaf: the closure passed to visitValues / applied to const + dict values
+static __device__ bool leaf_match_string(const DevProgram& P, const DevLeaf& L, const uint8_t* s, uint32_t n) {
+    const uint8_t* nd = P.blob + L.needle_off;
+    switch (L.kind) {
+    case F_PHRASE: return match_phrase(s, n, nd, L.needle_len);
+    case F_PREFIX: return match_prefix(s, n, nd, L.needle_len);
+    case F_EXACT: return bytes_equal(s, n, nd, L.needle_len);
+    case F_IN: return in_contains_string(L, P.blob, s, n);
+    case F_REGEXP: return regex_match(P.regexes[L.regex], P.blob, s, n);
+    }
+    return true;
+}
+
+// numeric value -> string (toUint8String .. toTimestampISO8601String, filter_prefix.go:365-408, filter_phrase.go:310-346)
+static __device__ int encoded_to_string(uint32_t vt, uint64_t raw, uint8_t* buf) {
+    switch (vt) {
+    case VT_UINT8: case VT_UINT16: case VT_UINT32: case VT_UINT64: return fmt_u64(buf, raw);
+    case VT_INT64: return fmt_i64(buf, unzigzag64(raw));
+    case VT_IPV4: return fmt_ipv4(buf, (uint32_t)raw);
+    case VT_ISO8601: return fmt_iso8601(buf, (int64_t)raw);
+    }
+    return -1;   // float64: shortest round-trip formatting is not implemented on the device (plan raises an error)
+}
+
+// ---- bloom probe, warp wide (bloomFilter.containsAll, lib/logstorage/bloomfilter.go:173-191) -----------------------------------
+// All 32 lanes call with identical arguments; lanes split the probe hashes; result is uniform.
+static __device__ bool bloom_contains_all_warp(const uint8_t* bloom_be, uint32_t nwords, const uint64_t* hashes, uint32_t nh) {
+    if (nwords == 0) return true;
+    uint64_t maxbits = (uint64_t)nwords * 64;
+    bool ok = true;
+    for (uint32_t i = lane_id(); i < nh; i += 32) {
+        uint64_t idx = hashes[i] % maxbits;
+        uint64_t w = ld_be64(bloom_be + (idx >> 6) * 8);   // words are stored big-endian (bloomfilter.go:49-55)
+        if (!((w >> (idx & 63)) & 1)) ok = false;
+    }
+    return __all_sync(0xffffffffu, ok);
+}
+
+// ---- bitmap helpers --------------------------------------------------------------------------------------------------
+// alive[b] = bitmap of block b is non-zero (bitmap.isZero, bitmap.go:74-81); one warp per block
+static __global__ void k_block_any(const uint64_t* __restrict__ reg, BatchView B, uint8_t* __restrict__ alive) {
+    uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (b >= B.nblocks) return;
+    uint64_t lo = B.blk_word_off[b], hi = B.blk_word_off[b + 1];
+    bool any = false;
+    for (uint64_t w = lo + lane_id(); w < hi; w += 32) any |= reg[w] != 0;
+    any = __any_sync(0xffffffffu, any);
+    if (lane_id() == 0) alive[b] = any;
+}
+static __global__ void k_andnot(uint64_t* __restrict__ a, const uint64_t* __restrict__ b, uint64_t n) {   // bitmap.andNot bitmap.go:99-111
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] &= ~b[i];
+}
+
+// ---- AND / OR bloom pre-pass (filterAnd.matchBloomFilters filter_and.go:76-111, filterOr.matchBloomFilters filter_or.go:80-115) ----
+// one warp per block; a failing block gets its bitmap words zeroed (bm.resetBits()).
+static __global__ void k_prepass(DevProgram P, BatchView B, uint32_t pp_begin, uint32_t pp_count, const int* __restrict__ slots /* per prepass entry */,
+                          int is_or, uint64_t* __restrict__ reg, const uint8_t* __restrict__ alive, unsigned long long* __restrict__ stats) {
+    uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (b >= B.nblocks || !alive[b]) return;
+    bool pass = is_or ? false : true;
+    unsigned long long bloom_bytes = 0;
+    for (uint32_t e = 0; e < pp_count; e++) {
+        const DevPrepass& pp = P.prepass[pp_begin + e];
+        int slot = slots[e];
+        const DevColumn* c = slot >= 0 ? &B.cols[(uint64_t)b * B.nfields + slot] : nullptr;
+        bool ok;
+        bool skip = false;   // OR: "continue" without a verdict
+        if (c && c->kind == COL_CONST) {
+            // matchStringByAllTokens(v, tokens)
+            const uint32_t* to = (const uint32_t*)(P.blob + pp.tok_offs_off);
+            const uint8_t* v = B.arena + c->meta_off;
+            ok = true;
+            for (uint32_t t = 0; t < pp.ntokens && ok; t++) ok = match_phrase(v, c->meta_len, P.blob + pp.tok_blob_off + to[t], to[t + 1] - to[t]);
+        } else if (!c || c->kind == COL_MISSING) {
+            ok = false; skip = true;
+        } else if (c->vt == VT_DICT) {
+            // matchDictValuesByAllTokens: dict values joined with ',' (filter_and.go:198-208); a token never contains ','
+            // so a phrase occurrence lies inside one value; value edges behave like the ',' separator (non-token char).
+            const uint32_t* dof = (const uint32_t*)(B.arena + c->meta_off);
+            const uint8_t* dv = B.arena + c->meta_off + 4 * (c->dict_len + 1);
+            const uint32_t* to = (const uint32_t*)(P.blob + pp.tok_offs_off);
+            ok = true;
+            for (uint32_t t = 0; t < pp.ntokens && ok; t++) {
+                bool found = false;
+                for (uint32_t d = 0; d < c->dict_len && !found; d++) found = match_phrase(dv + dof[d], dof[d + 1] - dof[d], P.blob + pp.tok_blob_off + to[t], to[t + 1] - to[t]);
+                ok = found;
+            }
+        } else {
+            bloom_bytes += 8ull * pp.nhashes;
+            ok = bloom_contains_all_warp(B.arena + c->bloom_off, c->bloom_words, P.u64s + pp.hashes_off, pp.nhashes);
+        }
+        if (is_or) { if (!skip && ok) { pass = true; break; } }
+        else if (!ok) { pass = false; break; }
+    }
+    if (is_or && pp_count == 0) pass = true;
+    if (lane_id() == 0 && bloom_bytes) atomicAdd(&stats[ST_BLOOM_BYTES], bloom_bytes);
+    if (!pass) for (uint64_t w = B.blk_word_off[b] + lane_id(); w < B.blk_word_off[b + 1]; w += 32) reg[w] = 0;
+}
+
+// ---- per (block, leaf) header dispatch: const / missing / dict / typed columns + leaf-level bloom probe ----------------------------
+// filterPhrase.applyToBlockSearch filter_phrase.go:61-111, filterPrefix :59-106, filterExact :186-235, filterIn :120-185,
+// filterRegexp :78-127 and the match*By* helpers they call.  One warp per block, all lanes run the same scalar logic.
+static __global__ void k_plan_leaf(DevProgram P, BatchView B, uint32_t leaf_idx, int slot, const uint8_t* __restrict__ alive,
+                            uint8_t* __restrict__ action, uint64_t* __restrict__ payload, unsigned long long* __restrict__ stats) {
+    uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (b >= B.nblocks) return;
+    const DevLeaf& L = P.leaves[leaf_idx];
+    uint8_t act = ACT_ALL; uint64_t pay = 0;
+    unsigned long long bloom_bytes = 0, values_bytes = 0; int err = 0;
+    if (!alive[b]) { if (lane_id() == 0) action[b] = ACT_NONE; return; }
+    if (L.kind == F_NOOP) { if (lane_id() == 0) action[b] = ACT_ALL; return; }
+    uint32_t rows = B.blk_rows[b];
+    const DevColumn* c = slot >= 0 ? &B.cols[(uint64_t)b * B.nfields + slot] : nullptr;
+    const uint8_t* nd = P.blob + L.needle_off; uint32_t nl = L.needle_len;
+    if (L.kind == F_IN && L.in_count == 0) act = ACT_NONE;   // fi.values.isEmpty()
+    else if (c && c->kind == COL_CONST) {
+        act = leaf_match_string(P, L, B.arena + c->meta_off, c->meta_len) ? ACT_ALL : ACT_NONE;
+    } else if (!c || c->kind == COL_MISSING) {
+        switch (L.kind) {
+        case F_PHRASE: case F_EXACT: act = nl == 0 ? ACT_ALL : ACT_NONE; break;
+        case F_PREFIX: act = ACT_NONE; break;
+        case F_IN: act = L.in_has_empty ? ACT_ALL : ACT_NONE; break;
+        case F_REGEXP: act = regex_match(P.regexes[L.regex], P.blob, nullptr, 0) ? ACT_ALL : ACT_NONE; break;
+        }
+    } else if (c->vt == VT_DICT) {
+        const uint32_t* dof = (const uint32_t*)(B.arena + c->meta_off);
+        const uint8_t* dv = B.arena + c->meta_off + 4 * (c->dict_len + 1);
+        uint32_t mask = 0;
+        for (uint32_t d = 0; d < c->dict_len; d++) if (leaf_match_string(P, L, dv + dof[d], dof[d + 1] - dof[d])) mask |= 1u << d;
+        if (mask == 0) act = ACT_NONE; else { act = ACT_DICT; pay = mask; }
+    } else {
+        uint32_t vt = c->vt;
+        const uint8_t* bloom = B.arena + c->bloom_off;
+        auto probe = [&](const uint64_t* h, uint32_t nh) -> bool {
+            if (nh == 0) return true;
+            bloom_bytes += 8ull * nh;
+            return bloom_contains_all_warp(bloom, c->bloom_words, h, nh);
+        };
+        const uint64_t* H = P.u64s + L.hashes_off;
+        if (vt == VT_STRING) {
+            bool ok = true;
+            if (L.kind == F_IN) {
+                // matchBloomFilterAnyTokenSet filter_in.go:202-218
+                ok = probe(H, L.nhashes);
+                if (ok && !(L.in_skip_sets || (uint64_t)L.in_nsets > 10ull * rows)) {
+                    bool any = false;
+                    const uint32_t* sets = P.u32s + L.in_sets_off;
+                    for (uint32_t s = 0; s < L.in_nsets && !any; s++) { bloom_bytes += 8ull * sets[2 * s + 1]; any = bloom_contains_all_warp(bloom, c->bloom_words, P.u64s + sets[2 * s], sets[2 * s + 1]); }
+                    ok = any;
+                }
+            } else ok = probe(H, L.nhashes);
+            if (!ok) act = ACT_NONE;
+            else if (c->data_const) act = leaf_match_string(P, L, B.arena + c->data_off, (uint32_t)c->data_len) ? ACT_ALL : ACT_NONE, values_bytes = 1;
+            else { act = L.str_strategy == STR_SCAN ? ACT_SCAN : L.str_strategy == STR_ALL ? ACT_ALL : ACT_ROW; values_bytes = 1; }
+        } else {
+            // numeric / ipv4 / iso8601 columns
+            uint32_t w = width_of_vt(vt);
+            bool fixed_ok = c->lens_type >= 4 && c->lens_const == w && c->data_len == (uint64_t)rows * w && !c->data_const;
+            const TypedNeedle& tn = L.typed[vt];
+            auto in_range = [&]() -> bool {
+                switch (vt) {
+                case VT_UINT8: case VT_UINT16: case VT_UINT32: case VT_UINT64: case VT_IPV4: return tn.val >= c->min_value && tn.val <= c->max_value;
+                case VT_INT64: case VT_ISO8601: return tn.sval >= (int64_t)c->min_value && tn.sval <= (int64_t)c->max_value;
+                case VT_FLOAT64: { double f = __longlong_as_double((long long)tn.val), mn = __longlong_as_double((long long)c->min_value), mx = __longlong_as_double((long long)c->max_value); return !(f < mn) && !(f > mx); }
+                }
+                return false;
+            };
+            auto exact_path = [&]() {   // match*ByExactValue -> matchBinaryValue (filter_exact.go:237-364)
+                if (!tn.ok || !in_range()) { act = ACT_NONE; return; }
+                if (!probe(H, L.nhashes)) { act = ACT_NONE; return; }
+                act = fixed_ok ? ACT_FIXED_EQ : ACT_ROW; pay = tn.val;
+            };
+            auto tostring_path = [&](bool use_bloom) {
+                if (use_bloom && !probe(H, L.nhashes)) { act = ACT_NONE; return; }
+                if (vt == VT_FLOAT64) { err = ERR_UNSUPPORTED_FLOAT_TOSTRING; act = ACT_NONE; return; }
+                act = ACT_ROW;
+            };
+            switch (L.kind) {
+            case F_EXACT: exact_path(); break;
+            case F_PHRASE:
+                if (vt == VT_FLOAT64) { if (!L.f64_phrase_gate) act = ACT_NONE; else if (L.f64_exact_form) exact_path(); else tostring_path(true); }
+                else if (vt == VT_IPV4 || vt == VT_ISO8601) { if (tn.ok) exact_path(); else tostring_path(true); }
+                else exact_path();
+                break;
+            case F_PREFIX:
+                if (nl == 0) act = ACT_ALL;
+                else if (vt == VT_UINT8 || vt == VT_UINT16 || vt == VT_UINT32 || vt == VT_UINT64) { if (!tn.ok || tn.val > c->max_value) act = ACT_NONE; else tostring_path(false); }
+                else if (vt == VT_INT64) { bool dash = nl == 1 && nd[0] == '-'; if (!dash && (!tn.ok || !in_range())) act = ACT_NONE; else tostring_path(false); }
+                else if (vt == VT_FLOAT64) { if (!L.f64_prefix_gate) act = ACT_NONE; else tostring_path(true); }
+                else tostring_path(true);
+                break;
+            case F_REGEXP: tostring_path(true); break;
+            case F_IN:
+                if (L.in_typed_cnt[vt] == 0) act = ACT_NONE;
+                else {
+                    bool ok = probe(H, L.nhashes);
+                    if (ok && !(L.in_skip_sets || (uint64_t)L.in_nsets > 10ull * rows)) {
+                        bool any = false;
+                        const uint32_t* sets = P.u32s + L.in_sets_off;
+                        for (uint32_t s = 0; s < L.in_nsets && !any; s++) { bloom_bytes += 8ull * sets[2 * s + 1]; any = bloom_contains_all_warp(bloom, c->bloom_words, P.u64s + sets[2 * s], sets[2 * s + 1]); }
+                        ok = any;
+                    }
+                    act = !ok ? ACT_NONE : fixed_ok ? ACT_FIXED_IN : ACT_ROW;
+                }
+                break;
+            }
+        }
+        if (act >= ACT_DICT || values_bytes) values_bytes = lens_stored_bytes(*c, rows) + c->data_len;   // getValuesForColumn was reached
+    }
+    if (c && c->kind == COL_VALUES && c->vt == VT_DICT && act == ACT_DICT) values_bytes = lens_stored_bytes(*c, rows) + c->data_len;
+    if (lane_id() == 0) {
+        action[b] = act; payload[b] = pay;
+        if (bloom_bytes) atomicAdd(&stats[ST_BLOOM_BYTES], bloom_bytes);
+        if (values_bytes) { atomicAdd(&stats[ST_VALUES_BYTES], values_bytes); atomicAdd(&stats[ST_COLUMNS_READ], 1ull); }
+        if (err) atomicMax(&stats[ST_ERROR], (unsigned long long)err);
+    }
+}
+
+// ---- lens decode -> per-bitmap-word row offsets (unmarshalUint64Items + the offsets implied by encoding.go:122-130) -----------------
+// row_off64[w] = byte offset (within the block's data) of row 64*(w - first word of the block).  One CTA per work item.
+static __global__ void k_lens_offsets(BatchView B, int slot, const uint32_t* __restrict__ work_blocks, const uint32_t* __restrict__ work_count,
+                               uint32_t* __restrict__ row_off64, uint8_t* __restrict__ ready, unsigned long long* __restrict__ stats) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry_s;
+    for (uint32_t j = blockIdx.x; j < work_count[0]; j += gridDim.x) {
+        uint32_t b = work_blocks[j];
+        if (ready[b]) continue;   // uniform per CTA
+        const DevColumn& c = B.cols[(uint64_t)b * B.nfields + slot];
+        uint32_t rows = B.blk_rows[b];
+        uint64_t w0 = B.blk_word_off[b]; uint32_t nw = (uint32_t)(B.blk_word_off[b + 1] - w0);
+        const uint8_t* lens = B.arena + c.lens_off;
+        if (threadIdx.x == 0) carry_s = 0;
+        __syncthreads();
+        for (uint32_t base = 0; base < nw; base += blockDim.x) {
+            uint32_t w = base + threadIdx.x;
+            uint32_t sum = 0;
+            if (w < nw) {
+                uint32_t r0 = w * 64, r1 = min(rows, r0 + 64);
+                if (c.lens_type == 0) {
+                    if (r1 - r0 == 64) {   // 64 u8 lens = four 16-byte vectors (r0 is a multiple of 64; lens_off is 16-byte aligned)
+                        const uint4* v = (const uint4*)(lens + r0);
+#pragma unroll
+                        for (int q = 0; q < 4; q++) { uint4 x = v[q]; sum += __vsadu4(x.x, 0) + __vsadu4(x.y, 0) + __vsadu4(x.z, 0) + __vsadu4(x.w, 0); }
+                    } else for (uint32_t r = r0; r < r1; r++) sum += lens[r];
+                } else if (c.lens_type < 4) for (uint32_t r = r0; r < r1; r++) sum += row_len(c, lens, r);
+                else sum = (r1 - r0) * c.lens_const;
+            }
+            // CTA exclusive scan of `sum`
+            uint32_t incl = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane_id() >= d) incl += t; }
+            if (lane_id() == 31) warp_sums[threadIdx.x >> 5] = incl;
+            __syncthreads();
+            uint32_t wid = threadIdx.x >> 5, wpre = 0;
+            for (uint32_t k = 0; k < wid; k++) wpre += warp_sums[k];
+            uint32_t excl = carry_s + wpre + incl - sum;
+            if (w < nw) row_off64[w0 + w] = excl;
+            __syncthreads();
+            if (threadIdx.x == blockDim.x - 1) carry_s = excl + sum;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            if ((uint64_t)carry_s != c.data_len) atomicMax(&stats[ST_ERROR], (unsigned long long)ERR_LENS_MISMATCH);   // encoding.go:124-126
+            ready[b] = 1;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- work list: blocks whose action selects `want`, with their tile counts (single CTA; nblocks is small) -------------------------------
+static __global__ void k_build_worklist(BatchView B, int slot, const uint8_t* __restrict__ action, uint8_t want, uint32_t tile_bytes,
+                                 uint32_t* __restrict__ work_blocks, uint32_t* __restrict__ tile_prefix, uint32_t* __restrict__ work_count,
+                                 unsigned long long* __restrict__ stats, int count_scan_bytes) {
+    __shared__ uint32_t s_cnt[1024], s_til[1024];
+    __shared__ uint32_t c_cnt, c_til;
+    if (threadIdx.x == 0) { c_cnt = 0; c_til = 0; }
+    __syncthreads();
+    unsigned long long scan_bytes = 0;
+    for (uint32_t base = 0; base < B.nblocks; base += blockDim.x) {
+        uint32_t b = base + threadIdx.x;
+        uint32_t flag = 0, tiles = 0;
+        if (b < B.nblocks && action[b] == want) {
+            flag = 1;
+            const DevColumn& c = B.cols[(uint64_t)b * B.nfields + slot];
+            tiles = (uint32_t)((c.data_len + tile_bytes - 1) / tile_bytes);
+            scan_bytes += c.data_len;
+        }
+        s_cnt[threadIdx.x] = flag; s_til[threadIdx.x] = tiles;
+        __syncthreads();
+        // Hillis-Steele inclusive scan over the CTA
+        for (uint32_t d = 1; d < blockDim.x; d <<= 1) {
+            uint32_t a = 0, t = 0;
+            if (threadIdx.x >= d) { a = s_cnt[threadIdx.x - d]; t = s_til[threadIdx.x - d]; }
+            __syncthreads();
+            s_cnt[threadIdx.x] += a; s_til[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (flag) { uint32_t pos = c_cnt + s_cnt[threadIdx.x] - 1; work_blocks[pos] = b; tile_prefix[pos] = c_til + s_til[threadIdx.x] - tiles; }
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) { c_cnt += s_cnt[threadIdx.x]; c_til += s_til[threadIdx.x]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { work_count[0] = c_cnt; work_count[1] = c_til; tile_prefix[c_cnt] = c_til; }
+    if (scan_bytes && count_scan_bytes) atomicAdd(&stats[ST_SCAN_BYTES], scan_bytes);
+}
+
+// ---- the hot kernel: row-agnostic substring scan over the decoded strings payload -------------------------------------------------------
+// Replaces bm.forEachSetBit(func(idx){ matchPhrase(values[idx], phrase) }) (filter_phrase.go:201-270, bitmap.go:128-153),
+// matchPrefix (filter_prefix.go:318-352) and the strings.Index(prefix) loop of regexutil (regex.go:162-212).
+// Every thread streams 16-byte vectors of the block's concatenated row bytes, compares the first min(4, L) needle bytes at all 16
+// byte positions (4-byte window compare), and only for candidates (rare) verifies the rest, maps the byte offset to its row through
+// row_off64 + the lens items, applies the boundary rules and sets the row's bit.  An occurrence in the reference's retry loop
+// ("pos++; continue") is any occurrence, so occurrences are independent and order-free.
+struct ScanParams {
+    uint32_t mode;            // SCAN_*
+    uint32_t needle_off, needle_len;
+    uint32_t n4, m4;          // first min(4,L) needle bytes, little-endian packed, and the mask
+    uint8_t starts_tok, ends_tok;
+    int32_t regex;
+};
+
+static __device__ __noinline__ void scan_verify(const DevProgram& P, const BatchView& B, const DevColumn& c, const ScanParams& sp, uint32_t b,
+                                         const uint32_t* __restrict__ row_off64, uint64_t pos, uint64_t* __restrict__ leaf_bm) {
+    const uint8_t* data = B.arena + c.data_off;
+    const uint8_t* nd = P.blob + sp.needle_off;
+    uint32_t L = sp.needle_len;
+    if (pos + L > c.data_len) return;
+    for (uint32_t k = 4; k < L; k++) if (data[pos + k] != nd[k]) return;
+    // byte offset -> row
+    uint32_t rows = B.blk_rows[b];
+    uint64_t w0 = B.blk_word_off[b];
+    uint32_t r; uint64_t off; uint32_t len;
+    const uint8_t* lens = B.arena + c.lens_off;
+    if (c.lens_type >= 4) {
+        len = c.lens_const;
+        if (len == 0) return;
+        r = (uint32_t)(pos / len); off = (uint64_t)r * len;
+        if (r >= rows) return;
+    } else {
+        uint32_t nw = (uint32_t)(B.blk_word_off[b + 1] - w0);
+        uint32_t lo = 0, hi = nw - 1;
+        while (lo < hi) { uint32_t mid = (lo + hi + 1) >> 1; if (row_off64[w0 + mid] <= pos) lo = mid; else hi = mid - 1; }
+        r = lo * 64; off = row_off64[w0 + lo];
+        for (;;) {
+            if (r >= rows) return;
+            len = row_len(c, lens, r);
+            if (pos < off + len) break;
+            off += len; r++;
+        }
+    }
+    uint64_t end = off + len;
+    if (pos + L > end) return;   // the occurrence straddles a row boundary
+    const uint8_t* s = data + off; uint32_t p = (uint32_t)(pos - off);
+    bool hit;
+    switch (sp.mode) {
+    case SCAN_PHRASE: hit = phrase_boundaries_ok(s, len, p, L, sp.starts_tok, sp.ends_tok); break;
+    case SCAN_PREFIX: hit = phrase_boundaries_ok(s, len, p, L, sp.starts_tok, false); break;
+    case SCAN_CONTAINS: hit = true; break;
+    case SCAN_RX_DOTPLUS: hit = p + L < len; break;
+    default: hit = dfa_run(P.regexes[sp.regex], P.blob, s + p + L, len - p - L); break;   // SCAN_RX_SUFFIX
+    }
+    if (hit) atomicOr((unsigned long long*)&leaf_bm[w0 + (r >> 6)], 1ull << (r & 63));
+}
+
+#define VL_SCAN_THREADS 256
+#define VL_SCAN_ITERS 4
+#define VL_TILE_BYTES (VL_SCAN_THREADS * 16 * VL_SCAN_ITERS)
+
+static __global__ void __launch_bounds__(VL_SCAN_THREADS) k_substr_scan(DevProgram P, BatchView B, int slot, ScanParams sp, const uint32_t* __restrict__ work_blocks,
+                                                                const uint32_t* __restrict__ tile_prefix, const uint32_t* __restrict__ work_count,
+                                                                const uint32_t* __restrict__ row_off64, uint64_t* __restrict__ leaf_bm) {
+    const uint32_t nwork = work_count[0], ntiles = work_count[1];
+    const uint32_t L = sp.needle_len;
+    for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        // tile -> (work item, tile index)
+        uint32_t lo = 0, hi = nwork - 1;
+        while (lo < hi) { uint32_t mid = (lo + hi + 1) >> 1; if (tile_prefix[mid] <= t) lo = mid; else hi = mid - 1; }
+        const uint32_t b = work_blocks[lo];
+        const DevColumn& c = B.cols[(uint64_t)b * B.nfields + slot];
+        const uint64_t n = c.data_len;
+        const uint8_t* data = B.arena + c.data_off;
+        const uint64_t t0 = (uint64_t)(t - tile_prefix[lo]) * VL_TILE_BYTES;
+        uint4 v[VL_SCAN_ITERS];
+        uint32_t halo[VL_SCAN_ITERS];
+#pragma unroll
+        for (int it = 0; it < VL_SCAN_ITERS; it++) {
+            uint64_t p = t0 + ((uint64_t)it * VL_SCAN_THREADS + threadIdx.x) * 16;
+            // payloads are padded with >= 32 readable bytes past data_len, so vector loads that start before n are safe
+            v[it] = p < n ? __ldg((const uint4*)(data + p)) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int it = 0; it < VL_SCAN_ITERS; it++) {
+            uint64_t p = t0 + ((uint64_t)it * VL_SCAN_THREADS + threadIdx.x) * 16;
+            uint32_t nx = __shfl_down_sync(0xffffffffu, v[it].x, 1);
+            if (lane_id() == 31) nx = (p + 16 < n) ? __ldg((const uint32_t*)(data + p + 16)) : 0;
+            halo[it] = nx;
+        }
+#pragma unroll
+        for (int it = 0; it < VL_SCAN_ITERS; it++) {
+            uint64_t p = t0 + ((uint64_t)it * VL_SCAN_THREADS + threadIdx.x) * 16;
+            if (p >= n) continue;
+            uint32_t w[5] = {v[it].x, v[it].y, v[it].z, v[it].w, halo[it]};
+            uint32_t cand = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    uint32_t win = j == 0 ? w[i] : __funnelshift_r(w[i], w[i + 1], 8 * j);
+                    if ((win & sp.m4) == sp.n4) cand |= 1u << (i * 4 + j);
+                }
+            }
+            while (cand) {
+                int k = __ffs(cand) - 1; cand &= cand - 1;
+                scan_verify(P, B, c, sp, b, row_off64, p + k, leaf_bm);
+            }
+        }
+        (void)L;
+    }
+}
+
+// ---- dict LUT / fixed-width equality / typed in(): one thread per bitmap word ---------------------------------------------------------------
+// matchEncodedValuesDict filter_phrase.go:272-289, matchBinaryValue filter_exact.go:356-364, matchAnyValue filter_in.go:187-200
+static __global__ void k_word_match(DevProgram P, BatchView B, uint32_t leaf_idx, int slot, const uint8_t* __restrict__ action, const uint64_t* __restrict__ payload,
+                             uint64_t* __restrict__ leaf_bm, unsigned long long* __restrict__ stats) {
+    uint64_t gw = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gw >= B.nwords) return;
+    uint32_t b = B.word_block[gw];
+    uint8_t act = action[b];
+    if (act != ACT_DICT && act != ACT_FIXED_EQ && act != ACT_FIXED_IN) return;
+    const DevColumn& c = B.cols[(uint64_t)b * B.nfields + slot];
+    const DevLeaf& L = P.leaves[leaf_idx];
+    uint32_t rows = B.blk_rows[b];
+    uint32_t r0 = (uint32_t)(gw - B.blk_word_off[b]) * 64, r1 = min(rows, r0 + 64);
+    const uint8_t* data = B.arena + c.data_off;
+    uint64_t bits = 0, pay = payload[b];
+    if (act == ACT_DICT) {
+        // dict ids: 1 byte per row; lens must be const 1 (or a per-row u8 block of ones for single-row blocks)
+        bool bad = false;
+        if (r1 - r0 == 64 && ((c.data_off + r0) & 15) == 0) {
+            const uint4* v = (const uint4*)(data + r0);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                uint4 x = __ldg(v + q); uint32_t ww[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) { uint32_t id = (ww[i] >> (8 * j)) & 0xFF; bad |= id >= c.dict_len; bits |= (uint64_t)((pay >> (id & 7)) & 1) << (q * 16 + i * 4 + j); }
+            }
+        } else for (uint32_t r = r0; r < r1; r++) { uint32_t id = data[r]; bad |= id >= c.dict_len; bits |= (uint64_t)((pay >> (id & 7)) & 1) << (r - r0); }
+        if (bad) atomicMax(&stats[ST_ERROR], (unsigned long long)ERR_DICT_INDEX);   // "too big index for dict value" filter_phrase.go:284-286
+    } else {
+        uint32_t w = width_of_vt(c.vt);
+        for (uint32_t r = r0; r < r1; r++) {
+            uint64_t v = load_fixed_be(data + (uint64_t)r * w, w);
+            bool hit = act == ACT_FIXED_EQ ? v == pay : in_contains_typed(L, P.u64s, c.vt, v);
+            bits |= (uint64_t)hit << (r - r0);
+        }
+    }
+    leaf_bm[gw] = bits;
+}
+
+// ---- generic per-row matcher: one warp per bitmap word, lanes take rows l and l+32 ------------------------------------------------------------
+// exact / in() / regexp-without-literal-prefix on string columns; numeric columns that must be formatted to text first.
+static __global__ void k_row_match(DevProgram P, BatchView B, uint32_t leaf_idx, int slot, const uint8_t* __restrict__ action, const uint64_t* __restrict__ payload,
+                            const uint32_t* __restrict__ row_off64, uint64_t* __restrict__ leaf_bm) {
+    uint64_t gw = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (gw >= B.nwords) return;
+    uint32_t b = B.word_block[gw];
+    if (action[b] != ACT_ROW) return;
+    const DevColumn& c = B.cols[(uint64_t)b * B.nfields + slot];
+    const DevLeaf& L = P.leaves[leaf_idx];
+    uint32_t rows = B.blk_rows[b];
+    uint32_t r0 = (uint32_t)(gw - B.blk_word_off[b]) * 64;
+    const uint8_t* data = B.arena + c.data_off;
+    const uint8_t* lens = B.arena + c.lens_off;
+    uint32_t la = 0, lb = 0;
+    uint32_t ra = r0 + lane_id(), rb = r0 + 32 + lane_id();
+    if (ra < rows) la = row_len(c, lens, ra);
+    if (rb < rows) lb = row_len(c, lens, rb);
+    // exclusive offsets: rows r0..r0+31 then r0+32..r0+63
+    uint32_t ia = la, ib = lb;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, ia, d), u = __shfl_up_sync(0xffffffffu, ib, d); if (lane_id() >= d) { ia += t; ib += u; } }
+    uint32_t tot_a = __shfl_sync(0xffffffffu, ia, 31);
+    uint64_t base = c.lens_type >= 4 ? (uint64_t)r0 * c.lens_const : row_off64[gw];
+    uint64_t oa = base + ia - la, ob = base + tot_a + ib - lb;
+    if (c.data_const) { oa = ob = 0; la = lb = (uint32_t)c.data_len; }   // every row = data (encoding.go:113-120)
+    bool ha = false, hb = false;
+    uint32_t vt = c.vt;
+    auto eval = [&](uint64_t off, uint32_t len) -> bool {
+        if (off + len > c.data_len) return false;   // malformed; k_lens_offsets reports the error
+        const uint8_t* s = data + off;
+        if (vt == VT_STRING) return leaf_match_string(P, L, s, len);
+        uint32_t w = width_of_vt(vt);
+        if (len != w) return false;
+        uint64_t raw = load_fixed_be(s, w);
+        if (L.kind == F_IN) return in_contains_typed(L, P.u64s, vt, raw);
+        if (L.kind == F_EXACT) return raw == payload[b];
+        if (L.kind == F_PHRASE && L.typed[vt].ok && !(vt == VT_FLOAT64 && !L.f64_exact_form)) return raw == payload[b];
+        uint8_t buf[32];
+        int n = encoded_to_string(vt, raw, buf);
+        if (n < 0) return false;
+        return leaf_match_string(P, L, buf, (uint32_t)n);
+    };
+    if (ra < rows) ha = eval(oa, la);
+    if (rb < rows) hb = eval(ob, lb);
+    uint32_t lo = __ballot_sync(0xffffffffu, ha), hi = __ballot_sync(0xffffffffu, hb);
+    if (lane_id() == 0) leaf_bm[gw] = ((uint64_t)hi << 32) | lo;
+}
+
+// ---- fold a leaf result into the running bitmap -------------------------------------------------------------------------------------------------
+static __global__ void k_apply_leaf(BatchView B, const uint8_t* __restrict__ action, const uint64_t* __restrict__ leaf_bm, uint64_t* __restrict__ reg) {
+    uint64_t gw = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gw >= B.nwords) return;
+    uint8_t act = action[B.word_block[gw]];
+    if (act == ACT_ALL) return;
+    reg[gw] = act == ACT_NONE ? 0 : (reg[gw] & leaf_bm[gw]);
+}
+
+// ---- finalize: per-block popcount (bitmap.onesCount bitmap.go:185-191 == blockResult.rowsLen) + totals -------------------------------------------
+static __global__ void k_finalize(BatchView B, const uint64_t* __restrict__ reg, uint32_t* __restrict__ counts, unsigned long long* __restrict__ stats,
+                           unsigned long long* __restrict__ totals4) {
+    uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (b >= B.nblocks) return;
+    uint64_t lo = B.blk_word_off[b], hi = B.blk_word_off[b + 1];
+    uint32_t n = 0;
+    for (uint64_t w = lo + lane_id(); w < hi; w += 32) n += __popcll(reg[w]);
+#pragma unroll
+    for (int d = 16; d; d >>= 1) n += __shfl_xor_sync(0xffffffffu, n, d);
+    if (lane_id() == 0) {
+        counts[b] = n;
+        atomicAdd(&totals4[0], (unsigned long long)B.blk_rows[b]);
+        if (n) {
+            atomicAdd(&stats[ST_ROWS_MATCHED], (unsigned long long)n); atomicAdd(&stats[ST_BLOCKS_MATCHED], 1ull);
+            atomicAdd(&stats[ST_BITMAP_BYTES], 8ull * (hi - lo));
+            atomicAdd(&totals4[1], (unsigned long long)n); atomicAdd(&totals4[2], 1ull);
+        }
+    }
+}
+
+// ---- hit-row offsets (bitmap.forEachSetBitReadonly bitmap.go:156-183) ----------------------------------------------------------------------------------
+static __global__ void k_scan_counts(const uint32_t* __restrict__ counts, uint32_t n, uint64_t* __restrict__ offs) {   // single CTA exclusive scan
+    __shared__ uint64_t s[1024];
+    __shared__ uint64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += blockDim.x) {
+        uint32_t i = base + threadIdx.x;
+        uint64_t v = i < n ? counts[i] : 0;
+        s[threadIdx.x] = v;
+        __syncthreads();
+        for (uint32_t d = 1; d < blockDim.x; d <<= 1) { uint64_t a = threadIdx.x >= d ? s[threadIdx.x - d] : 0; __syncthreads(); s[threadIdx.x] += a; __syncthreads(); }
+        if (i < n) offs[i] = carry + s[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry += s[threadIdx.x];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) offs[n] = carry;
+}
+static __global__ void k_hits_compact(BatchView B, const uint64_t* __restrict__ reg, const uint64_t* __restrict__ offs, uint32_t* __restrict__ hits, uint64_t cap) {
+    uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (b >= B.nblocks) return;
+    uint64_t lo = B.blk_word_off[b], hi = B.blk_word_off[b + 1];
+    uint64_t out = offs[b];
+    for (uint64_t w0 = lo; w0 < hi; w0 += 32) {
+        uint64_t w = w0 + lane_id();
+        uint64_t bits = w < hi ? reg[w] : 0;
+        uint32_t n = __popcll(bits), incl = n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane_id() >= d) incl += t; }
+        uint64_t pos = out + incl - n;
+        uint32_t rbase = (uint32_t)(w - lo) * 64;
+        while (bits) { int k = __ffsll((long long)bits) - 1; bits &= bits - 1; if (pos < cap) hits[pos] = rbase + k; pos++; }
+        out += __shfl_sync(0xffffffffu, incl, 31);
+    }
+}
+
+}  // namespace vl

@@ -1,0 +1,90 @@
+// POD layouts shared by the host program compiler (vl_program.cpp) and the CUDA engine (vl_engine.cu).
+#pragma once
+#include <stdint.h>
+
+namespace vl {
+
+enum { VT_STRING = 1, VT_DICT = 2, VT_UINT8 = 3, VT_UINT16 = 4, VT_UINT32 = 5, VT_UINT64 = 6, VT_FLOAT64 = 7, VT_IPV4 = 8, VT_ISO8601 = 9, VT_INT64 = 10, VT_MAX = 11 };
+enum { F_NOOP = 0, F_PHRASE, F_PREFIX, F_EXACT, F_IN, F_REGEXP, F_AND, F_OR, F_NOT };
+enum { COL_MISSING = 0, COL_CONST = 1, COL_VALUES = 2 };
+
+// One (block, field) cell of a resident batch: the columnHeader fields the scan needs + arena offsets of the payloads
+// (lib/logstorage/block_header.go:584-615).  Offsets are relative to the batch arena base.
+struct DevColumn {
+    uint8_t kind;          // COL_*
+    uint8_t vt;            // VT_*
+    uint8_t lens_type;     // uintBlockType 0..7 (lib/logstorage/encoding.go:177-187)
+    uint8_t dict_len;
+    uint8_t data_const;    // decode rule "every row = data" (encoding.go:113-120)
+    uint8_t pad[3];
+    uint32_t lens_const;   // the single item of a const lens block
+    uint32_t bloom_words;
+    uint64_t min_value, max_value;
+    uint64_t lens_off;     // lens items (after the type byte)
+    uint64_t data_off, data_len;
+    uint64_t bloom_off;
+    uint64_t meta_off;     // CONST: value bytes.  DICT: u32 offsets[dict_len+1] followed by the concatenated values
+    uint32_t meta_len;     // CONST: value length. DICT: total bytes of the concatenated values
+    uint32_t pad2;
+};
+
+struct TypedNeedle {       // result of parsing a needle for one valueType (filter_exact.go:237-354, in_values.go:141-315)
+    uint64_t val;          // value in the column's comparison domain: uint / zig-zag int64 / float64 bits / ipv4 / iso8601 ns
+    int64_t sval;          // signed view for the min/max range check of int64 / iso8601; float64: unused
+    uint8_t ok;
+    uint8_t pad[7];
+};
+
+struct DevRegex {          // device image of CompiledRegex (vl_regex.h)
+    uint32_t prefix_off, prefix_len;
+    uint32_t sub_off, sub_len;         // substrDotStar / substrDotPlus literal
+    uint8_t only_prefix, dot_star, dot_plus, sub_kind;   // sub_kind: 0 none, 1 substrDotStar, 2 substrDotPlus
+    uint32_t nclasses, nstates;
+    uint32_t bounds_off;               // int32[nclasses] in blob (4-byte aligned)
+    uint32_t ascii_off;                // uint8[128]
+    uint32_t trans_off;                // uint16[nstates*nclasses] (2-byte aligned)
+    uint32_t accept_off;               // uint8[nstates]
+};
+
+struct DevLeaf {
+    uint8_t kind;                      // F_PHRASE .. F_REGEXP, F_NOOP
+    uint8_t starts_tok, ends_tok;      // needle boundary flags (filter_phrase.go:229-239)
+    uint8_t f64_phrase_gate;           // phrase on float64: tryParseFloat64Exact ok || phrase in {".","+","-"} (filter_phrase.go:165-168)
+    uint8_t f64_exact_form;            // phrase contains '.' strictly inside (filter_phrase.go:169-173)
+    uint8_t f64_prefix_gate;           // prefix on float64 (filter_prefix.go:161-165)
+    uint8_t in_has_empty;              // "" is one of the in() values
+    uint8_t in_skip_sets;              // number of token sets > maxTokenSetsToInit (filter_in.go:206)
+    int32_t field;                     // index into the program's field table
+    uint32_t needle_off, needle_len;   // blob
+    uint32_t hashes_off, nhashes;      // u64 table: bloom probe hashes of the leaf's tokens (6 per token)
+    TypedNeedle typed[VT_MAX];         // phrase/exact/prefix needle parsed per valueType
+    // in(): string values + per-type sets
+    uint32_t in_count;                 // number of values
+    uint32_t in_offs_off;              // blob: u32 offsets[in_count+1] (4-byte aligned), relative to in_blob_off
+    uint32_t in_blob_off;
+    uint32_t in_sets_off, in_nsets;    // u32 table: per token set {hashes_off, nhashes}
+    uint32_t in_typed_off[VT_MAX];     // u64 table offset of the sorted typed set
+    uint32_t in_typed_cnt[VT_MAX];
+    int32_t regex;                     // index into the regex table or -1
+    // strategy for plain string columns, decided once per leaf on the host:
+    uint8_t str_strategy;              // STR_ROW: per-row matcher, STR_SCAN: row-agnostic substring scan, STR_ALL: every row matches
+    uint8_t scan_mode;                 // SCAN_* verifier of the substring scan
+    uint8_t pad[2];
+    uint32_t scan_needle_off, scan_needle_len;   // blob: the literal the scan searches for
+};
+
+struct DevPrepass {                    // one fieldTokens entry of an AND / OR node (filter_and.go:21-25)
+    int32_t field;
+    uint32_t ntokens;
+    uint32_t tok_offs_off;             // blob: u32 offsets[ntokens+1] (4-byte aligned) relative to tok_blob_off
+    uint32_t tok_blob_off;
+    uint32_t hashes_off, nhashes;      // u64 table
+};
+
+enum { STR_ROW = 0, STR_SCAN = 1, STR_ALL = 2 };
+// per (block, leaf) decision of the header dispatch
+enum { ACT_NONE = 0, ACT_ALL = 1, ACT_DICT = 2, ACT_SCAN = 3, ACT_FIXED_EQ = 4, ACT_FIXED_IN = 5, ACT_ROW = 6 };
+// scan verifier modes of the row-agnostic substring kernel
+enum { SCAN_PHRASE = 0, SCAN_PREFIX = 1, SCAN_CONTAINS = 2, SCAN_RX_DOTPLUS = 3, SCAN_RX_SUFFIX = 4 };
+
+}  // namespace vl

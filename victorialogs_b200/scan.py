@@ -1,0 +1,433 @@
+"""ctypes host-side mirror of lib/logstorage's filter / blockSearch interface on top of libvlscan.so (include/vlscan.h).
+
+The reference's host language is Go and there is no Go toolchain in this image, so the host side above the C ABI that a
+Go maintainer would write (INTEGRATION.md shows the cgo stub) is mirrored here in Python with the same names and
+argument meaning as the Go structs:
+
+    filterPhrase{fieldName, phrase}      -> Filter.phrase(field, phrase)        lib/logstorage/filter_phrase.go:25-32
+    filterPrefix{fieldName, prefix}      -> Filter.prefix(field, prefix)        filter_prefix.go:20-27
+    filterExact{fieldName, value}        -> Filter.exact(field, value)          filter_exact.go:17-24
+    filterIn{fieldName, values}          -> Filter.in_(field, values)           filter_in.go:14-18
+    filterRegexp{fieldName, re}          -> Filter.regexp(field, expr)          filter_regexp.go:17-24
+    filterAnd / filterOr / filterNot     -> Filter.and_ / or_ / not_            filter_and.go, filter_or.go, filter_not.go
+    blockSearch.search(bsw, bm)          -> Ctx.scan_batch(program, blocks)     block_search.go:207-226
+
+There is no CPU fallback: loading fails loudly when libvlscan.so is missing and every scan fails without a CUDA device.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+F_NOOP, F_PHRASE, F_PREFIX, F_EXACT, F_IN, F_REGEXP, F_AND, F_OR, F_NOT = range(9)
+VT_STRING, VT_DICT, VT_UINT8, VT_UINT16, VT_UINT32, VT_UINT64, VT_FLOAT64, VT_IPV4, VT_ISO8601, VT_INT64 = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
+COL_CONST, COL_VALUES = 1, 2
+STAGE_ONDISK, STAGE_DECODED = 0, 1
+
+
+class VlscanError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("vlscan error %d: %s" % (code, msg))
+        self.code = code
+
+
+class CColumn(C.Structure):
+    _fields_ = [("field", C.c_uint32), ("kind", C.c_uint8), ("value_type", C.c_uint8), ("stage", C.c_uint8), ("dict_len", C.c_uint8),
+                ("min_value", C.c_uint64), ("max_value", C.c_uint64),
+                ("const_value", C.c_void_p), ("const_len", C.c_uint64),
+                ("dict_blob", C.c_void_p), ("dict_offsets", C.c_void_p),
+                ("values", C.c_void_p), ("values_len", C.c_uint64),
+                ("lens_items", C.c_void_p), ("lens_items_len", C.c_uint64),
+                ("data", C.c_void_p), ("data_len", C.c_uint64),
+                ("bloom", C.c_void_p), ("bloom_len", C.c_uint64)]
+
+
+class CBlock(C.Structure):
+    _fields_ = [("rows", C.c_uint64), ("ncols", C.c_uint32), ("reserved", C.c_uint32), ("cols", C.POINTER(CColumn))]
+
+
+class CStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("blocks", "rows", "rows_matched", "blocks_matched", "values_bytes", "bloom_probe_bytes", "bitmap_bytes",
+                                          "columns_read", "gpu_launches", "h2d_bytes", "d2h_bytes")] + \
+               [("gpu_ms", C.c_double), ("scan_kernel_ms", C.c_double), ("scan_kernel_bytes", C.c_uint64)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class GenConfig(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("total_rows", C.c_uint64), ("rows_per_block", C.c_uint32), ("hot_block_permille", C.c_uint32),
+                ("hit_row_permille", C.c_uint32), ("columns_mask", C.c_uint32)]
+
+
+EXPORTS = ["vlscan_device_count", "vlscan_ctx_create", "vlscan_ctx_free", "vlscan_last_error", "vlscan_ctx_stream", "vlscan_ctx_sync",
+           "vlscan_program_create", "vlscan_program_free", "vlscan_program_nfields", "vlscan_program_field", "vlscan_program_leaf_tokens",
+           "vlscan_batch_upload", "vlscan_batch_free", "vlscan_batch_nblocks", "vlscan_batch_rows", "vlscan_batch_words", "vlscan_batch_device_bytes",
+           "vlscan_batch_generate", "vlscan_batch_download", "vlscan_host_blocks_get", "vlscan_host_blocks_field", "vlscan_host_blocks_bytes",
+           "vlscan_host_blocks_free", "vlscan_scan_resident", "vlscan_fetch_results", "vlscan_fetch_hits", "vlscan_result_device_ptrs", "vlscan_scan_batch"]
+
+
+def lib_path():
+    return os.path.join(_HERE, "libvlscan.so")
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise ImportError("libvlscan.so is missing (%s): build it with victorialogs_b200/build.sh; there is no fallback path" % path)
+        L = C.CDLL(path)
+        L.vlscan_ctx_create.restype = C.c_void_p
+        L.vlscan_last_error.restype = C.c_char_p
+        L.vlscan_last_error.argtypes = [C.c_void_p]
+        L.vlscan_ctx_stream.restype = C.c_void_p
+        L.vlscan_ctx_stream.argtypes = [C.c_void_p]
+        L.vlscan_program_field.restype = C.c_void_p
+        L.vlscan_host_blocks_field.restype = C.c_void_p
+        L.vlscan_host_blocks_get.restype = C.POINTER(CBlock)
+        L.vlscan_program_leaf_tokens.restype = C.c_int64
+        for n in ("vlscan_batch_nblocks", "vlscan_batch_rows", "vlscan_batch_words", "vlscan_batch_device_bytes", "vlscan_host_blocks_bytes"):
+            getattr(L, n).restype = C.c_uint64
+            getattr(L, n).argtypes = [C.c_void_p]
+        for n in ("vlscan_ctx_free", "vlscan_program_free", "vlscan_batch_free", "vlscan_host_blocks_free"):
+            getattr(L, n).argtypes = [C.c_void_p]
+            getattr(L, n).restype = None
+        _LIB = L
+    return _LIB
+
+
+def device_count():
+    return lib().vlscan_device_count()
+
+
+def _b(s):
+    return s.encode("utf-8", "surrogateescape") if isinstance(s, str) else bytes(s)
+
+
+def _varuint(n):
+    out = bytearray()
+    while n >= 0x80:
+        out.append((n & 0x7F) | 0x80)
+        n >>= 7
+    out.append(n)
+    return bytes(out)
+
+
+def _bytes(s):
+    s = _b(s)
+    return _varuint(len(s)) + s
+
+
+class Filter:
+    """A node of the filter tree; `blob` is its serialisation for vlscan_program_create (include/vlscan.h)."""
+
+    def __init__(self, blob, desc):
+        self.blob = blob
+        self.desc = desc
+
+    def __repr__(self):
+        return self.desc
+
+    @staticmethod
+    def noop():
+        return Filter(bytes([F_NOOP]), "*")
+
+    @staticmethod
+    def phrase(field, phrase):
+        return Filter(bytes([F_PHRASE]) + _bytes(field) + _bytes(phrase), "%r:%r" % (field, phrase))
+
+    @staticmethod
+    def prefix(field, prefix):
+        return Filter(bytes([F_PREFIX]) + _bytes(field) + _bytes(prefix), "%r:%r*" % (field, prefix))
+
+    @staticmethod
+    def exact(field, value):
+        return Filter(bytes([F_EXACT]) + _bytes(field) + _bytes(value), "%r:=%r" % (field, value))
+
+    @staticmethod
+    def in_(field, values):
+        values = list(values)
+        return Filter(bytes([F_IN]) + _bytes(field) + _varuint(len(values)) + b"".join(_bytes(v) for v in values), "%r:in(%r)" % (field, values))
+
+    @staticmethod
+    def regexp(field, expr):
+        return Filter(bytes([F_REGEXP]) + _bytes(field) + _bytes(expr), "%r:~%r" % (field, expr))
+
+    @staticmethod
+    def and_(filters):
+        return Filter(bytes([F_AND]) + _varuint(len(filters)) + b"".join(f.blob for f in filters), "(" + " AND ".join(f.desc for f in filters) + ")")
+
+    @staticmethod
+    def or_(filters):
+        return Filter(bytes([F_OR]) + _varuint(len(filters)) + b"".join(f.blob for f in filters), "(" + " OR ".join(f.desc for f in filters) + ")")
+
+    @staticmethod
+    def not_(f):
+        return Filter(bytes([F_NOT]) + f.blob, "!" + f.desc)
+
+
+class Program:
+    """Compiled filter tree (searchOptions.filter)."""
+
+    def __init__(self, flt):
+        self.h = C.c_void_p()
+        rc = lib().vlscan_program_create(flt.blob, C.c_size_t(len(flt.blob)), C.byref(self.h))
+        if rc:
+            raise VlscanError(rc, lib().vlscan_last_error(None).decode("utf-8", "replace"))
+        self.filter = flt
+
+    def fields(self):
+        out = []
+        for i in range(lib().vlscan_program_nfields(self.h)):
+            ln = C.c_size_t()
+            p = lib().vlscan_program_field(self.h, C.c_uint32(i), C.byref(ln))
+            out.append(C.string_at(p, ln.value))
+        return out
+
+    def leaf_tokens(self, leaf):
+        buf = C.create_string_buffer(1 << 16)
+        n = lib().vlscan_program_leaf_tokens(self.h, C.c_uint32(leaf), buf, C.c_size_t(1 << 16))
+        if n < 0:
+            raise IndexError(leaf)
+        return buf.raw[:n].split(b"\n") if n else []
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().vlscan_program_free(self.h)
+        except Exception:
+            pass
+
+
+class HostBlocks:
+    """A set of vlscan_block descriptors over host memory (what the Go shim would assemble per blockSearchWorkBatch)."""
+
+    def __init__(self, field_names, blocks):
+        """blocks: list of dict(rows=int, columns=[dict(field=name, kind='const'|'values', ...)])
+
+        values columns: value_type, min_value, max_value, dict (list of bytes), bloom (bytes) and either
+        values_block (bytes, on-disk stage) or lens_items + data (decoded stage)."""
+        self.field_names = [_b(f) for f in field_names]
+        fidx = {f: i for i, f in enumerate(self.field_names)}
+        self._keep = []
+        ncols = sum(len(b["columns"]) for b in blocks)
+        self.cols = (CColumn * max(ncols, 1))()
+        self.blocks = (CBlock * max(len(blocks), 1))()
+        self.nblocks = len(blocks)
+        k = 0
+
+        def buf(data):
+            data = bytes(data)
+            a = C.create_string_buffer(data, len(data)) if data else C.create_string_buffer(1)
+            self._keep.append(a)
+            return C.cast(a, C.c_void_p), len(data)
+
+        for bi, blk in enumerate(blocks):
+            first = k
+            for col in blk["columns"]:
+                c = self.cols[k]
+                c.field = fidx[_b(col["field"])]
+                if col["kind"] == "const":
+                    c.kind = COL_CONST
+                    c.const_value, c.const_len = buf(col["value"])
+                else:
+                    c.kind = COL_VALUES
+                    c.value_type = col["value_type"]
+                    c.min_value, c.max_value = col.get("min_value", 0), col.get("max_value", 0)
+                    d = col.get("dict") or []
+                    c.dict_len = len(d)
+                    if d:
+                        offs = np.zeros(len(d) + 1, dtype=np.uint32)
+                        offs[1:] = np.cumsum([len(x) for x in d])
+                        self._keep.append(offs)
+                        c.dict_offsets = offs.ctypes.data
+                        c.dict_blob, _ = buf(b"".join(d))
+                    if "values_block" in col:
+                        c.stage = STAGE_ONDISK
+                        c.values, c.values_len = buf(col["values_block"])
+                    else:
+                        c.stage = STAGE_DECODED
+                        c.lens_items, c.lens_items_len = buf(col["lens_items"])
+                        c.data, c.data_len = buf(col["data"])
+                    c.bloom, c.bloom_len = buf(col.get("bloom", b""))
+                k += 1
+            self.blocks[bi].rows = blk["rows"]
+            self.blocks[bi].ncols = k - first
+            self.blocks[bi].cols = C.cast(C.byref(self.cols, first * C.sizeof(CColumn)), C.POINTER(CColumn))
+        self.rows = [b["rows"] for b in blocks]
+
+    def name_arrays(self):
+        names = (C.c_char_p * max(len(self.field_names), 1))(*self.field_names)
+        lens = (C.c_size_t * max(len(self.field_names), 1))(*[len(f) for f in self.field_names])
+        return names, lens
+
+
+class DownloadedBlocks:
+    """Host copy (pinned memory owned by the library) of a device-resident batch: vlscan_batch_download."""
+
+    def __init__(self, ctx, batch):
+        self.h = C.c_void_p()
+        ctx._check(lib().vlscan_batch_download(ctx.h, batch.h, C.byref(self.h)))
+        nb, nf = C.c_uint64(), C.c_uint32()
+        self.blocks = lib().vlscan_host_blocks_get(self.h, C.byref(nb), C.byref(nf))
+        self.nblocks = nb.value
+        self.field_names = []
+        for i in range(nf.value):
+            ln = C.c_size_t()
+            p = lib().vlscan_host_blocks_field(self.h, C.c_uint32(i), C.byref(ln))
+            self.field_names.append(C.string_at(p, ln.value))
+        self.bytes = lib().vlscan_host_blocks_bytes(self.h)
+        self.rows = [self.blocks[i].rows for i in range(self.nblocks)]
+
+    def name_arrays(self):
+        names = (C.c_char_p * max(len(self.field_names), 1))(*self.field_names)
+        lens = (C.c_size_t * max(len(self.field_names), 1))(*[len(f) for f in self.field_names])
+        return names, lens
+
+    def column(self, block, field):
+        """-> dict view of one column (bytes copied out) for tests"""
+        blk = self.blocks[block]
+        fi = self.field_names.index(_b(field))
+        for k in range(blk.ncols):
+            c = blk.cols[k]
+            if c.field != fi:
+                continue
+            if c.kind == COL_CONST:
+                return dict(kind="const", value=C.string_at(c.const_value, c.const_len))
+            d = []
+            if c.dict_len:
+                offs = np.ctypeslib.as_array(C.cast(c.dict_offsets, C.POINTER(C.c_uint32)), (c.dict_len + 1,))
+                blob = C.string_at(c.dict_blob, int(offs[-1]))
+                d = [blob[int(offs[i]):int(offs[i + 1])] for i in range(c.dict_len)]
+            return dict(kind="values", value_type=c.value_type, min_value=c.min_value, max_value=c.max_value, dict=d,
+                        lens_items=C.string_at(c.lens_items, c.lens_items_len), data=C.string_at(c.data, c.data_len),
+                        bloom=C.string_at(c.bloom, c.bloom_len))
+        return None
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().vlscan_host_blocks_free(self.h)
+        except Exception:
+            pass
+
+
+class Batch:
+    def __init__(self, h, ctx):
+        self.h = h
+        self.ctx = ctx
+        L = lib()
+        self.nblocks = L.vlscan_batch_nblocks(h)
+        self.rows = L.vlscan_batch_rows(h)
+        self.words = L.vlscan_batch_words(h)
+        self.device_bytes = L.vlscan_batch_device_bytes(h)
+
+    def free(self):
+        if self.h:
+            lib().vlscan_batch_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Ctx:
+    """Per search-worker context (device + stream); mirrors the per-goroutine blockSearch of storage_search.go:1041-1043."""
+
+    def __init__(self, device=0):
+        h = lib().vlscan_ctx_create(C.c_int(device))
+        if not h:
+            raise VlscanError(100, lib().vlscan_last_error(None).decode("utf-8", "replace"))
+        self.h = C.c_void_p(h)
+
+    def _check(self, rc):
+        if rc:
+            raise VlscanError(rc, lib().vlscan_last_error(self.h).decode("utf-8", "replace"))
+
+    @property
+    def stream(self):
+        return lib().vlscan_ctx_stream(self.h)
+
+    def sync(self):
+        self._check(lib().vlscan_ctx_sync(self.h))
+
+    def upload(self, host_blocks, stats=None):
+        names, lens = host_blocks.name_arrays()
+        out = C.c_void_p()
+        self._check(lib().vlscan_batch_upload(self.h, names, lens, C.c_uint32(len(host_blocks.field_names)), host_blocks.blocks,
+                                              C.c_uint64(host_blocks.nblocks), C.byref(out), C.byref(stats) if stats is not None else None))
+        return Batch(out, self)
+
+    def generate(self, cfg, block_lo, block_hi):
+        out = C.c_void_p()
+        self._check(lib().vlscan_batch_generate(self.h, C.byref(cfg), C.c_uint64(block_lo), C.c_uint64(block_hi), C.byref(out)))
+        return Batch(out, self)
+
+    def download(self, batch):
+        return DownloadedBlocks(self, batch)
+
+    def scan_resident(self, program, batch, want_stats=True):
+        st = CStats() if want_stats else None
+        self._check(lib().vlscan_scan_resident(self.h, program.h, batch.h, C.byref(st) if st is not None else None))
+        self._last = batch
+        return st
+
+    def fetch(self, batch=None, bitmaps=True, counts=True, stats=None):
+        batch = batch or self._last
+        words = np.zeros(max(batch.words, 1), dtype=np.uint64) if bitmaps else None
+        cnt = np.zeros(max(batch.nblocks, 1), dtype=np.uint32) if counts else None
+        self._check(lib().vlscan_fetch_results(self.h, words.ctypes.data_as(C.c_void_p) if bitmaps else None,
+                                               cnt.ctypes.data_as(C.c_void_p) if counts else None, C.byref(stats) if stats is not None else None))
+        return (words[:batch.words] if bitmaps else None), (cnt[:batch.nblocks] if counts else None)
+
+    def fetch_hits(self, batch=None, cap=None):
+        batch = batch or self._last
+        cap = cap if cap is not None else max(int(batch.rows), 1)
+        hits = np.zeros(cap, dtype=np.uint32)
+        offs = np.zeros(batch.nblocks + 1, dtype=np.uint64)
+        self._check(lib().vlscan_fetch_hits(self.h, hits.ctypes.data_as(C.c_void_p), C.c_uint64(cap), offs.ctypes.data_as(C.c_void_p)))
+        return hits[:int(offs[-1])], offs
+
+    def result_device_ptrs(self):
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._check(lib().vlscan_result_device_ptrs(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def scan_batch(self, program, host_blocks, out_words=None, out_counts=None):
+        """End-to-end call on host buffers: upload + scan + fetch (vlscan_scan_batch). -> (words, counts, stats)"""
+        names, lens = host_blocks.name_arrays()
+        nwords = sum((r + 63) // 64 for r in host_blocks.rows)
+        words = out_words if out_words is not None else np.zeros(max(nwords, 1), dtype=np.uint64)
+        cnt = out_counts if out_counts is not None else np.zeros(max(host_blocks.nblocks, 1), dtype=np.uint32)
+        st = CStats()
+        self._check(lib().vlscan_scan_batch(self.h, program.h, names, lens, C.c_uint32(len(host_blocks.field_names)), host_blocks.blocks,
+                                            C.c_uint64(host_blocks.nblocks), words.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p), C.byref(st)))
+        return words[:nwords], cnt[:host_blocks.nblocks], st
+
+    def close(self):
+        if self.h:
+            lib().vlscan_ctx_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def split_bitmaps(words, rows_per_block):
+    """packed words -> list of per-block word arrays"""
+    out, off = [], 0
+    for r in rows_per_block:
+        n = (r + 63) // 64
+        out.append(words[off:off + n])
+        off += n
+    return out
