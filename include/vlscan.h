@@ -168,6 +168,9 @@ void vlscan_host_blocks_free(vlscan_host_blocks* hb);
  * (no host synchronisation) unless `stats` is non-NULL, in which case it synchronises and fills the counters. */
 int vlscan_scan_resident(vlscan_ctx* ctx, const vlscan_program* prog, const vlscan_batch* batch, vlscan_stats* stats);
 
+/* Counters + device timings of the most recent vlscan_scan_resident on this ctx (synchronises the ctx stream). */
+int vlscan_last_scan_stats(vlscan_ctx* ctx, vlscan_stats* stats);
+
 /* Fetch the results of the last vlscan_scan_resident on this ctx.
  *   out_bitmap_words : packed per-block bitmaps, block b at word offset sum_{i<b} ceil(rows_i/64); bit i%64 of word i/64
  *                      = row i, tail bits zero (lib/logstorage/bitmap.go:28-31,62-72) so Go can alias it as bitmap.a

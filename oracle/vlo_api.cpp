@@ -236,10 +236,11 @@ int vlo_gen_rows(const vlo_gen_config* cfg, uint64_t block_id, int column, uint8
 
 // Multi-threaded scan over generated blocks [block_lo, block_hi): the CPU baseline ("port").
 // Blocks are statically sharded across threads like Storage.search workers (storage_search.go:1040-1067).
-// mode 0: build blocks outside the timed region, time only blockSearch over pre-built (zstd-compressed) blocks ("with-zstd");
+// Blocks are built outside the timed region; the timed region is `passes` x blockSearch over the pre-built (ZSTD-compressed)
+// blocks ("with-zstd" variant of BASELINE.md); *secs covers all passes.
 // Returns seconds spent scanning in *secs; accumulates stats; out_counts (may be NULL) gets per-block match counts;
 // out_digest gets xor of xxh64(bitmap words) keyed by block id.
-int vlo_scan_generated(const vlo_gen_config* cfg, void* filter, uint64_t block_lo, uint64_t block_hi, int threads, double* secs,
+int vlo_scan_generated(const vlo_gen_config* cfg, void* filter, uint64_t block_lo, uint64_t block_hi, int threads, int passes, double* secs,
                        uint64_t* stats6, uint32_t* out_counts, uint64_t* out_digest, uint64_t* total_matches) {
     return guard([&] {
         uint64_t nb = block_hi - block_lo;
@@ -260,7 +261,9 @@ int vlo_scan_generated(const vlo_gen_config* cfg, void* filter, uint64_t block_l
             try {
                 BlockSearch bs; Bitmap bm;
                 uint64_t lo = nb * t / threads, hi = nb * (t + 1) / threads;
+                for (int pass = 0; pass < passes; pass++)
                 for (uint64_t i = lo; i < hi; i++) {
+                    if (pass) { block_search(bs, blocks[i], f, bm, nullptr); continue; }   // extra passes only add time (same work)
                     block_search(bs, blocks[i], f, bm, &sts[t]);
                     uint64_t ones = bm.ones();
                     if (out_counts) out_counts[i] = (uint32_t)ones;

@@ -361,15 +361,15 @@ def gen_rows(cfg, block_id, column, cap=None):
     return [raw[int(offs[i]):int(offs[i + 1])] for i in range(rows)]
 
 
-def scan_generated(cfg, flt, block_lo, block_hi, threads, want_counts=False):
+def scan_generated(cfg, flt, block_lo, block_hi, threads, want_counts=False, passes=1):
     """CPU baseline: multi-threaded blockSearch over generated blocks. -> dict(secs, stats, digest, matches, counts)"""
     secs = C.c_double()
     stats = np.zeros(6, dtype=np.uint64)
     dig, tot = C.c_uint64(), C.c_uint64()
     counts = np.zeros(block_hi - block_lo, dtype=np.uint32) if want_counts else None
-    r = lib().vlo_scan_generated(C.byref(cfg), flt.h, C.c_uint64(block_lo), C.c_uint64(block_hi), C.c_int(threads), C.byref(secs),
+    r = lib().vlo_scan_generated(C.byref(cfg), flt.h, C.c_uint64(block_lo), C.c_uint64(block_hi), C.c_int(threads), C.c_int(passes), C.byref(secs),
                                  stats.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p) if want_counts else None,
                                  C.byref(dig), C.byref(tot))
     if r:
         raise _err()
-    return dict(secs=secs.value, stats=stats, digest=dig.value, matches=tot.value, counts=counts)
+    return dict(secs=secs.value, passes=passes, stats=stats, digest=dig.value, matches=tot.value, counts=counts)

@@ -3,6 +3,9 @@
 // computing entry point fails with an error.
 #include <dlfcn.h>
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -154,6 +157,9 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
                       uint64_t nblocks, vlscan_batch* out, vlscan_stats* stats) {
     VL_CUDA(cudaSetDevice(ctx->device));
     if (nblocks > 0xFFFFFFF0ull) throw BadInput("too many blocks in one batch");
+    const bool dbg = getenv("VLSCAN_DEBUG_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_start = now(), t_desc = 0, t_alloc = 0, t_copy = 0;
     out->device = ctx->device; out->nfields = nfields;
     for (uint32_t f = 0; f < nfields; f++) out->field_names.emplace_back(field_names[f], field_name_lens[f]);
     std::vector<DevColumn> cols((size_t)nblocks * std::max<uint32_t>(nfields, 1));
@@ -210,18 +216,25 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
             if (c.value_type == VT_DICT) {
                 if (c.dict_len > 8) throw BadInput("valuesDict may contain max 8 items");
                 d.dict_len = c.dict_len;
-                auto meta = std::make_unique<std::vector<uint8_t>>();
                 uint32_t total = c.dict_len ? c.dict_offsets[c.dict_len] : 0;
-                meta->resize(4 * (c.dict_len + 1) + total);
-                if (c.dict_len) memcpy(meta->data(), c.dict_offsets, 4 * (c.dict_len + 1)); else memset(meta->data(), 0, 4);
-                if (total) memcpy(meta->data() + 4 * (c.dict_len + 1), c.dict_blob, total);
-                d.meta_len = total; d.meta_off = add_piece(meta->data(), meta->size());
-                owned.push_back(std::move(meta));
+                d.meta_len = total;
+                if (c.dict_len && c.dict_blob == (const uint8_t*)c.dict_offsets + 4 * (c.dict_len + 1)) {
+                    d.meta_off = add_piece((const uint8_t*)c.dict_offsets, 4 * (c.dict_len + 1) + total);   // caller memory already has the device layout
+                } else {
+                    auto meta = std::make_unique<std::vector<uint8_t>>();
+                    meta->resize(4 * (c.dict_len + 1) + total);
+                    if (c.dict_len) memcpy(meta->data(), c.dict_offsets, 4 * (c.dict_len + 1)); else memset(meta->data(), 0, 4);
+                    if (total) memcpy(meta->data() + 4 * (c.dict_len + 1), c.dict_blob, total);
+                    d.meta_off = add_piece(meta->data(), meta->size());
+                    owned.push_back(std::move(meta));
+                }
             }
         }
     }
     out->arena_bytes = cursor + kArenaPad;
+    t_desc = now();
     out->arena.ensure(out->arena_bytes);
+    t_alloc = now();
     // copy pieces: runs that are contiguous on both sides (src stride == dst stride) and live in pinned host memory go out as one
     // cudaMemcpyAsync; everything else is packed through a pinned staging ring.
     uint64_t h2d = 0;
@@ -236,40 +249,53 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
     };
     auto is_pinned = [&](const void* p) { cudaPointerAttributes a; if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; } return a.type == cudaMemoryTypeHost; };
     VL_CUDA(cudaMemsetAsync(out->arena.p, 0, out->arena_bytes, ctx->stream));
+    auto need_stage = [&]() {
+        if (stage) return;
+        stage = (uint8_t*)ctx->ensure_pinned(2 * CH);
+        for (int k = 0; k < 2; k++) { VL_CUDA(cudaEventCreateWithFlags(&evs[k], cudaEventDisableTiming)); VL_CUDA(cudaEventRecord(evs[k], ctx->stream)); }
+    };
+    bool all_pinned = !pieces.empty();
     size_t i = 0;
-    bool all_pinned = !pieces.empty() && is_pinned(pieces.front().src) && is_pinned(pieces.back().src);
-    if (!all_pinned && !pieces.empty()) { stage = (uint8_t*)ctx->ensure_pinned(2 * CH); VL_CUDA(cudaEventCreateWithFlags(&evs[0], cudaEventDisableTiming)); VL_CUDA(cudaEventCreateWithFlags(&evs[1], cudaEventDisableTiming)); VL_CUDA(cudaEventRecord(evs[0], ctx->stream)); VL_CUDA(cudaEventRecord(evs[1], ctx->stream)); }
     while (i < pieces.size()) {
-        if (all_pinned) {
-            size_t j = i; uint64_t len = pieces[i].len;
-            while (j + 1 < pieces.size() && pieces[j + 1].src - pieces[i].src == (ptrdiff_t)(pieces[j + 1].dst - pieces[i].dst) && pieces[j + 1].src > pieces[j].src) { j++; len = (pieces[j].dst - pieces[i].dst) + pieces[j].len; }
-            VL_CUDA(cudaMemcpyAsync(out->arena.as<uint8_t>() + pieces[i].dst, pieces[i].src, len, cudaMemcpyHostToDevice, ctx->stream));
-            h2d += len; i = j + 1;
+        // maximal run of pieces laid out identically on both sides (same stride between source and destination)
+        size_t j = i;
+        while (j + 1 < pieces.size() && pieces[j + 1].src > pieces[j].src && pieces[j + 1].src - pieces[i].src == (ptrdiff_t)(pieces[j + 1].dst - pieces[i].dst)) j++;
+        uint64_t run_len = (pieces[j].dst - pieces[i].dst) + pieces[j].len;
+        if (is_pinned(pieces[i].src) && is_pinned(pieces[j].src + pieces[j].len - 1)) {
+            // page-locked caller memory: one DMA for the whole run, gaps (alignment slack) included
+            flush();
+            VL_CUDA(cudaMemcpyAsync(out->arena.as<uint8_t>() + pieces[i].dst, pieces[i].src, run_len, cudaMemcpyHostToDevice, ctx->stream));
+            h2d += run_len; i = j + 1;
             continue;
         }
-        const Piece& pc = pieces[i];
-        uint64_t done = 0;
-        while (done < pc.len) {
-            if (chunk_open && (chunk_dst + fill != pc.dst + done || fill == CH)) flush();
-            if (!chunk_open) { chunk_open = true; chunk_dst = pc.dst + done; fill = 0; }
-            size_t take = (size_t)std::min<uint64_t>(pc.len - done, CH - fill);
-            memcpy(stage + (size_t)cur * CH + fill, pc.src + done, take);
-            fill += take; done += take;
-            // the gap up to the next piece (alignment + pad) is zero in the arena already; close the chunk at piece end unless adjacent
+        all_pinned = false;
+        need_stage();
+        for (; i <= j; i++) {
+            const Piece& pc = pieces[i];
+            uint64_t done = 0;
+            while (done < pc.len) {
+                if (chunk_open && (chunk_dst + fill != pc.dst + done || fill == CH)) flush();
+                if (!chunk_open) { chunk_open = true; chunk_dst = pc.dst + done; fill = 0; }
+                size_t take = (size_t)std::min<uint64_t>(pc.len - done, CH - fill);
+                memcpy(stage + (size_t)cur * CH + fill, pc.src + done, take);
+                fill += take; done += take;
+            }
+            // pack the inter-piece slack (zero in the arena already) when the next piece follows closely, so chunks stay large
+            if (i + 1 < pieces.size()) {
+                uint64_t gap = pieces[i + 1].dst - (pc.dst + pc.len);
+                if (gap <= 64 && fill + gap < CH) { memset(stage + (size_t)cur * CH + fill, 0, gap); fill += gap; } else flush();
+            }
         }
-        // allow packing of the inter-piece padding when the next piece follows within the pad distance
-        if (i + 1 < pieces.size()) {
-            uint64_t gap = pieces[i + 1].dst - (pc.dst + pc.len);
-            if (gap <= 64 && fill + gap < CH) { memset(stage + (size_t)cur * CH + fill, 0, gap); fill += gap; } else flush();
-        }
-        i++;
     }
     flush();
     for (int k = 0; k < 2; k++) if (evs[k]) cudaEventDestroy(evs[k]);
     out->cols.ensure(std::max<size_t>(cols.size() * sizeof(DevColumn), 16));
     if (!cols.empty()) VL_CUDA(cudaMemcpyAsync(out->cols.p, cols.data(), cols.size() * sizeof(DevColumn), cudaMemcpyHostToDevice, ctx->stream));
     h2d += cols.size() * sizeof(DevColumn);
+    if (dbg) { VL_CUDA(cudaStreamSynchronize(ctx->stream)); t_copy = now(); }
     finish_batch_layout(ctx, out, rows);   // synchronises the stream => `owned`, `cols`, staging are safe to drop
+    if (dbg) fprintf(stderr, "[vlscan upload] blocks=%llu bytes=%.1f MB pieces=%zu pinned=%d: describe %.1f ms, alloc %.1f ms, copy %.1f ms (%.1f GB/s), layout %.1f ms\n", (unsigned long long)nblocks,
+                     out->arena_bytes / 1e6, pieces.size(), (int)all_pinned, 1e3 * (t_desc - t_start), 1e3 * (t_alloc - t_desc), 1e3 * (t_copy - t_alloc), h2d / 1e9 / std::max(t_copy - t_alloc, 1e-9), 1e3 * (now() - t_copy));
     h2d += out->nwords * 12 + nblocks * 12;
     if (stats) stats->h2d_bytes += h2d;
 }
@@ -326,6 +352,8 @@ struct ScanRun {
                 VL_CUDA(cudaMemsetAsync(leaf_bm, 0, B.nwords * 8, ctx->stream));
                 k_build_worklist<<<1, 1024, 0, ctx->stream>>>(B, slot, action, (uint8_t)ACT_SCAN, (uint32_t)VL_TILE_BYTES, wb, tp, wc, stats, 1); launch_check(ctx);
                 k_lens_offsets<<<persistent, 256, 0, ctx->stream>>>(B, slot, wb, wc, ro, ready, stats); launch_check(ctx);
+                uint32_t* tb = ctx->tile_block.as<uint32_t>(); uint32_t* to = ctx->tile_off.as<uint32_t>();
+                k_expand_tiles<<<persistent, 64, 0, ctx->stream>>>(B, slot, wb, tp, wc, tb, to); launch_check(ctx);
                 ScanParams sp; memset(&sp, 0, sizeof sp);
                 sp.mode = L.scan_mode; sp.needle_off = L.scan_needle_off; sp.needle_len = L.scan_needle_len; sp.starts_tok = L.starts_tok; sp.ends_tok = L.ends_tok; sp.regex = L.regex;
                 const uint8_t* nd = prog->p.blob.data() + L.scan_needle_off;
@@ -334,7 +362,15 @@ struct ScanRun {
                 if (L.scan_mode == SCAN_CONTAINS || L.scan_mode >= SCAN_RX_DOTPLUS) { sp.starts_tok = sp.ends_tok = 0; }
                 auto& evp = next_scan_events();
                 VL_CUDA(cudaEventRecord(evp.first, ctx->stream));
-                k_substr_scan<<<persistent, VL_SCAN_THREADS, 0, ctx->stream>>>(P, B, slot, sp, wb, tp, wc, ro, leaf_bm); launch_check(ctx);
+                // persistent CTAs: exactly the resident set (148 SMs x resident CTAs per SM), each striding over the 64 KiB tiles
+                static int occ_full = 0, occ_part = 0;
+                if (!occ_full) {
+                    VL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_full, k_substr_scan<true>, VL_SCAN_THREADS, 0));
+                    VL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_part, k_substr_scan<false>, VL_SCAN_THREADS, 0));
+                }
+                if (L.scan_needle_len >= 4) k_substr_scan<true><<<ctx->sm_count * std::max(occ_full, 1), VL_SCAN_THREADS, 0, ctx->stream>>>(P, B, slot, sp, tb, to, wc, ro, leaf_bm);
+                else k_substr_scan<false><<<ctx->sm_count * std::max(occ_part, 1), VL_SCAN_THREADS, 0, ctx->stream>>>(P, B, slot, sp, tb, to, wc, ro, leaf_bm);
+                launch_check(ctx);
                 VL_CUDA(cudaEventRecord(evp.second, ctx->stream));
             }
             // per-row matcher (string exact / in / general regexp; numeric columns through text)
@@ -403,6 +439,10 @@ static void do_scan(vlscan_ctx* ctx, const vlscan_program* prog, const vlscan_ba
     uint64_t nb = std::max<uint64_t>(batch->nblocks, 1), nw = std::max<uint64_t>(batch->nwords, 1);
     ctx->alive.ensure(nb); ctx->action.ensure(nb); ctx->payload.ensure(nb * 8); ctx->leaf_bm.ensure(nw * 8);
     ctx->work_blocks.ensure(nb * 4); ctx->tile_prefix.ensure((nb + 1) * 4); ctx->work_count.ensure(16);
+    {   // upper bound of 64 KiB tiles of any single column: every payload byte belongs to one column, plus one partial tile per block
+        uint64_t max_tiles = batch->arena_bytes / VL_TILE_BYTES + nb + 16;
+        ctx->tile_block.ensure(max_tiles * 4); ctx->tile_off.ensure(max_tiles * 4);
+    }
     ctx->stats.ensure(ST_COUNT * 8); ctx->totals.ensure(32); ctx->counts.ensure(nb * 4);
     if (ctx->row_off64.size() < batch->nfields) { ctx->row_off64.resize(batch->nfields); ctx->ready.resize(batch->nfields); }
     ctx->ready_cleared.assign(batch->nfields, 0);
@@ -423,7 +463,7 @@ static void do_scan(vlscan_ctx* ctx, const vlscan_program* prog, const vlscan_ba
         launch_check(ctx);
     }
     VL_CUDA(cudaEventRecord(ctx->ev_end, ctx->stream));
-    ctx->last_batch = batch; ctx->has_result = true;
+    ctx->last_batch = batch; ctx->has_result = true; ctx->last_launches = ctx->launches - launches0;
     if (stats) {
         read_stats(ctx, stats, true);
         stats->blocks += batch->nblocks; stats->rows += batch->rows; stats->gpu_launches += ctx->launches - launches0;
@@ -457,7 +497,7 @@ void vlscan_ctx_free(vlscan_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    for (DevBuf* b : {&ctx->alive, &ctx->action, &ctx->payload, &ctx->leaf_bm, &ctx->work_blocks, &ctx->tile_prefix, &ctx->work_count, &ctx->stats, &ctx->totals, &ctx->counts, &ctx->slots, &ctx->hit_offs, &ctx->hits}) b->release();
+    for (DevBuf* b : {&ctx->alive, &ctx->action, &ctx->payload, &ctx->leaf_bm, &ctx->work_blocks, &ctx->tile_prefix, &ctx->work_count, &ctx->stats, &ctx->totals, &ctx->counts, &ctx->slots, &ctx->hit_offs, &ctx->hits, &ctx->tile_block, &ctx->tile_off}) b->release();
     for (auto& r : ctx->regs) r.release();
     for (auto& r : ctx->row_off64) r.release();
     for (auto& r : ctx->ready) r.release();
@@ -557,6 +597,15 @@ void vlscan_host_blocks_free(vlscan_host_blocks* hb) { if (!hb) return; if (hb->
 
 int vlscan_scan_resident(vlscan_ctx* ctx, const vlscan_program* prog, const vlscan_batch* batch, vlscan_stats* stats) {
     return guarded(ctx, [&] { do_scan(ctx, prog, batch, stats); });
+}
+
+int vlscan_last_scan_stats(vlscan_ctx* ctx, vlscan_stats* stats) {
+    return guarded(ctx, [&] {
+        if (!ctx->has_result) throw BadInput("no scan on this ctx yet");
+        VL_CUDA(cudaSetDevice(ctx->device));
+        read_stats(ctx, stats, true);
+        stats->blocks += ctx->last_batch->nblocks; stats->rows += ctx->last_batch->rows; stats->gpu_launches += ctx->last_launches;
+    });
 }
 
 int vlscan_fetch_results(vlscan_ctx* ctx, uint64_t* out_bitmap_words, uint32_t* out_match_counts, vlscan_stats* stats) {

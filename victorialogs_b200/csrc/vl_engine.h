@@ -69,7 +69,7 @@ struct vlscan_ctx {
     std::string err;
     uint64_t launches = 0;
     // scratch (grow-only)
-    vl::DevBuf alive, action, payload, leaf_bm, work_blocks, tile_prefix, work_count, stats, totals, counts, slots, hit_offs, hits;
+    vl::DevBuf alive, action, payload, leaf_bm, work_blocks, tile_prefix, work_count, stats, totals, counts, slots, hit_offs, hits, tile_block, tile_off;
     std::vector<vl::DevBuf> regs;          // bitmap registers of the tree interpreter
     std::vector<vl::DevBuf> row_off64;     // per batch field slot
     std::vector<vl::DevBuf> ready;         // per batch field slot: row_off64 computed for block b in this scan
@@ -80,6 +80,7 @@ struct vlscan_ctx {
     // last scan
     const vlscan_batch* last_batch = nullptr;
     bool has_result = false;
+    uint64_t last_launches = 0;
     int sm_count = 148;
     void* ensure_pinned(size_t n);
 };

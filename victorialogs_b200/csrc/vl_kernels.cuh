@@ -434,38 +434,49 @@ struct ScanParams {
     int32_t regex;
 };
 
-static __device__ __noinline__ void scan_verify(const DevProgram& P, const BatchView& B, const DevColumn& c, const ScanParams& sp, uint32_t b,
-                                         const uint32_t* __restrict__ row_off64, uint64_t pos, uint64_t* __restrict__ leaf_bm) {
+// Warp-cooperative verification of one candidate occurrence at byte `pos` of block b's data.  All 32 lanes call with identical
+// arguments (the caller broadcasts the candidate), so every branch below is warp-uniform: the tail compare is striped over the
+// lanes, the byte-offset -> row lookup loads the 64 lens of one bitmap word in parallel and prefix-sums them with shuffles.
+static __device__ __noinline__ void scan_verify_warp(const DevProgram& P, const BatchView& B, const DevColumn& c, const ScanParams& sp, uint32_t b,
+                                                     const uint32_t* __restrict__ row_off64, uint32_t pos, uint64_t* __restrict__ leaf_bm) {
     const uint8_t* data = B.arena + c.data_off;
     const uint8_t* nd = P.blob + sp.needle_off;
-    uint32_t L = sp.needle_len;
-    if (pos + L > c.data_len) return;
-    for (uint32_t k = 4; k < L; k++) if (data[pos + k] != nd[k]) return;
+    const uint32_t L = sp.needle_len, lane = lane_id();
+    if ((uint64_t)pos + L > c.data_len) return;
+    bool same = true;
+    for (uint32_t k = 4 + lane; k < L; k += 32) same &= data[pos + k] == nd[k];
+    if (!__all_sync(0xffffffffu, same)) return;
     // byte offset -> row
-    uint32_t rows = B.blk_rows[b];
-    uint64_t w0 = B.blk_word_off[b];
-    uint32_t r; uint64_t off; uint32_t len;
-    const uint8_t* lens = B.arena + c.lens_off;
+    const uint32_t rows = B.blk_rows[b];
+    const uint64_t w0 = B.blk_word_off[b];
+    uint32_t r, off, len;
     if (c.lens_type >= 4) {
         len = c.lens_const;
         if (len == 0) return;
-        r = (uint32_t)(pos / len); off = (uint64_t)r * len;
+        r = pos / len; off = r * len;
         if (r >= rows) return;
     } else {
+        const uint8_t* lens = B.arena + c.lens_off;
         uint32_t nw = (uint32_t)(B.blk_word_off[b + 1] - w0);
         uint32_t lo = 0, hi = nw - 1;
         while (lo < hi) { uint32_t mid = (lo + hi + 1) >> 1; if (row_off64[w0 + mid] <= pos) lo = mid; else hi = mid - 1; }
-        r = lo * 64; off = row_off64[w0 + lo];
-        for (;;) {
-            if (r >= rows) return;
-            len = row_len(c, lens, r);
-            if (pos < off + len) break;
-            off += len; r++;
-        }
+        const uint32_t r0 = lo * 64, base = row_off64[w0 + lo];
+        const uint32_t ra = r0 + lane, rb = r0 + 32 + lane;
+        uint32_t la = ra < rows ? row_len(c, lens, ra) : 0, lb = rb < rows ? row_len(c, lens, rb) : 0;
+        uint32_t ia = la, ib = lb;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, ia, d), u = __shfl_up_sync(0xffffffffu, ib, d); if (lane >= d) { ia += t; ib += u; } }
+        const uint32_t tot_a = __shfl_sync(0xffffffffu, ia, 31);
+        const uint32_t sa = base + ia - la, sb = base + tot_a + ib - lb;   // row starts
+        // the row holding pos is the LAST row whose start is <= pos (zero-length rows share a start with their successor)
+        const uint32_t ba = __ballot_sync(0xffffffffu, ra < rows && sa <= pos), bb = __ballot_sync(0xffffffffu, rb < rows && sb <= pos);
+        if (bb) { int src = 31 - __clz(bb); r = r0 + 32 + src; off = __shfl_sync(0xffffffffu, sb, src); len = __shfl_sync(0xffffffffu, lb, src); }
+        else if (ba) { int src = 31 - __clz(ba); r = r0 + src; off = __shfl_sync(0xffffffffu, sa, src); len = __shfl_sync(0xffffffffu, la, src); }
+        else return;
+        if (pos >= off + len) return;
     }
-    uint64_t end = off + len;
-    if (pos + L > end) return;   // the occurrence straddles a row boundary
-    const uint8_t* s = data + off; uint32_t p = (uint32_t)(pos - off);
+    if (pos + L > off + len) return;   // the occurrence straddles a row boundary
+    const uint8_t* s = data + off; const uint32_t p = pos - off;
     bool hit;
     switch (sp.mode) {
     case SCAN_PHRASE: hit = phrase_boundaries_ok(s, len, p, L, sp.starts_tok, sp.ends_tok); break;
@@ -474,62 +485,95 @@ static __device__ __noinline__ void scan_verify(const DevProgram& P, const Batch
     case SCAN_RX_DOTPLUS: hit = p + L < len; break;
     default: hit = dfa_run(P.regexes[sp.regex], P.blob, s + p + L, len - p - L); break;   // SCAN_RX_SUFFIX
     }
-    if (hit) atomicOr((unsigned long long*)&leaf_bm[w0 + (r >> 6)], 1ull << (r & 63));
+    if (hit && lane == 0) atomicOr((unsigned long long*)&leaf_bm[w0 + (r >> 6)], 1ull << (r & 63));
 }
 
 #define VL_SCAN_THREADS 256
-#define VL_SCAN_ITERS 4
-#define VL_TILE_BYTES (VL_SCAN_THREADS * 16 * VL_SCAN_ITERS)
+#define VL_SCAN_UNROLL 4                       /* independent 16-byte loads in flight per thread */
+#define VL_SCAN_ROUNDS 4                       /* rounds per tile */
+#define VL_TILE_BYTES (VL_SCAN_THREADS * 16 * VL_SCAN_UNROLL * VL_SCAN_ROUNDS)   /* 64 KiB of row bytes per CTA work item */
 
-static __global__ void __launch_bounds__(VL_SCAN_THREADS) k_substr_scan(DevProgram P, BatchView B, int slot, ScanParams sp, const uint32_t* __restrict__ work_blocks,
-                                                                const uint32_t* __restrict__ tile_prefix, const uint32_t* __restrict__ work_count,
-                                                                const uint32_t* __restrict__ row_off64, uint64_t* __restrict__ leaf_bm) {
-    const uint32_t nwork = work_count[0], ntiles = work_count[1];
-    const uint32_t L = sp.needle_len;
+// work item -> its tiles: tile_block[t] = block, tile_off[t] = first byte of the tile inside the block's data
+static __global__ void k_expand_tiles(BatchView B, int slot, const uint32_t* __restrict__ work_blocks, const uint32_t* __restrict__ tile_prefix,
+                                      const uint32_t* __restrict__ work_count, uint32_t* __restrict__ tile_block, uint32_t* __restrict__ tile_off) {
+    const uint32_t nwork = work_count[0];
+    for (uint32_t j = blockIdx.x; j < nwork; j += gridDim.x) {
+        const uint32_t first = tile_prefix[j], cnt = tile_prefix[j + 1] - first, b = work_blocks[j];
+        for (uint32_t k = threadIdx.x; k < cnt; k += blockDim.x) { tile_block[first + k] = b; tile_off[first + k] = k * (uint32_t)VL_TILE_BYTES; }
+    }
+}
+
+// does any of the 16 four-byte windows starting in {w0..w3} (continued by w4) equal n4 (under mask m4 when L < 4)?
+template <bool FULL4>
+__device__ __forceinline__ bool scan_any_window(const uint32_t (&w)[5], uint32_t n4, uint32_t m4) {
+    bool any = false;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t win = j == 0 ? w[i] : __funnelshift_r(w[i], w[i + 1], 8 * j);
+            if (!FULL4) win &= m4;
+            any |= win == n4;
+        }
+    }
+    return any;
+}
+__device__ __forceinline__ uint32_t scan_window_mask(const uint32_t (&w)[5], uint32_t n4, uint32_t m4) {
+    uint32_t cand = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t win = j == 0 ? w[i] : __funnelshift_r(w[i], w[i + 1], 8 * j);
+            if ((win & m4) == n4) cand |= 1u << (i * 4 + j);
+        }
+    }
+    return cand;
+}
+
+template <bool FULL4>
+static __global__ void __launch_bounds__(VL_SCAN_THREADS) k_substr_scan(DevProgram P, BatchView B, int slot, ScanParams sp, const uint32_t* __restrict__ tile_block,
+                                                                        const uint32_t* __restrict__ tile_off, const uint32_t* __restrict__ work_count,
+                                                                        const uint32_t* __restrict__ row_off64, uint64_t* __restrict__ leaf_bm) {
+    const uint32_t ntiles = work_count[1];
+    const uint32_t n4 = sp.n4, m4 = sp.m4;
     for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        // tile -> (work item, tile index)
-        uint32_t lo = 0, hi = nwork - 1;
-        while (lo < hi) { uint32_t mid = (lo + hi + 1) >> 1; if (tile_prefix[mid] <= t) lo = mid; else hi = mid - 1; }
-        const uint32_t b = work_blocks[lo];
+        const uint32_t b = __ldg(tile_block + t), tile0 = __ldg(tile_off + t);
         const DevColumn& c = B.cols[(uint64_t)b * B.nfields + slot];
-        const uint64_t n = c.data_len;
-        const uint8_t* data = B.arena + c.data_off;
-        const uint64_t t0 = (uint64_t)(t - tile_prefix[lo]) * VL_TILE_BYTES;
-        uint4 v[VL_SCAN_ITERS];
-        uint32_t halo[VL_SCAN_ITERS];
+        const uint32_t n = (uint32_t)c.data_len;           // < 4 GiB by construction (upload rejects larger payloads)
+        const uint8_t* __restrict__ data = B.arena + c.data_off;
+#pragma unroll 1
+        for (int round = 0; round < VL_SCAN_ROUNDS; round++) {
+            const uint32_t round0 = tile0 + (uint32_t)round * (VL_SCAN_THREADS * 16 * VL_SCAN_UNROLL);
+            if (round0 >= n) break;                           // uniform: the whole round lies past the data
+            const uint32_t base = round0 + threadIdx.x * 16;
+            uint4 v[VL_SCAN_UNROLL];
 #pragma unroll
-        for (int it = 0; it < VL_SCAN_ITERS; it++) {
-            uint64_t p = t0 + ((uint64_t)it * VL_SCAN_THREADS + threadIdx.x) * 16;
-            // payloads are padded with >= 32 readable bytes past data_len, so vector loads that start before n are safe
-            v[it] = p < n ? __ldg((const uint4*)(data + p)) : make_uint4(0, 0, 0, 0);
-        }
+            for (int u = 0; u < VL_SCAN_UNROLL; u++) {
+                uint32_t p = base + u * (VL_SCAN_THREADS * 16);
+                // payloads keep >= 32 readable bytes past data_len: a vector load that starts before n is always in bounds
+                v[u] = p < n ? __ldg((const uint4*)(data + p)) : make_uint4(0, 0, 0, 0);
+            }
 #pragma unroll
-        for (int it = 0; it < VL_SCAN_ITERS; it++) {
-            uint64_t p = t0 + ((uint64_t)it * VL_SCAN_THREADS + threadIdx.x) * 16;
-            uint32_t nx = __shfl_down_sync(0xffffffffu, v[it].x, 1);
-            if (lane_id() == 31) nx = (p + 16 < n) ? __ldg((const uint32_t*)(data + p + 16)) : 0;
-            halo[it] = nx;
-        }
-#pragma unroll
-        for (int it = 0; it < VL_SCAN_ITERS; it++) {
-            uint64_t p = t0 + ((uint64_t)it * VL_SCAN_THREADS + threadIdx.x) * 16;
-            if (p >= n) continue;
-            uint32_t w[5] = {v[it].x, v[it].y, v[it].z, v[it].w, halo[it]};
-            uint32_t cand = 0;
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    uint32_t win = j == 0 ? w[i] : __funnelshift_r(w[i], w[i + 1], 8 * j);
-                    if ((win & sp.m4) == sp.n4) cand |= 1u << (i * 4 + j);
+            for (int u = 0; u < VL_SCAN_UNROLL; u++) {
+                const uint32_t p = base + u * (VL_SCAN_THREADS * 16);
+                uint32_t nx = __shfl_down_sync(0xffffffffu, v[u].x, 1);
+                if (lane_id() == 31) nx = (p + 16 < n) ? __ldg((const uint32_t*)(data + p + 16)) : 0;
+                const uint32_t w[5] = {v[u].x, v[u].y, v[u].z, v[u].w, nx};
+                const bool mine = p < n && scan_any_window<FULL4>(w, n4, m4);
+                uint32_t vote = __ballot_sync(0xffffffffu, mine);
+                while (vote) {                                // rare: some lane of this warp holds a candidate; the warp verifies it together
+                    const int src = __ffs(vote) - 1; vote &= vote - 1;
+                    uint32_t cand = lane_id() == (uint32_t)src ? scan_window_mask(w, n4, m4) : 0;
+                    cand = __shfl_sync(0xffffffffu, cand, src);
+                    const uint32_t p0 = __shfl_sync(0xffffffffu, p, src);
+                    while (cand) {
+                        const int k = __ffs(cand) - 1; cand &= cand - 1;
+                        scan_verify_warp(P, B, c, sp, b, row_off64, p0 + k, leaf_bm);
+                    }
                 }
             }
-            while (cand) {
-                int k = __ffs(cand) - 1; cand &= cand - 1;
-                scan_verify(P, B, c, sp, b, row_off64, p + k, leaf_bm);
-            }
         }
-        (void)L;
     }
 }
 

@@ -67,7 +67,7 @@ EXPORTS = ["vlscan_device_count", "vlscan_ctx_create", "vlscan_ctx_free", "vlsca
            "vlscan_program_create", "vlscan_program_free", "vlscan_program_nfields", "vlscan_program_field", "vlscan_program_leaf_tokens",
            "vlscan_batch_upload", "vlscan_batch_free", "vlscan_batch_nblocks", "vlscan_batch_rows", "vlscan_batch_words", "vlscan_batch_device_bytes",
            "vlscan_batch_generate", "vlscan_batch_download", "vlscan_host_blocks_get", "vlscan_host_blocks_field", "vlscan_host_blocks_bytes",
-           "vlscan_host_blocks_free", "vlscan_scan_resident", "vlscan_fetch_results", "vlscan_fetch_hits", "vlscan_result_device_ptrs", "vlscan_scan_batch"]
+           "vlscan_host_blocks_free", "vlscan_scan_resident", "vlscan_last_scan_stats", "vlscan_fetch_results", "vlscan_fetch_hits", "vlscan_result_device_ptrs", "vlscan_scan_batch"]
 
 
 def lib_path():
@@ -377,6 +377,11 @@ class Ctx:
         st = CStats() if want_stats else None
         self._check(lib().vlscan_scan_resident(self.h, program.h, batch.h, C.byref(st) if st is not None else None))
         self._last = batch
+        return st
+
+    def last_scan_stats(self):
+        st = CStats()
+        self._check(lib().vlscan_last_scan_stats(self.h, C.byref(st)))
         return st
 
     def fetch(self, batch=None, bitmaps=True, counts=True, stats=None):
