@@ -293,6 +293,7 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
     if (!cols.empty()) VL_CUDA(cudaMemcpyAsync(out->cols.p, cols.data(), cols.size() * sizeof(DevColumn), cudaMemcpyHostToDevice, ctx->stream));
     h2d += cols.size() * sizeof(DevColumn);
     if (dbg) { VL_CUDA(cudaStreamSynchronize(ctx->stream)); t_copy = now(); }
+    if (nfields) out->note_columns(cols);
     finish_batch_layout(ctx, out, rows);   // synchronises the stream => `owned`, `cols`, staging are safe to drop
     if (dbg) fprintf(stderr, "[vlscan upload] blocks=%llu bytes=%.1f MB pieces=%zu pinned=%d: describe %.1f ms, alloc %.1f ms, copy %.1f ms (%.1f GB/s), layout %.1f ms\n", (unsigned long long)nblocks,
                      out->arena_bytes / 1e6, pieces.size(), (int)all_pinned, 1e3 * (t_desc - t_start), 1e3 * (t_alloc - t_desc), 1e3 * (t_copy - t_alloc), h2d / 1e9 / std::max(t_copy - t_alloc, 1e-9), 1e3 * (now() - t_copy));
@@ -347,13 +348,25 @@ struct ScanRun {
             uint32_t* ro = ctx->row_off64[slot].as<uint32_t>(); uint8_t* ready = ctx->ready[slot].as<uint8_t>();
             if (!ctx->ready_cleared[slot]) { VL_CUDA(cudaMemsetAsync(ready, 0, B.nblocks, ctx->stream)); ctx->ready_cleared[slot] = 1; }
             const int persistent = ctx->sm_count * 8;
+            // which kernels can have work is known from the value types this field takes in the batch (header dispatch is per block,
+            // on the device, but a field that is never a plain string column cannot produce ACT_SCAN, etc.)
+            const uint32_t vts = batch->slot_vt_mask.empty() ? ~0u : batch->slot_vt_mask[slot];
+            const bool has_string = vts >> VT_STRING & 1, has_dict = vts >> VT_DICT & 1;
+            const bool has_numeric = (vts & ~((1u << VT_STRING) | (1u << VT_DICT))) != 0;
             // row-agnostic substring scan
-            if (L.str_strategy == STR_SCAN) {
+            if (L.str_strategy == STR_SCAN && has_string) {
                 VL_CUDA(cudaMemsetAsync(leaf_bm, 0, B.nwords * 8, ctx->stream));
-                k_build_worklist<<<1, 1024, 0, ctx->stream>>>(B, slot, action, (uint8_t)ACT_SCAN, (uint32_t)VL_TILE_BYTES, wb, tp, wc, stats, 1); launch_check(ctx);
+                // default: the register-staged LDG.128 kernel (47.7 % of measured HBM peak on C2); VLSCAN_SCAN_VARIANT=tma selects the
+                // cp.async.bulk + mbarrier variant, which measured slower on B200 in round 1 (27 %) and is kept for the next round's tuning
+                static const bool use_tma = [] { const char* v = getenv("VLSCAN_SCAN_VARIANT"); return v && strcmp(v, "tma") == 0; }();
+                // work list of the blocks whose plan says ACT_SCAN, cut into 16 KiB chunks (TMA variant) or 64 KiB tiles (LDG variant)
+                k_build_worklist<<<1, 1024, 0, ctx->stream>>>(B, slot, action, (uint8_t)ACT_SCAN, use_tma ? (uint32_t)VL_TMA_CHUNK : (uint32_t)VL_TILE_BYTES, wb, tp, wc, stats, 1); launch_check(ctx);
                 k_lens_offsets<<<persistent, 256, 0, ctx->stream>>>(B, slot, wb, wc, ro, ready, stats); launch_check(ctx);
                 uint32_t* tb = ctx->tile_block.as<uint32_t>(); uint32_t* to = ctx->tile_off.as<uint32_t>();
-                k_expand_tiles<<<persistent, 64, 0, ctx->stream>>>(B, slot, wb, tp, wc, tb, to); launch_check(ctx);
+                ChunkDesc* chunks = ctx->chunks.as<ChunkDesc>();
+                if (use_tma) k_expand_chunks<<<persistent, 64, 0, ctx->stream>>>(B, slot, wb, tp, wc, chunks);
+                else k_expand_tiles<<<persistent, 64, 0, ctx->stream>>>(B, slot, wb, tp, wc, tb, to);
+                launch_check(ctx);
                 ScanParams sp; memset(&sp, 0, sizeof sp);
                 sp.mode = L.scan_mode; sp.needle_off = L.scan_needle_off; sp.needle_len = L.scan_needle_len; sp.starts_tok = L.starts_tok; sp.ends_tok = L.ends_tok; sp.regex = L.regex;
                 const uint8_t* nd = prog->p.blob.data() + L.scan_needle_off;
@@ -362,22 +375,32 @@ struct ScanRun {
                 if (L.scan_mode == SCAN_CONTAINS || L.scan_mode >= SCAN_RX_DOTPLUS) { sp.starts_tok = sp.ends_tok = 0; }
                 auto& evp = next_scan_events();
                 VL_CUDA(cudaEventRecord(evp.first, ctx->stream));
-                // persistent CTAs: exactly the resident set (148 SMs x resident CTAs per SM), each striding over the 64 KiB tiles
-                static int occ_full = 0, occ_part = 0;
+                // persistent CTAs: exactly the resident set (148 SMs x resident CTAs per SM), each striding over the work items
+                static int occ_full = 0, occ_part = 0, occ_tma_full = 0, occ_tma_part = 0;
                 if (!occ_full) {
                     VL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_full, k_substr_scan<true>, VL_SCAN_THREADS, 0));
                     VL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_part, k_substr_scan<false>, VL_SCAN_THREADS, 0));
+                    VL_CUDA(cudaFuncSetAttribute(k_substr_scan_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VL_TMA_SMEM));
+                    VL_CUDA(cudaFuncSetAttribute(k_substr_scan_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VL_TMA_SMEM));
+                    VL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_tma_full, k_substr_scan_tma<true>, VL_SCAN_THREADS, VL_TMA_SMEM));
+                    VL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_tma_part, k_substr_scan_tma<false>, VL_SCAN_THREADS, VL_TMA_SMEM));
                 }
-                if (L.scan_needle_len >= 4) k_substr_scan<true><<<ctx->sm_count * std::max(occ_full, 1), VL_SCAN_THREADS, 0, ctx->stream>>>(P, B, slot, sp, tb, to, wc, ro, leaf_bm);
+                if (use_tma) {
+                    // TMA-staged variant: cp.async.bulk global->shared through a 4-stage mbarrier ring (see vl_kernels.cuh)
+                    if (L.scan_needle_len >= 4) k_substr_scan_tma<true><<<ctx->sm_count * std::max(occ_tma_full, 1), VL_SCAN_THREADS, VL_TMA_SMEM, ctx->stream>>>(P, B, slot, sp, chunks, wc, ro, leaf_bm);
+                    else k_substr_scan_tma<false><<<ctx->sm_count * std::max(occ_tma_part, 1), VL_SCAN_THREADS, VL_TMA_SMEM, ctx->stream>>>(P, B, slot, sp, chunks, wc, ro, leaf_bm);
+                } else if (L.scan_needle_len >= 4) k_substr_scan<true><<<ctx->sm_count * std::max(occ_full, 1), VL_SCAN_THREADS, 0, ctx->stream>>>(P, B, slot, sp, tb, to, wc, ro, leaf_bm);
                 else k_substr_scan<false><<<ctx->sm_count * std::max(occ_part, 1), VL_SCAN_THREADS, 0, ctx->stream>>>(P, B, slot, sp, tb, to, wc, ro, leaf_bm);
                 launch_check(ctx);
                 VL_CUDA(cudaEventRecord(evp.second, ctx->stream));
             }
             // per-row matcher (string exact / in / general regexp; numeric columns through text)
-            k_build_worklist<<<1, 1024, 0, ctx->stream>>>(B, slot, action, (uint8_t)ACT_ROW, (uint32_t)VL_TILE_BYTES, wb, tp, wc, stats, 0); launch_check(ctx);
-            k_lens_offsets<<<persistent, 256, 0, ctx->stream>>>(B, slot, wb, wc, ro, ready, stats); launch_check(ctx);
-            k_row_match<<<cdiv(B.nwords * 32, 256), 256, 0, ctx->stream>>>(P, B, (uint32_t)leaf_idx, slot, action, payload, ro, leaf_bm); launch_check(ctx);
-            k_word_match<<<cdiv(B.nwords, 128), 128, 0, ctx->stream>>>(P, B, (uint32_t)leaf_idx, slot, action, payload, leaf_bm, stats); launch_check(ctx);
+            if ((has_string && L.str_strategy == STR_ROW) || has_numeric) {
+                k_build_worklist<<<1, 1024, 0, ctx->stream>>>(B, slot, action, (uint8_t)ACT_ROW, (uint32_t)VL_TILE_BYTES, wb, tp, wc, stats, 0); launch_check(ctx);
+                k_lens_offsets<<<persistent, 256, 0, ctx->stream>>>(B, slot, wb, wc, ro, ready, stats); launch_check(ctx);
+                k_row_match<<<cdiv(B.nwords * 32, 256), 256, 0, ctx->stream>>>(P, B, (uint32_t)leaf_idx, slot, action, payload, ro, leaf_bm); launch_check(ctx);
+            }
+            if (has_dict || has_numeric) { k_word_match<<<cdiv(B.nwords, 128), 128, 0, ctx->stream>>>(P, B, (uint32_t)leaf_idx, slot, action, payload, leaf_bm, stats); launch_check(ctx); }
         }
         if (B.nwords) { k_apply_leaf<<<cdiv(B.nwords, 256), 256, 0, ctx->stream>>>(B, action, leaf_bm, reg); launch_check(ctx); }
     }
@@ -440,8 +463,8 @@ static void do_scan(vlscan_ctx* ctx, const vlscan_program* prog, const vlscan_ba
     ctx->alive.ensure(nb); ctx->action.ensure(nb); ctx->payload.ensure(nb * 8); ctx->leaf_bm.ensure(nw * 8);
     ctx->work_blocks.ensure(nb * 4); ctx->tile_prefix.ensure((nb + 1) * 4); ctx->work_count.ensure(16);
     {   // upper bound of 64 KiB tiles of any single column: every payload byte belongs to one column, plus one partial tile per block
-        uint64_t max_tiles = batch->arena_bytes / VL_TILE_BYTES + nb + 16;
-        ctx->tile_block.ensure(max_tiles * 4); ctx->tile_off.ensure(max_tiles * 4);
+        uint64_t max_tiles = batch->arena_bytes / VL_TILE_BYTES + nb + 16, max_chunks = batch->arena_bytes / VL_TMA_CHUNK + nb + 16;
+        ctx->tile_block.ensure(max_tiles * 4); ctx->tile_off.ensure(max_tiles * 4); ctx->chunks.ensure(max_chunks * sizeof(ChunkDesc));
     }
     ctx->stats.ensure(ST_COUNT * 8); ctx->totals.ensure(32); ctx->counts.ensure(nb * 4);
     if (ctx->row_off64.size() < batch->nfields) { ctx->row_off64.resize(batch->nfields); ctx->ready.resize(batch->nfields); }
@@ -497,7 +520,7 @@ void vlscan_ctx_free(vlscan_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    for (DevBuf* b : {&ctx->alive, &ctx->action, &ctx->payload, &ctx->leaf_bm, &ctx->work_blocks, &ctx->tile_prefix, &ctx->work_count, &ctx->stats, &ctx->totals, &ctx->counts, &ctx->slots, &ctx->hit_offs, &ctx->hits, &ctx->tile_block, &ctx->tile_off}) b->release();
+    for (DevBuf* b : {&ctx->alive, &ctx->action, &ctx->payload, &ctx->leaf_bm, &ctx->work_blocks, &ctx->tile_prefix, &ctx->work_count, &ctx->stats, &ctx->totals, &ctx->counts, &ctx->slots, &ctx->hit_offs, &ctx->hits, &ctx->tile_block, &ctx->tile_off, &ctx->chunks}) b->release();
     for (auto& r : ctx->regs) r.release();
     for (auto& r : ctx->row_off64) r.release();
     for (auto& r : ctx->ready) r.release();

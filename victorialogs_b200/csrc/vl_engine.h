@@ -52,6 +52,11 @@ struct vlscan_batch {
     vl::DevBuf arena, cols, blk_rows, blk_word_off, word_block, init_bitmap;
     std::vector<uint32_t> h_rows;
     std::vector<uint64_t> h_word_off;
+    std::vector<uint32_t> slot_vt_mask;   // per field slot: bit vt set when some block stores the field with that valueType
+    void note_columns(const std::vector<vl::DevColumn>& cols) {
+        slot_vt_mask.assign(nfields, 0);
+        for (size_t i = 0; i < cols.size(); i++) if (cols[i].kind == vl::COL_VALUES) slot_vt_mask[i % nfields] |= 1u << cols[i].vt;
+    }
     vl::BatchView view() const {
         vl::BatchView v;
         v.arena = arena.as<uint8_t>(); v.cols = cols.as<vl::DevColumn>(); v.blk_rows = blk_rows.as<uint32_t>();
@@ -69,7 +74,7 @@ struct vlscan_ctx {
     std::string err;
     uint64_t launches = 0;
     // scratch (grow-only)
-    vl::DevBuf alive, action, payload, leaf_bm, work_blocks, tile_prefix, work_count, stats, totals, counts, slots, hit_offs, hits, tile_block, tile_off;
+    vl::DevBuf alive, action, payload, leaf_bm, work_blocks, tile_prefix, work_count, stats, totals, counts, slots, hit_offs, hits, tile_block, tile_off, chunks;
     std::vector<vl::DevBuf> regs;          // bitmap registers of the tree interpreter
     std::vector<vl::DevBuf> row_off64;     // per batch field slot
     std::vector<vl::DevBuf> ready;         // per batch field slot: row_off64 computed for block b in this scan

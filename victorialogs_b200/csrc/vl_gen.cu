@@ -340,6 +340,7 @@ extern "C" int vlscan_batch_generate(vlscan_ctx* ctx, const vlscan_gen_config* c
                 d_offs.release(); d_vals.release();
             }
         }
+        bt->note_columns(cols);
         finish_batch_layout(ctx, bt, rows);
         plans_d.release(); info_d.release();
         *out = bt;

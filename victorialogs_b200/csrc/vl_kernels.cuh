@@ -492,6 +492,7 @@ static __device__ __noinline__ void scan_verify_warp(const DevProgram& P, const 
 #define VL_SCAN_UNROLL 4                       /* independent 16-byte loads in flight per thread */
 #define VL_SCAN_ROUNDS 4                       /* rounds per tile */
 #define VL_TILE_BYTES (VL_SCAN_THREADS * 16 * VL_SCAN_UNROLL * VL_SCAN_ROUNDS)   /* 64 KiB of row bytes per CTA work item */
+#define VL_SCAN_QSTRIDE (VL_TILE_BYTES / VL_SCAN_UNROLL)                          /* distance between a thread's loads of one round */
 
 // work item -> its tiles: tile_block[t] = block, tile_off[t] = first byte of the tile inside the block's data
 static __global__ void k_expand_tiles(BatchView B, int slot, const uint32_t* __restrict__ work_blocks, const uint32_t* __restrict__ tile_prefix,
@@ -544,19 +545,21 @@ static __global__ void __launch_bounds__(VL_SCAN_THREADS) k_substr_scan(DevProgr
         const uint8_t* __restrict__ data = B.arena + c.data_off;
 #pragma unroll 1
         for (int round = 0; round < VL_SCAN_ROUNDS; round++) {
-            const uint32_t round0 = tile0 + (uint32_t)round * (VL_SCAN_THREADS * 16 * VL_SCAN_UNROLL);
+            // round r covers the r-th 4 KiB slice of each of the four 16 KiB quarters of the tile: a thread's 4 loads are 16 KiB apart,
+            // which spreads the requests of a warp over more L2 slices / HBM channels than 4 adjacent 4 KiB slices would
+            const uint32_t round0 = tile0 + (uint32_t)round * (VL_SCAN_THREADS * 16);
             if (round0 >= n) break;                           // uniform: the whole round lies past the data
             const uint32_t base = round0 + threadIdx.x * 16;
             uint4 v[VL_SCAN_UNROLL];
 #pragma unroll
             for (int u = 0; u < VL_SCAN_UNROLL; u++) {
-                uint32_t p = base + u * (VL_SCAN_THREADS * 16);
+                uint32_t p = base + u * VL_SCAN_QSTRIDE;
                 // payloads keep >= 32 readable bytes past data_len: a vector load that starts before n is always in bounds
                 v[u] = p < n ? __ldg((const uint4*)(data + p)) : make_uint4(0, 0, 0, 0);
             }
 #pragma unroll
             for (int u = 0; u < VL_SCAN_UNROLL; u++) {
-                const uint32_t p = base + u * (VL_SCAN_THREADS * 16);
+                const uint32_t p = base + u * VL_SCAN_QSTRIDE;
                 uint32_t nx = __shfl_down_sync(0xffffffffu, v[u].x, 1);
                 if (lane_id() == 31) nx = (p + 16 < n) ? __ldg((const uint32_t*)(data + p + 16)) : 0;
                 const uint32_t w[5] = {v[u].x, v[u].y, v[u].z, v[u].w, nx};
@@ -574,6 +577,119 @@ static __global__ void __launch_bounds__(VL_SCAN_THREADS) k_substr_scan(DevProgr
                 }
             }
         }
+    }
+}
+
+// ---- the same scan with TMA staging: cp.async.bulk (UBLKCP) global -> shared through a 4-stage mbarrier ring -----------------------------------
+// Bytes in flight no longer depend on how many registers hold pending loads: one elected thread keeps up to 3 x 16 KiB bulk copies per CTA
+// outstanding while all eight warps compare windows out of shared memory (conflict-free LDS.128; the 4 bytes that continue a vector are
+// simply the next word in shared memory, so no shuffles).  3 CTAs / SM x 3 x 16 KiB = 144 KiB in flight per SM.
+#define VL_TMA_STAGES 4
+#define VL_TMA_CHUNK 16384u
+#define VL_TMA_STRIDE (VL_TMA_CHUNK + 128u)   /* 16-byte header + chunk + the 16 continuation bytes, padded to 128 */
+#define VL_TMA_SMEM (VL_TMA_STAGES * VL_TMA_STRIDE + 128u)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile("{\n .reg .pred p;\n WAIT_LOOP:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra WAIT_DONE;\n bra WAIT_LOOP;\n WAIT_DONE:\n}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// work item -> its 16 KiB chunks: source offset in the arena, valid bytes, owning block, first byte inside the block's data
+struct ChunkDesc { uint64_t src; uint32_t block, off, len, pad; };
+static __global__ void k_expand_chunks(BatchView B, int slot, const uint32_t* __restrict__ work_blocks, const uint32_t* __restrict__ chunk_prefix,
+                                       const uint32_t* __restrict__ work_count, ChunkDesc* __restrict__ chunks) {
+    const uint32_t nwork = work_count[0];
+    for (uint32_t j = blockIdx.x; j < nwork; j += gridDim.x) {
+        const uint32_t first = chunk_prefix[j], cnt = chunk_prefix[j + 1] - first, b = work_blocks[j];
+        const DevColumn& c = B.cols[(uint64_t)b * B.nfields + slot];
+        for (uint32_t k = threadIdx.x; k < cnt; k += blockDim.x) {
+            ChunkDesc d; d.block = b; d.off = k * VL_TMA_CHUNK; d.src = c.data_off + d.off;
+            d.len = (uint32_t)min((uint64_t)VL_TMA_CHUNK, c.data_len - d.off); d.pad = 0;
+            chunks[first + k] = d;
+        }
+    }
+}
+
+template <bool FULL4>
+static __global__ void __launch_bounds__(VL_SCAN_THREADS, 3) k_substr_scan_tma(DevProgram P, BatchView B, int slot, ScanParams sp, const ChunkDesc* __restrict__ chunks,
+                                                                               const uint32_t* __restrict__ work_count, const uint32_t* __restrict__ row_off64,
+                                                                               uint64_t* __restrict__ leaf_bm) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t nchunks = work_count[1];
+    const uint32_t n4 = sp.n4, m4 = sp.m4;
+    const uint32_t sbase = smem_u32(smem);
+    // per stage: [0,16) header {block, off, len, -}, [16, 16+CHUNK+16) bytes
+    const uint32_t bars = sbase + VL_TMA_STAGES * VL_TMA_STRIDE;   // full[0..3] then empty[0..3], 8 bytes each
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < VL_TMA_STAGES; s++) { mbar_init(bars + 8 * s, 1); mbar_init(bars + 8 * (VL_TMA_STAGES + s), VL_SCAN_THREADS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // this CTA's chunks: q = blockIdx.x + i * gridDim.x
+    const uint32_t mine_cnt = nchunks > blockIdx.x ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    uint32_t issued = 0;
+    ChunkDesc next_desc;                                       // producer: descriptor of chunk `issued`, fetched one step ahead
+    if (threadIdx.x == 0 && mine_cnt) next_desc = chunks[blockIdx.x];
+    auto produce = [&]() {   // thread 0 only
+        if (issued >= mine_cnt) return;
+        const ChunkDesc d = next_desc;
+        if (issued + 1 < mine_cnt) next_desc = chunks[blockIdx.x + (uint64_t)(issued + 1) * gridDim.x];   // overlaps with the wait below
+        const uint32_t stage = issued % VL_TMA_STAGES, round = issued / VL_TMA_STAGES;
+        mbar_wait(bars + 8 * (VL_TMA_STAGES + stage), (round & 1) ^ 1);                  // all warps released this stage
+        uint32_t* hdr = (uint32_t*)(smem + stage * VL_TMA_STRIDE);
+        hdr[0] = d.block; hdr[1] = d.off; hdr[2] = d.len;
+        // the chunk plus the 16 bytes that continue its last vector; payloads keep >= 32 readable bytes past data_len
+        const uint32_t bytes = ((d.len + 15u) & ~15u) + 16u;
+        mbar_expect_tx(bars + 8 * stage, bytes);
+        tma_bulk_g2s(sbase + stage * VL_TMA_STRIDE + 16, B.arena + d.src, bytes, bars + 8 * stage);
+        issued++;
+    };
+    if (threadIdx.x == 0) for (int s = 0; s < VL_TMA_STAGES - 1; s++) produce();
+    for (uint32_t consumed = 0; consumed < mine_cnt; consumed++) {
+        const uint32_t stage = consumed % VL_TMA_STAGES, round = consumed / VL_TMA_STAGES;
+        if (threadIdx.x == 0) produce();                                                 // keep STAGES-1 copies in flight
+        mbar_wait(bars + 8 * stage, round & 1);                                          // bytes have landed
+        const uint8_t* buf = smem + stage * VL_TMA_STRIDE + 16;
+        const uint32_t* hdr = (const uint32_t*)(smem + stage * VL_TMA_STRIDE);
+        const uint32_t b = hdr[0], off = hdr[1], len = hdr[2];
+        bool mine = false;
+        uint4 v[4]; uint32_t nx[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) v[u] = *(const uint4*)(buf + (u * VL_SCAN_THREADS + threadIdx.x) * 16);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t i = (u * VL_SCAN_THREADS + threadIdx.x) * 16;
+            nx[u] = __shfl_down_sync(0xffffffffu, v[u].x, 1);
+            if (lane_id() == 31) nx[u] = *(const uint32_t*)(buf + i + 16);
+            const uint32_t w[5] = {v[u].x, v[u].y, v[u].z, v[u].w, nx[u]};
+            mine |= i < len && scan_any_window<FULL4>(w, n4, m4);
+        }
+        uint32_t vote = __ballot_sync(0xffffffffu, mine);
+        if (vote) {                                           // rare: verify the candidates of one lane with the whole warp
+            const DevColumn& c = B.cols[(uint64_t)b * B.nfields + slot];
+            while (vote) {
+                const int src = __ffs(vote) - 1; vote &= vote - 1;
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t i = (u * VL_SCAN_THREADS + (threadIdx.x & ~31u) + src) * 16;
+                    const uint32_t w[5] = {v[u].x, v[u].y, v[u].z, v[u].w, nx[u]};
+                    uint32_t cand = lane_id() == (uint32_t)src && i < len ? scan_window_mask(w, n4, m4) : 0;
+                    cand = __shfl_sync(0xffffffffu, cand, src);
+                    while (cand) {
+                        const int k = __ffs(cand) - 1; cand &= cand - 1;
+                        scan_verify_warp(P, B, c, sp, b, row_off64, off + i + k, leaf_bm);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane_id() == 0) mbar_arrive(bars + 8 * (VL_TMA_STAGES + stage));            // this warp is done with the stage
     }
 }
 
