@@ -164,7 +164,7 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
-    from victorialogs_b200 import scan as vs
+    from victorialogs_b200 import scan as vs, shard
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; libvlscan has no CPU fallback")
@@ -190,7 +190,7 @@ def main():
             _, _, totals = ctx.result_device_ptrs()
             with torch.cuda.stream(stream):
                 t = torch.as_tensor(_Arr(totals), device="cuda")
-                dist.all_reduce(t)     # the only collective of the path: final reduce of the match counters
+                shard.reduce_counters(t)     # the only collective of the path: final NCCL reduce of the match counters
 
     def sync_all():
         if world > 1:
