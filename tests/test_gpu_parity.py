@@ -224,3 +224,28 @@ def test_malformed_blocks_are_rejected(env):
     # the context stays usable afterwards
     got, counts, st = pu.gpu_rows(ctx, vs.Filter.phrase("f", "row"), [blk])
     assert len(got[0]) == 100
+
+
+def test_block_result_style_inputs(env):
+    """pipeFilter / applyToBlockResult shape (lib/logstorage/pipe_filter.go:73-97): already-decoded columns, no bloom filters,
+    no meaningful min/max.  An empty bloom matches everything (bloomfilter.go:175-177) and the widest min/max never prune, so the
+    same predicates must yield the same bits as the blockSearch path."""
+    oracle, vs, pu, ctx = env
+    n = 200
+    cols = [("u16", [b"%d" % (i * 37 % 60000) for i in range(n)]), ("i64", [b"%d" % ((i - 100) * 987654321) for i in range(n)]),
+            ("ip", [b"10.%d.%d.%d" % (i % 3, i % 251, (i * 7) % 256) for i in range(n)]), ("lvl", [[b"info", b"warn", b"error"][i % 3] for i in range(n)]),
+            ("msg", [b"row %d has status %d" % (i, 200 + i % 5) for i in range(n)])]
+    blk = oracle.Block.from_columns(cols)
+    d = pu.oracle_block_to_desc(blk, "decoded")
+    widest = {4: (0, 2**16 - 1), 10: (2**63, 2**63 - 1), 8: (0, 2**32 - 1)}
+    for c in d["columns"]:
+        c["bloom"] = b""
+        if c.get("value_type") in widest:
+            c["min_value"], c["max_value"] = widest[c["value_type"]]
+    hb = vs.HostBlocks(pu.field_names_of([blk]), [d])
+    F, G = oracle.Filter, vs.Filter
+    for kind, field, arg in [("phrase", "u16", "37"), ("exact", "i64", "-987654321"), ("prefix", "ip", "10.2"), ("phrase", "lvl", "error"), ("phrase", "msg", "203"),
+                             ("prefix", "msg", "sta"), ("regexp", "msg", "row 1.* 20[12]"), ("phrase", "msg", "absent")]:
+        want = oracle.bitmap_rows(blk.search(getattr(F, kind)(field, arg)), blk.rows)
+        words, counts, st = ctx.scan_batch(vs.Program(getattr(G, kind)(field, arg)), hb)
+        assert oracle.bitmap_rows(np.ascontiguousarray(words), blk.rows) == want, (kind, field, arg)

@@ -395,10 +395,11 @@ struct ScanRun {
                 VL_CUDA(cudaEventRecord(evp.second, ctx->stream));
             }
             // per-row matcher (string exact / in / general regexp; numeric columns through text)
-            if ((has_string && L.str_strategy == STR_ROW) || has_numeric) {
+            // (also the fallback of scan leaves for blocks with short rows, see k_plan_leaf); persistent grid over the ACT_ROW work list
+            if ((has_string && L.str_strategy != STR_ALL) || has_numeric) {
                 k_build_worklist<<<1, 1024, 0, ctx->stream>>>(B, slot, action, (uint8_t)ACT_ROW, (uint32_t)VL_TILE_BYTES, wb, tp, wc, stats, 0); launch_check(ctx);
                 k_lens_offsets<<<persistent, 256, 0, ctx->stream>>>(B, slot, wb, wc, ro, ready, stats); launch_check(ctx);
-                k_row_match<<<cdiv(B.nwords * 32, 256), 256, 0, ctx->stream>>>(P, B, (uint32_t)leaf_idx, slot, action, payload, ro, leaf_bm); launch_check(ctx);
+                k_row_match<<<persistent, 256, 0, ctx->stream>>>(P, B, (uint32_t)leaf_idx, slot, wb, wc, payload, ro, leaf_bm); launch_check(ctx);
             }
             if (has_dict || has_numeric) { k_word_match<<<cdiv(B.nwords, 128), 128, 0, ctx->stream>>>(P, B, (uint32_t)leaf_idx, slot, action, payload, leaf_bm, stats); launch_check(ctx); }
         }
@@ -525,6 +526,7 @@ void vlscan_ctx_free(vlscan_ctx* ctx) {
     for (auto& r : ctx->row_off64) r.release();
     for (auto& r : ctx->ready) r.release();
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    delete ctx->recycle;
     for (auto& e : ctx->scan_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
     if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
@@ -672,16 +674,20 @@ int vlscan_result_device_ptrs(vlscan_ctx* ctx, void** bitmap_words, void** match
 
 int vlscan_scan_batch(vlscan_ctx* ctx, const vlscan_program* prog, const char* const* field_names, const size_t* field_name_lens, uint32_t nfields,
                       const vlscan_block* blocks, uint64_t nblocks, uint64_t* out_bitmap_words, uint32_t* out_match_counts, vlscan_stats* stats) {
-    vlscan_batch* b = nullptr;
-    int rc = vlscan_batch_upload(ctx, field_names, field_name_lens, nfields, blocks, nblocks, &b, stats);
-    if (rc) return rc;
-    rc = vlscan_scan_resident(ctx, prog, b, nullptr);
+    // the staging batch (HBM arena + descriptor tables) is recycled across calls of this ctx: a search worker submits batch after
+    // batch, so cudaMalloc / cudaFree of a multi-GB arena per call would sit on the critical path
+    vlscan_batch* b = ctx->recycle ? ctx->recycle : new vlscan_batch();
+    ctx->recycle = nullptr;
+    b->field_names.clear(); b->slot_vt_mask.clear();
+    uint64_t launches0 = ctx->launches;
+    int rc = guarded(ctx, [&] { do_upload(ctx, field_names, field_name_lens, nfields, blocks, nblocks, b, stats); });
+    if (!rc) rc = vlscan_scan_resident(ctx, prog, b, nullptr);
     if (!rc) rc = vlscan_fetch_results(ctx, out_bitmap_words, out_match_counts, stats);
     if (!rc && stats) {
-        rc = guarded(ctx, [&] { read_stats(ctx, stats, true); stats->blocks += b->nblocks; stats->rows += b->rows; });
+        rc = guarded(ctx, [&] { read_stats(ctx, stats, true); stats->blocks += b->nblocks; stats->rows += b->rows; stats->gpu_launches += ctx->launches - launches0; });
     }
     ctx->has_result = false; ctx->last_batch = nullptr;
-    vlscan_batch_free(b);
+    ctx->recycle = b;
     return rc;
 }
 

@@ -84,6 +84,7 @@ struct vlscan_ctx {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> scan_events; size_t scan_events_used = 0;
     // last scan
     const vlscan_batch* last_batch = nullptr;
+    vlscan_batch* recycle = nullptr;       // staging batch reused by vlscan_scan_batch
     bool has_result = false;
     uint64_t last_launches = 0;
     int sm_count = 148;

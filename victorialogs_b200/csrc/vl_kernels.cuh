@@ -28,6 +28,7 @@ struct BatchView {
 };
 
 static __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+#define VL_SHORT_ROW_BYTES 48u   /* average row length below which a string block is matched per row instead of row-agnostically */
 static __device__ __forceinline__ uint32_t width_of_vt(uint32_t vt) {
     switch (vt) { case VT_DICT: case VT_UINT8: return 1; case VT_UINT16: return 2; case VT_UINT32: case VT_IPV4: return 4; case VT_UINT64: case VT_FLOAT64: case VT_ISO8601: case VT_INT64: return 8; }
     return 0;
@@ -90,6 +91,7 @@ static __device__ bool regex_match(const DevRegex& R, const uint8_t* blob, const
     if (R.dot_plus) return n > rem;
     if (R.sub_kind == 1) return find_bytes(s + rem, n - rem, sub, sl, 0) >= 0;
     if (R.sub_kind == 2) { int m = find_bytes(s + rem, n - rem, sub, sl, 0); return m > 0 && (uint32_t)m + sl < n - rem; }
+    if (R.tail_len) return find_bytes(s + rem, n - rem, blob + R.tail_off, R.tail_len, 0) >= 0;   // `.*LIT` after the first prefix occurrence
     for (;;) {
         if (dfa_run(R, blob, s + rem, n - rem)) return true;
         k = find_bytes(s, n, pre, pl, (uint32_t)k + 1);
@@ -266,7 +268,12 @@ static __global__ void k_plan_leaf(DevProgram P, BatchView B, uint32_t leaf_idx,
             } else ok = probe(H, L.nhashes);
             if (!ok) act = ACT_NONE;
             else if (c->data_const) act = leaf_match_string(P, L, B.arena + c->data_off, (uint32_t)c->data_len) ? ACT_ALL : ACT_NONE, values_bytes = 1;
-            else { act = L.str_strategy == STR_SCAN ? ACT_SCAN : L.str_strategy == STR_ALL ? ACT_ALL : ACT_ROW; values_bytes = 1; }
+            else {
+                act = L.str_strategy == STR_SCAN ? ACT_SCAN : L.str_strategy == STR_ALL ? ACT_ALL : ACT_ROW; values_bytes = 1;
+                // short rows (ids, paths, codes ...): candidates of the row-agnostic scan become dense relative to the bytes streamed and
+                // each costs a warp-wide verification, so such blocks take the per-row matcher instead (same predicate, same result)
+                if (act == ACT_SCAN && c->data_len < (uint64_t)VL_SHORT_ROW_BYTES * rows) act = ACT_ROW;
+            }
         } else {
             // numeric / ipv4 / iso8601 columns
             uint32_t w = width_of_vt(vt);
@@ -483,7 +490,21 @@ static __device__ __noinline__ void scan_verify_warp(const DevProgram& P, const 
     case SCAN_PREFIX: hit = phrase_boundaries_ok(s, len, p, L, sp.starts_tok, false); break;
     case SCAN_CONTAINS: hit = true; break;
     case SCAN_RX_DOTPLUS: hit = p + L < len; break;
-    default: hit = dfa_run(P.regexes[sp.regex], P.blob, s + p + L, len - p - L); break;   // SCAN_RX_SUFFIX
+    default: {                                                                              // SCAN_RX_SUFFIX
+        const DevRegex& R = P.regexes[sp.regex];
+        if (R.tail_len) {
+            // suffix `.*LIT`: the anchored automaton accepts iff LIT occurs in the remainder; lanes try start positions in parallel
+            const uint8_t* rem = s + p + L; const uint32_t rl = len - p - L, tl = R.tail_len; const uint8_t* lit = P.blob + R.tail_off;
+            bool found = false;
+            for (uint32_t i0 = 0; i0 + tl <= rl && !found; i0 += 32) {
+                uint32_t i = i0 + lane; bool eq = i + tl <= rl;
+                for (uint32_t k = 0; k < tl && eq; k++) eq = rem[i + k] == lit[k];
+                found = __any_sync(0xffffffffu, eq);
+            }
+            hit = found;
+        } else hit = dfa_run(R, P.blob, s + p + L, len - p - L);
+        break;
+    }
     }
     if (hit && lane == 0) atomicOr((unsigned long long*)&leaf_bm[w0 + (r >> 6)], 1ull << (r & 63));
 }
@@ -736,16 +757,19 @@ static __global__ void k_word_match(DevProgram P, BatchView B, uint32_t leaf_idx
 
 // ---- generic per-row matcher: one warp per bitmap word, lanes take rows l and l+32 ------------------------------------------------------------
 // exact / in() / regexp-without-literal-prefix on string columns; numeric columns that must be formatted to text first.
-static __global__ void k_row_match(DevProgram P, BatchView B, uint32_t leaf_idx, int slot, const uint8_t* __restrict__ action, const uint64_t* __restrict__ payload,
-                            const uint32_t* __restrict__ row_off64, uint64_t* __restrict__ leaf_bm) {
-    uint64_t gw = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (gw >= B.nwords) return;
-    uint32_t b = B.word_block[gw];
-    if (action[b] != ACT_ROW) return;
+// Persistent grid over the ACT_ROW work list: work item j = block work_blocks[j]; its bitmap words are dealt out to the CTA's warps.
+static __global__ void k_row_match(DevProgram P, BatchView B, uint32_t leaf_idx, int slot, const uint32_t* __restrict__ work_blocks,
+                                   const uint32_t* __restrict__ work_count, const uint64_t* __restrict__ payload,
+                                   const uint32_t* __restrict__ row_off64, uint64_t* __restrict__ leaf_bm) {
+  const uint32_t nwork = work_count[0];
+  const DevLeaf& L = P.leaves[leaf_idx];
+  for (uint32_t j = blockIdx.x; j < nwork; j += gridDim.x) {
+    const uint32_t b = work_blocks[j];
     const DevColumn& c = B.cols[(uint64_t)b * B.nfields + slot];
-    const DevLeaf& L = P.leaves[leaf_idx];
-    uint32_t rows = B.blk_rows[b];
-    uint32_t r0 = (uint32_t)(gw - B.blk_word_off[b]) * 64;
+    const uint32_t rows = B.blk_rows[b];
+    const uint64_t w_lo = B.blk_word_off[b], w_hi = B.blk_word_off[b + 1];
+   for (uint64_t gw = w_lo + (threadIdx.x >> 5); gw < w_hi; gw += blockDim.x >> 5) {
+    uint32_t r0 = (uint32_t)(gw - w_lo) * 64;
     const uint8_t* data = B.arena + c.data_off;
     const uint8_t* lens = B.arena + c.lens_off;
     uint32_t la = 0, lb = 0;
@@ -781,6 +805,8 @@ static __global__ void k_row_match(DevProgram P, BatchView B, uint32_t leaf_idx,
     if (rb < rows) hb = eval(ob, lb);
     uint32_t lo = __ballot_sync(0xffffffffu, ha), hi = __ballot_sync(0xffffffffu, hb);
     if (lane_id() == 0) leaf_bm[gw] = ((uint64_t)hi << 32) | lo;
+   }
+  }
 }
 
 // ---- fold a leaf result into the running bitmap -------------------------------------------------------------------------------------------------

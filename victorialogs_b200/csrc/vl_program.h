@@ -303,6 +303,7 @@ class ProgramBuilder {
         R.ascii_off = P.put_bytes(cr.suffix.ascii_class, 128);
         R.trans_off = P.put_bytes(cr.suffix.trans.data(), cr.suffix.trans.size() * 2, 2);
         R.accept_off = P.put_bytes(cr.suffix.accept_end.data(), cr.suffix.accept_end.size());
+        R.tail_off = P.put_bytes(cr.tailLiteral.data(), cr.tailLiteral.size()); R.tail_len = (uint32_t)cr.tailLiteral.size();
         P.regexes.push_back(R); P.host_regexes.push_back(cr);
         return (int)P.regexes.size() - 1;
     }

@@ -536,6 +536,7 @@ struct CompiledRegex {
     bool hasOrValues = false;          // informational; or-values are matched through the DFA (same language)
     RxDfa suffix;                      // anchored at the start of the remainder iff prefix != ""
     std::vector<std::string> literals; // GetLiterals() (regex.go:101-124), for bloom tokens
+    std::string tailLiteral;           // prefix != "" and suffix == `(?s:.*LIT)`: suffixRe.MatchString(rem) == strings.Contains(rem, LIT)
 
     static bool contains(const uint8_t* s, uint32_t n, const std::string& sub, uint32_t from = 0) { return find_bytes(s, n, (const uint8_t*)sub.data(), (uint32_t)sub.size(), from) >= 0; }
 
@@ -645,6 +646,9 @@ inline CompiledRegex compile_regex(const std::string& expr) {
     r.isSuffixDotPlus = rx_is_dot_rep(t, suffix, RX_PLUS);
     r.substrDotStar = rx_substring_literal(t, suffix, RX_STAR);
     r.substrDotPlus = rx_substring_literal(t, suffix, RX_PLUS);
+    if (!r.prefix.empty() && t.at(suffix).op == RX_SEQ && t.at(suffix).kids.size() == 2 && rx_is_dot_rep(t, t.at(suffix).kids[0], RX_STAR)) {
+        std::string tl; if (rx_plain_literal(t, t.at(suffix).kids[1], &tl) && !tl.empty()) r.tailLiteral = tl;
+    }
     int root = suffix;
     if (!r.prefix.empty()) { RxNode c; c.op = RX_SEQ; c.kids = {t.add(RX_BOT), suffix}; root = t.add(c); }
     r.suffix = RxCompiler(t).build(root);

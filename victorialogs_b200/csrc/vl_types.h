@@ -44,6 +44,7 @@ struct DevRegex {          // device image of CompiledRegex (vl_regex.h)
     uint32_t ascii_off;                // uint8[128]
     uint32_t trans_off;                // uint16[nstates*nclasses] (2-byte aligned)
     uint32_t accept_off;               // uint8[nstates]
+    uint32_t tail_off, tail_len;       // suffix == `.*LITERAL` (dot-all): the automaton accepts iff LITERAL occurs in the remainder
 };
 
 struct DevLeaf {
