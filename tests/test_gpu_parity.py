@@ -202,6 +202,46 @@ def test_block_shape_edge_cases(env):
     check(env, shapes["single row"], (F.noop(), G.noop()))
 
 
+def test_long_needles_all_alignments_and_tile_boundaries(env):
+    """Needles of 7+ bytes take the aligned-word filter (k_substr_scan_aligned): every byte alignment of an occurrence, occurrences
+    at row starts / ends, overlapping occurrences, and occurrences straddling the 4 KiB / 16 KiB / 64 KiB work-item boundaries."""
+    oracle, vs, pu, ctx = env
+    F, G = oracle.Filter, vs.Filter
+    rng = np.random.default_rng(7)
+    for needle in [b"timeout", b"timeouts", b"abcdefghi", b"aaaaaaaa", b"conn refused", b"0123456789abcdef0"]:
+        rows = []
+        for a in range(40):
+            pad = b"." * a
+            rows += [pad + needle, pad + needle + b" tail", pad + b"x" + needle, pad + needle + b"x", pad + b" " + needle + b" ", needle[:-1] + pad, needle + needle, needle[:3] + needle]
+        # long filler rows so that occurrences land on every kind of tile boundary: several 64 KiB tiles of data
+        filler = [bytes(rng.integers(97, 123, int(rng.integers(50, 200)), dtype=np.uint8)) for _ in range(2500)]
+        vals = []
+        for i, f in enumerate(filler):
+            vals.append(f)
+            if i % 7 == 0:
+                vals.append(rows[(i // 7) % len(rows)])
+        cols = [("f", vals)]
+        blk = oracle.Block.from_columns(cols)
+        _, data = oracle.decode_values_block(blk.columns[0].values_block)
+        assert len(data) > 200 * 1024
+        for kind in ("phrase", "prefix"):
+            check(env, [blk], (getattr(F, kind)("f", needle), getattr(G, kind)("f", needle)))
+        check(env, [blk], (F.regexp("f", needle.decode() + ".*"), G.regexp("f", needle.decode() + ".*")))
+        check(env, [blk], (F.regexp("f", needle.decode() + ".+tail"), G.regexp("f", needle.decode() + ".+tail")))
+    # an occurrence placed exactly across each boundary kind inside one huge row set
+    base = b"q" * 100
+    for boundary in (4096, 16384, 65536, 65536 + 4096):
+        for shift in range(-9, 3):
+            vals, total = [], 0
+            while total + 101 < boundary + shift - 50:
+                vals.append(base)
+                total += 100
+            vals.append(b"-" * (boundary + shift - total) + b"timeout here")
+            vals += [base] * 20
+            blk = oracle.Block.from_columns([("f", vals), ("g", [b"%d" % i for i in range(len(vals))])])
+            check(env, [blk], (F.phrase("f", "timeout"), G.phrase("f", "timeout")))
+
+
 def test_malformed_blocks_are_rejected(env):
     """Corrupt inputs return an error (the Go side turns it into logger.Panicf FATAL) instead of undefined behaviour."""
     oracle, vs, pu, ctx = env

@@ -372,6 +372,8 @@ struct ScanRun {
                 const uint8_t* nd = prog->p.blob.data() + L.scan_needle_off;
                 uint32_t k = std::min<uint32_t>(4, L.scan_needle_len);
                 for (uint32_t i = 0; i < k; i++) { sp.n4 |= (uint32_t)nd[i] << (8 * i); sp.m4 |= 0xFFu << (8 * i); }
+                const bool aligned_ok = L.scan_needle_len >= 7 && !getenv("VLSCAN_NO_ALIGNED");
+                if (aligned_ok) for (uint32_t s = 0; s < 4; s++) for (uint32_t i = 0; i < 4; i++) sp.sub4[s] |= (uint32_t)nd[s + i] << (8 * i);
                 if (L.scan_mode == SCAN_CONTAINS || L.scan_mode >= SCAN_RX_DOTPLUS) { sp.starts_tok = sp.ends_tok = 0; }
                 auto& evp = next_scan_events();
                 VL_CUDA(cudaEventRecord(evp.first, ctx->stream));
@@ -389,6 +391,10 @@ struct ScanRun {
                     // TMA-staged variant: cp.async.bulk global->shared through a 4-stage mbarrier ring (see vl_kernels.cuh)
                     if (L.scan_needle_len >= 4) k_substr_scan_tma<true><<<ctx->sm_count * std::max(occ_tma_full, 1), VL_SCAN_THREADS, VL_TMA_SMEM, ctx->stream>>>(P, B, slot, sp, chunks, wc, ro, leaf_bm);
                     else k_substr_scan_tma<false><<<ctx->sm_count * std::max(occ_tma_part, 1), VL_SCAN_THREADS, VL_TMA_SMEM, ctx->stream>>>(P, B, slot, sp, chunks, wc, ro, leaf_bm);
+                } else if (aligned_ok) {
+                    static int occ_al = 0;
+                    if (!occ_al) VL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_al, k_substr_scan_aligned, VL_SCAN_THREADS, 0));
+                    k_substr_scan_aligned<<<ctx->sm_count * std::max(occ_al, 1), VL_SCAN_THREADS, 0, ctx->stream>>>(P, B, slot, sp, tb, to, wc, ro, leaf_bm);
                 } else if (L.scan_needle_len >= 4) k_substr_scan<true><<<ctx->sm_count * std::max(occ_full, 1), VL_SCAN_THREADS, 0, ctx->stream>>>(P, B, slot, sp, tb, to, wc, ro, leaf_bm);
                 else k_substr_scan<false><<<ctx->sm_count * std::max(occ_part, 1), VL_SCAN_THREADS, 0, ctx->stream>>>(P, B, slot, sp, tb, to, wc, ro, leaf_bm);
                 launch_check(ctx);

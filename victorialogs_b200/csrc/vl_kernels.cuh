@@ -437,6 +437,7 @@ struct ScanParams {
     uint32_t mode;            // SCAN_*
     uint32_t needle_off, needle_len;
     uint32_t n4, m4;          // first min(4,L) needle bytes, little-endian packed, and the mask
+    uint32_t sub4[4];         // L >= 7: needle bytes [k, k+4) for k = 0..3 (aligned-word filter, see k_substr_scan)
     uint8_t starts_tok, ends_tok;
     int32_t regex;
 };
@@ -451,7 +452,7 @@ static __device__ __noinline__ void scan_verify_warp(const DevProgram& P, const 
     const uint32_t L = sp.needle_len, lane = lane_id();
     if ((uint64_t)pos + L > c.data_len) return;
     bool same = true;
-    for (uint32_t k = 4 + lane; k < L; k += 32) same &= data[pos + k] == nd[k];
+    for (uint32_t k = lane; k < L; k += 32) same &= data[pos + k] == nd[k];   // the filter only vouches for 4 of the L bytes
     if (!__all_sync(0xffffffffu, same)) return;
     // byte offset -> row
     const uint32_t rows = B.blk_rows[b];
@@ -594,6 +595,63 @@ static __global__ void __launch_bounds__(VL_SCAN_THREADS) k_substr_scan(DevProgr
                     while (cand) {
                         const int k = __ffs(cand) - 1; cand &= cand - 1;
                         scan_verify_warp(P, B, c, sp, b, row_off64, p0 + k, leaf_bm);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---- needles of 7+ bytes: aligned-word filter ------------------------------------------------------------------------------------------------
+// An occurrence at byte q covers the aligned word at a = (q + 3) & ~3 completely (a + 4 <= q + L when L >= 7), and that word equals needle bytes
+// [k, k+4) with k = a - q in 0..3.  So it suffices to compare every ALIGNED word of the stream with the four 4-byte needle substrings sub4[0..3]:
+// 16 compares per 16-byte vector and no funnel shifts, no neighbour word (the shifted-window filter needs 12 SHF + 16 ISETP + a shuffle).  A hit
+// on (word at a, k) is verified at q = a - k like any other candidate, so the result is identical.
+static __global__ void __launch_bounds__(VL_SCAN_THREADS, 5) k_substr_scan_aligned(DevProgram P, BatchView B, int slot, ScanParams sp, const uint32_t* __restrict__ tile_block,
+                                                                               const uint32_t* __restrict__ tile_off, const uint32_t* __restrict__ work_count,
+                                                                               const uint32_t* __restrict__ row_off64, uint64_t* __restrict__ leaf_bm) {
+    const uint32_t ntiles = work_count[1];
+    const uint32_t s0 = sp.sub4[0], s1 = sp.sub4[1], s2 = sp.sub4[2], s3 = sp.sub4[3];
+    for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const uint32_t b = __ldg(tile_block + t), tile0 = __ldg(tile_off + t);
+        const DevColumn& c = B.cols[(uint64_t)b * B.nfields + slot];
+        const uint32_t n = (uint32_t)c.data_len;
+        const uint8_t* __restrict__ data = B.arena + c.data_off;
+#pragma unroll 1
+        for (int round = 0; round < VL_SCAN_ROUNDS; round++) {
+            const uint32_t round0 = tile0 + (uint32_t)round * (VL_SCAN_THREADS * 16);
+            if (round0 >= n) break;
+            const uint32_t base = round0 + threadIdx.x * 16;
+            uint4 v[VL_SCAN_UNROLL];
+#pragma unroll
+            for (int u = 0; u < VL_SCAN_UNROLL; u++) {
+                uint32_t p = base + u * VL_SCAN_QSTRIDE;
+                v[u] = p < n ? __ldg((const uint4*)(data + p)) : make_uint4(0, 0, 0, 0);
+            }
+            bool mine = false;
+#pragma unroll
+            for (int u = 0; u < VL_SCAN_UNROLL; u++) {
+                const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                for (int i = 0; i < 4; i++) mine |= w[i] == s0 || w[i] == s1 || w[i] == s2 || w[i] == s3;
+            }
+            uint32_t vote = __ballot_sync(0xffffffffu, mine);   // zero padding past n never equals a needle substring that passes verification
+            while (vote) {
+                const int src = __ffs(vote) - 1; vote &= vote - 1;
+                const uint32_t pb = __shfl_sync(0xffffffffu, base, src);
+#pragma unroll
+                for (int u = 0; u < VL_SCAN_UNROLL; u++) {
+                    const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+                    uint32_t cand = 0;   // bit i*4+k: aligned word i equals needle substring k
+                    if (lane_id() == (uint32_t)src) {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) cand |= ((uint32_t)(w[i] == s0) | (uint32_t)(w[i] == s1) << 1 | (uint32_t)(w[i] == s2) << 2 | (uint32_t)(w[i] == s3) << 3) << (4 * i);
+                    }
+                    cand = __shfl_sync(0xffffffffu, cand, src);
+                    while (cand) {
+                        const int bit = __ffs(cand) - 1; cand &= cand - 1;
+                        const uint32_t a = pb + u * VL_SCAN_QSTRIDE + 4 * (bit >> 2), k = bit & 3;
+                        if (a >= k && a < n) scan_verify_warp(P, B, c, sp, b, row_off64, a - k, leaf_bm);
                     }
                 }
             }
