@@ -628,30 +628,34 @@ static __global__ void __launch_bounds__(VL_SCAN_THREADS, 5) k_substr_scan_align
                 uint32_t p = base + u * VL_SCAN_QSTRIDE;
                 v[u] = p < n ? __ldg((const uint4*)(data + p)) : make_uint4(0, 0, 0, 0);
             }
-            bool mine = false;
+            bool hit[VL_SCAN_UNROLL];
 #pragma unroll
             for (int u = 0; u < VL_SCAN_UNROLL; u++) {
                 const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+                hit[u] = false;
 #pragma unroll
-                for (int i = 0; i < 4; i++) mine |= w[i] == s0 || w[i] == s1 || w[i] == s2 || w[i] == s3;
+                for (int i = 0; i < 4; i++) hit[u] |= w[i] == s0 || w[i] == s1 || w[i] == s2 || w[i] == s3;
             }
-            uint32_t vote = __ballot_sync(0xffffffffu, mine);   // zero padding past n never equals a needle substring that passes verification
-            while (vote) {
-                const int src = __ffs(vote) - 1; vote &= vote - 1;
-                const uint32_t pb = __shfl_sync(0xffffffffu, base, src);
+            // zero padding past n never equals a needle substring that passes verification
+            if (__ballot_sync(0xffffffffu, hit[0] | hit[1] | hit[2] | hit[3])) {   // rare: some lane of this warp holds a candidate
 #pragma unroll
                 for (int u = 0; u < VL_SCAN_UNROLL; u++) {
-                    const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-                    uint32_t cand = 0;   // bit i*4+k: aligned word i equals needle substring k
-                    if (lane_id() == (uint32_t)src) {
+                    uint32_t vote = __ballot_sync(0xffffffffu, hit[u]);
+                    while (vote) {                               // the warp verifies the candidates of lane `src`, vector u, together
+                        const int src = __ffs(vote) - 1; vote &= vote - 1;
+                        const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+                        uint32_t cand = 0;   // bit i*4+k: aligned word i equals needle substring k
+                        if (lane_id() == (uint32_t)src) {
 #pragma unroll
-                        for (int i = 0; i < 4; i++) cand |= ((uint32_t)(w[i] == s0) | (uint32_t)(w[i] == s1) << 1 | (uint32_t)(w[i] == s2) << 2 | (uint32_t)(w[i] == s3) << 3) << (4 * i);
-                    }
-                    cand = __shfl_sync(0xffffffffu, cand, src);
-                    while (cand) {
-                        const int bit = __ffs(cand) - 1; cand &= cand - 1;
-                        const uint32_t a = pb + u * VL_SCAN_QSTRIDE + 4 * (bit >> 2), k = bit & 3;
-                        if (a >= k && a < n) scan_verify_warp(P, B, c, sp, b, row_off64, a - k, leaf_bm);
+                            for (int i = 0; i < 4; i++) cand |= ((uint32_t)(w[i] == s0) | (uint32_t)(w[i] == s1) << 1 | (uint32_t)(w[i] == s2) << 2 | (uint32_t)(w[i] == s3) << 3) << (4 * i);
+                        }
+                        cand = __shfl_sync(0xffffffffu, cand, src);
+                        const uint32_t pb = __shfl_sync(0xffffffffu, base, src) + u * VL_SCAN_QSTRIDE;
+                        while (cand) {
+                            const int bit = __ffs(cand) - 1; cand &= cand - 1;
+                            const uint32_t a = pb + 4 * (bit >> 2), k = bit & 3;
+                            if (a >= k && a < n) scan_verify_warp(P, B, c, sp, b, row_off64, a - k, leaf_bm);
+                        }
                     }
                 }
             }
