@@ -210,6 +210,12 @@ def main():
         step()
     ev1.record(stream)
     sync_all()
+    # the timed region is a few tens of milliseconds, shorter than one nvidia-smi sampling period: keep the same load running (untimed)
+    # until the sampler has seen ~1 s of it, so that `clocks` really is the SM clock / throttle state under this workload
+    t_hold = time.perf_counter()
+    while time.perf_counter() - t_hold < 1.0:
+        ctx.scan_resident(prog, batch, want_stats=False)
+        ctx.sync()
     clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1)
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")

@@ -466,8 +466,16 @@ static __device__ __noinline__ void scan_verify_warp(const DevProgram& P, const 
     } else {
         const uint8_t* lens = B.arena + c.lens_off;
         uint32_t nw = (uint32_t)(B.blk_word_off[b + 1] - w0);
+        // last bitmap word whose first row starts at or before pos: binary search down to a 64-entry window (no step at all for blocks
+        // of <= 4096 rows), then one parallel probe of that window -- one memory round trip instead of log2(nw) dependent ones
         uint32_t lo = 0, hi = nw - 1;
-        while (lo < hi) { uint32_t mid = (lo + hi + 1) >> 1; if (row_off64[w0 + mid] <= pos) lo = mid; else hi = mid - 1; }
+        while (hi - lo >= 64) { uint32_t mid = (lo + hi + 1) >> 1; if (row_off64[w0 + mid] <= pos) lo = mid; else hi = mid - 1; }
+        {
+            const uint32_t ia0 = lo + lane, ib0 = lo + 32 + lane;
+            const uint32_t oa = ia0 <= hi ? row_off64[w0 + ia0] : 0xFFFFFFFFu, ob = ib0 <= hi ? row_off64[w0 + ib0] : 0xFFFFFFFFu;
+            const uint32_t ma = __ballot_sync(0xffffffffu, oa <= pos), mb = __ballot_sync(0xffffffffu, ob <= pos);
+            lo += mb ? 32 + (31 - __clz(mb)) : (ma ? 31 - __clz(ma) : 0);   // offsets are non-decreasing: the predicate is a prefix of ones
+        }
         const uint32_t r0 = lo * 64, base = row_off64[w0 + lo];
         const uint32_t ra = r0 + lane, rb = r0 + 32 + lane;
         uint32_t la = ra < rows ? row_len(c, lens, ra) : 0, lb = rb < rows ? row_len(c, lens, rb) : 0;
