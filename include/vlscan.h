@@ -137,6 +137,10 @@ uint32_t vlscan_program_nfields(const vlscan_program* prog);
 const char* vlscan_program_field(const vlscan_program* prog, uint32_t i, size_t* len);
 /* token strings of a leaf (tests; mirrors filterPhrase.getTokens() etc.), '\n'-joined into buf; returns length or -1 */
 int64_t vlscan_program_leaf_tokens(const vlscan_program* prog, uint32_t leaf, char* buf, size_t cap);
+/* text of a float64 column value as the filters see it: marshalFloat64String (values_encoder.go:1397-1399), i.e.
+ * strconv.AppendFloat(f, 'f', -1, 64).  Host build of the routine the scan kernels run per row; returns the length
+ * (<= 344) or -1 when cap is too small.  No NUL terminator is written. */
+int vlscan_format_float64(uint64_t ieee_bits, char* buf, size_t cap);
 
 /* ---- batches ---------------------------------------------------------------------------------------------------- */
 /* Stage `nblocks` blocks into HBM (host pointers in, pinned staging + cudaMemcpyAsync inside).  Field names are the

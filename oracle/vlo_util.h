@@ -646,13 +646,23 @@ inline void marshal_ipv4_string(std::string& dst, uint32_t n) {
     marshal_uint64_string(dst, n >> 24); dst.push_back('.'); marshal_uint64_string(dst, (n >> 16) & 0xFF); dst.push_back('.');
     marshal_uint64_string(dst, (n >> 8) & 0xFF); dst.push_back('.'); marshal_uint64_string(dst, n & 0xFF);
 }
-// strconv.AppendFloat(dst, f, 'f', -1, 64): shortest round-trip digits, fixed notation (== std::to_chars fixed shortest).
+// strconv.AppendFloat(dst, f, 'f', -1, 64): the shortest round-trip DIGITS (strconv ftoa.go: shortest → %e digits), laid out
+// by fmtF in fixed notation: integer digits beyond the shortest ones are '0' (1.7976931348623157e308 prints as
+// 17976931348623157 followed by 292 zeros, not as the exact binary value, which is what to_chars(fixed) would print).
 inline void marshal_float64_string(std::string& dst, double f) {
     if (std::isnan(f)) { dst.append("NaN"); return; }
     if (std::isinf(f)) { dst.append(f > 0 ? "+Inf" : "-Inf"); return; }
-    char b[400];
-    auto r = std::to_chars(b, b + sizeof(b), f, std::chars_format::fixed);
-    dst.append(b, r.ptr);
+    if (std::signbit(f)) { dst.push_back('-'); f = -f; }
+    if (f == 0) { dst.push_back('0'); return; }
+    char b[64];
+    auto r = std::to_chars(b, b + sizeof(b), f, std::chars_format::scientific);   // d[.ddd]e[+-]XX, shortest digits
+    std::string digs; int e10 = 0; char* p = b;
+    for (; p < r.ptr && *p != 'e'; p++) if (*p != '.') digs.push_back(*p);
+    e10 = atoi(std::string(p + 1, r.ptr).c_str());
+    int point = e10 + 1;   // number of digits before the decimal point
+    if (point <= 0) { dst.append("0."); dst.append((size_t)-point, '0'); dst.append(digs); return; }
+    if ((size_t)point >= digs.size()) { dst.append(digs); dst.append((size_t)point - digs.size(), '0'); return; }
+    dst.append(digs, 0, (size_t)point); dst.push_back('.'); dst.append(digs, (size_t)point, std::string::npos);
 }
 // marshalTimestampISO8601String :1414-1418: time.Unix(0,nsecs).UTC().AppendFormat("2006-01-02T15:04:05.000Z")
 inline void marshal_timestamp_iso8601_string(std::string& dst, int64_t nsecs) {

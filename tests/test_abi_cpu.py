@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "vlscan.h")).read()
-    declared = sorted(set(re.findall(r"\b(vlscan_[a-z_]+)\s*\(", hdr)))
+    declared = sorted(set(re.findall(r"\b(vlscan_[a-z0-9_]+)\s*\(", hdr)))
     assert len(declared) >= 25
     L = vs.lib()
     for name in declared:
@@ -60,6 +60,29 @@ def test_program_fields_and_errors():
 def test_and_or_trees_compile():
     for q, cols, f, want in and_or_cases(vs.Filter):
         vs.Program(f)
+
+
+def test_format_float64_matches_oracle_and_golden(oracle):
+    # host build of the per-row float64 -> text routine of the scan kernels (marshalFloat64String, values_encoder.go:1397-1399)
+    import json, random, struct
+    here = os.path.dirname(os.path.abspath(__file__))
+    table = json.load(open(os.path.join(here, "golden", "func_tables.json")))["TestMarshalFloat64String"]
+    for f, want in table:   # values_encoder_test.go TestMarshalFloat64String
+        bits = struct.unpack(">Q", struct.pack(">d", float(bytes.fromhex(f["hex"]) if "hex" in f else f["num"])))[0]
+        assert vs.format_float64(bits) == bytes.fromhex(want["hex"])
+    rng = random.Random(20240922)
+    cases = [0, 1 << 63, 1, 0x7FEFFFFFFFFFFFFF, 0x7FF0000000000000, 0xFFF0000000000000, 0x7FF8000000000000, 0x0010000000000000, 0x000FFFFFFFFFFFFF]
+    cases += [rng.getrandbits(64) for _ in range(20000)]
+    cases += [rng.getrandbits(52) for _ in range(2000)]   # subnormals
+    cases += [struct.unpack(">Q", struct.pack(">d", rng.randint(-10**9, 10**9) / 10 ** rng.randint(0, 9)))[0] for _ in range(20000)]
+    cases += [struct.unpack(">Q", struct.pack(">d", float("%de%d" % (m, e))))[0] for e in range(-330, 310) for m in (1, 5, 9)]
+    cases += [(e << 52) | m for e in range(0, 2047, 3) for m in (0, 1, (1 << 52) - 1)]
+    for bits in cases:
+        x = struct.unpack(">d", struct.pack(">Q", bits))[0]
+        if x != x:
+            assert vs.format_float64(bits) == b"NaN"
+            continue
+        assert vs.format_float64(bits) == oracle.encoded_to_string(7, struct.pack(">Q", bits)), hex(bits)
 
 
 def test_no_cpu_fallback():

@@ -38,20 +38,12 @@ def check(env, columns_or_blocks, spec_or_pair, stage="ondisk"):
 def test_reference_filter_tables_on_gpu(env):
     """388 cases of filter_{phrase,prefix,exact,in,regexp,not}_test.go, on-disk stage (ZSTD decoded by the host stager)."""
     oracle, vs, pu, ctx = env
-    unsupported = 0
     for c in CASES:
         b = oracle.Block.from_columns(c["columns"])
         of, gf = build_filter(oracle.Filter, c["filter"]), build_filter(vs.Filter, c["filter"])
-        try:
-            got, counts, st = pu.gpu_rows(ctx, gf, [b])
-        except vs.VlscanError as e:
-            # declared limitation: phrase / prefix / regexp over float64 columns needs float -> text formatting on the device
-            assert "float64" in str(e), (c["src"], c["filter"], str(e))
-            unsupported += 1
-            continue
+        got, counts, st = pu.gpu_rows(ctx, gf, [b])
         assert got[0] == c["expected"], (c["src"], c["filter"])
         assert int(counts[0]) == len(c["expected"])
-    assert unsupported <= 40, unsupported
 
 
 def test_reference_filter_tables_decoded_stage(env):
@@ -59,11 +51,7 @@ def test_reference_filter_tables_decoded_stage(env):
     for c in CASES[::7]:
         b = oracle.Block.from_columns(c["columns"])
         gf = build_filter(vs.Filter, c["filter"])
-        try:
-            got, counts, st = pu.gpu_rows(ctx, gf, [b], stage="decoded")
-        except vs.VlscanError as e:
-            assert "float64" in str(e)
-            continue
+        got, counts, st = pu.gpu_rows(ctx, gf, [b], stage="decoded")
         assert got[0] == c["expected"], (c["src"], c["filter"])
 
 
@@ -174,6 +162,18 @@ def test_numeric_and_special_columns(env):
                         ("u8", []), ("ts", ["2024-03-05T12:04:28.004Z"])]:
         check(env, [blk], (F.in_(field, vals), G.in_(field, vals)))
     # combinators across column kinds
+    # float64 column: phrase / prefix / regexp go through the per-row float -> shortest text formatting on the device
+    fvals = [b"%d.%d" % (i * 7 - 900, i % 97) for i in range(n - 8)] + [b"9007199254740991", b"0.00000015", b"-0.000123", b"123456789.125", b"0.5", b"-12.25", b"12.50", b"125"]
+    fblk = oracle.Block.from_columns([("f", fvals), ("k", [b"k%d" % i for i in range(n)])])
+    assert {c.name: c.value_type for c in fblk.columns}[b"f"] == 7
+    for kind, arg in [("phrase", "123"), ("phrase", "-123"), ("phrase", "123.5"), ("phrase", "125"), ("phrase", "."), ("phrase", "-"), ("phrase", "0"), ("phrase", "56"), ("phrase", "9007199254740991"),
+                      ("phrase", "00000015"), ("phrase", "0.00000015"), ("phrase", "12.50"), ("phrase", "12.5"), ("prefix", "12"), ("prefix", "-1"), ("prefix", "0.0"), ("prefix", "."), ("prefix", "-"),
+                      ("prefix", "e"), ("prefix", "900719"), ("prefix", "5"), ("prefix", ""), ("exact", "9007199254740991"), ("exact", "123456789.125"), ("exact", "-0.000123"), ("exact", "12.50"),
+                      ("exact", "12.5"), ("exact", "nope")]:
+        check(env, [fblk], (getattr(F, kind)("f", arg), getattr(G, kind)("f", arg)))
+    for rx in ["^-", "\\.5$", "^90+7", "^0\\.0+15$", "^[0-9]+\\.125$", "e", "^-?[0-9]+$", "^-?[0-9]+\\.[0-9]{2}$"]:
+        check(env, [fblk], (F.regexp("f", rx), G.regexp("f", rx)))
+    check(env, [fblk], (F.in_("f", ["125", "-0.000123", "7"]), G.in_("f", ["125", "-0.000123", "7"])))
     tree_o = F.and_([F.phrase("msg", "status"), F.or_([F.phrase("lvl", "error"), F.in_("u8", ["7", "9"])]), F.not_(F.prefix("ip", "10.2"))])
     tree_g = G.and_([G.phrase("msg", "status"), G.or_([G.phrase("lvl", "error"), G.in_("u8", ["7", "9"])]), G.not_(G.prefix("ip", "10.2"))])
     check(env, [blk], (tree_o, tree_g))
@@ -289,3 +289,25 @@ def test_block_result_style_inputs(env):
         want = oracle.bitmap_rows(blk.search(getattr(F, kind)(field, arg)), blk.rows)
         words, counts, st = ctx.scan_batch(vs.Program(getattr(G, kind)(field, arg)), hb)
         assert oracle.bitmap_rows(np.ascontiguousarray(words), blk.rows) == want, (kind, field, arg)
+    # float64 column holding values the values encoder never emits (exponent range, subnormals, -0, Inf, NaN): the per-row text must
+    # still be strconv.AppendFloat(f,'f',-1,64).  Expected bits: the same predicate over a string column of those texts.
+    import struct, random
+    rng = random.Random(5)
+    bits = [0, 1 << 63, 1, 0x7FEFFFFFFFFFFFFF, 0xFFEFFFFFFFFFFFFF, 0x7FF0000000000000, 0xFFF0000000000000, 0x7FF8000000000000, 0x0010000000000000, 0x000FFFFFFFFFFFFF]
+    bits += [struct.unpack(">Q", struct.pack(">d", float(s)))[0] for s in ("1e21", "1e22", "1.5e-7", "5e-324", "123456.789", "-2.5e300", "3e-310", "1e23", "9.5e15")]
+    bits += [rng.getrandbits(64) for _ in range(181)]
+    texts = [oracle.encoded_to_string(7, struct.pack(">Q", b)) for b in bits]
+    sblk = oracle.Block.from_columns([("f", texts), ("k", [b"k%d" % i for i in range(len(bits))])])
+    assert {c.name: c.value_type for c in sblk.columns}[b"f"] == 1
+    tmpl = oracle.Block.from_columns([("f", [b"%d.5" % i for i in range(len(bits))])])   # same row count: borrow its lens block (all 8)
+    fd = pu.oracle_block_to_desc(tmpl, "decoded")
+    fc = fd["columns"][0]
+    assert fc["value_type"] == 7 and len(fc["data"]) == 8 * len(bits)
+    fc.update(min_value=0xFFF0000000000000, max_value=0x7FF0000000000000, bloom=b"", data=b"".join(struct.pack(">Q", b) for b in bits))
+    fhb = vs.HostBlocks([b"f"], [fd])
+    for kind, arg in [("phrase", "-"), ("phrase", "."), ("phrase", "0"), ("phrase", "100000"), ("phrase", "5"), ("prefix", "1797693134862315"), ("prefix", "0.0000"),
+                      ("prefix", "-"), ("prefix", "."), ("prefix", "e"), ("regexp", "0{200}"), ("regexp", "^-?0\\.0{300}"), ("regexp", "Inf|NaN"), ("regexp", "^\\+Inf$"), ("regexp", "^-0$"),
+                      ("regexp", "^[0-9]+$"), ("regexp", "^-?[0-9]*\\.?[0-9]*$")]:
+        want = oracle.bitmap_rows(sblk.search(getattr(F, kind)("f", arg)), sblk.rows)
+        words, counts, st = ctx.scan_batch(vs.Program(getattr(G, kind)("f", arg)), fhb)
+        assert oracle.bitmap_rows(np.ascontiguousarray(words), sblk.rows) == want, (kind, arg)

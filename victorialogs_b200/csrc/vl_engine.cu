@@ -562,6 +562,14 @@ int64_t vlscan_program_leaf_tokens(const vlscan_program* prog, uint32_t leaf, ch
     return (int64_t)s.size();
 }
 
+int vlscan_format_float64(uint64_t ieee_bits, char* buf, size_t cap) {
+    uint8_t tmp[VL_FMT_F64_MAX];
+    int n = vl::fmt_f64(tmp, ieee_bits);
+    if ((size_t)n > cap) return -1;
+    memcpy(buf, tmp, (size_t)n);
+    return n;
+}
+
 int vlscan_batch_upload(vlscan_ctx* ctx, const char* const* field_names, const size_t* field_name_lens, uint32_t nfields, const vlscan_block* blocks,
                         uint64_t nblocks, vlscan_batch** out, vlscan_stats* stats) {
     *out = nullptr;

@@ -250,4 +250,126 @@ VL_HDN int fmt_iso8601(uint8_t* buf, int64_t nsecs) {
     return 24;
 }
 
+// ---- float64 -> shortest decimal text: strconv.AppendFloat(dst, f, 'f', -1, 64) (marshalFloat64String, values_encoder.go:1397-1399) ----
+// Shortest digits that round-trip (Ryu, Adams 2018: the same digit string Go's shortest formatter produces), printed in fixed notation
+// without exponent.  Tables generated by tools/gen_ryu_tables.py.  Returns the length (<= 344 bytes incl. sign).
+#include "ryu_tables.inc"
+static const uint64_t H_RYU_POW5_INV_SPLIT[342][2] = { VL_RYU_POW5_INV_SPLIT_INIT };
+static const uint64_t H_RYU_POW5_SPLIT[326][2] = { VL_RYU_POW5_SPLIT_INIT };
+#ifdef __CUDACC__
+static __device__ const uint64_t D_RYU_POW5_INV_SPLIT[342][2] = { VL_RYU_POW5_INV_SPLIT_INIT };
+static __device__ const uint64_t D_RYU_POW5_SPLIT[326][2] = { VL_RYU_POW5_SPLIT_INIT };
+#endif
+#define VL_FMT_F64_MAX 352
+
+VL_HD uint64_t umul128(uint64_t a, uint64_t b, uint64_t* hi) {
+#ifdef __CUDA_ARCH__
+    *hi = __umul64hi(a, b); return a * b;
+#else
+    unsigned __int128 p = (unsigned __int128)a * b; *hi = (uint64_t)(p >> 64); return (uint64_t)p;
+#endif
+}
+VL_HD uint64_t ryu_mul_shift64(uint64_t m, uint64_t mul0, uint64_t mul1, int j) {
+    uint64_t hi0, hi2;
+    (void)umul128(m, mul0, &hi0);
+    uint64_t lo2 = umul128(m, mul1, &hi2);
+    uint64_t sum = hi0 + lo2;
+    if (sum < hi0) hi2++;
+    int dist = j - 64;
+    return dist == 0 ? sum : (hi2 << (64 - dist)) | (sum >> dist);
+}
+VL_HD uint32_t ryu_pow5_factor(uint64_t v) { uint32_t c = 0; for (;;) { uint64_t q = v / 5; if (v - 5 * q != 0) break; v = q; c++; } return c; }
+VL_HD uint32_t ryu_pow5bits(int32_t e) { return (uint32_t)(((e * 1217359) >> 19) + 1); }
+VL_HD uint32_t ryu_log10_pow2(int32_t e) { return (uint32_t)((e * 78913) >> 18); }
+VL_HD uint32_t ryu_log10_pow5(int32_t e) { return (uint32_t)((e * 732923) >> 20); }
+
+// shortest decimal: value == digits * 10^exp10 (digits has no sign; value != 0, finite)
+VL_HDN void ryu_d2d(uint64_t mant, uint32_t expo, uint64_t* digits, int32_t* exp10) {
+    int32_t e2; uint64_t m2;
+    if (expo == 0) { e2 = 1 - 1023 - 52 - 2; m2 = mant; } else { e2 = (int32_t)expo - 1023 - 52 - 2; m2 = (1ull << 52) | mant; }
+    const bool acceptBounds = (m2 & 1) == 0;
+    const uint64_t mv = 4 * m2;
+    const uint32_t mmShift = mant != 0 || expo <= 1;
+    uint64_t vr, vp, vm; int32_t e10;
+    bool vmTZ = false, vrTZ = false;
+    if (e2 >= 0) {
+        const uint32_t q = ryu_log10_pow2(e2) - (e2 > 3);
+        e10 = (int32_t)q;
+        const int32_t k = VL_RYU_POW5_INV_BITCOUNT + (int32_t)ryu_pow5bits((int32_t)q) - 1;
+        const int32_t i = -e2 + (int32_t)q + k;
+#ifdef __CUDA_ARCH__
+        const uint64_t m0 = D_RYU_POW5_INV_SPLIT[q][0], m1 = D_RYU_POW5_INV_SPLIT[q][1];
+#else
+        const uint64_t m0 = H_RYU_POW5_INV_SPLIT[q][0], m1 = H_RYU_POW5_INV_SPLIT[q][1];
+#endif
+        vr = ryu_mul_shift64(4 * m2, m0, m1, i); vp = ryu_mul_shift64(4 * m2 + 2, m0, m1, i); vm = ryu_mul_shift64(4 * m2 - 1 - mmShift, m0, m1, i);
+        if (q <= 21) {
+            const uint32_t mvMod5 = (uint32_t)(mv % 5);
+            if (mvMod5 == 0) vrTZ = ryu_pow5_factor(mv) >= q;
+            else if (acceptBounds) vmTZ = ryu_pow5_factor(mv - 1 - mmShift) >= q;
+            else vp -= ryu_pow5_factor(mv + 2) >= q;
+        }
+    } else {
+        const uint32_t q = ryu_log10_pow5(-e2) - (-e2 > 1);
+        e10 = (int32_t)q + e2;
+        const int32_t i = -e2 - (int32_t)q;
+        const int32_t k = (int32_t)ryu_pow5bits(i) - VL_RYU_POW5_BITCOUNT;
+        const int32_t j = (int32_t)q - k;
+#ifdef __CUDA_ARCH__
+        const uint64_t m0 = D_RYU_POW5_SPLIT[i][0], m1 = D_RYU_POW5_SPLIT[i][1];
+#else
+        const uint64_t m0 = H_RYU_POW5_SPLIT[i][0], m1 = H_RYU_POW5_SPLIT[i][1];
+#endif
+        vr = ryu_mul_shift64(4 * m2, m0, m1, j); vp = ryu_mul_shift64(4 * m2 + 2, m0, m1, j); vm = ryu_mul_shift64(4 * m2 - 1 - mmShift, m0, m1, j);
+        if (q <= 1) {
+            vrTZ = true;
+            if (acceptBounds) vmTZ = mmShift == 1; else --vp;
+        } else if (q < 63) vrTZ = (mv & ((1ull << q) - 1)) == 0;
+    }
+    int32_t removed = 0; uint32_t last = 0; uint64_t out;
+    if (vmTZ || vrTZ) {
+        while (vp / 10 > vm / 10) { vmTZ &= vm % 10 == 0; vrTZ &= last == 0; last = (uint32_t)(vr % 10); vr /= 10; vp /= 10; vm /= 10; removed++; }
+        if (vmTZ) while (vm % 10 == 0) { vrTZ &= last == 0; last = (uint32_t)(vr % 10); vr /= 10; vp /= 10; vm /= 10; removed++; }
+        if (vrTZ && last == 5 && vr % 2 == 0) last = 4;   // round even when exactly halfway
+        out = vr + ((vr == vm && (!acceptBounds || !vmTZ)) || last >= 5);
+    } else {
+        bool roundUp = false;
+        while (vp / 10 > vm / 10) { roundUp = vr % 10 >= 5; vr /= 10; vp /= 10; vm /= 10; removed++; }
+        out = vr + (vr == vm || roundUp);
+    }
+    *digits = out; *exp10 = e10 + removed;
+}
+
+VL_HDN int fmt_f64(uint8_t* buf, uint64_t bits) {
+    const bool neg = bits >> 63;
+    const uint64_t mant = bits & ((1ull << 52) - 1);
+    const uint32_t expo = (uint32_t)((bits >> 52) & 0x7FF);
+    int n = 0;
+    if (expo == 0x7FF) {   // strconv: "NaN", "+Inf", "-Inf"
+        const char* s = mant ? "NaN" : (neg ? "-Inf" : "+Inf");
+        while (s[n]) { buf[n] = (uint8_t)s[n]; n++; }
+        return n;
+    }
+    if (neg) buf[n++] = '-';
+    if (expo == 0 && mant == 0) { buf[n++] = '0'; return n; }
+    uint64_t dig; int32_t e10;
+    ryu_d2d(mant, expo, &dig, &e10);
+    uint8_t d[20]; int nd = 0;
+    while (dig) { d[nd++] = (uint8_t)('0' + dig % 10); dig /= 10; }   // least significant first
+    if (e10 >= 0) {
+        for (int i = nd - 1; i >= 0; i--) buf[n++] = d[i];
+        for (int i = 0; i < e10; i++) buf[n++] = '0';
+    } else {
+        int point = nd + e10;   // digits before the decimal point
+        if (point > 0) {
+            for (int i = nd - 1; i >= 0; i--) { if (nd - 1 - i == point) buf[n++] = '.'; buf[n++] = d[i]; }
+        } else {
+            buf[n++] = '0'; buf[n++] = '.';
+            for (int i = 0; i < -point; i++) buf[n++] = '0';
+            for (int i = nd - 1; i >= 0; i--) buf[n++] = d[i];
+        }
+    }
+    return n;
+}
+
 }  // namespace vl

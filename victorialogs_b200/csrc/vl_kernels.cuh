@@ -135,7 +135,16 @@ static __device__ int encoded_to_string(uint32_t vt, uint64_t raw, uint8_t* buf)
     case VT_IPV4: return fmt_ipv4(buf, (uint32_t)raw);
     case VT_ISO8601: return fmt_iso8601(buf, (int64_t)raw);
     }
-    return -1;   // float64: shortest round-trip formatting is not implemented on the device (plan raises an error)
+    return -1;   // float64 takes leaf_match_f64 (its text can be 300+ bytes long)
+}
+
+// float64 value -> shortest decimal text -> string matcher (toFloat64String, filter_phrase.go:304-308; matchFloat64ByPrefix,
+// filter_prefix.go:224-252; matchFloat64ByRegex filter_regexp.go).  Kept out of line: the 352-byte text buffer must not
+// grow the frame of the common integer path.
+static __device__ __noinline__ bool leaf_match_f64(const DevProgram& P, const DevLeaf& L, uint64_t raw) {
+    uint8_t buf[VL_FMT_F64_MAX];
+    int n = fmt_f64(buf, raw);
+    return leaf_match_string(P, L, buf, (uint32_t)n);
 }
 
 // ---- bloom probe, warp wide (bloomFilter.containsAll, lib/logstorage/bloomfilter.go:173-191) -----------------------------------
@@ -294,7 +303,6 @@ static __global__ void k_plan_leaf(DevProgram P, BatchView B, uint32_t leaf_idx,
             };
             auto tostring_path = [&](bool use_bloom) {
                 if (use_bloom && !probe(H, L.nhashes)) { act = ACT_NONE; return; }
-                if (vt == VT_FLOAT64) { err = ERR_UNSUPPORTED_FLOAT_TOSTRING; act = ACT_NONE; return; }
                 act = ACT_ROW;
             };
             switch (L.kind) {
@@ -866,6 +874,7 @@ static __global__ void k_row_match(DevProgram P, BatchView B, uint32_t leaf_idx,
         if (L.kind == F_IN) return in_contains_typed(L, P.u64s, vt, raw);
         if (L.kind == F_EXACT) return raw == payload[b];
         if (L.kind == F_PHRASE && L.typed[vt].ok && !(vt == VT_FLOAT64 && !L.f64_exact_form)) return raw == payload[b];
+        if (vt == VT_FLOAT64) return leaf_match_f64(P, L, raw);
         uint8_t buf[32];
         int n = encoded_to_string(vt, raw, buf);
         if (n < 0) return false;

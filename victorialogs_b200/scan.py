@@ -64,7 +64,7 @@ class GenConfig(C.Structure):
 
 
 EXPORTS = ["vlscan_device_count", "vlscan_ctx_create", "vlscan_ctx_free", "vlscan_last_error", "vlscan_ctx_stream", "vlscan_ctx_sync",
-           "vlscan_program_create", "vlscan_program_free", "vlscan_program_nfields", "vlscan_program_field", "vlscan_program_leaf_tokens",
+           "vlscan_program_create", "vlscan_program_free", "vlscan_program_nfields", "vlscan_program_field", "vlscan_program_leaf_tokens", "vlscan_format_float64",
            "vlscan_batch_upload", "vlscan_batch_free", "vlscan_batch_nblocks", "vlscan_batch_rows", "vlscan_batch_words", "vlscan_batch_device_bytes",
            "vlscan_batch_generate", "vlscan_batch_download", "vlscan_host_blocks_get", "vlscan_host_blocks_field", "vlscan_host_blocks_bytes",
            "vlscan_host_blocks_free", "vlscan_scan_resident", "vlscan_last_scan_stats", "vlscan_fetch_results", "vlscan_fetch_hits", "vlscan_result_device_ptrs", "vlscan_scan_batch"]
@@ -96,8 +96,19 @@ def lib():
         for n in ("vlscan_ctx_free", "vlscan_program_free", "vlscan_batch_free", "vlscan_host_blocks_free"):
             getattr(L, n).argtypes = [C.c_void_p]
             getattr(L, n).restype = None
+        L.vlscan_format_float64.argtypes = [C.c_uint64, C.c_char_p, C.c_size_t]
+        L.vlscan_format_float64.restype = C.c_int
         _LIB = L
     return _LIB
+
+
+def format_float64(bits):
+    """Text of a float64 column value (IEEE bits) as the scan kernels format it; marshalFloat64String, values_encoder.go:1397."""
+    buf = C.create_string_buffer(352)
+    n = lib().vlscan_format_float64(C.c_uint64(bits), buf, C.c_size_t(352))
+    if n < 0:
+        raise ValueError(bits)
+    return buf.raw[:n]
 
 
 def device_count():
