@@ -42,8 +42,8 @@ enum { VLSCAN_COL_CONST = 1, VLSCAN_COL_VALUES = 2 };
 enum {
     VLSCAN_STAGE_ONDISK = 0,  /* `values` = the bytes at [valuesOffset, +valuesSize) of the values file:
                                  bytesBlock(uintBlock lens) ++ bytesBlock(data), plain or ZSTD
-                                 (lib/logstorage/encoding.go:16-50,343-426); ZSTD frames are decoded on the host with
-                                 libzstd at staging time, exactly where the reference calls cgo libzstd today       */
+                                 (lib/logstorage/encoding.go:16-50,343-426); the bytes go to HBM as they are and the
+                                 ZSTD frames are decoded there (where the reference calls cgo libzstd per block)    */
     VLSCAN_STAGE_DECODED = 1  /* `lens_items` / `data` = what unmarshalBytesBlock yields for the two sub-blocks
                                  (encoding.go:372-426): the uintBlock items incl. their type byte, and the data     */
 };
@@ -165,6 +165,21 @@ const vlscan_block* vlscan_host_blocks_get(const vlscan_host_blocks* hb, uint64_
 const char* vlscan_host_blocks_field(const vlscan_host_blocks* hb, uint32_t i, size_t* len);
 uint64_t vlscan_host_blocks_bytes(const vlscan_host_blocks* hb);
 void vlscan_host_blocks_free(vlscan_host_blocks* hb);
+/* Writer-side helper for benches and tests: re-encode the values blocks of `in` into their on-disk form,
+ * marshalBytesBlock(lens items) ++ marshalBytesBlock(data) with the reference's size-dependent ZSTD level
+ * (lib/logstorage/encoding.go:16-50,343-370), using libzstd on `threads` host threads (0 = all).  The result lives in one
+ * pinned buffer whose layout lets vlscan_batch_upload / vlscan_scan_batch move it with two DMA transfers.
+ * Compression is the only thing libzstd is used for; frames are decoded on the device. */
+int vlscan_host_blocks_compress(const vlscan_host_blocks* in, int threads, vlscan_host_blocks** out);
+
+/* ---- device ZSTD decoder --------------------------------------------------------------------------------------------
+ * VLSCAN_STAGE_ONDISK payloads are copied to HBM compressed and regenerated there (replaces the libzstd call behind
+ * unmarshalBytesBlock, encoding.go:372-426 -> lib/encoding/compress.go:24-32).  This entry point runs the same decoder on
+ * `nframes` independent frames given as host pointers, for parity tests against libzstd: frame i must regenerate exactly
+ * dst_offsets[i+1]-dst_offsets[i] bytes, written to dst + dst_offsets[i].  Frames must declare their content size and use
+ * no dictionary; content checksums are skipped, not verified. */
+int vlscan_zstd_decompress(vlscan_ctx* ctx, uint32_t nframes, const void* const* frames, const size_t* frame_lens, void* dst,
+                           const uint64_t* dst_offsets);
 
 /* ---- the scan ---------------------------------------------------------------------------------------------------- */
 /* Scan a resident batch: equivalent of `for each block: bm.init(rows); bm.setBits(); filter.applyToBlockSearch(bs, bm)`

@@ -5,8 +5,11 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xcudafe --diag_suppress=177 ${VL_NVCC_EXTRA}"
 mkdir -p build
-$NVCC $FLAGS -c csrc/vl_engine.cu -o build/vl_engine.o &
-$NVCC $FLAGS -c csrc/vl_gen.cu -o build/vl_gen.o &
-wait
-$NVCC -shared -o libvlscan.so build/vl_engine.o build/vl_gen.o -ldl
+pids=()
+for tu in vl_engine vl_gen vl_zstd; do
+    $NVCC $FLAGS -c csrc/$tu.cu -o build/$tu.o &
+    pids+=($!)
+done
+for p in "${pids[@]}"; do wait $p; done
+$NVCC -shared -o libvlscan.so build/vl_engine.o build/vl_gen.o build/vl_zstd.o -ldl
 echo built victorialogs_b200/libvlscan.so

@@ -3,7 +3,9 @@
 // computing entry point fails with an error.
 #include <dlfcn.h>
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -74,48 +76,23 @@ template <class F> int guarded(vlscan_ctx* ctx, F&& f) {
     catch (const std::exception& e) { set_thread_error(e.what()); if (ctx) ctx->err = e.what(); return -3; }
 }
 
-// ---- libzstd (host staging of VLSCAN_STAGE_ONDISK payloads; the reference reaches the same library through cgo) -----------
-struct Zstd {
-    unsigned long long (*frame_size)(const void*, size_t) = nullptr;
-    size_t (*decompress)(void*, size_t, const void*, size_t) = nullptr;
+// ---- libzstd, COMPRESSION only: vlscan_host_blocks_compress plays the reference's writer (marshalBytesBlock, encoding.go:343-360) so that
+// benches and tests can feed on-disk-stage blocks.  Nothing on the scan path calls into it: frames are decoded on the device (vl_zstd.cuh).
+struct ZstdWriter {
+    size_t (*compress)(void*, size_t, const void*, size_t, int) = nullptr;
+    size_t (*bound)(size_t) = nullptr;
     unsigned (*is_error)(size_t) = nullptr;
     bool ok = false;
-    Zstd() {
+    ZstdWriter() {
         void* h = dlopen("libzstd.so.1", RTLD_NOW | RTLD_GLOBAL);
         if (!h) return;
-        frame_size = (decltype(frame_size))dlsym(h, "ZSTD_getFrameContentSize");
-        decompress = (decltype(decompress))dlsym(h, "ZSTD_decompress");
+        compress = (decltype(compress))dlsym(h, "ZSTD_compress");
+        bound = (decltype(bound))dlsym(h, "ZSTD_compressBound");
         is_error = (decltype(is_error))dlsym(h, "ZSTD_isError");
-        ok = frame_size && decompress && is_error;
+        ok = compress && bound && is_error;
     }
 };
-Zstd& zstd() { static Zstd z; return z; }
-
-// unmarshalBytesBlock lib/logstorage/encoding.go:372-426; returns bytes consumed
-size_t host_unmarshal_bytes_block(std::vector<uint8_t>& dst, const uint8_t* src, size_t n) {
-    if (n < 1) throw BadInput("cannot unmarshal block type from empty src");
-    if (src[0] == 0) {
-        if (n < 2) throw BadInput("cannot unmarshal plain block size from empty src");
-        size_t len = src[1];
-        if (n - 2 < len) throw BadInput("cannot read plain block: not enough bytes");
-        dst.insert(dst.end(), src + 2, src + 2 + len);
-        return 2 + len;
-    }
-    if (src[0] == 1) {
-        uint64_t clen = 0; int sh = 0; size_t i = 1; bool done = false;
-        for (; i < n && i < 11; i++) { clen |= (uint64_t)(src[i] & 0x7F) << sh; sh += 7; if (src[i] < 0x80) { done = true; i++; break; } }
-        if (!done) throw BadInput("cannot unmarshal compressed block size");
-        if (n - i < clen) throw BadInput("cannot read compressed block: not enough bytes");
-        if (!zstd().ok) throw BadInput("libzstd.so.1 is not available for decoding a ZSTD values block");
-        unsigned long long dl = zstd().frame_size(src + i, clen);
-        if (dl == (unsigned long long)-1 || dl == (unsigned long long)-2 || dl > (64ull << 20)) throw BadInput("cannot decompress block: bad frame header");
-        size_t old = dst.size(); dst.resize(old + dl);
-        size_t got = zstd().decompress(dst.data() + old, dl, src + i, clen);
-        if (zstd().is_error(got) || got != dl) throw BadInput("cannot decompress block");
-        return i + clen;
-    }
-    throw BadInput("unexpected block type; supported types: 0, 1");
-}
+ZstdWriter& zstd_writer() { static ZstdWriter z; return z; }
 
 void launch_check(vlscan_ctx* ctx) { ctx->launches++; VL_CUDA(cudaGetLastError()); }
 inline unsigned cdiv(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
@@ -166,10 +143,18 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
     memset(cols.data(), 0, cols.size() * sizeof(DevColumn));
     std::vector<uint32_t> rows(nblocks);
     struct Piece { const uint8_t* src; uint64_t len; uint64_t dst; };
-    std::vector<Piece> pieces;
-    std::vector<std::unique_ptr<std::vector<uint8_t>>> owned;   // decoded ONDISK payloads, dict metadata
+    std::vector<Piece> pieces, zpieces;   // host -> arena, host -> compressed staging (on-disk values blocks)
+    std::vector<std::unique_ptr<std::vector<uint8_t>>> owned;   // dict metadata built here
     uint64_t cursor = 16;   // the first 16 bytes stay unused so that every payload has a readable byte in front of it
     auto add_piece = [&](const uint8_t* src, uint64_t len) { uint64_t off = arena_reserve(cursor, len); if (len) pieces.push_back({src, len, off}); return off; };
+    // On-disk values blocks are not copied into the arena: their bytes go to the compressed staging buffer as they are and the device
+    // regenerates them (vl_zstd.cuh) into arena regions placed behind everything that is copied, so that host memory laid out like
+    // the copied part still goes out as one DMA.  Region offsets are relative to `regen_base` until the loop below has sized that part.
+    ZstdJob zjob;
+    uint64_t zcursor = 16, regen_cursor = 0;
+    struct Ondisk { uint64_t col; uint32_t lens_frame, data_frame; uint64_t lens_rel, data_rel; };
+    std::vector<Ondisk> ondisk;
+    std::vector<OndiskCol> ocols;
     for (uint64_t b = 0; b < nblocks; b++) {
         const vlscan_block& blk = blocks[b];
         if (blk.rows > (8u << 20)) throw BadInput("block rows exceed maxRowsPerBlock (8Mi)");   // consts.go:24
@@ -186,31 +171,38 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
             if (c.kind != VLSCAN_COL_VALUES) throw BadInput("unknown column kind");
             if (c.value_type < VT_STRING || c.value_type >= VT_MAX) throw BadInput("unknown valueType");
             d.kind = COL_VALUES; d.vt = c.value_type; d.min_value = c.min_value; d.max_value = c.max_value;
-            const uint8_t* lens_items; uint64_t lens_len; const uint8_t* data; uint64_t data_len;
             if (c.stage == VLSCAN_STAGE_ONDISK) {
-                // stringsBlockUnmarshaler.unmarshal: bytesBlock(lens) ++ bytesBlock(data) (encoding.go:83-108)
-                auto lv = std::make_unique<std::vector<uint8_t>>(); auto dv = std::make_unique<std::vector<uint8_t>>();
-                size_t c1 = host_unmarshal_bytes_block(*lv, c.values, c.values_len);
-                size_t c2 = host_unmarshal_bytes_block(*dv, c.values + c1, c.values_len - c1);
+                // stringsBlockUnmarshaler.unmarshal: bytesBlock(lens) ++ bytesBlock(data) (encoding.go:83-108).  The host reads the
+                // containers, the frame header and the block headers; the payload is regenerated on the device.
+                const uint64_t zoff = zcursor; zcursor += c.values_len;
+                if (c.values_len) zpieces.push_back({c.values, c.values_len, zoff});
+                uint64_t lens_len = 0, data_len = 0; uint32_t f1 = 0, f2 = 0;
+                size_t c1 = zjob.add_bytes_block(c.values, c.values_len, zoff, &lens_len, &f1);
+                size_t c2 = zjob.add_bytes_block(c.values + c1, c.values_len - c1, zoff + c1, &data_len, &f2);
                 if (c1 + c2 != c.values_len) throw BadInput("unexpected non-empty tail after reading bytes block with strings");
-                lens_items = lv->data(); lens_len = lv->size(); data = dv->data(); data_len = dv->size();
-                owned.push_back(std::move(lv)); owned.push_back(std::move(dv));
+                if (data_len > 0xFFFFFFFFull) throw BadInput("values block too large");
+                // the uint block type byte lands on offset 15 of its region, so the lens items behind it are 16-byte aligned
+                const uint64_t lr = arena_reserve(regen_cursor, lens_len + 15), dr = arena_reserve(regen_cursor, data_len);
+                d.lens_off = lr + 16; d.data_off = dr; d.data_len = data_len;
+                const uint64_t ci = (uint64_t)b * nfields + c.field;
+                ondisk.push_back({ci, f1, f2, lr + 15, dr});
+                ocols.push_back({ci, lens_len, blk.rows});   // lens header checks + lens_type / lens_const / data_const: k_finish_ondisk_cols
             } else if (c.stage == VLSCAN_STAGE_DECODED) {
-                lens_items = c.lens_items; lens_len = c.lens_items_len; data = c.data; data_len = c.data_len;
+                const uint8_t* lens_items = c.lens_items; const uint64_t lens_len = c.lens_items_len, data_len = c.data_len;
+                // unmarshalUint64Items header checks (encoding.go:246-336)
+                if (lens_len < 1) throw BadInput("cannot unmarshal uint64 block type from empty src");
+                uint8_t lt = lens_items[0];
+                if (lt > 7) throw BadInput("unexpected uint64 block type");
+                uint64_t want = lt < 4 ? (blk.rows << lt) : (1ull << (lt - 4));
+                if (lens_len - 1 != want) throw BadInput("unexpected block length for uint items");
+                d.lens_type = lt;
+                if (lt >= 4) { uint64_t v = 0; for (uint64_t i = 0; i < want; i++) v = (v << 8) | lens_items[1 + i]; if (v > 0xFFFFFFFFull) throw BadInput("row length does not fit 32 bits"); d.lens_const = (uint32_t)v; }
+                if (data_len > 0xFFFFFFFFull) throw BadInput("values block too large");
+                d.lens_off = add_piece(lens_items + 1, lens_len - 1);
+                d.data_off = add_piece(c.data, data_len); d.data_len = data_len;
+                // decode rule of encoding.go:113-120: rows >= 2, all lens equal, len(data) == lens[0] => every row = data
+                d.data_const = (blk.rows >= 2 && lt >= 4 && data_len == d.lens_const) ? 1 : 0;
             } else throw BadInput("unknown values stage");
-            // unmarshalUint64Items header checks (encoding.go:246-336)
-            if (lens_len < 1) throw BadInput("cannot unmarshal uint64 block type from empty src");
-            uint8_t lt = lens_items[0];
-            if (lt > 7) throw BadInput("unexpected uint64 block type");
-            uint64_t want = lt < 4 ? (blk.rows << lt) : (1ull << (lt - 4));
-            if (lens_len - 1 != want) throw BadInput("unexpected block length for uint items");
-            d.lens_type = lt;
-            if (lt >= 4) { uint64_t v = 0; for (uint64_t i = 0; i < want; i++) v = (v << 8) | lens_items[1 + i]; if (v > 0xFFFFFFFFull) throw BadInput("row length does not fit 32 bits"); d.lens_const = (uint32_t)v; }
-            if (data_len > 0xFFFFFFFFull) throw BadInput("values block too large");
-            d.lens_off = add_piece(lens_items + 1, lens_len - 1);
-            d.data_off = add_piece(data, data_len); d.data_len = data_len;
-            // decode rule of encoding.go:113-120: rows >= 2, all lens equal, len(data) == lens[0] => every row = data
-            d.data_const = (blk.rows >= 2 && lt >= 4 && data_len == d.lens_const) ? 1 : 0;
             if (c.bloom_len % 8) throw BadInput("cannot unmarshal bloomFilter from src with size not multiple by 8");   // bloomfilter.go:59-61
             d.bloom_words = (uint32_t)(c.bloom_len / 8); d.bloom_off = add_piece(c.bloom, c.bloom_len);
             if (c.value_type == VT_DICT) {
@@ -231,18 +223,28 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
             }
         }
     }
+    // regenerated regions follow the copied part
+    const uint64_t regen_base = (cursor + kArenaAlign - 1) / kArenaAlign * kArenaAlign;
+    for (const Ondisk& o : ondisk) {
+        DevColumn& d = cols[o.col];
+        d.lens_off += regen_base; d.data_off += regen_base;
+        zjob.set_dst(o.lens_frame, regen_base + o.lens_rel); zjob.set_dst(o.data_frame, regen_base + o.data_rel);
+    }
+    if (!ondisk.empty()) cursor = regen_base + regen_cursor;
     out->arena_bytes = cursor + kArenaPad;
     t_desc = now();
     out->arena.ensure(out->arena_bytes);
+    if (!zpieces.empty()) ctx->zsrc.ensure(zcursor + 64);
     t_alloc = now();
     // copy pieces: runs that are contiguous on both sides (src stride == dst stride) and live in pinned host memory go out as one
     // cudaMemcpyAsync; everything else is packed through a pinned staging ring.
     uint64_t h2d = 0;
     const size_t CH = 32u << 20;
     uint8_t* stage = nullptr; cudaEvent_t evs[2] = {nullptr, nullptr}; int cur = 0; size_t fill = 0; uint64_t chunk_dst = 0; bool chunk_open = false;
+    uint8_t* dev_base = out->arena.as<uint8_t>();   // destination buffer of the pieces being copied
     auto flush = [&]() {
         if (!chunk_open || !fill) { chunk_open = false; fill = 0; return; }
-        VL_CUDA(cudaMemcpyAsync(out->arena.as<uint8_t>() + chunk_dst, stage + (size_t)cur * CH, fill, cudaMemcpyHostToDevice, ctx->stream));
+        VL_CUDA(cudaMemcpyAsync(dev_base + chunk_dst, stage + (size_t)cur * CH, fill, cudaMemcpyHostToDevice, ctx->stream));
         VL_CUDA(cudaEventRecord(evs[cur], ctx->stream));
         h2d += fill; cur ^= 1; fill = 0; chunk_open = false;
         VL_CUDA(cudaEventSynchronize(evs[cur]));
@@ -254,7 +256,9 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
         stage = (uint8_t*)ctx->ensure_pinned(2 * CH);
         for (int k = 0; k < 2; k++) { VL_CUDA(cudaEventCreateWithFlags(&evs[k], cudaEventDisableTiming)); VL_CUDA(cudaEventRecord(evs[k], ctx->stream)); }
     };
-    bool all_pinned = !pieces.empty();
+    bool all_pinned = !pieces.empty() || !zpieces.empty();
+    auto copy_pieces = [&](const std::vector<Piece>& pieces, uint8_t* base) {
+    dev_base = base;
     size_t i = 0;
     while (i < pieces.size()) {
         // maximal run of pieces laid out identically on both sides (same stride between source and destination)
@@ -264,7 +268,7 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
         if (is_pinned(pieces[i].src) && is_pinned(pieces[j].src + pieces[j].len - 1)) {
             // page-locked caller memory: one DMA for the whole run, gaps (alignment slack) included
             flush();
-            VL_CUDA(cudaMemcpyAsync(out->arena.as<uint8_t>() + pieces[i].dst, pieces[i].src, run_len, cudaMemcpyHostToDevice, ctx->stream));
+            VL_CUDA(cudaMemcpyAsync(dev_base + pieces[i].dst, pieces[i].src, run_len, cudaMemcpyHostToDevice, ctx->stream));
             h2d += run_len; i = j + 1;
             continue;
         }
@@ -288,10 +292,29 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
         }
     }
     flush();
+    };
+    copy_pieces(pieces, out->arena.as<uint8_t>());
+    if (!zpieces.empty()) copy_pieces(zpieces, ctx->zsrc.as<uint8_t>());
     for (int k = 0; k < 2; k++) if (evs[k]) cudaEventDestroy(evs[k]);
     out->cols.ensure(std::max<size_t>(cols.size() * sizeof(DevColumn), 16));
     if (!cols.empty()) VL_CUDA(cudaMemcpyAsync(out->cols.p, cols.data(), cols.size() * sizeof(DevColumn), cudaMemcpyHostToDevice, ctx->stream));
     h2d += cols.size() * sizeof(DevColumn);
+    if (!ondisk.empty()) {
+        // regenerate the on-disk payloads in HBM, then derive lens_type / lens_const / data_const from the regenerated lens blocks
+        zjob.run(ctx, ctx->zsrc.as<uint8_t>(), out->arena.as<uint8_t>());
+        ctx->zcols.ensure(16 + ocols.size() * sizeof(OndiskCol));
+        VL_CUDA(cudaMemsetAsync(ctx->zcols.p, 0, 16, ctx->stream));
+        VL_CUDA(cudaMemcpyAsync(ctx->zcols.as<uint8_t>() + 16, ocols.data(), ocols.size() * sizeof(OndiskCol), cudaMemcpyHostToDevice, ctx->stream));
+        k_finish_ondisk_cols<<<cdiv(ocols.size(), 128), 128, 0, ctx->stream>>>(out->arena.as<uint8_t>(), out->cols.as<DevColumn>(), (const OndiskCol*)(ctx->zcols.as<uint8_t>() + 16),
+                                                                                 (uint32_t)ocols.size(), ctx->zcols.as<unsigned long long>());
+        launch_check(ctx);
+        h2d += ocols.size() * sizeof(OndiskCol);
+        zjob.check(ctx);   // synchronises the stream
+        unsigned long long cst[2] = {0, 0};
+        VL_CUDA(cudaMemcpy(cst, ctx->zcols.p, 16, cudaMemcpyDeviceToHost));
+        static const char* what[] = {"", "cannot unmarshal uint64 block type from empty src", "unexpected uint64 block type", "unexpected block length for uint items", "row length does not fit 32 bits"};
+        if (cst[0]) throw BadInput(what[std::min<unsigned long long>(cst[0], 4)]);
+    }
     if (dbg) { VL_CUDA(cudaStreamSynchronize(ctx->stream)); t_copy = now(); }
     if (nfields) out->note_columns(cols);
     finish_batch_layout(ctx, out, rows);   // synchronises the stream => `owned`, `cols`, staging are safe to drop
@@ -531,6 +554,8 @@ void vlscan_ctx_free(vlscan_ctx* ctx) {
     for (auto& r : ctx->regs) r.release();
     for (auto& r : ctx->row_off64) r.release();
     for (auto& r : ctx->ready) r.release();
+    ctx->zsrc.release(); ctx->zcols.release(); ctx->ztest.release();
+    zstd_dev_free(ctx->zdev);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     delete ctx->recycle;
     for (auto& e : ctx->scan_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -629,6 +654,110 @@ int vlscan_batch_download(vlscan_ctx* ctx, const vlscan_batch* batch, vlscan_hos
     *out = hb;
     return 0;
 }
+// The reference's writer for one values block: marshalBytesBlock(lens items) ++ marshalBytesBlock(data) (encoding.go:16-50, 343-370)
+static void marshal_bytes_block(std::vector<uint8_t>& dst, const uint8_t* src, size_t n) {
+    if (n < 128) { dst.push_back(0); dst.push_back((uint8_t)n); dst.insert(dst.end(), src, src + n); return; }
+    ZstdWriter& z = zstd_writer();
+    if (!z.ok) throw BadInput("libzstd.so.1 is not available for compressing values blocks");
+    int level = n <= 512 ? 1 : n <= 4096 ? 2 : 3;   // getCompressLevel, encoding.go:362-370
+    size_t cap = z.bound(n), old = dst.size();
+    dst.push_back(1);
+    dst.resize(old + 1 + 10 + cap);
+    size_t got = z.compress(dst.data() + old + 11, cap, src, n, level);
+    if (z.is_error(got)) throw BadInput("ZSTD_compress failed");
+    uint8_t vu[10]; int k = 0; uint64_t v = got; while (v >= 0x80) { vu[k++] = (uint8_t)(v | 0x80); v >>= 7; } vu[k++] = (uint8_t)v;   // MarshalVarUint64
+    memcpy(dst.data() + old + 1, vu, k);
+    memmove(dst.data() + old + 1 + k, dst.data() + old + 11, got);
+    dst.resize(old + 1 + k + got);
+}
+
+int vlscan_host_blocks_compress(const vlscan_host_blocks* in, int threads, vlscan_host_blocks** out) {
+    *out = nullptr;
+    auto* hb = new vlscan_host_blocks();
+    int rc = guarded(nullptr, [&] {
+        const size_t ncols = in->cols.size();
+        std::vector<std::vector<uint8_t>> packed(ncols);
+        std::atomic<size_t> next{0}; std::atomic<bool> failed{false}; std::string fail_msg; std::mutex mu;
+        auto work = [&] {
+            for (;;) {
+                size_t i0 = next.fetch_add(64); if (i0 >= ncols || failed) return;
+                for (size_t i = i0; i < std::min(ncols, i0 + 64); i++) {
+                    const vlscan_column& c = in->cols[i];
+                    if (c.kind != VLSCAN_COL_VALUES) continue;
+                    try {
+                        if (c.stage == VLSCAN_STAGE_ONDISK) packed[i].assign(c.values, c.values + c.values_len);
+                        else { marshal_bytes_block(packed[i], c.lens_items, c.lens_items_len); marshal_bytes_block(packed[i], c.data, c.data_len); }
+                    } catch (const BadInput& e) { std::lock_guard<std::mutex> g(mu); fail_msg = e.msg; failed = true; return; }
+                }
+            }
+        };
+        int nt = threads > 0 ? threads : (int)std::max(1u, std::thread::hardware_concurrency());
+        std::vector<std::thread> pool; for (int t = 1; t < nt; t++) pool.emplace_back(work);
+        work(); for (auto& t : pool) t.join();
+        if (failed) throw BadInput(fail_msg);
+        // layout: [copied part: consts, blooms, dict tables, strided exactly like the upload arena][values blocks, back to back]
+        uint64_t cursor = 16, vbytes = 0;
+        std::vector<uint64_t> off_a(ncols, 0), off_b(ncols, 0), off_v(ncols, 0);
+        for (size_t i = 0; i < ncols; i++) {
+            const vlscan_column& c = in->cols[i];
+            if (c.kind == VLSCAN_COL_CONST) { off_a[i] = arena_reserve(cursor, c.const_len); continue; }
+            off_a[i] = arena_reserve(cursor, c.bloom_len);
+            if (c.value_type == VT_DICT) off_b[i] = arena_reserve(cursor, 4 * (c.dict_len + 1) + (c.dict_len ? c.dict_offsets[c.dict_len] : 0));
+            off_v[i] = vbytes; vbytes += packed[i].size();
+        }
+        const uint64_t vbase = (cursor + kArenaPad + 63) / 64 * 64;
+        hb->bytes = vbase + vbytes + 64;
+        VL_CUDA(cudaMallocHost(&hb->pinned, hb->bytes));
+        uint8_t* base = (uint8_t*)hb->pinned;
+        memset(base, 0, vbase);
+        hb->fields = in->fields; hb->cols = in->cols; hb->blocks = in->blocks;
+        for (size_t i = 0; i < ncols; i++) {
+            vlscan_column& c = hb->cols[i];
+            if (c.kind == VLSCAN_COL_CONST) { if (c.const_len) memcpy(base + off_a[i], c.const_value, c.const_len); c.const_value = base + off_a[i]; continue; }
+            if (c.bloom_len) memcpy(base + off_a[i], c.bloom, c.bloom_len);
+            c.bloom = base + off_a[i];
+            if (c.value_type == VT_DICT) {
+                uint32_t total = c.dict_len ? c.dict_offsets[c.dict_len] : 0;
+                uint8_t* m = base + off_b[i];
+                if (c.dict_len) memcpy(m, c.dict_offsets, 4 * (c.dict_len + 1)); else memset(m, 0, 4);
+                if (total) memcpy(m + 4 * (c.dict_len + 1), c.dict_blob, total);
+                c.dict_offsets = (const uint32_t*)m; c.dict_blob = m + 4 * (c.dict_len + 1);
+            }
+            memcpy(base + vbase + off_v[i], packed[i].data(), packed[i].size());
+            c.stage = VLSCAN_STAGE_ONDISK; c.values = base + vbase + off_v[i]; c.values_len = packed[i].size();
+            c.lens_items = nullptr; c.lens_items_len = 0; c.data = nullptr; c.data_len = 0;
+            std::vector<uint8_t>().swap(packed[i]);
+        }
+        size_t k = 0;
+        for (size_t b = 0; b < hb->blocks.size(); b++) { hb->blocks[b].cols = hb->cols.data() + k; k += hb->blocks[b].ncols; }
+    });
+    if (rc) { if (hb->pinned) cudaFreeHost(hb->pinned); delete hb; return rc; }
+    *out = hb;
+    return 0;
+}
+
+int vlscan_zstd_decompress(vlscan_ctx* ctx, uint32_t nframes, const void* const* frames, const size_t* frame_lens, void* dst, const uint64_t* dst_offsets) {
+    return guarded(ctx, [&] {
+        VL_CUDA(cudaSetDevice(ctx->device));
+        ZstdJob job;
+        std::vector<uint8_t> packed(16, 0);
+        for (uint32_t i = 0; i < nframes; i++) {
+            uint64_t regen = 0; uint32_t id = 0;
+            job.add_frame((const uint8_t*)frames[i], frame_lens[i], packed.size(), &regen, &id);
+            if (regen != dst_offsets[i + 1] - dst_offsets[i]) throw BadInput("cannot decompress block: frame content size differs from the destination size");
+            job.set_dst(id, 16 + dst_offsets[i]);
+            packed.insert(packed.end(), (const uint8_t*)frames[i], (const uint8_t*)frames[i] + frame_lens[i]);
+        }
+        const uint64_t total = nframes ? dst_offsets[nframes] : 0;
+        ctx->zsrc.ensure(packed.size() + 64); ctx->ztest.ensure(16 + total + 64);
+        VL_CUDA(cudaMemcpyAsync(ctx->zsrc.p, packed.data(), packed.size(), cudaMemcpyHostToDevice, ctx->stream));
+        VL_CUDA(cudaMemsetAsync(ctx->ztest.p, 0xA5, 16 + total + 64, ctx->stream));
+        job.run(ctx, ctx->zsrc.as<uint8_t>(), ctx->ztest.as<uint8_t>());
+        job.check(ctx);
+        if (total) VL_CUDA(cudaMemcpy(dst, ctx->ztest.as<uint8_t>() + 16, total, cudaMemcpyDeviceToHost));
+    });
+}
+
 const vlscan_block* vlscan_host_blocks_get(const vlscan_host_blocks* hb, uint64_t* nblocks, uint32_t* nfields) { *nblocks = hb->blocks.size(); *nfields = (uint32_t)hb->fields.size(); return hb->blocks.data(); }
 const char* vlscan_host_blocks_field(const vlscan_host_blocks* hb, uint32_t i, size_t* len) { *len = hb->fields[i].size(); return hb->fields[i].data(); }
 uint64_t vlscan_host_blocks_bytes(const vlscan_host_blocks* hb) { return hb->bytes; }

@@ -7,6 +7,7 @@
 #include <vector>
 #include "../../include/vlscan.h"
 #include "vl_kernels.cuh"
+#include "vl_zstd.h"
 
 namespace vl {
 
@@ -79,6 +80,8 @@ struct vlscan_ctx {
     std::vector<vl::DevBuf> row_off64;     // per batch field slot
     std::vector<vl::DevBuf> ready;         // per batch field slot: row_off64 computed for block b in this scan
     std::vector<char> ready_cleared;
+    vl::DevBuf zsrc, zcols, ztest;         // compressed staging of on-disk values blocks; their column list; test output
+    vl::ZstdDev* zdev = nullptr;           // device ZSTD decoder scratch (vl_zstd.cu)
     void* pinned = nullptr; size_t pinned_cap = 0;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> scan_events; size_t scan_events_used = 0;

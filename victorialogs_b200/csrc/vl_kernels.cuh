@@ -346,6 +346,37 @@ static __global__ void k_plan_leaf(DevProgram P, BatchView B, uint32_t leaf_idx,
     }
 }
 
+// ---- on-disk columns: header checks of the lens block (unmarshalUint64Items, encoding.go:246-336) once the device has regenerated it ----
+// The uint block type byte sits right in front of the lens items (lens_off - 1).  status[0] = max error code.
+struct OndiskCol { uint64_t col; uint64_t lens_total; uint64_t rows; };
+static __global__ void k_finish_ondisk_cols(const uint8_t* __restrict__ arena, DevColumn* __restrict__ cols, const OndiskCol* __restrict__ oc, uint32_t n,
+                                            unsigned long long* __restrict__ status) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    DevColumn& c = cols[oc[i].col];
+    const uint64_t total = oc[i].lens_total, rows = oc[i].rows;
+    unsigned err = 0;
+    if (total < 1) err = 1;
+    else {
+        const uint8_t* p = arena + c.lens_off - 1;
+        uint32_t lt = p[0];
+        if (lt > 7) err = 2;
+        else {
+            uint64_t want = lt < 4 ? (rows << lt) : (1ull << (lt - 4));
+            if (total - 1 != want) err = 3;
+            else {
+                c.lens_type = (uint8_t)lt;
+                if (lt >= 4) {
+                    uint64_t v = 0; for (uint64_t k = 0; k < want; k++) v = (v << 8) | p[1 + k];
+                    if (v > 0xFFFFFFFFull) err = 4;
+                    else { c.lens_const = (uint32_t)v; c.data_const = (rows >= 2 && c.data_len == v) ? 1 : 0; }   // encoding.go:113-120
+                }
+            }
+        }
+    }
+    if (err) atomicMax(&status[0], (unsigned long long)err);
+}
+
 // ---- lens decode -> per-bitmap-word row offsets (unmarshalUint64Items + the offsets implied by encoding.go:122-130) -----------------
 // row_off64[w] = byte offset (within the block's data) of row 64*(w - first word of the block).  One CTA per work item.
 static __global__ void k_lens_offsets(BatchView B, int slot, const uint32_t* __restrict__ work_blocks, const uint32_t* __restrict__ work_count,

@@ -1,0 +1,284 @@
+// Device ZSTD decoder: host-side frame walk, scratch layout and launch sequence.  See vl_zstd.cuh for the kernels.
+#include "vl_zstd.h"
+
+#include <algorithm>
+#include <cstring>
+
+#include "vl_engine.h"
+#include "vl_zstd.cuh"
+
+namespace vl {
+
+using namespace zs;
+
+struct ZstdDev {
+    DevBuf frames, blocks, bstate, huf_tab, fse_tab, huf_state, fse_state, predef, lits, seqs, frame_err, status, lists;
+    bool predef_ready = false;
+    void release() {
+        DevBuf* all[] = {&frames, &blocks, &bstate, &huf_tab, &fse_tab, &huf_state, &fse_state, &predef, &lits, &seqs, &frame_err, &status, &lists};
+        for (DevBuf* b : all) b->release();
+    }
+};
+void zstd_dev_free(ZstdDev* d) { if (d) { d->release(); delete d; } }
+
+namespace {
+const uint32_t kNone = 0xFFFFFFFEu;                 // "no table seen yet in this frame"
+const uint64_t kMaxFrameContent = 1ull << 30;       // a values block never regenerates more than this (consts.go: blocks are <= 2 MB uncompressed)
+const uint32_t kBlockMax = 128u << 10;              // Block_Maximum_Size upper bound
+// scratch limits of one launch group (groups are cut at frame boundaries)
+const uint64_t kGroupLits = 1ull << 30, kGroupSeqs = 48ull << 20;
+const uint32_t kGroupSlots = 48u << 10;
+
+inline uint32_t le16(const uint8_t* p) { return p[0] | (p[1] << 8); }
+inline uint32_t le24(const uint8_t* p) { return p[0] | (p[1] << 8) | (p[2] << 16); }
+inline uint32_t le32(const uint8_t* p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
+inline uint64_t le40(const uint8_t* p) { return (uint64_t)le32(p) | ((uint64_t)p[4] << 32); }
+inline uint64_t le64(const uint8_t* p) { return (uint64_t)le32(p) | ((uint64_t)le32(p + 4) << 32); }
+inline unsigned cdiv_u(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
+
+struct Group { uint32_t frame_lo, frame_hi; uint32_t huf_lo, huf_hi, lit_lo, lit_hi, seq_lo, seq_hi, ord_lo, ord_hi; };
+}  // namespace
+
+struct ZstdJob::Impl {
+    std::vector<ZFrame> frames;
+    std::vector<ZBlock> blocks;
+    std::vector<Group> groups;
+    // running scratch use of the open group
+    uint64_t g_lits = 0, g_seqs = 0; uint32_t g_huf = 0, g_fse = 0; uint32_t g_frame_lo = 0;
+    uint64_t max_lits = 0, max_seqs = 0; uint32_t max_huf = 0, max_fse = 0;
+    uint64_t n_compressed = 0, n_seqs = 0;
+    bool ran = false;
+
+    void close_group() {
+        if (g_frame_lo == frames.size()) return;
+        Group g{}; g.frame_lo = g_frame_lo; g.frame_hi = (uint32_t)frames.size();
+        groups.push_back(g);
+        max_lits = std::max(max_lits, g_lits); max_seqs = std::max(max_seqs, g_seqs); max_huf = std::max(max_huf, g_huf); max_fse = std::max(max_fse, g_fse);
+        g_lits = g_seqs = 0; g_huf = g_fse = 0; g_frame_lo = (uint32_t)frames.size();
+    }
+
+    // Assigns scratch to the blocks [blk_lo, end) of the frame that was just parsed and appends the frame.
+    void commit_frame(ZFrame fr) {
+        uint64_t lits = 0, seqs = 0; uint32_t huf = 0, fse = 0;
+        for (uint32_t i = fr.blk_lo; i < blocks.size(); i++) {
+            const ZBlock& b = blocks[i];
+            if (b.type != ZB_COMPRESSED) continue;
+            if (b.lit_type >= ZL_COMPRESSED) lits += b.lit_regen;
+            seqs += b.nseq; huf += b.huf_own != Z_PREDEF; fse += b.fse_own != Z_PREDEF;
+        }
+        if (g_frame_lo != frames.size() && (g_lits + lits > kGroupLits || g_seqs + seqs > kGroupSeqs || g_huf + huf > kGroupSlots || g_fse + fse > kGroupSlots)) close_group();
+        // slots inside the frame were numbered from 0; rebase them into the group
+        for (uint32_t i = fr.blk_lo; i < blocks.size(); i++) {
+            ZBlock& b = blocks[i];
+            if (b.type != ZB_COMPRESSED) continue;
+            if (b.lit_type >= ZL_COMPRESSED) { b.lit_off = g_lits; g_lits += b.lit_regen; }
+            b.seq_base = g_seqs; g_seqs += b.nseq;
+            if (b.huf_own != Z_PREDEF) b.huf_own += g_huf;
+            if (b.huf_slot != Z_PREDEF) b.huf_slot += g_huf;
+            if (b.fse_own != Z_PREDEF) b.fse_own += g_fse;
+            if (b.ll_slot != Z_PREDEF) b.ll_slot += g_fse;
+            if (b.of_slot != Z_PREDEF) b.of_slot += g_fse;
+            if (b.ml_slot != Z_PREDEF) b.ml_slot += g_fse;
+            n_compressed++; n_seqs += b.nseq;
+        }
+        g_huf += huf; g_fse += fse;
+        fr.blk_hi = (uint32_t)blocks.size();
+        frames.push_back(fr);
+    }
+
+    void parse_compressed_block(const uint8_t* b, uint32_t bsize, ZBlock& B, uint32_t& frame_huf, uint32_t& frame_fse, uint32_t& prev_huf, uint32_t prev_fse[3]) {
+        if (bsize < 2) throw BadInput("cannot decompress block: compressed ZSTD block is too short");
+        uint32_t lt = b[0] & 3, sf = (b[0] >> 2) & 3, hl, regen, comp, streams = 0;
+        if (lt < ZL_COMPRESSED) {
+            if (sf == 0 || sf == 2) { hl = 1; regen = b[0] >> 3; }
+            else if (sf == 1) { hl = 2; regen = le16(b) >> 4; }
+            else { hl = 3; if (bsize < 3) throw BadInput("cannot decompress block: truncated literals header"); regen = le24(b) >> 4; }
+            comp = lt == ZL_RAW ? regen : 1;
+        } else {
+            if (bsize < 5) throw BadInput("cannot decompress block: truncated literals header");
+            if (sf < 2) { hl = 3; uint32_t v = le24(b); regen = (v >> 4) & 0x3FF; comp = v >> 14; streams = sf == 0 ? 1 : 4; }
+            else if (sf == 2) { hl = 4; uint32_t v = le32(b); regen = (v >> 4) & 0x3FFF; comp = v >> 18; streams = 4; }
+            else { hl = 5; uint64_t v = le40(b); regen = (uint32_t)((v >> 4) & 0x3FFFF); comp = (uint32_t)(v >> 22); streams = 4; }
+        }
+        if (regen > kBlockMax) throw BadInput("cannot decompress block: literals section exceeds the maximum block size");
+        if ((uint64_t)hl + comp >= bsize) throw BadInput("cannot decompress block: literals section exceeds the block");
+        uint32_t q = hl + comp, nseq = b[q];
+        if (nseq < 128) q += 1;
+        else if (nseq < 255) { if (q + 2 > bsize) throw BadInput("cannot decompress block: truncated sequences header"); nseq = ((nseq - 128) << 8) + b[q + 1]; q += 2; }
+        else { if (q + 3 > bsize) throw BadInput("cannot decompress block: truncated sequences header"); nseq = b[q + 1] + (b[q + 2] << 8) + 0x7F00; q += 3; }
+        B.lit_type = (uint8_t)lt; B.lit_streams = (uint8_t)streams; B.lit_hdr = hl; B.lit_regen = regen; B.lit_comp = comp; B.nseq = nseq; B.seq_hdr = q;
+        B.huf_own = Z_PREDEF; B.huf_slot = Z_PREDEF; B.fse_own = Z_PREDEF; B.ll_slot = B.of_slot = B.ml_slot = Z_PREDEF; B.modes = 0;
+        if (lt == ZL_COMPRESSED) { B.huf_own = B.huf_slot = frame_huf++; prev_huf = B.huf_own; }
+        else if (lt == ZL_TREELESS) { if (prev_huf == kNone) throw BadInput("cannot decompress block: treeless literals without a previous Huffman table"); B.huf_slot = prev_huf; }
+        if (nseq == 0) { if (q != bsize) throw BadInput("cannot decompress block: bytes after an empty sequences section"); return; }
+        if (q >= bsize) throw BadInput("cannot decompress block: truncated sequences header");
+        B.modes = b[q];
+        if (B.modes & 3) throw BadInput("cannot decompress block: reserved bits set in the symbol compression modes");
+        uint32_t* slot[3] = {&B.ll_slot, &B.of_slot, &B.ml_slot};
+        for (int k = 0; k < 3; k++) {
+            int mode = (B.modes >> (6 - 2 * k)) & 3;
+            if (mode == 0) *slot[k] = Z_PREDEF;
+            else if (mode == 3) { if (prev_fse[k] == kNone) throw BadInput("cannot decompress block: repeat mode without a previous table"); *slot[k] = prev_fse[k]; }
+            else { if (B.fse_own == Z_PREDEF) B.fse_own = frame_fse++; *slot[k] = B.fse_own; }
+            prev_fse[k] = *slot[k];
+        }
+    }
+
+    void parse_frame(const uint8_t* f, size_t n, uint64_t zoff, uint64_t* regen, uint32_t* id) {
+        if (n < 6 || le32(f) != 0xFD2FB528u) throw BadInput("cannot decompress block: not a ZSTD frame");
+        uint32_t fhd = f[4], fcs_flag = fhd >> 6, single = (fhd >> 5) & 1, cks = (fhd >> 2) & 1, did_flag = fhd & 3;
+        if (fhd & 8) throw BadInput("cannot decompress block: reserved bit set in the frame header");
+        size_t pos = 5;
+        uint64_t window = 0;
+        if (!single) {
+            if (pos >= n) throw BadInput("cannot decompress block: truncated frame header");
+            uint32_t wd = f[pos++]; uint32_t wlog = 10 + (wd >> 3);
+            if (wlog > 31) throw BadInput("cannot decompress block: window too large");
+            window = (1ull << wlog) + ((1ull << wlog) >> 3) * (wd & 7);
+        }
+        static const int did_sz[4] = {0, 1, 2, 4};
+        if (pos + did_sz[did_flag] > n) throw BadInput("cannot decompress block: truncated frame header");
+        uint32_t did = 0; for (int i = 0; i < did_sz[did_flag]; i++) did |= (uint32_t)f[pos + i] << (8 * i);
+        pos += did_sz[did_flag];
+        if (did) throw BadInput("cannot decompress block: dictionaries are not supported");
+        int fcs_sz = fcs_flag == 0 ? (single ? 1 : 0) : fcs_flag == 1 ? 2 : fcs_flag == 2 ? 4 : 8;
+        if (!fcs_sz) throw BadInput("cannot decompress block: the frame does not declare its content size");
+        if (pos + fcs_sz > n) throw BadInput("cannot decompress block: truncated frame header");
+        uint64_t fcs = fcs_sz == 1 ? f[pos] : fcs_sz == 2 ? le16(f + pos) + 256u : fcs_sz == 4 ? le32(f + pos) : le64(f + pos);
+        pos += fcs_sz;
+        if (fcs > kMaxFrameContent) throw BadInput("cannot decompress block: frame content size is too large");
+        if (single) window = fcs;
+        const uint32_t block_max = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(window, 1), kBlockMax);
+        ZFrame fr{}; fr.fcs = fcs; fr.blk_lo = (uint32_t)blocks.size(); fr.dst = 0;
+        uint32_t frame_huf = 0, frame_fse = 0, prev_huf = kNone, prev_fse[3] = {kNone, kNone, kNone};
+        const uint32_t fid = (uint32_t)frames.size();
+        for (;;) {
+            if (pos + 3 > n) throw BadInput("cannot decompress block: truncated block header");
+            uint32_t h = le24(f + pos); pos += 3;
+            uint32_t last = h & 1, type = (h >> 1) & 3, bsize = h >> 3;
+            if (type == 3) throw BadInput("cannot decompress block: reserved block type");
+            if (bsize > block_max) throw BadInput("cannot decompress block: block exceeds the maximum block size");
+            size_t content = type == ZB_RLE ? 1 : bsize;
+            if (pos + content > n) throw BadInput("cannot decompress block: truncated block");
+            ZBlock B{}; B.src = zoff + pos; B.size = bsize; B.frame = fid; B.type = (uint8_t)type;
+            B.huf_own = B.huf_slot = B.fse_own = B.ll_slot = B.of_slot = B.ml_slot = Z_PREDEF;
+            if (type == ZB_COMPRESSED) parse_compressed_block(f + pos, bsize, B, frame_huf, frame_fse, prev_huf, prev_fse);
+            blocks.push_back(B);
+            pos += content;
+            if (last) break;
+        }
+        if (cks) { if (pos + 4 > n) throw BadInput("cannot decompress block: truncated content checksum"); pos += 4; }   // not verified
+        if (pos != n) throw BadInput("cannot decompress block: unexpected bytes after the ZSTD frame");
+        *regen = fcs; *id = fid;
+        commit_frame(fr);
+    }
+};
+
+ZstdJob::ZstdJob() : m(new Impl) {}
+ZstdJob::~ZstdJob() { delete m; }
+bool ZstdJob::empty() const { return m->frames.empty(); }
+uint64_t ZstdJob::frames() const { return m->frames.size(); }
+uint64_t ZstdJob::compressed_blocks() const { return m->n_compressed; }
+uint64_t ZstdJob::sequences() const { return m->n_seqs; }
+void ZstdJob::set_dst(uint32_t id, uint64_t arena_off) { m->frames[id].dst = arena_off; }
+
+void ZstdJob::add_frame(const uint8_t* f, size_t n, uint64_t zoff, uint64_t* regen, uint32_t* id) { m->parse_frame(f, n, zoff, regen, id); }
+
+size_t ZstdJob::add_bytes_block(const uint8_t* p, size_t n, uint64_t zoff, uint64_t* regen, uint32_t* id) {
+    if (n < 1) throw BadInput("cannot unmarshal block type from empty src");
+    if (p[0] == 0) {           // marshalBytesTypePlain
+        if (n < 2) throw BadInput("cannot unmarshal plain block size from empty src");
+        size_t len = p[1];
+        if (n - 2 < len) throw BadInput("cannot read plain block: not enough bytes");
+        ZFrame fr{}; fr.fcs = len; fr.blk_lo = (uint32_t)m->blocks.size();
+        ZBlock B{}; B.src = zoff + 2; B.size = (uint32_t)len; B.frame = (uint32_t)m->frames.size(); B.type = ZB_RAW;
+        B.huf_own = B.huf_slot = B.fse_own = B.ll_slot = B.of_slot = B.ml_slot = Z_PREDEF;
+        m->blocks.push_back(B);
+        *regen = len; *id = (uint32_t)m->frames.size();
+        m->commit_frame(fr);
+        return 2 + len;
+    }
+    if (p[0] == 1) {           // marshalBytesTypeZSTD
+        uint64_t clen = 0; int sh = 0; size_t i = 1; bool done = false;
+        for (; i < n && i < 11; i++) { clen |= (uint64_t)(p[i] & 0x7F) << sh; sh += 7; if (p[i] < 0x80) { done = true; i++; break; } }
+        if (!done) throw BadInput("cannot unmarshal compressed block size");
+        if (n - i < clen) throw BadInput("cannot read compressed block: not enough bytes");
+        m->parse_frame(p + i, clen, zoff + i, regen, id);
+        return i + clen;
+    }
+    throw BadInput("unexpected block type; supported types: 0, 1");
+}
+
+void ZstdJob::run(vlscan_ctx* ctx, const uint8_t* zsrc, uint8_t* arena) {
+    Impl& J = *m;
+    if (J.frames.empty()) return;
+    J.close_group();
+    if (!ctx->zdev) ctx->zdev = new ZstdDev;
+    ZstdDev& D = *ctx->zdev;
+    cudaStream_t st = ctx->stream;
+    // per group work lists, all in one upload: blocks with a Huffman description | blocks with Huffman streams | blocks with sequences |
+    // frames ordered by size (largest first: the tail of a launch is then made of short frames)
+    std::vector<uint32_t> lists;
+    for (Group& g : J.groups) {
+        const uint32_t blo = J.frames[g.frame_lo].blk_lo, bhi = J.frames[g.frame_hi - 1].blk_hi;
+        auto by_desc = [&](std::vector<std::pair<uint32_t, uint32_t>>& v) { std::stable_sort(v.begin(), v.end(), [](const auto& a, const auto& b) { return a.first > b.first; }); for (auto& e : v) lists.push_back(e.second); };
+        std::vector<std::pair<uint32_t, uint32_t>> v;
+        for (uint32_t i = blo; i < bhi; i++) if (J.blocks[i].type == ZB_COMPRESSED && J.blocks[i].lit_type == ZL_COMPRESSED) v.push_back({0, i});
+        g.huf_lo = (uint32_t)lists.size(); by_desc(v); g.huf_hi = (uint32_t)lists.size(); v.clear();
+        for (uint32_t i = blo; i < bhi; i++) if (J.blocks[i].type == ZB_COMPRESSED && J.blocks[i].lit_type >= ZL_COMPRESSED) v.push_back({J.blocks[i].lit_regen >> 9, i});
+        g.lit_lo = (uint32_t)lists.size(); by_desc(v); g.lit_hi = (uint32_t)lists.size(); v.clear();
+        for (uint32_t i = blo; i < bhi; i++) if (J.blocks[i].type == ZB_COMPRESSED && J.blocks[i].nseq) v.push_back({J.blocks[i].nseq >> 6, i});
+        g.seq_lo = (uint32_t)lists.size(); by_desc(v); g.seq_hi = (uint32_t)lists.size(); v.clear();
+        for (uint32_t i = g.frame_lo; i < g.frame_hi; i++) v.push_back({(uint32_t)(J.frames[i].fcs >> 10), i});
+        g.ord_lo = (uint32_t)lists.size(); by_desc(v); g.ord_hi = (uint32_t)lists.size();
+    }
+    D.frames.ensure(J.frames.size() * sizeof(ZFrame)); D.blocks.ensure(J.blocks.size() * sizeof(ZBlock)); D.bstate.ensure(J.blocks.size() * sizeof(ZBlockState));
+    D.frame_err.ensure(J.frames.size() * 4); D.status.ensure(16); D.lists.ensure(std::max<size_t>(lists.size() * 4, 16));
+    D.huf_tab.ensure(std::max<size_t>((size_t)J.max_huf * Z_HUF_TABLE * 2, 16)); D.huf_state.ensure(std::max<size_t>((size_t)J.max_huf * sizeof(ZSlotState), 16));
+    D.fse_tab.ensure(std::max<size_t>((size_t)J.max_fse * Z_FSE_SLOT * 4, 16)); D.fse_state.ensure(std::max<size_t>((size_t)J.max_fse * sizeof(ZSlotState), 16));
+    D.lits.ensure(J.max_lits + 64); D.seqs.ensure(std::max<size_t>(J.max_seqs * 16, 16));
+    if (!D.predef_ready) {
+        D.predef.ensure(Z_FSE_SLOT * 4);
+        k_zstd_predef<<<1, 32, 0, st>>>(D.predef.as<uint32_t>());
+        ctx->launches++; VL_CUDA(cudaGetLastError());
+        D.predef_ready = true;
+    }
+    VL_CUDA(cudaMemcpyAsync(D.frames.p, J.frames.data(), J.frames.size() * sizeof(ZFrame), cudaMemcpyHostToDevice, st));
+    VL_CUDA(cudaMemcpyAsync(D.blocks.p, J.blocks.data(), J.blocks.size() * sizeof(ZBlock), cudaMemcpyHostToDevice, st));
+    if (!lists.empty()) VL_CUDA(cudaMemcpyAsync(D.lists.p, lists.data(), lists.size() * 4, cudaMemcpyHostToDevice, st));
+    VL_CUDA(cudaMemsetAsync(D.frame_err.p, 0, J.frames.size() * 4, st));
+    VL_CUDA(cudaMemsetAsync(D.status.p, 0, 16, st));
+    VL_CUDA(cudaMemsetAsync(D.bstate.p, 0, J.blocks.size() * sizeof(ZBlockState), st));
+    ZView V{};
+    V.src = zsrc; V.arena = arena; V.frames = D.frames.as<ZFrame>(); V.blocks = D.blocks.as<ZBlock>(); V.bstate = D.bstate.as<ZBlockState>();
+    V.huf_tab = D.huf_tab.as<uint16_t>(); V.fse_tab = D.fse_tab.as<uint32_t>(); V.huf_state = D.huf_state.as<ZSlotState>(); V.fse_state = D.fse_state.as<ZSlotState>();
+    V.predef = D.predef.as<uint32_t>(); V.lits = D.lits.as<uint8_t>(); V.seqs = D.seqs.as<uint4>(); V.frame_err = D.frame_err.as<unsigned int>();
+    V.status = D.status.as<unsigned long long>();
+    const uint32_t* L = D.lists.as<uint32_t>();
+    auto launched = [&] { ctx->launches++; VL_CUDA(cudaGetLastError()); };
+    for (const Group& g : J.groups) {
+        uint32_t nh = g.huf_hi - g.huf_lo, nl = g.lit_hi - g.lit_lo, ns = g.seq_hi - g.seq_lo, nf = g.frame_hi - g.frame_lo;
+        if (nh) { k_huf_build<<<cdiv_u(nh, 4), 128, 0, st>>>(V, L + g.huf_lo, nh); launched(); }
+        if (nl) { k_huf_decode<<<cdiv_u((uint64_t)nl * 4, 128), 128, 0, st>>>(V, L + g.lit_lo, nl); launched(); }
+        if (ns) {
+            k_fse_build<<<cdiv_u(ns, 64), 64, 0, st>>>(V, L + g.seq_lo, ns); launched();
+            k_seq_decode<<<cdiv_u(ns, 64), 64, 0, st>>>(V, L + g.seq_lo, ns); launched();
+        }
+        k_seq_resolve<<<cdiv_u(nf, 64), 64, 0, st>>>(V, g.frame_lo, nf); launched();
+        k_execute<<<cdiv_u((uint64_t)nf * 32, 128), 128, 0, st>>>(V, L + g.ord_lo, nf); launched();
+    }
+    J.ran = true;
+}
+
+void ZstdJob::check(vlscan_ctx* ctx) {
+    if (!m->ran) return;
+    unsigned long long stt[2] = {0, 0};
+    VL_CUDA(cudaMemcpyAsync(stt, ctx->zdev->status.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    VL_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (!stt[0]) return;
+    static const char* what[] = {"", "bad Huffman tree description", "bad Huffman stream", "bad FSE table description", "bad sequences bitstream", "match offset beyond the regenerated data",
+                                 "regenerated size differs from the frame content size", "bad literals section"};
+    throw BadInput(std::string("cannot decompress block: ") + (stt[0] < 8 ? what[stt[0]] : "corrupted frame") + " (frame " + std::to_string(stt[1] - 1) + " of the batch)");
+}
+
+}  // namespace vl

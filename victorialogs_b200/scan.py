@@ -67,7 +67,7 @@ EXPORTS = ["vlscan_device_count", "vlscan_ctx_create", "vlscan_ctx_free", "vlsca
            "vlscan_program_create", "vlscan_program_free", "vlscan_program_nfields", "vlscan_program_field", "vlscan_program_leaf_tokens", "vlscan_format_float64",
            "vlscan_batch_upload", "vlscan_batch_free", "vlscan_batch_nblocks", "vlscan_batch_rows", "vlscan_batch_words", "vlscan_batch_device_bytes",
            "vlscan_batch_generate", "vlscan_batch_download", "vlscan_host_blocks_get", "vlscan_host_blocks_field", "vlscan_host_blocks_bytes",
-           "vlscan_host_blocks_free", "vlscan_scan_resident", "vlscan_last_scan_stats", "vlscan_fetch_results", "vlscan_fetch_hits", "vlscan_result_device_ptrs", "vlscan_scan_batch"]
+           "vlscan_host_blocks_free", "vlscan_host_blocks_compress", "vlscan_zstd_decompress", "vlscan_scan_resident", "vlscan_last_scan_stats", "vlscan_fetch_results", "vlscan_fetch_hits", "vlscan_result_device_ptrs", "vlscan_scan_batch"]
 
 
 def lib_path():
@@ -280,9 +280,12 @@ class HostBlocks:
 class DownloadedBlocks:
     """Host copy (pinned memory owned by the library) of a device-resident batch: vlscan_batch_download."""
 
-    def __init__(self, ctx, batch):
+    def __init__(self, ctx, batch, _handle=None):
         self.h = C.c_void_p()
-        ctx._check(lib().vlscan_batch_download(ctx.h, batch.h, C.byref(self.h)))
+        if _handle is not None:
+            self.h = _handle
+        else:
+            ctx._check(lib().vlscan_batch_download(ctx.h, batch.h, C.byref(self.h)))
         nb, nf = C.c_uint64(), C.c_uint32()
         self.blocks = lib().vlscan_host_blocks_get(self.h, C.byref(nb), C.byref(nf))
         self.nblocks = nb.value
@@ -314,10 +317,21 @@ class DownloadedBlocks:
                 offs = np.ctypeslib.as_array(C.cast(c.dict_offsets, C.POINTER(C.c_uint32)), (c.dict_len + 1,))
                 blob = C.string_at(c.dict_blob, int(offs[-1]))
                 d = [blob[int(offs[i]):int(offs[i + 1])] for i in range(c.dict_len)]
-            return dict(kind="values", value_type=c.value_type, min_value=c.min_value, max_value=c.max_value, dict=d,
-                        lens_items=C.string_at(c.lens_items, c.lens_items_len), data=C.string_at(c.data, c.data_len),
-                        bloom=C.string_at(c.bloom, c.bloom_len))
+            out = dict(kind="values", value_type=c.value_type, min_value=c.min_value, max_value=c.max_value, dict=d, bloom=C.string_at(c.bloom, c.bloom_len))
+            if c.stage == STAGE_ONDISK:
+                out["values_block"] = C.string_at(c.values, c.values_len)
+            else:
+                out["lens_items"], out["data"] = C.string_at(c.lens_items, c.lens_items_len), C.string_at(c.data, c.data_len)
+            return out
         return None
+
+    def compress(self, threads=0):
+        """Writer-side re-encoding into the on-disk stage (marshalBytesBlock, encoding.go:343-370): vlscan_host_blocks_compress."""
+        h = C.c_void_p()
+        rc = lib().vlscan_host_blocks_compress(self.h, C.c_int(threads), C.byref(h))
+        if rc:
+            raise VlscanError(rc, lib().vlscan_last_error(None).decode("utf-8", "replace"))
+        return DownloadedBlocks(None, None, _handle=h)
 
     def __del__(self):
         try:
@@ -368,6 +382,20 @@ class Ctx:
 
     def sync(self):
         self._check(lib().vlscan_ctx_sync(self.h))
+
+    def zstd_decompress(self, frames, sizes):
+        """Decode independent ZSTD frames (bytes) on the device -> list of bytes; sizes = regenerated size of each frame."""
+        n = len(frames)
+        keep = [C.create_string_buffer(f, len(f)) if f else C.create_string_buffer(1) for f in frames]
+        ptrs = (C.c_void_p * max(n, 1))(*[C.cast(k, C.c_void_p) for k in keep])
+        lens = (C.c_size_t * max(n, 1))(*[len(f) for f in frames])
+        offs = np.zeros(n + 1, dtype=np.uint64)
+        offs[1:] = np.cumsum(np.asarray(sizes, dtype=np.uint64)) if n else 0
+        total = int(offs[-1])
+        dst = C.create_string_buffer(max(total, 1))
+        self._check(lib().vlscan_zstd_decompress(self.h, C.c_uint32(n), ptrs, lens, dst, offs.ctypes.data_as(C.c_void_p)))
+        raw = dst.raw
+        return [raw[int(offs[i]):int(offs[i + 1])] for i in range(n)]
 
     def upload(self, host_blocks, stats=None):
         names, lens = host_blocks.name_arrays()
