@@ -299,9 +299,12 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
     out->cols.ensure(std::max<size_t>(cols.size() * sizeof(DevColumn), 16));
     if (!cols.empty()) VL_CUDA(cudaMemcpyAsync(out->cols.p, cols.data(), cols.size() * sizeof(DevColumn), cudaMemcpyHostToDevice, ctx->stream));
     h2d += cols.size() * sizeof(DevColumn);
+    double t_h2d = 0, t_zrun = 0;
+    if (dbg) { VL_CUDA(cudaStreamSynchronize(ctx->stream)); t_h2d = now(); }
     if (!ondisk.empty()) {
         // regenerate the on-disk payloads in HBM, then derive lens_type / lens_const / data_const from the regenerated lens blocks
         zjob.run(ctx, ctx->zsrc.as<uint8_t>(), out->arena.as<uint8_t>());
+        if (dbg) t_zrun = now();
         ctx->zcols.ensure(16 + ocols.size() * sizeof(OndiskCol));
         VL_CUDA(cudaMemsetAsync(ctx->zcols.p, 0, 16, ctx->stream));
         VL_CUDA(cudaMemcpyAsync(ctx->zcols.as<uint8_t>() + 16, ocols.data(), ocols.size() * sizeof(OndiskCol), cudaMemcpyHostToDevice, ctx->stream));
@@ -318,8 +321,10 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
     if (dbg) { VL_CUDA(cudaStreamSynchronize(ctx->stream)); t_copy = now(); }
     if (nfields) out->note_columns(cols);
     finish_batch_layout(ctx, out, rows);   // synchronises the stream => `owned`, `cols`, staging are safe to drop
-    if (dbg) fprintf(stderr, "[vlscan upload] blocks=%llu bytes=%.1f MB pieces=%zu pinned=%d: describe %.1f ms, alloc %.1f ms, copy %.1f ms (%.1f GB/s), layout %.1f ms\n", (unsigned long long)nblocks,
-                     out->arena_bytes / 1e6, pieces.size(), (int)all_pinned, 1e3 * (t_desc - t_start), 1e3 * (t_alloc - t_desc), 1e3 * (t_copy - t_alloc), h2d / 1e9 / std::max(t_copy - t_alloc, 1e-9), 1e3 * (now() - t_copy));
+    if (dbg) fprintf(stderr, "[vlscan upload] blocks=%llu arena=%.1f MB h2d=%.1f MB pieces=%zu+%zu pinned=%d: describe %.1f ms, alloc %.1f ms, copy %.1f ms (%.1f GB/s), "
+                             "zstd %llu frames / %llu blocks / %llu sequences: enqueue %.1f ms, decode %.1f ms; layout %.1f ms\n", (unsigned long long)nblocks,
+                     out->arena_bytes / 1e6, h2d / 1e6, pieces.size(), zpieces.size(), (int)all_pinned, 1e3 * (t_desc - t_start), 1e3 * (t_alloc - t_desc), 1e3 * (t_h2d - t_alloc), h2d / 1e9 / std::max(t_h2d - t_alloc, 1e-9),
+                     (unsigned long long)zjob.frames(), (unsigned long long)zjob.compressed_blocks(), (unsigned long long)zjob.sequences(), 1e3 * (t_zrun > 0 ? t_zrun - t_h2d : 0), 1e3 * (t_copy - (t_zrun > 0 ? t_zrun : t_h2d)), 1e3 * (now() - t_copy));
     h2d += out->nwords * 12 + nblocks * 12;
     if (stats) stats->h2d_bytes += h2d;
 }

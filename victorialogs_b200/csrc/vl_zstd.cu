@@ -2,6 +2,8 @@
 #include "vl_zstd.h"
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "vl_engine.h"
@@ -152,6 +154,7 @@ struct ZstdJob::Impl {
         ZFrame fr{}; fr.fcs = fcs; fr.blk_lo = (uint32_t)blocks.size(); fr.dst = 0;
         uint32_t frame_huf = 0, frame_fse = 0, prev_huf = kNone, prev_fse[3] = {kNone, kNone, kNone};
         const uint32_t fid = (uint32_t)frames.size();
+        bool seen_sequences = false;
         for (;;) {
             if (pos + 3 > n) throw BadInput("cannot decompress block: truncated block header");
             uint32_t h = le24(f + pos); pos += 3;
@@ -162,7 +165,11 @@ struct ZstdJob::Impl {
             if (pos + content > n) throw BadInput("cannot decompress block: truncated block");
             ZBlock B{}; B.src = zoff + pos; B.size = bsize; B.frame = fid; B.type = (uint8_t)type;
             B.huf_own = B.huf_slot = B.fse_own = B.ll_slot = B.of_slot = B.ml_slot = Z_PREDEF;
-            if (type == ZB_COMPRESSED) parse_compressed_block(f + pos, bsize, B, frame_huf, frame_fse, prev_huf, prev_fse);
+            if (type == ZB_COMPRESSED) {
+                parse_compressed_block(f + pos, bsize, B, frame_huf, frame_fse, prev_huf, prev_fse);
+                B.rep_known = seen_sequences ? 0 : 1;
+                if (B.nseq) seen_sequences = true;
+            }
             blocks.push_back(B);
             pos += content;
             if (last) break;
@@ -255,18 +262,33 @@ void ZstdJob::run(vlscan_ctx* ctx, const uint8_t* zsrc, uint8_t* arena) {
     V.predef = D.predef.as<uint32_t>(); V.lits = D.lits.as<uint8_t>(); V.seqs = D.seqs.as<uint4>(); V.frame_err = D.frame_err.as<unsigned int>();
     V.status = D.status.as<unsigned long long>();
     const uint32_t* L = D.lists.as<uint32_t>();
-    auto launched = [&] { ctx->launches++; VL_CUDA(cudaGetLastError()); };
+    // VLSCAN_DEBUG_TIMING: device time per phase (events around every launch; summed over the groups)
+    const bool dbg = getenv("VLSCAN_DEBUG_TIMING") != nullptr;
+    static const char* phase_name[6] = {"huf_build", "huf_decode", "fse_build", "seq_decode", "seq_resolve", "execute"};
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> marks;
+    int phase = 0;
+    auto begin = [&](int p) { phase = p; if (dbg) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); marks.push_back({p, {a, b}}); } };
+    auto launched = [&] { ctx->launches++; VL_CUDA(cudaGetLastError()); if (dbg) cudaEventRecord(marks.back().second.second, st); };
     for (const Group& g : J.groups) {
         uint32_t nh = g.huf_hi - g.huf_lo, nl = g.lit_hi - g.lit_lo, ns = g.seq_hi - g.seq_lo, nf = g.frame_hi - g.frame_lo;
-        if (nh) { k_huf_build<<<cdiv_u(nh, 4), 128, 0, st>>>(V, L + g.huf_lo, nh); launched(); }
-        if (nl) { k_huf_decode<<<cdiv_u((uint64_t)nl * 4, 128), 128, 0, st>>>(V, L + g.lit_lo, nl); launched(); }
+        if (nh) { begin(0); k_huf_build<<<cdiv_u(nh, 4), 128, 0, st>>>(V, L + g.huf_lo, nh); launched(); }
+        if (nl) { begin(1); k_huf_decode<<<cdiv_u((uint64_t)nl * 4, 128), 128, 0, st>>>(V, L + g.lit_lo, nl); launched(); }
         if (ns) {
-            k_fse_build<<<cdiv_u(ns, 64), 64, 0, st>>>(V, L + g.seq_lo, ns); launched();
-            k_seq_decode<<<cdiv_u(ns, 64), 64, 0, st>>>(V, L + g.seq_lo, ns); launched();
+            begin(2); k_fse_build<<<cdiv_u(ns, 64), 64, 0, st>>>(V, L + g.seq_lo, ns); launched();
+            begin(3); k_seq_decode<<<cdiv_u(ns, 64), 64, 0, st>>>(V, L + g.seq_lo, ns); launched();
         }
-        k_seq_resolve<<<cdiv_u(nf, 64), 64, 0, st>>>(V, g.frame_lo, nf); launched();
-        k_execute<<<cdiv_u((uint64_t)nf * 32, 128), 128, 0, st>>>(V, L + g.ord_lo, nf); launched();
+        begin(4); k_seq_resolve<<<cdiv_u(nf, 64), 64, 0, st>>>(V, g.frame_lo, nf); launched();
+        begin(5); k_execute<<<cdiv_u((uint64_t)nf * 32, 128), 128, 0, st>>>(V, L + g.ord_lo, nf); launched();
     }
+    if (dbg) {
+        VL_CUDA(cudaStreamSynchronize(st));
+        float tot[6] = {0, 0, 0, 0, 0, 0};
+        for (auto& mk : marks) { float ms = 0; cudaEventElapsedTime(&ms, mk.second.first, mk.second.second); tot[mk.first] += ms; cudaEventDestroy(mk.second.first); cudaEventDestroy(mk.second.second); }
+        fprintf(stderr, "[vlscan zstd] %zu groups:", J.groups.size());
+        for (int p = 0; p < 6; p++) fprintf(stderr, " %s %.2f ms", phase_name[p], tot[p]);
+        fprintf(stderr, "\n");
+    }
+    (void)phase;
     J.ran = true;
 }
 
