@@ -151,10 +151,79 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
     // regenerates them (vl_zstd.cuh) into arena regions placed behind everything that is copied, so that host memory laid out like
     // the copied part still goes out as one DMA.  Region offsets are relative to `regen_base` until the loop below has sized that part.
     ZstdJob zjob;
-    uint64_t zcursor = 16, regen_cursor = 0;
+    uint64_t zcursor = 64, regen_cursor = 0;   // headroom: the bit readers load whole aligned words around a stream
     struct Ondisk { uint64_t col; uint32_t lens_frame, data_frame; uint64_t lens_rel, data_rel; };
     std::vector<Ondisk> ondisk;
     std::vector<OndiskCol> ocols;
+    // copy pieces: runs that are contiguous on both sides (src stride == dst stride) and live in pinned host memory go out as one
+    // cudaMemcpyAsync; everything else is packed through a pinned staging ring.
+    uint64_t h2d = 0;
+    const size_t CH = 32u << 20;
+    uint8_t* stage = nullptr; cudaEvent_t evs[2] = {nullptr, nullptr}; int cur = 0; size_t fill = 0; uint64_t chunk_dst = 0; bool chunk_open = false;
+    uint8_t* dev_base = nullptr;   // destination buffer of the pieces being copied
+    auto flush = [&]() {
+        if (!chunk_open || !fill) { chunk_open = false; fill = 0; return; }
+        VL_CUDA(cudaMemcpyAsync(dev_base + chunk_dst, stage + (size_t)cur * CH, fill, cudaMemcpyHostToDevice, ctx->stream));
+        VL_CUDA(cudaEventRecord(evs[cur], ctx->stream));
+        h2d += fill; cur ^= 1; fill = 0; chunk_open = false;
+        VL_CUDA(cudaEventSynchronize(evs[cur]));
+    };
+    auto is_pinned = [&](const void* p) { cudaPointerAttributes a; if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; } return a.type == cudaMemoryTypeHost; };
+    auto need_stage = [&]() {
+        if (stage) return;
+        stage = (uint8_t*)ctx->ensure_pinned(2 * CH);
+        for (int k = 0; k < 2; k++) { VL_CUDA(cudaEventCreateWithFlags(&evs[k], cudaEventDisableTiming)); VL_CUDA(cudaEventRecord(evs[k], ctx->stream)); }
+    };
+    bool all_pinned = true;
+    auto copy_pieces = [&](const std::vector<Piece>& pieces, uint8_t* base) {
+    dev_base = base;
+    size_t i = 0;
+    while (i < pieces.size()) {
+        // maximal run of pieces laid out identically on both sides (same stride between source and destination)
+        size_t j = i;
+        while (j + 1 < pieces.size() && pieces[j + 1].src > pieces[j].src && pieces[j + 1].src - pieces[i].src == (ptrdiff_t)(pieces[j + 1].dst - pieces[i].dst)) j++;
+        uint64_t run_len = (pieces[j].dst - pieces[i].dst) + pieces[j].len;
+        if (is_pinned(pieces[i].src) && is_pinned(pieces[j].src + pieces[j].len - 1)) {
+            // page-locked caller memory: one DMA for the whole run, gaps (alignment slack) included
+            flush();
+            VL_CUDA(cudaMemcpyAsync(dev_base + pieces[i].dst, pieces[i].src, run_len, cudaMemcpyHostToDevice, ctx->stream));
+            h2d += run_len; i = j + 1;
+            continue;
+        }
+        all_pinned = false;
+        need_stage();
+        for (; i <= j; i++) {
+            const Piece& pc = pieces[i];
+            uint64_t done = 0;
+            while (done < pc.len) {
+                if (chunk_open && (chunk_dst + fill != pc.dst + done || fill == CH)) flush();
+                if (!chunk_open) { chunk_open = true; chunk_dst = pc.dst + done; fill = 0; }
+                size_t take = (size_t)std::min<uint64_t>(pc.len - done, CH - fill);
+                memcpy(stage + (size_t)cur * CH + fill, pc.src + done, take);
+                fill += take; done += take;
+            }
+            // pack the inter-piece slack (zero in the arena already) when the next piece follows closely, so chunks stay large
+            if (i + 1 < pieces.size()) {
+                uint64_t gap = pieces[i + 1].dst - (pc.dst + pc.len);
+                if (gap <= 64 && fill + gap < CH) { memset(stage + (size_t)cur * CH + fill, 0, gap); fill += gap; } else flush();
+            }
+        }
+    }
+    flush();
+    };
+    // Pre-pass: the compressed bytes of on-disk values blocks are shipped first (their place in the staging buffer is a running sum), so
+    // that the DMA engine is busy while the host walks frame and block headers in the loop below.
+    {
+        uint64_t zc = 64;
+        for (uint64_t b = 0; b < nblocks; b++)
+            for (uint32_t k = 0; k < blocks[b].ncols; k++) {
+                const vlscan_column& c = blocks[b].cols[k];
+                if (c.kind != VLSCAN_COL_VALUES || c.stage != VLSCAN_STAGE_ONDISK) continue;
+                if (c.values_len) zpieces.push_back({c.values, c.values_len, zc});
+                zc += c.values_len;
+            }
+        if (!zpieces.empty()) { ctx->zsrc.ensure(zc + 64); copy_pieces(zpieces, ctx->zsrc.as<uint8_t>()); }
+    }
     for (uint64_t b = 0; b < nblocks; b++) {
         const vlscan_block& blk = blocks[b];
         if (blk.rows > (8u << 20)) throw BadInput("block rows exceed maxRowsPerBlock (8Mi)");   // consts.go:24
@@ -175,7 +244,6 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
                 // stringsBlockUnmarshaler.unmarshal: bytesBlock(lens) ++ bytesBlock(data) (encoding.go:83-108).  The host reads the
                 // containers, the frame header and the block headers; the payload is regenerated on the device.
                 const uint64_t zoff = zcursor; zcursor += c.values_len;
-                if (c.values_len) zpieces.push_back({c.values, c.values_len, zoff});
                 uint64_t lens_len = 0, data_len = 0; uint32_t f1 = 0, f2 = 0;
                 size_t c1 = zjob.add_bytes_block(c.values, c.values_len, zoff, &lens_len, &f1);
                 size_t c2 = zjob.add_bytes_block(c.values + c1, c.values_len - c1, zoff + c1, &data_len, &f2);
@@ -234,67 +302,9 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
     out->arena_bytes = cursor + kArenaPad;
     t_desc = now();
     out->arena.ensure(out->arena_bytes);
-    if (!zpieces.empty()) ctx->zsrc.ensure(zcursor + 64);
     t_alloc = now();
-    // copy pieces: runs that are contiguous on both sides (src stride == dst stride) and live in pinned host memory go out as one
-    // cudaMemcpyAsync; everything else is packed through a pinned staging ring.
-    uint64_t h2d = 0;
-    const size_t CH = 32u << 20;
-    uint8_t* stage = nullptr; cudaEvent_t evs[2] = {nullptr, nullptr}; int cur = 0; size_t fill = 0; uint64_t chunk_dst = 0; bool chunk_open = false;
-    uint8_t* dev_base = out->arena.as<uint8_t>();   // destination buffer of the pieces being copied
-    auto flush = [&]() {
-        if (!chunk_open || !fill) { chunk_open = false; fill = 0; return; }
-        VL_CUDA(cudaMemcpyAsync(dev_base + chunk_dst, stage + (size_t)cur * CH, fill, cudaMemcpyHostToDevice, ctx->stream));
-        VL_CUDA(cudaEventRecord(evs[cur], ctx->stream));
-        h2d += fill; cur ^= 1; fill = 0; chunk_open = false;
-        VL_CUDA(cudaEventSynchronize(evs[cur]));
-    };
-    auto is_pinned = [&](const void* p) { cudaPointerAttributes a; if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; } return a.type == cudaMemoryTypeHost; };
     VL_CUDA(cudaMemsetAsync(out->arena.p, 0, out->arena_bytes, ctx->stream));
-    auto need_stage = [&]() {
-        if (stage) return;
-        stage = (uint8_t*)ctx->ensure_pinned(2 * CH);
-        for (int k = 0; k < 2; k++) { VL_CUDA(cudaEventCreateWithFlags(&evs[k], cudaEventDisableTiming)); VL_CUDA(cudaEventRecord(evs[k], ctx->stream)); }
-    };
-    bool all_pinned = !pieces.empty() || !zpieces.empty();
-    auto copy_pieces = [&](const std::vector<Piece>& pieces, uint8_t* base) {
-    dev_base = base;
-    size_t i = 0;
-    while (i < pieces.size()) {
-        // maximal run of pieces laid out identically on both sides (same stride between source and destination)
-        size_t j = i;
-        while (j + 1 < pieces.size() && pieces[j + 1].src > pieces[j].src && pieces[j + 1].src - pieces[i].src == (ptrdiff_t)(pieces[j + 1].dst - pieces[i].dst)) j++;
-        uint64_t run_len = (pieces[j].dst - pieces[i].dst) + pieces[j].len;
-        if (is_pinned(pieces[i].src) && is_pinned(pieces[j].src + pieces[j].len - 1)) {
-            // page-locked caller memory: one DMA for the whole run, gaps (alignment slack) included
-            flush();
-            VL_CUDA(cudaMemcpyAsync(dev_base + pieces[i].dst, pieces[i].src, run_len, cudaMemcpyHostToDevice, ctx->stream));
-            h2d += run_len; i = j + 1;
-            continue;
-        }
-        all_pinned = false;
-        need_stage();
-        for (; i <= j; i++) {
-            const Piece& pc = pieces[i];
-            uint64_t done = 0;
-            while (done < pc.len) {
-                if (chunk_open && (chunk_dst + fill != pc.dst + done || fill == CH)) flush();
-                if (!chunk_open) { chunk_open = true; chunk_dst = pc.dst + done; fill = 0; }
-                size_t take = (size_t)std::min<uint64_t>(pc.len - done, CH - fill);
-                memcpy(stage + (size_t)cur * CH + fill, pc.src + done, take);
-                fill += take; done += take;
-            }
-            // pack the inter-piece slack (zero in the arena already) when the next piece follows closely, so chunks stay large
-            if (i + 1 < pieces.size()) {
-                uint64_t gap = pieces[i + 1].dst - (pc.dst + pc.len);
-                if (gap <= 64 && fill + gap < CH) { memset(stage + (size_t)cur * CH + fill, 0, gap); fill += gap; } else flush();
-            }
-        }
-    }
-    flush();
-    };
     copy_pieces(pieces, out->arena.as<uint8_t>());
-    if (!zpieces.empty()) copy_pieces(zpieces, ctx->zsrc.as<uint8_t>());
     for (int k = 0; k < 2; k++) if (evs[k]) cudaEventDestroy(evs[k]);
     out->cols.ensure(std::max<size_t>(cols.size() * sizeof(DevColumn), 16));
     if (!cols.empty()) VL_CUDA(cudaMemcpyAsync(out->cols.p, cols.data(), cols.size() * sizeof(DevColumn), cudaMemcpyHostToDevice, ctx->stream));
@@ -745,7 +755,7 @@ int vlscan_zstd_decompress(vlscan_ctx* ctx, uint32_t nframes, const void* const*
     return guarded(ctx, [&] {
         VL_CUDA(cudaSetDevice(ctx->device));
         ZstdJob job;
-        std::vector<uint8_t> packed(16, 0);
+        std::vector<uint8_t> packed(64, 0);
         for (uint32_t i = 0; i < nframes; i++) {
             uint64_t regen = 0; uint32_t id = 0;
             job.add_frame((const uint8_t*)frames[i], frame_lens[i], packed.size(), &regen, &id);

@@ -28,8 +28,10 @@ const uint32_t kNone = 0xFFFFFFFEu;                 // "no table seen yet in thi
 const uint64_t kMaxFrameContent = 1ull << 30;       // a values block never regenerates more than this (consts.go: blocks are <= 2 MB uncompressed)
 const uint32_t kBlockMax = 128u << 10;              // Block_Maximum_Size upper bound
 // scratch limits of one launch group (groups are cut at frame boundaries)
-const uint64_t kGroupLits = 1ull << 30, kGroupSeqs = 48ull << 20;
-const uint32_t kGroupSlots = 48u << 10;
+// The lane-per-block phases are latency bound (a serial chain per block), so a group should hold as many blocks as the device can keep
+// in flight (~190 k lanes on 148 SMs): the limits below only bound scratch to ~16 GB for very large uploads.
+const uint64_t kGroupLits = 6ull << 30, kGroupSeqs = 512ull << 20;
+const uint32_t kGroupSlots = 256u << 10;
 
 inline uint32_t le16(const uint8_t* p) { return p[0] | (p[1] << 8); }
 inline uint32_t le24(const uint8_t* p) { return p[0] | (p[1] << 8) | (p[2] << 16); }
@@ -242,11 +244,12 @@ void ZstdJob::run(vlscan_ctx* ctx, const uint8_t* zsrc, uint8_t* arena) {
     D.frames.ensure(J.frames.size() * sizeof(ZFrame)); D.blocks.ensure(J.blocks.size() * sizeof(ZBlock)); D.bstate.ensure(J.blocks.size() * sizeof(ZBlockState));
     D.frame_err.ensure(J.frames.size() * 4); D.status.ensure(16); D.lists.ensure(std::max<size_t>(lists.size() * 4, 16));
     D.huf_tab.ensure(std::max<size_t>((size_t)J.max_huf * Z_HUF_TABLE * 2, 16)); D.huf_state.ensure(std::max<size_t>((size_t)J.max_huf * sizeof(ZSlotState), 16));
-    D.fse_tab.ensure(std::max<size_t>((size_t)J.max_fse * Z_FSE_SLOT * 4, 16)); D.fse_state.ensure(std::max<size_t>((size_t)J.max_fse * sizeof(ZSlotState), 16));
+    D.fse_tab.ensure(std::max<size_t>((size_t)J.max_fse * Z_FSE_SLOT * sizeof(uint2), 16)); D.fse_state.ensure(std::max<size_t>((size_t)J.max_fse * sizeof(ZSlotState), 16));
     D.lits.ensure(J.max_lits + 64); D.seqs.ensure(std::max<size_t>(J.max_seqs * 16, 16));
     if (!D.predef_ready) {
-        D.predef.ensure(Z_FSE_SLOT * 4);
-        k_zstd_predef<<<1, 32, 0, st>>>(D.predef.as<uint32_t>());
+        D.predef.ensure(Z_FSE_SLOT * sizeof(uint2));
+        k_zstd_predef<<<1, 32, 0, st>>>(D.predef.as<uint2>());
+        VL_CUDA(cudaFuncSetAttribute(k_huf_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Z_HUF_CTA_BLOCKS * Z_HUF_TABLE * 2)));
         ctx->launches++; VL_CUDA(cudaGetLastError());
         D.predef_ready = true;
     }
@@ -258,8 +261,8 @@ void ZstdJob::run(vlscan_ctx* ctx, const uint8_t* zsrc, uint8_t* arena) {
     VL_CUDA(cudaMemsetAsync(D.bstate.p, 0, J.blocks.size() * sizeof(ZBlockState), st));
     ZView V{};
     V.src = zsrc; V.arena = arena; V.frames = D.frames.as<ZFrame>(); V.blocks = D.blocks.as<ZBlock>(); V.bstate = D.bstate.as<ZBlockState>();
-    V.huf_tab = D.huf_tab.as<uint16_t>(); V.fse_tab = D.fse_tab.as<uint32_t>(); V.huf_state = D.huf_state.as<ZSlotState>(); V.fse_state = D.fse_state.as<ZSlotState>();
-    V.predef = D.predef.as<uint32_t>(); V.lits = D.lits.as<uint8_t>(); V.seqs = D.seqs.as<uint4>(); V.frame_err = D.frame_err.as<unsigned int>();
+    V.huf_tab = D.huf_tab.as<uint16_t>(); V.fse_tab = D.fse_tab.as<uint2>(); V.huf_state = D.huf_state.as<ZSlotState>(); V.fse_state = D.fse_state.as<ZSlotState>();
+    V.predef = D.predef.as<uint2>(); V.lits = D.lits.as<uint8_t>(); V.seqs = D.seqs.as<uint4>(); V.frame_err = D.frame_err.as<unsigned int>();
     V.status = D.status.as<unsigned long long>();
     const uint32_t* L = D.lists.as<uint32_t>();
     // VLSCAN_DEBUG_TIMING: device time per phase (events around every launch; summed over the groups)
@@ -272,7 +275,7 @@ void ZstdJob::run(vlscan_ctx* ctx, const uint8_t* zsrc, uint8_t* arena) {
     for (const Group& g : J.groups) {
         uint32_t nh = g.huf_hi - g.huf_lo, nl = g.lit_hi - g.lit_lo, ns = g.seq_hi - g.seq_lo, nf = g.frame_hi - g.frame_lo;
         if (nh) { begin(0); k_huf_build<<<cdiv_u(nh, 4), 128, 0, st>>>(V, L + g.huf_lo, nh); launched(); }
-        if (nl) { begin(1); k_huf_decode<<<cdiv_u((uint64_t)nl * 4, 128), 128, 0, st>>>(V, L + g.lit_lo, nl); launched(); }
+        if (nl) { begin(1); k_huf_decode<<<cdiv_u(nl, Z_HUF_CTA_BLOCKS), Z_HUF_CTA_BLOCKS * 4, Z_HUF_CTA_BLOCKS * Z_HUF_TABLE * 2, st>>>(V, L + g.lit_lo, nl); launched(); }
         if (ns) {
             begin(2); k_fse_build<<<cdiv_u(ns, 64), 64, 0, st>>>(V, L + g.seq_lo, ns); launched();
             begin(3); k_seq_decode<<<cdiv_u(ns, 64), 64, 0, st>>>(V, L + g.seq_lo, ns); launched();
