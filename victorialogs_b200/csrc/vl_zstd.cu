@@ -244,11 +244,12 @@ void ZstdJob::run(vlscan_ctx* ctx, const uint8_t* zsrc, uint8_t* arena) {
     D.frames.ensure(J.frames.size() * sizeof(ZFrame)); D.blocks.ensure(J.blocks.size() * sizeof(ZBlock)); D.bstate.ensure(J.blocks.size() * sizeof(ZBlockState));
     D.frame_err.ensure(J.frames.size() * 4); D.status.ensure(16); D.lists.ensure(std::max<size_t>(lists.size() * 4, 16));
     D.huf_tab.ensure(std::max<size_t>((size_t)J.max_huf * Z_HUF_TABLE * 2, 16)); D.huf_state.ensure(std::max<size_t>((size_t)J.max_huf * sizeof(ZSlotState), 16));
-    D.fse_tab.ensure(std::max<size_t>((size_t)J.max_fse * Z_FSE_SLOT * sizeof(uint2), 16)); D.fse_state.ensure(std::max<size_t>((size_t)J.max_fse * sizeof(ZSlotState), 16));
+    D.fse_tab.ensure(std::max<size_t>((size_t)J.max_fse * Z_FSE_SLOT_BYTES, 16)); D.fse_state.ensure(std::max<size_t>((size_t)J.max_fse * sizeof(ZSlotState), 16));
     D.lits.ensure(J.max_lits + 64); D.seqs.ensure(std::max<size_t>(J.max_seqs * 16, 16));
     if (!D.predef_ready) {
-        D.predef.ensure(Z_FSE_SLOT * sizeof(uint2));
-        k_zstd_predef<<<1, 32, 0, st>>>(D.predef.as<uint2>());
+        D.predef.ensure(Z_FSE_SLOT_BYTES);
+        k_zstd_predef<<<1, 32, 0, st>>>(D.predef.as<uint8_t>());
+        VL_CUDA(cudaFuncSetAttribute(k_seq_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Z_SEQ_CTA_LANES * Z_FSE_SLOT_BYTES)));
         VL_CUDA(cudaFuncSetAttribute(k_huf_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Z_HUF_CTA_BLOCKS * Z_HUF_TABLE * 2)));
         ctx->launches++; VL_CUDA(cudaGetLastError());
         D.predef_ready = true;
@@ -261,8 +262,8 @@ void ZstdJob::run(vlscan_ctx* ctx, const uint8_t* zsrc, uint8_t* arena) {
     VL_CUDA(cudaMemsetAsync(D.bstate.p, 0, J.blocks.size() * sizeof(ZBlockState), st));
     ZView V{};
     V.src = zsrc; V.arena = arena; V.frames = D.frames.as<ZFrame>(); V.blocks = D.blocks.as<ZBlock>(); V.bstate = D.bstate.as<ZBlockState>();
-    V.huf_tab = D.huf_tab.as<uint16_t>(); V.fse_tab = D.fse_tab.as<uint2>(); V.huf_state = D.huf_state.as<ZSlotState>(); V.fse_state = D.fse_state.as<ZSlotState>();
-    V.predef = D.predef.as<uint2>(); V.lits = D.lits.as<uint8_t>(); V.seqs = D.seqs.as<uint4>(); V.frame_err = D.frame_err.as<unsigned int>();
+    V.huf_tab = D.huf_tab.as<uint16_t>(); V.fse_tab = D.fse_tab.as<uint8_t>(); V.huf_state = D.huf_state.as<ZSlotState>(); V.fse_state = D.fse_state.as<ZSlotState>();
+    V.predef = D.predef.as<uint8_t>(); V.lits = D.lits.as<uint8_t>(); V.seqs = D.seqs.as<uint4>(); V.frame_err = D.frame_err.as<unsigned int>();
     V.status = D.status.as<unsigned long long>();
     const uint32_t* L = D.lists.as<uint32_t>();
     // VLSCAN_DEBUG_TIMING: device time per phase (events around every launch; summed over the groups)
@@ -278,7 +279,7 @@ void ZstdJob::run(vlscan_ctx* ctx, const uint8_t* zsrc, uint8_t* arena) {
         if (nl) { begin(1); k_huf_decode<<<cdiv_u(nl, Z_HUF_CTA_BLOCKS), Z_HUF_CTA_BLOCKS * 4, Z_HUF_CTA_BLOCKS * Z_HUF_TABLE * 2, st>>>(V, L + g.lit_lo, nl); launched(); }
         if (ns) {
             begin(2); k_fse_build<<<cdiv_u(ns, 64), 64, 0, st>>>(V, L + g.seq_lo, ns); launched();
-            begin(3); k_seq_decode<<<cdiv_u(ns, 64), 64, 0, st>>>(V, L + g.seq_lo, ns); launched();
+            begin(3); k_seq_decode<<<cdiv_u(ns, Z_SEQ_CTA_LANES), 64, Z_SEQ_CTA_LANES * Z_FSE_SLOT_BYTES, st>>>(V, L + g.seq_lo, ns); launched();
         }
         begin(4); k_seq_resolve<<<cdiv_u(nf, 64), 64, 0, st>>>(V, g.frame_lo, nf); launched();
         begin(5); k_execute<<<cdiv_u((uint64_t)nf * 32, 128), 128, 0, st>>>(V, L + g.ord_lo, nf); launched();
