@@ -151,7 +151,7 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
     // regenerates them (vl_zstd.cuh) into arena regions placed behind everything that is copied, so that host memory laid out like
     // the copied part still goes out as one DMA.  Region offsets are relative to `regen_base` until the loop below has sized that part.
     ZstdJob zjob;
-    uint64_t zcursor = 64, regen_cursor = 0;   // headroom: the bit readers load whole aligned words around a stream
+    uint64_t zcursor = 512, regen_cursor = 0;   // headroom: the bit readers load whole aligned words around a stream
     struct Ondisk { uint64_t col; uint32_t lens_frame, data_frame; uint64_t lens_rel, data_rel; };
     std::vector<Ondisk> ondisk;
     std::vector<OndiskCol> ocols;
@@ -161,10 +161,18 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
     const size_t CH = 32u << 20;
     uint8_t* stage = nullptr; cudaEvent_t evs[2] = {nullptr, nullptr}; int cur = 0; size_t fill = 0; uint64_t chunk_dst = 0; bool chunk_open = false;
     uint8_t* dev_base = nullptr;   // destination buffer of the pieces being copied
+    // All host->device payload copies run on the ctx's copy stream; the compute stream picks them up through events.  While the
+    // compressed staging buffer is being filled, `zmarks` records (end offset, event) pairs so that the decoder of a launch group can
+    // start as soon as the bytes of that group have landed, while later bytes are still in flight.
+    cudaStream_t cs = ctx->copy_stream;
+    std::vector<std::pair<uint64_t, cudaEvent_t>> zmarks;
+    bool marking = false;
+    auto mark = [&](uint64_t end_off) { cudaEvent_t e; VL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); VL_CUDA(cudaEventRecord(e, cs)); zmarks.push_back({end_off, e}); };
     auto flush = [&]() {
         if (!chunk_open || !fill) { chunk_open = false; fill = 0; return; }
-        VL_CUDA(cudaMemcpyAsync(dev_base + chunk_dst, stage + (size_t)cur * CH, fill, cudaMemcpyHostToDevice, ctx->stream));
-        VL_CUDA(cudaEventRecord(evs[cur], ctx->stream));
+        VL_CUDA(cudaMemcpyAsync(dev_base + chunk_dst, stage + (size_t)cur * CH, fill, cudaMemcpyHostToDevice, cs));
+        VL_CUDA(cudaEventRecord(evs[cur], cs));
+        if (marking) mark(chunk_dst + fill);
         h2d += fill; cur ^= 1; fill = 0; chunk_open = false;
         VL_CUDA(cudaEventSynchronize(evs[cur]));
     };
@@ -172,7 +180,7 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
     auto need_stage = [&]() {
         if (stage) return;
         stage = (uint8_t*)ctx->ensure_pinned(2 * CH);
-        for (int k = 0; k < 2; k++) { VL_CUDA(cudaEventCreateWithFlags(&evs[k], cudaEventDisableTiming)); VL_CUDA(cudaEventRecord(evs[k], ctx->stream)); }
+        for (int k = 0; k < 2; k++) { VL_CUDA(cudaEventCreateWithFlags(&evs[k], cudaEventDisableTiming)); VL_CUDA(cudaEventRecord(evs[k], cs)); }
     };
     bool all_pinned = true;
     auto copy_pieces = [&](const std::vector<Piece>& pieces, uint8_t* base) {
@@ -186,8 +194,18 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
         if (is_pinned(pieces[i].src) && is_pinned(pieces[j].src + pieces[j].len - 1)) {
             // page-locked caller memory: one DMA for the whole run, gaps (alignment slack) included
             flush();
-            VL_CUDA(cudaMemcpyAsync(dev_base + pieces[i].dst, pieces[i].src, run_len, cudaMemcpyHostToDevice, ctx->stream));
-            h2d += run_len; i = j + 1;
+            // (split at piece boundaries every ~128 MB so that consumers can be released chunk by chunk)
+            size_t a = i;
+            while (a <= j) {
+                size_t b2 = a;
+                while (b2 < j && (pieces[b2].dst + pieces[b2].len) - pieces[a].dst < (128ull << 20)) b2++;
+                const uint64_t len = (pieces[b2].dst - pieces[a].dst) + pieces[b2].len;
+                VL_CUDA(cudaMemcpyAsync(dev_base + pieces[a].dst, pieces[a].src, len, cudaMemcpyHostToDevice, cs));
+                if (marking) mark(pieces[b2].dst + pieces[b2].len);
+                h2d += len; a = b2 + 1;
+            }
+            (void)run_len;
+            i = j + 1;
             continue;
         }
         all_pinned = false;
@@ -214,7 +232,7 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
     // Pre-pass: the compressed bytes of on-disk values blocks are shipped first (their place in the staging buffer is a running sum), so
     // that the DMA engine is busy while the host walks frame and block headers in the loop below.
     {
-        uint64_t zc = 64;
+        uint64_t zc = 512;
         for (uint64_t b = 0; b < nblocks; b++)
             for (uint32_t k = 0; k < blocks[b].ncols; k++) {
                 const vlscan_column& c = blocks[b].cols[k];
@@ -222,7 +240,7 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
                 if (c.values_len) zpieces.push_back({c.values, c.values_len, zc});
                 zc += c.values_len;
             }
-        if (!zpieces.empty()) { ctx->zsrc.ensure(zc + 64); copy_pieces(zpieces, ctx->zsrc.as<uint8_t>()); }
+        if (!zpieces.empty()) { ctx->zsrc.ensure(zc + 512); marking = true; copy_pieces(zpieces, ctx->zsrc.as<uint8_t>()); marking = false; }
     }
     for (uint64_t b = 0; b < nblocks; b++) {
         const vlscan_block& blk = blocks[b];
@@ -303,17 +321,29 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
     t_desc = now();
     out->arena.ensure(out->arena_bytes);
     t_alloc = now();
+    // the arena is cleared on the compute stream; the copy stream takes over from there
+    cudaEvent_t ev_cleared = nullptr, ev_copied = nullptr;
+    VL_CUDA(cudaEventCreateWithFlags(&ev_cleared, cudaEventDisableTiming)); VL_CUDA(cudaEventCreateWithFlags(&ev_copied, cudaEventDisableTiming));
     VL_CUDA(cudaMemsetAsync(out->arena.p, 0, out->arena_bytes, ctx->stream));
+    VL_CUDA(cudaEventRecord(ev_cleared, ctx->stream));
+    VL_CUDA(cudaStreamWaitEvent(cs, ev_cleared, 0));
     copy_pieces(pieces, out->arena.as<uint8_t>());
     for (int k = 0; k < 2; k++) if (evs[k]) cudaEventDestroy(evs[k]);
     out->cols.ensure(std::max<size_t>(cols.size() * sizeof(DevColumn), 16));
-    if (!cols.empty()) VL_CUDA(cudaMemcpyAsync(out->cols.p, cols.data(), cols.size() * sizeof(DevColumn), cudaMemcpyHostToDevice, ctx->stream));
+    if (!cols.empty()) VL_CUDA(cudaMemcpyAsync(out->cols.p, cols.data(), cols.size() * sizeof(DevColumn), cudaMemcpyHostToDevice, cs));
+    VL_CUDA(cudaEventRecord(ev_copied, cs));
     h2d += cols.size() * sizeof(DevColumn);
     double t_h2d = 0, t_zrun = 0;
-    if (dbg) { VL_CUDA(cudaStreamSynchronize(ctx->stream)); t_h2d = now(); }
+    if (dbg) t_h2d = now();
     if (!ondisk.empty()) {
-        // regenerate the on-disk payloads in HBM, then derive lens_type / lens_const / data_const from the regenerated lens blocks
+        // regenerate the on-disk payloads in HBM (each launch group as soon as its compressed bytes have arrived), then derive
+        // lens_type / lens_const / data_const from the regenerated lens blocks
+        zjob.set_group_hook([&](uint64_t src_end) {
+            for (auto& m : zmarks) if (m.first >= src_end) { VL_CUDA(cudaStreamWaitEvent(ctx->stream, m.second, 0)); return; }
+            if (!zmarks.empty()) VL_CUDA(cudaStreamWaitEvent(ctx->stream, zmarks.back().second, 0));
+        });
         zjob.run(ctx, ctx->zsrc.as<uint8_t>(), out->arena.as<uint8_t>());
+        VL_CUDA(cudaStreamWaitEvent(ctx->stream, ev_copied, 0));
         if (dbg) t_zrun = now();
         ctx->zcols.ensure(16 + ocols.size() * sizeof(OndiskCol));
         VL_CUDA(cudaMemsetAsync(ctx->zcols.p, 0, 16, ctx->stream));
@@ -328,13 +358,17 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
         static const char* what[] = {"", "cannot unmarshal uint64 block type from empty src", "unexpected uint64 block type", "unexpected block length for uint items", "row length does not fit 32 bits"};
         if (cst[0]) throw BadInput(what[std::min<unsigned long long>(cst[0], 4)]);
     }
+    VL_CUDA(cudaStreamWaitEvent(ctx->stream, ev_copied, 0));
     if (dbg) { VL_CUDA(cudaStreamSynchronize(ctx->stream)); t_copy = now(); }
     if (nfields) out->note_columns(cols);
     finish_batch_layout(ctx, out, rows);   // synchronises the stream => `owned`, `cols`, staging are safe to drop
+    for (auto& m : zmarks) cudaEventDestroy(m.second);
+    cudaEventDestroy(ev_cleared); cudaEventDestroy(ev_copied);
     if (dbg) fprintf(stderr, "[vlscan upload] blocks=%llu arena=%.1f MB h2d=%.1f MB pieces=%zu+%zu pinned=%d: describe %.1f ms, alloc %.1f ms, copy %.1f ms (%.1f GB/s), "
                              "zstd %llu frames / %llu blocks / %llu sequences: enqueue %.1f ms, decode %.1f ms; layout %.1f ms\n", (unsigned long long)nblocks,
                      out->arena_bytes / 1e6, h2d / 1e6, pieces.size(), zpieces.size(), (int)all_pinned, 1e3 * (t_desc - t_start), 1e3 * (t_alloc - t_desc), 1e3 * (t_h2d - t_alloc), h2d / 1e9 / std::max(t_h2d - t_alloc, 1e-9),
                      (unsigned long long)zjob.frames(), (unsigned long long)zjob.compressed_blocks(), (unsigned long long)zjob.sequences(), 1e3 * (t_zrun > 0 ? t_zrun - t_h2d : 0), 1e3 * (t_copy - (t_zrun > 0 ? t_zrun : t_h2d)), 1e3 * (now() - t_copy));
+    (void)all_pinned;
     h2d += out->nwords * 12 + nblocks * 12;
     if (stats) stats->h2d_bytes += h2d;
 }
@@ -555,6 +589,7 @@ vlscan_ctx* vlscan_ctx_create(int device) {
         ctx->device = ((device % n) + n) % n;
         VL_CUDA(cudaSetDevice(ctx->device));
         VL_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        VL_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         VL_CUDA(cudaEventCreate(&ctx->ev_begin)); VL_CUDA(cudaEventCreate(&ctx->ev_end));
         cudaDeviceProp prop; VL_CUDA(cudaGetDeviceProperties(&prop, ctx->device)); ctx->sm_count = prop.multiProcessorCount;
     });
@@ -564,6 +599,7 @@ vlscan_ctx* vlscan_ctx_create(int device) {
 void vlscan_ctx_free(vlscan_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (DevBuf* b : {&ctx->alive, &ctx->action, &ctx->payload, &ctx->leaf_bm, &ctx->work_blocks, &ctx->tile_prefix, &ctx->work_count, &ctx->stats, &ctx->totals, &ctx->counts, &ctx->slots, &ctx->hit_offs, &ctx->hits, &ctx->tile_block, &ctx->tile_off, &ctx->chunks}) b->release();
     for (auto& r : ctx->regs) r.release();
@@ -576,6 +612,7 @@ void vlscan_ctx_free(vlscan_ctx* ctx) {
     for (auto& e : ctx->scan_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
     if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -615,6 +652,7 @@ int vlscan_batch_upload(vlscan_ctx* ctx, const char* const* field_names, const s
     *out = nullptr;
     auto* b = new vlscan_batch();
     int rc = guarded(ctx, [&] { do_upload(ctx, field_names, field_name_lens, nfields, blocks, nblocks, b, stats); });
+    if (rc) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->stream); }   // nothing may still read the caller's buffers
     if (rc) { delete b; return rc; }
     *out = b;
     return 0;
@@ -755,7 +793,7 @@ int vlscan_zstd_decompress(vlscan_ctx* ctx, uint32_t nframes, const void* const*
     return guarded(ctx, [&] {
         VL_CUDA(cudaSetDevice(ctx->device));
         ZstdJob job;
-        std::vector<uint8_t> packed(64, 0);
+        std::vector<uint8_t> packed(512, 0);
         for (uint32_t i = 0; i < nframes; i++) {
             uint64_t regen = 0; uint32_t id = 0;
             job.add_frame((const uint8_t*)frames[i], frame_lens[i], packed.size(), &regen, &id);
@@ -764,7 +802,7 @@ int vlscan_zstd_decompress(vlscan_ctx* ctx, uint32_t nframes, const void* const*
             packed.insert(packed.end(), (const uint8_t*)frames[i], (const uint8_t*)frames[i] + frame_lens[i]);
         }
         const uint64_t total = nframes ? dst_offsets[nframes] : 0;
-        ctx->zsrc.ensure(packed.size() + 64); ctx->ztest.ensure(16 + total + 64);
+        ctx->zsrc.ensure(packed.size() + 512); ctx->ztest.ensure(16 + total + 64);
         VL_CUDA(cudaMemcpyAsync(ctx->zsrc.p, packed.data(), packed.size(), cudaMemcpyHostToDevice, ctx->stream));
         VL_CUDA(cudaMemsetAsync(ctx->ztest.p, 0xA5, 16 + total + 64, ctx->stream));
         job.run(ctx, ctx->zsrc.as<uint8_t>(), ctx->ztest.as<uint8_t>());
@@ -839,6 +877,7 @@ int vlscan_scan_batch(vlscan_ctx* ctx, const vlscan_program* prog, const char* c
     b->field_names.clear(); b->slot_vt_mask.clear();
     uint64_t launches0 = ctx->launches;
     int rc = guarded(ctx, [&] { do_upload(ctx, field_names, field_name_lens, nfields, blocks, nblocks, b, stats); });
+    if (rc) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->stream); }   // nothing may still read the caller's buffers
     if (!rc) rc = vlscan_scan_resident(ctx, prog, b, nullptr);
     if (!rc) rc = vlscan_fetch_results(ctx, out_bitmap_words, out_match_counts, stats);
     if (!rc && stats) {

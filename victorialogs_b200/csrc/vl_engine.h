@@ -71,7 +71,8 @@ struct vlscan_batch {
 
 struct vlscan_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;        // compute stream: kernels, small copies, results
+    cudaStream_t copy_stream = nullptr;   // host -> device payload copies of vlscan_batch_upload / vlscan_scan_batch
     std::string err;
     uint64_t launches = 0;
     // scratch (grow-only)

@@ -16,11 +16,28 @@ using namespace zs;
 struct ZstdDev {
     DevBuf frames, blocks, bstate, huf_tab, fse_tab, huf_state, fse_state, predef, lits, seqs, frame_err, status, lists;
     bool predef_ready = false;
+    void* hpin = nullptr; size_t hpin_cap = 0;   // page-locked staging of the descriptor tables (read by k_pull_words over PCIe)
+    void* ensure_hpin(size_t n) {
+        if (n <= hpin_cap) return hpin;
+        if (hpin) cudaFreeHost(hpin);
+        hpin = nullptr; hpin_cap = 0;
+        VL_CUDA(cudaMallocHost(&hpin, n + n / 4 + 4096)); hpin_cap = n + n / 4 + 4096;
+        return hpin;
+    }
     void release() {
         DevBuf* all[] = {&frames, &blocks, &bstate, &huf_tab, &fse_tab, &huf_state, &fse_state, &predef, &lits, &seqs, &frame_err, &status, &lists};
         for (DevBuf* b : all) b->release();
+        if (hpin) cudaFreeHost(hpin);
+        hpin = nullptr; hpin_cap = 0;
     }
 };
+
+// Descriptor tables reach the device through a kernel that reads page-locked host memory, not through cudaMemcpyAsync: the host->device
+// copy engine is busy (and its queue full) with the compressed payload of the same upload, and a copy queued behind it would hold the
+// decoder back until the whole payload has landed.
+static __global__ void k_pull_words(uint4* __restrict__ dst, const uint4* __restrict__ src, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
 void zstd_dev_free(ZstdDev* d) { if (d) { d->release(); delete d; } }
 
 namespace {
@@ -28,10 +45,10 @@ const uint32_t kNone = 0xFFFFFFFEu;                 // "no table seen yet in thi
 const uint64_t kMaxFrameContent = 1ull << 30;       // a values block never regenerates more than this (consts.go: blocks are <= 2 MB uncompressed)
 const uint32_t kBlockMax = 128u << 10;              // Block_Maximum_Size upper bound
 // scratch limits of one launch group (groups are cut at frame boundaries)
-// The lane-per-block phases are latency bound (a serial chain per block), so a group should hold as many blocks as the device can keep
-// in flight (~190 k lanes on 148 SMs): the limits below only bound scratch to ~16 GB for very large uploads.
-const uint64_t kGroupLits = 6ull << 30, kGroupSeqs = 512ull << 20;
-const uint32_t kGroupSlots = 256u << 10;
+// A group must hold enough blocks to fill the device for the lane-per-block phases (148 SMs x 56 sequence lanes = 8.3 k blocks per
+// wave); beyond a few waves, smaller groups are better: group g is decoded while the bytes of group g+1 are still being copied.
+const uint64_t kGroupLits = 2ull << 30, kGroupSeqs = 256ull << 20;
+const uint32_t kGroupSlots = 96u << 10;
 
 inline uint32_t le16(const uint8_t* p) { return p[0] | (p[1] << 8); }
 inline uint32_t le24(const uint8_t* p) { return p[0] | (p[1] << 8) | (p[2] << 16); }
@@ -52,6 +69,7 @@ struct ZstdJob::Impl {
     uint64_t max_lits = 0, max_seqs = 0; uint32_t max_huf = 0, max_fse = 0;
     uint64_t n_compressed = 0, n_seqs = 0;
     bool ran = false;
+    std::function<void(uint64_t)> group_hook;
 
     void close_group() {
         if (g_frame_lo == frames.size()) return;
@@ -190,6 +208,7 @@ uint64_t ZstdJob::frames() const { return m->frames.size(); }
 uint64_t ZstdJob::compressed_blocks() const { return m->n_compressed; }
 uint64_t ZstdJob::sequences() const { return m->n_seqs; }
 void ZstdJob::set_dst(uint32_t id, uint64_t arena_off) { m->frames[id].dst = arena_off; }
+void ZstdJob::set_group_hook(std::function<void(uint64_t)> f) { m->group_hook = std::move(f); }
 
 void ZstdJob::add_frame(const uint8_t* f, size_t n, uint64_t zoff, uint64_t* regen, uint32_t* id) { m->parse_frame(f, n, zoff, regen, id); }
 
@@ -241,22 +260,31 @@ void ZstdJob::run(vlscan_ctx* ctx, const uint8_t* zsrc, uint8_t* arena) {
         for (uint32_t i = g.frame_lo; i < g.frame_hi; i++) v.push_back({(uint32_t)(J.frames[i].fcs >> 10), i});
         g.ord_lo = (uint32_t)lists.size(); by_desc(v); g.ord_hi = (uint32_t)lists.size();
     }
-    D.frames.ensure(J.frames.size() * sizeof(ZFrame)); D.blocks.ensure(J.blocks.size() * sizeof(ZBlock)); D.bstate.ensure(J.blocks.size() * sizeof(ZBlockState));
-    D.frame_err.ensure(J.frames.size() * 4); D.status.ensure(16); D.lists.ensure(std::max<size_t>(lists.size() * 4, 16));
+    D.frames.ensure(J.frames.size() * sizeof(ZFrame) + 16); D.blocks.ensure(J.blocks.size() * sizeof(ZBlock) + 16); D.bstate.ensure(J.blocks.size() * sizeof(ZBlockState));
+    D.frame_err.ensure(J.frames.size() * 4); D.status.ensure(16); D.lists.ensure(lists.size() * 4 + 16);
     D.huf_tab.ensure(std::max<size_t>((size_t)J.max_huf * Z_HUF_TABLE * 2, 16)); D.huf_state.ensure(std::max<size_t>((size_t)J.max_huf * sizeof(ZSlotState), 16));
     D.fse_tab.ensure(std::max<size_t>((size_t)J.max_fse * Z_FSE_SLOT_BYTES, 16)); D.fse_state.ensure(std::max<size_t>((size_t)J.max_fse * sizeof(ZSlotState), 16));
     D.lits.ensure(J.max_lits + 64); D.seqs.ensure(std::max<size_t>(J.max_seqs * 16, 16));
     if (!D.predef_ready) {
         D.predef.ensure(Z_FSE_SLOT_BYTES);
         k_zstd_predef<<<1, 32, 0, st>>>(D.predef.as<uint8_t>());
-        VL_CUDA(cudaFuncSetAttribute(k_seq_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Z_SEQ_CTA_LANES * Z_FSE_SLOT_BYTES)));
-        VL_CUDA(cudaFuncSetAttribute(k_huf_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Z_HUF_CTA_BLOCKS * Z_HUF_TABLE * 2)));
+        VL_CUDA(cudaFuncSetAttribute(k_seq_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Z_SEQ_CTA_LANES * (Z_FSE_SLOT_BYTES + Z_LINEBUF))));
+        VL_CUDA(cudaFuncSetAttribute(k_huf_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Z_HUF_CTA_BLOCKS * (Z_HUF_TABLE * 2 + 4 * Z_LINEBUF))));
         ctx->launches++; VL_CUDA(cudaGetLastError());
         D.predef_ready = true;
     }
-    VL_CUDA(cudaMemcpyAsync(D.frames.p, J.frames.data(), J.frames.size() * sizeof(ZFrame), cudaMemcpyHostToDevice, st));
-    VL_CUDA(cudaMemcpyAsync(D.blocks.p, J.blocks.data(), J.blocks.size() * sizeof(ZBlock), cudaMemcpyHostToDevice, st));
-    if (!lists.empty()) VL_CUDA(cudaMemcpyAsync(D.lists.p, lists.data(), lists.size() * 4, cudaMemcpyHostToDevice, st));
+    {
+        auto up16 = [](size_t n) { return (n + 15) / 16 * 16; };
+        const size_t nf = up16(J.frames.size() * sizeof(ZFrame)), nb = up16(J.blocks.size() * sizeof(ZBlock)), nl = up16(lists.size() * 4);
+        uint8_t* h = (uint8_t*)D.ensure_hpin(nf + nb + nl + 64);
+        memcpy(h, J.frames.data(), J.frames.size() * sizeof(ZFrame));
+        memcpy(h + nf, J.blocks.data(), J.blocks.size() * sizeof(ZBlock));
+        if (!lists.empty()) memcpy(h + nf + nb, lists.data(), lists.size() * 4);
+        k_pull_words<<<296, 256, 0, st>>>(D.frames.as<uint4>(), (const uint4*)h, nf / 16); ctx->launches++;
+        k_pull_words<<<296, 256, 0, st>>>(D.blocks.as<uint4>(), (const uint4*)(h + nf), nb / 16); ctx->launches++;
+        if (nl) { k_pull_words<<<296, 256, 0, st>>>(D.lists.as<uint4>(), (const uint4*)(h + nf + nb), nl / 16); ctx->launches++; }
+        VL_CUDA(cudaGetLastError());
+    }
     VL_CUDA(cudaMemsetAsync(D.frame_err.p, 0, J.frames.size() * 4, st));
     VL_CUDA(cudaMemsetAsync(D.status.p, 0, 16, st));
     VL_CUDA(cudaMemsetAsync(D.bstate.p, 0, J.blocks.size() * sizeof(ZBlockState), st));
@@ -275,11 +303,16 @@ void ZstdJob::run(vlscan_ctx* ctx, const uint8_t* zsrc, uint8_t* arena) {
     auto launched = [&] { ctx->launches++; VL_CUDA(cudaGetLastError()); if (dbg) cudaEventRecord(marks.back().second.second, st); };
     for (const Group& g : J.groups) {
         uint32_t nh = g.huf_hi - g.huf_lo, nl = g.lit_hi - g.lit_lo, ns = g.seq_hi - g.seq_lo, nf = g.frame_hi - g.frame_lo;
+        if (J.group_hook) {
+            uint64_t need = 0;
+            for (uint32_t i = J.frames[g.frame_lo].blk_lo; i < J.frames[g.frame_hi - 1].blk_hi; i++) need = std::max<uint64_t>(need, J.blocks[i].src + (J.blocks[i].type == ZB_RLE ? 1 : J.blocks[i].size));
+            J.group_hook(need);
+        }
         if (nh) { begin(0); k_huf_build<<<cdiv_u(nh, 4), 128, 0, st>>>(V, L + g.huf_lo, nh); launched(); }
-        if (nl) { begin(1); k_huf_decode<<<cdiv_u(nl, Z_HUF_CTA_BLOCKS), Z_HUF_CTA_BLOCKS * 4, Z_HUF_CTA_BLOCKS * Z_HUF_TABLE * 2, st>>>(V, L + g.lit_lo, nl); launched(); }
+        if (nl) { begin(1); k_huf_decode<<<cdiv_u(nl, Z_HUF_CTA_BLOCKS), Z_HUF_CTA_BLOCKS * 4, Z_HUF_CTA_BLOCKS * (Z_HUF_TABLE * 2 + 4 * Z_LINEBUF), st>>>(V, L + g.lit_lo, nl); launched(); }
         if (ns) {
             begin(2); k_fse_build<<<cdiv_u(ns, 64), 64, 0, st>>>(V, L + g.seq_lo, ns); launched();
-            begin(3); k_seq_decode<<<cdiv_u(ns, Z_SEQ_CTA_LANES), 64, Z_SEQ_CTA_LANES * Z_FSE_SLOT_BYTES, st>>>(V, L + g.seq_lo, ns); launched();
+            begin(3); k_seq_decode<<<cdiv_u(ns, Z_SEQ_CTA_LANES), 64, Z_SEQ_CTA_LANES * (Z_FSE_SLOT_BYTES + Z_LINEBUF), st>>>(V, L + g.seq_lo, ns); launched();
         }
         begin(4); k_seq_resolve<<<cdiv_u(nf, 64), 64, 0, st>>>(V, g.frame_lo, nf); launched();
         begin(5); k_execute<<<cdiv_u((uint64_t)nf * 32, 128), 128, 0, st>>>(V, L + g.ord_lo, nf); launched();

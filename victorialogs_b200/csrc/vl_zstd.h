@@ -3,6 +3,7 @@
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -33,6 +34,9 @@ public:
     uint64_t frames() const;
     uint64_t compressed_blocks() const;
     uint64_t sequences() const;
+    // called right before the kernels of a launch group are enqueued, with the end offset (in the compressed staging buffer) of the
+    // last byte the group reads: lets the caller make the stream wait for exactly that part of an upload still in flight
+    void set_group_hook(std::function<void(uint64_t src_end)> f);
     // enqueue all decode phases on ctx->stream; zsrc / arena are device pointers
     void run(vlscan_ctx* ctx, const uint8_t* zsrc, uint8_t* arena);
     // after the stream was synchronised: throws BadInput("cannot decompress block: ...") if a frame failed on the device
