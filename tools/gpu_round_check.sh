@@ -1,7 +1,5 @@
 mkdir -p gpurun_out
-timeout 150 python -m pytest tests/test_gpu_zstd.py -m gpu -x -q > gpurun_out/pytest_zstd.log 2>&1; rc=$?; echo "zstd pytest rc=$rc"; tail -5 gpurun_out/pytest_zstd.log
-[ $rc -ne 0 ] && exit 1
-timeout 400 python -m pytest tests -m gpu -x -q --deselect tests/test_gpu_zstd.py > gpurun_out/pytest_gpu.log 2>&1; rc=$?; echo "pytest rc=$rc"; tail -5 gpurun_out/pytest_gpu.log
-[ $rc -ne 0 ] && exit 1
-VLSCAN_DEBUG_TIMING=1 timeout 400 python bench.py --no-cpu-baseline --steps 3 --e2e-steps 1 > gpurun_out/bench_C2_zd.log 2> gpurun_out/bench_C2_zd.err; grep "vlscan upload\|vlscan zstd" gpurun_out/bench_C2_zd.err | tail -2
-timeout 400 python bench.py --no-cpu-baseline --steps 3 > gpurun_out/bench_C2_z.log 2> gpurun_out/bench_C2_z.err; tail -1 gpurun_out/bench_C2_z.log | python -c "import sys,json; print(json.loads(sys.stdin.read())['e2e'])"
+timeout 120 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+timeout 500 python bench.py > gpurun_out/BENCH_final.json 2> gpurun_out/BENCH_final.err; tail -1 gpurun_out/BENCH_final.json | cut -c1-150
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/BENCH_ref_final.json 2>/dev/null; tail -1 gpurun_out/BENCH_ref_final.json | cut -c1-200
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_e2e.csv python bench.py --rows 30000000 --steps 3 --warmup 3 --e2e-steps 1 --no-cpu-baseline > gpurun_out/ncu_e2e.log 2>&1; tail -1 gpurun_out/ncu_e2e.log | cut -c1-100
