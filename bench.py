@@ -252,7 +252,7 @@ def main():
                 # the reference's writer re-encodes every values block into its on-disk form (ZSTD frames); the scan call then ships the
                 # compressed bytes and regenerates them on the device.  Not timed: it is the ingestion side.
                 t1 = time.perf_counter()
-                disk = host.compress()
+                disk = host.compress(threads=max(1, (os.cpu_count() or 1) // world))   # ranks share the host cores
                 t_comp = time.perf_counter() - t1
                 del host
                 host = disk
