@@ -286,4 +286,53 @@ int vlo_scan_generated(const vlo_gen_config* cfg, void* filter, uint64_t block_l
     });
 }
 
+
+// The scenario of TestBitmap (lib/logstorage/bitmap_test.go:7-133) on the restated bitmap; returns 0, or 1000*bits + the number of the
+// check that failed.
+int vlo_bitmap_selftest(int max_bits) {
+    for (int i = 0; i < max_bits; i++) {
+        auto fail = [&](int step) { return 1000 * i + step; };
+        Bitmap bm; bm.init((uint64_t)i);
+        if (bm.bitsLen != (uint64_t)i) return fail(1);
+        if (!bm.is_zero()) return fail(2);
+        if (i == 0 && !bm.are_all_bits_set()) return fail(3);
+        if (i > 0 && bm.are_all_bits_set()) return fail(4);
+        if (bm.ones() != 0) return fail(5);
+        bm.set_bits();
+        if (bm.ones() != (uint64_t)i) return fail(6);
+        uint64_t next = 0; bool ok = true;
+        bm.for_each_set_bit_readonly([&](uint64_t idx) { if (idx >= (uint64_t)i || idx != next) ok = false; next++; });
+        if (!ok || next != (uint64_t)i) return fail(7);
+        if (!bm.are_all_bits_set()) return fail(8);
+        bm.for_each_set_bit([&](uint64_t idx) { return idx % 2 != 0; });   // clear the even bits
+        if (i <= 1 && !bm.is_zero()) return fail(9);
+        if (i > 1 && bm.is_zero()) return fail(10);
+        if (i == 0 && !bm.are_all_bits_set()) return fail(11);
+        if (i > 0 && bm.are_all_bits_set()) return fail(12);
+        next = 1; ok = true;
+        bm.for_each_set_bit_readonly([&](uint64_t idx) { if (idx != next) ok = false; next += 2; });
+        if (!ok || next < (uint64_t)i) return fail(13);
+        bm.for_each_set_bit([&](uint64_t) { return false; });   // clear all
+        if (!bm.is_zero()) return fail(14);
+        if (i == 0 && !bm.are_all_bits_set()) return fail(15);
+        if (i > 0 && bm.are_all_bits_set()) return fail(16);
+        if (bm.ones() != 0) return fail(17);
+        uint64_t cnt = 0; bm.for_each_set_bit_readonly([&](uint64_t) { cnt++; });
+        if (cnt) return fail(18);
+        for (int k = 0; k < i; k++) {
+            if (bm.ones() != (uint64_t)k) return fail(19);
+            if (bm.is_set_bit((uint64_t)k)) return fail(20);
+            bm.set_bit((uint64_t)k);
+            if (!bm.is_set_bit((uint64_t)k)) return fail(21);
+            if (bm.ones() != (uint64_t)k + 1) return fail(22);
+        }
+        // andNot (bitmap.go:99-111) against an independent model
+        Bitmap x; x.init((uint64_t)i);
+        for (int k = 0; k < i; k += 3) x.set_bit((uint64_t)k);
+        bm.and_not(x);
+        for (int k = 0; k < i; k++) if (bm.is_set_bit((uint64_t)k) != (k % 3 != 0)) return fail(23);
+    }
+    return 0;
+}
+
 }  // extern "C"

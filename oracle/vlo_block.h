@@ -166,6 +166,28 @@ struct Bitmap {
     bool is_zero() const { for (auto w : a) if (w) return false; return true; }
     void and_not(const Bitmap& x) { for (size_t i = 0; i < a.size(); i++) a[i] &= ~x.a[i]; }
     uint64_t ones() const { uint64_t n = 0; for (auto w : a) n += __builtin_popcountll(w); return n; }
+    bool are_all_bits_set() const {   // :83-97
+        for (size_t i = 0; i < a.size(); i++) {
+            if (a[i] == ~0ULL) continue;
+            if (i + 1 < a.size()) return false;
+            uint64_t tail = bitsLen % 64;
+            if (tail == 0 || a[i] != (1ULL << tail) - 1) return false;
+        }
+        return true;
+    }
+    void set_bit(uint64_t i) { a[i / 64] |= 1ULL << (i % 64); }               // :113-118
+    bool is_set_bit(uint64_t i) const { return (a[i / 64] >> (i % 64)) & 1; }   // :120-125
+    template <class F> void for_each_set_bit_readonly(F&& f) const {           // :156-183
+        for (size_t i = 0; i < a.size(); i++) {
+            uint64_t w = a[i];
+            for (int j = 0; w && j < 64; j++) {
+                if (!(w >> j & 1)) continue;
+                uint64_t idx = i * 64 + j;
+                if (idx >= bitsLen) break;
+                f(idx);
+            }
+        }
+    }
     template <class F> void for_each_set_bit(F&& f) {   // :128-153: f returns whether to keep the bit
         for (size_t i = 0; i < a.size(); i++) {
             uint64_t w = a[i]; if (!w) continue;

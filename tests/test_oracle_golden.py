@@ -162,6 +162,11 @@ def test_values_encoder(oracle):
     check(["same"] * n, None, 0, 0)   # const column: not a regular column
 
 
+def test_bitmap_invariants(oracle):
+    # bitmap_test.go:7-133 TestBitmap (sizes 0..99 there; through 200 here to cross three words) + andNot
+    assert oracle.lib().vlo_bitmap_selftest(200) == 0
+
+
 def test_strings_block_codec(oracle):
     # encoding_test.go:17-97 TestMarshalUnmarshalStringsBlock (round trip + exact bytes of the plain single-item case)
     assert oracle.marshal_strings_block([b"foo"]).hex() == "000200030003666f6f"
