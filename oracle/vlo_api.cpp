@@ -185,6 +185,16 @@ void* vlo_filter_in(const void* f, uint64_t fl, const uint8_t* blob, const uint6
     std::vector<std::string> vals; for (auto v : unpack(blob, offs, n)) vals.emplace_back(v);
     return new FilterHandle{std::make_shared<FilterIn>(sv((const char*)f, fl), vals)};
 }
+void* vlo_filter_exact_prefix(const void* f, uint64_t fl, const void* p, uint64_t pl) { return new FilterHandle{std::make_shared<FilterExactPrefix>(sv((const char*)f, fl), sv((const char*)p, pl))}; }
+void* vlo_filter_sequence(const void* f, uint64_t fl, const uint8_t* blob, const uint64_t* offs, uint64_t n) {
+    std::vector<std::string> vals; for (auto v : unpack(blob, offs, n)) vals.emplace_back(v);
+    return new FilterHandle{std::make_shared<FilterSequence>(sv((const char*)f, fl), vals)};
+}
+void* vlo_filter_len_range(const void* f, uint64_t fl, uint64_t mn, uint64_t mx) { return new FilterHandle{std::make_shared<FilterLenRange>(sv((const char*)f, fl), mn, mx)}; }
+void* vlo_filter_string_range(const void* f, uint64_t fl, const void* a, uint64_t al, const void* b, uint64_t bl) {
+    return new FilterHandle{std::make_shared<FilterStringRange>(sv((const char*)f, fl), sv((const char*)a, al), sv((const char*)b, bl))};
+}
+void* vlo_filter_ipv4_range(const void* f, uint64_t fl, uint32_t mn, uint32_t mx) { return new FilterHandle{std::make_shared<FilterIPv4Range>(sv((const char*)f, fl), mn, mx)}; }
 void* vlo_filter_regexp(const void* f, uint64_t fl, const void* p, uint64_t pl) {
     FilterHandle* h = nullptr;
     if (guard([&] { h = new FilterHandle{std::make_shared<FilterRegexp>(sv((const char*)f, fl), sv((const char*)p, pl))}; })) return nullptr;

@@ -9,6 +9,7 @@
 #pragma once
 #include "vlo_util.h"
 #include "vlo_regex.h"
+#include <functional>
 #include <map>
 #include <memory>
 
@@ -205,9 +206,9 @@ struct Bitmap {
 
 // ---- predicates ----------------------------------------------------------------------------------------------------
 // getPhrasePos / matchPhrase filter_phrase.go:211-270
-inline bool match_phrase(sv s, sv phrase) {
-    if (phrase.empty()) return s.empty();
-    if (phrase.size() > s.size()) return false;
+inline int64_t get_phrase_pos(sv s, sv phrase) {   // :220-270; -1 when the phrase is not found
+    if (phrase.empty()) return 0;
+    if (phrase.size() > s.size()) return -1;
     const uint8_t* sp = (const uint8_t*)s.data();
     int sz;
     int32_t r = (uint8_t)phrase[0];
@@ -219,7 +220,7 @@ inline bool match_phrase(sv s, sv phrase) {
     size_t pos = 0;
     for (;;) {
         size_t n = s.find(phrase, pos);
-        if (n == sv::npos) return false;
+        if (n == sv::npos) return -1;
         pos = n;
         if (startsWithToken && pos > 0) {
             int32_t q = sp[pos - 1];
@@ -231,9 +232,32 @@ inline bool match_phrase(sv s, sv phrase) {
             if (q >= 0x80) q = decode_rune(sp + pos + phrase.size(), s.size() - pos - phrase.size(), &sz);
             if (q == RuneError || is_token_rune(q)) { pos++; continue; }
         }
-        return true;
+        return (int64_t)pos;
     }
 }
+inline bool match_phrase(sv s, sv phrase) {   // :211-218
+    if (phrase.empty()) return s.empty();   // the empty phrase matches only the empty string
+    return get_phrase_pos(s, phrase) >= 0;
+}
+// matchSequence filter_sequence.go:260-269
+inline bool match_sequence(sv s, const std::vector<std::string>& phrases) {
+    for (auto& ph : phrases) {
+        int64_t n = get_phrase_pos(s, ph);
+        if (n < 0) return false;
+        s.remove_prefix((size_t)n + ph.size());
+    }
+    return true;
+}
+// matchExactPrefix filter_exact_prefix.go:275-277
+inline bool match_exact_prefix(sv s, sv prefix) { return s.size() >= prefix.size() && s.compare(0, prefix.size(), prefix) == 0; }
+// matchLenRange filter_len_range.go:333-336: utf8.RuneCountInString counts every invalid byte as one rune
+inline bool match_len_range(sv s, uint64_t minLen, uint64_t maxLen) {
+    uint64_t n = 0; const uint8_t* p = (const uint8_t*)s.data(); size_t left = s.size();
+    while (left) { int sz; decode_rune(p, left, &sz); p += sz; left -= (size_t)sz; n++; }
+    return n >= minLen && n <= maxLen;
+}
+// matchStringRange filter_string_range.go:226-230: plain byte-wise comparison
+inline bool match_string_range(sv s, sv minValue, sv maxValue) { return s.compare(minValue) >= 0 && s.compare(maxValue) < 0; }
 // matchPrefix filter_prefix.go:318-352
 inline bool match_prefix(sv s, sv prefix) {
     if (prefix.empty()) return !s.empty();
@@ -346,7 +370,7 @@ inline std::string encoded_to_string(uint8_t vt, sv v) {
 // ---- filters ---------------------------------------------------------------------------------------------------------
 struct FieldTokens { std::string field; std::vector<std::string> tokens; std::vector<uint64_t> hashes; };
 
-enum FilterKind { F_NOOP, F_PHRASE, F_PREFIX, F_EXACT, F_IN, F_REGEXP, F_AND, F_OR, F_NOT };
+enum FilterKind { F_NOOP, F_PHRASE, F_PREFIX, F_EXACT, F_IN, F_REGEXP, F_AND, F_OR, F_NOT, F_EXACT_PREFIX, F_SEQUENCE, F_LEN_RANGE, F_STRING_RANGE, F_IPV4_RANGE };
 
 struct Filter {
     FilterKind kind;
@@ -487,6 +511,195 @@ struct FilterPrefix : Filter {   // filter_prefix.go:20-106
             bs.visit_values(ch, bm, [&](sv x) { return match_prefix(encoded_to_string(ch->valueType, x), prefix); });
             break;
         }
+        default: throw std::runtime_error("unknown valueType");
+        }
+    }
+};
+
+// Filters of SURVEY §8(f) rank 3 (oracle side first; the product follows in round 2).  Same skeleton as above: const column, missing
+// column, then the per-valueType paths of the reference with their header-level early outs.
+inline void dict_lut(BlockSearch& bs, const Column* ch, Bitmap& bm, const std::function<bool(sv)>& f) {
+    std::vector<uint8_t> lut; for (auto& d : ch->dict) lut.push_back(f(d) ? 1 : 0);
+    bs.match_encoded_dict(ch, bm, lut);
+}
+
+struct FilterExactPrefix : Filter {   // filter_exact_prefix.go:13-277
+    std::string field, prefix; std::vector<std::string> tokens; std::vector<uint64_t> hashes;
+    FilterExactPrefix(sv f, sv p) : field(f), prefix(p) { kind = F_EXACT_PREFIX; tokens = tokens_skip_last(prefix); hashes = tokens_hashes(tokens); }
+    bool leaf_tokens(std::string* f, std::vector<std::string>* t) override { *f = field; *t = tokens; return true; }
+    void apply(BlockSearch& bs, Bitmap& bm) override {
+        sv v = bs.const_value(field);
+        if (!v.empty()) { if (!match_exact_prefix(v, prefix)) bm.reset_bits(); return; }
+        const Column* ch = bs.column(field);
+        if (!ch) { if (!match_exact_prefix("", prefix)) bm.reset_bits(); return; }
+        auto to_string_visit = [&] { bs.visit_values(ch, bm, [&](sv x) { return match_exact_prefix(encoded_to_string(ch->valueType, x), prefix); }); };
+        switch (ch->valueType) {
+        case VT_STRING:
+            if (!bs.bloom_all(ch, hashes)) { bm.reset_bits(); return; }
+            bs.visit_values(ch, bm, [&](sv x) { return match_exact_prefix(x, prefix); });
+            break;
+        case VT_DICT: dict_lut(bs, ch, bm, [&](sv d) { return match_exact_prefix(d, prefix); }); break;
+        case VT_UINT8: case VT_UINT16: case VT_UINT32: case VT_UINT64: {   // matchMinMaxExactPrefix :258-273
+            if (prefix.empty()) return;
+            if (!hashes.empty()) { bm.reset_bits(); return; }
+            uint64_t n;
+            if (!try_parse_uint64(prefix, &n) || n > ch->maxValue) { bm.reset_bits(); return; }
+            to_string_visit(); break;
+        }
+        case VT_INT64: {   // :235-256
+            if (prefix.empty()) return;
+            if (!hashes.empty()) { bm.reset_bits(); return; }
+            if (prefix != "-") {
+                int64_t n;
+                if (!try_parse_int64(prefix, &n) || n > (int64_t)ch->maxValue || n < (int64_t)ch->minValue) { bm.reset_bits(); return; }
+            }
+            to_string_visit(); break;
+        }
+        case VT_FLOAT64:   // :141-157
+            if (prefix.empty()) return;
+            if (hashes.size() > 2 * 6 || !bs.bloom_all(ch, hashes)) { bm.reset_bits(); return; }
+            to_string_visit(); break;
+        case VT_IPV4:      // :123-139
+            if (prefix.empty()) return;
+            if (prefix < "0" || prefix > "9" || hashes.size() > 3 * 6 || !bs.bloom_all(ch, hashes)) { bm.reset_bits(); return; }
+            to_string_visit(); break;
+        case VT_ISO8601:   // :105-121
+            if (prefix.empty()) return;
+            if (prefix < "0" || prefix > "9" || !bs.bloom_all(ch, hashes)) { bm.reset_bits(); return; }
+            to_string_visit(); break;
+        default: throw std::runtime_error("unknown valueType");
+        }
+    }
+};
+
+struct FilterSequence : Filter {   // filter_sequence.go:12-269
+    std::string field; std::vector<std::string> phrases; std::vector<std::string> tokens; std::vector<uint64_t> hashes;
+    FilterSequence(sv f, const std::vector<std::string>& ph) : field(f) {
+        kind = F_SEQUENCE;
+        for (auto& p : ph) if (!p.empty()) phrases.push_back(p);   // getNonEmptyPhrases :58-67
+        std::vector<sv> views(phrases.begin(), phrases.end());
+        tokens = tokenize_strings(views); hashes = tokens_hashes(tokens);
+    }
+    bool leaf_tokens(std::string* f, std::vector<std::string>* t) override { *f = field; *t = tokens; return true; }
+    void apply(BlockSearch& bs, Bitmap& bm) override {
+        if (phrases.empty()) return;
+        sv v = bs.const_value(field);
+        if (!v.empty()) { if (!match_sequence(v, phrases)) bm.reset_bits(); return; }
+        const Column* ch = bs.column(field);
+        if (!ch) { if (!match_sequence("", phrases)) bm.reset_bits(); return; }
+        auto to_string_visit = [&] {
+            if (!bs.bloom_all(ch, hashes)) { bm.reset_bits(); return; }
+            bs.visit_values(ch, bm, [&](sv x) { return match_sequence(encoded_to_string(ch->valueType, x), phrases); });
+        };
+        switch (ch->valueType) {
+        case VT_STRING:
+            if (!bs.bloom_all(ch, hashes)) { bm.reset_bits(); return; }
+            bs.visit_values(ch, bm, [&](sv x) { return match_sequence(x, phrases); });
+            break;
+        case VT_DICT: dict_lut(bs, ch, bm, [&](sv d) { return match_sequence(d, phrases); }); break;
+        case VT_UINT8: case VT_UINT16: case VT_UINT32: case VT_UINT64: case VT_INT64:   // :213-258: one phrase => exact value
+            if (phrases.size() > 1) { bm.reset_bits(); return; }
+            match_numeric_exact(bs, ch, bm, phrases[0], hashes); break;
+        case VT_FLOAT64: to_string_visit(); break;
+        case VT_IPV4: case VT_ISO8601:   // :139-175: one phrase => the phrase filter's path for the type
+            if (phrases.size() == 1) { single_phrase(bs, ch, bm); return; }
+            to_string_visit(); break;
+        default: throw std::runtime_error("unknown valueType");
+        }
+    }
+    void single_phrase(BlockSearch& bs, const Column* ch, Bitmap& bm) {   // matchIPv4ByPhrase / matchTimestampISO8601ByPhrase with the sequence's tokens
+        const std::string& phrase = phrases[0];
+        bool exact;
+        if (ch->valueType == VT_IPV4) { uint32_t ip; exact = try_parse_ipv4(phrase, &ip); } else { int64_t t; exact = try_parse_timestamp_iso8601(phrase, &t); }
+        if (exact) { match_numeric_exact(bs, ch, bm, phrase, hashes); return; }
+        if (!bs.bloom_all(ch, hashes)) { bm.reset_bits(); return; }
+        bs.visit_values(ch, bm, [&](sv x) { return match_phrase(encoded_to_string(ch->valueType, x), phrase); });
+    }
+};
+
+struct FilterLenRange : Filter {   // filter_len_range.go:14-348
+    std::string field; uint64_t minLen, maxLen;
+    FilterLenRange(sv f, uint64_t mn, uint64_t mx) : field(f), minLen(mn), maxLen(mx) { kind = F_LEN_RANGE; }
+    static size_t dec_len_u(uint64_t v) { std::string s; marshal_uint64_string(s, v); return s.size(); }
+    static size_t dec_len_i(int64_t v) { std::string s; marshal_int64_string(s, v); return s.size(); }
+    void apply(BlockSearch& bs, Bitmap& bm) override {
+        if (minLen > maxLen) { bm.reset_bits(); return; }
+        sv v = bs.const_value(field);
+        if (!v.empty()) { if (!match_len_range(v, minLen, maxLen)) bm.reset_bits(); return; }
+        const Column* ch = bs.column(field);
+        if (!ch) { if (!match_len_range("", minLen, maxLen)) bm.reset_bits(); return; }
+        auto to_string_visit = [&] { bs.visit_values(ch, bm, [&](sv x) { return match_len_range(encoded_to_string(ch->valueType, x), minLen, maxLen); }); };
+        auto uint_path = [&](uint64_t max_digits) {   // matchUintNByLenRange + matchMinMaxValueLen :338-348
+            if (minLen > max_digits || maxLen == 0) { bm.reset_bits(); return; }
+            if (maxLen < dec_len_u(ch->minValue) || minLen > dec_len_u(ch->maxValue)) { bm.reset_bits(); return; }
+            to_string_visit();
+        };
+        switch (ch->valueType) {
+        case VT_STRING: bs.visit_values(ch, bm, [&](sv x) { return match_len_range(x, minLen, maxLen); }); break;
+        case VT_DICT: dict_lut(bs, ch, bm, [&](sv d) { return match_len_range(d, minLen, maxLen); }); break;
+        case VT_UINT8: uint_path(3); break;
+        case VT_UINT16: uint_path(5); break;
+        case VT_UINT32: uint_path(10); break;
+        case VT_UINT64: uint_path(20); break;
+        case VT_INT64: {   // :305-331
+            if (minLen > 21 || maxLen == 0) { bm.reset_bits(); return; }
+            size_t mx = std::max(dec_len_i((int64_t)ch->minValue), dec_len_i((int64_t)ch->maxValue));
+            if ((uint64_t)mx < minLen) { bm.reset_bits(); return; }
+            to_string_visit(); break;
+        }
+        case VT_FLOAT64: if (minLen > 24 || maxLen == 0) { bm.reset_bits(); return; } to_string_visit(); break;
+        case VT_IPV4: if (minLen > 15 || maxLen < 7) { bm.reset_bits(); return; } to_string_visit(); break;
+        case VT_ISO8601: if (minLen > 24 || maxLen < 24) bm.reset_bits(); break;   // every value is len("2006-01-02T15:04:05.000Z") long; no values are read
+        default: throw std::runtime_error("unknown valueType");
+        }
+    }
+};
+
+struct FilterStringRange : Filter {   // filter_string_range.go:12-230
+    std::string field, minValue, maxValue;
+    FilterStringRange(sv f, sv mn, sv mx) : field(f), minValue(mn), maxValue(mx) { kind = F_STRING_RANGE; }
+    void apply(BlockSearch& bs, Bitmap& bm) override {
+        if (minValue > maxValue) { bm.reset_bits(); return; }
+        sv v = bs.const_value(field);
+        if (!v.empty()) { if (!match_string_range(v, minValue, maxValue)) bm.reset_bits(); return; }
+        const Column* ch = bs.column(field);
+        if (!ch) { if (!match_string_range("", minValue, maxValue)) bm.reset_bits(); return; }
+        auto to_string_visit = [&] { bs.visit_values(ch, bm, [&](sv x) { return match_string_range(encoded_to_string(ch->valueType, x), minValue, maxValue); }); };
+        switch (ch->valueType) {
+        case VT_STRING: bs.visit_values(ch, bm, [&](sv x) { return match_string_range(x, minValue, maxValue); }); break;
+        case VT_DICT: dict_lut(bs, ch, bm, [&](sv d) { return match_string_range(d, minValue, maxValue); }); break;
+        case VT_UINT8: case VT_UINT16: case VT_UINT32: case VT_UINT64: case VT_IPV4: case VT_ISO8601:
+            if (minValue > "9" || maxValue < "0") { bm.reset_bits(); return; }
+            to_string_visit(); break;
+        case VT_INT64:   // :213-224
+            if ((minValue != "-" && minValue > "9") || (maxValue != "-" && maxValue < "0")) { bm.reset_bits(); return; }
+            to_string_visit(); break;
+        case VT_FLOAT64:
+            if (minValue > "9" || maxValue < "+") { bm.reset_bits(); return; }
+            to_string_visit(); break;
+        default: throw std::runtime_error("unknown valueType");
+        }
+    }
+};
+
+struct FilterIPv4Range : Filter {   // filter_ipv4_range.go:12-191
+    std::string field; uint32_t minValue, maxValue;
+    FilterIPv4Range(sv f, uint32_t mn, uint32_t mx) : field(f), minValue(mn), maxValue(mx) { kind = F_IPV4_RANGE; }
+    bool match_str(sv s) const { uint32_t n; return try_parse_ipv4(s, &n) && n >= minValue && n <= maxValue; }
+    void apply(BlockSearch& bs, Bitmap& bm) override {
+        if (minValue > maxValue) { bm.reset_bits(); return; }
+        sv v = bs.const_value(field);
+        if (!v.empty()) { if (!match_str(v)) bm.reset_bits(); return; }
+        const Column* ch = bs.column(field);
+        if (!ch) { bm.reset_bits(); return; }
+        switch (ch->valueType) {
+        case VT_STRING: bs.visit_values(ch, bm, [&](sv x) { return match_str(x); }); break;
+        case VT_DICT: dict_lut(bs, ch, bm, [&](sv d) { return match_str(d); }); break;
+        case VT_IPV4:   // matchIPv4ByRange :176-191
+            if (ch->minValue > (uint64_t)maxValue || ch->maxValue < (uint64_t)minValue) { bm.reset_bits(); return; }
+            bs.visit_values(ch, bm, [&](sv x) { if (x.size() != 4) throw std::runtime_error("unexpected length for binary representation of IPv4"); uint32_t n = get_be32((const uint8_t*)x.data()); return n >= minValue && n <= maxValue; });
+            break;
+        case VT_UINT8: case VT_UINT16: case VT_UINT32: case VT_UINT64: case VT_INT64: case VT_FLOAT64: case VT_ISO8601: bm.reset_bits(); break;
         default: throw std::runtime_error("unknown valueType");
         }
     }

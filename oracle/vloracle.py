@@ -43,7 +43,8 @@ def lib():
                      "vlo_regex_describe", "vlo_encoded_to_string", "vlo_marshal_strings_block", "vlo_filter_tokens"):
             getattr(L, name).restype = C.c_int64
         for name in ("vlo_block_build", "vlo_filter_phrase", "vlo_filter_prefix", "vlo_filter_exact", "vlo_filter_in", "vlo_filter_regexp",
-                     "vlo_filter_noop", "vlo_filter_and", "vlo_filter_or", "vlo_filter_not", "vlo_gen_block"):
+                     "vlo_filter_noop", "vlo_filter_and", "vlo_filter_or", "vlo_filter_not", "vlo_gen_block",
+                     "vlo_filter_exact_prefix", "vlo_filter_sequence", "vlo_filter_len_range", "vlo_filter_string_range", "vlo_filter_ipv4_range"):
             getattr(L, name).restype = C.c_void_p
         for name in ("vlo_block_rows", "vlo_block_ncolumns", "vlo_block_nconsts"):
             getattr(L, name).restype = C.c_uint64
@@ -330,6 +331,33 @@ class Filter:
     def regexp(field, expr):
         f, p = _b(field), _b(expr)
         return Filter(lib().vlo_filter_regexp(f, C.c_uint64(len(f)), p, C.c_uint64(len(p))))
+
+    # --- SURVEY §8(f) rank 3 filters (oracle side; pinned by the reference's filter_*_test.go tables) ---
+    @staticmethod
+    def exact_prefix(field, prefix):
+        f, p = _b(field), _b(prefix)
+        return Filter(lib().vlo_filter_exact_prefix(f, C.c_uint64(len(f)), p, C.c_uint64(len(p))))
+
+    @staticmethod
+    def sequence(field, phrases):
+        f = _b(field)
+        blob, offs = _pack(phrases)
+        return Filter(lib().vlo_filter_sequence(f, C.c_uint64(len(f)), blob, offs.ctypes.data_as(C.c_void_p), C.c_uint64(len(phrases))))
+
+    @staticmethod
+    def len_range(field, min_len, max_len):
+        f = _b(field)
+        return Filter(lib().vlo_filter_len_range(f, C.c_uint64(len(f)), C.c_uint64(min_len), C.c_uint64(max_len)))
+
+    @staticmethod
+    def string_range(field, min_value, max_value):
+        f, a, b = _b(field), _b(min_value), _b(max_value)
+        return Filter(lib().vlo_filter_string_range(f, C.c_uint64(len(f)), a, C.c_uint64(len(a)), b, C.c_uint64(len(b))))
+
+    @staticmethod
+    def ipv4_range(field, min_value, max_value):
+        f = _b(field)
+        return Filter(lib().vlo_filter_ipv4_range(f, C.c_uint64(len(f)), C.c_uint32(min_value), C.c_uint32(max_value)))
 
     @staticmethod
     def noop():

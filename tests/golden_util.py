@@ -6,8 +6,8 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def load_filter_cases():
-    cases = json.load(open(os.path.join(HERE, "golden", "filter_cases.json")))
+def load_filter_cases(name="filter_cases.json"):
+    cases = json.load(open(os.path.join(HERE, "golden", name)))
     for c in cases:
         c["columns"] = [(bytes.fromhex(col["name"]), [bytes.fromhex(v) for v in col["values"]]) for col in c["columns"]]
         # generateRowsFromColumns (filter_test.go:248-277) also adds the stream tags as fields
@@ -40,6 +40,16 @@ def build_filter(F, spec):
     field = bytes.fromhex(spec["field"])
     if k == "in":
         return F.in_(field, [bytes.fromhex(v) for v in spec["values"]])
+    if k == "sequence":
+        return F.sequence(field, [bytes.fromhex(v) for v in spec["values"]])
+    if k == "len_range":
+        return F.len_range(field, spec["min"], spec["max"])
+    if k == "ipv4_range":
+        return F.ipv4_range(field, spec["min"], spec["max"])
+    if k == "string_range":
+        return F.string_range(field, bytes.fromhex(spec["min"]), bytes.fromhex(spec["max"]))
+    if k == "exact_prefix":
+        return F.exact_prefix(field, bytes.fromhex(spec["arg"]))
     arg = bytes.fromhex(spec["arg"])
     return {"phrase": F.phrase, "prefix": F.prefix, "exact": F.exact, "regexp": F.regexp}[k](field, arg)
 

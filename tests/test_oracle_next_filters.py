@@ -1,0 +1,48 @@
+"""Oracle for the filters of SURVEY §8(f) rank 3 (exact_prefix, seq(), len_range(), string_range(), ipv4_range()), pinned by the
+reference's own tables: every testFilterMatchForColumns case of filter_{exact_prefix,sequence,len_range,string_range,ipv4_range}_test.go
+(transcribed by tests/golden/extract_go_fixtures.py into tests/golden/filter_cases_next.json).  The product does not compile these
+filter kinds yet; this is the checker it will be held to."""
+import pytest
+
+from golden_util import load_filter_cases, build_filter
+
+CASES = load_filter_cases("filter_cases_next.json")
+
+
+def test_counts():
+    kinds = {}
+    for c in CASES:
+        kinds[c["filter"]["kind"]] = kinds.get(c["filter"]["kind"], 0) + 1
+    assert kinds == {"exact_prefix": 62, "sequence": 103, "len_range": 30, "string_range": 48, "ipv4_range": 24}
+
+
+@pytest.mark.parametrize("idx", range(len(CASES)))
+def test_reference_tables(oracle, idx):
+    c = CASES[idx]
+    b = oracle.Block.from_columns(c["columns"])
+    f = build_filter(oracle.Filter, c["filter"])
+    got = oracle.bitmap_rows(b.search(f), b.rows)
+    assert got == c["expected"], (c["src"], c["filter"])
+
+
+def test_predicates(oracle):
+    F = oracle.Filter
+    # matchSequence (filter_sequence.go:260-269): phrases in order, each after the end of the previous one
+    blk = oracle.Block.from_columns([("m", [b"a b c", b"c b a", b"ab c", b"a-b-c", b"a b", b"", b"a a b c c"]), ("k", [b"%d" % i for i in range(7)])])
+    rows = lambda f: oracle.bitmap_rows(blk.search(f), blk.rows)
+    assert rows(F.sequence("m", ["a", "b", "c"])) == [0, 3, 6]
+    assert rows(F.sequence("m", ["c", "a"])) == [1]
+    assert rows(F.sequence("m", ["", ""])) == list(range(7))          # only empty phrases: matches everything
+    assert rows(F.sequence("m", ["a", "", "b"])) == [0, 3, 4, 6]      # empty phrases are dropped
+    assert rows(F.exact_prefix("m", "a b")) == [0, 4]
+    assert rows(F.exact_prefix("m", "")) == list(range(7))
+    # len_range counts runes, invalid bytes one each (utf8.RuneCountInString)
+    u = oracle.Block.from_columns([("m", ["йцу".encode(), b"\xff\xfe", b"abc", b"", "日本".encode() + b"\x80"]), ("k", [b"%d" % i for i in range(5)])])
+    assert oracle.bitmap_rows(u.search(F.len_range("m", 3, 3)), u.rows) == [0, 2, 4]
+    assert oracle.bitmap_rows(u.search(F.len_range("m", 0, 0)), u.rows) == [3]
+    assert oracle.bitmap_rows(u.search(F.len_range("m", 5, 1)), u.rows) == []
+    # string_range is a plain byte comparison, half open
+    assert rows(F.string_range("m", "a b", "ab c")) == [0, 3, 4]      # "a a b c c" < "a b"; "ab c" itself is excluded
+    ip = oracle.Block.from_columns([("ip", [b"10.0.0.%d" % i for i in range(20)]), ("k", [b"%d" % i for i in range(20)])])
+    assert oracle.bitmap_rows(ip.search(F.ipv4_range("ip", 0x0A000005, 0x0A000007)), ip.rows) == [5, 6, 7]
+    assert oracle.bitmap_rows(ip.search(F.ipv4_range("k", 0, 0xFFFFFFFF)), ip.rows) == []      # a uint8 column never matches
