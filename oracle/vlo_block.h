@@ -370,7 +370,7 @@ inline std::string encoded_to_string(uint8_t vt, sv v) {
 // ---- filters ---------------------------------------------------------------------------------------------------------
 struct FieldTokens { std::string field; std::vector<std::string> tokens; std::vector<uint64_t> hashes; };
 
-enum FilterKind { F_NOOP, F_PHRASE, F_PREFIX, F_EXACT, F_IN, F_REGEXP, F_AND, F_OR, F_NOT, F_EXACT_PREFIX, F_SEQUENCE, F_LEN_RANGE, F_STRING_RANGE, F_IPV4_RANGE };
+enum FilterKind { F_NOOP, F_PHRASE, F_PREFIX, F_EXACT, F_IN, F_REGEXP, F_AND, F_OR, F_NOT, F_EXACT_PREFIX, F_SEQUENCE, F_LEN_RANGE, F_STRING_RANGE, F_IPV4_RANGE, F_CONTAINS_ALL, F_CONTAINS_ANY };
 
 struct Filter {
     FilterKind kind;
@@ -798,6 +798,100 @@ struct FilterIn : Filter {   // filter_in.go:14-234 + in_values.go
             if (!any) { bm.reset_bits(); return; }
         }
         bs.visit_values(ch, bm, [&](sv x) { return bin.count(std::string(x)) > 0; });
+    }
+};
+
+// contains_all() / contains_any(): the values are phrases (filter_contains_all.go, filter_contains_any.go, in_values.go)
+inline bool match_all_phrases(sv v, const std::vector<std::string>& phrases) {   // filter_contains_all.go:310-321
+    for (auto& p : phrases) { if (p.empty()) continue; if (!match_phrase(v, p)) return false; }
+    return true;
+}
+inline bool match_any_phrase(sv v, const std::vector<std::string>& phrases) {    // filter_contains_any.go:293-300
+    for (auto& p : phrases) if (match_phrase(v, p)) return true;
+    return false;
+}
+
+struct FilterContainsAll : Filter {   // filter_contains_all.go:12-321
+    FilterIn iv;   // reuses the inValues restatement (string set, typed sets)
+    std::vector<uint64_t> hashesAll;   // inValues.getTokensHashesAll in_values.go:94-102
+    FilterContainsAll(sv f, const std::vector<std::string>& vals) : iv(f, vals) {
+        kind = F_CONTAINS_ALL;
+        std::vector<sv> views(iv.values.begin(), iv.values.end());
+        for (uint64_t h : tokenize_hashes(views)) append_hashes_hashes(hashesAll, h);
+    }
+    size_t non_empty_values_len() const { return iv.strset.size() - iv.strset.count(""); }   // :80-88
+    void apply(BlockSearch& bs, Bitmap& bm) override {
+        const auto& phrases = iv.values;
+        if (phrases.empty() || (phrases.size() == 1 && phrases[0].empty())) return;
+        sv v = bs.const_value(iv.field);
+        if (!v.empty()) { if (!match_all_phrases(v, phrases)) bm.reset_bits(); return; }
+        const Column* ch = bs.column(iv.field);
+        if (!ch) { if (!match_all_phrases("", phrases)) bm.reset_bits(); return; }
+        switch (ch->valueType) {
+        case VT_STRING:
+            if (!bs.bloom_all(ch, hashesAll)) { bm.reset_bits(); return; }
+            bs.visit_values(ch, bm, [&](sv x) { return match_all_phrases(x, phrases); });
+            break;
+        case VT_DICT: dict_lut(bs, ch, bm, [&](sv d) { return match_all_phrases(d, phrases); }); break;
+        case VT_UINT8: case VT_UINT16: case VT_UINT32: case VT_UINT64: {   // matchAllValues :168-189
+            size_t n = non_empty_values_len();
+            if (n == 0) return;
+            auto bin = iv.bin_values(ch->valueType);
+            if (n != 1 || n != bin.size()) { bm.reset_bits(); return; }
+            if (!bs.bloom_all(ch, hashesAll)) { bm.reset_bits(); return; }
+            const std::string& want = *bin.begin();
+            bs.visit_values(ch, bm, [&](sv x) { return x == want; });
+            break;
+        }
+        case VT_INT64: case VT_FLOAT64: case VT_IPV4: case VT_ISO8601:
+            if (!bs.bloom_all(ch, hashesAll)) { bm.reset_bits(); return; }
+            bs.visit_values(ch, bm, [&](sv x) { return match_all_phrases(encoded_to_string(ch->valueType, x), phrases); });
+            break;
+        default: throw std::runtime_error("unknown valueType");
+        }
+    }
+};
+
+struct FilterContainsAny : Filter {   // filter_contains_any.go:12-300
+    FilterIn iv;   // common tokens + per-value token sets: getTokensHashesAny == the in() filter's
+    FilterContainsAny(sv f, const std::vector<std::string>& vals) : iv(f, vals) { kind = F_CONTAINS_ANY; }
+    void apply(BlockSearch& bs, Bitmap& bm) override {
+        const auto& phrases = iv.values;
+        if (phrases.empty()) { bm.reset_bits(); return; }
+        if (iv.strset.count("")) return;   // hasEmptyValue: the empty phrase matches everything here
+        sv v = bs.const_value(iv.field);
+        if (!v.empty()) { if (!match_any_phrase(v, phrases)) bm.reset_bits(); return; }
+        const Column* ch = bs.column(iv.field);
+        if (!ch) { if (!match_any_phrase("", phrases)) bm.reset_bits(); return; }
+        // matchValuesAnyPhrase :170-189: only the phrases whose own tokens pass the bloom filter are tried on the rows
+        auto any_phrase = [&](bool to_string) {
+            if (!bs.bloom_all(ch, iv.commonHashes)) { bm.reset_bits(); return; }
+            const BloomFilter& bf = bs.bloom(ch);
+            std::vector<std::string> alive;
+            for (size_t i = 0; i < phrases.size(); i++) { if (bs.st) bs.st->bloom_probe_bytes += 8 * iv.tokenSetsHashes[i].size(); if (bf.contains_all(iv.tokenSetsHashes[i])) alive.push_back(phrases[i]); }
+            if (alive.empty()) { bm.reset_bits(); return; }
+            if (to_string) bs.visit_values(ch, bm, [&](sv x) { return match_any_phrase(encoded_to_string(ch->valueType, x), alive); });
+            else bs.visit_values(ch, bm, [&](sv x) { return match_any_phrase(x, alive); });
+        };
+        switch (ch->valueType) {
+        case VT_STRING: any_phrase(false); break;
+        case VT_DICT: dict_lut(bs, ch, bm, [&](sv d) { return match_any_phrase(d, phrases); }); break;
+        case VT_UINT8: case VT_UINT16: case VT_UINT32: case VT_UINT64: {   // matchAnyValue filter_in.go:187-218
+            auto bin = iv.bin_values(ch->valueType);
+            if (bin.empty()) { bm.reset_bits(); return; }
+            if (!bs.bloom_all(ch, iv.commonHashes)) { bm.reset_bits(); return; }
+            if (!(iv.tokenSetsHashes.size() > 1000 || iv.tokenSetsHashes.size() > 10 * bs.b->rows)) {
+                bool any = false;
+                const BloomFilter& bf = bs.bloom(ch);
+                for (auto& t : iv.tokenSetsHashes) { if (bs.st) bs.st->bloom_probe_bytes += 8 * t.size(); if (bf.contains_all(t)) { any = true; break; } }
+                if (!any) { bm.reset_bits(); return; }
+            }
+            bs.visit_values(ch, bm, [&](sv x) { return bin.count(std::string(x)) > 0; });
+            break;
+        }
+        case VT_INT64: case VT_FLOAT64: case VT_IPV4: case VT_ISO8601: any_phrase(true); break;
+        default: throw std::runtime_error("unknown valueType");
+        }
     }
 };
 

@@ -252,6 +252,9 @@ def filter_spec(v):
         return {"kind": "exact_prefix", "field": hx(field), "arg": hx(f.get("prefix", b""))}
     if kind == "filterSequence":
         return {"kind": "sequence", "field": hx(field), "values": [hx(x) for x in (f.get("phrases") or [])]}
+    if kind in ("filterContainsAll", "filterContainsAny"):
+        vals = f["values"][2].get("values", []) if "values" in f else []
+        return {"kind": "contains_all" if kind == "filterContainsAll" else "contains_any", "field": hx(field), "values": [hx(x) for x in (vals or [])]}
     if kind == "filterLenRange":
         return {"kind": "len_range", "field": hx(field), "min": num("minLen"), "max": num("maxLen")}
     if kind == "filterStringRange":
@@ -262,7 +265,7 @@ def filter_spec(v):
 
 
 SUPPORTED = ("filterPhrase", "filterPrefix", "filterExact", "filterRegexp", "filterIn", "filterNot",
-             "filterExactPrefix", "filterSequence", "filterLenRange", "filterStringRange", "filterIPv4Range")
+             "filterExactPrefix", "filterSequence", "filterLenRange", "filterStringRange", "filterIPv4Range", "filterContainsAll", "filterContainsAny")
 
 
 def extract_filter_cases(path):
@@ -405,7 +408,8 @@ def main():
     # filters of SURVEY §8(f) rank 3: the oracle implements them already, the product does not yet (kept in a file of their own so
     # that the GPU parity tests keep iterating over exactly the kinds libvlscan compiles)
     cases = []
-    for name in ("filter_exact_prefix_test.go", "filter_sequence_test.go", "filter_len_range_test.go", "filter_string_range_test.go", "filter_ipv4_range_test.go"):
+    for name in ("filter_exact_prefix_test.go", "filter_sequence_test.go", "filter_len_range_test.go", "filter_string_range_test.go", "filter_ipv4_range_test.go",
+                 "filter_contains_all_test.go", "filter_contains_any_test.go"):
         c = extract_filter_cases(os.path.join(REF, name))
         print(name, len(c))
         cases.extend(c)

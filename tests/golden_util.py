@@ -40,6 +40,8 @@ def build_filter(F, spec):
     field = bytes.fromhex(spec["field"])
     if k == "in":
         return F.in_(field, [bytes.fromhex(v) for v in spec["values"]])
+    if k in ("contains_all", "contains_any"):
+        return getattr(F, k)(field, [bytes.fromhex(v) for v in spec["values"]])
     if k == "sequence":
         return F.sequence(field, [bytes.fromhex(v) for v in spec["values"]])
     if k == "len_range":

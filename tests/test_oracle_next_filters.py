@@ -13,7 +13,7 @@ def test_counts():
     kinds = {}
     for c in CASES:
         kinds[c["filter"]["kind"]] = kinds.get(c["filter"]["kind"], 0) + 1
-    assert kinds == {"exact_prefix": 62, "sequence": 103, "len_range": 30, "string_range": 48, "ipv4_range": 24}
+    assert kinds == {"exact_prefix": 62, "sequence": 103, "len_range": 30, "string_range": 48, "ipv4_range": 24, "contains_all": 104, "contains_any": 88}
 
 
 @pytest.mark.parametrize("idx", range(len(CASES)))
