@@ -370,7 +370,8 @@ inline std::string encoded_to_string(uint8_t vt, sv v) {
 // ---- filters ---------------------------------------------------------------------------------------------------------
 struct FieldTokens { std::string field; std::vector<std::string> tokens; std::vector<uint64_t> hashes; };
 
-enum FilterKind { F_NOOP, F_PHRASE, F_PREFIX, F_EXACT, F_IN, F_REGEXP, F_AND, F_OR, F_NOT, F_EXACT_PREFIX, F_SEQUENCE, F_LEN_RANGE, F_STRING_RANGE, F_IPV4_RANGE, F_CONTAINS_ALL, F_CONTAINS_ANY };
+enum FilterKind { F_NOOP, F_PHRASE, F_PREFIX, F_EXACT, F_IN, F_REGEXP, F_AND, F_OR, F_NOT, F_EXACT_PREFIX, F_SEQUENCE, F_LEN_RANGE, F_STRING_RANGE, F_IPV4_RANGE, F_CONTAINS_ALL, F_CONTAINS_ANY,
+                  F_ANY_CASE_PHRASE, F_ANY_CASE_PREFIX, F_VALUE_TYPE };
 
 struct Filter {
     FilterKind kind;
@@ -892,6 +893,90 @@ struct FilterContainsAny : Filter {   // filter_contains_any.go:12-300
         case VT_INT64: case VT_FLOAT64: case VT_IPV4: case VT_ISO8601: any_phrase(true); break;
         default: throw std::runtime_error("unknown valueType");
         }
+    }
+};
+
+// i(phrase) / i(prefix*): case-insensitive forms.  The needle is lower-cased once; a value is lower-cased only when it is not plain
+// lower-case ASCII already.  The byte-length check happens BEFORE the value is lower-cased (lower-casing can change the byte length).
+inline bool match_any_case_phrase(sv s, sv phraseLower) {   // filter_any_case_phrase.go:161-178
+    if (phraseLower.empty()) return s.empty();
+    if (phraseLower.size() > s.size()) return false;
+    if (is_ascii_lowercase(s)) return match_phrase(s, phraseLower);
+    return match_phrase(strings_to_lower(s), phraseLower);
+}
+inline bool match_any_case_prefix(sv s, sv prefixLower) {   // filter_any_case_prefix.go:150-167
+    if (prefixLower.empty()) return !s.empty();
+    if (prefixLower.size() > s.size()) return false;
+    if (is_ascii_lowercase(s)) return match_prefix(s, prefixLower);
+    return match_prefix(strings_to_lower(s), prefixLower);
+}
+inline std::vector<uint64_t> upper_tokens_hashes(const std::vector<std::string>& tokens) {
+    std::vector<std::string> up; for (auto& t : tokens) up.push_back(strings_to_upper(t));
+    return tokens_hashes(up);
+}
+
+struct FilterAnyCasePhrase : Filter {   // filter_any_case_phrase.go:14-190
+    std::string field, phrase;
+    FilterPhrase lower, upper;   // the numeric paths are the phrase filter's, run with the lower- (iso8601: upper-) cased phrase and THIS filter's tokens
+    FilterAnyCasePhrase(sv f, sv p) : field(f), phrase(p), lower(f, strings_to_lower(p)), upper(f, strings_to_upper(p)) {
+        kind = F_ANY_CASE_PHRASE;
+        std::vector<std::string> tokens = tokenize_string(phrase);   // initTokens :44-53: tokens of the phrase as written
+        lower.hashes = tokens_hashes(tokens); upper.hashes = upper_tokens_hashes(tokens);
+    }
+    void apply(BlockSearch& bs, Bitmap& bm) override {
+        const std::string& pl = lower.phrase;
+        sv v = bs.const_value(field);
+        if (!v.empty()) { if (!match_any_case_phrase(v, pl)) bm.reset_bits(); return; }
+        const Column* ch = bs.column(field);
+        if (!ch) { if (!pl.empty()) bm.reset_bits(); return; }
+        switch (ch->valueType) {
+        case VT_STRING: bs.visit_values(ch, bm, [&](sv x) { return match_any_case_phrase(x, pl); }); break;   // no bloom probe: tokens are case sensitive
+        case VT_DICT: dict_lut(bs, ch, bm, [&](sv d) { return match_any_case_phrase(d, pl); }); break;
+        case VT_ISO8601: upper.apply(bs, bm); break;
+        default: lower.apply(bs, bm);
+        }
+    }
+};
+
+struct FilterAnyCasePrefix : Filter {   // filter_any_case_prefix.go:14-182
+    std::string field, prefix;
+    FilterPrefix lower, upper;
+    FilterAnyCasePrefix(sv f, sv p) : field(f), prefix(p), lower(f, strings_to_lower(p)), upper(f, strings_to_upper(p)) {
+        kind = F_ANY_CASE_PREFIX;
+        std::vector<std::string> tokens = tokens_skip_last(prefix);   // initTokens :56-65
+        lower.hashes = tokens_hashes(tokens); upper.hashes = upper_tokens_hashes(tokens);
+    }
+    void apply(BlockSearch& bs, Bitmap& bm) override {
+        const std::string& pl = lower.prefix;
+        sv v = bs.const_value(field);
+        if (!v.empty()) { if (!match_any_case_prefix(v, pl)) bm.reset_bits(); return; }
+        const Column* ch = bs.column(field);
+        if (!ch) { bm.reset_bits(); return; }
+        switch (ch->valueType) {
+        case VT_STRING: bs.visit_values(ch, bm, [&](sv x) { return match_any_case_prefix(x, pl); }); break;
+        case VT_DICT: dict_lut(bs, ch, bm, [&](sv d) { return match_any_case_prefix(d, pl); }); break;
+        case VT_ISO8601: upper.apply(bs, bm); break;
+        default: lower.apply(bs, bm);
+        }
+    }
+};
+
+struct FilterValueType : Filter {   // filter_value_type.go:12-67; names: valueType.String() values_encoder.go
+    std::string field, typ;
+    FilterValueType(sv f, sv t) : field(f), typ(t) { kind = F_VALUE_TYPE; }
+    static const char* name_of(uint8_t vt) {
+        switch (vt) {
+        case VT_STRING: return "string"; case VT_DICT: return "dict"; case VT_UINT8: return "uint8"; case VT_UINT16: return "uint16"; case VT_UINT32: return "uint32";
+        case VT_UINT64: return "uint64"; case VT_INT64: return "int64"; case VT_FLOAT64: return "float64"; case VT_IPV4: return "ipv4"; case VT_ISO8601: return "iso8601";
+        }
+        return "unknown";
+    }
+    void apply(BlockSearch& bs, Bitmap& bm) override {
+        sv v = bs.const_value(field);
+        if (!v.empty()) { if (typ != "const") bm.reset_bits(); return; }
+        const Column* ch = bs.column(field);
+        if (!ch) { bm.reset_bits(); return; }
+        if (typ != name_of(ch->valueType)) bm.reset_bits();
     }
 };
 

@@ -88,6 +88,29 @@ inline void append_rune(std::string& dst, int32_t r) {
 }
 
 #include "unicode_tables.inc"
+#include "unicode_case.inc"
+
+// unicode.ToLower / unicode.ToUpper (simple case mappings) and the string forms the i(...) filters use:
+// strings.ToLower / strings.ToUpper / stringsutil.AppendLowercase (vm/lib/stringsutil/stringsutil.go:26-51).  All three walk the string
+// rune by rune; an invalid byte decodes to utf8.RuneError and is written back as U+FFFD (3 bytes).
+inline int32_t map_case(const unsigned int (*tab)[2], int n, int32_t r) {
+    int lo = 0, hi = n - 1;
+    while (lo <= hi) { int mid = (lo + hi) / 2; if ((int32_t)tab[mid][0] == r) return (int32_t)tab[mid][1]; if ((int32_t)tab[mid][0] < r) lo = mid + 1; else hi = mid - 1; }
+    return r;
+}
+inline int32_t to_lower_rune(int32_t r) { if (r < 0x80) return (r >= 'A' && r <= 'Z') ? r + 32 : r; return map_case(VL_TOLOWER, VL_TOLOWER_COUNT, r); }
+inline int32_t to_upper_rune(int32_t r) { if (r < 0x80) return (r >= 'a' && r <= 'z') ? r - 32 : r; return map_case(VL_TOUPPER, VL_TOUPPER_COUNT, r); }
+inline std::string map_string(sv s, int32_t (*f)(int32_t)) {
+    std::string out; const uint8_t* p = (const uint8_t*)s.data(); size_t left = s.size();
+    while (left) { int sz; int32_t r = decode_rune(p, left, &sz); append_rune(out, f(r)); p += sz; left -= (size_t)sz; }
+    return out;
+}
+inline std::string strings_to_lower(sv s) { return map_string(s, to_lower_rune); }
+inline std::string strings_to_upper(sv s) { return map_string(s, to_upper_rune); }
+inline bool is_ascii_lowercase(sv s) {   // filter_any_case_phrase.go isASCIILowercase
+    for (unsigned char c : s) if (c >= 0x80 || (c >= 'A' && c <= 'Z')) return false;
+    return true;
+}
 
 // lib/logstorage/tokenizer.go:128-148 isTokenChar / isTokenRune
 inline bool is_token_char(uint8_t c) {

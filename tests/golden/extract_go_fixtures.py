@@ -255,6 +255,12 @@ def filter_spec(v):
     if kind in ("filterContainsAll", "filterContainsAny"):
         vals = f["values"][2].get("values", []) if "values" in f else []
         return {"kind": "contains_all" if kind == "filterContainsAll" else "contains_any", "field": hx(field), "values": [hx(x) for x in (vals or [])]}
+    if kind == "filterAnyCasePhrase":
+        return {"kind": "any_case_phrase", "field": hx(field), "arg": hx(f.get("phrase", b""))}
+    if kind == "filterAnyCasePrefix":
+        return {"kind": "any_case_prefix", "field": hx(field), "arg": hx(f.get("prefix", b""))}
+    if kind == "filterValueType":
+        return {"kind": "value_type", "field": hx(field), "arg": hx(f.get("valueType", b""))}
     if kind == "filterLenRange":
         return {"kind": "len_range", "field": hx(field), "min": num("minLen"), "max": num("maxLen")}
     if kind == "filterStringRange":
@@ -265,7 +271,8 @@ def filter_spec(v):
 
 
 SUPPORTED = ("filterPhrase", "filterPrefix", "filterExact", "filterRegexp", "filterIn", "filterNot",
-             "filterExactPrefix", "filterSequence", "filterLenRange", "filterStringRange", "filterIPv4Range", "filterContainsAll", "filterContainsAny")
+             "filterExactPrefix", "filterSequence", "filterLenRange", "filterStringRange", "filterIPv4Range", "filterContainsAll", "filterContainsAny",
+             "filterAnyCasePhrase", "filterAnyCasePrefix", "filterValueType")
 
 
 def extract_filter_cases(path):
@@ -409,7 +416,8 @@ def main():
     # that the GPU parity tests keep iterating over exactly the kinds libvlscan compiles)
     cases = []
     for name in ("filter_exact_prefix_test.go", "filter_sequence_test.go", "filter_len_range_test.go", "filter_string_range_test.go", "filter_ipv4_range_test.go",
-                 "filter_contains_all_test.go", "filter_contains_any_test.go"):
+                 "filter_contains_all_test.go", "filter_contains_any_test.go", "filter_any_case_phrase_test.go", "filter_any_case_prefix_test.go",
+                 "filter_value_type_test.go"):
         c = extract_filter_cases(os.path.join(REF, name))
         print(name, len(c))
         cases.extend(c)

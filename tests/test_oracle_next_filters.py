@@ -13,7 +13,8 @@ def test_counts():
     kinds = {}
     for c in CASES:
         kinds[c["filter"]["kind"]] = kinds.get(c["filter"]["kind"], 0) + 1
-    assert kinds == {"exact_prefix": 62, "sequence": 103, "len_range": 30, "string_range": 48, "ipv4_range": 24, "contains_all": 104, "contains_any": 88}
+    assert kinds == {"exact_prefix": 62, "sequence": 103, "len_range": 30, "string_range": 48, "ipv4_range": 24, "contains_all": 104, "contains_any": 88,
+                     "any_case_phrase": 107, "any_case_prefix": 114, "value_type": 35}
 
 
 @pytest.mark.parametrize("idx", range(len(CASES)))
@@ -43,6 +44,17 @@ def test_predicates(oracle):
     assert oracle.bitmap_rows(u.search(F.len_range("m", 5, 1)), u.rows) == []
     # string_range is a plain byte comparison, half open
     assert rows(F.string_range("m", "a b", "ab c")) == [0, 3, 4]      # "a a b c c" < "a b"; "ab c" itself is excluded
+    # i(...): the value is lower-cased rune by rune (unicode.ToLower); invalid bytes become U+FFFD; the byte-length check precedes it
+    cs = oracle.Block.from_columns([("m", [b"Foo BAR", "ПРИВЕТ мир".encode(), b"foo\xffBAR", "İstanbul".encode(), b"foo bar", "ǅ".encode()]), ("k", [b"%d" % i for i in range(6)])])
+    crow = lambda f: oracle.bitmap_rows(cs.search(f), cs.rows)
+    assert crow(F.any_case_phrase("m", "BAR")) == [0, 4]             # row 2 becomes "foo�bar": U+FFFD decodes to RuneError, which counts as a token char
+    assert crow(F.any_case_phrase("m", "foo�bar".encode())) == []    # 9-byte phrase vs 7-byte value: rejected by the byte-length check that precedes lower-casing
+    assert crow(F.any_case_phrase("m", "привет")) == [1]
+    assert crow(F.any_case_prefix("m", "ПРИ")) == [1]
+    assert crow(F.any_case_phrase("m", "istanbul")) == [3]           # U+0130 -> 'i' (simple mapping, not "i̇")
+    assert crow(F.any_case_phrase("m", "ǆ")) == [5] and crow(F.any_case_phrase("m", "Ǆ")) == [5]
+    assert crow(F.any_case_prefix("m", "")) == list(range(6))
+    assert crow(F.value_type("m", "string")) == list(range(6)) and crow(F.value_type("m", "dict")) == []
     ip = oracle.Block.from_columns([("ip", [b"10.0.0.%d" % i for i in range(20)]), ("k", [b"%d" % i for i in range(20)])])
     assert oracle.bitmap_rows(ip.search(F.ipv4_range("ip", 0x0A000005, 0x0A000007)), ip.rows) == [5, 6, 7]
     assert oracle.bitmap_rows(ip.search(F.ipv4_range("k", 0, 0xFFFFFFFF)), ip.rows) == []      # a uint8 column never matches
