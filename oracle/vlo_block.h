@@ -6,6 +6,8 @@
 //   lib/logstorage/block_search.go:207-226,232-324,411-474 (blockSearch.search / header + bloom + values access)
 //   lib/logstorage/bitmap.go:28-191
 //   lib/logstorage/filter_{phrase,prefix,exact,in,regexp,and,or,not,noop}.go, lib/logstorage/in_values.go
+//   and, ahead of the product: filter_{exact_prefix,sequence,contains_all,contains_any,len_range,string_range,
+//   ipv4_range,any_case_phrase,any_case_prefix,value_type}.go
 #pragma once
 #include "vlo_util.h"
 #include "vlo_regex.h"
