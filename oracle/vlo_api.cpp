@@ -201,6 +201,7 @@ void* vlo_filter_contains_any(const void* f, uint64_t fl, const uint8_t* blob, c
 void* vlo_filter_any_case_phrase(const void* f, uint64_t fl, const void* p, uint64_t pl) { return new FilterHandle{std::make_shared<FilterAnyCasePhrase>(sv((const char*)f, fl), sv((const char*)p, pl))}; }
 void* vlo_filter_any_case_prefix(const void* f, uint64_t fl, const void* p, uint64_t pl) { return new FilterHandle{std::make_shared<FilterAnyCasePrefix>(sv((const char*)f, fl), sv((const char*)p, pl))}; }
 void* vlo_filter_value_type(const void* f, uint64_t fl, const void* p, uint64_t pl) { return new FilterHandle{std::make_shared<FilterValueType>(sv((const char*)f, fl), sv((const char*)p, pl))}; }
+void* vlo_filter_eq_field(const void* f, uint64_t fl, const void* p, uint64_t pl) { return new FilterHandle{std::make_shared<FilterEqField>(sv((const char*)f, fl), sv((const char*)p, pl))}; }
 void* vlo_filter_len_range(const void* f, uint64_t fl, uint64_t mn, uint64_t mx) { return new FilterHandle{std::make_shared<FilterLenRange>(sv((const char*)f, fl), mn, mx)}; }
 void* vlo_filter_string_range(const void* f, uint64_t fl, const void* a, uint64_t al, const void* b, uint64_t bl) {
     return new FilterHandle{std::make_shared<FilterStringRange>(sv((const char*)f, fl), sv((const char*)a, al), sv((const char*)b, bl))};

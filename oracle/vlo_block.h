@@ -373,7 +373,7 @@ inline std::string encoded_to_string(uint8_t vt, sv v) {
 struct FieldTokens { std::string field; std::vector<std::string> tokens; std::vector<uint64_t> hashes; };
 
 enum FilterKind { F_NOOP, F_PHRASE, F_PREFIX, F_EXACT, F_IN, F_REGEXP, F_AND, F_OR, F_NOT, F_EXACT_PREFIX, F_SEQUENCE, F_LEN_RANGE, F_STRING_RANGE, F_IPV4_RANGE, F_CONTAINS_ALL, F_CONTAINS_ANY,
-                  F_ANY_CASE_PHRASE, F_ANY_CASE_PREFIX, F_VALUE_TYPE };
+                  F_ANY_CASE_PHRASE, F_ANY_CASE_PREFIX, F_VALUE_TYPE, F_EQ_FIELD };
 
 struct Filter {
     FilterKind kind;
@@ -979,6 +979,39 @@ struct FilterValueType : Filter {   // filter_value_type.go:12-67; names: valueT
         const Column* ch = bs.column(field);
         if (!ch) { bm.reset_bits(); return; }
         if (typ != name_of(ch->valueType)) bm.reset_bits();
+    }
+};
+
+// the string value of `field` in row idx, as blockResult.getValues would yield it: const value, "" for a missing field, dict entry, or
+// the text form of a typed value
+inline std::string row_string(BlockSearch& bs, sv field, uint64_t idx) {
+    sv v = bs.const_value(field);
+    if (!v.empty()) return std::string(v);
+    const Column* ch = bs.column(field);
+    if (!ch) return std::string();
+    sv x = bs.values(ch)[idx];
+    if (ch->valueType == VT_DICT) { if (x.size() != 1 || (uint8_t)x[0] >= ch->dict.size()) throw std::runtime_error("bad dict value"); return ch->dict[(uint8_t)x[0]]; }
+    return encoded_to_string(ch->valueType, x);
+}
+
+struct FilterEqField : Filter {   // filter_eq_field.go:14-238  (field:eq_field(other))
+    std::string field, other;
+    FilterEqField(sv f, sv o) : field(canonical(f)), other(canonical(o)) { kind = F_EQ_FIELD; }
+    void by_strings(BlockSearch& bs, Bitmap& bm) { bm.for_each_set_bit([&](uint64_t idx) { return row_string(bs, field, idx) == row_string(bs, other, idx); }); }   // applyFilterString
+    void apply(BlockSearch& bs, Bitmap& bm) override {
+        if (field == other) return;
+        sv v = bs.const_value(field), vo = bs.const_value(other);
+        if (!v.empty() || !vo.empty()) {
+            if (!v.empty() && !vo.empty()) { if (v != vo) bm.reset_bits(); return; }
+            by_strings(bs, bm); return;
+        }
+        const Column* ch = bs.column(field); const Column* co = bs.column(other);
+        if (!ch || !co) { if (!ch && !co) return; by_strings(bs, bm); return; }
+        if (ch->valueType != co->valueType || ch->valueType == VT_STRING) { by_strings(bs, bm); return; }
+        if (bm.is_zero()) return;
+        const auto& a = bs.values(ch); const auto& b = bs.values(co);
+        if (ch->valueType == VT_DICT) bm.for_each_set_bit([&](uint64_t idx) { return ch->dict.at((uint8_t)a[idx][0]) == co->dict.at((uint8_t)b[idx][0]); });   // applyFilterDict
+        else bm.for_each_set_bit([&](uint64_t idx) { return a[idx] == b[idx]; });   // applyFilterBinValue: same type, same binary form
     }
 };
 

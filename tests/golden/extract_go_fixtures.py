@@ -261,6 +261,8 @@ def filter_spec(v):
         return {"kind": "any_case_prefix", "field": hx(field), "arg": hx(f.get("prefix", b""))}
     if kind == "filterValueType":
         return {"kind": "value_type", "field": hx(field), "arg": hx(f.get("valueType", b""))}
+    if kind == "filterEqField":
+        return {"kind": "eq_field", "field": hx(field), "arg": hx(f.get("otherFieldName", b""))}
     if kind == "filterLenRange":
         return {"kind": "len_range", "field": hx(field), "min": num("minLen"), "max": num("maxLen")}
     if kind == "filterStringRange":
@@ -272,7 +274,7 @@ def filter_spec(v):
 
 SUPPORTED = ("filterPhrase", "filterPrefix", "filterExact", "filterRegexp", "filterIn", "filterNot",
              "filterExactPrefix", "filterSequence", "filterLenRange", "filterStringRange", "filterIPv4Range", "filterContainsAll", "filterContainsAny",
-             "filterAnyCasePhrase", "filterAnyCasePrefix", "filterValueType")
+             "filterAnyCasePhrase", "filterAnyCasePrefix", "filterValueType", "filterEqField")
 
 
 def extract_filter_cases(path):
@@ -417,7 +419,7 @@ def main():
     cases = []
     for name in ("filter_exact_prefix_test.go", "filter_sequence_test.go", "filter_len_range_test.go", "filter_string_range_test.go", "filter_ipv4_range_test.go",
                  "filter_contains_all_test.go", "filter_contains_any_test.go", "filter_any_case_phrase_test.go", "filter_any_case_prefix_test.go",
-                 "filter_value_type_test.go"):
+                 "filter_value_type_test.go", "filter_eq_field_test.go"):
         c = extract_filter_cases(os.path.join(REF, name))
         print(name, len(c))
         cases.extend(c)

@@ -50,7 +50,7 @@ def build_filter(F, spec):
         return F.ipv4_range(field, spec["min"], spec["max"])
     if k == "string_range":
         return F.string_range(field, bytes.fromhex(spec["min"]), bytes.fromhex(spec["max"]))
-    if k in ("exact_prefix", "any_case_phrase", "any_case_prefix", "value_type"):
+    if k in ("exact_prefix", "any_case_phrase", "any_case_prefix", "value_type", "eq_field"):
         return getattr(F, k)(field, bytes.fromhex(spec["arg"]))
     arg = bytes.fromhex(spec["arg"])
     return {"phrase": F.phrase, "prefix": F.prefix, "exact": F.exact, "regexp": F.regexp}[k](field, arg)

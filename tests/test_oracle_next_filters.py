@@ -14,7 +14,7 @@ def test_counts():
     for c in CASES:
         kinds[c["filter"]["kind"]] = kinds.get(c["filter"]["kind"], 0) + 1
     assert kinds == {"exact_prefix": 62, "sequence": 103, "len_range": 30, "string_range": 48, "ipv4_range": 24, "contains_all": 104, "contains_any": 88,
-                     "any_case_phrase": 107, "any_case_prefix": 114, "value_type": 35}
+                     "any_case_phrase": 107, "any_case_prefix": 114, "value_type": 35, "eq_field": 78}
 
 
 @pytest.mark.parametrize("idx", range(len(CASES)))
