@@ -126,10 +126,16 @@ int vlscan_ctx_sync(vlscan_ctx* ctx);                        /* cudaStreamSynchr
  *   6 AND     (filter_and.go:15-20)       varuint(n) n x node
  *   7 OR      (filter_or.go:36-41)        varuint(n) n x node
  *   8 NOT     (filter_not.go:11-13)       node
+ *   9 EXACT_PREFIX (filter_exact_prefix.go:13-20)   bytes(fieldName) bytes(prefix)                         `f:="abc"*`
+ *  10 LEN_RANGE    (filter_len_range.go:14-22)      bytes(fieldName) varuint(minLen) varuint(maxLen)        `f:len_range(a, b)`
+ *  11 STRING_RANGE (filter_string_range.go:12-20)   bytes(fieldName) bytes(minValue) bytes(maxValue)        `f:string_range(a, b)`, [min, max)
+ *  12 IPV4_RANGE   (filter_ipv4_range.go:12-20)     bytes(fieldName) varuint(minValue) varuint(maxValue)    `f:ipv4_range(a, b)`, inclusive
+ *  13 VALUE_TYPE   (filter_value_type.go:12-15)     bytes(fieldName) bytes(type name)                       `f:value_type(uint8)`
  * Token hashes, merged AND/OR per-field tokens, typed needles and regex automata are derived here, like the
  * sync.Once initialisers of the Go filters do on first use.  Returns <0 with an error text for malformed trees,
  * regexps that do not compile and regexps outside the supported syntax. */
-enum { VLSCAN_F_NOOP = 0, VLSCAN_F_PHRASE, VLSCAN_F_PREFIX, VLSCAN_F_EXACT, VLSCAN_F_IN, VLSCAN_F_REGEXP, VLSCAN_F_AND, VLSCAN_F_OR, VLSCAN_F_NOT };
+enum { VLSCAN_F_NOOP = 0, VLSCAN_F_PHRASE, VLSCAN_F_PREFIX, VLSCAN_F_EXACT, VLSCAN_F_IN, VLSCAN_F_REGEXP, VLSCAN_F_AND, VLSCAN_F_OR, VLSCAN_F_NOT,
+       VLSCAN_F_EXACT_PREFIX = 9, VLSCAN_F_LEN_RANGE = 10, VLSCAN_F_STRING_RANGE = 11, VLSCAN_F_IPV4_RANGE = 12, VLSCAN_F_VALUE_TYPE = 13 };
 int vlscan_program_create(const void* tree, size_t tree_len, vlscan_program** out);
 void vlscan_program_free(vlscan_program* prog);
 /* canonical names of the fields the tree references (so the caller lists only those columns per block) */
@@ -141,6 +147,11 @@ int64_t vlscan_program_leaf_tokens(const vlscan_program* prog, uint32_t leaf, ch
  * strconv.AppendFloat(f, 'f', -1, 64).  Host build of the routine the scan kernels run per row; returns the length
  * (<= 344) or -1 when cap is too small.  No NUL terminator is written. */
 int vlscan_format_float64(uint64_t ieee_bits, char* buf, size_t cap);
+/* Host build of the per-value predicate the row kernels run for filter kinds 9..12 (matchExactPrefix, matchLenRange,
+ * matchStringRange, matchIPv4Range): arg1 = prefix / minValue, arg2 = maxValue, aux0..aux1 = minLen..maxLen or the IPv4
+ * bounds.  Returns 1 / 0, or -1 for other kinds.  For tests against the oracle. */
+int vlscan_eval_predicate(int kind, const void* value, size_t value_len, const void* arg1, size_t arg1_len, const void* arg2,
+                          size_t arg2_len, uint64_t aux0, uint64_t aux1);
 
 /* ---- batches ---------------------------------------------------------------------------------------------------- */
 /* Stage `nblocks` blocks into HBM (host pointers in, pinned staging + cudaMemcpyAsync inside).  Field names are the

@@ -68,6 +68,17 @@ int vlo_bloom_contains_all_tokens(const uint8_t* bloom, uint64_t bloom_len, cons
 
 int vlo_match_phrase(const void* s, uint64_t sl, const void* p, uint64_t pl) { return match_phrase(sv((const char*)s, sl), sv((const char*)p, pl)); }
 int vlo_match_prefix(const void* s, uint64_t sl, const void* p, uint64_t pl) { return match_prefix(sv((const char*)s, sl), sv((const char*)p, pl)); }
+// single-value predicates of exact_prefix (9) / len_range (10) / string_range (11) / ipv4_range (12); kind numbers as in include/vlscan.h
+int vlo_eval_predicate(int kind, const void* s, uint64_t sl, const void* a, uint64_t al, const void* b, uint64_t bl, uint64_t aux0, uint64_t aux1) {
+    sv v((const char*)s, sl), x((const char*)a, al), y((const char*)b, bl);
+    switch (kind) {
+    case 9: return match_exact_prefix(v, x);
+    case 10: return match_len_range(v, aux0, aux1);
+    case 11: return match_string_range(v, x, y);
+    case 12: { uint32_t n; return try_parse_ipv4(v, &n) && n >= aux0 && n <= aux1; }
+    }
+    return -1;
+}
 int64_t vlo_skip_first_last_token(const void* s, uint64_t sl, char* out, uint64_t cap) {
     std::string r = skip_first_last_token(sv((const char*)s, sl));
     if (r.size() > cap) return -1;

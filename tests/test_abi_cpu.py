@@ -45,6 +45,73 @@ def test_program_tokens_match_oracle(oracle):
     assert seen > 250
 
 
+PRODUCT_NEXT_KINDS = ("exact_prefix", "len_range", "string_range", "ipv4_range", "value_type")
+
+
+def test_next_filter_kinds_compile_and_tokens(oracle):
+    """The filters of SURVEY §8(f) rank 3 that libvlscan compiles so far: every reference-table filter builds; exact_prefix tokens
+    (getTokensSkipLast) equal the oracle's; the kinds not built yet are rejected, not guessed."""
+    seen = {}
+    for c in load_filter_cases("filter_cases_next.json"):
+        spec = c["filter"]
+        k = spec["kind"]
+        if k not in PRODUCT_NEXT_KINDS:
+            continue
+        p = vs.Program(build_filter(vs.Filter, spec))
+        assert p.fields() == [bytes.fromhex(spec["field"]) or b"_msg"]
+        if k == "exact_prefix":
+            assert p.leaf_tokens(0) == build_filter(oracle.Filter, spec).tokens(), spec
+        else:
+            assert p.leaf_tokens(0) == []
+        seen[k] = seen.get(k, 0) + 1
+    assert seen == {"exact_prefix": 62, "len_range": 30, "string_range": 48, "ipv4_range": 24, "value_type": 35}
+    with pytest.raises(vs.VlscanError):
+        vs.Program(vs.Filter(bytes([vs.F_IPV4_RANGE, 1, ord("f")]) + bytes([0x80, 0x80, 0x80, 0x80, 0x10, 0]), "ipv4 bound > 32 bits"))
+    for kind in (14, 15, 16, 17, 18, 19):
+        with pytest.raises(vs.VlscanError):
+            vs.Program(vs.Filter(bytes([kind, 1, ord("f"), 1, ord("x")]), "kind not built yet"))
+    # AND: exact_prefix contributes its tokens to the per-field bloom pre-pass (filter_and.go:141-143)
+    vs.Program(vs.Filter.and_([vs.Filter.exact_prefix("m", "foo bar"), vs.Filter.len_range("m", 1, 5), vs.Filter.not_(vs.Filter.value_type("m", "dict"))]))
+
+
+def test_value_predicates_match_oracle(oracle):
+    """vl::range_predicate - the function the row kernels call for kinds 9..12, here in its host build - against the oracle's
+    matchExactPrefix / matchLenRange / matchStringRange / matchIPv4Range on seeded random values (ASCII, UTF-8, invalid bytes,
+    IPv4-looking strings incl. the two-character quirk of tryParseDateUint64)."""
+    import random
+    rng = random.Random(20250923)
+    O = oracle.lib()
+    O.vlo_eval_predicate.argtypes = [C.c_int, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint64]
+
+    def rnd_string():
+        kind = rng.randrange(6)
+        if kind == 0:
+            return bytes(rng.choice(b"ab 01.-") for _ in range(rng.randrange(0, 8)))
+        if kind == 1:
+            return "".join(rng.choice("aйц日🙂é ") for _ in range(rng.randrange(0, 6))).encode()
+        if kind == 2:
+            return bytes(rng.getrandbits(8) for _ in range(rng.randrange(0, 7)))
+        if kind == 3:
+            return b".".join(b"%d" % rng.choice([0, 1, 7, 10, 99, 127, 255, 256, 300]) for _ in range(rng.choice([3, 4, 4, 4, 5])))
+        if kind == 4:
+            return b".".join(bytes(rng.choice(b"0123456789:/a") for _ in range(rng.randrange(0, 4))) for _ in range(4))
+        return b"%d" % rng.randrange(-10**6, 10**12)
+
+    n = 0
+    for _ in range(20000):
+        s, a, b = rnd_string(), rnd_string(), rnd_string()
+        lo, hi = sorted([rng.randrange(0, 9), rng.randrange(0, 9)])
+        ip_lo, ip_hi = sorted([rng.getrandbits(32), rng.getrandbits(32)])
+        for kind, a1, a2, x0, x1 in ((9, a, b"", 0, 0), (10, b"", b"", lo, hi), (11, a, b, 0, 0), (12, b"", b"", ip_lo, ip_hi), (12, b"", b"", 0, 0xFFFFFFFF)):
+            want = O.vlo_eval_predicate(kind, s, len(s), a1, len(a1), a2, len(a2), x0, x1)
+            assert want in (0, 1)
+            assert vs.eval_predicate(kind, s, a1, a2, x0, x1) == bool(want), (kind, s, a1, a2, x0, x1)
+            n += want
+    assert n > 5000   # the sample is not vacuous
+    with pytest.raises(ValueError):
+        vs.eval_predicate(1, b"x")
+
+
 def test_program_fields_and_errors():
     p = vs.Program(vs.Filter.and_([vs.Filter.phrase("", "GET"), vs.Filter.prefix("path", "api"), vs.Filter.in_("status", ["500", "502", "503"])]))
     assert p.fields() == [b"_msg", b"path", b"status"]

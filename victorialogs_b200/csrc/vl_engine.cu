@@ -639,6 +639,11 @@ int64_t vlscan_program_leaf_tokens(const vlscan_program* prog, uint32_t leaf, ch
     return (int64_t)s.size();
 }
 
+int vlscan_eval_predicate(int kind, const void* value, size_t value_len, const void* arg1, size_t arg1_len, const void* arg2, size_t arg2_len, uint64_t aux0, uint64_t aux1) {
+    if (kind < F_EXACT_PREFIX || kind > F_IPV4_RANGE || value_len > 0xFFFFFFFFull || arg1_len > 0xFFFFFFFFull || arg2_len > 0xFFFFFFFFull) return -1;
+    return vl::range_predicate(kind, (const uint8_t*)value, (uint32_t)value_len, (const uint8_t*)arg1, (uint32_t)arg1_len, (const uint8_t*)arg2, (uint32_t)arg2_len, aux0, aux1) ? 1 : 0;
+}
+
 int vlscan_format_float64(uint64_t ieee_bits, char* buf, size_t cap) {
     uint8_t tmp[VL_FMT_F64_MAX];
     int n = vl::fmt_f64(tmp, ieee_bits);

@@ -250,6 +250,54 @@ VL_HDN int fmt_iso8601(uint8_t* buf, int64_t nsecs) {
     return 24;
 }
 
+// ---- predicates of the range / length filters ------------------------------------------------------------------------------------------
+// utf8.RuneCountInString (matchLenRange, filter_len_range.go:333-336): every invalid byte counts as one rune
+VL_HDN uint64_t rune_count(const uint8_t* s, uint32_t n) {
+    uint64_t c = 0;
+    for (uint32_t i = 0; i < n;) { if (s[i] < 0x80) { i++; c++; continue; } int w; decode_rune(s + i, n - i, &w); i += (uint32_t)w; c++; }
+    return c;
+}
+// Go string comparison: bytewise, the shorter string first on a tie (-1, 0, 1)
+VL_HDN int bytes_cmp(const uint8_t* a, uint32_t n, const uint8_t* b, uint32_t m) {
+    uint32_t k = n < m ? n : m;
+    for (uint32_t i = 0; i < k; i++) if (a[i] != b[i]) return a[i] < b[i] ? -1 : 1;
+    return n == m ? 0 : n < m ? -1 : 1;
+}
+// tryParseIPv4 (values_encoder.go:675-730) over tryParseDateUint64 (:588-619), whose two-character fast path checks the first digit only
+VL_HDN bool parse_date_u64_hd(const uint8_t* s, uint32_t n, uint64_t* out) {
+    if (n == 0 || n > 9) return false;
+    if (n == 2) { if (s[0] < '0' || s[0] > '9') return false; *out = 10ull * (uint8_t)(s[0] - '0') + (uint8_t)(s[1] - (uint8_t)'0'); return true; }
+    uint64_t v = 0;
+    for (uint32_t i = 0; i < n; i++) { if (s[i] < '0' || s[i] > '9') return false; v = v * 10 + (uint64_t)(s[i] - '0'); }
+    *out = v; return true;
+}
+VL_HDN bool parse_ipv4_hd(const uint8_t* s, uint32_t n, uint32_t* out) {
+    if (n < 7 || n > 15) return false;
+    uint32_t dots = 0; for (uint32_t i = 0; i < n; i++) dots += s[i] == '.';
+    if (dots != 3) return false;
+    uint32_t ip = 0, pos = 0;
+    for (int k = 0; k < 4; k++) {
+        uint32_t e = pos;
+        if (k < 3) { while (s[e] != '.') e++; if (e == pos || e - pos > 3) return false; } else e = n;
+        uint64_t v;
+        if (!parse_date_u64_hd(s + pos, e - pos, &v) || v > 255) return false;
+        ip = (ip << 8) | (uint32_t)v;
+        pos = e + 1;
+    }
+    *out = ip; return true;
+}
+
+// the per-value predicate of the filter kinds 9..12 (include/vlscan.h); a = needle, b = second needle (string_range: maxValue)
+VL_HDN bool range_predicate(int kind, const uint8_t* s, uint32_t n, const uint8_t* a, uint32_t an, const uint8_t* b, uint32_t bn, uint64_t aux0, uint64_t aux1) {
+    switch (kind) {
+    case 9: return n >= an && bytes_equal(s, an, a, an);                                   // matchExactPrefix filter_exact_prefix.go:275-277
+    case 10: { uint64_t c = rune_count(s, n); return c >= aux0 && c <= aux1; }             // matchLenRange filter_len_range.go:333-336
+    case 11: return bytes_cmp(s, n, a, an) >= 0 && bytes_cmp(s, n, b, bn) < 0;             // matchStringRange filter_string_range.go:226-230
+    case 12: { uint32_t ip; return parse_ipv4_hd(s, n, &ip) && ip >= aux0 && ip <= aux1; }  // matchIPv4Range filter_ipv4_range.go:167-173
+    }
+    return false;
+}
+
 // ---- float64 -> shortest decimal text: strconv.AppendFloat(dst, f, 'f', -1, 64) (marshalFloat64String, values_encoder.go:1397-1399) ----
 // Shortest digits that round-trip (Ryu, Adams 2018: the same digit string Go's shortest formatter produces), printed in fixed notation
 // without exponent.  Tables generated by tools/gen_ryu_tables.py.  Returns the length (<= 344 bytes incl. sign).

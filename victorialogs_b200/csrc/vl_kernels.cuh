@@ -123,6 +123,9 @@ static __device__ bool leaf_match_string(const DevProgram& P, const DevLeaf& L, 
     case F_EXACT: return bytes_equal(s, n, nd, L.needle_len);
     case F_IN: return in_contains_string(L, P.blob, s, n);
     case F_REGEXP: return regex_match(P.regexes[L.regex], P.blob, s, n);
+    case F_EXACT_PREFIX: case F_LEN_RANGE: case F_STRING_RANGE: case F_IPV4_RANGE:   // matchExactPrefix / matchLenRange / matchStringRange / matchIPv4Range
+        return range_predicate(L.kind, s, n, nd, L.needle_len, P.blob + L.needle2_off, L.needle2_len, L.aux0, L.aux1);
+    case F_VALUE_TYPE: return false;   // decided from the column header alone (k_plan_leaf)
     }
     return true;
 }
@@ -238,16 +241,22 @@ static __global__ void k_plan_leaf(DevProgram P, BatchView B, uint32_t leaf_idx,
     uint32_t rows = B.blk_rows[b];
     const DevColumn* c = slot >= 0 ? &B.cols[(uint64_t)b * B.nfields + slot] : nullptr;
     const uint8_t* nd = P.blob + L.needle_off; uint32_t nl = L.needle_len;
-    if (L.kind == F_IN && L.in_count == 0) act = ACT_NONE;   // fi.values.isEmpty()
+    if ((L.kind == F_IN && L.in_count == 0) || L.always_none) act = ACT_NONE;   // fi.values.isEmpty(); minLen > maxLen, minValue > maxValue
     else if (c && c->kind == COL_CONST) {
-        act = leaf_match_string(P, L, B.arena + c->meta_off, c->meta_len) ? ACT_ALL : ACT_NONE;
+        if (L.kind == F_VALUE_TYPE) act = L.aux0 == VTYPE_CONST ? ACT_ALL : ACT_NONE;   // filter_value_type.go:46-52
+        else act = leaf_match_string(P, L, B.arena + c->meta_off, c->meta_len) ? ACT_ALL : ACT_NONE;
     } else if (!c || c->kind == COL_MISSING) {
         switch (L.kind) {
-        case F_PHRASE: case F_EXACT: act = nl == 0 ? ACT_ALL : ACT_NONE; break;
+        case F_PHRASE: case F_EXACT: case F_EXACT_PREFIX: act = nl == 0 ? ACT_ALL : ACT_NONE; break;
         case F_PREFIX: act = ACT_NONE; break;
         case F_IN: act = L.in_has_empty ? ACT_ALL : ACT_NONE; break;
         case F_REGEXP: act = regex_match(P.regexes[L.regex], P.blob, nullptr, 0) ? ACT_ALL : ACT_NONE; break;
+        case F_LEN_RANGE: act = L.aux0 == 0 ? ACT_ALL : ACT_NONE; break;                                // matchLenRange("", min, max)
+        case F_STRING_RANGE: act = (nl == 0 && L.needle2_len > 0) ? ACT_ALL : ACT_NONE; break;           // "" >= min && "" < max
+        case F_IPV4_RANGE: case F_VALUE_TYPE: act = ACT_NONE; break;
         }
+    } else if (L.kind == F_VALUE_TYPE) {
+        act = L.aux0 == c->vt ? ACT_ALL : ACT_NONE;   // valueType.String() == wanted name (filter_value_type.go:59-66); no payload is read
     } else if (c->vt == VT_DICT) {
         const uint32_t* dof = (const uint32_t*)(B.arena + c->meta_off);
         const uint8_t* dv = B.arena + c->meta_off + 4 * (c->dict_len + 1);
@@ -332,6 +341,46 @@ static __global__ void k_plan_leaf(DevProgram P, BatchView B, uint32_t leaf_idx,
                     }
                     act = !ok ? ACT_NONE : fixed_ok ? ACT_FIXED_IN : ACT_ROW;
                 }
+                break;
+            case F_EXACT_PREFIX: {   // match*ByExactPrefix filter_exact_prefix.go:105-273
+                const bool is_uint = vt == VT_UINT8 || vt == VT_UINT16 || vt == VT_UINT32 || vt == VT_UINT64;
+                if (nl == 0) act = ACT_ALL;
+                else if (is_uint) act = (L.nhashes > 0 || !tn.ok || tn.val > c->max_value) ? ACT_NONE : ACT_ROW;   // matchMinMaxExactPrefix
+                else if (vt == VT_INT64) {
+                    bool dash = nl == 1 && nd[0] == '-';
+                    if (L.nhashes > 0) act = ACT_NONE;
+                    else if (!dash && (!tn.ok || tn.sval > (int64_t)c->max_value || tn.sval < (int64_t)c->min_value)) act = ACT_NONE;
+                    else act = ACT_ROW;
+                }
+                else if (vt == VT_FLOAT64) act = (L.nhashes > 2 * 6 || !probe(H, L.nhashes)) ? ACT_NONE : ACT_ROW;
+                else if (vt == VT_IPV4) act = (!(L.gates & GATE_DIGIT_PREFIX) || L.nhashes > 3 * 6 || !probe(H, L.nhashes)) ? ACT_NONE : ACT_ROW;
+                else act = (!(L.gates & GATE_DIGIT_PREFIX) || !probe(H, L.nhashes)) ? ACT_NONE : ACT_ROW;   // iso8601
+                break;
+            }
+            case F_LEN_RANGE: {      // match*ByLenRange filter_len_range.go:209-348
+                const uint64_t mn = L.aux0, mx = L.aux1;
+                uint8_t tmp[24];
+                if (vt == VT_UINT8 || vt == VT_UINT16 || vt == VT_UINT32 || vt == VT_UINT64) {
+                    const uint64_t maxd = vt == VT_UINT8 ? 3 : vt == VT_UINT16 ? 5 : vt == VT_UINT32 ? 10 : 20;
+                    if (mn > maxd || mx == 0) act = ACT_NONE;
+                    else if (mx < (uint64_t)fmt_u64(tmp, c->min_value) || mn > (uint64_t)fmt_u64(tmp, c->max_value)) act = ACT_NONE;   // matchMinMaxValueLen
+                    else act = ACT_ROW;
+                } else if (vt == VT_INT64) {
+                    if (mn > 21 || mx == 0) act = ACT_NONE;
+                    else { int a = fmt_i64(tmp, (int64_t)c->min_value), b2 = fmt_i64(tmp, (int64_t)c->max_value); act = (uint64_t)(a > b2 ? a : b2) < mn ? ACT_NONE : ACT_ROW; }
+                } else if (vt == VT_FLOAT64) act = (mn > 24 || mx == 0) ? ACT_NONE : ACT_ROW;
+                else if (vt == VT_IPV4) act = (mn > 15 || mx < 7) ? ACT_NONE : ACT_ROW;
+                else act = (mn > 24 || mx < 24) ? ACT_NONE : ACT_ALL;   // iso8601: every value is 24 characters long, nothing is read
+                break;
+            }
+            case F_STRING_RANGE:     // match*ByStringRange filter_string_range.go:88-224
+                if (vt == VT_INT64) act = (L.gates & GATE_SR_INT) ? ACT_ROW : ACT_NONE;
+                else if (vt == VT_FLOAT64) act = (L.gates & GATE_SR_FLOAT) ? ACT_ROW : ACT_NONE;
+                else act = (L.gates & GATE_SR_UINT) ? ACT_ROW : ACT_NONE;
+                break;
+            case F_IPV4_RANGE:       // filter_ipv4_range.go:113-131, matchIPv4ByRange :176-191
+                if (vt != VT_IPV4) act = ACT_NONE;
+                else act = (c->min_value > L.aux1 || c->max_value < L.aux0) ? ACT_NONE : ACT_ROW;
                 break;
             }
         }
@@ -903,6 +952,7 @@ static __global__ void k_row_match(DevProgram P, BatchView B, uint32_t leaf_idx,
         if (len != w) return false;
         uint64_t raw = load_fixed_be(s, w);
         if (L.kind == F_IN) return in_contains_typed(L, P.u64s, vt, raw);
+        if (L.kind == F_IPV4_RANGE) return raw >= L.aux0 && raw <= L.aux1;   // only ipv4 columns get here (k_plan_leaf)
         if (L.kind == F_EXACT) return raw == payload[b];
         if (L.kind == F_PHRASE && L.typed[vt].ok && !(vt == VT_FLOAT64 && !L.f64_exact_form)) return raw == payload[b];
         if (vt == VT_FLOAT64) return leaf_match_f64(P, L, raw);

@@ -285,6 +285,47 @@ class ProgramBuilder {
             regex_strategy(P.leaves[l], P.regexes.back());
             P.nodes[id].leaf = l; break;
         }
+        case F_EXACT_PREFIX: {   // filter_exact_prefix.go:13-54: tokens = getTokensSkipLast(prefix)
+            std::string f = bytes(), s = bytes();
+            int l = new_leaf(kind, f, s, host_tokenize({host_strip_last_token(s)}));
+            DevLeaf& L = P.leaves[l]; typed_needles(L, s);
+            if (!(s < "0" || s > "9")) L.gates |= GATE_DIGIT_PREFIX;
+            P.nodes[id].leaf = l; break;
+        }
+        case F_LEN_RANGE: {      // filter_len_range.go:14-22
+            std::string f = bytes(); uint64_t mn = varuint(), mx = varuint();
+            int l = new_leaf(kind, f, "", {});
+            DevLeaf& L = P.leaves[l]; L.aux0 = mn; L.aux1 = mx; L.always_none = mn > mx;
+            P.nodes[id].leaf = l; break;
+        }
+        case F_STRING_RANGE: {   // filter_string_range.go:12-20; the per-type gates of :88-224 depend on the arguments only
+            std::string f = bytes(), a = bytes(), b = bytes();
+            int l = new_leaf(kind, f, a, {});
+            uint32_t off2 = P.put_bytes(b.data(), b.size());
+            DevLeaf& L = P.leaves[l]; L.needle2_off = off2; L.needle2_len = (uint32_t)b.size();
+            L.always_none = a > b;
+            if (!(a > "9" || b < "0")) L.gates |= GATE_SR_UINT;
+            if (!((a != "-" && a > "9") || (b != "-" && b < "0"))) L.gates |= GATE_SR_INT;
+            if (!(a > "9" || b < "+")) L.gates |= GATE_SR_FLOAT;
+            P.nodes[id].leaf = l; break;
+        }
+        case F_IPV4_RANGE: {     // filter_ipv4_range.go:12-20
+            std::string f = bytes(); uint64_t mn = varuint(), mx = varuint();
+            if (mn > 0xFFFFFFFFull || mx > 0xFFFFFFFFull) throw ProgError("ipv4_range bounds do not fit 32 bits");
+            int l = new_leaf(kind, f, "", {});
+            DevLeaf& L = P.leaves[l]; L.aux0 = mn; L.aux1 = mx; L.always_none = mn > mx;
+            P.nodes[id].leaf = l; break;
+        }
+        case F_VALUE_TYPE: {     // filter_value_type.go:12-15; names: valueType.String() values_encoder.go:62-89
+            std::string f = bytes(), t = bytes();
+            int l = new_leaf(kind, f, t, {});
+            static const std::pair<const char*, int> names[] = {{"const", VTYPE_CONST}, {"string", VT_STRING}, {"dict", VT_DICT}, {"uint8", VT_UINT8}, {"uint16", VT_UINT16},
+                {"uint32", VT_UINT32}, {"uint64", VT_UINT64}, {"int64", VT_INT64}, {"float64", VT_FLOAT64}, {"ipv4", VT_IPV4}, {"iso8601", VT_ISO8601}};
+            uint64_t code = VTYPE_NO_SUCH;
+            for (auto& nm : names) if (t == nm.first) code = (uint64_t)nm.second;
+            P.leaves[l].aux0 = code;
+            P.nodes[id].leaf = l; break;
+        }
         case F_AND: case F_OR: { uint64_t c = varuint(); if (c > 100000) throw ProgError("too many children"); for (uint64_t k = 0; k < c; k++) { int ch = node(); P.nodes[id].kids.push_back(ch); } break; }
         case F_NOT: { int ch = node(); P.nodes[id].kids.push_back(ch); break; }
         default: throw ProgError("unknown filter kind " + std::to_string(kind));
@@ -353,7 +394,7 @@ class ProgramBuilder {
         P.leaf_tokens.back() = common;
     }
     // ---- AND / OR bloom pre-pass token merging -------------------------------------------------------------------------
-    bool leaf_has_tokens(int kind) const { return kind == F_PHRASE || kind == F_PREFIX || kind == F_EXACT || kind == F_REGEXP; }
+    bool leaf_has_tokens(int kind) const { return kind == F_PHRASE || kind == F_PREFIX || kind == F_EXACT || kind == F_REGEXP || kind == F_EXACT_PREFIX; }
     const std::vector<FT>& by_field(int id) {
         if (node_ft_done_[id]) return node_ft_[id];
         node_ft_done_[id] = true;

@@ -5,7 +5,9 @@
 namespace vl {
 
 enum { VT_STRING = 1, VT_DICT = 2, VT_UINT8 = 3, VT_UINT16 = 4, VT_UINT32 = 5, VT_UINT64 = 6, VT_FLOAT64 = 7, VT_IPV4 = 8, VT_ISO8601 = 9, VT_INT64 = 10, VT_MAX = 11 };
-enum { F_NOOP = 0, F_PHRASE, F_PREFIX, F_EXACT, F_IN, F_REGEXP, F_AND, F_OR, F_NOT };
+enum { F_NOOP = 0, F_PHRASE, F_PREFIX, F_EXACT, F_IN, F_REGEXP, F_AND, F_OR, F_NOT,
+       F_EXACT_PREFIX = 9, F_LEN_RANGE = 10, F_STRING_RANGE = 11, F_IPV4_RANGE = 12, F_VALUE_TYPE = 13 };
+enum { VTYPE_CONST = 0, VTYPE_NO_SUCH = 255 };   // F_VALUE_TYPE: DevLeaf.aux0 = VT_* code of the wanted type, or one of these
 enum { COL_MISSING = 0, COL_CONST = 1, COL_VALUES = 2 };
 
 // One (block, field) cell of a resident batch: the columnHeader fields the scan needs + arena offsets of the payloads
@@ -70,9 +72,18 @@ struct DevLeaf {
     // strategy for plain string columns, decided once per leaf on the host:
     uint8_t str_strategy;              // STR_ROW: per-row matcher, STR_SCAN: row-agnostic substring scan, STR_ALL: every row matches
     uint8_t scan_mode;                 // SCAN_* verifier of the substring scan
-    uint8_t pad[2];
+    uint8_t always_none;               // the filter's own arguments exclude every row (minLen > maxLen, minValue > maxValue)
+    uint8_t gates;                     // header-level gates decided on the host from the arguments alone (GATE_* bits)
     uint32_t scan_needle_off, scan_needle_len;   // blob: the literal the scan searches for
+    // exact_prefix / len_range / string_range / ipv4_range / value_type
+    uint64_t aux0, aux1;               // len_range: minLen, maxLen; ipv4_range: minValue, maxValue; value_type: wanted type code
+    uint32_t needle2_off, needle2_len; // string_range: maxValue (needle = minValue)
 };
+// DevLeaf.gates
+enum { GATE_DIGIT_PREFIX = 1,          // exact_prefix: !(prefix < "0" || prefix > "9")
+       GATE_SR_UINT = 2,               // string_range on uint / ipv4 / iso8601 text: !(min > "9" || max < "0")
+       GATE_SR_INT = 4,                // string_range on int64 text (filter_string_range.go:213-217)
+       GATE_SR_FLOAT = 8 };            // string_range on float64 text: !(min > "9" || max < "+")
 
 struct DevPrepass {                    // one fieldTokens entry of an AND / OR node (filter_and.go:21-25)
     int32_t field;

@@ -23,6 +23,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 F_NOOP, F_PHRASE, F_PREFIX, F_EXACT, F_IN, F_REGEXP, F_AND, F_OR, F_NOT = range(9)
+F_EXACT_PREFIX, F_LEN_RANGE, F_STRING_RANGE, F_IPV4_RANGE, F_VALUE_TYPE = 9, 10, 11, 12, 13
 VT_STRING, VT_DICT, VT_UINT8, VT_UINT16, VT_UINT32, VT_UINT64, VT_FLOAT64, VT_IPV4, VT_ISO8601, VT_INT64 = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
 COL_CONST, COL_VALUES = 1, 2
 STAGE_ONDISK, STAGE_DECODED = 0, 1
@@ -64,7 +65,7 @@ class GenConfig(C.Structure):
 
 
 EXPORTS = ["vlscan_device_count", "vlscan_ctx_create", "vlscan_ctx_free", "vlscan_last_error", "vlscan_ctx_stream", "vlscan_ctx_sync",
-           "vlscan_program_create", "vlscan_program_free", "vlscan_program_nfields", "vlscan_program_field", "vlscan_program_leaf_tokens", "vlscan_format_float64",
+           "vlscan_program_create", "vlscan_program_free", "vlscan_program_nfields", "vlscan_program_field", "vlscan_program_leaf_tokens", "vlscan_format_float64", "vlscan_eval_predicate",
            "vlscan_batch_upload", "vlscan_batch_free", "vlscan_batch_nblocks", "vlscan_batch_rows", "vlscan_batch_words", "vlscan_batch_device_bytes",
            "vlscan_batch_generate", "vlscan_batch_download", "vlscan_host_blocks_get", "vlscan_host_blocks_field", "vlscan_host_blocks_bytes",
            "vlscan_host_blocks_free", "vlscan_host_blocks_compress", "vlscan_zstd_decompress", "vlscan_scan_resident", "vlscan_last_scan_stats", "vlscan_fetch_results", "vlscan_fetch_hits", "vlscan_result_device_ptrs", "vlscan_scan_batch"]
@@ -100,6 +101,17 @@ def lib():
         L.vlscan_format_float64.restype = C.c_int
         _LIB = L
     return _LIB
+
+
+def eval_predicate(kind, value, arg1=b"", arg2=b"", aux0=0, aux1=0):
+    """Host build of the per-value predicate of filter kinds 9..12 (vlscan_eval_predicate)."""
+    value, arg1, arg2 = _b(value), _b(arg1), _b(arg2)
+    L = lib()
+    L.vlscan_eval_predicate.argtypes = [C.c_int, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_uint64, C.c_uint64]
+    r = L.vlscan_eval_predicate(kind, value, len(value), arg1, len(arg1), arg2, len(arg2), aux0, aux1)
+    if r < 0:
+        raise ValueError(kind)
+    return bool(r)
 
 
 def format_float64(bits):
@@ -167,6 +179,26 @@ class Filter:
     @staticmethod
     def regexp(field, expr):
         return Filter(bytes([F_REGEXP]) + _bytes(field) + _bytes(expr), "%r:~%r" % (field, expr))
+
+    @staticmethod
+    def exact_prefix(field, prefix):       # &filterExactPrefix{fieldName, prefix}
+        return Filter(bytes([F_EXACT_PREFIX]) + _bytes(field) + _bytes(prefix), "%r:=%r*" % (field, prefix))
+
+    @staticmethod
+    def len_range(field, min_len, max_len):   # &filterLenRange{fieldName, minLen, maxLen}
+        return Filter(bytes([F_LEN_RANGE]) + _bytes(field) + _varuint(min_len) + _varuint(max_len), "%r:len_range(%d, %d)" % (field, min_len, max_len))
+
+    @staticmethod
+    def string_range(field, min_value, max_value):   # &filterStringRange{fieldName, minValue, maxValue}
+        return Filter(bytes([F_STRING_RANGE]) + _bytes(field) + _bytes(min_value) + _bytes(max_value), "%r:string_range(%r, %r)" % (field, min_value, max_value))
+
+    @staticmethod
+    def ipv4_range(field, min_value, max_value):     # &filterIPv4Range{fieldName, minValue, maxValue}
+        return Filter(bytes([F_IPV4_RANGE]) + _bytes(field) + _varuint(min_value) + _varuint(max_value), "%r:ipv4_range(%#x, %#x)" % (field, min_value, max_value))
+
+    @staticmethod
+    def value_type(field, type_name):      # &filterValueType{fieldName, valueType}
+        return Filter(bytes([F_VALUE_TYPE]) + _bytes(field) + _bytes(type_name), "%r:value_type(%r)" % (field, type_name))
 
     @staticmethod
     def and_(filters):
