@@ -213,6 +213,11 @@ void* vlo_filter_any_case_phrase(const void* f, uint64_t fl, const void* p, uint
 void* vlo_filter_any_case_prefix(const void* f, uint64_t fl, const void* p, uint64_t pl) { return new FilterHandle{std::make_shared<FilterAnyCasePrefix>(sv((const char*)f, fl), sv((const char*)p, pl))}; }
 void* vlo_filter_value_type(const void* f, uint64_t fl, const void* p, uint64_t pl) { return new FilterHandle{std::make_shared<FilterValueType>(sv((const char*)f, fl), sv((const char*)p, pl))}; }
 void* vlo_filter_eq_field(const void* f, uint64_t fl, const void* p, uint64_t pl) { return new FilterHandle{std::make_shared<FilterEqField>(sv((const char*)f, fl), sv((const char*)p, pl))}; }
+void* vlo_filter_range(const void* f, uint64_t fl, double mn, double mx) { return new FilterHandle{std::make_shared<FilterRange>(sv((const char*)f, fl), mn, mx)}; }
+void* vlo_filter_le_field(const void* f, uint64_t fl, const void* p, uint64_t pl, int exclude_equal) {
+    return new FilterHandle{std::make_shared<FilterLeField>(sv((const char*)f, fl), sv((const char*)p, pl), exclude_equal != 0)};
+}
+double vlo_parse_math_number(const void* s, uint64_t n) { return parse_math_number(sv((const char*)s, n)); }
 void* vlo_filter_len_range(const void* f, uint64_t fl, uint64_t mn, uint64_t mx) { return new FilterHandle{std::make_shared<FilterLenRange>(sv((const char*)f, fl), mn, mx)}; }
 void* vlo_filter_string_range(const void* f, uint64_t fl, const void* a, uint64_t al, const void* b, uint64_t bl) {
     return new FilterHandle{std::make_shared<FilterStringRange>(sv((const char*)f, fl), sv((const char*)a, al), sv((const char*)b, bl))};

@@ -10,6 +10,7 @@
 //   ipv4_range,any_case_phrase,any_case_prefix,value_type}.go
 #pragma once
 #include "vlo_util.h"
+#include "vlo_mathnum.h"
 #include "vlo_regex.h"
 #include <functional>
 #include <map>
@@ -373,7 +374,7 @@ inline std::string encoded_to_string(uint8_t vt, sv v) {
 struct FieldTokens { std::string field; std::vector<std::string> tokens; std::vector<uint64_t> hashes; };
 
 enum FilterKind { F_NOOP, F_PHRASE, F_PREFIX, F_EXACT, F_IN, F_REGEXP, F_AND, F_OR, F_NOT, F_EXACT_PREFIX, F_SEQUENCE, F_LEN_RANGE, F_STRING_RANGE, F_IPV4_RANGE, F_CONTAINS_ALL, F_CONTAINS_ANY,
-                  F_ANY_CASE_PHRASE, F_ANY_CASE_PREFIX, F_VALUE_TYPE, F_EQ_FIELD };
+                  F_ANY_CASE_PHRASE, F_ANY_CASE_PREFIX, F_VALUE_TYPE, F_EQ_FIELD, F_RANGE, F_LE_FIELD };
 
 struct Filter {
     FilterKind kind;
@@ -1012,6 +1013,96 @@ struct FilterEqField : Filter {   // filter_eq_field.go:14-238  (field:eq_field(
         const auto& a = bs.values(ch); const auto& b = bs.values(co);
         if (ch->valueType == VT_DICT) bm.for_each_set_bit([&](uint64_t idx) { return ch->dict.at((uint8_t)a[idx][0]) == co->dict.at((uint8_t)b[idx][0]); });   // applyFilterDict
         else bm.for_each_set_bit([&](uint64_t idx) { return a[idx] == b[idx]; });   // applyFilterBinValue: same type, same binary form
+    }
+};
+
+struct FilterRange : Filter {   // filter_range.go:14-420  (f:range[a, b], f:>a, f:<=b ...)
+    std::string field; double minValue, maxValue;
+    FilterRange(sv f, double mn, double mx) : field(f), minValue(mn), maxValue(mx) { kind = F_RANGE; }
+    bool match_str(sv s) const { double f = parse_math_number(s); return f >= minValue && f <= maxValue; }   // matchRange :352-355
+    static uint64_t u64_clamp(double f) { return f < 0 ? 0 : f > 18446744073709551615.0 ? UINT64_MAX : (uint64_t)f; }   // toUint64Clamp :362-370
+    static int64_t i64_clamp(double f) { return f < -9223372036854775808.0 ? INT64_MIN : f > 9223372036854775807.0 ? INT64_MAX : (int64_t)f; }   // toInt64Clamp :377-385
+    void apply(BlockSearch& bs, Bitmap& bm) override {
+        if (minValue > maxValue) { bm.reset_bits(); return; }
+        sv v = bs.const_value(field);
+        if (!v.empty()) { if (!match_str(v)) bm.reset_bits(); return; }
+        const Column* ch = bs.column(field);
+        if (!ch) { bm.reset_bits(); return; }
+        const double mnc = std::ceil(minValue), mxf = std::floor(maxValue);
+        switch (ch->valueType) {
+        case VT_STRING: bs.visit_values(ch, bm, [&](sv x) { return match_str(x); }); break;
+        case VT_DICT: dict_lut(bs, ch, bm, [&](sv d) { return match_str(d); }); break;
+        case VT_UINT8: case VT_UINT16: case VT_UINT32: case VT_UINT64: {   // matchUintNByRange :246-313
+            uint64_t lo = u64_clamp(mnc), hi = u64_clamp(mxf);
+            if (maxValue < 0 || lo > ch->maxValue || hi < ch->minValue) { bm.reset_bits(); return; }
+            size_t w = ch->valueType == VT_UINT8 ? 1 : ch->valueType == VT_UINT16 ? 2 : ch->valueType == VT_UINT32 ? 4 : 8;
+            bs.visit_values(ch, bm, [&](sv x) {
+                if (x.size() != w) throw std::runtime_error("unexpected length for binary representation of a uint");
+                const uint8_t* p = (const uint8_t*)x.data();
+                uint64_t n = w == 1 ? p[0] : w == 2 ? get_be16(p) : w == 4 ? get_be32(p) : get_be64(p);
+                return n >= lo && n <= hi;
+            });
+            break;
+        }
+        case VT_INT64: {   // :314-330
+            int64_t lo = i64_clamp(mnc), hi = i64_clamp(mxf);
+            if (lo > (int64_t)ch->maxValue || hi < (int64_t)ch->minValue) { bm.reset_bits(); return; }
+            bs.visit_values(ch, bm, [&](sv x) { int64_t n = unzigzag(get_be64((const uint8_t*)x.data())); return n >= lo && n <= hi; });
+            break;
+        }
+        case VT_FLOAT64: {   // :216-228
+            double cmn, cmx; memcpy(&cmn, &ch->minValue, 8); memcpy(&cmx, &ch->maxValue, 8);
+            if (minValue > cmx || maxValue < cmn) { bm.reset_bits(); return; }
+            bs.visit_values(ch, bm, [&](sv x) { uint64_t b = get_be64((const uint8_t*)x.data()); double f; memcpy(&f, &b, 8); return f >= minValue && f <= maxValue; });
+            break;
+        }
+        case VT_IPV4: {   // toUint32Range + matchIPv4ByRange
+            auto clamp32 = [](double f) -> uint32_t { return f < 0 ? 0u : f > 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)f; };
+            uint32_t lo = clamp32(mnc), hi = clamp32(mxf);
+            if (ch->minValue > (uint64_t)hi || ch->maxValue < (uint64_t)lo) { bm.reset_bits(); return; }
+            bs.visit_values(ch, bm, [&](sv x) { uint32_t n = get_be32((const uint8_t*)x.data()); return n >= lo && n <= hi; });
+            break;
+        }
+        case VT_ISO8601: {   // :331-347
+            int64_t lo = i64_clamp(mnc), hi = i64_clamp(mxf);
+            if (maxValue < 0 || lo > (int64_t)ch->maxValue || hi < (int64_t)ch->minValue) { bm.reset_bits(); return; }
+            bs.visit_values(ch, bm, [&](sv x) { int64_t n = (int64_t)get_be64((const uint8_t*)x.data()); return n >= lo && n <= hi; });
+            break;
+        }
+        default: throw std::runtime_error("unknown valueType");
+        }
+    }
+};
+
+// le_field() / lt_field(): filter_le_field.go:14-313
+inline bool le_values_string(sv a, sv b, bool excl) {   // :283-297
+    double fa = parse_math_number(a);
+    if (!std::isnan(fa)) { double fb = parse_math_number(b); if (!std::isnan(fb)) return excl ? fa < fb : fa <= fb; }
+    return excl ? a < b : a <= b;
+}
+struct FilterLeField : Filter {
+    std::string field, other; bool excl;
+    FilterLeField(sv f, sv o, bool e) : field(canonical(f)), other(canonical(o)), excl(e) { kind = F_LE_FIELD; }
+    void by_strings(BlockSearch& bs, Bitmap& bm) { bm.for_each_set_bit([&](uint64_t idx) { return le_values_string(row_string(bs, field, idx), row_string(bs, other, idx), excl); }); }
+    void apply(BlockSearch& bs, Bitmap& bm) override {
+        if (field == other) { if (excl) bm.reset_bits(); return; }
+        sv v = bs.const_value(field), vo = bs.const_value(other);
+        if (!v.empty() || !vo.empty()) {
+            if (!v.empty() && !vo.empty()) { if (!le_values_string(v, vo, excl)) bm.reset_bits(); return; }
+            by_strings(bs, bm); return;
+        }
+        const Column* ch = bs.column(field); const Column* co = bs.column(other);
+        if (!ch || !co) { if (!ch && !co) { if (excl) bm.reset_bits(); return; } by_strings(bs, bm); return; }
+        if (ch->valueType != co->valueType || ch->valueType == VT_STRING) { by_strings(bs, bm); return; }
+        if (bm.is_zero()) return;
+        const auto& a = bs.values(ch); const auto& b = bs.values(co);
+        switch (ch->valueType) {
+        case VT_DICT: bm.for_each_set_bit([&](uint64_t i) { return le_values_string(ch->dict.at((uint8_t)a[i][0]), co->dict.at((uint8_t)b[i][0]), excl); }); break;
+        case VT_INT64: bm.for_each_set_bit([&](uint64_t i) { int64_t x = unzigzag(get_be64((const uint8_t*)a[i].data())), y = unzigzag(get_be64((const uint8_t*)b[i].data())); return excl ? x < y : x <= y; }); break;
+        case VT_FLOAT64: bm.for_each_set_bit([&](uint64_t i) { uint64_t p = get_be64((const uint8_t*)a[i].data()), q = get_be64((const uint8_t*)b[i].data()); double x, y; memcpy(&x, &p, 8); memcpy(&y, &q, 8); return excl ? x < y : x <= y; }); break;
+        default:   // applyFilterUint :246-252: uint8..uint64, ipv4, iso8601 compare their big-endian encodings AS STRINGS through leValuesString
+            bm.for_each_set_bit([&](uint64_t i) { return le_values_string(a[i], b[i], excl); });
+        }
     }
 };
 

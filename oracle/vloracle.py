@@ -44,8 +44,9 @@ def lib():
             getattr(L, name).restype = C.c_int64
         for name in ("vlo_block_build", "vlo_filter_phrase", "vlo_filter_prefix", "vlo_filter_exact", "vlo_filter_in", "vlo_filter_regexp",
                      "vlo_filter_noop", "vlo_filter_and", "vlo_filter_or", "vlo_filter_not", "vlo_gen_block",
-                     "vlo_filter_exact_prefix", "vlo_filter_sequence", "vlo_filter_contains_all", "vlo_filter_contains_any", "vlo_filter_any_case_phrase", "vlo_filter_any_case_prefix", "vlo_filter_value_type", "vlo_filter_eq_field", "vlo_filter_len_range", "vlo_filter_string_range", "vlo_filter_ipv4_range"):
+                     "vlo_filter_exact_prefix", "vlo_filter_sequence", "vlo_filter_contains_all", "vlo_filter_contains_any", "vlo_filter_any_case_phrase", "vlo_filter_any_case_prefix", "vlo_filter_value_type", "vlo_filter_eq_field", "vlo_filter_range", "vlo_filter_le_field", "vlo_filter_len_range", "vlo_filter_string_range", "vlo_filter_ipv4_range"):
             getattr(L, name).restype = C.c_void_p
+        L.vlo_parse_math_number.restype = C.c_double
         for name in ("vlo_block_rows", "vlo_block_ncolumns", "vlo_block_nconsts"):
             getattr(L, name).restype = C.c_uint64
         _LIB = L
@@ -358,6 +359,16 @@ class Filter:
     def value_type(field, type_name):
         f, p = _b(field), _b(type_name)
         return Filter(lib().vlo_filter_value_type(f, C.c_uint64(len(f)), p, C.c_uint64(len(p))))
+
+    @staticmethod
+    def range(field, min_value, max_value):
+        f = _b(field)
+        return Filter(lib().vlo_filter_range(f, C.c_uint64(len(f)), C.c_double(min_value), C.c_double(max_value)))
+
+    @staticmethod
+    def le_field(field, other_field, exclude_equal=False):
+        f, p = _b(field), _b(other_field)
+        return Filter(lib().vlo_filter_le_field(f, C.c_uint64(len(f)), p, C.c_uint64(len(p)), C.c_int(1 if exclude_equal else 0)))
 
     @staticmethod
     def eq_field(field, other_field):

@@ -261,6 +261,13 @@ def filter_spec(v):
         return {"kind": "any_case_prefix", "field": hx(field), "arg": hx(f.get("prefix", b""))}
     if kind == "filterValueType":
         return {"kind": "value_type", "field": hx(field), "arg": hx(f.get("valueType", b""))}
+    def fnum(k):   # float literal, `inf`, `-inf`
+        v = f.get(k, ("num", "0"))
+        return v[1] if v[0] in ("num", "ident") else "0"
+    if kind == "filterRange":
+        return {"kind": "range", "field": hx(field), "min": fnum("minValue"), "max": fnum("maxValue")}
+    if kind == "filterLeField":
+        return {"kind": "le_field", "field": hx(field), "arg": hx(f.get("otherFieldName", b"")), "exclude_equal": bool(f.get("excludeEqualValues", False))}
     if kind == "filterEqField":
         return {"kind": "eq_field", "field": hx(field), "arg": hx(f.get("otherFieldName", b""))}
     if kind == "filterLenRange":
@@ -274,7 +281,7 @@ def filter_spec(v):
 
 SUPPORTED = ("filterPhrase", "filterPrefix", "filterExact", "filterRegexp", "filterIn", "filterNot",
              "filterExactPrefix", "filterSequence", "filterLenRange", "filterStringRange", "filterIPv4Range", "filterContainsAll", "filterContainsAny",
-             "filterAnyCasePhrase", "filterAnyCasePrefix", "filterValueType", "filterEqField")
+             "filterAnyCasePhrase", "filterAnyCasePrefix", "filterValueType", "filterEqField", "filterRange", "filterLeField")
 
 
 def extract_filter_cases(path):
@@ -419,7 +426,7 @@ def main():
     cases = []
     for name in ("filter_exact_prefix_test.go", "filter_sequence_test.go", "filter_len_range_test.go", "filter_string_range_test.go", "filter_ipv4_range_test.go",
                  "filter_contains_all_test.go", "filter_contains_any_test.go", "filter_any_case_phrase_test.go", "filter_any_case_prefix_test.go",
-                 "filter_value_type_test.go", "filter_eq_field_test.go"):
+                 "filter_value_type_test.go", "filter_eq_field_test.go", "filter_range_test.go", "filter_le_field_test.go"):
         c = extract_filter_cases(os.path.join(REF, name))
         print(name, len(c))
         cases.extend(c)

@@ -40,6 +40,10 @@ def build_filter(F, spec):
     field = bytes.fromhex(spec["field"])
     if k == "in":
         return F.in_(field, [bytes.fromhex(v) for v in spec["values"]])
+    if k == "range":
+        return F.range(field, float(spec["min"]), float(spec["max"]))
+    if k == "le_field":
+        return F.le_field(field, bytes.fromhex(spec["arg"]), spec["exclude_equal"])
     if k in ("contains_all", "contains_any"):
         return getattr(F, k)(field, [bytes.fromhex(v) for v in spec["values"]])
     if k == "sequence":

@@ -14,7 +14,7 @@ def test_counts():
     for c in CASES:
         kinds[c["filter"]["kind"]] = kinds.get(c["filter"]["kind"], 0) + 1
     assert kinds == {"exact_prefix": 62, "sequence": 103, "len_range": 30, "string_range": 48, "ipv4_range": 24, "contains_all": 104, "contains_any": 88,
-                     "any_case_phrase": 107, "any_case_prefix": 114, "value_type": 35, "eq_field": 78}
+                     "any_case_phrase": 107, "any_case_prefix": 114, "value_type": 35, "eq_field": 78, "range": 62, "le_field": 139}
 
 
 @pytest.mark.parametrize("idx", range(len(CASES)))
@@ -24,6 +24,23 @@ def test_reference_tables(oracle, idx):
     f = build_filter(oracle.Filter, c["filter"])
     got = oracle.bitmap_rows(b.search(f), b.rows)
     assert got == c["expected"], (c["src"], c["filter"])
+
+
+def test_parse_math_number(oracle):
+    # parseMathNumber (pipe_math.go:1066-1080): float, duration, byte size, Go float / int literal, RFC 3339 timestamp, IPv4 -> float64
+    import math
+    f = lambda s: oracle.lib().vlo_parse_math_number(s if isinstance(s, bytes) else s.encode(), len(s if isinstance(s, bytes) else s.encode()))
+    table = {"10": 10.0, "-7": -7.0, "1.5": 1.5, "1_000": 1000.0, "1e3": 1000.0, "1.5E-3": 0.0015, "5s": 5e9, "1h30m": 5.4e12, "-5m": -3e11, "1.5ms": 1.5e6, "2µs": 2000.0,
+             "3ns": 3.0, "1w": 7 * 86400e9, "10KB": 10000.0, "1KiB": 1024.0, "1.5K": 1500.0, "2MiB": 2097152.0, "3B": 3.0, "0x10": 16.0, "0b101": 5.0, "0o17": 15.0, "017": 17.0,   # "017": tryParseUint64 rejects the leading zero, strconv.ParseFloat reads it as 17 before ParseInt is tried
+             "1__0": 10.0, "_1": 1.0,   # tryParseUint64 skips every underscore (values_encoder.go:566)
+             "inf": math.inf, "-inf": -math.inf, "+Inf": math.inf, "1.2.3.4": 16909060.0, "255.255.255.255": 4294967295.0,
+             "2006-01-02T15:04:05Z": 1136214245e9, "2006-01-02T15:04:05.5Z": 1136214245.5e9, "2006-01-02T15:04:05.123456789+01:00": (1136214245 - 3600) * 1e9 + 123456789,
+             "2006-01-02 15:04:05-02:30": (1136214245 + 9000) * 1e9, "18446744073709551615": 18446744073709551615.0}
+    for s, want in table.items():
+        got = f(s)
+        assert got == want, (s, got, want)
+    for s in ["", "foo", "a 10", "1.5.", "5 s", "10kb", "0x", "1e", "--1", "1.2.3", "2006-01-02", "2006-01-02T15:04:05+1:00", "nan", "Infinity"]:
+        assert math.isnan(f(s)), (s, f(s))
 
 
 def test_predicates(oracle):
