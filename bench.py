@@ -302,7 +302,10 @@ def main():
             "gpu_launches": int(st.gpu_launches) * args.steps,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_substr_scan", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
-                         "traffic": None, "peak_source": peak_src, "kernel_ms_per_launch": k_avg, "algorithmic_bytes_per_launch": int(kbytes),
+                         "traffic": None,   # no ncu capture exists for this exact launch; the one that does (30 M rows of the same workload):
+                         "traffic_capture": {"rows": 30000000, "dram_bytes_per_launch": 4403560752, "algorithmic_bytes_per_launch": 3806642565, "ratio": 1.157,
+                                             "source": "profiles/ncu_k_substr_scan_r01.csv (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"},
+                         "peak_source": peak_src, "kernel_ms_per_launch": k_avg, "algorithmic_bytes_per_launch": int(kbytes),
                          "kernel_share_of_step": (k_avg / statistics.mean(gms)) if gms and statistics.mean(gms) > 0 else None},
             "e2e": e2e, "cpu_baseline": cpu,
         }
