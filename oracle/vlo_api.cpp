@@ -162,6 +162,25 @@ void* vlo_block_build(const uint8_t* names_blob, const uint64_t* names_offs, uin
     return h;
 }
 void vlo_block_free(void* h) { delete (BlockHandle*)h; }
+int vlo_block_set_timestamps(void* h, const int64_t* ts, uint64_t n) { return guard([&] { ((BlockHandle*)h)->b.set_timestamps(std::vector<int64_t>(ts, ts + n)); }); }
+// encoded timestamps of a block: pointer + length, marshal type, min / max (timestampsHeader)
+int vlo_block_timestamps(void* h, const uint8_t** data, uint64_t* len, int* marshal_type, int64_t* min_ts, int64_t* max_ts) {
+    Block& b = ((BlockHandle*)h)->b;
+    if (!b.hasTimestamps) return -1;
+    *data = (const uint8_t*)b.ts.data.data(); *len = b.ts.data.size(); *marshal_type = b.ts.mt; *min_ts = b.minTimestamp; *max_ts = b.maxTimestamp;
+    return 0;
+}
+// encoding.MarshalTimestamps(ts, 64) / UnmarshalTimestamps
+int64_t vlo_marshal_timestamps(const int64_t* ts, uint64_t n, uint8_t* out, uint64_t cap, int* marshal_type, int64_t* first) {
+    int64_t r = -1;
+    guard([&] { EncodedInt64s e = marshal_int64_array(std::vector<int64_t>(ts, ts + n)); if (e.data.size() > cap) throw std::runtime_error("output buffer too small");
+                memcpy(out, e.data.data(), e.data.size()); *marshal_type = e.mt; *first = e.first; r = (int64_t)e.data.size(); });
+    return r;
+}
+int vlo_unmarshal_timestamps(const uint8_t* src, uint64_t n, int marshal_type, int64_t first, uint64_t items, int64_t* out) {
+    return guard([&] { auto v = unmarshal_int64_array(sv((const char*)src, n), (uint8_t)marshal_type, first, items); memcpy(out, v.data(), v.size() * 8); });
+}
+void* vlo_filter_time(int64_t mn, int64_t mx) { return new FilterHandle{std::make_shared<FilterTime>(mn, mx)}; }
 uint64_t vlo_block_rows(void* h) { return ((BlockHandle*)h)->b.rows; }
 uint64_t vlo_block_ncolumns(void* h) { return ((BlockHandle*)h)->b.columns.size(); }
 uint64_t vlo_block_nconsts(void* h) { return ((BlockHandle*)h)->b.consts.size(); }

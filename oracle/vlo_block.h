@@ -11,6 +11,7 @@
 #pragma once
 #include "vlo_util.h"
 #include "vlo_mathnum.h"
+#include "vlo_timestamps.h"
 #include "vlo_regex.h"
 #include <functional>
 #include <map>
@@ -35,6 +36,13 @@ struct Block {
     uint64_t rows = 0;
     std::vector<Column> columns;
     std::vector<ConstColumn> consts;
+    // timestamps column (optional in this oracle): encoded block + timestampsHeader fields (block_header.go timestampsHeader)
+    bool hasTimestamps = false; EncodedInt64s ts; int64_t minTimestamp = 0, maxTimestamp = 0;
+    void set_timestamps(const std::vector<int64_t>& a) {   // block.go:674-690: rows are sorted by time
+        if (a.size() != rows) throw std::runtime_error("timestamps count differs from rows");
+        for (size_t i = 1; i < a.size(); i++) if (a[i] < a[i - 1]) throw std::runtime_error("timestamps must be sorted");
+        ts = marshal_int64_array(a); hasTimestamps = true; minTimestamp = a.front(); maxTimestamp = a.back();
+    }
 };
 
 inline std::string canonical(sv name) { return name.empty() ? std::string("_msg") : std::string(name); }   // getCanonicalColumnName
@@ -300,8 +308,13 @@ struct BlockSearch {
     std::map<std::string, BloomFilter> bloomCache;
     struct Vals { DecodedStringsBlock dec; std::vector<sv> values; };
     std::map<std::string, std::unique_ptr<Vals>> valuesCache;
+    std::vector<int64_t> timestampsCache; bool timestampsCached = false;
+    const std::vector<int64_t>& timestamps() {   // getTimestamps block_search.go:479-506
+        if (!timestampsCached) { timestampsCache = unmarshal_int64_array(b->ts.data, b->ts.mt, b->minTimestamp, b->rows); timestampsCached = true; }
+        return timestampsCache;
+    }
 
-    void reset(const Block* blk, ScanStats* s) { b = blk; st = s; bloomCache.clear(); valuesCache.clear(); }
+    void reset(const Block* blk, ScanStats* s) { b = blk; st = s; bloomCache.clear(); valuesCache.clear(); timestampsCached = false; }
     sv const_value(sv name) const {   // getConstColumnValue block_search.go:232-276
         std::string n = canonical(name);
         for (auto& cc : b->consts) if (cc.name == n) return cc.value;
@@ -374,7 +387,7 @@ inline std::string encoded_to_string(uint8_t vt, sv v) {
 struct FieldTokens { std::string field; std::vector<std::string> tokens; std::vector<uint64_t> hashes; };
 
 enum FilterKind { F_NOOP, F_PHRASE, F_PREFIX, F_EXACT, F_IN, F_REGEXP, F_AND, F_OR, F_NOT, F_EXACT_PREFIX, F_SEQUENCE, F_LEN_RANGE, F_STRING_RANGE, F_IPV4_RANGE, F_CONTAINS_ALL, F_CONTAINS_ANY,
-                  F_ANY_CASE_PHRASE, F_ANY_CASE_PREFIX, F_VALUE_TYPE, F_EQ_FIELD, F_RANGE, F_LE_FIELD };
+                  F_ANY_CASE_PHRASE, F_ANY_CASE_PREFIX, F_VALUE_TYPE, F_EQ_FIELD, F_RANGE, F_LE_FIELD, F_TIME };
 
 struct Filter {
     FilterKind kind;
@@ -1103,6 +1116,20 @@ struct FilterLeField : Filter {
         default:   // applyFilterUint :246-252: uint8..uint64, ipv4, iso8601 compare their big-endian encodings AS STRINGS through leValuesString
             bm.for_each_set_bit([&](uint64_t i) { return le_values_string(a[i], b[i], excl); });
         }
+    }
+};
+
+struct FilterTime : Filter {   // filter_time.go:14-137  (_time:[min, max], nanoseconds, both ends inclusive)
+    int64_t minTimestamp, maxTimestamp;
+    FilterTime(int64_t mn, int64_t mx) : minTimestamp(mn), maxTimestamp(mx) { kind = F_TIME; }
+    void apply(BlockSearch& bs, Bitmap& bm) override {
+        if (minTimestamp > maxTimestamp) { bm.reset_bits(); return; }
+        if (!bs.b->hasTimestamps) throw std::runtime_error("the block has no timestamps");
+        if (minTimestamp > bs.b->maxTimestamp || maxTimestamp < bs.b->minTimestamp) { bm.reset_bits(); return; }   // header-level prune
+        if (minTimestamp <= bs.b->minTimestamp && maxTimestamp >= bs.b->maxTimestamp) return;                     // the whole block is inside
+        if (bm.is_zero()) return;
+        const auto& t = bs.timestamps();
+        bm.for_each_set_bit([&](uint64_t idx) { return t[idx] >= minTimestamp && t[idx] <= maxTimestamp; });
     }
 };
 

@@ -44,9 +44,10 @@ def lib():
             getattr(L, name).restype = C.c_int64
         for name in ("vlo_block_build", "vlo_filter_phrase", "vlo_filter_prefix", "vlo_filter_exact", "vlo_filter_in", "vlo_filter_regexp",
                      "vlo_filter_noop", "vlo_filter_and", "vlo_filter_or", "vlo_filter_not", "vlo_gen_block",
-                     "vlo_filter_exact_prefix", "vlo_filter_sequence", "vlo_filter_contains_all", "vlo_filter_contains_any", "vlo_filter_any_case_phrase", "vlo_filter_any_case_prefix", "vlo_filter_value_type", "vlo_filter_eq_field", "vlo_filter_range", "vlo_filter_le_field", "vlo_filter_len_range", "vlo_filter_string_range", "vlo_filter_ipv4_range"):
+                     "vlo_filter_exact_prefix", "vlo_filter_sequence", "vlo_filter_contains_all", "vlo_filter_contains_any", "vlo_filter_any_case_phrase", "vlo_filter_any_case_prefix", "vlo_filter_value_type", "vlo_filter_eq_field", "vlo_filter_range", "vlo_filter_le_field", "vlo_filter_time", "vlo_filter_len_range", "vlo_filter_string_range", "vlo_filter_ipv4_range"):
             getattr(L, name).restype = C.c_void_p
         L.vlo_parse_math_number.restype = C.c_double
+        L.vlo_marshal_timestamps.restype = C.c_int64
         for name in ("vlo_block_rows", "vlo_block_ncolumns", "vlo_block_nconsts"):
             getattr(L, name).restype = C.c_uint64
         _LIB = L
@@ -274,6 +275,20 @@ class Block:
             raise _err()
         return Block(h)
 
+    def set_timestamps(self, timestamps):
+        """timestamps: sorted int64 nanoseconds, one per row (the block's _time column)."""
+        a = np.asarray(timestamps, dtype=np.int64)
+        if lib().vlo_block_set_timestamps(self.h, a.ctypes.data_as(C.c_void_p), C.c_uint64(len(a))):
+            raise _err()
+        return self
+
+    def timestamps_block(self):
+        """-> (encoded bytes, marshalType, minTimestamp, maxTimestamp): what timestamps.bin + the block header hold"""
+        p, n, mt, mn, mx = C.c_void_p(), C.c_uint64(), C.c_int(), C.c_int64(), C.c_int64()
+        if lib().vlo_block_timestamps(self.h, C.byref(p), C.byref(n), C.byref(mt), C.byref(mn), C.byref(mx)):
+            raise ValueError("the block has no timestamps")
+        return C.string_at(p, n.value), mt.value, mn.value, mx.value
+
     @staticmethod
     def generated(cfg, block_id):
         h = lib().vlo_gen_block(C.byref(cfg), C.c_uint64(block_id))
@@ -371,6 +386,10 @@ class Filter:
         return Filter(lib().vlo_filter_le_field(f, C.c_uint64(len(f)), p, C.c_uint64(len(p)), C.c_int(1 if exclude_equal else 0)))
 
     @staticmethod
+    def time(min_timestamp, max_timestamp):
+        return Filter(lib().vlo_filter_time(C.c_int64(min_timestamp), C.c_int64(max_timestamp)))
+
+    @staticmethod
     def eq_field(field, other_field):
         f, p = _b(field), _b(other_field)
         return Filter(lib().vlo_filter_eq_field(f, C.c_uint64(len(f)), p, C.c_uint64(len(p))))
@@ -419,6 +438,24 @@ class Filter:
     @staticmethod
     def not_(f):
         return Filter(lib().vlo_filter_not(f.h), keep=(f,))
+
+
+def marshal_timestamps(timestamps):
+    """encoding.MarshalTimestamps(ts, 64) -> (bytes, marshalType, firstTimestamp)"""
+    a = np.asarray(timestamps, dtype=np.int64)
+    out = C.create_string_buffer(len(a) * 10 + 64)
+    mt, first = C.c_int(), C.c_int64()
+    n = lib().vlo_marshal_timestamps(a.ctypes.data_as(C.c_void_p), C.c_uint64(len(a)), out, C.c_uint64(len(out)), C.byref(mt), C.byref(first))
+    if n < 0:
+        raise _err()
+    return out.raw[:n], mt.value, first.value
+
+
+def unmarshal_timestamps(data, marshal_type, first, items):
+    out = np.zeros(items, dtype=np.int64)
+    if lib().vlo_unmarshal_timestamps(data, C.c_uint64(len(data)), C.c_int(marshal_type), C.c_int64(first), C.c_uint64(items), out.ctypes.data_as(C.c_void_p)):
+        raise _err()
+    return out
 
 
 def gen_rows(cfg, block_id, column, cap=None):

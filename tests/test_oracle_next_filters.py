@@ -26,6 +26,61 @@ def test_reference_tables(oracle, idx):
     assert got == c["expected"], (c["src"], c["filter"])
 
 
+def test_filter_time_reference_table(oracle):
+    # filter_time_test.go:13-88 TestFilterTime: one block, five rows; bounds in nanoseconds, both inclusive
+    ts = [1, 9, 123, 456, 789]
+    blk = oracle.Block.from_columns([("_msg", [b"some value for row %d" % i for i in range(5)])]).set_timestamps(ts)
+    table = [(-10, 1, [0]), (-10, 10, [0, 1]), (1, 1, [0]), (2, 456, [1, 2, 3]), (2, 457, [1, 2, 3]), (120, 788, [2, 3]), (120, 789, [2, 3, 4]),
+             (120, 10000, [2, 3, 4]), (789, 1000, [4]), (-1000, 0, []), (790, 1000, [])]
+    for lo, hi, want in table:
+        assert oracle.bitmap_rows(blk.search(oracle.Filter.time(lo, hi)), blk.rows) == want, (lo, hi)
+    assert oracle.bitmap_rows(blk.search(oracle.Filter.time(5, 4)), blk.rows) == []
+    both = oracle.Filter.and_([oracle.Filter.time(2, 500), oracle.Filter.phrase("_msg", "row")])
+    assert oracle.bitmap_rows(blk.search(both), blk.rows) == [1, 2, 3]
+
+
+def test_timestamps_codec(oracle):
+    """encoding.MarshalTimestamps(ts, 64) / UnmarshalTimestamps (vm/lib/encoding): marshal types, hand-derived bytes, round trips."""
+    import random
+    import numpy as np
+    # hand-derived from nearest_delta2.go + MarshalVarInt64 (zig-zag, 7-bit groups): first=1, d1=8 -> 0x10; then the deltas of deltas
+    # 123-9-8=106 -> zz 212 -> D4 01; 456-123-114=219 -> zz 438 -> B6 03; 789-456-333=0 -> 00
+    data, mt, first = oracle.marshal_timestamps([1, 9, 123, 456, 789])
+    assert (data, mt, first) == (bytes.fromhex("10d401b60300"), 5, 1)
+    assert oracle.marshal_timestamps([7, 7, 7]) == (b"", 3, 7)                       # MarshalTypeConst
+    assert oracle.marshal_timestamps([10, 13, 16, 19]) == (bytes([6]), 2, 10)        # MarshalTypeDeltaConst: varint(zigzag(3))
+    assert oracle.marshal_timestamps([5]) == (b"", 3, 5)
+    rng = random.Random(4)
+    base = 1_700_000_000_000_000_000
+    arrays = {
+        "jitter": np.cumsum([rng.randint(0, 2_000_000) for _ in range(3000)]) + base,          # sorted, zstd'ed delta2
+        "short": np.cumsum([rng.randint(0, 1000) for _ in range(20)]) + base,                   # < 128 bytes: plain delta2
+        "dups": np.sort(np.array([base + rng.randint(0, 50) for _ in range(500)])),
+        "gauge": np.array([rng.randint(-1000, 1000) for _ in range(400)]),                      # not sorted: nearest delta
+        "extremes": np.array([-2**63, -1, 0, 2**63 - 1, 5, -2**63], dtype=np.int64),
+    }
+    seen = set()
+    for name, a in arrays.items():
+        a = np.asarray(a, dtype=np.int64)
+        data, mt, first = oracle.marshal_timestamps(a)
+        seen.add(mt)
+        assert first == int(a[0])
+        assert np.array_equal(oracle.unmarshal_timestamps(data, mt, first, len(a)), a), name
+    assert {1, 5, 4}.issubset(seen) or {1, 5, 6}.issubset(seen)
+    # a block carries its encoded timestamps and header fields
+    # (random jitter does not compress by 10 %, so it stays NearestDelta2 = 5; a few distinct steps do compress: ZSTDNearestDelta2 = 1)
+    steps = np.cumsum([rng.choice([1_000_000, 1_000_000, 1_000_000, 2_000_000]) for _ in range(3000)]) + base
+    blk = oracle.Block.from_columns([("_msg", [b"x%d" % i for i in range(3000)])]).set_timestamps(steps)
+    data, mt, mn, mx = blk.timestamps_block()
+    assert mt == 1 and mn == int(steps[0]) and mx == int(steps[-1]) and len(data) < 3000
+    assert oracle.marshal_timestamps(arrays["jitter"])[1] == 5
+    lo, hi = int(steps[100]), int(steps[199])
+    got = oracle.bitmap_rows(blk.search(oracle.Filter.time(lo, hi)), blk.rows)
+    assert got == list(range(100, 200))
+    with pytest.raises(RuntimeError):
+        oracle.Block.from_columns([("_msg", [b"a", b"b"])]).set_timestamps([2, 1])
+
+
 def test_parse_math_number(oracle):
     # parseMathNumber (pipe_math.go:1066-1080): float, duration, byte size, Go float / int literal, RFC 3339 timestamp, IPv4 -> float64
     import math
