@@ -180,6 +180,8 @@ int64_t vlo_marshal_timestamps(const int64_t* ts, uint64_t n, uint8_t* out, uint
 int vlo_unmarshal_timestamps(const uint8_t* src, uint64_t n, int marshal_type, int64_t first, uint64_t items, int64_t* out) {
     return guard([&] { auto v = unmarshal_int64_array(sv((const char*)src, n), (uint8_t)marshal_type, first, items); memcpy(out, v.data(), v.size() * 8); });
 }
+void* vlo_filter_day_range(int64_t start, int64_t end, int64_t offset) { return new FilterHandle{std::make_shared<FilterDayRange>(start, end, offset)}; }
+void* vlo_filter_week_range(int start_day, int end_day, int64_t offset) { return new FilterHandle{std::make_shared<FilterWeekRange>(start_day, end_day, offset)}; }
 void* vlo_filter_time(int64_t mn, int64_t mx) { return new FilterHandle{std::make_shared<FilterTime>(mn, mx)}; }
 uint64_t vlo_block_rows(void* h) { return ((BlockHandle*)h)->b.rows; }
 uint64_t vlo_block_ncolumns(void* h) { return ((BlockHandle*)h)->b.columns.size(); }

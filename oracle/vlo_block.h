@@ -387,7 +387,7 @@ inline std::string encoded_to_string(uint8_t vt, sv v) {
 struct FieldTokens { std::string field; std::vector<std::string> tokens; std::vector<uint64_t> hashes; };
 
 enum FilterKind { F_NOOP, F_PHRASE, F_PREFIX, F_EXACT, F_IN, F_REGEXP, F_AND, F_OR, F_NOT, F_EXACT_PREFIX, F_SEQUENCE, F_LEN_RANGE, F_STRING_RANGE, F_IPV4_RANGE, F_CONTAINS_ALL, F_CONTAINS_ANY,
-                  F_ANY_CASE_PHRASE, F_ANY_CASE_PREFIX, F_VALUE_TYPE, F_EQ_FIELD, F_RANGE, F_LE_FIELD, F_TIME };
+                  F_ANY_CASE_PHRASE, F_ANY_CASE_PREFIX, F_VALUE_TYPE, F_EQ_FIELD, F_RANGE, F_LE_FIELD, F_TIME, F_DAY_RANGE, F_WEEK_RANGE };
 
 struct Filter {
     FilterKind kind;
@@ -1130,6 +1130,34 @@ struct FilterTime : Filter {   // filter_time.go:14-137  (_time:[min, max], nano
         if (bm.is_zero()) return;
         const auto& t = bs.timestamps();
         bm.for_each_set_bit([&](uint64_t idx) { return t[idx] >= minTimestamp && t[idx] <= maxTimestamp; });
+    }
+};
+
+struct FilterDayRange : Filter {   // filter_day_range.go:13-124  (_time:day_range[hh:mm, hh:mm] offset ...): nanoseconds inside the day
+    int64_t start, end, offset;
+    FilterDayRange(int64_t s, int64_t e, int64_t o) : start(s), end(e), offset(o) { kind = F_DAY_RANGE; }
+    void apply(BlockSearch& bs, Bitmap& bm) override {
+        if (start > end) { bm.reset_bits(); return; }
+        if (start == 0 && end == 86400000000000LL - 1) return;
+        if (bm.is_zero()) return;
+        const auto& t = bs.timestamps();
+        bm.for_each_set_bit([&](uint64_t idx) { int64_t d = (t[idx] - offset) % 86400000000000LL; return d >= start && d <= end; });   // Go's % truncates like C++'s
+    }
+};
+struct FilterWeekRange : Filter {   // filter_week_range.go:14-126: time.Weekday (Sunday = 0) of the UTC date
+    int startDay, endDay; int64_t offset;
+    FilterWeekRange(int s, int e, int64_t o) : startDay(s), endDay(e), offset(o) { kind = F_WEEK_RANGE; }
+    static int weekday(int64_t ts) {
+        int64_t day = ts / 86400000000000LL; if (ts % 86400000000000LL < 0) day--;   // floor: time.Unix(0, ts).UTC()
+        int64_t w = (day + 4) % 7; if (w < 0) w += 7;                                 // 1970-01-01 was a Thursday
+        return (int)w;
+    }
+    void apply(BlockSearch& bs, Bitmap& bm) override {
+        if (startDay > endDay) { bm.reset_bits(); return; }
+        if (startDay <= 0 && endDay >= 6) return;
+        if (bm.is_zero()) return;
+        const auto& t = bs.timestamps();
+        bm.for_each_set_bit([&](uint64_t idx) { int d = weekday(t[idx] - offset); return d >= startDay && d <= endDay; });
     }
 };
 

@@ -44,7 +44,7 @@ def lib():
             getattr(L, name).restype = C.c_int64
         for name in ("vlo_block_build", "vlo_filter_phrase", "vlo_filter_prefix", "vlo_filter_exact", "vlo_filter_in", "vlo_filter_regexp",
                      "vlo_filter_noop", "vlo_filter_and", "vlo_filter_or", "vlo_filter_not", "vlo_gen_block",
-                     "vlo_filter_exact_prefix", "vlo_filter_sequence", "vlo_filter_contains_all", "vlo_filter_contains_any", "vlo_filter_any_case_phrase", "vlo_filter_any_case_prefix", "vlo_filter_value_type", "vlo_filter_eq_field", "vlo_filter_range", "vlo_filter_le_field", "vlo_filter_time", "vlo_filter_len_range", "vlo_filter_string_range", "vlo_filter_ipv4_range"):
+                     "vlo_filter_exact_prefix", "vlo_filter_sequence", "vlo_filter_contains_all", "vlo_filter_contains_any", "vlo_filter_any_case_phrase", "vlo_filter_any_case_prefix", "vlo_filter_value_type", "vlo_filter_eq_field", "vlo_filter_range", "vlo_filter_le_field", "vlo_filter_time", "vlo_filter_day_range", "vlo_filter_week_range", "vlo_filter_len_range", "vlo_filter_string_range", "vlo_filter_ipv4_range"):
             getattr(L, name).restype = C.c_void_p
         L.vlo_parse_math_number.restype = C.c_double
         L.vlo_marshal_timestamps.restype = C.c_int64
@@ -384,6 +384,14 @@ class Filter:
     def le_field(field, other_field, exclude_equal=False):
         f, p = _b(field), _b(other_field)
         return Filter(lib().vlo_filter_le_field(f, C.c_uint64(len(f)), p, C.c_uint64(len(p)), C.c_int(1 if exclude_equal else 0)))
+
+    @staticmethod
+    def day_range(start, end, offset=0):
+        return Filter(lib().vlo_filter_day_range(C.c_int64(start), C.c_int64(end), C.c_int64(offset)))
+
+    @staticmethod
+    def week_range(start_day, end_day, offset=0):
+        return Filter(lib().vlo_filter_week_range(C.c_int(start_day), C.c_int(end_day), C.c_int64(offset)))
 
     @staticmethod
     def time(min_timestamp, max_timestamp):

@@ -39,6 +39,23 @@ def test_filter_time_reference_table(oracle):
     assert oracle.bitmap_rows(blk.search(both), blk.rows) == [1, 2, 3]
 
 
+def test_day_and_week_range_reference_tables(oracle):
+    F = oracle.Filter
+    # filter_day_range_test.go TestFilterDayRange (start, end, offset in nanoseconds inside the day)
+    blk = oracle.Block.from_columns([("_msg", [b"some value for row %d" % i for i in range(5)])]).set_timestamps([1, 9, 123, 456, 789])
+    for start, end, off, want in [(0, 1, 0, [0]), (0, 10, 0, [0, 1]), (1, 1, 0, [0]), (1, 1, 8, [1]), (10, 10, -9, [0]), (2, 456, 0, [1, 2, 3]), (2, 457, 0, [1, 2, 3]),
+                                  (120, 788, 0, [2, 3]), (120, 789, 0, [2, 3, 4]), (120, 10000, 0, [2, 3, 4]), (789, 1000, 0, [4]), (1, 1, 10, []), (0, 1000, 10_000, []), (790, 1000, 0, [])]:
+        assert oracle.bitmap_rows(blk.search(F.day_range(start, end, off)), blk.rows) == want, (start, end, off)
+    # filter_week_range_test.go TestFilterWeekRange: sunday = 2024-06-09T01:00:00Z; rows at +0, +1, +2, +4, +6 days
+    day, hour = 86400 * 10**9, 3600 * 10**9
+    sunday = 1717894800 * 10**9
+    wk = oracle.Block.from_columns([("_msg", [b"some value for row %d" % i for i in range(5)])]).set_timestamps([sunday, sunday + day, sunday + 2 * day, sunday + 4 * day, sunday + 6 * day])
+    SUN, MON, THU, FRI, SAT = 0, 1, 4, 5, 6
+    for a, b, off, want in [(SUN, SUN, 0, [0]), (SUN, MON, 0, [0, 1]), (MON, MON, 0, [1]), (MON, MON, 3 * day, [3]), (MON, MON, -2 * day, [4]), (SUN, SAT, 0, [0, 1, 2, 3, 4]),
+                            (FRI, FRI, 0, []), (THU, THU, 2 * hour, []), (FRI, FRI, -1 * hour, [])]:
+        assert oracle.bitmap_rows(wk.search(F.week_range(a, b, off)), wk.rows) == want, (a, b, off)
+
+
 def test_timestamps_codec(oracle):
     """encoding.MarshalTimestamps(ts, 64) / UnmarshalTimestamps (vm/lib/encoding): marshal types, hand-derived bytes, round trips."""
     import random
