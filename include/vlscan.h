@@ -191,6 +191,11 @@ int vlscan_host_blocks_compress(const vlscan_host_blocks* in, int threads, vlsca
  * no dictionary; content checksums are skipped, not verified. */
 int vlscan_zstd_decompress(vlscan_ctx* ctx, uint32_t nframes, const void* const* frames, const size_t* frame_lens, void* dst,
                            const uint64_t* dst_offsets);
+/* The host half of that decoder alone (no device needed): walk ONE bytes block (marshalBytesBlock container, encoding.go:343-360)
+ * exactly like the stager does - container, frame header, block headers, literals / sequences section headers - and report
+ * out[0] = bytes consumed, out[1] = regenerated length, out[2] = ZSTD blocks, out[3] = compressed blocks, out[4] = sequences.
+ * Returns <0 with an error text for malformed input.  For tests (the walker parses untrusted bytes). */
+int vlscan_zstd_inspect(const void* bytes_block, size_t len, uint64_t out[5]);
 
 /* ---- the scan ---------------------------------------------------------------------------------------------------- */
 /* Scan a resident batch: equivalent of `for each block: bm.init(rows); bm.setBits(); filter.applyToBlockSearch(bs, bm)`

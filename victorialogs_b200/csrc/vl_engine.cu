@@ -794,6 +794,15 @@ int vlscan_host_blocks_compress(const vlscan_host_blocks* in, int threads, vlsca
     return 0;
 }
 
+int vlscan_zstd_inspect(const void* bytes_block, size_t len, uint64_t out[5]) {
+    return guarded(nullptr, [&] {
+        ZstdJob job;
+        uint64_t regen = 0; uint32_t id = 0;
+        size_t used = job.add_bytes_block((const uint8_t*)bytes_block, len, 512, &regen, &id);
+        out[0] = used; out[1] = regen; out[2] = job.blocks(); out[3] = job.compressed_blocks(); out[4] = job.sequences();
+    });
+}
+
 int vlscan_zstd_decompress(vlscan_ctx* ctx, uint32_t nframes, const void* const* frames, const size_t* frame_lens, void* dst, const uint64_t* dst_offsets) {
     return guarded(ctx, [&] {
         VL_CUDA(cudaSetDevice(ctx->device));

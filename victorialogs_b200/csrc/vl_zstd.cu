@@ -205,6 +205,7 @@ ZstdJob::ZstdJob() : m(new Impl) {}
 ZstdJob::~ZstdJob() { delete m; }
 bool ZstdJob::empty() const { return m->frames.empty(); }
 uint64_t ZstdJob::frames() const { return m->frames.size(); }
+uint64_t ZstdJob::blocks() const { return m->blocks.size(); }
 uint64_t ZstdJob::compressed_blocks() const { return m->n_compressed; }
 uint64_t ZstdJob::sequences() const { return m->n_seqs; }
 void ZstdJob::set_dst(uint32_t id, uint64_t arena_off) { m->frames[id].dst = arena_off; }

@@ -32,6 +32,7 @@ public:
     void set_dst(uint32_t id, uint64_t arena_off);
     bool empty() const;
     uint64_t frames() const;
+    uint64_t blocks() const;
     uint64_t compressed_blocks() const;
     uint64_t sequences() const;
     // called right before the kernels of a launch group are enqueued, with the end offset (in the compressed staging buffer) of the

@@ -68,7 +68,7 @@ EXPORTS = ["vlscan_device_count", "vlscan_ctx_create", "vlscan_ctx_free", "vlsca
            "vlscan_program_create", "vlscan_program_free", "vlscan_program_nfields", "vlscan_program_field", "vlscan_program_leaf_tokens", "vlscan_format_float64", "vlscan_eval_predicate",
            "vlscan_batch_upload", "vlscan_batch_free", "vlscan_batch_nblocks", "vlscan_batch_rows", "vlscan_batch_words", "vlscan_batch_device_bytes",
            "vlscan_batch_generate", "vlscan_batch_download", "vlscan_host_blocks_get", "vlscan_host_blocks_field", "vlscan_host_blocks_bytes",
-           "vlscan_host_blocks_free", "vlscan_host_blocks_compress", "vlscan_zstd_decompress", "vlscan_scan_resident", "vlscan_last_scan_stats", "vlscan_fetch_results", "vlscan_fetch_hits", "vlscan_result_device_ptrs", "vlscan_scan_batch"]
+           "vlscan_host_blocks_free", "vlscan_host_blocks_compress", "vlscan_zstd_decompress", "vlscan_zstd_inspect", "vlscan_scan_resident", "vlscan_last_scan_stats", "vlscan_fetch_results", "vlscan_fetch_hits", "vlscan_result_device_ptrs", "vlscan_scan_batch"]
 
 
 def lib_path():
@@ -112,6 +112,15 @@ def eval_predicate(kind, value, arg1=b"", arg2=b"", aux0=0, aux1=0):
     if r < 0:
         raise ValueError(kind)
     return bool(r)
+
+
+def zstd_inspect(bytes_block):
+    """Host-side walk of one bytes block (vlscan_zstd_inspect) -> dict(consumed, regenerated, blocks, compressed_blocks, sequences)."""
+    out = (C.c_uint64 * 5)()
+    rc = lib().vlscan_zstd_inspect(bytes_block, C.c_size_t(len(bytes_block)), out)
+    if rc:
+        raise VlscanError(rc, lib().vlscan_last_error(None).decode("utf-8", "replace"))
+    return dict(consumed=out[0], regenerated=out[1], blocks=out[2], compressed_blocks=out[3], sequences=out[4])
 
 
 def format_float64(bits):
