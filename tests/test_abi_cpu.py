@@ -23,6 +23,30 @@ def test_library_exports_every_declared_symbol():
     assert sorted(declared) == sorted(vs.EXPORTS)
 
 
+def test_header_is_plain_c_and_links(tmp_path):
+    # cgo compiles include/vlscan.h as C: it has to parse as strict C99, and a C translation unit that takes the address of every
+    # declared entry point has to link against libvlscan.so with no C++ runtime on the command line
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    hdr = open(os.path.join(ROOT, "include", "vlscan.h")).read()
+    declared = sorted(set(re.findall(r"\b(vlscan_[a-z0-9_]+)\s*\(", hdr)))
+    src = tmp_path / "abi_check.c"
+    src.write_text("#include <stddef.h>\n#include <stdint.h>\n#include \"vlscan.h\"\n"
+                   "typedef void (*fn)(void);\nfn table[] = {\n"
+                   + "".join("  (fn)%s,\n" % n for n in declared) + "};\n"
+                   "int main(void) { return (int)(sizeof table / sizeof table[0]) == 0; }\n")
+    libdir = os.path.dirname(vs.lib()._name)
+    out = tmp_path / "abi_check"
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic",
+                        "-I", os.path.join(ROOT, "include"), str(src), "-o", str(out),
+                        "-L", libdir, "-l:libvlscan.so", "-Wl,--unresolved-symbols=ignore-in-shared-libs"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
 def test_struct_layouts_match_header():
     # sizes asserted against the C layout rules of include/vlscan.h (x86-64 SysV)
     assert C.sizeof(vs.CColumn) == 4 + 4 + 8 + 8 + 8 * 12
