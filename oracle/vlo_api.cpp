@@ -2,6 +2,7 @@
 // bench.py's cpu_baseline / --impl reference legs.
 #include "vlo_block.h"
 #include "vlo_gen.h"
+#include "vlo_part.h"
 #include <thread>
 #include <atomic>
 #include <chrono>
@@ -392,6 +393,175 @@ int vlo_bitmap_selftest(int max_bits) {
         for (int k = 0; k < i; k++) if (bm.is_set_bit((uint64_t)k) != (k % 3 != 0)) return fail(23);
     }
     return 0;
+}
+
+// ---- part files (vlo_part.h) -----------------------------------------------------------------------------------------------
+// Records travel as flat u64 arrays:
+//   blockHeader[15]      = accountID, projectID, id.hi, id.lo, uncompressedSizeBytes, rowsCount, th.blockOffset, th.blockSize, th.minTimestamp,
+//                          th.maxTimestamp, th.marshalType, columnsHeaderIndexOffset, columnsHeaderIndexSize, columnsHeaderOffset, columnsHeaderSize
+//   indexBlockHeader[8]  = accountID, projectID, id.hi, id.lo, minTimestamp, maxTimestamp, indexBlockOffset, indexBlockSize
+//   columnHeader[7]      = valueType, minValue, maxValue, valuesOffset, valuesSize, bloomFilterOffset, bloomFilterSize
+//   partHeader[8]        = FormatVersion, CompressedSizeBytes, UncompressedSizeBytes, RowsCount, BlocksCount, MinTimestamp, MaxTimestamp, BloomValuesShardsCount
+static void bh_from(const uint64_t* f, BlockHeader& b) {
+    b.streamID = StreamID{(uint32_t)f[0], (uint32_t)f[1], f[2], f[3]}; b.uncompressedSizeBytes = f[4]; b.rowsCount = f[5];
+    b.timestampsHeader.blockOffset = f[6]; b.timestampsHeader.blockSize = f[7]; b.timestampsHeader.minTimestamp = (int64_t)f[8]; b.timestampsHeader.maxTimestamp = (int64_t)f[9];
+    b.timestampsHeader.marshalType = (uint8_t)f[10]; b.columnsHeaderIndexOffset = f[11]; b.columnsHeaderIndexSize = f[12]; b.columnsHeaderOffset = f[13]; b.columnsHeaderSize = f[14];
+}
+static void bh_to(const BlockHeader& b, uint64_t* f) {
+    f[0] = b.streamID.accountID; f[1] = b.streamID.projectID; f[2] = b.streamID.hi; f[3] = b.streamID.lo; f[4] = b.uncompressedSizeBytes; f[5] = b.rowsCount;
+    f[6] = b.timestampsHeader.blockOffset; f[7] = b.timestampsHeader.blockSize; f[8] = (uint64_t)b.timestampsHeader.minTimestamp; f[9] = (uint64_t)b.timestampsHeader.maxTimestamp;
+    f[10] = b.timestampsHeader.marshalType; f[11] = b.columnsHeaderIndexOffset; f[12] = b.columnsHeaderIndexSize; f[13] = b.columnsHeaderOffset; f[14] = b.columnsHeaderSize;
+}
+static void ih_to(const IndexBlockHeader& h, uint64_t* f) {
+    f[0] = h.streamID.accountID; f[1] = h.streamID.projectID; f[2] = h.streamID.hi; f[3] = h.streamID.lo; f[4] = (uint64_t)h.minTimestamp; f[5] = (uint64_t)h.maxTimestamp; f[6] = h.indexBlockOffset; f[7] = h.indexBlockSize;
+}
+static void ch_from(const uint64_t* f, ColumnHeader& c) { c.valueType = (uint8_t)f[0]; c.minValue = f[1]; c.maxValue = f[2]; c.valuesOffset = f[3]; c.valuesSize = f[4]; c.bloomFilterOffset = f[5]; c.bloomFilterSize = f[6]; }
+static void ch_to(const ColumnHeader& c, uint64_t* f) { f[0] = c.valueType; f[1] = c.minValue; f[2] = c.maxValue; f[3] = c.valuesOffset; f[4] = c.valuesSize; f[5] = c.bloomFilterOffset; f[6] = c.bloomFilterSize; }
+static int64_t emit(const std::string& s, uint8_t* out, uint64_t cap) { if (s.size() > cap) throw std::runtime_error("output buffer too small"); memcpy(out, s.data(), s.size()); return (int64_t)s.size(); }
+
+int64_t vlo_part_marshal_block_header(const uint64_t* f15, uint8_t* out, uint64_t cap) {
+    int64_t r = -1; guard([&] { BlockHeader b; bh_from(f15, b); std::string s; b.marshal(s); r = emit(s, out, cap); }); return r;
+}
+// returns the number of records (validated like unmarshalBlockHeaders) or -1
+int64_t vlo_part_unmarshal_block_headers(const uint8_t* src, uint64_t n, unsigned format_version, uint64_t* out, uint64_t cap_records) {
+    int64_t r = -1;
+    guard([&] { auto v = unmarshal_block_headers(sv((const char*)src, n), format_version); if (v.size() > cap_records) throw std::runtime_error("output buffer too small");
+                for (size_t i = 0; i < v.size(); i++) bh_to(v[i], out + 15 * i);
+                r = (int64_t)v.size(); });
+    return r;
+}
+int64_t vlo_part_marshal_index_block_header(const uint64_t* f8, uint8_t* out, uint64_t cap) {
+    int64_t r = -1;
+    guard([&] { IndexBlockHeader h; h.streamID = StreamID{(uint32_t)f8[0], (uint32_t)f8[1], f8[2], f8[3]}; h.minTimestamp = (int64_t)f8[4]; h.maxTimestamp = (int64_t)f8[5]; h.indexBlockOffset = f8[6]; h.indexBlockSize = f8[7];
+                std::string s; h.marshal(s); r = emit(s, out, cap); });
+    return r;
+}
+int64_t vlo_part_unmarshal_index_block_headers(const uint8_t* src, uint64_t n, uint64_t* out, uint64_t cap_records) {
+    int64_t r = -1;
+    guard([&] { auto v = unmarshal_index_block_headers(sv((const char*)src, n)); if (v.size() > cap_records) throw std::runtime_error("output buffer too small");
+                for (size_t i = 0; i < v.size(); i++) ih_to(v[i], out + 8 * i);
+                r = (int64_t)v.size(); });
+    return r;
+}
+int64_t vlo_part_marshal_column_header(const uint64_t* f7, const uint8_t* dict_blob, const uint64_t* dict_offs, uint64_t ndict, uint8_t* out, uint64_t cap) {
+    int64_t r = -1;
+    guard([&] { ColumnHeader c; ch_from(f7, c); for (auto d : unpack(dict_blob, dict_offs, ndict)) c.dict.emplace_back(d); std::string s; c.marshal(s); r = emit(s, out, cap); });
+    return r;
+}
+// returns the bytes consumed or -1; dict values come back packed (dict_offs has room for 257 entries)
+int64_t vlo_part_unmarshal_column_header(const uint8_t* src, uint64_t n, unsigned format_version, uint64_t* f7, uint8_t* dict_out, uint64_t dict_cap, uint64_t* dict_offs, uint64_t* ndict) {
+    int64_t r = -1;
+    guard([&] { PReader rd(sv((const char*)src, n)); ColumnHeader c; c.unmarshal(rd, format_version); ch_to(c, f7);
+                std::string cat; dict_offs[0] = 0; for (size_t i = 0; i < c.dict.size(); i++) { cat += c.dict[i]; dict_offs[i + 1] = cat.size(); }
+                emit(cat, dict_out, dict_cap); *ndict = c.dict.size(); r = (int64_t)(n - rd.n); });
+    return r;
+}
+// refs: pairs (columnNameID, offset)
+int64_t vlo_part_marshal_columns_header_index(const uint64_t* refs, uint64_t nrefs, const uint64_t* crefs, uint64_t ncrefs, uint8_t* out, uint64_t cap) {
+    int64_t r = -1;
+    guard([&] { ColumnsHeaderIndex x; for (uint64_t i = 0; i < nrefs; i++) x.columnHeadersRefs.push_back({refs[2 * i], refs[2 * i + 1]}); for (uint64_t i = 0; i < ncrefs; i++) x.constColumnsRefs.push_back({crefs[2 * i], crefs[2 * i + 1]});
+                std::string s; x.marshal(s); r = emit(s, out, cap); });
+    return r;
+}
+int vlo_part_unmarshal_columns_header_index(const uint8_t* src, uint64_t n, uint64_t* refs, uint64_t* nrefs, uint64_t* crefs, uint64_t* ncrefs, uint64_t cap_pairs) {
+    return guard([&] { ColumnsHeaderIndex x; x.unmarshal(sv((const char*)src, n));
+                       if (x.columnHeadersRefs.size() > cap_pairs || x.constColumnsRefs.size() > cap_pairs) throw std::runtime_error("output buffer too small");
+                       for (size_t i = 0; i < x.columnHeadersRefs.size(); i++) { refs[2 * i] = x.columnHeadersRefs[i].columnNameID; refs[2 * i + 1] = x.columnHeadersRefs[i].offset; }
+                       for (size_t i = 0; i < x.constColumnsRefs.size(); i++) { crefs[2 * i] = x.constColumnsRefs[i].columnNameID; crefs[2 * i + 1] = x.constColumnsRefs[i].offset; }
+                       *nrefs = x.columnHeadersRefs.size(); *ncrefs = x.constColumnsRefs.size(); });
+}
+// columnsHeader.marshal with a fresh columnNameIDGenerator: names = ncols column names then nconst const-column names; values = nconst values.
+// Dict columns are not supported by this entry point.  out gets the columnsHeader, idx_out the columnsHeaderIndex.
+int64_t vlo_part_marshal_columns_header(uint64_t ncols, const uint64_t* f7s, const uint8_t* names_blob, const uint64_t* names_offs, uint64_t nconst, const uint8_t* vals_blob, const uint64_t* vals_offs,
+                                        uint8_t* out, uint64_t cap, uint8_t* idx_out, uint64_t idx_cap, uint64_t* idx_len) {
+    int64_t r = -1;
+    guard([&] { auto names = unpack(names_blob, names_offs, ncols + nconst); auto vals = unpack(vals_blob, vals_offs, nconst);
+                ColumnsHeader csh;
+                for (uint64_t i = 0; i < ncols; i++) { ColumnHeader c; ch_from(f7s + 7 * i, c); c.name = std::string(names[i]); csh.columnHeaders.push_back(c); }
+                for (uint64_t i = 0; i < nconst; i++) csh.constColumns.push_back({std::string(names[ncols + i]), std::string(vals[i])});
+                ColumnsHeaderIndex idx; ColumnNameIDGenerator g; std::string s, si; csh.marshal(s, idx, g); idx.marshal(si);
+                *idx_len = (uint64_t)emit(si, idx_out, idx_cap); r = emit(s, out, cap); });
+    return r;
+}
+// unmarshals a columnsHeader + its index, resolves names, marshals both again and reports whether the bytes are identical (1), differ (0) or are malformed (-1).
+// The names come back joined by '\0' (columns first, then const columns).
+int vlo_part_columns_header_roundtrip(const uint8_t* src, uint64_t n, const uint8_t* idx_src, uint64_t idx_n, const uint8_t* names_blob, const uint64_t* names_offs, uint64_t nnames,
+                                      char* names_out, uint64_t names_cap, uint64_t* names_len) {
+    int same = -1;
+    guard([&] { std::vector<std::string> names; for (auto s : unpack(names_blob, names_offs, nnames)) names.emplace_back(s);
+                ColumnsHeader csh; csh.unmarshal(sv((const char*)src, n), partFormatLatestVersion);
+                ColumnsHeaderIndex idx; idx.unmarshal(sv((const char*)idx_src, idx_n)); csh.set_column_names(idx, names);
+                ColumnNameIDGenerator g; for (auto& s : names) g.get(s);
+                ColumnsHeaderIndex idx2; std::string s, si; csh.marshal(s, idx2, g); idx2.marshal(si);
+                std::string cat; for (auto& c : csh.columnHeaders) { cat += c.name; cat.push_back('\0'); } for (auto& c : csh.constColumns) { cat += c.name; cat.push_back('\0'); }
+                *names_len = (uint64_t)emit(cat, (uint8_t*)names_out, names_cap);
+                same = s == std::string((const char*)src, n) && si == std::string((const char*)idx_src, idx_n); });
+    return same;
+}
+int64_t vlo_part_header_json(const uint64_t* f8, char* out, uint64_t cap) {
+    int64_t r = -1;
+    guard([&] { PartHeader ph; ph.FormatVersion = f8[0]; ph.CompressedSizeBytes = f8[1]; ph.UncompressedSizeBytes = f8[2]; ph.RowsCount = f8[3]; ph.BlocksCount = f8[4]; ph.MinTimestamp = (int64_t)f8[5];
+                ph.MaxTimestamp = (int64_t)f8[6]; ph.BloomValuesShardsCount = f8[7]; r = emit(ph.to_json(), (uint8_t*)out, cap); });
+    return r;
+}
+static void ph_to(const PartHeader& ph, uint64_t* f) {
+    f[0] = ph.FormatVersion; f[1] = ph.CompressedSizeBytes; f[2] = ph.UncompressedSizeBytes; f[3] = ph.RowsCount; f[4] = ph.BlocksCount; f[5] = (uint64_t)ph.MinTimestamp; f[6] = (uint64_t)ph.MaxTimestamp; f[7] = ph.BloomValuesShardsCount;
+}
+int vlo_part_header_parse(const char* json, uint64_t n, uint64_t* f8) { return guard([&] { ph_to(PartHeader::from_json(sv(json, n)), f8); }); }
+
+struct PartWriterHandle { PartWriter w; std::vector<const std::string*> names; };
+struct PartReaderHandle { PartFiles files; PartReader r; std::vector<BlockHeader> bhs; };
+
+void* vlo_part_writer_new(uint64_t max_index_block, uint64_t max_shards) {
+    auto* h = new PartWriterHandle; if (max_index_block) h->w.maxIndexBlock = max_index_block; if (max_shards) h->w.maxShards = max_shards; return h;
+}
+void vlo_part_writer_free(void* h) { delete (PartWriterHandle*)h; }
+int vlo_part_writer_add_block(void* h, const uint64_t* sid4, void* block, uint64_t uncompressed_size) {
+    return guard([&] { ((PartWriterHandle*)h)->w.write_block(StreamID{(uint32_t)sid4[0], (uint32_t)sid4[1], sid4[2], sid4[3]}, ((BlockHandle*)block)->b, uncompressed_size); });
+}
+int vlo_part_writer_finalize(void* h, uint64_t* f8) { return guard([&] { auto& w = ((PartWriterHandle*)h)->w; w.finalize(); ph_to(w.ph, f8); }); }
+uint64_t vlo_part_writer_nfiles(void* h) { return ((PartWriterHandle*)h)->w.files.size(); }
+void vlo_part_writer_file(void* h, uint64_t i, const char** name, uint64_t* name_len, const uint8_t** data, uint64_t* len) {
+    auto it = ((PartWriterHandle*)h)->w.files.begin(); std::advance(it, (long)i);
+    *name = it->first.data(); *name_len = it->first.size(); *data = (const uint8_t*)it->second.data(); *len = it->second.size();
+}
+// opens a part given as packed (file name, contents) lists; reads every index block up front
+void* vlo_part_reader_open(const uint8_t* names_blob, const uint64_t* names_offs, const uint8_t* data_blob, const uint64_t* data_offs, uint64_t nfiles) {
+    PartReaderHandle* h = new PartReaderHandle;
+    if (guard([&] { auto names = unpack(names_blob, names_offs, nfiles); auto datas = unpack(data_blob, data_offs, nfiles);
+                    for (uint64_t i = 0; i < nfiles; i++) h->files[std::string(names[i])] = std::string(datas[i]);
+                    h->r.open(h->files);
+                    for (auto& ih : h->r.indexBlockHeaders) { auto v = h->r.read_index_block(ih); h->bhs.insert(h->bhs.end(), v.begin(), v.end()); }
+                    if (h->bhs.size() != h->r.ph.BlocksCount) throw PartError("the number of block headers differs from partHeader.BlocksCount");
+                    uint64_t rows = 0; for (auto& b : h->bhs) rows += b.rowsCount;
+                    if (rows != h->r.ph.RowsCount) throw PartError("the number of rows differs from partHeader.RowsCount"); })) { delete h; return nullptr; }
+    return h;
+}
+void vlo_part_reader_free(void* h) { delete (PartReaderHandle*)h; }
+void vlo_part_reader_header(void* h, uint64_t* f8) { ph_to(((PartReaderHandle*)h)->r.ph, f8); }
+uint64_t vlo_part_reader_nindex(void* h) { return ((PartReaderHandle*)h)->r.indexBlockHeaders.size(); }
+void vlo_part_reader_index_header(void* h, uint64_t i, uint64_t* f8) { ih_to(((PartReaderHandle*)h)->r.indexBlockHeaders[i], f8); }
+uint64_t vlo_part_reader_nblocks(void* h) { return ((PartReaderHandle*)h)->bhs.size(); }
+void vlo_part_reader_block_header(void* h, uint64_t i, uint64_t* f15) { bh_to(((PartReaderHandle*)h)->bhs[i], f15); }
+void* vlo_part_reader_block(void* h, uint64_t i) {
+    BlockHandle* b = nullptr; auto* p = (PartReaderHandle*)h;
+    if (guard([&] { b = new BlockHandle{p->r.read_block(p->bhs.at(i))}; })) return nullptr;
+    return b;
+}
+// column names joined by '\0', in columnNameID order
+int64_t vlo_part_reader_column_names(void* h, char* out, uint64_t cap) {
+    int64_t r = -1; guard([&] { std::string cat; for (auto& s : ((PartReaderHandle*)h)->r.columnNames) { cat += s; cat.push_back('\0'); } r = emit(cat, (uint8_t*)out, cap); }); return r;
+}
+// blockSearch.getColumnHeader: 1 found, 0 no such column in the block, -1 error
+int vlo_part_reader_column_header(void* h, uint64_t i, const char* name, uint64_t name_len, uint64_t* f7) {
+    int found = -1; auto* p = (PartReaderHandle*)h;
+    guard([&] { ColumnHeader c; bool ok = p->r.get_column_header(p->bhs.at(i), sv(name, name_len), &c); if (ok) ch_to(c, f7); found = ok; });
+    return found;
+}
+int64_t vlo_part_reader_const_value(void* h, uint64_t i, const char* name, uint64_t name_len, char* out, uint64_t cap) {
+    int64_t r = -1; auto* p = (PartReaderHandle*)h;
+    guard([&] { r = emit(p->r.get_const_column_value(p->bhs.at(i), sv(name, name_len)), (uint8_t*)out, cap); });
+    return r;
 }
 
 }  // extern "C"

@@ -489,3 +489,264 @@ def scan_generated(cfg, flt, block_lo, block_hi, threads, want_counts=False, pas
     if r:
         raise _err()
     return dict(secs=secs.value, passes=passes, stats=stats, digest=dig.value, matches=tot.value, counts=counts)
+
+
+# ---- part files (oracle/vlo_part.h) --------------------------------------------------------------------------------------
+BLOCK_HEADER_FIELDS = ("account_id", "project_id", "id_hi", "id_lo", "uncompressed_size_bytes", "rows_count", "ts_block_offset", "ts_block_size",
+                       "min_timestamp", "max_timestamp", "ts_marshal_type", "columns_header_index_offset", "columns_header_index_size",
+                       "columns_header_offset", "columns_header_size")
+INDEX_BLOCK_HEADER_FIELDS = ("account_id", "project_id", "id_hi", "id_lo", "min_timestamp", "max_timestamp", "index_block_offset", "index_block_size")
+COLUMN_HEADER_FIELDS = ("value_type", "min_value", "max_value", "values_offset", "values_size", "bloom_filter_offset", "bloom_filter_size")
+PART_HEADER_FIELDS = ("FormatVersion", "CompressedSizeBytes", "UncompressedSizeBytes", "RowsCount", "BlocksCount", "MinTimestamp", "MaxTimestamp",
+                      "BloomValuesShardsCount")
+_SIGNED = {"min_timestamp", "max_timestamp", "MinTimestamp", "MaxTimestamp"}
+
+
+def _to_u64s(fields, d):
+    return np.array([int(d.get(k, 0)) & 0xFFFFFFFFFFFFFFFF for k in fields], dtype=np.uint64)
+
+
+def _from_u64s(fields, a):
+    out = {}
+    for k, v in zip(fields, a):
+        v = int(v)
+        out[k] = v - (1 << 64) if k in _SIGNED and v >= 1 << 63 else v
+    return out
+
+
+def _i64(fn, *args):
+    fn.restype = C.c_int64
+    r = fn(*args)
+    if r < 0:
+        raise _err()
+    return r
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def marshal_block_header(**f):
+    out = C.create_string_buffer(256)
+    a = _to_u64s(BLOCK_HEADER_FIELDS, f)
+    n = _i64(lib().vlo_part_marshal_block_header, _ptr(a), out, C.c_uint64(256))
+    return out.raw[:n]
+
+
+def unmarshal_block_headers(data, format_version=3):
+    data = bytes(data)
+    cap = len(data) // 30 + 1
+    out = np.zeros(cap * 15, dtype=np.uint64)
+    n = _i64(lib().vlo_part_unmarshal_block_headers, data, C.c_uint64(len(data)), C.c_uint(format_version), _ptr(out), C.c_uint64(cap))
+    return [_from_u64s(BLOCK_HEADER_FIELDS, out[15 * i:15 * i + 15]) for i in range(n)]
+
+
+def marshal_index_block_header(**f):
+    out = C.create_string_buffer(64)
+    a = _to_u64s(INDEX_BLOCK_HEADER_FIELDS, f)
+    n = _i64(lib().vlo_part_marshal_index_block_header, _ptr(a), out, C.c_uint64(64))
+    return out.raw[:n]
+
+
+def unmarshal_index_block_headers(data):
+    data = bytes(data)
+    cap = len(data) // 56 + 1
+    out = np.zeros(cap * 8, dtype=np.uint64)
+    n = _i64(lib().vlo_part_unmarshal_index_block_headers, data, C.c_uint64(len(data)), _ptr(out), C.c_uint64(cap))
+    return [_from_u64s(INDEX_BLOCK_HEADER_FIELDS, out[8 * i:8 * i + 8]) for i in range(n)]
+
+
+def marshal_column_header(dict_values=(), **f):
+    out = C.create_string_buffer(4096)
+    a = _to_u64s(COLUMN_HEADER_FIELDS, f)
+    db, do = _pack(dict_values)
+    n = _i64(lib().vlo_part_marshal_column_header, _ptr(a), db, _ptr(do), C.c_uint64(len(dict_values)), out, C.c_uint64(4096))
+    return out.raw[:n]
+
+
+def unmarshal_column_header(data, format_version=3):
+    """-> (fields dict incl. 'dict', bytes consumed)"""
+    data = bytes(data)
+    f7 = np.zeros(7, dtype=np.uint64)
+    dbuf = C.create_string_buffer(len(data) + 1)
+    doffs = np.zeros(257, dtype=np.uint64)
+    nd = C.c_uint64()
+    used = _i64(lib().vlo_part_unmarshal_column_header, data, C.c_uint64(len(data)), C.c_uint(format_version), _ptr(f7), dbuf, C.c_uint64(len(data) + 1), _ptr(doffs), C.byref(nd))
+    d = _from_u64s(COLUMN_HEADER_FIELDS, f7)
+    d["dict"] = [dbuf.raw[int(doffs[i]):int(doffs[i + 1])] for i in range(nd.value)]
+    return d, used
+
+
+def marshal_columns_header_index(refs, const_refs):
+    """refs / const_refs: lists of (columnNameID, offset)"""
+    a = np.array([x for r in refs for x in r], dtype=np.uint64)
+    b = np.array([x for r in const_refs for x in r], dtype=np.uint64)
+    cap = 20 * (len(refs) + len(const_refs)) + 20
+    out = C.create_string_buffer(cap)
+    n = _i64(lib().vlo_part_marshal_columns_header_index, _ptr(a), C.c_uint64(len(refs)), _ptr(b), C.c_uint64(len(const_refs)), out, C.c_uint64(cap))
+    return out.raw[:n]
+
+
+def unmarshal_columns_header_index(data):
+    data = bytes(data)
+    cap = len(data) + 1
+    a, b = np.zeros(2 * cap, dtype=np.uint64), np.zeros(2 * cap, dtype=np.uint64)
+    na, nb = C.c_uint64(), C.c_uint64()
+    if lib().vlo_part_unmarshal_columns_header_index(data, C.c_uint64(len(data)), _ptr(a), C.byref(na), _ptr(b), C.byref(nb), C.c_uint64(cap)):
+        raise _err()
+    return ([(int(a[2 * i]), int(a[2 * i + 1])) for i in range(na.value)], [(int(b[2 * i]), int(b[2 * i + 1])) for i in range(nb.value)])
+
+
+def marshal_columns_header(columns, const_columns):
+    """columns: list of (name, fields dict without dict values); const_columns: list of (name, value) -> (columnsHeader bytes, columnsHeaderIndex bytes)"""
+    f = np.concatenate([_to_u64s(COLUMN_HEADER_FIELDS, c[1]) for c in columns]) if columns else np.zeros(0, dtype=np.uint64)
+    nb, no = _pack([c[0] for c in columns] + [c[0] for c in const_columns])
+    vb, vo = _pack([c[1] for c in const_columns])
+    cap = 64 * len(columns) + sum(len(_b(c[1])) + 16 for c in const_columns) + 64
+    out, idx = C.create_string_buffer(cap), C.create_string_buffer(cap)
+    il = C.c_uint64()
+    n = _i64(lib().vlo_part_marshal_columns_header, C.c_uint64(len(columns)), _ptr(f), nb, _ptr(no), C.c_uint64(len(const_columns)), vb, _ptr(vo),
+             out, C.c_uint64(cap), idx, C.c_uint64(cap), C.byref(il))
+    return out.raw[:n], idx.raw[:il.value]
+
+
+def columns_header_roundtrip(csh, idx, names):
+    """unmarshal + setColumnNames + marshal again -> (bytes identical?, resolved names: columns then const columns)"""
+    csh, idx = bytes(csh), bytes(idx)
+    nb, no = _pack(names)
+    cap = sum(len(_b(x)) + 1 for x in names) * 4 + len(csh) * 260 + 64
+    out = C.create_string_buffer(cap)
+    ol = C.c_uint64()
+    r = lib().vlo_part_columns_header_roundtrip(csh, C.c_uint64(len(csh)), idx, C.c_uint64(len(idx)), nb, _ptr(no), C.c_uint64(len(names)), out, C.c_uint64(cap), C.byref(ol))
+    if r < 0:
+        raise _err()
+    return bool(r), out.raw[:ol.value].split(b"\0")[:-1]
+
+
+def part_header_json(**f):
+    out = C.create_string_buffer(512)
+    a = _to_u64s(PART_HEADER_FIELDS, f)
+    n = _i64(lib().vlo_part_header_json, _ptr(a), out, C.c_uint64(512))
+    return out.raw[:n]
+
+
+def part_header_parse(text):
+    text = _b(text)
+    f8 = np.zeros(8, dtype=np.uint64)
+    if lib().vlo_part_header_parse(text, C.c_uint64(len(text)), _ptr(f8)):
+        raise _err()
+    return _from_u64s(PART_HEADER_FIELDS, f8)
+
+
+class PartWriter:
+    """blockStreamWriter for a file part: add blocks in (streamID, minTimestamp) order, then finalize() -> {file name: bytes}."""
+
+    def __init__(self, max_index_block=0, max_shards=0):
+        L = lib()
+        L.vlo_part_writer_new.restype = C.c_void_p
+        L.vlo_part_writer_nfiles.restype = C.c_uint64
+        self.h = C.c_void_p(L.vlo_part_writer_new(C.c_uint64(max_index_block), C.c_uint64(max_shards)))
+        self.header = None
+
+    def __del__(self):
+        try:
+            lib().vlo_part_writer_free(self.h)
+        except Exception:
+            pass
+
+    def add_block(self, stream_id, block, uncompressed_size=0):
+        """stream_id: (accountID, projectID, hi, lo)"""
+        sid = np.array(stream_id, dtype=np.uint64)
+        if lib().vlo_part_writer_add_block(self.h, _ptr(sid), block.h, C.c_uint64(uncompressed_size)):
+            raise _err()
+
+    def finalize(self):
+        L = lib()
+        f8 = np.zeros(8, dtype=np.uint64)
+        if L.vlo_part_writer_finalize(self.h, _ptr(f8)):
+            raise _err()
+        self.header = _from_u64s(PART_HEADER_FIELDS, f8)
+        files = {}
+        for i in range(L.vlo_part_writer_nfiles(self.h)):
+            n, nl, d, dl = C.c_void_p(), C.c_uint64(), C.c_void_p(), C.c_uint64()
+            L.vlo_part_writer_file(self.h, C.c_uint64(i), C.byref(n), C.byref(nl), C.byref(d), C.byref(dl))
+            files[C.string_at(n, nl.value).decode()] = C.string_at(d, dl.value)
+        return files
+
+
+def save_part(files, path):
+    os.makedirs(path, exist_ok=False)      # fs.MustMkdirFailIfExist
+    for name, data in files.items():
+        with open(os.path.join(path, name), "wb") as f:
+            f.write(data)
+
+
+def load_part(path):
+    return {name: open(os.path.join(path, name), "rb").read() for name in sorted(os.listdir(path))}
+
+
+class PartReader:
+    """part.mustOpenFilePart + the block access of blockSearch, over {file name: bytes}."""
+
+    def __init__(self, files):
+        L = lib()
+        L.vlo_part_reader_open.restype = C.c_void_p
+        L.vlo_part_reader_block.restype = C.c_void_p
+        for name in ("vlo_part_reader_nindex", "vlo_part_reader_nblocks"):
+            getattr(L, name).restype = C.c_uint64
+        names = sorted(files)
+        nb, no = _pack(names)
+        db, do = _pack([files[k] for k in names])
+        h = L.vlo_part_reader_open(nb, _ptr(no), db, _ptr(do), C.c_uint64(len(names)))
+        if not h:
+            raise _err()
+        self.h = C.c_void_p(h)
+        f8 = np.zeros(8, dtype=np.uint64)
+        L.vlo_part_reader_header(self.h, _ptr(f8))
+        self.header = _from_u64s(PART_HEADER_FIELDS, f8)
+        self.nblocks = L.vlo_part_reader_nblocks(self.h)
+        cap = sum(len(v) for v in files.values()) * 300 + 1024
+        out = C.create_string_buffer(cap)
+        n = _i64(L.vlo_part_reader_column_names, self.h, out, C.c_uint64(cap))
+        self.column_names = out.raw[:n].split(b"\0")[:-1]
+
+    def __del__(self):
+        try:
+            lib().vlo_part_reader_free(self.h)
+        except Exception:
+            pass
+
+    def index_block_headers(self):
+        L = lib()
+        res = []
+        for i in range(L.vlo_part_reader_nindex(self.h)):
+            f8 = np.zeros(8, dtype=np.uint64)
+            L.vlo_part_reader_index_header(self.h, C.c_uint64(i), _ptr(f8))
+            res.append(_from_u64s(INDEX_BLOCK_HEADER_FIELDS, f8))
+        return res
+
+    def block_header(self, i):
+        f = np.zeros(15, dtype=np.uint64)
+        lib().vlo_part_reader_block_header(self.h, C.c_uint64(i), _ptr(f))
+        return _from_u64s(BLOCK_HEADER_FIELDS, f)
+
+    def block(self, i):
+        h = lib().vlo_part_reader_block(self.h, C.c_uint64(i))
+        if not h:
+            raise _err()
+        return Block(h)
+
+    def column_header(self, i, name):
+        """blockSearch.getColumnHeader -> fields dict or None"""
+        name = _b(name)
+        f7 = np.zeros(7, dtype=np.uint64)
+        r = lib().vlo_part_reader_column_header(self.h, C.c_uint64(i), name, C.c_uint64(len(name)), _ptr(f7))
+        if r < 0:
+            raise _err()
+        return _from_u64s(COLUMN_HEADER_FIELDS, f7) if r else None
+
+    def const_value(self, i, name):
+        name = _b(name)
+        out = C.create_string_buffer(1 << 16)
+        n = _i64(lib().vlo_part_reader_const_value, self.h, C.c_uint64(i), name, C.c_uint64(len(name)), out, C.c_uint64(1 << 16))
+        return out.raw[:n]
