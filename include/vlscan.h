@@ -196,6 +196,13 @@ int vlscan_zstd_decompress(vlscan_ctx* ctx, uint32_t nframes, const void* const*
  * out[0] = bytes consumed, out[1] = regenerated length, out[2] = ZSTD blocks, out[3] = compressed blocks, out[4] = sequences.
  * Returns <0 with an error text for malformed input.  For tests (the walker parses untrusted bytes). */
 int vlscan_zstd_inspect(const void* bytes_block, size_t len, uint64_t out[5]);
+/* The same walk over every VLSCAN_STAGE_ONDISK column of `nblocks` blocks, as vlscan_batch_upload / vlscan_scan_batch run it, on
+ * `threads` host threads (0: one block after the other on the calling thread; uploads use $VLSCAN_HOST_THREADS, default min(16, cores)).
+ * out[0..3] = digest of everything the walk hands to the device (frame table, ZSTD block table with scratch offsets and table slots,
+ * launch groups, work lists): the same for every thread count.  out[4] = frames, out[5] = ZSTD blocks, out[6] = launch groups,
+ * out[7] = compressed blocks, out[8] = sequences, out[9] / out[10] = nanoseconds spent walking / building the work lists, out[11] = 0.
+ * No device needed.  For tests and host-side tuning. */
+int vlscan_zstd_walk_digest(const vlscan_block* blocks, uint64_t nblocks, int threads, uint64_t out[12]);
 
 /* ---- the scan ---------------------------------------------------------------------------------------------------- */
 /* Scan a resident batch: equivalent of `for each block: bm.init(rows); bm.setBits(); filter.applyToBlockSearch(bs, bm)`

@@ -207,3 +207,26 @@ def test_ondisk_stage_equals_decoded_stage(ctx):
         assert np.array_equal(w1, w2) and np.array_equal(c1, c2)
         assert s1.rows_matched == s2.rows_matched and s1.values_bytes == s2.values_bytes
         assert s2.h2d_bytes < s1.h2d_bytes / 2
+
+
+def test_ondisk_upload_is_independent_of_host_threads(ctx, monkeypatch):
+    """The header walk of an upload runs on $VLSCAN_HOST_THREADS threads (0 = block by block on the caller's thread): same tables, same bitmaps."""
+    vs, cx = ctx
+    nb = 700                                                 # 2800 values blocks: 11 shards at the default 16 threads
+    cfg = vs.GenConfig(seed=77, total_rows=nb * 3000, rows_per_block=3000, hot_block_permille=500, hit_row_permille=60, columns_mask=0xF)
+    batch = cx.generate(cfg, 0, nb)
+    host = vs.DownloadedBlocks(cx, batch)
+    disk = host.compress()
+    prog = vs.Program(vs.Filter.and_([vs.Filter.phrase("_msg", "timeout"), vs.Filter.phrase("level", "error")]))
+    w0, c0, s0 = cx.scan_batch(prog, host)
+    digests = set()
+    for threads in ("0", "1", "3", "16", None):
+        if threads is None:
+            monkeypatch.delenv("VLSCAN_HOST_THREADS", raising=False)
+        else:
+            monkeypatch.setenv("VLSCAN_HOST_THREADS", threads)
+            digests.add(vs.zstd_walk_digest(disk, int(threads))["digest"])
+        w, c, s = cx.scan_batch(prog, disk)
+        assert np.array_equal(w, w0) and np.array_equal(c, c0) and s.rows_matched == s0.rows_matched, threads
+    assert len(digests) == 1
+    assert int(c0.sum()) > 0

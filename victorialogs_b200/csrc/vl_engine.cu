@@ -130,6 +130,26 @@ void finish_batch_layout(vlscan_ctx* ctx, vlscan_batch* b, const std::vector<uin
 }  // namespace vl
 
 // ---- upload --------------------------------------------------------------------------------------------------------------
+// The on-disk values blocks of a batch in (block, column) order; each one's place in the compressed staging buffer is a running sum that
+// starts behind 512 bytes of headroom (the device bit readers load whole aligned words around a stream).  Returns the end of the last one.
+static uint64_t collect_values_blocks(const vlscan_block* blocks, uint64_t nblocks, std::vector<ZValuesBlock>& zv) {
+    uint64_t zc = 512;
+    for (uint64_t b = 0; b < nblocks; b++)
+        for (uint32_t k = 0; k < blocks[b].ncols; k++) {
+            const vlscan_column& c = blocks[b].cols[k];
+            if (c.kind != VLSCAN_COL_VALUES || c.stage != VLSCAN_STAGE_ONDISK) continue;
+            zv.push_back({c.values, (size_t)c.values_len, zc});
+            zc += c.values_len;
+        }
+    return zc;
+}
+// Host threads for the header walk and the descriptor tables of an upload: VLSCAN_HOST_THREADS, else up to 16 (one process per GPU shares the
+// box with its peers).  0 selects the single-threaded block-by-block walk.
+static int host_threads() {
+    if (const char* e = getenv("VLSCAN_HOST_THREADS")) return std::max(0, std::min(256, atoi(e)));
+    return (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+}
+
 static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const size_t* field_name_lens, uint32_t nfields, const vlscan_block* blocks,
                       uint64_t nblocks, vlscan_batch* out, vlscan_stats* stats) {
     VL_CUDA(cudaSetDevice(ctx->device));
@@ -151,7 +171,7 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
     // regenerates them (vl_zstd.cuh) into arena regions placed behind everything that is copied, so that host memory laid out like
     // the copied part still goes out as one DMA.  Region offsets are relative to `regen_base` until the loop below has sized that part.
     ZstdJob zjob;
-    uint64_t zcursor = 512, regen_cursor = 0;   // headroom: the bit readers load whole aligned words around a stream
+    uint64_t regen_cursor = 0;
     struct Ondisk { uint64_t col; uint32_t lens_frame, data_frame; uint64_t lens_rel, data_rel; };
     std::vector<Ondisk> ondisk;
     std::vector<OndiskCol> ocols;
@@ -230,17 +250,15 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
     flush();
     };
     // Pre-pass: the compressed bytes of on-disk values blocks are shipped first (their place in the staging buffer is a running sum), so
-    // that the DMA engine is busy while the host walks frame and block headers in the loop below.
+    // that the DMA engine is busy while the host walks frame and block headers.
+    std::vector<ZValuesBlock> zv; std::vector<ZValuesInfo> zinfo; size_t zbad = SIZE_MAX, zo = 0; std::string zmsg;
     {
-        uint64_t zc = 512;
-        for (uint64_t b = 0; b < nblocks; b++)
-            for (uint32_t k = 0; k < blocks[b].ncols; k++) {
-                const vlscan_column& c = blocks[b].cols[k];
-                if (c.kind != VLSCAN_COL_VALUES || c.stage != VLSCAN_STAGE_ONDISK) continue;
-                if (c.values_len) zpieces.push_back({c.values, c.values_len, zc});
-                zc += c.values_len;
-            }
+        const uint64_t zc = collect_values_blocks(blocks, nblocks, zv);
+        for (const ZValuesBlock& v : zv) if (v.n) zpieces.push_back({v.p, v.n, v.zoff});
         if (!zpieces.empty()) { ctx->zsrc.ensure(zc + 512); marking = true; copy_pieces(zpieces, ctx->zsrc.as<uint8_t>()); marking = false; }
+        // frame, block and section headers of all of them, on several host threads; a malformed block is reported when the loop below gets to it
+        zinfo.resize(zv.size());
+        if (!zv.empty()) zjob.add_values_blocks(zv.data(), zv.size(), host_threads(), zinfo.data(), &zbad, &zmsg);
     }
     for (uint64_t b = 0; b < nblocks; b++) {
         const vlscan_block& blk = blocks[b];
@@ -261,11 +279,10 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
             if (c.stage == VLSCAN_STAGE_ONDISK) {
                 // stringsBlockUnmarshaler.unmarshal: bytesBlock(lens) ++ bytesBlock(data) (encoding.go:83-108).  The host reads the
                 // containers, the frame header and the block headers; the payload is regenerated on the device.
-                const uint64_t zoff = zcursor; zcursor += c.values_len;
-                uint64_t lens_len = 0, data_len = 0; uint32_t f1 = 0, f2 = 0;
-                size_t c1 = zjob.add_bytes_block(c.values, c.values_len, zoff, &lens_len, &f1);
-                size_t c2 = zjob.add_bytes_block(c.values + c1, c.values_len - c1, zoff + c1, &data_len, &f2);
-                if (c1 + c2 != c.values_len) throw BadInput("unexpected non-empty tail after reading bytes block with strings");
+                if (zo == zbad) throw BadInput(zmsg);
+                const uint64_t lens_len = zinfo[zo].lens_len, data_len = zinfo[zo].data_len;
+                const uint32_t f1 = (uint32_t)(2 * zo), f2 = f1 + 1;
+                zo++;
                 if (data_len > 0xFFFFFFFFull) throw BadInput("values block too large");
                 // the uint block type byte lands on offset 15 of its region, so the lens items behind it are 16-byte aligned
                 const uint64_t lr = arena_reserve(regen_cursor, lens_len + 15), dr = arena_reserve(regen_cursor, data_len);
@@ -800,6 +817,27 @@ int vlscan_zstd_inspect(const void* bytes_block, size_t len, uint64_t out[5]) {
         uint64_t regen = 0; uint32_t id = 0;
         size_t used = job.add_bytes_block((const uint8_t*)bytes_block, len, 512, &regen, &id);
         out[0] = used; out[1] = regen; out[2] = job.blocks(); out[3] = job.compressed_blocks(); out[4] = job.sequences();
+    });
+}
+
+int vlscan_zstd_walk_digest(const vlscan_block* blocks, uint64_t nblocks, int threads, uint64_t out[12]) {
+    return guarded(nullptr, [&] {
+        auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        std::vector<ZValuesBlock> zv;
+        collect_values_blocks(blocks, nblocks, zv);
+        std::vector<ZValuesInfo> info(zv.size());
+        ZstdJob job; size_t bad = SIZE_MAX; std::string msg;
+        const double t0 = now();
+        if (!zv.empty()) job.add_values_blocks(zv.data(), zv.size(), threads, info.data(), &bad, &msg);
+        const double t1 = now();
+        if (bad != SIZE_MAX) throw BadInput("values block " + std::to_string(bad) + ": " + msg);
+        job.prepare();
+        const double t2 = now();
+        job.digest(out);
+        uint64_t h = 5; for (const ZValuesInfo& x : info) { h = (h ^ x.lens_len) * 0x9E3779B97F4A7C15ull; h = (h ^ x.data_len) * 0x9E3779B97F4A7C15ull; h ^= h >> 29; }
+        out[0] ^= h;
+        out[4] = job.frames(); out[5] = job.blocks(); out[6] = job.groups(); out[7] = job.compressed_blocks(); out[8] = job.sequences();
+        out[9] = (uint64_t)((t1 - t0) * 1e9); out[10] = (uint64_t)((t2 - t1) * 1e9); out[11] = 0;
     });
 }
 

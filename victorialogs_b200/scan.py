@@ -68,7 +68,7 @@ EXPORTS = ["vlscan_device_count", "vlscan_ctx_create", "vlscan_ctx_free", "vlsca
            "vlscan_program_create", "vlscan_program_free", "vlscan_program_nfields", "vlscan_program_field", "vlscan_program_leaf_tokens", "vlscan_format_float64", "vlscan_eval_predicate",
            "vlscan_batch_upload", "vlscan_batch_free", "vlscan_batch_nblocks", "vlscan_batch_rows", "vlscan_batch_words", "vlscan_batch_device_bytes",
            "vlscan_batch_generate", "vlscan_batch_download", "vlscan_host_blocks_get", "vlscan_host_blocks_field", "vlscan_host_blocks_bytes",
-           "vlscan_host_blocks_free", "vlscan_host_blocks_compress", "vlscan_zstd_decompress", "vlscan_zstd_inspect", "vlscan_scan_resident", "vlscan_last_scan_stats", "vlscan_fetch_results", "vlscan_fetch_hits", "vlscan_result_device_ptrs", "vlscan_scan_batch"]
+           "vlscan_host_blocks_free", "vlscan_host_blocks_compress", "vlscan_zstd_decompress", "vlscan_zstd_inspect", "vlscan_zstd_walk_digest", "vlscan_scan_resident", "vlscan_last_scan_stats", "vlscan_fetch_results", "vlscan_fetch_hits", "vlscan_result_device_ptrs", "vlscan_scan_batch"]
 
 
 def lib_path():
@@ -121,6 +121,17 @@ def zstd_inspect(bytes_block):
     if rc:
         raise VlscanError(rc, lib().vlscan_last_error(None).decode("utf-8", "replace"))
     return dict(consumed=out[0], regenerated=out[1], blocks=out[2], compressed_blocks=out[3], sequences=out[4])
+
+
+def zstd_walk_digest(host_blocks, threads):
+    """Host-side header walk over every on-disk column of a HostBlocks / DownloadedBlocks (vlscan_zstd_walk_digest)
+    -> dict(digest=(4 ints), frames, blocks, groups, compressed_blocks, sequences, walk_seconds, lists_seconds)."""
+    out = (C.c_uint64 * 12)()
+    rc = lib().vlscan_zstd_walk_digest(host_blocks.blocks, C.c_uint64(host_blocks.nblocks), C.c_int(threads), out)
+    if rc:
+        raise VlscanError(rc, lib().vlscan_last_error(None).decode("utf-8", "replace"))
+    return dict(digest=tuple(out[:4]), frames=out[4], blocks=out[5], groups=out[6], compressed_blocks=out[7], sequences=out[8],
+                walk_seconds=out[9] * 1e-9, lists_seconds=out[10] * 1e-9)
 
 
 def format_float64(bits):
@@ -272,11 +283,17 @@ class HostBlocks:
         self.nblocks = len(blocks)
         k = 0
 
+        seen = {}
+
         def buf(data):
             data = bytes(data)
+            hit = seen.get(id(data))       # the same bytes object described twice (repeated blocks) is staged once
+            if hit is not None:
+                return hit
             a = C.create_string_buffer(data, len(data)) if data else C.create_string_buffer(1)
-            self._keep.append(a)
-            return C.cast(a, C.c_void_p), len(data)
+            self._keep.append((a, data))
+            seen[id(data)] = (C.cast(a, C.c_void_p), len(data))
+            return seen[id(data)]
 
         for bi, blk in enumerate(blocks):
             first = k
