@@ -256,6 +256,8 @@ def main():
                 t_comp = time.perf_counter() - t1
                 del host
                 host = disk
+            # host threads the library may use inside an upload (ZSTD header walk); the ranks of a box share its cores
+            os.environ.setdefault("VLSCAN_HOST_THREADS", str(max(1, min(32, (os.cpu_count() or 1) // world))))
             nwords = sum((r + 63) // 64 for r in host.rows)
             words = np.zeros(max(nwords, 1), dtype=np.uint64)
             counts = np.zeros(max(host.nblocks, 1), dtype=np.uint32)
@@ -274,7 +276,8 @@ def main():
             e2e = {"value": rows * world * args.e2e_steps / dt, "unit": "rows/s", "h2d_bytes_per_step": int(est.h2d_bytes) * world, "d2h_bytes_per_step": int(est.d2h_bytes) * world,
                    "ms_per_step": 1000 * dt / args.e2e_steps, "steps": args.e2e_steps, "matched": int(counts.sum()),
                    "input_stage": "on-disk values blocks (ZSTD frames, decoded on the device)" if args.e2e_stage == "ondisk" else "decoded values blocks",
-                   "host_bytes": int(host.bytes), "writer_compress_seconds": round(t_comp, 2)}
+                   "host_bytes": int(host.bytes), "writer_compress_seconds": round(t_comp, 2), "host_threads": int(os.environ["VLSCAN_HOST_THREADS"]),
+                   "matched_equals_resident": int(counts.sum()) == int(st.rows_matched)}
             del host
         except Exception as e:   # pinned host memory for the full data set may not be available
             e2e = {"value": None, "unit": "rows/s", "error": str(e)[:200]}
