@@ -1,0 +1,61 @@
+"""The host-side parsers that read untrusted bytes - filter-tree program compiler with its regexp compiler, and the bytes-block / ZSTD
+header walk - built with AddressSanitizer + UndefinedBehaviorSanitizer (tests/host_asan/harness.cpp) and fed mutated real inputs.
+Any out-of-bounds read, overflow, leak-on-throw or foreign exception type fails the run."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+from victorialogs_b200 import scan as vs
+from golden_util import load_filter_cases, build_filter
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def harness(tmp_path_factory):
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no g++")
+    out = tmp_path_factory.mktemp("asan") / "harness"
+    cmd = [gxx, "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-fno-omit-frame-pointer",
+           "-I", os.path.join(ROOT, "victorialogs_b200", "csrc"), os.path.join(ROOT, "tests", "host_asan", "harness.cpp"), "-o", str(out)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    if r.returncode != 0 and "sanitize" in r.stderr and "cannot find" in r.stderr:
+        pytest.skip("sanitizer runtime not installed")
+    assert r.returncode == 0, r.stderr[-3000:]
+    return str(out)
+
+
+def run(harness, mode, seed_dir, iters, seed):
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=1:abort_on_error=0", UBSAN_OPTIONS="print_stacktrace=1")
+    r = subprocess.run([harness, mode, str(seed_dir), str(iters), str(seed)], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, (r.returncode, r.stdout[-300:], r.stderr[-4000:])
+    ok, bad = (int(x) for x in r.stdout.split()[1::2])
+    return ok, bad
+
+
+def test_program_compiler_under_sanitizers(harness, tmp_path):
+    seeds = [build_filter(vs.Filter, c["filter"]).blob for c in load_filter_cases()[::5]]
+    nxt = ("exact_prefix", "len_range", "string_range", "ipv4_range", "value_type")
+    seeds += [build_filter(vs.Filter, c["filter"]).blob for c in load_filter_cases("filter_cases_next.json") if c["filter"]["kind"] in nxt][::4]
+    seeds.append(vs.Filter.and_([vs.Filter.phrase("a", "b c"), vs.Filter.or_([vs.Filter.regexp("x", "a.*b|c+"), vs.Filter.not_(vs.Filter.in_("y", ["1", "2"]))])]).blob)
+    seeds.append(vs.Filter.regexp("_msg", "(?i)^(foo|ba[rz]+)\\d{2,5}[^a-c]*.+$").blob)
+    for i, s in enumerate(seeds):
+        (tmp_path / ("%04d" % i)).write_bytes(s)
+    ok, bad = run(harness, "tree", tmp_path, 60000, 1)
+    assert ok > 1000 and bad > 10000
+
+
+def test_zstd_header_walk_under_sanitizers(harness, tmp_path, oracle):
+    k = 0
+    for rpb in (3000, 64, 9000):       # one ZSTD block per frame / plain containers / several ZSTD blocks per frame
+        cfg = oracle.GenConfig(seed=3, total_rows=rpb * 4, rows_per_block=rpb, hot_block_permille=500, hit_row_permille=60, columns_mask=0b1111)
+        for b in range(4):
+            for c in oracle.Block.generated(cfg, b).columns:
+                (tmp_path / ("%04d" % k)).write_bytes(c.values_block)
+                k += 1
+    assert k >= 40
+    ok, bad = run(harness, "zstd", tmp_path, 40000, 2)
+    assert ok > 1000 and bad > 10000

@@ -8,6 +8,7 @@
 #include "../../include/vlscan.h"
 #include "vl_kernels.cuh"
 #include "vl_zstd.h"
+#include "vl_zstd_walk.h"   // BadInput
 
 namespace vl {
 
@@ -18,7 +19,6 @@ void set_thread_error(const std::string& s);
         if (e__ != cudaSuccess) throw CudaFail(std::string(#call) + ": " + cudaGetErrorString(e__), (int)e__);        \
     } while (0)
 struct CudaFail { std::string msg; int code; CudaFail(std::string m, int c) : msg(std::move(m)), code(c) {} };
-struct BadInput { std::string msg; explicit BadInput(std::string m) : msg(std::move(m)) {} };
 
 struct DevBuf {
     void* p = nullptr; size_t cap = 0;

@@ -20,53 +20,10 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "vl_zstd_types.h"
 
 namespace vl {
 namespace zs {
-
-enum { ZERR_NONE = 0, ZERR_HUF_DESC = 1, ZERR_HUF_STREAM = 2, ZERR_FSE_DESC = 3, ZERR_SEQ_STREAM = 4, ZERR_OFFSET = 5, ZERR_SIZE = 6, ZERR_LITERALS = 7 };
-enum { ZB_RAW = 0, ZB_RLE = 1, ZB_COMPRESSED = 2 };
-enum { ZL_RAW = 0, ZL_RLE = 1, ZL_COMPRESSED = 2, ZL_TREELESS = 3 };
-static const uint32_t Z_PREDEF = 0xFFFFFFFFu;
-static const uint32_t Z_HUF_TABLE = 2048;            // entries per Huffman slot (Max_Number_of_Bits = 11)
-// One FSE slot = the three sequence decoding tables of a block in the layout the sequence decoder stages into shared memory:
-//   u16 trans[1280]  state -> baseline | nbits << 12      (LL at 0, ML at 512, OF at 1024; 2^accuracy entries each are used)
-//   u8  sym[1280]    state -> literal-length / match-length / offset code
-static const uint32_t Z_FSE_LL = 0, Z_FSE_ML = 512, Z_FSE_OF = 1024, Z_FSE_ENTRIES = 1280, Z_FSE_SLOT_BYTES = 3 * 1280;
-
-struct ZFrame {            // one ZSTD frame, or one plain bytes block (then: a single raw block)
-    uint64_t dst;          // arena offset of the regenerated bytes
-    uint64_t fcs;          // Frame_Content_Size
-    uint32_t blk_lo, blk_hi;
-};
-struct ZBlock {
-    uint64_t src;          // offset of Block_Content in the compressed staging buffer
-    uint64_t lit_off;      // literal scratch offset (Compressed / Treeless literals)
-    uint64_t seq_base;     // first sequence record of the block in the sequence scratch
-    uint32_t size;         // Block_Size (RLE: regenerated size, content is one byte)
-    uint32_t frame;
-    uint32_t lit_hdr;      // length of Literals_Section_Header
-    uint32_t lit_regen, lit_comp;
-    uint32_t nseq;
-    uint32_t seq_hdr;      // offset inside the block of the Symbol_Compression_Modes byte
-    uint32_t huf_slot;     // Huffman table slot to decode with (own slot, or the previous table for Treeless literals)
-    uint32_t huf_own;      // slot this block's tree description is built into (Compressed literals), else Z_PREDEF
-    uint32_t fse_own;      // slot for tables described in this block, else Z_PREDEF
-    uint32_t ll_slot, of_slot, ml_slot;   // slot to decode each symbol type with; Z_PREDEF = predefined distribution
-    uint8_t type, lit_type, lit_streams, modes;
-    uint8_t rep_known;     // no earlier block of the frame has sequences: the repeat offsets start as {1, 4, 8}
-    uint8_t pad[3];
-};
-struct ZBlockState {       // produced on the device
-    uint32_t huf_desc_len; // bytes of the Huffman tree description
-    uint32_t seq_bits_off; // offset inside the block where the sequence bitstream starts
-    uint32_t out_len;      // regenerated size of the block
-    uint32_t out_base;     // offset of the block's output inside its frame
-    uint32_t clean_from;   // sequences [clean_from, nseq) were resolved without knowing the repeat offsets the block started with;
-                           // nseq + 1: the history never became independent of them
-    uint32_t rep[3];       // repeat offsets after the last sequence (valid when clean_from <= nseq)
-};
-struct ZSlotState { uint8_t huf_maxbits, ll_al, of_al, ml_al; };
 
 struct ZView {
     const uint8_t* src;        // compressed staging buffer
