@@ -204,6 +204,34 @@ int vlscan_zstd_inspect(const void* bytes_block, size_t len, uint64_t out[5]);
  * No device needed.  For tests and host-side tuning. */
 int vlscan_zstd_walk_digest(const vlscan_block* blocks, uint64_t nblocks, int threads, uint64_t out[12]);
 
+/* ---- part directory reader -----------------------------------------------------------------------------------------
+ * For hosts without the Go process: opens one part directory the way part.mustOpenFilePart does (lib/logstorage/part.go:105-173;
+ * format versions 1..3) and hands out, for any block range and field list, the vlscan_block descriptors (VLSCAN_STAGE_ONDISK, pointing
+ * into the memory-mapped bloom / values files) that vlscan_scan_batch and vlscan_batch_upload take - what blockSearch.getColumnHeader /
+ * getConstColumnValue / getBloomFilterForColumn / getValuesForColumn (block_search.go:232-474) locate lazily per block.
+ * The part's own ZSTD-compressed metadata (column_names.bin, metaindex.bin, the blocks of index.bin: a few KB..MB) is inflated by the
+ * device decoder of `ctx`, or, when the embedding process has its own ZSTD (the Go process does), by `inflate`: it must regenerate
+ * exactly dst_len bytes from the frame and return 0.  Values blocks never go through `inflate`. */
+typedef struct vlscan_part vlscan_part;
+typedef int (*vlscan_inflate_fn)(void* user, const void* frame, size_t frame_len, void* dst, size_t dst_len);
+int vlscan_part_open(vlscan_ctx* ctx /* may be NULL with inflate */, const char* path, vlscan_inflate_fn inflate /* may be NULL with ctx */, void* user, vlscan_part** out);
+void vlscan_part_free(vlscan_part* part);
+/* partHeader (metadata.json): FormatVersion, CompressedSizeBytes, UncompressedSizeBytes, RowsCount, BlocksCount, MinTimestamp, MaxTimestamp,
+ * BloomValuesShardsCount */
+void vlscan_part_header(const vlscan_part* part, uint64_t out[8]);
+uint64_t vlscan_part_nblocks(const vlscan_part* part);
+/* blockHeader i in index order (streamID, then minTimestamp): accountID, projectID, streamID.hi, streamID.lo, uncompressedSizeBytes, rowsCount,
+ * timestamps blockOffset, blockSize, minTimestamp, maxTimestamp, marshalType, columnsHeaderIndexOffset, -Size, columnsHeaderOffset, -Size */
+int vlscan_part_block_header(const vlscan_part* part, uint64_t i, uint64_t out[15]);
+uint32_t vlscan_part_ncolumn_names(const vlscan_part* part);
+const char* vlscan_part_column_name(const vlscan_part* part, uint32_t i, size_t* len);   /* "" is the message field */
+/* Descriptors of the blocks [block_lo, block_hi) whose [minTimestamp, maxTimestamp] overlaps [min_timestamp, max_timestamp], restricted to
+ * the given fields ("_msg" or "" = the message field); a field a block does not have is simply absent from it.  The result stays valid
+ * while the part is open; vlscan_host_blocks_source tells which block of the part each described block is. */
+int vlscan_part_blocks(const vlscan_part* part, const char* const* field_names, const size_t* field_name_lens, uint32_t nfields, uint64_t block_lo,
+                       uint64_t block_hi, int64_t min_timestamp, int64_t max_timestamp, vlscan_host_blocks** out);
+const uint64_t* vlscan_host_blocks_source(const vlscan_host_blocks* hb, uint64_t* n);
+
 /* ---- the scan ---------------------------------------------------------------------------------------------------- */
 /* Scan a resident batch: equivalent of `for each block: bm.init(rows); bm.setBits(); filter.applyToBlockSearch(bs, bm)`
  * (block_search.go:207-215).  Results stay on the device until fetched; the call only enqueues work on the ctx stream

@@ -1,7 +1,9 @@
 // Sanitizer build of the host-side parsers of libvlscan.so that read untrusted bytes:
 //   tree  the filter-tree program compiler incl. the regexp compiler (victorialogs_b200/csrc/vl_program.h, vl_regex.h)
 //   zstd  the bytes-block / ZSTD header walk                         (victorialogs_b200/csrc/vl_zstd_walk.h)
-// usage: harness tree|zstd <seed directory> <iterations> <rng seed>
+//   part  the part directory reader                                  (victorialogs_b200/csrc/vl_part.h; the seed directory is ONE part directory,
+//         each iteration damages one of its files in a scratch copy; metadata frames are inflated with libzstd)
+// usage: harness tree|zstd|part <seed directory> <iterations> <rng seed>
 // Every input lives in a heap block of its exact size, so AddressSanitizer sees any read past its end; malformed input must end in
 // the parser's own exception type.  Built and run by tests/test_host_asan_cpu.py with -fsanitize=address,undefined.
 #include <dirent.h>
@@ -12,8 +14,15 @@
 #include <memory>
 #include <string>
 #include <vector>
+#define VL_PART_HEAP_FILES 1
 #include "vl_program.h"
 #include "vl_zstd_walk.h"
+#include "vl_part.h"
+
+extern "C" {   // the image has libzstd.so.1 but no zstd.h
+size_t ZSTD_decompress(void* dst, size_t dstCapacity, const void* src, size_t compressedSize);
+unsigned ZSTD_isError(size_t code);
+}
 
 static uint64_t rng_state = 88172645463325252ull;
 static uint64_t rnd() { rng_state ^= rng_state << 13; rng_state ^= rng_state >> 7; rng_state ^= rng_state << 17; return rng_state; }
@@ -49,9 +58,60 @@ static std::string mutate(const std::vector<std::string>& seeds) {
     return b;
 }
 
+static std::string mutate_one(const std::string& in) { std::vector<std::string> one{in}; return mutate(one); }
+
+// part mode: `dir` is copied file by file into `scratch`; every iteration one file of the copy is replaced by a damaged version
+static int fuzz_part(const char* dir, long iters) {
+    std::vector<std::string> names; std::map<std::string, std::string> files;
+    DIR* d = opendir(dir);
+    if (!d) { perror(dir); return 2; }
+    while (dirent* e = readdir(d)) if (e->d_name[0] != '.') names.push_back(e->d_name);
+    closedir(d);
+    std::sort(names.begin(), names.end());
+    for (auto& n : names) { std::ifstream f(std::string(dir) + "/" + n, std::ios::binary); files[n] = std::string((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>()); }
+    char tmpl[] = "/tmp/vl_part_fuzz_XXXXXX";
+    const char* scratch = mkdtemp(tmpl);
+    if (!scratch) { perror("mkdtemp"); return 2; }
+    auto put = [&](const std::string& n, const std::string& data) { std::ofstream f(std::string(scratch) + "/" + n, std::ios::binary | std::ios::trunc); f.write(data.data(), (std::streamsize)data.size()); };
+    for (auto& kv : files) put(kv.first, kv.second);
+    const vl::part::Inflate inflate = [](const uint8_t* f, size_t n, uint8_t* dst, size_t dn) {
+        const size_t got = ZSTD_decompress(dst, dn, f, n);
+        if (ZSTD_isError(got) || got != dn) throw vl::BadInput("cannot decompress a metadata frame");
+    };
+    std::vector<std::string> fields{"_msg", "level", "status", "bytes", "delta", "ratio", "ip", "ts", "host", "sparse", "only_in_1", "nope"};
+    long ok = 0, bad = 0;
+    for (long it = -1; it < iters; it++) {
+        std::string victim;
+        if (it >= 0) {
+            do victim = names[below(names.size())]; while (below(4) && (victim.rfind("values.bin", 0) == 0 || victim.rfind("bloom.bin", 0) == 0 || victim.rfind("message_", 0) == 0 || victim == "timestamps.bin"));
+            put(victim, below(16) ? mutate_one(files[victim]) : std::string());
+        }
+        try {
+            vl::part::PartReader r; r.open(scratch, inflate);
+            vl::part::Described dsc; r.describe(fields, 0, r.blockHeaders.size(), INT64_MIN, INT64_MAX, dsc);
+            uint64_t sum = 0;   // touch every byte the descriptors point at
+            for (const vlscan_column& c : dsc.cols) {
+                for (uint64_t i = 0; i < c.const_len; i++) sum += c.const_value[i];
+                for (uint64_t i = 0; i < c.values_len; i++) sum += c.values[i];
+                for (uint64_t i = 0; i < c.bloom_len; i++) sum += c.bloom[i];
+                if (c.dict_len) for (uint32_t i = 0; i < c.dict_offsets[c.dict_len]; i++) sum += c.dict_blob[i];
+            }
+            if (sum == 0x1234567812345678ull) printf("!");
+            ok++;
+        } catch (const vl::BadInput&) { bad++; }
+        if (it < 0 && bad) { fprintf(stderr, "the undamaged part was rejected\n"); return 4; }
+        if (it >= 0) put(victim, files[victim]);
+    }
+    for (auto& n : names) unlink((std::string(scratch) + "/" + n).c_str());
+    rmdir(scratch);
+    printf("accepted %ld rejected %ld\n", ok, bad);
+    return 0;
+}
+
 int main(int argc, char** argv) {
-    if (argc < 5) { fprintf(stderr, "usage: harness tree|zstd <seed dir> <iterations> <rng seed>\n"); return 2; }
+    if (argc < 5) { fprintf(stderr, "usage: harness tree|zstd|part <seed dir> <iterations> <rng seed>\n"); return 2; }
     const std::string mode = argv[1];
+    if (mode == "part") { rng_state ^= (uint64_t)atoll(argv[4]) * 0x9E3779B97F4A7C15ull; return fuzz_part(argv[2], atol(argv[3])); }
     const std::vector<std::string> seeds = read_seeds(argv[2]);
     const long iters = atol(argv[3]);
     rng_state ^= (uint64_t)atoll(argv[4]) * 0x9E3779B97F4A7C15ull;

@@ -1,5 +1,5 @@
-"""The host-side parsers that read untrusted bytes - filter-tree program compiler with its regexp compiler, and the bytes-block / ZSTD
-header walk - built with AddressSanitizer + UndefinedBehaviorSanitizer (tests/host_asan/harness.cpp) and fed mutated real inputs.
+"""The host-side parsers that read untrusted bytes - filter-tree program compiler with its regexp compiler, the bytes-block / ZSTD
+header walk and the part directory reader - built with AddressSanitizer + UndefinedBehaviorSanitizer (tests/host_asan/harness.cpp) and fed mutated real inputs.
 Any out-of-bounds read, overflow, leak-on-throw or foreign exception type fails the run."""
 import os
 import shutil
@@ -20,7 +20,7 @@ def harness(tmp_path_factory):
         pytest.skip("no g++")
     out = tmp_path_factory.mktemp("asan") / "harness"
     cmd = [gxx, "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-fno-omit-frame-pointer",
-           "-I", os.path.join(ROOT, "victorialogs_b200", "csrc"), os.path.join(ROOT, "tests", "host_asan", "harness.cpp"), "-o", str(out)]
+           "-I", os.path.join(ROOT, "victorialogs_b200", "csrc"), os.path.join(ROOT, "tests", "host_asan", "harness.cpp"), "-o", str(out), "-l:libzstd.so.1"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     if r.returncode != 0 and "sanitize" in r.stderr and "cannot find" in r.stderr:
         pytest.skip("sanitizer runtime not installed")
@@ -59,3 +59,10 @@ def test_zstd_header_walk_under_sanitizers(harness, tmp_path, oracle):
     assert k >= 40
     ok, bad = run(harness, "zstd", tmp_path, 40000, 2)
     assert ok > 1000 and bad > 10000
+
+
+def test_part_reader_under_sanitizers(harness, tmp_path):
+    from test_part_reader_cpu import write_part
+    path, files, originals, header = write_part(tmp_path, "part", seed=3)
+    ok, bad = run(harness, "part", path, 4000, 3)
+    assert ok > 200 and bad > 2000

@@ -14,6 +14,7 @@
 #include <mutex>
 #include "vl_engine.h"
 #include "vl_program.h"
+#include "vl_part.h"
 
 using namespace vl;
 
@@ -54,7 +55,10 @@ struct vlscan_host_blocks {
     std::vector<vlscan_column> cols;
     std::vector<std::string> fields;
     std::vector<std::vector<uint32_t>> dict_offsets;
+    std::vector<std::unique_ptr<std::vector<uint8_t>>> owned;   // dict tables rebuilt from a part's column headers
+    std::vector<uint64_t> source;                               // vlscan_part_blocks: index of each block inside the part
 };
+struct vlscan_part { vl::part::PartReader r; };
 
 void* vlscan_ctx::ensure_pinned(size_t n) {
     if (n <= pinned_cap) return pinned;
@@ -841,8 +845,9 @@ int vlscan_zstd_walk_digest(const vlscan_block* blocks, uint64_t nblocks, int th
     });
 }
 
-int vlscan_zstd_decompress(vlscan_ctx* ctx, uint32_t nframes, const void* const* frames, const size_t* frame_lens, void* dst, const uint64_t* dst_offsets) {
-    return guarded(ctx, [&] {
+// the device decoder on independent frames given as host pointers (metadata of a part, parity tests)
+static void zstd_decompress_frames(vlscan_ctx* ctx, uint32_t nframes, const void* const* frames, const size_t* frame_lens, void* dst, const uint64_t* dst_offsets) {
+    {
         VL_CUDA(cudaSetDevice(ctx->device));
         ZstdJob job;
         std::vector<uint8_t> packed(512, 0);
@@ -860,8 +865,64 @@ int vlscan_zstd_decompress(vlscan_ctx* ctx, uint32_t nframes, const void* const*
         job.run(ctx, ctx->zsrc.as<uint8_t>(), ctx->ztest.as<uint8_t>());
         job.check(ctx);
         if (total) VL_CUDA(cudaMemcpy(dst, ctx->ztest.as<uint8_t>() + 16, total, cudaMemcpyDeviceToHost));
+    }
+}
+
+int vlscan_zstd_decompress(vlscan_ctx* ctx, uint32_t nframes, const void* const* frames, const size_t* frame_lens, void* dst, const uint64_t* dst_offsets) {
+    return guarded(ctx, [&] { zstd_decompress_frames(ctx, nframes, frames, frame_lens, dst, dst_offsets); });
+}
+
+// ---- part directory reader (vl_part.h) ------------------------------------------------------------------------------------
+int vlscan_part_open(vlscan_ctx* ctx, const char* path, vlscan_inflate_fn inflate, void* user, vlscan_part** out) {
+    *out = nullptr;
+    auto* p = new vlscan_part();
+    int rc = guarded(ctx, [&] {
+        if (!inflate && !ctx) throw BadInput("vlscan_part_open needs a ctx (device ZSTD decoder) or an inflate callback");
+        vl::part::Inflate inf;
+        if (inflate) inf = [&](const uint8_t* f, size_t n, uint8_t* dst, size_t dn) { if (inflate(user, f, n, dst, dn) != 0) throw BadInput("the inflate callback failed on a metadata frame of the part"); };
+        else inf = [&](const uint8_t* f, size_t n, uint8_t* dst, size_t dn) { const void* fr[1] = {f}; const size_t ln[1] = {n}; const uint64_t offs[2] = {0, dn}; zstd_decompress_frames(ctx, 1, fr, ln, dst, offs); };
+        p->r.open(path, inf);
+    });
+    if (rc) { delete p; return rc; }
+    *out = p;
+    return 0;
+}
+void vlscan_part_free(vlscan_part* part) { delete part; }
+void vlscan_part_header(const vlscan_part* part, uint64_t out[8]) {
+    const vl::part::PartHeader& h = part->r.ph;
+    out[0] = h.FormatVersion; out[1] = h.CompressedSizeBytes; out[2] = h.UncompressedSizeBytes; out[3] = h.RowsCount; out[4] = h.BlocksCount;
+    out[5] = (uint64_t)h.MinTimestamp; out[6] = (uint64_t)h.MaxTimestamp; out[7] = h.BloomValuesShardsCount;
+}
+uint64_t vlscan_part_nblocks(const vlscan_part* part) { return part->r.blockHeaders.size(); }
+int vlscan_part_block_header(const vlscan_part* part, uint64_t i, uint64_t out[15]) {
+    return guarded(nullptr, [&] {
+        if (i >= part->r.blockHeaders.size()) throw BadInput("block index outside the part");
+        const vl::part::BlockHeader& b = part->r.blockHeaders[i];
+        out[0] = b.sid.accountID; out[1] = b.sid.projectID; out[2] = b.sid.hi; out[3] = b.sid.lo; out[4] = b.uncompressedSizeBytes; out[5] = b.rowsCount;
+        out[6] = b.tsOffset; out[7] = b.tsSize; out[8] = (uint64_t)b.minTimestamp; out[9] = (uint64_t)b.maxTimestamp; out[10] = b.tsMarshalType;
+        out[11] = b.chIndexOffset; out[12] = b.chIndexSize; out[13] = b.chOffset; out[14] = b.chSize;
     });
 }
+uint32_t vlscan_part_ncolumn_names(const vlscan_part* part) { return (uint32_t)part->r.columnNames.size(); }
+const char* vlscan_part_column_name(const vlscan_part* part, uint32_t i, size_t* len) { const std::string& s = part->r.columnNames[i]; *len = s.size(); return s.data(); }
+int vlscan_part_blocks(const vlscan_part* part, const char* const* field_names, const size_t* field_name_lens, uint32_t nfields, uint64_t block_lo, uint64_t block_hi,
+                       int64_t min_timestamp, int64_t max_timestamp, vlscan_host_blocks** out) {
+    *out = nullptr;
+    auto* hb = new vlscan_host_blocks();
+    int rc = guarded(nullptr, [&] {
+        std::vector<std::string> fields;
+        for (uint32_t f = 0; f < nfields; f++) { std::string n(field_names[f], field_name_lens[f]); fields.push_back(n.empty() ? "_msg" : n); }
+        for (size_t a = 0; a < fields.size(); a++) for (size_t b = a + 1; b < fields.size(); b++) if (fields[a] == fields[b]) throw BadInput("duplicate field name");
+        vl::part::Described d;
+        part->r.describe(fields, block_lo, block_hi, min_timestamp, max_timestamp, d);
+        hb->fields = std::move(d.fields); hb->cols = std::move(d.cols); hb->blocks = std::move(d.blocks); hb->owned = std::move(d.owned); hb->source = std::move(d.source);
+        for (const vlscan_column& c : hb->cols) hb->bytes += c.const_len + c.values_len + c.bloom_len;
+    });
+    if (rc) { delete hb; return rc; }
+    *out = hb;
+    return 0;
+}
+const uint64_t* vlscan_host_blocks_source(const vlscan_host_blocks* hb, uint64_t* n) { *n = hb->source.size(); return hb->source.data(); }
 
 const vlscan_block* vlscan_host_blocks_get(const vlscan_host_blocks* hb, uint64_t* nblocks, uint32_t* nfields) { *nblocks = hb->blocks.size(); *nfields = (uint32_t)hb->fields.size(); return hb->blocks.data(); }
 const char* vlscan_host_blocks_field(const vlscan_host_blocks* hb, uint32_t i, size_t* len) { *len = hb->fields[i].size(); return hb->fields[i].data(); }

@@ -68,7 +68,8 @@ EXPORTS = ["vlscan_device_count", "vlscan_ctx_create", "vlscan_ctx_free", "vlsca
            "vlscan_program_create", "vlscan_program_free", "vlscan_program_nfields", "vlscan_program_field", "vlscan_program_leaf_tokens", "vlscan_format_float64", "vlscan_eval_predicate",
            "vlscan_batch_upload", "vlscan_batch_free", "vlscan_batch_nblocks", "vlscan_batch_rows", "vlscan_batch_words", "vlscan_batch_device_bytes",
            "vlscan_batch_generate", "vlscan_batch_download", "vlscan_host_blocks_get", "vlscan_host_blocks_field", "vlscan_host_blocks_bytes",
-           "vlscan_host_blocks_free", "vlscan_host_blocks_compress", "vlscan_zstd_decompress", "vlscan_zstd_inspect", "vlscan_zstd_walk_digest", "vlscan_scan_resident", "vlscan_last_scan_stats", "vlscan_fetch_results", "vlscan_fetch_hits", "vlscan_result_device_ptrs", "vlscan_scan_batch"]
+           "vlscan_host_blocks_free", "vlscan_host_blocks_compress", "vlscan_zstd_decompress", "vlscan_zstd_inspect", "vlscan_zstd_walk_digest", "vlscan_part_open", "vlscan_part_free", "vlscan_part_header", "vlscan_part_nblocks", "vlscan_part_block_header",
+           "vlscan_part_ncolumn_names", "vlscan_part_column_name", "vlscan_part_blocks", "vlscan_host_blocks_source", "vlscan_scan_resident", "vlscan_last_scan_stats", "vlscan_fetch_results", "vlscan_fetch_hits", "vlscan_result_device_ptrs", "vlscan_scan_batch"]
 
 
 def lib_path():
@@ -395,6 +396,96 @@ class DownloadedBlocks:
         try:
             if self.h:
                 lib().vlscan_host_blocks_free(self.h)
+        except Exception:
+            pass
+
+
+INFLATE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t)
+BLOCK_HEADER_FIELDS = ("account_id", "project_id", "id_hi", "id_lo", "uncompressed_size_bytes", "rows_count", "ts_block_offset", "ts_block_size",
+                       "min_timestamp", "max_timestamp", "ts_marshal_type", "columns_header_index_offset", "columns_header_index_size",
+                       "columns_header_offset", "columns_header_size")
+PART_HEADER_FIELDS = ("FormatVersion", "CompressedSizeBytes", "UncompressedSizeBytes", "RowsCount", "BlocksCount", "MinTimestamp", "MaxTimestamp",
+                      "BloomValuesShardsCount")
+
+
+def _signed(v):
+    return v - (1 << 64) if v >= 1 << 63 else v
+
+
+class Part:
+    """One part directory opened through vlscan_part_open (part.mustOpenFilePart, lib/logstorage/part.go:105-173).
+
+    ctx: the device decoder inflates the part's metadata; inflate: a Python callable (frame bytes, regenerated size) -> bytes used instead
+    (an embedding process with its own ZSTD)."""
+
+    def __init__(self, path, ctx=None, inflate=None):
+        L = lib()
+        L.vlscan_part_nblocks.restype = C.c_uint64
+        L.vlscan_part_nblocks.argtypes = [C.c_void_p]
+        L.vlscan_part_ncolumn_names.restype = C.c_uint32
+        L.vlscan_part_ncolumn_names.argtypes = [C.c_void_p]
+        L.vlscan_part_column_name.restype = C.c_void_p
+        L.vlscan_part_free.argtypes = [C.c_void_p]
+        L.vlscan_part_free.restype = None
+        L.vlscan_host_blocks_source.restype = C.POINTER(C.c_uint64)
+        self._cb = None
+        if inflate is not None:
+            def cb(user, frame, n, dst, dn):
+                try:
+                    out = inflate(C.string_at(frame, n), dn)
+                    if len(out) != dn:
+                        return 1
+                    C.memmove(dst, out, dn)
+                    return 0
+                except Exception:
+                    return 2
+            self._cb = INFLATE_FN(cb)
+        self.h = C.c_void_p()
+        rc = L.vlscan_part_open(ctx.h if ctx is not None else None, _b(path), self._cb if self._cb is not None else C.cast(None, INFLATE_FN), None, C.byref(self.h))
+        if rc:
+            raise VlscanError(rc, L.vlscan_last_error(ctx.h if ctx is not None else None).decode("utf-8", "replace"))
+        out = (C.c_uint64 * 8)()
+        L.vlscan_part_header(self.h, out)
+        self.header = {k: (_signed(out[i]) if k in ("MinTimestamp", "MaxTimestamp") else out[i]) for i, k in enumerate(PART_HEADER_FIELDS)}
+        self.nblocks = L.vlscan_part_nblocks(self.h)
+        self.column_names = []
+        for i in range(L.vlscan_part_ncolumn_names(self.h)):
+            ln = C.c_size_t()
+            p = L.vlscan_part_column_name(self.h, C.c_uint32(i), C.byref(ln))
+            self.column_names.append(C.string_at(p, ln.value))
+
+    def block_header(self, i):
+        out = (C.c_uint64 * 15)()
+        rc = lib().vlscan_part_block_header(self.h, C.c_uint64(i), out)
+        if rc:
+            raise VlscanError(rc, lib().vlscan_last_error(None).decode("utf-8", "replace"))
+        return {k: (_signed(out[j]) if k in ("min_timestamp", "max_timestamp") else out[j]) for j, k in enumerate(BLOCK_HEADER_FIELDS)}
+
+    def blocks(self, fields, lo=0, hi=None, min_timestamp=-(1 << 63), max_timestamp=(1 << 63) - 1):
+        """-> DownloadedBlocks-like descriptors (on-disk stage) of the blocks [lo, hi) overlapping the time range; .source = their indices in the part"""
+        fields = [_b(f) for f in fields]
+        names = (C.c_char_p * max(len(fields), 1))(*fields)
+        lens = (C.c_size_t * max(len(fields), 1))(*[len(f) for f in fields])
+        h = C.c_void_p()
+        rc = lib().vlscan_part_blocks(self.h, names, lens, C.c_uint32(len(fields)), C.c_uint64(lo), C.c_uint64(self.nblocks if hi is None else hi),
+                                      C.c_int64(min_timestamp), C.c_int64(max_timestamp), C.byref(h))
+        if rc:
+            raise VlscanError(rc, lib().vlscan_last_error(None).decode("utf-8", "replace"))
+        hb = DownloadedBlocks(None, None, _handle=h)
+        n = C.c_uint64()
+        p = lib().vlscan_host_blocks_source(h, C.byref(n))
+        hb.source = [p[i] for i in range(n.value)]
+        hb._part = self           # the descriptors point into the part's mapped files
+        return hb
+
+    def close(self):
+        if self.h:
+            lib().vlscan_part_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
         except Exception:
             pass
 
