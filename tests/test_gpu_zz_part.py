@@ -63,3 +63,25 @@ def test_part_on_disk_scans_like_the_blocks_it_was_written_from(env, tmp_path):
     words, counts, st = ctx.scan_batch(prog, sub)
     of = OF.phrase("_msg", "timeout")
     assert [int(c) for c in counts] == [len(oracle.bitmap_rows(originals[i][1].search(of), originals[i][1].rows)) for i in want_src]
+
+
+def test_search_part_loop(env, tmp_path):
+    """search_part = the block loop of Storage.search for one part: time pruning per block, batches through vlscan_scan_batch"""
+    oracle, vs, ctx = env
+    path, files, originals, header = write_part(tmp_path, "part2", seed=33, streams=5, blocks_per_stream=4)
+    part = vs.Part(path, ctx=ctx)
+    gf = vs.Filter.or_([vs.Filter.phrase("_msg", "reset"), vs.Filter.exact("level", "error")])
+    of = oracle.Filter.or_([oracle.Filter.phrase("_msg", "reset"), oracle.Filter.exact("level", "error")])
+    lo_t, hi_t = originals[3][2][1 if len(originals[3][2]) > 1 else 0], originals[14][2][-1]
+    for batch_blocks in (3, 1000):
+        hits = vs.search_part(ctx, part, gf, lo_t, hi_t, batch_blocks=batch_blocks)
+        want = []
+        for i, (sid, b, ts) in enumerate(originals):
+            if ts[-1] < lo_t or ts[0] > hi_t:
+                continue
+            rows = oracle.bitmap_rows(b.search(of), b.rows)
+            if rows:
+                want.append((i, rows, lo_t <= ts[0] and ts[-1] <= hi_t))
+        assert [(src, oracle.bitmap_rows(np.ascontiguousarray(w), originals[src][1].rows), inside) for src, w, c, inside in hits] == want
+        assert [c for _, _, c, _ in hits] == [len(r) for _, r, _ in want]
+    assert any(not inside for *_, inside in hits) or len(originals[3][2]) == 1

@@ -490,6 +490,28 @@ class Part:
             pass
 
 
+def search_part(ctx, part, flt, min_timestamp=-(1 << 63), max_timestamp=(1 << 63) - 1, batch_blocks=8192):
+    """The block loop of Storage.search for one part (storage_search.go:1022-1063 below the partition level): blocks are pruned by their
+    time range, the filter tree runs on the rest in batches of `batch_blocks` through vlscan_scan_batch.
+
+    -> list of (block index in the part, bitmap words, match count, inside) for blocks with matches.  `inside` is False for a block that
+    only partly overlaps [min_timestamp, max_timestamp]: its rows still need the per-row `_time` check (filterTime, filter_time.go:114-137),
+    which this engine does not run yet."""
+    prog = Program(flt)
+    fields = prog.fields()
+    hits = []
+    for lo in range(0, part.nblocks, batch_blocks):
+        hb = part.blocks(fields, lo, min(part.nblocks, lo + batch_blocks), min_timestamp, max_timestamp)
+        if hb.nblocks == 0:
+            continue
+        words, counts, _ = ctx.scan_batch(prog, hb)
+        for src, w, c in zip(hb.source, split_bitmaps(words, hb.rows), counts):
+            if c:
+                bh = part.block_header(src)
+                hits.append((src, w.copy(), int(c), min_timestamp <= bh["min_timestamp"] and bh["max_timestamp"] <= max_timestamp))
+    return hits
+
+
 class Batch:
     def __init__(self, h, ctx):
         self.h = h
