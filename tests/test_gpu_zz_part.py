@@ -84,4 +84,4 @@ def test_search_part_loop(env, tmp_path):
                 want.append((i, rows, lo_t <= ts[0] and ts[-1] <= hi_t))
         assert [(src, oracle.bitmap_rows(np.ascontiguousarray(w), originals[src][1].rows), inside) for src, w, c, inside in hits] == want
         assert [c for _, _, c, _ in hits] == [len(r) for _, r, _ in want]
-    assert any(not inside for *_, inside in hits) or len(originals[3][2]) == 1
+        assert len(want) > 3
