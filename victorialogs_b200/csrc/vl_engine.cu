@@ -262,7 +262,10 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
         if (!zpieces.empty()) { ctx->zsrc.ensure(zc + 512); marking = true; copy_pieces(zpieces, ctx->zsrc.as<uint8_t>()); marking = false; }
         // frame, block and section headers of all of them, on several host threads; a malformed block is reported when the loop below gets to it
         zinfo.resize(zv.size());
+        const double t_w = now();
         if (!zv.empty()) zjob.add_values_blocks(zv.data(), zv.size(), host_threads(), zinfo.data(), &zbad, &zmsg);
+        if (dbg) fprintf(stderr, "[vlscan upload] header walk of %zu values blocks on %d host threads: %.1f ms (after %.1f ms of collecting and enqueueing the copies)\n",
+                         zv.size(), host_threads(), 1e3 * (now() - t_w), 1e3 * (t_w - t_start));
     }
     for (uint64_t b = 0; b < nblocks; b++) {
         const vlscan_block& blk = blocks[b];

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <array>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -311,7 +312,10 @@ void ZstdJob::digest(uint64_t out[4]) const {
 void ZstdJob::run(vlscan_ctx* ctx, const uint8_t* zsrc, uint8_t* arena) {
     Impl& J = *m;
     if (J.frames.empty()) return;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_prep = now();
     J.prepare();
+    const double t_lists = now();
     const std::vector<uint32_t>& lists = J.lists;
     if (!ctx->zdev) ctx->zdev = new ZstdDev;
     ZstdDev& D = *ctx->zdev;
@@ -333,9 +337,12 @@ void ZstdJob::run(vlscan_ctx* ctx, const uint8_t* zsrc, uint8_t* arena) {
         auto up16 = [](size_t n) { return (n + 15) / 16 * 16; };
         const size_t nf = up16(J.frames.size() * sizeof(ZFrame)), nb = up16(J.blocks.size() * sizeof(ZBlock)), nl = up16(lists.size() * 4);
         uint8_t* h = (uint8_t*)D.ensure_hpin(nf + nb + nl + 64);
+        const double t_cp = now();
         J.spread_copy(h, J.frames.data(), J.frames.size() * sizeof(ZFrame));
         J.spread_copy(h + nf, J.blocks.data(), J.blocks.size() * sizeof(ZBlock));
         if (!lists.empty()) J.spread_copy(h + nf + nb, lists.data(), lists.size() * 4);
+        if (getenv("VLSCAN_DEBUG_TIMING")) fprintf(stderr, "[vlscan zstd] host: work lists of %zu launch groups %.1f ms, %.1f MB of tables to pinned memory %.1f ms (%d threads)\n",
+                                                   J.groups.size(), 1e3 * (t_lists - t_prep), (nf + nb + nl) / 1e6, 1e3 * (now() - t_cp), std::max(J.threads, 1));
         k_pull_words<<<296, 256, 0, st>>>(D.frames.as<uint4>(), (const uint4*)h, nf / 16); ctx->launches++;
         k_pull_words<<<296, 256, 0, st>>>(D.blocks.as<uint4>(), (const uint4*)(h + nf), nb / 16); ctx->launches++;
         if (nl) { k_pull_words<<<296, 256, 0, st>>>(D.lists.as<uint4>(), (const uint4*)(h + nf + nb), nl / 16); ctx->launches++; }
