@@ -77,8 +77,23 @@ int vlo_eval_predicate(int kind, const void* s, uint64_t sl, const void* a, uint
     case 10: return match_len_range(v, aux0, aux1);
     case 11: return match_string_range(v, x, y);
     case 12: { uint32_t n; return try_parse_ipv4(v, &n) && n >= aux0 && n <= aux1; }
+    case 14: return match_any_case_phrase(v, x);     // x = strings.ToLower(phrase)
+    case 15: return match_any_case_prefix(v, x);
+    case 16: case 17: case 18: {                     // x = phrase list: each phrase as varuint length + bytes
+        std::vector<std::string> phrases;
+        const uint8_t* p = (const uint8_t*)x.data(); size_t n = x.size();
+        while (n) { uint64_t l; int k = get_varuint(p, n, &l); if (k <= 0 || l > n - (size_t)k) return -1; phrases.emplace_back((const char*)p + k, l); p += k + l; n -= (size_t)k + l; }
+        return kind == 16 ? match_sequence(v, phrases) : kind == 17 ? match_all_phrases(v, phrases) : match_any_phrase(v, phrases);
+    }
     }
     return -1;
+}
+// strings.ToLower
+int64_t vlo_strings_to_lower(const void* s, uint64_t sl, char* out, uint64_t cap) {
+    std::string r = strings_to_lower(sv((const char*)s, sl));
+    if (r.size() > cap) return -1;
+    memcpy(out, r.data(), r.size());
+    return (int64_t)r.size();
 }
 int64_t vlo_skip_first_last_token(const void* s, uint64_t sl, char* out, uint64_t cap) {
     std::string r = skip_first_last_token(sv((const char*)s, sl));

@@ -136,6 +136,79 @@ def test_value_predicates_match_oracle(oracle):
         vs.eval_predicate(1, b"x")
 
 
+def test_next_value_predicates_match_oracle(oracle):
+    """The host builds of the predicates that are written for the device but not wired into the row kernels yet (csrc/vl_anycase.cuh):
+    i(phrase) / i(prefix*) on a value that is lowercased on the fly - never materialised -, seq(), contains_all(), contains_any().
+    Against the oracle, which lowercases into a buffer like the reference (stringsutil.AppendLowercase) and was pinned by the reference's
+    tables (tests/test_oracle_next_filters.py)."""
+    import random
+    rng = random.Random(20250924)
+    O = oracle.lib()
+    O.vlo_eval_predicate.argtypes = [C.c_int, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint64]
+    O.vlo_strings_to_lower.restype = C.c_int64
+
+    def lower(b):
+        out = C.create_string_buffer(4 * len(b) + 8)
+        n = O.vlo_strings_to_lower(b, C.c_uint64(len(b)), out, C.c_uint64(len(out)))
+        assert n >= 0
+        return out.raw[:n]
+
+    # letters whose lowercase has another byte length (İ -> i, Ⱥ -> ⱥ, K (Kelvin) -> k), cased and uncased scripts, digits, separators
+    alphabet = ["a", "B", "c", "Z", "é", "É", "й", "Й", "ß", "İ", "Ⱥ", "ⱥ", "K", "Σ", "ς", "日", "🙂", "𐐀", "𐐨", "0", "7", "_", " ", ".", "-", ":", "/"]
+
+    def rnd_text(lo=0, hi=10):
+        k = rng.randrange(5)
+        if k == 0:
+            return bytes(rng.choice(b"abAB 01._-") for _ in range(rng.randrange(lo, hi)))
+        if k == 1:
+            return bytes(rng.getrandbits(8) for _ in range(rng.randrange(lo, hi)))
+        s = "".join(rng.choice(alphabet) for _ in range(rng.randrange(lo, hi))).encode()
+        if k == 2 and s:                                           # damage the encoding somewhere
+            i = rng.randrange(len(s))
+            s = s[:i] + bytes([rng.choice([0x80, 0xC3, 0xE2, 0xF0, 0xFF])]) + s[i + rng.randrange(0, 2):]
+        return s
+
+    def sub_of(s):
+        if not s or rng.random() < 0.3:
+            return rnd_text(0, 4)
+        i = rng.randrange(len(s))
+        return s[i:i + rng.randrange(1, 6)]
+
+    def pack(phrases):
+        out = b""
+        for p in phrases:
+            n, enc = len(p), bytearray()
+            while n >= 0x80:
+                enc.append((n & 0x7F) | 0x80)
+                n >>= 7
+            enc.append(n)
+            out += bytes(enc) + p
+        return out
+
+    hits = {k: 0 for k in (14, 15, 16, 17, 18)}
+    for _ in range(30000):
+        s = rnd_text(0, 14)
+        needle = lower(sub_of(s) if rng.random() < 0.7 else rnd_text(0, 5))
+        for kind in (14, 15):
+            want = O.vlo_eval_predicate(kind, s, len(s), needle, len(needle), b"", 0, 0, 0)
+            assert want in (0, 1)
+            assert vs.eval_predicate(kind, s, needle) == bool(want), (kind, s, needle)
+            hits[kind] += want
+        phrases = [sub_of(s) if rng.random() < 0.8 else b"" for _ in range(rng.randrange(0, 4))]
+        packed = pack(phrases)
+        for kind in (16, 17, 18):
+            want = O.vlo_eval_predicate(kind, s, len(s), packed, len(packed), b"", 0, 0, 0)
+            assert want in (0, 1)
+            assert vs.eval_predicate(kind, s, packed) == bool(want), (kind, s, phrases)
+            hits[kind] += want
+    assert all(v > 2000 for v in hits.values()), hits
+    # the byte-length check happens before lowercasing (filter_any_case_phrase.go:164-166): Ⱥ (2 bytes) lowercases to ⱥ (3 bytes)
+    assert vs.eval_predicate(14, "Ⱥ".encode(), "ⱥ".encode()) is False and vs.eval_predicate(14, "ȺȺ".encode(), "ⱥ".encode()) is False
+    assert vs.eval_predicate(14, "Ⱥ x".encode(), "ⱥ".encode()) is True
+    assert vs.eval_predicate(14, "İstanbul".encode(), b"istanbul") is True and vs.eval_predicate(15, "X İSTANBUL".encode(), b"ist") is True
+    assert vs.eval_predicate(14, b"FOO\xffBAR", b"bar") is False and vs.eval_predicate(14, b"FOO\xff BAR", b"bar") is True     # an invalid byte counts as a token char
+
+
 def test_program_fields_and_errors():
     p = vs.Program(vs.Filter.and_([vs.Filter.phrase("", "GET"), vs.Filter.prefix("path", "api"), vs.Filter.in_("status", ["500", "502", "503"])]))
     assert p.fields() == [b"_msg", b"path", b"status"]

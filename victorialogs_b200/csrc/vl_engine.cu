@@ -15,6 +15,8 @@
 #include "vl_engine.h"
 #include "vl_program.h"
 #include "vl_part.h"
+#define VL_ANYCASE_HOST_ONLY 1   // only vlscan_eval_predicate uses these so far
+#include "vl_anycase.cuh"
 
 using namespace vl;
 
@@ -664,7 +666,17 @@ int64_t vlscan_program_leaf_tokens(const vlscan_program* prog, uint32_t leaf, ch
 }
 
 int vlscan_eval_predicate(int kind, const void* value, size_t value_len, const void* arg1, size_t arg1_len, const void* arg2, size_t arg2_len, uint64_t aux0, uint64_t aux1) {
-    if (kind < F_EXACT_PREFIX || kind > F_IPV4_RANGE || value_len > 0xFFFFFFFFull || arg1_len > 0xFFFFFFFFull || arg2_len > 0xFFFFFFFFull) return -1;
+    if (value_len > 0xFFFFFFFFull || arg1_len > 0xFFFFFFFFull || arg2_len > 0xFFFFFFFFull) return -1;
+    const uint8_t* v = (const uint8_t*)value; const uint32_t vn = (uint32_t)value_len;
+    const uint8_t* a = (const uint8_t*)arg1; const uint32_t an = (uint32_t)arg1_len;
+    switch (kind) {   // predicates of the kinds that are not wired into the row kernels yet (vl_anycase.cuh)
+    case 14: return vl::any_case_match(v, vn, a, an, false) ? 1 : 0;
+    case 15: return vl::any_case_match(v, vn, a, an, true) ? 1 : 0;
+    case 16: return vl::match_sequence(v, vn, vl::PhraseList{a, an}) ? 1 : 0;
+    case 17: return vl::match_all_phrases(v, vn, vl::PhraseList{a, an}) ? 1 : 0;
+    case 18: return vl::match_any_phrase(v, vn, vl::PhraseList{a, an}) ? 1 : 0;
+    }
+    if (kind < F_EXACT_PREFIX || kind > F_IPV4_RANGE) return -1;
     return vl::range_predicate(kind, (const uint8_t*)value, (uint32_t)value_len, (const uint8_t*)arg1, (uint32_t)arg1_len, (const uint8_t*)arg2, (uint32_t)arg2_len, aux0, aux1) ? 1 : 0;
 }
 
