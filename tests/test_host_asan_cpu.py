@@ -66,3 +66,30 @@ def test_part_reader_under_sanitizers(harness, tmp_path):
     path, files, originals, header = write_part(tmp_path, "part", seed=3)
     ok, bad = run(harness, "part", path, 4000, 3)
     assert ok > 200 and bad > 2000
+
+
+def test_threaded_header_walk_under_thread_sanitizer(tmp_path, oracle):
+    """tests/host_asan/walk_tsan.cpp: the multi-threaded walk (csrc/vl_zstd_job.h) over ~100 k values blocks on 1..33 threads under
+    ThreadSanitizer: no data race, one digest, one first error."""
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no g++")
+    exe = tmp_path / "walk_tsan"
+    r = subprocess.run([gxx, "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-fno-omit-frame-pointer", "-pthread", "-I", os.path.join(ROOT, "victorialogs_b200", "csrc"),
+                        os.path.join(ROOT, "tests", "host_asan", "walk_tsan.cpp"), "-o", str(exe)], capture_output=True, text=True, timeout=300)
+    if r.returncode != 0 and "tsan" in r.stderr and "cannot find" in r.stderr:
+        pytest.skip("ThreadSanitizer runtime not installed")
+    assert r.returncode == 0, r.stderr[-3000:]
+    seeds = tmp_path / "seeds"
+    seeds.mkdir()
+    k = 0
+    for rpb in (3000, 64, 9000):
+        cfg = oracle.GenConfig(seed=3, total_rows=rpb * 4, rows_per_block=rpb, hot_block_permille=500, hit_row_permille=60, columns_mask=0b1111)
+        for b in range(4):
+            for c in oracle.Block.generated(cfg, b).columns:
+                (seeds / ("%04d" % k)).write_bytes(c.values_block)
+                k += 1
+    r = subprocess.run([str(exe), str(seeds), "2000"], capture_output=True, text=True, timeout=600, env=dict(os.environ, TSAN_OPTIONS="halt_on_error=1"))
+    assert r.returncode == 0, (r.returncode, r.stdout[-500:], r.stderr[-4000:])
+    assert "ok groups=" in r.stdout and int(r.stdout.rsplit("=", 1)[1]) >= 2      # the run crossed launch-group boundaries
+    assert "WARNING: ThreadSanitizer" not in r.stderr
