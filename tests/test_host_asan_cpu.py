@@ -93,3 +93,16 @@ def test_threaded_header_walk_under_thread_sanitizer(tmp_path, oracle):
     assert r.returncode == 0, (r.returncode, r.stdout[-500:], r.stderr[-4000:])
     assert "ok groups=" in r.stdout and int(r.stdout.rsplit("=", 1)[1]) >= 2      # the run crossed launch-group boundaries
     assert "WARNING: ThreadSanitizer" not in r.stderr
+
+
+def test_next_predicates_build_as_device_code(tmp_path):
+    """csrc/vl_anycase.cuh is host+device: its host builds are checked against the oracle (tests/test_abi_cpu.py); here nvcc has to accept
+    the same functions inside a kernel for sm_100a - no stack frame, no spills."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("no nvcc")
+    r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-Xcudafe", "--diag_suppress=177", "-Xptxas", "-v",
+                        "-I", os.path.join(ROOT, "victorialogs_b200", "csrc"), "-c", os.path.join(ROOT, "tests", "host_asan", "anycase_kernel.cu"), "-o", str(tmp_path / "k.o")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert "0 bytes stack frame, 0 bytes spill stores, 0 bytes spill loads" in r.stderr
