@@ -476,22 +476,26 @@ struct ScanRun {
                 auto& evp = next_scan_events();
                 VL_CUDA(cudaEventRecord(evp.first, ctx->stream));
                 // persistent CTAs: exactly the resident set (148 SMs x resident CTAs per SM), each striding over the work items
-                static int occ_full = 0, occ_part = 0, occ_tma_full = 0, occ_tma_part = 0;
-                if (!occ_full) {
-                    VL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_full, k_substr_scan<true>, VL_SCAN_THREADS, 0));
-                    VL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_part, k_substr_scan<false>, VL_SCAN_THREADS, 0));
-                    VL_CUDA(cudaFuncSetAttribute(k_substr_scan_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VL_TMA_SMEM));
-                    VL_CUDA(cudaFuncSetAttribute(k_substr_scan_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VL_TMA_SMEM));
-                    VL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_tma_full, k_substr_scan_tma<true>, VL_SCAN_THREADS, VL_TMA_SMEM));
-                    VL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_tma_part, k_substr_scan_tma<false>, VL_SCAN_THREADS, VL_TMA_SMEM));
-                }
+                // (computed once per process, by whichever search worker gets here first: function-local static initialisation is thread safe)
+                struct ScanOcc {
+                    int full = 0, part = 0, tma_full = 0, tma_part = 0, aligned = 0;
+                    ScanOcc() {
+                        VL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&full, k_substr_scan<true>, VL_SCAN_THREADS, 0));
+                        VL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&part, k_substr_scan<false>, VL_SCAN_THREADS, 0));
+                        VL_CUDA(cudaFuncSetAttribute(k_substr_scan_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VL_TMA_SMEM));
+                        VL_CUDA(cudaFuncSetAttribute(k_substr_scan_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VL_TMA_SMEM));
+                        VL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tma_full, k_substr_scan_tma<true>, VL_SCAN_THREADS, VL_TMA_SMEM));
+                        VL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tma_part, k_substr_scan_tma<false>, VL_SCAN_THREADS, VL_TMA_SMEM));
+                        VL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&aligned, k_substr_scan_aligned, VL_SCAN_THREADS, 0));
+                    }
+                };
+                static const ScanOcc occ;
+                const int occ_full = occ.full, occ_part = occ.part, occ_tma_full = occ.tma_full, occ_tma_part = occ.tma_part, occ_al = occ.aligned;
                 if (use_tma) {
                     // TMA-staged variant: cp.async.bulk global->shared through a 4-stage mbarrier ring (see vl_kernels.cuh)
                     if (L.scan_needle_len >= 4) k_substr_scan_tma<true><<<ctx->sm_count * std::max(occ_tma_full, 1), VL_SCAN_THREADS, VL_TMA_SMEM, ctx->stream>>>(P, B, slot, sp, chunks, wc, ro, leaf_bm);
                     else k_substr_scan_tma<false><<<ctx->sm_count * std::max(occ_tma_part, 1), VL_SCAN_THREADS, VL_TMA_SMEM, ctx->stream>>>(P, B, slot, sp, chunks, wc, ro, leaf_bm);
                 } else if (aligned_ok) {
-                    static int occ_al = 0;
-                    if (!occ_al) VL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_al, k_substr_scan_aligned, VL_SCAN_THREADS, 0));
                     k_substr_scan_aligned<<<ctx->sm_count * std::max(occ_al, 1), VL_SCAN_THREADS, 0, ctx->stream>>>(P, B, slot, sp, tb, to, wc, ro, leaf_bm);
                 } else if (L.scan_needle_len >= 4) k_substr_scan<true><<<ctx->sm_count * std::max(occ_full, 1), VL_SCAN_THREADS, 0, ctx->stream>>>(P, B, slot, sp, tb, to, wc, ro, leaf_bm);
                 else k_substr_scan<false><<<ctx->sm_count * std::max(occ_part, 1), VL_SCAN_THREADS, 0, ctx->stream>>>(P, B, slot, sp, tb, to, wc, ro, leaf_bm);
