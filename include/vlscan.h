@@ -226,6 +226,9 @@ uint64_t vlscan_part_nblocks(const vlscan_part* part);
 /* blockHeader i in index order (streamID, then minTimestamp): accountID, projectID, streamID.hi, streamID.lo, uncompressedSizeBytes, rowsCount,
  * timestamps blockOffset, blockSize, minTimestamp, maxTimestamp, marshalType, columnsHeaderIndexOffset, -Size, columnsHeaderOffset, -Size */
 int vlscan_part_block_header(const vlscan_part* part, uint64_t i, uint64_t out[15]);
+/* the encoded timestamps of block i as stored in timestamps.bin (encoding.MarshalTimestamps; marshalType, first value = minTimestamp and
+ * rowsCount are in the block header): for the rows of blocks that only partly overlap a time range, until the engine filters _time itself */
+int vlscan_part_timestamps(const vlscan_part* part, uint64_t i, const uint8_t** data, uint64_t* len);
 uint32_t vlscan_part_ncolumn_names(const vlscan_part* part);
 const char* vlscan_part_column_name(const vlscan_part* part, uint32_t i, size_t* len);   /* "" is the message field */
 /* Descriptors of the blocks [block_lo, block_hi) whose [minTimestamp, maxTimestamp] overlaps [min_timestamp, max_timestamp], restricted to

@@ -90,6 +90,13 @@ def test_reader_hands_out_what_the_writer_was_given(tmp_path):
     assert hb.nblocks == len(originals) and hb.source == list(range(len(originals)))
     for i, (sid, b, ts) in enumerate(originals):
         check_block(hb, i, fields, b)
+        # the timestamps block: the bytes the writer stored, decodable with the header fields alone
+        bh = p.block_header(i)
+        data = p.timestamps(i)
+        assert (data, bh["ts_marshal_type"], bh["min_timestamp"], bh["max_timestamp"]) == b.timestamps_block()
+        assert list(vo.unmarshal_timestamps(data, bh["ts_marshal_type"], bh["min_timestamp"], bh["rows_count"])) == ts
+    with pytest.raises(vs.VlscanError, match="outside the part"):
+        p.timestamps(p.nblocks)
     # a field list in another order, "" as the name of the message field, a sub-range of blocks
     sub = [b"status", b"", b"host"]
     hb2 = p.blocks(sub, lo=2, hi=7)

@@ -922,6 +922,14 @@ int vlscan_part_block_header(const vlscan_part* part, uint64_t i, uint64_t out[1
         out[11] = b.chIndexOffset; out[12] = b.chIndexSize; out[13] = b.chOffset; out[14] = b.chSize;
     });
 }
+int vlscan_part_timestamps(const vlscan_part* part, uint64_t i, const uint8_t** data, uint64_t* len) {
+    return guarded(nullptr, [&] {
+        if (i >= part->r.blockHeaders.size()) throw BadInput("block index outside the part");
+        const vl::part::BlockHeader& b = part->r.blockHeaders[i];
+        if (b.tsSize > vl::part::kMaxTimestampsBlockSize) throw BadInput("timestamps block size is too big");   // getTimestamps block_search.go:490-493
+        *data = part->r.timestamps_file().at(b.tsOffset, b.tsSize, "a timestamps block"); *len = b.tsSize;
+    });
+}
 uint32_t vlscan_part_ncolumn_names(const vlscan_part* part) { return (uint32_t)part->r.columnNames.size(); }
 const char* vlscan_part_column_name(const vlscan_part* part, uint32_t i, size_t* len) { const std::string& s = part->r.columnNames[i]; *len = s.size(); return s.data(); }
 int vlscan_part_blocks(const vlscan_part* part, const char* const* field_names, const size_t* field_name_lens, uint32_t nfields, uint64_t block_lo, uint64_t block_hi,

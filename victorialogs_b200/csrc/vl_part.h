@@ -33,7 +33,7 @@
 namespace vl {
 namespace part {
 
-const uint64_t kFormatLatest = 3, kMaxRowsPerBlock = 8u << 20, kMaxColumnsPerBlock = 2000, kMaxIndexBlockSize = 8u << 20, kMaxValuesBlockSize = 8u << 20,
+const uint64_t kFormatLatest = 3, kMaxTimestampsBlockSize = 8u << 20, kMaxRowsPerBlock = 8u << 20, kMaxColumnsPerBlock = 2000, kMaxIndexBlockSize = 8u << 20, kMaxValuesBlockSize = 8u << 20,
                kMaxBloomFilterBlockSize = 8u << 20, kMaxColumnsHeaderSize = 8u << 20, kMaxColumnsHeaderIndexSize = 8u << 20;   // lib/logstorage/consts.go:6-59
 
 // inflates one ZSTD frame into exactly dst_len bytes (the Frame_Content_Size the caller read from the frame header); throws BadInput

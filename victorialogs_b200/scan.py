@@ -68,7 +68,7 @@ EXPORTS = ["vlscan_device_count", "vlscan_ctx_create", "vlscan_ctx_free", "vlsca
            "vlscan_program_create", "vlscan_program_free", "vlscan_program_nfields", "vlscan_program_field", "vlscan_program_leaf_tokens", "vlscan_format_float64", "vlscan_eval_predicate",
            "vlscan_batch_upload", "vlscan_batch_free", "vlscan_batch_nblocks", "vlscan_batch_rows", "vlscan_batch_words", "vlscan_batch_device_bytes",
            "vlscan_batch_generate", "vlscan_batch_download", "vlscan_host_blocks_get", "vlscan_host_blocks_field", "vlscan_host_blocks_bytes",
-           "vlscan_host_blocks_free", "vlscan_host_blocks_compress", "vlscan_zstd_decompress", "vlscan_zstd_inspect", "vlscan_zstd_walk_digest", "vlscan_part_open", "vlscan_part_free", "vlscan_part_header", "vlscan_part_nblocks", "vlscan_part_block_header",
+           "vlscan_host_blocks_free", "vlscan_host_blocks_compress", "vlscan_zstd_decompress", "vlscan_zstd_inspect", "vlscan_zstd_walk_digest", "vlscan_part_open", "vlscan_part_free", "vlscan_part_header", "vlscan_part_nblocks", "vlscan_part_block_header", "vlscan_part_timestamps",
            "vlscan_part_ncolumn_names", "vlscan_part_column_name", "vlscan_part_blocks", "vlscan_host_blocks_source", "vlscan_scan_resident", "vlscan_last_scan_stats", "vlscan_fetch_results", "vlscan_fetch_hits", "vlscan_result_device_ptrs", "vlscan_scan_batch"]
 
 
@@ -460,6 +460,14 @@ class Part:
         if rc:
             raise VlscanError(rc, lib().vlscan_last_error(None).decode("utf-8", "replace"))
         return {k: (_signed(out[j]) if k in ("min_timestamp", "max_timestamp") else out[j]) for j, k in enumerate(BLOCK_HEADER_FIELDS)}
+
+    def timestamps(self, i):
+        """-> the encoded timestamps block of block i (bytes of timestamps.bin); marshal type, first value and row count are in block_header(i)"""
+        p, n = C.c_void_p(), C.c_uint64()
+        rc = lib().vlscan_part_timestamps(self.h, C.c_uint64(i), C.byref(p), C.byref(n))
+        if rc:
+            raise VlscanError(rc, lib().vlscan_last_error(None).decode("utf-8", "replace"))
+        return C.string_at(p, n.value) if n.value else b""
 
     def blocks(self, fields, lo=0, hi=None, min_timestamp=-(1 << 63), max_timestamp=(1 << 63) - 1):
         """-> DownloadedBlocks-like descriptors (on-disk stage) of the blocks [lo, hi) overlapping the time range; .source = their indices in the part"""
