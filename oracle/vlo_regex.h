@@ -142,10 +142,23 @@ struct RegexParser {
             }
             RP n = mk(op); n->sub.push_back(a); n->rmin = mn; n->rmax = mx;
             if (op == R_REPEAT && (mn > 1000 || mx > 1000)) fail("invalid repeat count");
+            if (op == R_REPEAT && (mn >= 2 || mx >= 2) && !repeat_is_valid(n, 1000)) fail("invalid repeat count");   // parser.repeat, regexp/syntax/parse.go
             a = n;
             repeated = true;
         }
         return a;
+    }
+    // repeatIsValid (regexp/syntax/parse.go): nested {n,m} repeats may not multiply to more than 1000 copies of the innermost expression
+    static bool repeat_is_valid(const RP& re, int n) {
+        if (re->op == R_REPEAT) {
+            int m = re->rmax;
+            if (m == 0) return true;
+            if (m < 0) m = re->rmin;
+            if (m > n) return false;
+            if (m > 0) n /= m;
+        }
+        for (auto& s : re->sub) if (!repeat_is_valid(s, n)) return false;
+        return true;
     }
     bool parse_repeat_counts(int* mn, int* mx) {   // at '{'; on success pos is after '}'
         size_t p = pos + 1;

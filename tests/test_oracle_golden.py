@@ -239,6 +239,24 @@ def test_regexp_dotall_and_quirks(oracle):
         rm("a**", b"x")
 
 
+def test_regexp_repeat_limits(oracle):
+    """Go's parser rejects {n,m} repeats above 1000 and nested ones that multiply to more than 1000 copies (repeatIsValid,
+    regexp/syntax/parse.go); *, + and ? do not count.  The oracle and the product's compiler follow the same rule."""
+    from victorialogs_b200 import scan as vs
+    cases = {"x{1000}": True, "x{1001}": False, "x{2,1}": False, "(x{50}){50}": False, "(x{2}){500}": True, "(x{2}){501}": False, "((x{10}){10}){10}": True,
+             "((x{10}){10}){11}": False, "(?:x{0,1000}){2}": False, "(x{0}){5000}": False, "(x{1001}){0}": False, "(?:x{2}){0}y{1000}": True, "(x*){1000}": True,
+             "(x{1000})*": True, "(x{30}|y{41}){25}": False, "(x{2,}){500}": True, "(x{3,}){500}": False}
+    for rx, ok in cases.items():
+        if ok:
+            oracle.regex_match(rx, b"xx")
+            vs.Program(vs.Filter.regexp("_msg", rx))
+        else:
+            with pytest.raises(RuntimeError, match="invalid repeat count"):
+                oracle.regex_match(rx, b"xx")
+            with pytest.raises(vs.VlscanError, match="invalid repeat count"):
+                vs.Program(vs.Filter.regexp("_msg", rx))
+
+
 def test_regexp_vs_python_re(oracle):
     """Differential check of the oracle's Pike VM against Python's `re` on the declared syntax subset (boolean
     matching is independent of leftmost-first vs leftmost-longest). Subjects are ASCII + valid UTF-8."""

@@ -262,6 +262,20 @@ class RxParser {
         i_ = p + 1;
         return true;
     }
+    // repeatIsValid (regexp/syntax/parse.go): nested {n,m} repeats may not multiply to more than 1000 copies of the innermost expression
+    bool repeat_is_valid(int node, int n) {
+        const RxNode& re = t_.at(node);
+        if (re.op == RX_COUNTED) {
+            int m = re.hi;
+            if (m == 0) return true;
+            if (m < 0) m = re.lo;
+            if (m > n) return false;
+            if (m > 0) n /= m;
+        }
+        const std::vector<int> kids = re.kids;
+        for (int k : kids) if (!repeat_is_valid(k, n)) return false;
+        return true;
+    }
     int repetition() {
         int a = atom();
         if (a < 0) return a;
@@ -276,6 +290,7 @@ class RxParser {
             if (had) bad("invalid nested repetition operator");
             if (!done() && cur() == '?') i_++;   // non-greedy marker: irrelevant for boolean matching
             int n = t_.add(op); t_.at(n).kids.push_back(a); t_.at(n).lo = lo; t_.at(n).hi = hi;
+            if (op == RX_COUNTED && (lo >= 2 || hi >= 2) && !repeat_is_valid(n, 1000)) bad("invalid repeat count");   // parser.repeat, regexp/syntax/parse.go
             a = n;
         }
         return a;
