@@ -199,7 +199,10 @@ struct RegexParser {
         }
         }
     }
+    int depth = 0;
     RP parse_group() {
+        if (++depth > 1000) fail("expression nests too deeply");   // ErrNestingDepth (regexp/syntax maxHeight = 1000); here every parenthesis counts
+        struct Leave { int& d; ~Leave() { d--; } } leave{depth};
         pos++;   // (
         SavedFlags saved{fI, fS, fM};
         bool capture = true;

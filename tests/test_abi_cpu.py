@@ -209,6 +209,41 @@ def test_next_value_predicates_match_oracle(oracle):
     assert vs.eval_predicate(14, b"FOO\xffBAR", b"bar") is False and vs.eval_predicate(14, b"FOO\xff BAR", b"bar") is True     # an invalid byte counts as a token char
 
 
+def test_hostile_nesting_is_refused_not_crashed():
+    """Recursion of the compilers is bounded: a filter tree deeper than 64 levels and a regexp with more than 1000 open parentheses are
+    errors (Go's regexp refuses trees higher than 1000 too: ErrNestingDepth), not stack overflows.  Runs in a child so that a crash is a
+    test failure, not the end of the test session."""
+    import subprocess
+    import sys
+    import textwrap
+    child = textwrap.dedent('''
+        import sys
+        sys.path.insert(0, %r)
+        from victorialogs_b200 import scan as vs
+        leaf = vs.Filter.phrase("a", "b").blob
+        def tree(blob):
+            try:
+                vs.Program(vs.Filter(blob, "deep")); return "ok"
+            except vs.VlscanError as e:
+                return "nests too deeply" in str(e) and "deep"
+        assert tree(bytes([8]) * 60 + leaf) == "ok"
+        for n in (64, 5000, 99000):
+            assert tree(bytes([8]) * n + leaf) == "deep", n
+            assert tree((bytes([6, 2]) + leaf) * n + leaf) == "deep", n
+        def rx(n, open_="("):
+            try:
+                vs.Program(vs.Filter.regexp("_msg", open_ * n + "a" + ")" * n)); return "ok"
+            except vs.VlscanError as e:
+                return "nests too deeply" in str(e) and "deep"
+        assert rx(1000) == "ok" and rx(1000, "(?:") == "ok"
+        for n in (1001, 400000):
+            assert rx(n) == "deep" and rx(n, "(?:") == "deep" and rx(n, "(?i:") == "deep", n
+        print("fine")
+    ''')
+    r = subprocess.run([sys.executable, "-c", child % ROOT], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "fine" in r.stdout, (r.returncode, r.stdout[-300:], r.stderr[-1500:])
+
+
 def test_program_fields_and_errors():
     p = vs.Program(vs.Filter.and_([vs.Filter.phrase("", "GET"), vs.Filter.prefix("path", "api"), vs.Filter.in_("status", ["500", "502", "503"])]))
     assert p.fields() == [b"_msg", b"path", b"status"]

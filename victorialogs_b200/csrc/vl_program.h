@@ -238,9 +238,13 @@ class ProgramBuilder {
             else if (R.sub_kind == 1) scan(SCAN_CONTAINS, R.sub_off, R.sub_len);
         }
     }
+    int depth_ = 0;
     int node() {
         if (i_ >= n_) throw ProgError("truncated filter tree");
         if (P.nodes.size() > 100000) throw ProgError("filter tree too large");
+        // the compiler, the token merging and the scan interpreter recurse once per level, and the interpreter holds a bitmap register per level
+        if (++depth_ > 64) throw ProgError("filter tree nests too deeply (more than 64 levels)");
+        struct Leave { int& d; ~Leave() { d--; } } leave{depth_};
         int kind = p_[i_++];
         int id = (int)P.nodes.size(); P.nodes.emplace_back(); node_ft_.emplace_back(); node_ft_done_.push_back(false);
         P.nodes[id].kind = kind;

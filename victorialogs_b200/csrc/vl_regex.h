@@ -88,6 +88,7 @@ public:
 class RxParser {
     const std::string& s_; size_t i_ = 0; RxTree& t_;
     struct Mode { bool icase = false, dotnl = true, multiline = false; } m_;
+    int depth_ = 0;   // open parentheses: the parser and every later pass recurse once per level
 
     [[noreturn]] void bad(const std::string& why) const { throw RxError("error parsing regexp: " + why + ": `" + s_ + "`"); }
     bool done() const { return i_ >= s_.size(); }
@@ -205,6 +206,10 @@ class RxParser {
         return klass(rs);
     }
     int group() {
+        // Go (>= 1.19) refuses trees higher than 1000 (ErrNestingDepth, regexp/syntax/parse.go maxHeight); here every parenthesis counts, which also
+        // bounds the recursion of this compiler on hostile input
+        if (++depth_ > 1000) bad("expression nests too deeply");
+        struct Leave { int& d; ~Leave() { d--; } } leave{depth_};
         i_++;
         Mode outer = m_;
         bool capturing = true;
@@ -510,12 +515,15 @@ public:
         };
         intern({}, T_BEGIN);
         std::vector<int> cl;
+        size_t work = 0;   // NFA threads visited over all (state, class) pairs: bounds the compile time of hostile expressions to about a second
         for (uint32_t s = 0; s < states.size(); s++) {
             auto [pcs, prev] = states[s];
             std::vector<int> seeds = pcs; seeds.push_back(0);   // unanchored search: a new thread starts at every position
             d.trans.resize((size_t)(s + 1) * d.nclasses);
             for (uint32_t k = 0; k < d.nclasses; k++) {
                 bool m; closure(seeds, prev, ctype[k], cl, &m);
+                work += cl.size() + seeds.size();
+                if (work > 30000000) throw RxError("regexp is too complex for the DFA engine (work limit exceeded)");
                 std::vector<int> next;
                 for (int pc : cl) if (consumes(code_[pc], k)) next.push_back(pc + 1);
                 std::sort(next.begin(), next.end()); next.erase(std::unique(next.begin(), next.end()), next.end());
