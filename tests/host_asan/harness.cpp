@@ -44,7 +44,7 @@ static std::string mutate(const std::vector<std::string>& seeds) {
     std::string b = seeds[below(seeds.size())];
     static const uint8_t edge[] = {0x00, 0x01, 0x7F, 0x80, 0xFF, 0xFE, 0x28, 0xB5, 0x2F, 0xFD};
     for (int k = (int)below(4); k >= 0; k--) {
-        switch (below(8)) {
+        switch (below(9)) {
         case 0: if (!b.empty()) b[below(b.size())] = (char)rnd(); break;
         case 1: if (!b.empty()) b[below(b.size())] ^= (char)(1u << below(8)); break;
         case 2: if (!b.empty()) b.resize(below(b.size())); break;
@@ -53,6 +53,12 @@ static std::string mutate(const std::vector<std::string>& seeds) {
         case 5: { const std::string& o = seeds[below(seeds.size())]; size_t a = below(o.size() + 1), n = below(o.size() - a + 1); b.insert(below(b.size() + 1), o, a, n); break; }
         case 6: if (b.size() > 2) { size_t a = below(b.size()), n = below(std::min<size_t>(b.size() - a, 64) + 1); b.erase(a, n); } break;
         case 7: for (int i = (int)below(6); i >= 0; i--) b.push_back((char)rnd()); break;
+        case 8: {   // nesting bomb: a long run of one structural byte (NOT / AND / OR node kinds, parentheses, repetition)
+            static const char bomb[] = {8, 6, 7, '(', ')', '[', '{', '*', '|', '\\'};
+            const size_t len = below(4) ? below(300) : below(200000);
+            b.insert(below(b.size() + 1), len, bomb[below(sizeof bomb)]);
+            break;
+        }
         }
     }
     return b;
