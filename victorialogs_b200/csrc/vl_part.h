@@ -245,6 +245,7 @@ private:
     static std::vector<uint8_t> inflate_frame(const uint8_t* p, size_t n, const Inflate& inflate, const char* what) {
         std::vector<zs::ZBlock> blocks; zs::ZFrame fr{};
         try { zwalk::parse_frame_into(blocks, 0, p, n, 0, fr); } catch (const BadInput& e) { throw BadInput(std::string("cannot decompress ") + what + ": " + e.msg); }
+        if (fr.fcs > (256u << 20)) throw BadInput(std::string("cannot decompress ") + what + ": it claims to regenerate more than 256 MB");   // metadata: 56 B per index block, <= 128 KB per index block
         std::vector<uint8_t> out((size_t)fr.fcs);
         inflate(p, n, out.data(), out.size());
         return out;
