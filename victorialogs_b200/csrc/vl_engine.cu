@@ -660,7 +660,7 @@ int vlscan_program_create(const void* tree, size_t tree_len, vlscan_program** ou
 }
 void vlscan_program_free(vlscan_program* prog) { delete prog; }
 uint32_t vlscan_program_nfields(const vlscan_program* prog) { return (uint32_t)prog->p.fields.size(); }
-const char* vlscan_program_field(const vlscan_program* prog, uint32_t i, size_t* len) { *len = prog->p.fields[i].size(); return prog->p.fields[i].data(); }
+const char* vlscan_program_field(const vlscan_program* prog, uint32_t i, size_t* len) { if (i >= prog->p.fields.size()) { *len = 0; return nullptr; } *len = prog->p.fields[i].size(); return prog->p.fields[i].data(); }
 int64_t vlscan_program_leaf_tokens(const vlscan_program* prog, uint32_t leaf, char* buf, size_t cap) {
     if (leaf >= prog->p.leaf_tokens.size()) return -1;
     std::string s; for (size_t i = 0; i < prog->p.leaf_tokens[leaf].size(); i++) { if (i) s.push_back('\n'); s += prog->p.leaf_tokens[leaf][i]; }
@@ -931,7 +931,7 @@ int vlscan_part_timestamps(const vlscan_part* part, uint64_t i, const uint8_t** 
     });
 }
 uint32_t vlscan_part_ncolumn_names(const vlscan_part* part) { return (uint32_t)part->r.columnNames.size(); }
-const char* vlscan_part_column_name(const vlscan_part* part, uint32_t i, size_t* len) { const std::string& s = part->r.columnNames[i]; *len = s.size(); return s.data(); }
+const char* vlscan_part_column_name(const vlscan_part* part, uint32_t i, size_t* len) { if (i >= part->r.columnNames.size()) { *len = 0; return nullptr; } const std::string& s = part->r.columnNames[i]; *len = s.size(); return s.data(); }
 int vlscan_part_blocks(const vlscan_part* part, const char* const* field_names, const size_t* field_name_lens, uint32_t nfields, uint64_t block_lo, uint64_t block_hi,
                        int64_t min_timestamp, int64_t max_timestamp, vlscan_host_blocks** out) {
     *out = nullptr;
@@ -952,7 +952,7 @@ int vlscan_part_blocks(const vlscan_part* part, const char* const* field_names, 
 const uint64_t* vlscan_host_blocks_source(const vlscan_host_blocks* hb, uint64_t* n) { *n = hb->source.size(); return hb->source.data(); }
 
 const vlscan_block* vlscan_host_blocks_get(const vlscan_host_blocks* hb, uint64_t* nblocks, uint32_t* nfields) { *nblocks = hb->blocks.size(); *nfields = (uint32_t)hb->fields.size(); return hb->blocks.data(); }
-const char* vlscan_host_blocks_field(const vlscan_host_blocks* hb, uint32_t i, size_t* len) { *len = hb->fields[i].size(); return hb->fields[i].data(); }
+const char* vlscan_host_blocks_field(const vlscan_host_blocks* hb, uint32_t i, size_t* len) { if (i >= hb->fields.size()) { *len = 0; return nullptr; } *len = hb->fields[i].size(); return hb->fields[i].data(); }
 uint64_t vlscan_host_blocks_bytes(const vlscan_host_blocks* hb) { return hb->bytes; }
 void vlscan_host_blocks_free(vlscan_host_blocks* hb) { if (!hb) return; if (hb->pinned) cudaFreeHost(hb->pinned); delete hb; }
 
