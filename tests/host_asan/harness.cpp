@@ -1,6 +1,8 @@
 // Sanitizer build of the host-side parsers of libvlscan.so that read untrusted bytes:
 //   tree  the filter-tree program compiler incl. the regexp compiler (victorialogs_b200/csrc/vl_program.h, vl_regex.h)
 //   zstd  the bytes-block / ZSTD header walk                         (victorialogs_b200/csrc/vl_zstd_walk.h)
+//   pred  the per-value predicates and formatters that the row kernels run on every value - host builds of the same host+device code
+//         (vl_hd.cuh, vl_anycase.cuh): random values, needles and number bits in exact-size heap blocks
 //   part  the part directory reader                                  (victorialogs_b200/csrc/vl_part.h; the seed directory is ONE part directory,
 //         each iteration damages one of its files in a scratch copy; metadata frames are inflated with libzstd)
 // usage: harness tree|zstd|part <seed directory> <iterations> <rng seed>
@@ -18,6 +20,7 @@
 #include "vl_program.h"
 #include "vl_zstd_walk.h"
 #include "vl_part.h"
+#include "vl_anycase.cuh"
 
 extern "C" {   // the image has libzstd.so.1 but no zstd.h
 size_t ZSTD_decompress(void* dst, size_t dstCapacity, const void* src, size_t compressedSize);
@@ -62,6 +65,61 @@ static std::string mutate(const std::vector<std::string>& seeds) {
         }
     }
     return b;
+}
+
+// exact-size heap copy of a byte string (AddressSanitizer then sees any read past its end, and before its start)
+struct Exact {
+    std::unique_ptr<uint8_t[]> p; uint32_t n;
+    explicit Exact(const std::string& s) : p(new uint8_t[s.size() ? s.size() : 1]), n((uint32_t)s.size()) { if (n) memcpy(p.get(), s.data(), n); }
+};
+static std::string random_value() {
+    static const char* pieces[] = {"error", "GET", " ", "/api/v1", "10.0.0.1", ".", "-", "_", "0", "255", "2024-05-06T07:08:09.123Z", "\xc3\xa9", "\xd0\x99", "\xe6\x97\xa5", "\xf0\x9f\x99\x82", "\xc4\xb0", "\xc8\xba",
+                                   "\xff", "\xe2\x82", "\xf0\x9f", "A", "Z", "timeout", ":", "1e5", "-17", "18446744073709551615", "0.5"};
+    std::string v;
+    switch (below(4)) {
+    case 0: for (int i = (int)below(12); i > 0; i--) v += pieces[below(sizeof pieces / sizeof *pieces)]; break;
+    case 1: for (int i = (int)below(24); i > 0; i--) v.push_back((char)rnd()); break;
+    case 2: for (int i = (int)below(40); i > 0; i--) v.push_back("ab AB01._-:/"[below(12)]); break;
+    default: for (int i = (int)below(6); i > 0; i--) { v += pieces[below(sizeof pieces / sizeof *pieces)]; if (below(3) == 0) v.push_back((char)rnd()); } break;
+    }
+    return v;
+}
+static std::string pack_list(const std::vector<std::string>& v) {
+    std::string out;
+    for (auto& ph : v) { size_t n = ph.size(); while (n >= 0x80) { out.push_back((char)((n & 0x7F) | 0x80)); n >>= 7; } out.push_back((char)n); out += ph; }
+    return out;
+}
+static int fuzz_predicates(long iters) {
+    uint64_t acc = 0;
+    for (long it = 0; it < iters; it++) {
+        const std::string sv = random_value();
+        std::string nv = below(3) ? random_value() : sv.substr(below(sv.size() + 1), below(8));
+        const std::string bv = random_value();
+        Exact s(sv), a(nv), b(bv);
+        acc += vl::match_phrase(s.p.get(), s.n, a.p.get(), a.n) + 2 * vl::match_prefix(s.p.get(), s.n, a.p.get(), a.n) + 4 * vl::bytes_equal(s.p.get(), s.n, a.p.get(), a.n);
+        for (int kind = 9; kind <= 12; kind++) acc += vl::range_predicate(kind, s.p.get(), s.n, a.p.get(), a.n, b.p.get(), b.n, rnd() % 12, rnd() % 0x100000000ull);
+        acc += vl::any_case_match(s.p.get(), s.n, a.p.get(), a.n, false) + vl::any_case_match(s.p.get(), s.n, a.p.get(), a.n, true);
+        std::vector<std::string> phrases; for (int i = (int)below(4); i > 0; i--) phrases.push_back(below(2) ? sv.substr(below(sv.size() + 1), below(6)) : random_value().substr(0, below(5)));
+        std::string packed = pack_list(phrases);
+        if (below(8) == 0 && !packed.empty()) packed[below(packed.size())] = (char)rnd();      // a damaged list must not be read past its end either
+        Exact L(packed);
+        acc += vl::match_sequence(s.p.get(), s.n, vl::PhraseList{L.p.get(), L.n}) + vl::match_all_phrases(s.p.get(), s.n, vl::PhraseList{L.p.get(), L.n}) + vl::match_any_phrase(s.p.get(), s.n, vl::PhraseList{L.p.get(), L.n});
+        acc += vl::rune_count(s.p.get(), s.n) + (uint64_t)vl::bytes_cmp(s.p.get(), s.n, a.p.get(), a.n) + vl::xxh64(s.p.get(), s.n);
+        uint64_t u; uint32_t ip; acc += vl::parse_date_u64_hd(s.p.get(), s.n, &u) + vl::parse_ipv4_hd(s.p.get(), s.n, &ip);
+        int w; acc += (uint64_t)vl::decode_rune(s.p.get(), s.n, &w) + (uint64_t)vl::decode_last_rune(s.p.get(), s.n, &w);
+        // number -> text formatters into buffers of exactly the documented size
+        {
+            std::unique_ptr<uint8_t[]> f(new uint8_t[VL_FMT_F64_MAX]);
+            uint64_t bits = rnd(); if (below(4) == 0) bits &= 0x800FFFFFFFFFFFFFull; if (below(4) == 0) bits |= 0x7FE0000000000000ull;
+            const int n = vl::fmt_f64(f.get(), bits); if (n <= 0 || n > VL_FMT_F64_MAX) { fprintf(stderr, "fmt_f64 length %d\n", n); return 3; }
+            std::unique_ptr<uint8_t[]> g(new uint8_t[32]);
+            acc += (uint64_t)vl::fmt_u64(g.get(), rnd()) + (uint64_t)vl::fmt_i64(g.get(), (int64_t)rnd()) + (uint64_t)vl::fmt_ipv4(g.get(), (uint32_t)rnd());
+            const int64_t ns = below(2) ? (int64_t)rnd() : (int64_t)(rnd() % 4102444800ull) * 1000000000ll + (int64_t)(rnd() % 1000000000ull);   // any int64 / years 1970..2100
+            acc += (uint64_t)vl::fmt_iso8601(g.get(), ns);
+        }
+    }
+    printf("accepted %ld rejected %ld\n", iters, (long)(acc & 1));
+    return 0;
 }
 
 static std::string mutate_one(const std::string& in) { std::vector<std::string> one{in}; return mutate(one); }
@@ -117,6 +175,7 @@ static int fuzz_part(const char* dir, long iters) {
 int main(int argc, char** argv) {
     if (argc < 5) { fprintf(stderr, "usage: harness tree|zstd|part <seed dir> <iterations> <rng seed>\n"); return 2; }
     const std::string mode = argv[1];
+    if (mode == "pred") { rng_state ^= (uint64_t)atoll(argv[4]) * 0x9E3779B97F4A7C15ull; return fuzz_predicates(atol(argv[3])); }
     if (mode == "part") { rng_state ^= (uint64_t)atoll(argv[4]) * 0x9E3779B97F4A7C15ull; return fuzz_part(argv[2], atol(argv[3])); }
     const std::vector<std::string> seeds = read_seeds(argv[2]);
     const long iters = atol(argv[3]);

@@ -106,3 +106,10 @@ def test_next_predicates_build_as_device_code(tmp_path):
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-3000:]
     assert "0 bytes stack frame, 0 bytes spill stores, 0 bytes spill loads" in r.stderr
+
+
+def test_value_predicates_under_sanitizers(harness, tmp_path):
+    """the per-value predicates and number formatters of the row kernels (host builds of vl_hd.cuh / vl_anycase.cuh) on random values in
+    exact-size heap blocks: what the device runs on every log value must not read a byte outside the value or the needle"""
+    ok, bad = run(harness, "pred", tmp_path, 400000, 4)
+    assert ok == 400000
