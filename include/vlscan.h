@@ -150,6 +150,8 @@ int vlscan_format_float64(uint64_t ieee_bits, char* buf, size_t cap);
 /* Host build of the per-value predicate the row kernels run for filter kinds 9..12 (matchExactPrefix, matchLenRange,
  * matchStringRange, matchIPv4Range): arg1 = prefix / minValue, arg2 = maxValue, aux0..aux1 = minLen..maxLen or the IPv4
  * bounds.  Returns 1 / 0, or -1 for other kinds.  For tests against the oracle.
+ * kind 5 (REGEXP): arg1 = the expression; compiled like a regexp leaf and matched by the host mirror of the device automaton (the
+ * form const and dict values are matched with); -2 when the expression does not compile.
  * Also answers for the predicates that are written (host+device, csrc/vl_anycase.cuh) but not yet wired into the row kernels, under
  * provisional numbers: 14 = matchAnyCasePhrase, 15 = matchAnyCasePrefix (arg1 = the phrase / prefix already lowercased by
  * strings.ToLower), 16 = matchSequence, 17 = matchAllPhrases, 18 = matchAnyPhrase (arg1 = phrase list, each as varuint length + bytes). */

@@ -209,6 +209,58 @@ def test_next_value_predicates_match_oracle(oracle):
     assert vs.eval_predicate(14, b"FOO\xffBAR", b"bar") is False and vs.eval_predicate(14, b"FOO\xff BAR", b"bar") is True     # an invalid byte counts as a token char
 
 
+def test_regexp_automaton_matches_oracle(oracle):
+    """The compiled form of a regexp leaf - prefix / suffix split plus the rune-class DFA with delayed assertions, in its host mirror
+    (what const and dict values are matched with; the kernels step the same tables) - against the oracle's Pike VM on random expressions
+    of the supported syntax and random subjects (UTF-8, newlines, an invalid byte)."""
+    import random
+    rng = random.Random(7)
+    atoms = ["a", "b", "c", "x", "é", "й", "日", ".", "\\d", "\\w", "\\s", "\\W", "\\D", "[a-c]", "[^a-c]", "[0-9x]", "[[:alpha:]]", "\\.", "\\b", "\\B", "^", "$", "\\A", "\\z",
+             " ", "_", "0", "-", "foo", "bar", "(?i)q", "\\x41", "[é-я]"]
+
+    def gen(depth=0):
+        k = rng.randrange(10)
+        if depth > 3 or k < 4:
+            return rng.choice(atoms)
+        if k == 4:
+            return gen(depth + 1) + gen(depth + 1)
+        if k == 5:
+            return "(" + gen(depth + 1) + "|" + gen(depth + 1) + ")"
+        if k == 6:
+            return "(?:" + gen(depth + 1) + ")" + rng.choice(["*", "+", "?", "{2}", "{1,3}", "{0,2}", "*?", "{2,}"])
+        if k == 7:
+            return "(" + gen(depth + 1) + ")" + rng.choice(["*", "+", "?"])
+        if k == 8:
+            return rng.choice([".*", ".+"]) + gen(depth + 1) + rng.choice(["", ".*", ".+"])
+        return rng.choice(["(?i)", "(?s)", "(?m)", "(?-s)", "(?i:", "("]) + gen(depth + 1)
+
+    alphabet = ["a", "b", "c", "x", "A", "Q", "q", "é", "É", "й", "日", " ", "\n", "0", "9", "_", "-", ".", "foo", "bar"]
+    compared = 0
+    for _ in range(1500):
+        rx = gen()
+        rx += ")" * max(0, rx.count("(") - rx.count(")"))
+        try:
+            oracle.regex_match(rx, b"")
+            valid = True
+        except RuntimeError:
+            valid = False
+        for _ in range(10):
+            s = "".join(rng.choice(alphabet) for _ in range(rng.randrange(0, 9))).encode()
+            if rng.random() < 0.1:
+                s += b"\xff"
+            try:
+                got = vs.eval_predicate(5, s, rx.encode())
+            except ValueError:
+                got = None
+            if not valid:
+                assert got is None, ("the oracle rejects it, the compiler accepts it", rx)
+                break
+            assert got is not None, ("the compiler rejects it", rx)
+            assert got == oracle.regex_match(rx, s), (rx, s)
+            compared += 1
+    assert compared > 10000
+
+
 def test_hostile_nesting_is_refused_not_crashed():
     """Recursion of the compilers is bounded: a filter tree deeper than 64 levels and a regexp with more than 1000 open parentheses are
     errors (Go's regexp refuses trees higher than 1000 too: ErrNestingDepth), not stack overflows.  Runs in a child so that a crash is a

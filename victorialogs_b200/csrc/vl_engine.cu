@@ -674,6 +674,9 @@ int vlscan_eval_predicate(int kind, const void* value, size_t value_len, const v
     const uint8_t* v = (const uint8_t*)value; const uint32_t vn = (uint32_t)value_len;
     const uint8_t* a = (const uint8_t*)arg1; const uint32_t an = (uint32_t)arg1_len;
     switch (kind) {   // predicates of the kinds that are not wired into the row kernels yet (vl_anycase.cuh)
+    case F_REGEXP: {   // arg1 = the expression: compiled like a regexp leaf, matched by the host mirror of the device automaton (const / dict values take this path)
+        try { return vl::compile_regex(std::string((const char*)a, an)).match(v, vn) ? 1 : 0; } catch (const vl::RxError& e) { vl::set_thread_error(e.what()); return -2; }
+    }
     case 14: return vl::any_case_match(v, vn, a, an, false) ? 1 : 0;
     case 15: return vl::any_case_match(v, vn, a, an, true) ? 1 : 0;
     case 16: return vl::match_sequence(v, vn, vl::PhraseList{a, an}) ? 1 : 0;
