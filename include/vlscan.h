@@ -147,6 +147,10 @@ int64_t vlscan_program_leaf_tokens(const vlscan_program* prog, uint32_t leaf, ch
  * strconv.AppendFloat(f, 'f', -1, 64).  Host build of the routine the scan kernels run per row; returns the length
  * (<= 344) or -1 when cap is too small.  No NUL terminator is written. */
 int vlscan_format_float64(uint64_t ieee_bits, char* buf, size_t cap);
+/* how the program compiler reads a filter argument as a value of a typed column (tryParseUint64 / tryParseInt64 / tryParseFloat64Exact /
+ * tryParseIPv4 / tryParseTimestampISO8601, values_encoder.go:428-850): 1 and *out = the value (int64 and float64 as their bits) when the text
+ * is one, 0 when it is not, -1 for value types without a typed form.  For tests against the oracle. */
+int vlscan_parse_typed(int value_type, const void* s, size_t len, uint64_t* out);
 /* Host build of the per-value predicate the row kernels run for filter kinds 9..12 (matchExactPrefix, matchLenRange,
  * matchStringRange, matchIPv4Range): arg1 = prefix / minValue, arg2 = maxValue, aux0..aux1 = minLen..maxLen or the IPv4
  * bounds.  Returns 1 / 0, or -1 for other kinds.  For tests against the oracle.

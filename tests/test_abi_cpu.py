@@ -209,6 +209,60 @@ def test_next_value_predicates_match_oracle(oracle):
     assert vs.eval_predicate(14, b"FOO\xffBAR", b"bar") is False and vs.eval_predicate(14, b"FOO\xff BAR", b"bar") is True     # an invalid byte counts as a token char
 
 
+def test_typed_needles_match_oracle(oracle):
+    """How the program compiler reads a filter argument as a value of a typed column (the typed needles of phrase / exact / in() leaves)
+    against the oracle's tryParseUint64 / Int64 / Float64 / IPv4 / TimestampISO8601, on seeded number-like strings."""
+    import random
+    import struct
+    rng = random.Random(11)
+
+    def text():
+        k = rng.randrange(9)
+        if k == 0:
+            return str(rng.choice([0, 1, 7, 255, 256, 65535, 65536, 2 ** 32 - 1, 2 ** 32, 2 ** 53, 2 ** 53 + 1, 2 ** 63 - 1, 2 ** 63, 2 ** 64 - 1, 2 ** 64]) + rng.randrange(-1, 2))
+        if k == 1:
+            return rng.choice(["", "-", "+", "-0", "00", "01", "1_000", "_1", "1_", "1__0", "0x10", "1e5", "1E5", " 1", "1 ", "٣"]) + rng.choice(["", "5"])
+        if k == 2:
+            return "%s%d.%s" % (rng.choice(["", "-"]), rng.randrange(0, 10 ** rng.randrange(1, 18)), "".join(rng.choice("0123456789") for _ in range(rng.randrange(0, 18))))
+        if k == 3:
+            return rng.choice([".5", "5.", "1.2.3", "-.5", "1._5", "1.5_0", "0.000000000000000000001", "123456789012345678901234567", "1234567890123456789012345678"])
+        if k == 4:
+            return ".".join(str(rng.choice([0, 1, 9, 10, 99, 100, 255, 256, 999, 1000])) for _ in range(rng.choice([3, 4, 4, 4, 5])))
+        if k == 5:
+            return ".".join(rng.choice(["1", "01", "001", "1a", ":9", "/1", "", "25", "255"]) for _ in range(4))
+        if k == 6:
+            return "%04d-%02d-%02dT%02d:%02d:%02d.%03dZ" % (rng.choice([1676, 1677, 1970, 2024, 2262, 2263]), rng.randrange(0, 14), rng.randrange(0, 33), rng.randrange(0, 26),
+                                                          rng.randrange(0, 62), rng.randrange(0, 62), rng.randrange(0, 1000))
+        if k == 7:
+            base = "2024-05-06T07:08:09.123Z"
+            i = rng.randrange(len(base))
+            return base[:i] + rng.choice(["x", " ", "", "0", ":", "-"]) + base[i + 1:]
+        return str(rng.randrange(-10 ** 19, 10 ** 19))
+
+    hits = {}
+    for _ in range(40000):
+        s = text().encode()
+        u, ok = oracle.try_parse_uint64(s)
+        for vt in (vs.VT_UINT8, vs.VT_UINT64):
+            assert vs.parse_typed(vt, s) == (u if ok else None), (vt, s)
+        hits["u"] = hits.get("u", 0) + ok
+        i, ok = oracle.try_parse_int64(s)
+        assert vs.parse_typed(vs.VT_INT64, s) == ((i & (2 ** 64 - 1)) if ok else None), s
+        hits["i"] = hits.get("i", 0) + ok
+        f, ok = oracle.try_parse_float64(s)
+        assert vs.parse_typed(vs.VT_FLOAT64, s) == (struct.unpack("<Q", struct.pack("<d", f))[0] if ok else None), s
+        hits["f"] = hits.get("f", 0) + ok
+        ip, ok = oracle.try_parse_ipv4(s)
+        assert vs.parse_typed(vs.VT_IPV4, s) == (ip if ok else None), s
+        hits["ip"] = hits.get("ip", 0) + ok
+        t, ok = oracle.try_parse_iso8601(s)
+        assert vs.parse_typed(vs.VT_ISO8601, s) == ((t & (2 ** 64 - 1)) if ok else None), s
+        hits["ts"] = hits.get("ts", 0) + ok
+    assert all(v > 500 for v in hits.values()), hits
+    with pytest.raises(ValueError):
+        vs.parse_typed(vs.VT_STRING, b"x")
+
+
 def test_regexp_automaton_matches_oracle(oracle):
     """The compiled form of a regexp leaf - prefix / suffix split plus the rune-class DFA with delayed assertions, in its host mirror
     (what const and dict values are matched with; the kernels step the same tables) - against the oracle's Pike VM on random expressions

@@ -687,6 +687,19 @@ int vlscan_eval_predicate(int kind, const void* value, size_t value_len, const v
     return vl::range_predicate(kind, (const uint8_t*)value, (uint32_t)value_len, (const uint8_t*)arg1, (uint32_t)arg1_len, (const uint8_t*)arg2, (uint32_t)arg2_len, aux0, aux1) ? 1 : 0;
 }
 
+int vlscan_parse_typed(int value_type, const void* s, size_t len, uint64_t* out) {
+    const std::string v((const char*)s, len);
+    uint64_t u = 0; int64_t i = 0; double f = 0; uint32_t ip = 0;
+    switch (value_type) {
+    case VT_UINT8: case VT_UINT16: case VT_UINT32: case VT_UINT64: if (!vl::parse_u64(v, &u)) return 0; *out = u; return 1;
+    case VT_INT64: if (!vl::parse_i64(v, &i)) return 0; *out = (uint64_t)i; return 1;
+    case VT_FLOAT64: if (!vl::parse_f64_exact(v, &f)) return 0; memcpy(out, &f, 8); return 1;
+    case VT_IPV4: if (!vl::parse_ipv4(v, &ip)) return 0; *out = ip; return 1;
+    case VT_ISO8601: if (!vl::parse_iso8601(v, &i)) return 0; *out = (uint64_t)i; return 1;
+    }
+    return -1;
+}
+
 int vlscan_format_float64(uint64_t ieee_bits, char* buf, size_t cap) {
     uint8_t tmp[VL_FMT_F64_MAX];
     int n = vl::fmt_f64(tmp, ieee_bits);

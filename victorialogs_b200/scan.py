@@ -65,7 +65,7 @@ class GenConfig(C.Structure):
 
 
 EXPORTS = ["vlscan_device_count", "vlscan_ctx_create", "vlscan_ctx_free", "vlscan_last_error", "vlscan_ctx_stream", "vlscan_ctx_sync",
-           "vlscan_program_create", "vlscan_program_free", "vlscan_program_nfields", "vlscan_program_field", "vlscan_program_leaf_tokens", "vlscan_format_float64", "vlscan_eval_predicate",
+           "vlscan_program_create", "vlscan_program_free", "vlscan_program_nfields", "vlscan_program_field", "vlscan_program_leaf_tokens", "vlscan_format_float64", "vlscan_parse_typed", "vlscan_eval_predicate",
            "vlscan_batch_upload", "vlscan_batch_free", "vlscan_batch_nblocks", "vlscan_batch_rows", "vlscan_batch_words", "vlscan_batch_device_bytes",
            "vlscan_batch_generate", "vlscan_batch_download", "vlscan_host_blocks_get", "vlscan_host_blocks_field", "vlscan_host_blocks_bytes",
            "vlscan_host_blocks_free", "vlscan_host_blocks_compress", "vlscan_zstd_decompress", "vlscan_zstd_inspect", "vlscan_zstd_walk_digest", "vlscan_part_open", "vlscan_part_free", "vlscan_part_header", "vlscan_part_nblocks", "vlscan_part_block_header", "vlscan_part_timestamps",
@@ -133,6 +133,16 @@ def zstd_walk_digest(host_blocks, threads):
         raise VlscanError(rc, lib().vlscan_last_error(None).decode("utf-8", "replace"))
     return dict(digest=tuple(out[:4]), frames=out[4], blocks=out[5], groups=out[6], compressed_blocks=out[7], sequences=out[8],
                 walk_seconds=out[9] * 1e-9, lists_seconds=out[10] * 1e-9)
+
+
+def parse_typed(value_type, text):
+    """vlscan_parse_typed -> the value as an unsigned 64-bit pattern, or None when the text is not a value of that type"""
+    text = _b(text)
+    out = C.c_uint64()
+    r = lib().vlscan_parse_typed(C.c_int(value_type), text, C.c_size_t(len(text)), C.byref(out))
+    if r < 0:
+        raise ValueError(value_type)
+    return out.value if r else None
 
 
 def format_float64(bits):
