@@ -143,6 +143,10 @@ uint32_t vlscan_program_nfields(const vlscan_program* prog);
 const char* vlscan_program_field(const vlscan_program* prog, uint32_t i, size_t* len);
 /* token strings of a leaf (tests; mirrors filterPhrase.getTokens() etc.), '\n'-joined into buf; returns length or -1 */
 int64_t vlscan_program_leaf_tokens(const vlscan_program* prog, uint32_t leaf, char* buf, size_t cap);
+/* the per-field tokens of the bloom pre-pass of every AND / OR node (filterAnd.byFieldTokens filter_and.go:122-187, filterOr.byFieldTokens
+ * filter_or.go:126-193), nodes in pre-order, one line each: "A" or "O", then per field "\t" field "\x1f" token "\x1f" token ...; returns the
+ * length or -1 when cap is too small.  For tests against the oracle. */
+int64_t vlscan_program_prepass_tokens(const vlscan_program* prog, char* buf, size_t cap);
 /* text of a float64 column value as the filters see it: marshalFloat64String (values_encoder.go:1397-1399), i.e.
  * strconv.AppendFloat(f, 'f', -1, 64).  Host build of the routine the scan kernels run per row; returns the length
  * (<= 344) or -1 when cap is too small.  No NUL terminator is written. */

@@ -279,6 +279,23 @@ int64_t vlo_filter_tokens(void* h, char* out, uint64_t cap) {
     memcpy(out, s.data(), s.size()); return (int64_t)s.size();
 }
 
+// The per-field tokens of the bloom pre-pass of every AND / OR node of a tree (filterAnd.byFieldTokens / filterOr.byFieldTokens), in pre-order:
+// one line per node: "A" or "O", then for each field "\t" field "\x1f" token "\x1f" token ...
+static void dump_prepass(const FP& f, std::string& out) {
+    if (auto* a = dynamic_cast<FilterAnd*>(f.get())) {
+        out += "A"; for (auto& ft : a->by_field_tokens()) { out += "\t" + ft.field; for (auto& t : ft.tokens) out += "\x1f" + t; } out += "\n";
+        for (auto& k : a->filters) dump_prepass(k, out);
+    } else if (auto* o = dynamic_cast<FilterOr*>(f.get())) {
+        out += "O"; for (auto& ft : o->by_field_tokens()) { out += "\t" + ft.field; for (auto& t : ft.tokens) out += "\x1f" + t; } out += "\n";
+        for (auto& k : o->filters) dump_prepass(k, out);
+    } else if (auto* n = dynamic_cast<FilterNot*>(f.get())) dump_prepass(n->f, out);
+}
+int64_t vlo_filter_prepass_tokens(void* h, char* out, uint64_t cap) {
+    int64_t r = -1;
+    guard([&] { std::string s; dump_prepass(((FilterHandle*)h)->f, s); if (s.size() > cap) throw std::runtime_error("output buffer too small"); memcpy(out, s.data(), s.size()); r = (int64_t)s.size(); });
+    return r;
+}
+
 // blockSearch.search for one block: out_words must hold ceil(rows/64) u64. stats (6 u64, may be NULL) are ACCUMULATED.
 int vlo_block_search(void* block, void* filter, uint64_t* out_words, uint64_t* stats6) {
     return guard([&] {

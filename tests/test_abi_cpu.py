@@ -209,6 +209,81 @@ def test_next_value_predicates_match_oracle(oracle):
     assert vs.eval_predicate(14, b"FOO\xffBAR", b"bar") is False and vs.eval_predicate(14, b"FOO\xff BAR", b"bar") is True     # an invalid byte counts as a token char
 
 
+def test_and_or_prepass_tokens_match_oracle(oracle):
+    """The bloom pre-pass of AND / OR nodes prunes whole blocks, so wrong tokens there would be false negatives: the per-field tokens the
+    program compiler merges (union under AND incl. the common tokens of nested ORs, intersection under OR incl. nested ANDs) against the
+    oracle's getCommonTokensForAndFilters / getCommonTokensForOrFilters on the reference's AND / OR tables and on random trees."""
+    import random
+    rng = random.Random(13)
+    O = oracle.lib()
+    O.vlo_filter_prepass_tokens.restype = C.c_int64
+    L = vs.lib()
+    L.vlscan_program_prepass_tokens.restype = C.c_int64
+
+    def dump_oracle(f):
+        buf = C.create_string_buffer(1 << 20)
+        n = O.vlo_filter_prepass_tokens(f.h, buf, C.c_uint64(1 << 20))
+        assert n >= 0
+        return buf.raw[:n]
+
+    def dump_product(f):
+        p = vs.Program(f)
+        buf = C.create_string_buffer(1 << 20)
+        n = L.vlscan_program_prepass_tokens(p.h, buf, C.c_size_t(1 << 20))
+        assert n >= 0
+        return buf.raw[:n]
+
+    def canon(d):      # field order inside a node is not part of the contract; token order inside a field is (hash order is irrelevant, the set is not)
+        out = []
+        for line in d.split(b"\n")[:-1]:
+            parts = line.split(b"\t")
+            out.append((parts[0], sorted((p.split(b"\x1f")[0].replace(b"_msg", b"") or b"", tuple(sorted(p.split(b"\x1f")[1:]))) for p in parts[1:])))
+        return out
+
+    words = ["error", "timeout", "GET", "a b", "foo_bar", "x-y z", "conn refused", "é", "", "10.0.0.1", "a", "b"]
+    fields = ["_msg", "level", "path"]
+
+    def leaf(F):
+        k = rng.randrange(7)
+        f, w = rng.choice(fields), rng.choice(words)
+        if k == 0:
+            return F.phrase(f, w)
+        if k == 1:
+            return F.prefix(f, w)
+        if k == 2:
+            return F.exact(f, w)
+        if k == 3:
+            return F.regexp(f, rng.choice(["conn.*refused", "foo", "a+b", "err(or)? 5", ".*x.*"]))
+        if k == 4:
+            return F.in_(f, [rng.choice(words) for _ in range(rng.randrange(1, 4))])
+        if k == 5:
+            return F.exact_prefix(f, w)
+        return F.noop()
+
+    def tree(F, depth=0):
+        k = rng.randrange(6)
+        if depth >= 3 or k <= 1:
+            return leaf(F)
+        if k == 2:
+            return F.not_(tree(F, depth + 1))
+        kids = [tree(F, depth + 1) for _ in range(rng.randrange(1, 5))]
+        return F.and_(kids) if k in (3, 4) else F.or_(kids)
+
+    compared = 0
+    for (q, cols, pf, want), (_, _, of, _) in zip(and_or_cases(vs.Filter), and_or_cases(oracle.Filter)):
+        assert canon(dump_product(pf)) == canon(dump_oracle(of)), q
+        compared += 1
+    for trial in range(600):
+        state = rng.getstate()
+        pf = tree(vs.Filter)
+        rng.setstate(state)
+        of = tree(oracle.Filter)
+        a, b = canon(dump_product(pf)), canon(dump_oracle(of))
+        assert a == b, (trial, pf, a, b)
+        compared += len(a)
+    assert compared > 600
+
+
 def test_typed_needles_match_oracle(oracle):
     """How the program compiler reads a filter argument as a value of a typed column (the typed needles of phrase / exact / in() leaves)
     against the oracle's tryParseUint64 / Int64 / Float64 / IPv4 / TimestampISO8601, on seeded number-like strings."""

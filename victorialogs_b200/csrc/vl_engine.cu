@@ -687,6 +687,25 @@ int vlscan_eval_predicate(int kind, const void* value, size_t value_len, const v
     return vl::range_predicate(kind, (const uint8_t*)value, (uint32_t)value_len, (const uint8_t*)arg1, (uint32_t)arg1_len, (const uint8_t*)arg2, (uint32_t)arg2_len, aux0, aux1) ? 1 : 0;
 }
 
+int64_t vlscan_program_prepass_tokens(const vlscan_program* prog, char* buf, size_t cap) {
+    const Program& P = prog->p;
+    std::string s;
+    for (const PNode& nd : P.nodes) {   // nodes are numbered in pre-order
+        if (nd.kind != F_AND && nd.kind != F_OR) continue;
+        s += nd.kind == F_AND ? "A" : "O";
+        for (int k = 0; k < nd.prepass_count; k++) {
+            const DevPrepass& pp = P.prepass[(size_t)nd.prepass_begin + k];
+            s += "\t" + P.fields[pp.field];
+            const uint32_t* offs = (const uint32_t*)(P.blob.data() + pp.tok_offs_off);
+            for (uint32_t t = 0; t < pp.ntokens; t++) { s += "\x1f"; s.append((const char*)P.blob.data() + pp.tok_blob_off + offs[t], offs[t + 1] - offs[t]); }
+        }
+        s += "\n";
+    }
+    if (s.size() > cap) return -1;
+    memcpy(buf, s.data(), s.size());
+    return (int64_t)s.size();
+}
+
 int vlscan_parse_typed(int value_type, const void* s, size_t len, uint64_t* out) {
     const std::string v((const char*)s, len);
     uint64_t u = 0; int64_t i = 0; double f = 0; uint32_t ip = 0;
