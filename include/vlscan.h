@@ -147,6 +147,10 @@ int64_t vlscan_program_leaf_tokens(const vlscan_program* prog, uint32_t leaf, ch
  * filter_or.go:126-193), nodes in pre-order, one line each: "A" or "O", then per field "\t" field "\x1f" token "\x1f" token ...; returns the
  * length or -1 when cap is too small.  For tests against the oracle. */
 int64_t vlscan_program_prepass_tokens(const vlscan_program* prog, char* buf, size_t cap);
+/* the bloom probe hashes of an in() leaf (inValues.getTokensHashesAny, in_values.go:104-140,317-371): out = n_common, the common hashes,
+ * n_sets (UINT64_MAX when there are more than maxTokenSetsToInit = 1000 values and no set is kept), then per value set: n, hashes.
+ * Returns the number of u64 written, -1 when the leaf is not an in() or cap is too small.  For tests against the oracle. */
+int64_t vlscan_program_in_hashes(const vlscan_program* prog, uint32_t leaf, uint64_t* out, size_t cap);
 /* text of a float64 column value as the filters see it: marshalFloat64String (values_encoder.go:1397-1399), i.e.
  * strconv.AppendFloat(f, 'f', -1, 64).  Host build of the routine the scan kernels run per row; returns the length
  * (<= 344) or -1 when cap is too small.  No NUL terminator is written. */

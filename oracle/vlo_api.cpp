@@ -290,6 +290,18 @@ static void dump_prepass(const FP& f, std::string& out) {
         for (auto& k : o->filters) dump_prepass(k, out);
     } else if (auto* n = dynamic_cast<FilterNot*>(f.get())) dump_prepass(n->f, out);
 }
+// in(): the hashes of the common tokens, then of every per-value token set (in_values.go:317-371): out = [n_common, common..., n_sets, {n, hashes...}...]
+int64_t vlo_filter_in_hashes(void* h, uint64_t* out, uint64_t cap) {
+    auto* f = dynamic_cast<FilterIn*>(((FilterHandle*)h)->f.get());
+    if (!f) return -1;
+    std::vector<uint64_t> v;
+    v.push_back(f->commonHashes.size()); v.insert(v.end(), f->commonHashes.begin(), f->commonHashes.end());
+    v.push_back(f->tokenSetsHashes.size());
+    for (auto& s : f->tokenSetsHashes) { v.push_back(s.size()); v.insert(v.end(), s.begin(), s.end()); }
+    if (v.size() > cap) return -1;
+    memcpy(out, v.data(), v.size() * 8);
+    return (int64_t)v.size();
+}
 int64_t vlo_filter_prepass_tokens(void* h, char* out, uint64_t cap) {
     int64_t r = -1;
     guard([&] { std::string s; dump_prepass(((FilterHandle*)h)->f, s); if (s.size() > cap) throw std::runtime_error("output buffer too small"); memcpy(out, s.data(), s.size()); r = (int64_t)s.size(); });

@@ -284,6 +284,53 @@ def test_and_or_prepass_tokens_match_oracle(oracle):
     assert compared > 600
 
 
+def test_in_probe_hashes_match_oracle(oracle):
+    """in(): the hashes probed in the bloom filter - common tokens of all values, then the remaining tokens of every value, a block
+    being skipped when no value's set is contained (matchBloomFilterAnyTokenSet) - against the oracle, hash by hash."""
+    import random
+    import numpy as np
+    rng = random.Random(17)
+    O = oracle.lib()
+    O.vlo_filter_in_hashes.restype = C.c_int64
+    L = vs.lib()
+    L.vlscan_program_in_hashes.restype = C.c_int64
+    words = ["error", "timeout", "GET /api", "a b c", "foo_bar", "x-y z", "conn refused", "é ü", "", "10.0.0.1", "a", "b", "status 500", "status 502", "status"]
+
+    def parse(a):
+        a = [int(x) for x in a]
+        nc = a[0]
+        common, rest = sorted(a[1:1 + nc]), a[1 + nc:]
+        if rest[0] == 2 ** 64 - 1:
+            return common, None
+        sets, i = [], 1
+        for _ in range(rest[0]):
+            n = rest[i]
+            sets.append(tuple(sorted(rest[i + 1:i + 1 + n])))
+            i += 1 + n
+        assert i == len(rest)
+        return common, sets
+
+    for trial in range(400):
+        vals = [rng.choice(words) + rng.choice(["", " x", " timeout"]) for _ in range(rng.choice([0, 1, 2, 3, 5, 9]))]
+        if trial == 0:
+            vals = ["v%d common" % i for i in range(1001)]          # above maxTokenSetsToInit
+        pa = np.zeros(200000, dtype=np.uint64)
+        oa = np.zeros(200000, dtype=np.uint64)
+        p = vs.Program(vs.Filter.in_("f", vals))
+        n1 = L.vlscan_program_in_hashes(p.h, C.c_uint32(0), pa.ctypes.data_as(C.c_void_p), C.c_size_t(len(pa)))
+        f = oracle.Filter.in_("f", vals)
+        n2 = O.vlo_filter_in_hashes(f.h, oa.ctypes.data_as(C.c_void_p), C.c_uint64(len(oa)))
+        assert n1 > 0 and n2 > 0
+        pc, ps = parse(pa[:n1])
+        oc, os_ = parse(oa[:n2])
+        assert pc == oc, vals
+        if ps is None:
+            assert len(os_) > 1000                                  # the oracle keeps them and skips them at probe time, like the reference
+        else:
+            assert ps == os_, vals
+    assert L.vlscan_program_in_hashes(vs.Program(vs.Filter.phrase("f", "x")).h, C.c_uint32(0), pa.ctypes.data_as(C.c_void_p), C.c_size_t(8)) == -1
+
+
 def test_typed_needles_match_oracle(oracle):
     """How the program compiler reads a filter argument as a value of a typed column (the typed needles of phrase / exact / in() leaves)
     against the oracle's tryParseUint64 / Int64 / Float64 / IPv4 / TimestampISO8601, on seeded number-like strings."""

@@ -706,6 +706,25 @@ int64_t vlscan_program_prepass_tokens(const vlscan_program* prog, char* buf, siz
     return (int64_t)s.size();
 }
 
+int64_t vlscan_program_in_hashes(const vlscan_program* prog, uint32_t leaf, uint64_t* out, size_t cap) {
+    const Program& P = prog->p;
+    if (leaf >= P.leaves.size() || P.leaves[leaf].kind != F_IN) return -1;
+    const DevLeaf& L = P.leaves[leaf];
+    std::vector<uint64_t> v;
+    v.push_back(L.nhashes); v.insert(v.end(), P.u64s.begin() + L.hashes_off, P.u64s.begin() + L.hashes_off + L.nhashes);
+    if (L.in_skip_sets) v.push_back(UINT64_MAX);   // more than maxTokenSetsToInit value sets: none is kept
+    else {
+        v.push_back(L.in_nsets);
+        for (uint32_t k = 0; k < L.in_nsets; k++) {
+            const uint32_t off = P.u32s[L.in_sets_off + 2 * k], n = P.u32s[L.in_sets_off + 2 * k + 1];
+            v.push_back(n); v.insert(v.end(), P.u64s.begin() + off, P.u64s.begin() + off + n);
+        }
+    }
+    if (v.size() > cap) return -1;
+    memcpy(out, v.data(), v.size() * 8);
+    return (int64_t)v.size();
+}
+
 int vlscan_parse_typed(int value_type, const void* s, size_t len, uint64_t* out) {
     const std::string v((const char*)s, len);
     uint64_t u = 0; int64_t i = 0; double f = 0; uint32_t ip = 0;
