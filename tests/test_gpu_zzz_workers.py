@@ -35,7 +35,7 @@ def test_concurrent_workers_on_one_device():
             ctx = vs.Ctx(0)
             own = [vs.Program(t) for t in trees]                  # and programs of its own
             host, disk = slices[w]
-            barrier.wait()
+            barrier.wait(timeout=120)
             for r in range(rounds):
                 for k in range(len(trees)):
                     prog = shared[k] if (r + w) % 2 == 0 else own[k]
