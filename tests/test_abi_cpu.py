@@ -437,6 +437,48 @@ def test_regexp_automaton_matches_oracle(oracle):
     assert compared > 10000
 
 
+def test_host_entry_points_are_reentrant(oracle):
+    """8 host threads at once through the entry points that need no device: the (itself multi-threaded) header walk, the program compiler,
+    a malformed tree whose error text must stay on the calling thread, the regexp mirror.  (tests/test_gpu_zzz_workers.py does the same with
+    one vlscan_ctx per thread on a device.)"""
+    import threading
+    from parity_util import oracle_block_to_desc, field_names_of
+    cfg = oracle.GenConfig(seed=5, total_rows=3000 * 30, rows_per_block=3000, hot_block_permille=500, hit_row_permille=60, columns_mask=0b1111)
+    blocks = [oracle.Block.generated(cfg, i) for i in range(30)]
+    hb = vs.HostBlocks(field_names_of(blocks), [oracle_block_to_desc(b) for b in blocks] * 30)
+    ref = vs.zstd_walk_digest(hb, 1)["digest"]
+    F = vs.Filter
+    trees = [F.and_([F.phrase("_msg", "timeout"), F.phrase("level", "error")]), F.regexp("_msg", "conn.*refused"), F.or_([F.in_("status", ["500", "503"]), F.prefix("path", "api")])]
+    errors = []
+
+    def worker(w):
+        try:
+            for r in range(12):
+                if vs.zstd_walk_digest(hb, [0, 1, 4, 16][(r + w) % 4])["digest"] != ref:
+                    errors.append("digest differs")
+                for t in trees:
+                    p = vs.Program(t)
+                    p.fields()
+                    p.leaf_tokens(0)
+                try:
+                    vs.Program(vs.Filter(bytes([200 + w]), "bad"))
+                    errors.append("malformed tree accepted")
+                except vs.VlscanError as e:
+                    if ("unknown filter kind %d" % (200 + w)) not in str(e):
+                        errors.append("error text of another thread: " + str(e))
+                if not vs.eval_predicate(5, b"conn was refused", b"conn.*refused"):
+                    errors.append("regexp mirror")
+        except Exception as e:          # noqa: BLE001 - reported below
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(w,)) for w in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    assert not errors, errors[:3]
+
+
 def test_hostile_nesting_is_refused_not_crashed():
     """Recursion of the compilers is bounded: a filter tree deeper than 64 levels and a regexp with more than 1000 open parentheses are
     errors (Go's regexp refuses trees higher than 1000 too: ErrNestingDepth), not stack overflows.  Runs in a child so that a crash is a
