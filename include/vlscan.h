@@ -151,6 +151,9 @@ int64_t vlscan_program_prepass_tokens(const vlscan_program* prog, char* buf, siz
  * n_sets (UINT64_MAX when there are more than maxTokenSetsToInit = 1000 values and no set is kept), then per value set: n, hashes.
  * Returns the number of u64 written, -1 when the leaf is not an in() or cap is too small.  For tests against the oracle. */
 int64_t vlscan_program_in_hashes(const vlscan_program* prog, uint32_t leaf, uint64_t* out, size_t cap);
+/* the sorted typed value set an in() leaf is matched with on a column of `value_type` (inValues.getUint8Values ... getTimestampISO8601Values,
+ * in_values.go:141-315): uintN / ipv4 as numbers, int64 zig-zag coded, float64 as bits, iso8601 as nanoseconds.  Returns the count or -1. */
+int64_t vlscan_program_in_typed(const vlscan_program* prog, uint32_t leaf, int value_type, uint64_t* out, size_t cap);
 /* text of a float64 column value as the filters see it: marshalFloat64String (values_encoder.go:1397-1399), i.e.
  * strconv.AppendFloat(f, 'f', -1, 64).  Host build of the routine the scan kernels run per row; returns the length
  * (<= 344) or -1 when cap is too small.  No NUL terminator is written. */

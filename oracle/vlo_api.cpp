@@ -302,6 +302,18 @@ int64_t vlo_filter_in_hashes(void* h, uint64_t* out, uint64_t cap) {
     memcpy(out, v.data(), v.size() * 8);
     return (int64_t)v.size();
 }
+// in(): the typed value set for a column of value type vt (in_values.go:141-315) as sorted u64 (uintN / ipv4: the number; int64: zig-zag;
+// float64: the bits; iso8601: nanoseconds)
+int64_t vlo_filter_in_typed(void* h, int vt, uint64_t* out, uint64_t cap) {
+    auto* f = dynamic_cast<FilterIn*>(((FilterHandle*)h)->f.get());
+    if (!f) return -1;
+    std::vector<uint64_t> v;
+    for (auto& b : f->bin_values((uint8_t)vt)) { uint64_t x = 0; for (unsigned char c : b) x = (x << 8) | c; v.push_back(x); }
+    std::sort(v.begin(), v.end());
+    if (v.size() > cap) return -1;
+    memcpy(out, v.data(), v.size() * 8);
+    return (int64_t)v.size();
+}
 int64_t vlo_filter_prepass_tokens(void* h, char* out, uint64_t cap) {
     int64_t r = -1;
     guard([&] { std::string s; dump_prepass(((FilterHandle*)h)->f, s); if (s.size() > cap) throw std::runtime_error("output buffer too small"); memcpy(out, s.data(), s.size()); r = (int64_t)s.size(); });

@@ -329,6 +329,21 @@ def test_in_probe_hashes_match_oracle(oracle):
         else:
             assert ps == os_, vals
     assert L.vlscan_program_in_hashes(vs.Program(vs.Filter.phrase("f", "x")).h, C.c_uint32(0), pa.ctypes.data_as(C.c_void_p), C.c_size_t(8)) == -1
+    # the typed value sets a numeric column is matched with (in_values.go:141-315)
+    O.vlo_filter_in_typed.restype = C.c_int64
+    L.vlscan_program_in_typed.restype = C.c_int64
+    pool = ["0", "1", "255", "256", "65535", "65536", "4294967295", "4294967296", "18446744073709551615", "18446744073709551616", "-1", "-9223372036854775808", "007", "1_0",
+            "1.5", "-0.25", "1.50", "9007199254740993", "10.0.0.1", "255.255.255.255", "256.1.1.1", "1.2.3", "2024-05-06T07:08:09.123Z", "2024-05-06 07:08:09.123Z", "abc", ""]
+    nonempty = 0
+    for trial in range(200):
+        vals = [rng.choice(pool) for _ in range(rng.randrange(1, 9))]
+        p, f = vs.Program(vs.Filter.in_("f", vals)), oracle.Filter.in_("f", vals)
+        for vt in (vs.VT_UINT8, vs.VT_UINT16, vs.VT_UINT32, vs.VT_UINT64, vs.VT_INT64, vs.VT_FLOAT64, vs.VT_IPV4, vs.VT_ISO8601):
+            n1 = L.vlscan_program_in_typed(p.h, C.c_uint32(0), C.c_int(vt), pa.ctypes.data_as(C.c_void_p), C.c_size_t(len(pa)))
+            n2 = O.vlo_filter_in_typed(f.h, C.c_int(vt), oa.ctypes.data_as(C.c_void_p), C.c_uint64(len(oa)))
+            assert n1 == n2 >= 0 and list(pa[:n1]) == list(oa[:n2]), (vals, vt)
+            nonempty += n1 > 0
+    assert nonempty > 300
 
 
 def test_typed_needles_match_oracle(oracle):

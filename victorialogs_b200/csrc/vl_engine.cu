@@ -725,6 +725,16 @@ int64_t vlscan_program_in_hashes(const vlscan_program* prog, uint32_t leaf, uint
     return (int64_t)v.size();
 }
 
+int64_t vlscan_program_in_typed(const vlscan_program* prog, uint32_t leaf, int value_type, uint64_t* out, size_t cap) {
+    const Program& P = prog->p;
+    if (leaf >= P.leaves.size() || P.leaves[leaf].kind != F_IN || value_type < VT_UINT8 || value_type >= VT_MAX) return -1;
+    const DevLeaf& L = P.leaves[leaf];
+    const uint32_t n = L.in_typed_cnt[value_type];
+    if (n > cap) return -1;
+    if (n) memcpy(out, P.u64s.data() + L.in_typed_off[value_type], (size_t)n * 8);
+    return (int64_t)n;
+}
+
 int vlscan_parse_typed(int value_type, const void* s, size_t len, uint64_t* out) {
     const std::string v((const char*)s, len);
     uint64_t u = 0; int64_t i = 0; double f = 0; uint32_t ip = 0;
