@@ -202,17 +202,20 @@ def test_block_shape_edge_cases(env):
     check(env, shapes["single row"], (F.noop(), G.noop()))
 
 
-def test_long_needles_all_alignments_and_tile_boundaries(env):
-    """Needles of 7+ bytes take the aligned-word filter (k_substr_scan_aligned): every byte alignment of an occurrence, occurrences
-    at row starts / ends, overlapping occurrences, and occurrences straddling the 4 KiB / 16 KiB / 64 KiB work-item boundaries."""
+def test_needles_all_lengths_alignments_and_tile_boundaries(env):
+    """The substring scan looks at aligned 4-byte words only (k_substr_scan: per start alignment one (mask, pattern) pair, full masks from
+    7 bytes on): needles of every length 1..17, every byte alignment of an occurrence, occurrences at row starts / ends, overlapping
+    occurrences, occurrences straddling the 4 KiB / 16 KiB / 64 KiB work-item boundaries; phrase, prefix, and the regexp shapes that use the
+    scan (literal prefix + suffix automaton, `PREFIX.*LITERAL` scanned by its longer literal)."""
     oracle, vs, pu, ctx = env
     F, G = oracle.Filter, vs.Filter
     rng = np.random.default_rng(7)
-    for needle in [b"timeout", b"timeouts", b"abcdefghi", b"aaaaaaaa", b"conn refused", b"0123456789abcdef0"]:
+    for needle in [b"t", b"ti", b"GET", b"conn", b"error", b"timeou", b"timeout", b"timeouts", b"abcdefghi", b"aaaaaaaa", b"aaa", b"conn refused", b"0123456789abcdef0"]:
         rows = []
         for a in range(40):
             pad = b"." * a
-            rows += [pad + needle, pad + needle + b" tail", pad + b"x" + needle, pad + needle + b"x", pad + b" " + needle + b" ", needle[:-1] + pad, needle + needle, needle[:3] + needle]
+            rows += [pad + needle, pad + needle + b" tail", pad + b"x" + needle, pad + needle + b"x", pad + b" " + needle + b" ", needle[:-1] + pad, needle + needle, needle[:3] + needle,
+                     b"xq " + pad + needle, needle + pad + b" xq", b"xq" + needle, b"x" + pad + b"q" + needle]
         # long filler rows so that occurrences land on every kind of tile boundary: several 64 KiB tiles of data
         filler = [bytes(rng.integers(97, 123, int(rng.integers(50, 200)), dtype=np.uint8)) for _ in range(2500)]
         vals = []
@@ -226,8 +229,40 @@ def test_long_needles_all_alignments_and_tile_boundaries(env):
         assert len(data) > 200 * 1024
         for kind in ("phrase", "prefix"):
             check(env, [blk], (getattr(F, kind)("f", needle), getattr(G, kind)("f", needle)))
-        check(env, [blk], (F.regexp("f", needle.decode() + ".*"), G.regexp("f", needle.decode() + ".*")))
-        check(env, [blk], (F.regexp("f", needle.decode() + ".+tail"), G.regexp("f", needle.decode() + ".+tail")))
+        for expr in (needle.decode() + ".*", needle.decode() + ".+tail", "xq.*" + needle.decode(), needle.decode() + ".*xq", needle.decode() + "[ x]+t"):
+            check(env, [blk], (F.regexp("f", expr), G.regexp("f", expr)))
+
+
+def test_dense_candidates_and_ragged_lens(env):
+    """Every lane of a warp holds candidates at once: half of the rows match, rows of 0..600 bytes (u16 lens items), empty rows between
+    them, and a block of equally long rows (const lens item).  Same bits as the per-row reference loop."""
+    oracle, vs, pu, ctx = env
+    F, G = oracle.Filter, vs.Filter
+    rng = np.random.default_rng(11)
+    words = [b"timeout", b"timeouts", b"error", b"conn 10.0.0.7 refused", b"connection refuse", b"GET /api", b"message", b"terror"]
+    def row(maxlen):
+        parts = []
+        for _ in range(int(rng.integers(0, 6))):
+            parts.append(words[int(rng.integers(0, len(words)))] if rng.random() < 0.5 else bytes(rng.integers(97, 123, int(rng.integers(1, maxlen)), dtype=np.uint8)))
+        return b" ".join(parts)
+    ragged = [row(12) if i % 5 else b"" for i in range(6000)]          # short rows: the per-row matcher
+    ragged2 = [row(60) if i % 5 else b"" for i in range(6000)]         # the substring scan, empty rows in between
+    wide = [row(150) for _ in range(3000)]
+    assert max(len(v) for v in wide) > 255
+    fixed = [(b"timeout " if i % 2 else b"timeouts") + b"%056d" % i for i in range(5000)]   # 64 bytes each: const lens item, scanned
+    blocks = [oracle.Block.from_columns([("f", ragged), ("k", [b"%d" % i for i in range(len(ragged))])]),
+              oracle.Block.from_columns([("f", ragged2), ("k", [b"%d" % i for i in range(len(ragged2))])]),
+              oracle.Block.from_columns([("f", wide), ("k", [b"%d" % i for i in range(len(wide))])]),
+              oracle.Block.from_columns([("f", fixed), ("k", [b"%d" % i for i in range(len(fixed))])])]
+    for kind, arg in [("phrase", "timeout"), ("phrase", "error"), ("prefix", "time"), ("phrase", "GET"), ("phrase", "t"), ("regexp", "conn.*refused"), ("regexp", "timeout.*error"),
+                      ("regexp", "e.*timeouts"), ("regexp", "error [a-z]+ t")]:
+        for stage in ("ondisk", "decoded"):
+            check(env, blocks, (getattr(F, kind)("f", arg), getattr(G, kind)("f", arg)), stage)
+
+
+def test_tile_boundary_occurrences(env):
+    oracle, vs, pu, ctx = env
+    F, G = oracle.Filter, vs.Filter
     # an occurrence placed exactly across each boundary kind inside one huge row set
     base = b"q" * 100
     for boundary in (4096, 16384, 65536, 65536 + 4096):

@@ -416,8 +416,6 @@ struct ScanRun {
     void free_reg() { regs_used--; }
     void copy_reg(uint64_t* dst, const uint64_t* src) { if (B.nwords) VL_CUDA(cudaMemcpyAsync(dst, src, B.nwords * 8, cudaMemcpyDeviceToDevice, ctx->stream)); }
     void andnot(uint64_t* a, const uint64_t* b) { if (!B.nwords) return; k_andnot<<<cdiv(B.nwords, 256), 256, 0, ctx->stream>>>(a, b, B.nwords); launch_check(ctx); }
-    void block_any(const uint64_t* reg) { k_block_any<<<cdiv((uint64_t)B.nblocks * 32, 256), 256, 0, ctx->stream>>>(reg, B, ctx->alive.as<uint8_t>()); launch_check(ctx); }
-
     void prepass(const PNode& nd, uint64_t* reg) {
         if (nd.prepass_count == 0) return;
         std::vector<int> slots(nd.prepass_count);
@@ -426,9 +424,8 @@ struct ScanRun {
         size_t off = slots_cursor; slots_cursor += slots.size();
         ctx->slots.ensure(std::max<size_t>(slots_total * 4, 16));
         VL_CUDA(cudaMemcpyAsync(ctx->slots.as<int>() + off, slots.data(), slots.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-        block_any(reg);
         k_prepass<<<cdiv((uint64_t)B.nblocks * 32, 128), 128, 0, ctx->stream>>>(P, B, (uint32_t)nd.prepass_begin, (uint32_t)nd.prepass_count, ctx->slots.as<int>() + off,
-                                                                             nd.kind == F_OR, reg, ctx->alive.as<uint8_t>(), stats);
+                                                                             nd.kind == F_OR, reg, stats);
         launch_check(ctx);
     }
     size_t slots_cursor = 0, slots_total = 0;
@@ -438,12 +435,14 @@ struct ScanRun {
         if (L.kind == F_NOOP) return;
         int slot = field_slot[L.field];
         uint8_t* action = ctx->action.as<uint8_t>(); uint64_t* payload = ctx->payload.as<uint64_t>(); uint64_t* leaf_bm = ctx->leaf_bm.as<uint64_t>();
-        block_any(reg);
-        k_plan_leaf<<<cdiv((uint64_t)B.nblocks * 32, 128), 128, 0, ctx->stream>>>(P, B, (uint32_t)leaf_idx, slot, ctx->alive.as<uint8_t>(), action, payload, stats);
+        uint32_t* lens_blocks = ctx->lens_blocks.as<uint32_t>(); uint32_t* row_blocks = ctx->row_blocks.as<uint32_t>(); uint32_t* wc = ctx->work_count.as<uint32_t>();
+        uint32_t* tb = ctx->tile_block.as<uint32_t>(); uint32_t* to = ctx->tile_off.as<uint32_t>();
+        // bm.isZero() per block, header dispatch + leaf bloom probe -> per-block action, and the work lists of the kernels below
+        VL_CUDA(cudaMemsetAsync(wc, 0, WC_COUNT * 4, ctx->stream));
+        k_plan_leaf<<<cdiv(B.nblocks, VL_PLAN_WARPS), VL_PLAN_WARPS * 32, 0, ctx->stream>>>(P, B, (uint32_t)leaf_idx, slot, reg, action, payload, lens_blocks, row_blocks, tb, to, wc, stats);
         launch_check(ctx);
         if (slot >= 0 && B.nwords) {
-            uint32_t* wb = ctx->work_blocks.as<uint32_t>(); uint32_t* tp = ctx->tile_prefix.as<uint32_t>(); uint32_t* wc = ctx->work_count.as<uint32_t>();
-            uint32_t* ro = ctx->row_off64[slot].as<uint32_t>(); uint8_t* ready = ctx->ready[slot].as<uint8_t>();
+            uint32_t* ro = ctx->row_off8[slot].as<uint32_t>(); uint8_t* ready = ctx->ready[slot].as<uint8_t>();
             if (!ctx->ready_cleared[slot]) { VL_CUDA(cudaMemsetAsync(ready, 0, B.nblocks, ctx->stream)); ctx->ready_cleared[slot] = 1; }
             const int persistent = ctx->sm_count * 8;
             // which kernels can have work is known from the value types this field takes in the batch (header dispatch is per block,
@@ -451,64 +450,26 @@ struct ScanRun {
             const uint32_t vts = batch->slot_vt_mask.empty() ? ~0u : batch->slot_vt_mask[slot];
             const bool has_string = vts >> VT_STRING & 1, has_dict = vts >> VT_DICT & 1;
             const bool has_numeric = (vts & ~((1u << VT_STRING) | (1u << VT_DICT))) != 0;
+            const bool may_scan = L.str_strategy == STR_SCAN && has_string;
+            const bool may_row = (has_string && L.str_strategy != STR_ALL) || has_numeric;   // also the fallback of scan leaves for blocks with short rows (k_plan_leaf)
+            if (may_scan || may_row) { k_lens_offsets<<<persistent, 256, 0, ctx->stream>>>(B, slot, lens_blocks, wc, ro, ready, stats); launch_check(ctx); }
             // row-agnostic substring scan
-            if (L.str_strategy == STR_SCAN && has_string) {
+            if (may_scan) {
                 VL_CUDA(cudaMemsetAsync(leaf_bm, 0, B.nwords * 8, ctx->stream));
-                // default: the register-staged LDG.128 kernel (47.7 % of measured HBM peak on C2); VLSCAN_SCAN_VARIANT=tma selects the
-                // cp.async.bulk + mbarrier variant, which measured slower on B200 in round 1 (27 %) and is kept for the next round's tuning
-                static const bool use_tma = [] { const char* v = getenv("VLSCAN_SCAN_VARIANT"); return v && strcmp(v, "tma") == 0; }();
-                // work list of the blocks whose plan says ACT_SCAN, cut into 16 KiB chunks (TMA variant) or 64 KiB tiles (LDG variant)
-                k_build_worklist<<<1, 1024, 0, ctx->stream>>>(B, slot, action, (uint8_t)ACT_SCAN, use_tma ? (uint32_t)VL_TMA_CHUNK : (uint32_t)VL_TILE_BYTES, wb, tp, wc, stats, 1); launch_check(ctx);
-                k_lens_offsets<<<persistent, 256, 0, ctx->stream>>>(B, slot, wb, wc, ro, ready, stats); launch_check(ctx);
-                uint32_t* tb = ctx->tile_block.as<uint32_t>(); uint32_t* to = ctx->tile_off.as<uint32_t>();
-                ChunkDesc* chunks = ctx->chunks.as<ChunkDesc>();
-                if (use_tma) k_expand_chunks<<<persistent, 64, 0, ctx->stream>>>(B, slot, wb, tp, wc, chunks);
-                else k_expand_tiles<<<persistent, 64, 0, ctx->stream>>>(B, slot, wb, tp, wc, tb, to);
-                launch_check(ctx);
                 ScanParams sp; memset(&sp, 0, sizeof sp);
                 sp.mode = L.scan_mode; sp.needle_off = L.scan_needle_off; sp.needle_len = L.scan_needle_len; sp.starts_tok = L.starts_tok; sp.ends_tok = L.ends_tok; sp.regex = L.regex;
-                const uint8_t* nd = prog->p.blob.data() + L.scan_needle_off;
-                uint32_t k = std::min<uint32_t>(4, L.scan_needle_len);
-                for (uint32_t i = 0; i < k; i++) { sp.n4 |= (uint32_t)nd[i] << (8 * i); sp.m4 |= 0xFFu << (8 * i); }
-                const bool aligned_ok = L.scan_needle_len >= 7 && !getenv("VLSCAN_NO_ALIGNED");
-                if (aligned_ok) for (uint32_t s = 0; s < 4; s++) for (uint32_t i = 0; i < 4; i++) sp.sub4[s] |= (uint32_t)nd[s + i] << (8 * i);
+                const bool masked = fill_scan_patterns(prog->p.blob.data() + L.scan_needle_off, L.scan_needle_len, sp.pat, sp.msk, sp.delta, sp.nd16);
                 if (L.scan_mode == SCAN_CONTAINS || L.scan_mode >= SCAN_RX_DOTPLUS) { sp.starts_tok = sp.ends_tok = 0; }
                 auto& evp = next_scan_events();
                 VL_CUDA(cudaEventRecord(evp.first, ctx->stream));
-                // persistent CTAs: exactly the resident set (148 SMs x resident CTAs per SM), each striding over the work items
-                // (computed once per process, by whichever search worker gets here first: function-local static initialisation is thread safe)
-                struct ScanOcc {
-                    int full = 0, part = 0, tma_full = 0, tma_part = 0, aligned = 0;
-                    ScanOcc() {
-                        VL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&full, k_substr_scan<true>, VL_SCAN_THREADS, 0));
-                        VL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&part, k_substr_scan<false>, VL_SCAN_THREADS, 0));
-                        VL_CUDA(cudaFuncSetAttribute(k_substr_scan_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VL_TMA_SMEM));
-                        VL_CUDA(cudaFuncSetAttribute(k_substr_scan_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VL_TMA_SMEM));
-                        VL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tma_full, k_substr_scan_tma<true>, VL_SCAN_THREADS, VL_TMA_SMEM));
-                        VL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tma_part, k_substr_scan_tma<false>, VL_SCAN_THREADS, VL_TMA_SMEM));
-                        VL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&aligned, k_substr_scan_aligned, VL_SCAN_THREADS, 0));
-                    }
-                };
-                static const ScanOcc occ;
-                const int occ_full = occ.full, occ_part = occ.part, occ_tma_full = occ.tma_full, occ_tma_part = occ.tma_part, occ_al = occ.aligned;
-                if (use_tma) {
-                    // TMA-staged variant: cp.async.bulk global->shared through a 4-stage mbarrier ring (see vl_kernels.cuh)
-                    if (L.scan_needle_len >= 4) k_substr_scan_tma<true><<<ctx->sm_count * std::max(occ_tma_full, 1), VL_SCAN_THREADS, VL_TMA_SMEM, ctx->stream>>>(P, B, slot, sp, chunks, wc, ro, leaf_bm);
-                    else k_substr_scan_tma<false><<<ctx->sm_count * std::max(occ_tma_part, 1), VL_SCAN_THREADS, VL_TMA_SMEM, ctx->stream>>>(P, B, slot, sp, chunks, wc, ro, leaf_bm);
-                } else if (aligned_ok) {
-                    k_substr_scan_aligned<<<ctx->sm_count * std::max(occ_al, 1), VL_SCAN_THREADS, 0, ctx->stream>>>(P, B, slot, sp, tb, to, wc, ro, leaf_bm);
-                } else if (L.scan_needle_len >= 4) k_substr_scan<true><<<ctx->sm_count * std::max(occ_full, 1), VL_SCAN_THREADS, 0, ctx->stream>>>(P, B, slot, sp, tb, to, wc, ro, leaf_bm);
-                else k_substr_scan<false><<<ctx->sm_count * std::max(occ_part, 1), VL_SCAN_THREADS, 0, ctx->stream>>>(P, B, slot, sp, tb, to, wc, ro, leaf_bm);
+                // persistent CTAs: exactly the resident set (SMs x resident CTAs per SM), each striding over the tile table
+                if (masked) k_substr_scan<true><<<ctx->sm_count * ctx->scan_occ[1], VL_SCAN_THREADS, 0, ctx->stream>>>(P, B, slot, sp, tb, to, wc, ro, leaf_bm);
+                else k_substr_scan<false><<<ctx->sm_count * ctx->scan_occ[0], VL_SCAN_THREADS, 0, ctx->stream>>>(P, B, slot, sp, tb, to, wc, ro, leaf_bm);
                 launch_check(ctx);
                 VL_CUDA(cudaEventRecord(evp.second, ctx->stream));
             }
-            // per-row matcher (string exact / in / general regexp; numeric columns through text)
-            // (also the fallback of scan leaves for blocks with short rows, see k_plan_leaf); persistent grid over the ACT_ROW work list
-            if ((has_string && L.str_strategy != STR_ALL) || has_numeric) {
-                k_build_worklist<<<1, 1024, 0, ctx->stream>>>(B, slot, action, (uint8_t)ACT_ROW, (uint32_t)VL_TILE_BYTES, wb, tp, wc, stats, 0); launch_check(ctx);
-                k_lens_offsets<<<persistent, 256, 0, ctx->stream>>>(B, slot, wb, wc, ro, ready, stats); launch_check(ctx);
-                k_row_match<<<persistent, 256, 0, ctx->stream>>>(P, B, (uint32_t)leaf_idx, slot, wb, wc, payload, ro, leaf_bm); launch_check(ctx);
-            }
+            // per-row matcher (string exact / in / general regexp; numeric columns through text); persistent grid over the ACT_ROW work list
+            if (may_row) { k_row_match<<<persistent, 256, 0, ctx->stream>>>(P, B, (uint32_t)leaf_idx, slot, row_blocks, wc, payload, ro, leaf_bm); launch_check(ctx); }
             if (has_dict || has_numeric) { k_word_match<<<cdiv(B.nwords, 128), 128, 0, ctx->stream>>>(P, B, (uint32_t)leaf_idx, slot, action, payload, leaf_bm, stats); launch_check(ctx); }
         }
         if (B.nwords) { k_apply_leaf<<<cdiv(B.nwords, 256), 256, 0, ctx->stream>>>(B, action, leaf_bm, reg); launch_check(ctx); }
@@ -569,23 +530,22 @@ static void do_scan(vlscan_ctx* ctx, const vlscan_program* prog, const vlscan_ba
     for (size_t f = 0; f < pr.fields.size(); f++) for (uint32_t s = 0; s < batch->nfields; s++) if (batch->field_names[s] == pr.fields[f]) run.field_slot[f] = (int)s;
     for (auto& nd : pr.nodes) run.slots_total += nd.prepass_count;
     uint64_t nb = std::max<uint64_t>(batch->nblocks, 1), nw = std::max<uint64_t>(batch->nwords, 1);
-    ctx->alive.ensure(nb); ctx->action.ensure(nb); ctx->payload.ensure(nb * 8); ctx->leaf_bm.ensure(nw * 8);
-    ctx->work_blocks.ensure(nb * 4); ctx->tile_prefix.ensure((nb + 1) * 4); ctx->work_count.ensure(16);
+    ctx->action.ensure(nb); ctx->payload.ensure(nb * 8); ctx->leaf_bm.ensure(nw * 8);
+    ctx->lens_blocks.ensure(nb * 4); ctx->row_blocks.ensure(nb * 4); ctx->work_count.ensure(WC_COUNT * 4);
     {   // upper bound of 64 KiB tiles of any single column: every payload byte belongs to one column, plus one partial tile per block
-        uint64_t max_tiles = batch->arena_bytes / VL_TILE_BYTES + nb + 16, max_chunks = batch->arena_bytes / VL_TMA_CHUNK + nb + 16;
-        ctx->tile_block.ensure(max_tiles * 4); ctx->tile_off.ensure(max_tiles * 4); ctx->chunks.ensure(max_chunks * sizeof(ChunkDesc));
+        uint64_t max_tiles = batch->arena_bytes / VL_TILE_BYTES + nb + 16;
+        ctx->tile_block.ensure(max_tiles * 4); ctx->tile_off.ensure(max_tiles * 4);
     }
     ctx->stats.ensure(ST_COUNT * 8); ctx->totals.ensure(32); ctx->counts.ensure(nb * 4);
-    if (ctx->row_off64.size() < batch->nfields) { ctx->row_off64.resize(batch->nfields); ctx->ready.resize(batch->nfields); }
+    if (ctx->row_off8.size() < batch->nfields) { ctx->row_off8.resize(batch->nfields); ctx->ready.resize(batch->nfields); }
     ctx->ready_cleared.assign(batch->nfields, 0);
-    for (uint32_t s = 0; s < batch->nfields; s++) { ctx->row_off64[s].ensure(nw * 4); ctx->ready[s].ensure(nb); }
+    for (uint32_t s = 0; s < batch->nfields; s++) { ctx->row_off8[s].ensure(nw * 32); ctx->ready[s].ensure(nb); }
     uint64_t launches0 = ctx->launches;
     ctx->scan_events_used = 0;
     run.stats = ctx->stats.as<unsigned long long>();
     VL_CUDA(cudaEventRecord(ctx->ev_begin, ctx->stream));
     VL_CUDA(cudaMemsetAsync(ctx->stats.p, 0, ST_COUNT * 8, ctx->stream));
     VL_CUDA(cudaMemsetAsync(ctx->totals.p, 0, 32, ctx->stream));
-    VL_CUDA(cudaMemsetAsync(ctx->work_count.p, 0, 16, ctx->stream));
     // bm.init(rows); bm.setBits()   (block_search.go:213-214)
     uint64_t* reg = run.new_reg();
     run.copy_reg(reg, batch->init_bitmap.as<uint64_t>());
@@ -622,6 +582,10 @@ vlscan_ctx* vlscan_ctx_create(int device) {
         VL_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         VL_CUDA(cudaEventCreate(&ctx->ev_begin)); VL_CUDA(cudaEventCreate(&ctx->ev_end));
         cudaDeviceProp prop; VL_CUDA(cudaGetDeviceProperties(&prop, ctx->device)); ctx->sm_count = prop.multiProcessorCount;
+        // resident CTAs per SM of the two scan instantiations on THIS device (the persistent grids are sized by it)
+        VL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->scan_occ[0], k_substr_scan<false>, VL_SCAN_THREADS, 0));
+        VL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->scan_occ[1], k_substr_scan<true>, VL_SCAN_THREADS, 0));
+        for (int& o : ctx->scan_occ) o = std::max(o, 1);
     });
     if (rc) { delete ctx; return nullptr; }
     return ctx;
@@ -631,9 +595,9 @@ void vlscan_ctx_free(vlscan_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    for (DevBuf* b : {&ctx->alive, &ctx->action, &ctx->payload, &ctx->leaf_bm, &ctx->work_blocks, &ctx->tile_prefix, &ctx->work_count, &ctx->stats, &ctx->totals, &ctx->counts, &ctx->slots, &ctx->hit_offs, &ctx->hits, &ctx->tile_block, &ctx->tile_off, &ctx->chunks}) b->release();
+    for (DevBuf* b : {&ctx->action, &ctx->payload, &ctx->leaf_bm, &ctx->lens_blocks, &ctx->row_blocks, &ctx->work_count, &ctx->stats, &ctx->totals, &ctx->counts, &ctx->slots, &ctx->hit_offs, &ctx->hits, &ctx->tile_block, &ctx->tile_off}) b->release();
     for (auto& r : ctx->regs) r.release();
-    for (auto& r : ctx->row_off64) r.release();
+    for (auto& r : ctx->row_off8) r.release();
     for (auto& r : ctx->ready) r.release();
     ctx->zsrc.release(); ctx->zcols.release(); ctx->ztest.release();
     zstd_dev_free(ctx->zdev);

@@ -76,10 +76,10 @@ struct vlscan_ctx {
     std::string err;
     uint64_t launches = 0;
     // scratch (grow-only)
-    vl::DevBuf alive, action, payload, leaf_bm, work_blocks, tile_prefix, work_count, stats, totals, counts, slots, hit_offs, hits, tile_block, tile_off, chunks;
+    vl::DevBuf action, payload, leaf_bm, lens_blocks, row_blocks, work_count, stats, totals, counts, slots, hit_offs, hits, tile_block, tile_off;
     std::vector<vl::DevBuf> regs;          // bitmap registers of the tree interpreter
-    std::vector<vl::DevBuf> row_off64;     // per batch field slot
-    std::vector<vl::DevBuf> ready;         // per batch field slot: row_off64 computed for block b in this scan
+    std::vector<vl::DevBuf> row_off8;      // per batch field slot: byte offset of every 8th row (k_lens_offsets)
+    std::vector<vl::DevBuf> ready;         // per batch field slot: row_off8 computed for block b in this scan
     std::vector<char> ready_cleared;
     vl::DevBuf zsrc, zcols, ztest;         // compressed staging of on-disk values blocks; their column list; test output
     vl::ZstdDev* zdev = nullptr;           // device ZSTD decoder scratch (vl_zstd.cu)
@@ -92,6 +92,7 @@ struct vlscan_ctx {
     bool has_result = false;
     uint64_t last_launches = 0;
     int sm_count = 148;
+    int scan_occ[2] = {1, 1};              // resident CTAs per SM of k_substr_scan<false> / <true> on this device
     void* ensure_pinned(size_t n);
 };
 

@@ -165,15 +165,12 @@ static __device__ bool bloom_contains_all_warp(const uint8_t* bloom_be, uint32_t
 }
 
 // ---- bitmap helpers --------------------------------------------------------------------------------------------------
-// alive[b] = bitmap of block b is non-zero (bitmap.isZero, bitmap.go:74-81); one warp per block
-static __global__ void k_block_any(const uint64_t* __restrict__ reg, BatchView B, uint8_t* __restrict__ alive) {
-    uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (b >= B.nblocks) return;
-    uint64_t lo = B.blk_word_off[b], hi = B.blk_word_off[b + 1];
+// is the bitmap of block b non-zero (bitmap.isZero, bitmap.go:74-81)?  All 32 lanes call with the same b; the result is uniform.
+static __device__ __forceinline__ bool block_alive_warp(const uint64_t* __restrict__ reg, const BatchView& B, uint32_t b) {
+    const uint64_t lo = B.blk_word_off[b], hi = B.blk_word_off[b + 1];
     bool any = false;
     for (uint64_t w = lo + lane_id(); w < hi; w += 32) any |= reg[w] != 0;
-    any = __any_sync(0xffffffffu, any);
-    if (lane_id() == 0) alive[b] = any;
+    return __any_sync(0xffffffffu, any);
 }
 static __global__ void k_andnot(uint64_t* __restrict__ a, const uint64_t* __restrict__ b, uint64_t n) {   // bitmap.andNot bitmap.go:99-111
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -183,9 +180,9 @@ static __global__ void k_andnot(uint64_t* __restrict__ a, const uint64_t* __rest
 // ---- AND / OR bloom pre-pass (filterAnd.matchBloomFilters filter_and.go:76-111, filterOr.matchBloomFilters filter_or.go:80-115) ----
 // one warp per block; a failing block gets its bitmap words zeroed (bm.resetBits()).
 static __global__ void k_prepass(DevProgram P, BatchView B, uint32_t pp_begin, uint32_t pp_count, const int* __restrict__ slots /* per prepass entry */,
-                          int is_or, uint64_t* __restrict__ reg, const uint8_t* __restrict__ alive, unsigned long long* __restrict__ stats) {
+                          int is_or, uint64_t* __restrict__ reg, unsigned long long* __restrict__ stats) {
     uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (b >= B.nblocks || !alive[b]) return;
+    if (b >= B.nblocks || !block_alive_warp(reg, B, b)) return;
     bool pass = is_or ? false : true;
     unsigned long long bloom_bytes = 0;
     for (uint32_t e = 0; e < pp_count; e++) {
@@ -229,15 +226,29 @@ static __global__ void k_prepass(DevProgram P, BatchView B, uint32_t pp_begin, u
 // ---- per (block, leaf) header dispatch: const / missing / dict / typed columns + leaf-level bloom probe ----------------------------
 // filterPhrase.applyToBlockSearch filter_phrase.go:61-111, filterPrefix :59-106, filterExact :186-235, filterIn :120-185,
 // filterRegexp :78-127 and the match*By* helpers they call.  One warp per block, all lanes run the same scalar logic.
-static __global__ void k_plan_leaf(DevProgram P, BatchView B, uint32_t leaf_idx, int slot, const uint8_t* __restrict__ alive,
-                            uint8_t* __restrict__ action, uint64_t* __restrict__ payload, unsigned long long* __restrict__ stats) {
-    uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (b >= B.nblocks) return;
+// The same kernel decides bm.isZero() for the block and appends the block to the work lists of the kernels that follow: blocks whose lens
+// items must be decoded, the 64 KiB tiles of the row-agnostic scan, blocks of the per-row matcher.  The lists are unordered (appended with
+// one atomic per CTA and list): every consumer only needs the set.
+#define VL_PLAN_WARPS 8
+enum { WC_LENS = 0, WC_TILES = 1, WC_ROW = 2, WC_COUNT = 4 };
+#define VL_TILE_BYTES 65536u                  /* row bytes per work item of the substring scan */
+static __global__ void __launch_bounds__(VL_PLAN_WARPS * 32) k_plan_leaf(DevProgram P, BatchView B, uint32_t leaf_idx, int slot, const uint64_t* __restrict__ reg,
+                            uint8_t* __restrict__ action, uint64_t* __restrict__ payload, uint32_t* __restrict__ lens_blocks, uint32_t* __restrict__ row_blocks,
+                            uint32_t* __restrict__ tile_block, uint32_t* __restrict__ tile_off, uint32_t* __restrict__ work_count,
+                            unsigned long long* __restrict__ stats) {
+    __shared__ uint32_t s_cnt[VL_PLAN_WARPS][3], s_off[VL_PLAN_WARPS][3];
+    __shared__ unsigned long long s_stat[VL_PLAN_WARPS][4];
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t b = blockIdx.x * VL_PLAN_WARPS + warp;
     const DevLeaf& L = P.leaves[leaf_idx];
-    uint8_t act = ACT_ALL; uint64_t pay = 0;
-    unsigned long long bloom_bytes = 0, values_bytes = 0; int err = 0;
-    if (!alive[b]) { if (lane_id() == 0) action[b] = ACT_NONE; return; }
-    if (L.kind == F_NOOP) { if (lane_id() == 0) action[b] = ACT_ALL; return; }
+    uint8_t act = ACT_NONE; uint64_t pay = 0;
+    unsigned long long bloom_bytes = 0, values_bytes = 0, scan_bytes = 0; int err = 0;
+    uint32_t need_lens = 0, need_row = 0, ntiles = 0;
+    const bool valid = b < B.nblocks;
+    const bool alive = valid && block_alive_warp(reg, B, b);
+    if (alive && L.kind == F_NOOP) act = ACT_ALL;
+    else if (alive) {
+    act = ACT_ALL;
     uint32_t rows = B.blk_rows[b];
     const DevColumn* c = slot >= 0 ? &B.cols[(uint64_t)b * B.nfields + slot] : nullptr;
     const uint8_t* nd = P.blob + L.needle_off; uint32_t nl = L.needle_len;
@@ -387,12 +398,34 @@ static __global__ void k_plan_leaf(DevProgram P, BatchView B, uint32_t leaf_idx,
         if (act >= ACT_DICT || values_bytes) values_bytes = lens_stored_bytes(*c, rows) + c->data_len;   // getValuesForColumn was reached
     }
     if (c && c->kind == COL_VALUES && c->vt == VT_DICT && act == ACT_DICT) values_bytes = lens_stored_bytes(*c, rows) + c->data_len;
-    if (lane_id() == 0) {
-        action[b] = act; payload[b] = pay;
-        if (bloom_bytes) atomicAdd(&stats[ST_BLOOM_BYTES], bloom_bytes);
-        if (values_bytes) { atomicAdd(&stats[ST_VALUES_BYTES], values_bytes); atomicAdd(&stats[ST_COLUMNS_READ], 1ull); }
-        if (err) atomicMax(&stats[ST_ERROR], (unsigned long long)err);
+    if (c && c->kind == COL_VALUES && (act == ACT_SCAN || act == ACT_ROW)) {
+        need_lens = 1;
+        if (act == ACT_SCAN) { ntiles = (uint32_t)((c->data_len + VL_TILE_BYTES - 1) / VL_TILE_BYTES); scan_bytes = c->data_len; }
+        else need_row = 1;
     }
+    }
+    if (lane_id() == 0) {
+        if (valid) { action[b] = act; payload[b] = pay; }
+        if (err) atomicMax(&stats[ST_ERROR], (unsigned long long)err);
+        s_cnt[warp][0] = need_lens; s_cnt[warp][1] = ntiles; s_cnt[warp][2] = need_row;
+        s_stat[warp][0] = bloom_bytes; s_stat[warp][1] = values_bytes; s_stat[warp][2] = values_bytes ? 1 : 0; s_stat[warp][3] = scan_bytes;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {            // one atomic per CTA and list
+        uint32_t tot = 0;
+        for (int w = 0; w < VL_PLAN_WARPS; w++) { s_off[w][threadIdx.x] = tot; tot += s_cnt[w][threadIdx.x]; }
+        const uint32_t base = tot ? atomicAdd(&work_count[threadIdx.x], tot) : 0;
+        for (int w = 0; w < VL_PLAN_WARPS; w++) s_off[w][threadIdx.x] += base;
+    } else if (threadIdx.x >= 32 && threadIdx.x < 36) {
+        const int k = threadIdx.x - 32;
+        unsigned long long tot = 0;
+        for (int w = 0; w < VL_PLAN_WARPS; w++) tot += s_stat[w][k];
+        if (tot) atomicAdd(&stats[k == 0 ? ST_BLOOM_BYTES : k == 1 ? ST_VALUES_BYTES : k == 2 ? ST_COLUMNS_READ : ST_SCAN_BYTES], tot);
+    }
+    __syncthreads();
+    if (need_lens && lane_id() == 0) lens_blocks[s_off[warp][0]] = b;
+    if (need_row && lane_id() == 0) row_blocks[s_off[warp][2]] = b;
+    for (uint32_t k = lane_id(); k < ntiles; k += 32) { tile_block[s_off[warp][1] + k] = b; tile_off[s_off[warp][1] + k] = k * VL_TILE_BYTES; }
 }
 
 // ---- on-disk columns: header checks of the lens block (unmarshalUint64Items, encoding.go:246-336) once the device has regenerated it ----
@@ -426,122 +459,130 @@ static __global__ void k_finish_ondisk_cols(const uint8_t* __restrict__ arena, D
     if (err) atomicMax(&status[0], (unsigned long long)err);
 }
 
-// ---- lens decode -> per-bitmap-word row offsets (unmarshalUint64Items + the offsets implied by encoding.go:122-130) -----------------
-// row_off64[w] = byte offset (within the block's data) of row 64*(w - first word of the block).  One CTA per work item.
-static __global__ void k_lens_offsets(BatchView B, int slot, const uint32_t* __restrict__ work_blocks, const uint32_t* __restrict__ work_count,
-                               uint32_t* __restrict__ row_off64, uint8_t* __restrict__ ready, unsigned long long* __restrict__ stats) {
-    __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t carry_s;
-    for (uint32_t j = blockIdx.x; j < work_count[0]; j += gridDim.x) {
-        uint32_t b = work_blocks[j];
+// ---- lens decode -> byte offset of every 8th row (unmarshalUint64Items + the offsets implied by encoding.go:122-130) --------------------
+// row_off8[8 * w + g] = byte offset (within the block's data) of row 64 * (w - first word of the block) + 8 * g, for every bitmap word w of the
+// block.  One CTA per block of the lens work list, one thread per bitmap word.  Sums are taken in 64 bits: a lens block whose items do not add
+// up to the data length (encoding.go:124-126) is reported, never wrapped into agreement.
+static __global__ void k_lens_offsets(BatchView B, int slot, const uint32_t* __restrict__ lens_blocks, const uint32_t* __restrict__ work_count,
+                               uint32_t* __restrict__ row_off8, uint8_t* __restrict__ ready, unsigned long long* __restrict__ stats) {
+    __shared__ unsigned long long warp_sums[32];
+    __shared__ unsigned long long carry_s;
+    const uint32_t nwork = work_count[WC_LENS];
+    for (uint32_t j = blockIdx.x; j < nwork; j += gridDim.x) {
+        uint32_t b = lens_blocks[j];
         if (ready[b]) continue;   // uniform per CTA
         const DevColumn& c = B.cols[(uint64_t)b * B.nfields + slot];
         uint32_t rows = B.blk_rows[b];
         uint64_t w0 = B.blk_word_off[b]; uint32_t nw = (uint32_t)(B.blk_word_off[b + 1] - w0);
         const uint8_t* lens = B.arena + c.lens_off;
+        if (c.lens_type >= 4) {   // one const item: nothing to decode, the consumers divide
+            if (threadIdx.x == 0) {
+                if ((unsigned long long)rows * c.lens_const != c.data_len) atomicMax(&stats[ST_ERROR], (unsigned long long)ERR_LENS_MISMATCH);
+                ready[b] = 1;
+            }
+            continue;
+        }
         if (threadIdx.x == 0) carry_s = 0;
         __syncthreads();
         for (uint32_t base = 0; base < nw; base += blockDim.x) {
             uint32_t w = base + threadIdx.x;
-            uint32_t sum = 0;
+            uint32_t g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            unsigned long long sum = 0;
             if (w < nw) {
                 uint32_t r0 = w * 64, r1 = min(rows, r0 + 64);
                 if (c.lens_type == 0) {
                     if (r1 - r0 == 64) {   // 64 u8 lens = four 16-byte vectors (r0 is a multiple of 64; lens_off is 16-byte aligned)
                         const uint4* v = (const uint4*)(lens + r0);
 #pragma unroll
-                        for (int q = 0; q < 4; q++) { uint4 x = v[q]; sum += __vsadu4(x.x, 0) + __vsadu4(x.y, 0) + __vsadu4(x.z, 0) + __vsadu4(x.w, 0); }
-                    } else for (uint32_t r = r0; r < r1; r++) sum += lens[r];
-                } else if (c.lens_type < 4) for (uint32_t r = r0; r < r1; r++) sum += row_len(c, lens, r);
-                else sum = (r1 - r0) * c.lens_const;
+                        for (int q = 0; q < 4; q++) { uint4 x = v[q]; g[2 * q] = __vsadu4(x.x, 0) + __vsadu4(x.y, 0); g[2 * q + 1] = __vsadu4(x.z, 0) + __vsadu4(x.w, 0); }
+                    } else for (uint32_t r = r0; r < r1; r++) g[(r - r0) >> 3] += lens[r];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) sum += g[q];
+                } else {
+                    unsigned long long g64[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                    for (uint32_t r = r0; r < r1; r++) g64[(r - r0) >> 3] += c.lens_type == 3 ? ld_be64(lens + 8 * (uint64_t)r) : (unsigned long long)row_len(c, lens, r);
+#pragma unroll
+                    for (int q = 0; q < 8; q++) { sum += g64[q]; g[q] = (uint32_t)min(g64[q], 0xFFFFFFFFull); }
+                    if (sum > 0xFFFFFFFFull) sum = 0x100000000ull;   // cannot equal a data length (< 4 GiB); keeps the CTA sum from wrapping
+                }
             }
             // CTA exclusive scan of `sum`
-            uint32_t incl = sum;
+            unsigned long long incl = sum;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane_id() >= d) incl += t; }
+            for (int d = 1; d < 32; d <<= 1) { unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d); if (lane_id() >= d) incl += t; }
             if (lane_id() == 31) warp_sums[threadIdx.x >> 5] = incl;
             __syncthreads();
-            uint32_t wid = threadIdx.x >> 5, wpre = 0;
+            uint32_t wid = threadIdx.x >> 5; unsigned long long wpre = 0;
             for (uint32_t k = 0; k < wid; k++) wpre += warp_sums[k];
-            uint32_t excl = carry_s + wpre + incl - sum;
-            if (w < nw) row_off64[w0 + w] = excl;
+            unsigned long long excl = carry_s + wpre + incl - sum;
+            if (w < nw) {
+                uint32_t o = (uint32_t)min(excl, 0xFFFFFFFFull);
+                uint4 a, bq;
+                a.x = o; o += g[0]; a.y = o; o += g[1]; a.z = o; o += g[2]; a.w = o; o += g[3];
+                bq.x = o; o += g[4]; bq.y = o; o += g[5]; bq.z = o; o += g[6]; bq.w = o;
+                uint4* dst = (uint4*)(row_off8 + ((w0 + w) << 3));
+                dst[0] = a; dst[1] = bq;
+            }
             __syncthreads();
             if (threadIdx.x == blockDim.x - 1) carry_s = excl + sum;
             __syncthreads();
         }
         if (threadIdx.x == 0) {
-            if ((uint64_t)carry_s != c.data_len) atomicMax(&stats[ST_ERROR], (unsigned long long)ERR_LENS_MISMATCH);   // encoding.go:124-126
+            if (carry_s != c.data_len) atomicMax(&stats[ST_ERROR], (unsigned long long)ERR_LENS_MISMATCH);   // encoding.go:124-126
             ready[b] = 1;
         }
         __syncthreads();
     }
 }
 
-// ---- work list: blocks whose action selects `want`, with their tile counts (single CTA; nblocks is small) -------------------------------
-static __global__ void k_build_worklist(BatchView B, int slot, const uint8_t* __restrict__ action, uint8_t want, uint32_t tile_bytes,
-                                 uint32_t* __restrict__ work_blocks, uint32_t* __restrict__ tile_prefix, uint32_t* __restrict__ work_count,
-                                 unsigned long long* __restrict__ stats, int count_scan_bytes) {
-    __shared__ uint32_t s_cnt[1024], s_til[1024];
-    __shared__ uint32_t c_cnt, c_til;
-    if (threadIdx.x == 0) { c_cnt = 0; c_til = 0; }
-    __syncthreads();
-    unsigned long long scan_bytes = 0;
-    for (uint32_t base = 0; base < B.nblocks; base += blockDim.x) {
-        uint32_t b = base + threadIdx.x;
-        uint32_t flag = 0, tiles = 0;
-        if (b < B.nblocks && action[b] == want) {
-            flag = 1;
-            const DevColumn& c = B.cols[(uint64_t)b * B.nfields + slot];
-            tiles = (uint32_t)((c.data_len + tile_bytes - 1) / tile_bytes);
-            scan_bytes += c.data_len;
-        }
-        s_cnt[threadIdx.x] = flag; s_til[threadIdx.x] = tiles;
-        __syncthreads();
-        // Hillis-Steele inclusive scan over the CTA
-        for (uint32_t d = 1; d < blockDim.x; d <<= 1) {
-            uint32_t a = 0, t = 0;
-            if (threadIdx.x >= d) { a = s_cnt[threadIdx.x - d]; t = s_til[threadIdx.x - d]; }
-            __syncthreads();
-            s_cnt[threadIdx.x] += a; s_til[threadIdx.x] += t;
-            __syncthreads();
-        }
-        if (flag) { uint32_t pos = c_cnt + s_cnt[threadIdx.x] - 1; work_blocks[pos] = b; tile_prefix[pos] = c_til + s_til[threadIdx.x] - tiles; }
-        __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) { c_cnt += s_cnt[threadIdx.x]; c_til += s_til[threadIdx.x]; }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) { work_count[0] = c_cnt; work_count[1] = c_til; tile_prefix[c_cnt] = c_til; }
-    if (scan_bytes && count_scan_bytes) atomicAdd(&stats[ST_SCAN_BYTES], scan_bytes);
-}
-
 // ---- the hot kernel: row-agnostic substring scan over the decoded strings payload -------------------------------------------------------
 // Replaces bm.forEachSetBit(func(idx){ matchPhrase(values[idx], phrase) }) (filter_phrase.go:201-270, bitmap.go:128-153),
-// matchPrefix (filter_prefix.go:318-352) and the strings.Index(prefix) loop of regexutil (regex.go:162-212).
-// Every thread streams 16-byte vectors of the block's concatenated row bytes, compares the first min(4, L) needle bytes at all 16
-// byte positions (4-byte window compare), and only for candidates (rare) verifies the rest, maps the byte offset to its row through
-// row_off64 + the lens items, applies the boundary rules and sets the row's bit.  An occurrence in the reference's retry loop
-// ("pos++; continue") is any occurrence, so occurrences are independent and order-free.
+// matchPrefix (filter_prefix.go:318-352) and the strings.Index(literal) loop of regexutil (regex.go:162-212).
+//
+// Filter.  Every thread streams 16-byte vectors of the block's concatenated row bytes and looks only at ALIGNED 4-byte words.  An occurrence of
+// the needle that starts at byte r (0..3) of some word leaves min(4 - r, L) of its bytes in that word and min(4, L - (4 - r)) in the next one;
+// the host picks, per r, the word that carries more needle bytes and hands the kernel its (mask, pattern) pair and the distance `delta[r]` from
+// that word back to the start of the occurrence.  A word of the stream that equals one of the four patterns under its mask is a candidate:
+// <= 4 LOP3 + 4 ISETP per word, no funnel shifts, no bytes from the neighbour lane.  For needles of >= 7 bytes all four masks are full (every
+// occurrence covers a whole aligned word) and the instantiation without masks is used.
+//
+// Verification.  Candidates are verified by the lane that found them, all lanes of a warp in parallel: full compare, byte offset -> row through
+// row_off8 (interpolation guess, bracket check, binary search, then at most 8 lens items), rejection of occurrences that straddle a row, the
+// boundary rules of the filter kind, atomicOr of the row's bit.  An occurrence in the reference's retry loop ("pos++; continue") is any
+// occurrence, so occurrences are independent and order-free -- that is what makes the row-agnostic formulation exact.
 struct ScanParams {
     uint32_t mode;            // SCAN_*
     uint32_t needle_off, needle_len;
-    uint32_t n4, m4;          // first min(4,L) needle bytes, little-endian packed, and the mask
-    uint32_t sub4[4];         // L >= 7: needle bytes [k, k+4) for k = 0..3 (aligned-word filter, see k_substr_scan)
+    uint32_t pat[4], msk[4];  // per start alignment r: (word & msk[r]) == pat[r]
+    int32_t delta[4];         // occurrence start = byte address of the matching word + delta[r]
+    uint32_t nd16[4];         // the first 16 needle bytes (little-endian words), compared out of registers
     uint8_t starts_tok, ends_tok;
     int32_t regex;
 };
 
-// Warp-cooperative verification of one candidate occurrence at byte `pos` of block b's data.  All 32 lanes call with identical
-// arguments (the caller broadcasts the candidate), so every branch below is warp-uniform: the tail compare is striped over the
-// lanes, the byte-offset -> row lookup loads the 64 lens of one bitmap word in parallel and prefix-sums them with shuffles.
-static __device__ __noinline__ void scan_verify_warp(const DevProgram& P, const BatchView& B, const DevColumn& c, const ScanParams& sp, uint32_t b,
-                                                     const uint32_t* __restrict__ row_off64, uint32_t pos, uint64_t* __restrict__ leaf_bm) {
+static __device__ __forceinline__ uint32_t ld_u32_unaligned(const uint8_t* p) {   // two aligned loads + a funnel shift; reads up to 7 bytes past p
+    const uint32_t* a = (const uint32_t*)((uintptr_t)p & ~(uintptr_t)3);
+    return __funnelshift_r(a[0], a[1], 8 * (uint32_t)((uintptr_t)p & 3));
+}
+
+// Verification of one candidate occurrence at byte `pos` of block b's data by a single lane.
+static __device__ __forceinline__ void scan_verify_lane(const DevProgram& P, const BatchView& B, const DevColumn& c, const ScanParams& sp, uint32_t b,
+                                                     const uint32_t* __restrict__ row_off8, uint32_t pos, uint64_t* __restrict__ leaf_bm) {
     const uint8_t* data = B.arena + c.data_off;
-    const uint8_t* nd = P.blob + sp.needle_off;
-    const uint32_t L = sp.needle_len, lane = lane_id();
-    if ((uint64_t)pos + L > c.data_len) return;
-    bool same = true;
-    for (uint32_t k = lane; k < L; k += 32) same &= data[pos + k] == nd[k];   // the filter only vouches for 4 of the L bytes
-    if (!__all_sync(0xffffffffu, same)) return;
+    const uint32_t L = sp.needle_len, n = (uint32_t)c.data_len;
+    if ((uint64_t)pos + L > n) return;
+    // the filter only vouches for some of the L bytes.  Payloads keep >= 32 readable bytes past data_len, so whole words may be compared.
+    {
+        const uint32_t head = L < 16 ? L : 16;
+#pragma unroll
+        for (uint32_t k = 0; k < 16; k += 4) {
+            if (k >= head) break;
+            const uint32_t m = head - k >= 4 ? 0xFFFFFFFFu : (1u << (8 * (head - k))) - 1;
+            if ((ld_u32_unaligned(data + pos + k) ^ sp.nd16[k >> 2]) & m) return;
+        }
+        const uint8_t* nd = P.blob + sp.needle_off;
+        for (uint32_t k = 16; k < L; k++) if (data[pos + k] != nd[k]) return;
+    }
     // byte offset -> row
     const uint32_t rows = B.blk_rows[b];
     const uint64_t w0 = B.blk_word_off[b];
@@ -553,33 +594,32 @@ static __device__ __noinline__ void scan_verify_warp(const DevProgram& P, const 
         if (r >= rows) return;
     } else {
         const uint8_t* lens = B.arena + c.lens_off;
-        uint32_t nw = (uint32_t)(B.blk_word_off[b + 1] - w0);
-        // last bitmap word whose first row starts at or before pos: binary search down to a 64-entry window (no step at all for blocks
-        // of <= 4096 rows), then one parallel probe of that window -- one memory round trip instead of log2(nw) dependent ones
-        uint32_t lo = 0, hi = nw - 1;
-        while (hi - lo >= 64) { uint32_t mid = (lo + hi + 1) >> 1; if (row_off64[w0 + mid] <= pos) lo = mid; else hi = mid - 1; }
+        const uint32_t* ro = row_off8 + (w0 << 3);
+        const uint32_t n8 = (rows + 7) >> 3;
+        // last group of 8 rows that starts at or before pos.  Row lengths of one block are close to uniform, so pos * n8 / n is almost always
+        // within one group of the answer: check that bracket first, fall back to the whole range.
+        uint32_t lo, hi;
         {
-            const uint32_t ia0 = lo + lane, ib0 = lo + 32 + lane;
-            const uint32_t oa = ia0 <= hi ? row_off64[w0 + ia0] : 0xFFFFFFFFu, ob = ib0 <= hi ? row_off64[w0 + ib0] : 0xFFFFFFFFu;
-            const uint32_t ma = __ballot_sync(0xffffffffu, oa <= pos), mb = __ballot_sync(0xffffffffu, ob <= pos);
-            lo += mb ? 32 + (31 - __clz(mb)) : (ma ? 31 - __clz(ma) : 0);   // offsets are non-decreasing: the predicate is a prefix of ones
+            const uint32_t g = min((uint32_t)(__uint2float_rz(pos) * __fdividef(__uint2float_rz(n8), __uint2float_rz(n))), n8 - 1);
+            lo = g ? g - 1 : 0; hi = min(g + 1, n8 - 1);
+            if (!(ro[lo] <= pos && (hi + 1 >= n8 || ro[hi + 1] > pos))) { lo = 0; hi = n8 - 1; }
         }
-        const uint32_t r0 = lo * 64, base = row_off64[w0 + lo];
-        const uint32_t ra = r0 + lane, rb = r0 + 32 + lane;
-        uint32_t la = ra < rows ? row_len(c, lens, ra) : 0, lb = rb < rows ? row_len(c, lens, rb) : 0;
-        uint32_t ia = la, ib = lb;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, ia, d), u = __shfl_up_sync(0xffffffffu, ib, d); if (lane >= d) { ia += t; ib += u; } }
-        const uint32_t tot_a = __shfl_sync(0xffffffffu, ia, 31);
-        const uint32_t sa = base + ia - la, sb = base + tot_a + ib - lb;   // row starts
+        while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if (ro[mid] <= pos) lo = mid; else hi = mid - 1; }
         // the row holding pos is the LAST row whose start is <= pos (zero-length rows share a start with their successor)
-        const uint32_t ba = __ballot_sync(0xffffffffu, ra < rows && sa <= pos), bb = __ballot_sync(0xffffffffu, rb < rows && sb <= pos);
-        if (bb) { int src = 31 - __clz(bb); r = r0 + 32 + src; off = __shfl_sync(0xffffffffu, sb, src); len = __shfl_sync(0xffffffffu, lb, src); }
-        else if (ba) { int src = 31 - __clz(ba); r = r0 + src; off = __shfl_sync(0xffffffffu, sa, src); len = __shfl_sync(0xffffffffu, la, src); }
-        else return;
-        if (pos >= off + len) return;
+        const uint32_t r0 = lo * 8, kmax = min(8u, rows - r0);
+        uint32_t o = ro[lo];
+        r = r0; off = o; len = 0;
+        if (c.lens_type == 0) {
+            const uint2 lw = *(const uint2*)(lens + r0);   // r0 is a multiple of 8 and lens_off is 16-byte aligned
+            const uint64_t l8 = ((uint64_t)lw.y << 32) | lw.x;
+            for (uint32_t k = 0; k < kmax && o <= pos; k++) { const uint32_t l = (uint32_t)(l8 >> (8 * k)) & 0xFF; r = r0 + k; off = o; len = l; o += l; }
+        } else {
+            for (uint32_t k = 0; k < kmax && o <= pos; k++) { const uint32_t l = row_len(c, lens, r0 + k); r = r0 + k; off = o; len = l; o += l; }
+        }
+        if (pos < off || pos - off >= len) return;
     }
-    if (pos + L > off + len) return;   // the occurrence straddles a row boundary
+    if ((uint64_t)off + len > n) return;   // malformed lens (reported by k_lens_offsets): never read outside the payload
+    if (pos + L > off + len) return;       // the occurrence straddles a row boundary
     const uint8_t* s = data + off; const uint32_t p = pos - off;
     bool hit;
     switch (sp.mode) {
@@ -587,75 +627,60 @@ static __device__ __noinline__ void scan_verify_warp(const DevProgram& P, const 
     case SCAN_PREFIX: hit = phrase_boundaries_ok(s, len, p, L, sp.starts_tok, false); break;
     case SCAN_CONTAINS: hit = true; break;
     case SCAN_RX_DOTPLUS: hit = p + L < len; break;
-    default: {                                                                              // SCAN_RX_SUFFIX
+    case SCAN_RX_TAIL: {   // the needle is the literal of a `PREFIX.*LITERAL` expression: it matches iff PREFIX occurs entirely before this occurrence
         const DevRegex& R = P.regexes[sp.regex];
-        if (R.tail_len) {
-            // suffix `.*LIT`: the anchored automaton accepts iff LIT occurs in the remainder; lanes try start positions in parallel
-            const uint8_t* rem = s + p + L; const uint32_t rl = len - p - L, tl = R.tail_len; const uint8_t* lit = P.blob + R.tail_off;
-            bool found = false;
-            for (uint32_t i0 = 0; i0 + tl <= rl && !found; i0 += 32) {
-                uint32_t i = i0 + lane; bool eq = i + tl <= rl;
-                for (uint32_t k = 0; k < tl && eq; k++) eq = rem[i + k] == lit[k];
-                found = __any_sync(0xffffffffu, eq);
-            }
-            hit = found;
-        } else hit = dfa_run(R, P.blob, s + p + L, len - p - L);
+        hit = find_bytes(s, p, P.blob + R.prefix_off, R.prefix_len, 0) >= 0;
+        break;
+    }
+    default: {             // SCAN_RX_SUFFIX: the needle is the literal prefix, the remainder of the row goes through the suffix automaton
+        const DevRegex& R = P.regexes[sp.regex];
+        if (R.tail_len) hit = find_bytes(s + p + L, len - p - L, P.blob + R.tail_off, R.tail_len, 0) >= 0;   // suffix `.*LIT`
+        else hit = dfa_run(R, P.blob, s + p + L, len - p - L);
         break;
     }
     }
-    if (hit && lane == 0) atomicOr((unsigned long long*)&leaf_bm[w0 + (r >> 6)], 1ull << (r & 63));
+    if (hit) atomicOr((unsigned long long*)&leaf_bm[w0 + (r >> 6)], 1ull << (r & 63));
 }
 
 #define VL_SCAN_THREADS 256
 #define VL_SCAN_UNROLL 4                       /* independent 16-byte loads in flight per thread */
 #define VL_SCAN_ROUNDS 4                       /* rounds per tile */
-#define VL_TILE_BYTES (VL_SCAN_THREADS * 16 * VL_SCAN_UNROLL * VL_SCAN_ROUNDS)   /* 64 KiB of row bytes per CTA work item */
 #define VL_SCAN_QSTRIDE (VL_TILE_BYTES / VL_SCAN_UNROLL)                          /* distance between a thread's loads of one round */
+static_assert(VL_TILE_BYTES == VL_SCAN_THREADS * 16 * VL_SCAN_UNROLL * VL_SCAN_ROUNDS, "tile size");
 
-// work item -> its tiles: tile_block[t] = block, tile_off[t] = first byte of the tile inside the block's data
-static __global__ void k_expand_tiles(BatchView B, int slot, const uint32_t* __restrict__ work_blocks, const uint32_t* __restrict__ tile_prefix,
-                                      const uint32_t* __restrict__ work_count, uint32_t* __restrict__ tile_block, uint32_t* __restrict__ tile_off) {
-    const uint32_t nwork = work_count[0];
-    for (uint32_t j = blockIdx.x; j < nwork; j += gridDim.x) {
-        const uint32_t first = tile_prefix[j], cnt = tile_prefix[j + 1] - first, b = work_blocks[j];
-        for (uint32_t k = threadIdx.x; k < cnt; k += blockDim.x) { tile_block[first + k] = b; tile_off[first + k] = k * (uint32_t)VL_TILE_BYTES; }
+template <bool MASKED>
+static __device__ __forceinline__ uint32_t scan_word_hits(uint32_t w, const ScanParams& sp) {   // bit r: the word matches pattern r
+    if (MASKED) return (uint32_t)((w & sp.msk[0]) == sp.pat[0]) | (uint32_t)((w & sp.msk[1]) == sp.pat[1]) << 1 | (uint32_t)((w & sp.msk[2]) == sp.pat[2]) << 2 | (uint32_t)((w & sp.msk[3]) == sp.pat[3]) << 3;
+    return (uint32_t)(w == sp.pat[0]) | (uint32_t)(w == sp.pat[1]) << 1 | (uint32_t)(w == sp.pat[2]) << 2 | (uint32_t)(w == sp.pat[3]) << 3;
+}
+
+// The slow path of the scan: enumerate the candidates of one lane's four vectors and verify each.  Kept out of line on purpose: behind a call
+// boundary the compiler cannot share sub-expressions with the filter of the hot loop (it spilled 16 masked words per round to do so), and the
+// registers the verification needs do not count against the 48 of the streaming loop.
+template <bool MASKED>
+static __device__ __noinline__ void scan_candidates(const DevProgram& P, const BatchView& B, const DevColumn& c, const ScanParams& sp, uint32_t b,
+                                                    const uint32_t* __restrict__ row_off8, uint64_t* __restrict__ leaf_bm, uint4 v0, uint4 v1, uint4 v2, uint4 v3,
+                                                    uint32_t base, uint32_t n) {
+    const uint32_t w[16] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
+    unsigned long long cand = 0;             // bit 16 * u + 4 * i + r: word i of vector u matches pattern r
+#pragma unroll
+    for (int k = 0; k < 16; k++) cand |= (unsigned long long)scan_word_hits<MASKED>(w[k], sp) << (4 * k);
+    while (cand) {
+        const int bit = __ffsll((long long)cand) - 1; cand &= cand - 1;
+        const int u = bit >> 4, i = (bit >> 2) & 3, r = bit & 3;
+        // vectors past the end of the data were not loaded (zeros); a zero word can only match a pattern of NUL bytes, rejected by the bounds below
+        const int64_t q = (int64_t)base + u * (int64_t)VL_SCAN_QSTRIDE + 4 * i + sp.delta[r];
+        if (q >= 0 && q < (int64_t)n) scan_verify_lane(P, B, c, sp, b, row_off8, (uint32_t)q, leaf_bm);
     }
 }
 
-// does any of the 16 four-byte windows starting in {w0..w3} (continued by w4) equal n4 (under mask m4 when L < 4)?
-template <bool FULL4>
-__device__ __forceinline__ bool scan_any_window(const uint32_t (&w)[5], uint32_t n4, uint32_t m4) {
-    bool any = false;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            uint32_t win = j == 0 ? w[i] : __funnelshift_r(w[i], w[i + 1], 8 * j);
-            if (!FULL4) win &= m4;
-            any |= win == n4;
-        }
-    }
-    return any;
-}
-__device__ __forceinline__ uint32_t scan_window_mask(const uint32_t (&w)[5], uint32_t n4, uint32_t m4) {
-    uint32_t cand = 0;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            uint32_t win = j == 0 ? w[i] : __funnelshift_r(w[i], w[i + 1], 8 * j);
-            if ((win & m4) == n4) cand |= 1u << (i * 4 + j);
-        }
-    }
-    return cand;
-}
-
-template <bool FULL4>
-static __global__ void __launch_bounds__(VL_SCAN_THREADS) k_substr_scan(DevProgram P, BatchView B, int slot, ScanParams sp, const uint32_t* __restrict__ tile_block,
-                                                                        const uint32_t* __restrict__ tile_off, const uint32_t* __restrict__ work_count,
-                                                                        const uint32_t* __restrict__ row_off64, uint64_t* __restrict__ leaf_bm) {
-    const uint32_t ntiles = work_count[1];
-    const uint32_t n4 = sp.n4, m4 = sp.m4;
+// Persistent grid: 148 SMs x 5 resident CTAs x 256 threads, each CTA strides over the tile table built by k_plan_leaf.  Per round a thread has
+// four independent LDG.128 in flight, 16 KiB apart (a warp's requests spread over more L2 slices / HBM channels than adjacent 4 KiB slices would).
+template <bool MASKED>
+static __global__ void __launch_bounds__(VL_SCAN_THREADS, 5) k_substr_scan(const __grid_constant__ DevProgram P, const __grid_constant__ BatchView B, int slot, const __grid_constant__ ScanParams sp, const uint32_t* __restrict__ tile_block,
+                                                                           const uint32_t* __restrict__ tile_off, const uint32_t* __restrict__ work_count,
+                                                                           const uint32_t* __restrict__ row_off8, uint64_t* __restrict__ leaf_bm) {
+    const uint32_t ntiles = work_count[WC_TILES];
     for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const uint32_t b = __ldg(tile_block + t), tile0 = __ldg(tile_off + t);
         const DevColumn& c = B.cols[(uint64_t)b * B.nfields + slot];
@@ -663,8 +688,6 @@ static __global__ void __launch_bounds__(VL_SCAN_THREADS) k_substr_scan(DevProgr
         const uint8_t* __restrict__ data = B.arena + c.data_off;
 #pragma unroll 1
         for (int round = 0; round < VL_SCAN_ROUNDS; round++) {
-            // round r covers the r-th 4 KiB slice of each of the four 16 KiB quarters of the tile: a thread's 4 loads are 16 KiB apart,
-            // which spreads the requests of a warp over more L2 slices / HBM channels than 4 adjacent 4 KiB slices would
             const uint32_t round0 = tile0 + (uint32_t)round * (VL_SCAN_THREADS * 16);
             if (round0 >= n) break;                           // uniform: the whole round lies past the data
             const uint32_t base = round0 + threadIdx.x * 16;
@@ -675,200 +698,21 @@ static __global__ void __launch_bounds__(VL_SCAN_THREADS) k_substr_scan(DevProgr
                 // payloads keep >= 32 readable bytes past data_len: a vector load that starts before n is always in bounds
                 v[u] = p < n ? __ldg((const uint4*)(data + p)) : make_uint4(0, 0, 0, 0);
             }
-#pragma unroll
-            for (int u = 0; u < VL_SCAN_UNROLL; u++) {
-                const uint32_t p = base + u * VL_SCAN_QSTRIDE;
-                uint32_t nx = __shfl_down_sync(0xffffffffu, v[u].x, 1);
-                if (lane_id() == 31) nx = (p + 16 < n) ? __ldg((const uint32_t*)(data + p + 16)) : 0;
-                const uint32_t w[5] = {v[u].x, v[u].y, v[u].z, v[u].w, nx};
-                const bool mine = p < n && scan_any_window<FULL4>(w, n4, m4);
-                uint32_t vote = __ballot_sync(0xffffffffu, mine);
-                while (vote) {                                // rare: some lane of this warp holds a candidate; the warp verifies it together
-                    const int src = __ffs(vote) - 1; vote &= vote - 1;
-                    uint32_t cand = lane_id() == (uint32_t)src ? scan_window_mask(w, n4, m4) : 0;
-                    cand = __shfl_sync(0xffffffffu, cand, src);
-                    const uint32_t p0 = __shfl_sync(0xffffffffu, p, src);
-                    while (cand) {
-                        const int k = __ffs(cand) - 1; cand &= cand - 1;
-                        scan_verify_warp(P, B, c, sp, b, row_off64, p0 + k, leaf_bm);
-                    }
-                }
-            }
-        }
-    }
-}
-
-// ---- needles of 7+ bytes: aligned-word filter ------------------------------------------------------------------------------------------------
-// An occurrence at byte q covers the aligned word at a = (q + 3) & ~3 completely (a + 4 <= q + L when L >= 7), and that word equals needle bytes
-// [k, k+4) with k = a - q in 0..3.  So it suffices to compare every ALIGNED word of the stream with the four 4-byte needle substrings sub4[0..3]:
-// 16 compares per 16-byte vector and no funnel shifts, no neighbour word (the shifted-window filter needs 12 SHF + 16 ISETP + a shuffle).  A hit
-// on (word at a, k) is verified at q = a - k like any other candidate, so the result is identical.
-static __global__ void __launch_bounds__(VL_SCAN_THREADS, 5) k_substr_scan_aligned(DevProgram P, BatchView B, int slot, ScanParams sp, const uint32_t* __restrict__ tile_block,
-                                                                               const uint32_t* __restrict__ tile_off, const uint32_t* __restrict__ work_count,
-                                                                               const uint32_t* __restrict__ row_off64, uint64_t* __restrict__ leaf_bm) {
-    const uint32_t ntiles = work_count[1];
-    const uint32_t s0 = sp.sub4[0], s1 = sp.sub4[1], s2 = sp.sub4[2], s3 = sp.sub4[3];
-    for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const uint32_t b = __ldg(tile_block + t), tile0 = __ldg(tile_off + t);
-        const DevColumn& c = B.cols[(uint64_t)b * B.nfields + slot];
-        const uint32_t n = (uint32_t)c.data_len;
-        const uint8_t* __restrict__ data = B.arena + c.data_off;
-#pragma unroll 1
-        for (int round = 0; round < VL_SCAN_ROUNDS; round++) {
-            const uint32_t round0 = tile0 + (uint32_t)round * (VL_SCAN_THREADS * 16);
-            if (round0 >= n) break;
-            const uint32_t base = round0 + threadIdx.x * 16;
-            uint4 v[VL_SCAN_UNROLL];
-#pragma unroll
-            for (int u = 0; u < VL_SCAN_UNROLL; u++) {
-                uint32_t p = base + u * VL_SCAN_QSTRIDE;
-                v[u] = p < n ? __ldg((const uint4*)(data + p)) : make_uint4(0, 0, 0, 0);
-            }
             bool hit[VL_SCAN_UNROLL];
 #pragma unroll
             for (int u = 0; u < VL_SCAN_UNROLL; u++) {
                 const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
                 hit[u] = false;
 #pragma unroll
-                for (int i = 0; i < 4; i++) hit[u] |= w[i] == s0 || w[i] == s1 || w[i] == s2 || w[i] == s3;
-            }
-            // zero padding past n never equals a needle substring that passes verification
-            if (__ballot_sync(0xffffffffu, hit[0] | hit[1] | hit[2] | hit[3])) {   // rare: some lane of this warp holds a candidate
-#pragma unroll
-                for (int u = 0; u < VL_SCAN_UNROLL; u++) {
-                    uint32_t vote = __ballot_sync(0xffffffffu, hit[u]);
-                    while (vote) {                               // the warp verifies the candidates of lane `src`, vector u, together
-                        const int src = __ffs(vote) - 1; vote &= vote - 1;
-                        const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-                        uint32_t cand = 0;   // bit i*4+k: aligned word i equals needle substring k
-                        if (lane_id() == (uint32_t)src) {
-#pragma unroll
-                            for (int i = 0; i < 4; i++) cand |= ((uint32_t)(w[i] == s0) | (uint32_t)(w[i] == s1) << 1 | (uint32_t)(w[i] == s2) << 2 | (uint32_t)(w[i] == s3) << 3) << (4 * i);
-                        }
-                        cand = __shfl_sync(0xffffffffu, cand, src);
-                        const uint32_t pb = __shfl_sync(0xffffffffu, base, src) + u * VL_SCAN_QSTRIDE;
-                        while (cand) {
-                            const int bit = __ffs(cand) - 1; cand &= cand - 1;
-                            const uint32_t a = pb + 4 * (bit >> 2), k = bit & 3;
-                            if (a >= k && a < n) scan_verify_warp(P, B, c, sp, b, row_off64, a - k, leaf_bm);
-                        }
-                    }
+                for (int i = 0; i < 4; i++) {
+                    if (MASKED) hit[u] |= (w[i] & sp.msk[0]) == sp.pat[0] || (w[i] & sp.msk[1]) == sp.pat[1] || (w[i] & sp.msk[2]) == sp.pat[2] || (w[i] & sp.msk[3]) == sp.pat[3];
+                    else hit[u] |= w[i] == sp.pat[0] || w[i] == sp.pat[1] || w[i] == sp.pat[2] || w[i] == sp.pat[3];
                 }
             }
+            // (zero padding past n can only equal a pattern that fails verification: the occurrence would end past n)
+            // rare: this lane holds candidates and verifies them itself (the warp's other lanes wait, or do the same with theirs)
+            if (hit[0] | hit[1] | hit[2] | hit[3]) scan_candidates<MASKED>(P, B, c, sp, b, row_off8, leaf_bm, v[0], v[1], v[2], v[3], base, n);
         }
-    }
-}
-
-// ---- the same scan with TMA staging: cp.async.bulk (UBLKCP) global -> shared through a 4-stage mbarrier ring -----------------------------------
-// Bytes in flight no longer depend on how many registers hold pending loads: one elected thread keeps up to 3 x 16 KiB bulk copies per CTA
-// outstanding while all eight warps compare windows out of shared memory (conflict-free LDS.128; the 4 bytes that continue a vector are
-// simply the next word in shared memory, so no shuffles).  3 CTAs / SM x 3 x 16 KiB = 144 KiB in flight per SM.
-#define VL_TMA_STAGES 4
-#define VL_TMA_CHUNK 16384u
-#define VL_TMA_STRIDE (VL_TMA_CHUNK + 128u)   /* 16-byte header + chunk + the 16 continuation bytes, padded to 128 */
-#define VL_TMA_SMEM (VL_TMA_STAGES * VL_TMA_STRIDE + 128u)
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(bar) : "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(bar), "r"(bytes) : "memory"); }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile("{\n .reg .pred p;\n WAIT_LOOP:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra WAIT_DONE;\n bra WAIT_LOOP;\n WAIT_DONE:\n}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-
-// work item -> its 16 KiB chunks: source offset in the arena, valid bytes, owning block, first byte inside the block's data
-struct ChunkDesc { uint64_t src; uint32_t block, off, len, pad; };
-static __global__ void k_expand_chunks(BatchView B, int slot, const uint32_t* __restrict__ work_blocks, const uint32_t* __restrict__ chunk_prefix,
-                                       const uint32_t* __restrict__ work_count, ChunkDesc* __restrict__ chunks) {
-    const uint32_t nwork = work_count[0];
-    for (uint32_t j = blockIdx.x; j < nwork; j += gridDim.x) {
-        const uint32_t first = chunk_prefix[j], cnt = chunk_prefix[j + 1] - first, b = work_blocks[j];
-        const DevColumn& c = B.cols[(uint64_t)b * B.nfields + slot];
-        for (uint32_t k = threadIdx.x; k < cnt; k += blockDim.x) {
-            ChunkDesc d; d.block = b; d.off = k * VL_TMA_CHUNK; d.src = c.data_off + d.off;
-            d.len = (uint32_t)min((uint64_t)VL_TMA_CHUNK, c.data_len - d.off); d.pad = 0;
-            chunks[first + k] = d;
-        }
-    }
-}
-
-template <bool FULL4>
-static __global__ void __launch_bounds__(VL_SCAN_THREADS, 3) k_substr_scan_tma(DevProgram P, BatchView B, int slot, ScanParams sp, const ChunkDesc* __restrict__ chunks,
-                                                                               const uint32_t* __restrict__ work_count, const uint32_t* __restrict__ row_off64,
-                                                                               uint64_t* __restrict__ leaf_bm) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    const uint32_t nchunks = work_count[1];
-    const uint32_t n4 = sp.n4, m4 = sp.m4;
-    const uint32_t sbase = smem_u32(smem);
-    // per stage: [0,16) header {block, off, len, -}, [16, 16+CHUNK+16) bytes
-    const uint32_t bars = sbase + VL_TMA_STAGES * VL_TMA_STRIDE;   // full[0..3] then empty[0..3], 8 bytes each
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < VL_TMA_STAGES; s++) { mbar_init(bars + 8 * s, 1); mbar_init(bars + 8 * (VL_TMA_STAGES + s), VL_SCAN_THREADS / 32); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    // this CTA's chunks: q = blockIdx.x + i * gridDim.x
-    const uint32_t mine_cnt = nchunks > blockIdx.x ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    uint32_t issued = 0;
-    ChunkDesc next_desc;                                       // producer: descriptor of chunk `issued`, fetched one step ahead
-    if (threadIdx.x == 0 && mine_cnt) next_desc = chunks[blockIdx.x];
-    auto produce = [&]() {   // thread 0 only
-        if (issued >= mine_cnt) return;
-        const ChunkDesc d = next_desc;
-        if (issued + 1 < mine_cnt) next_desc = chunks[blockIdx.x + (uint64_t)(issued + 1) * gridDim.x];   // overlaps with the wait below
-        const uint32_t stage = issued % VL_TMA_STAGES, round = issued / VL_TMA_STAGES;
-        mbar_wait(bars + 8 * (VL_TMA_STAGES + stage), (round & 1) ^ 1);                  // all warps released this stage
-        uint32_t* hdr = (uint32_t*)(smem + stage * VL_TMA_STRIDE);
-        hdr[0] = d.block; hdr[1] = d.off; hdr[2] = d.len;
-        // the chunk plus the 16 bytes that continue its last vector; payloads keep >= 32 readable bytes past data_len
-        const uint32_t bytes = ((d.len + 15u) & ~15u) + 16u;
-        mbar_expect_tx(bars + 8 * stage, bytes);
-        tma_bulk_g2s(sbase + stage * VL_TMA_STRIDE + 16, B.arena + d.src, bytes, bars + 8 * stage);
-        issued++;
-    };
-    if (threadIdx.x == 0) for (int s = 0; s < VL_TMA_STAGES - 1; s++) produce();
-    for (uint32_t consumed = 0; consumed < mine_cnt; consumed++) {
-        const uint32_t stage = consumed % VL_TMA_STAGES, round = consumed / VL_TMA_STAGES;
-        if (threadIdx.x == 0) produce();                                                 // keep STAGES-1 copies in flight
-        mbar_wait(bars + 8 * stage, round & 1);                                          // bytes have landed
-        const uint8_t* buf = smem + stage * VL_TMA_STRIDE + 16;
-        const uint32_t* hdr = (const uint32_t*)(smem + stage * VL_TMA_STRIDE);
-        const uint32_t b = hdr[0], off = hdr[1], len = hdr[2];
-        bool mine = false;
-        uint4 v[4]; uint32_t nx[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) v[u] = *(const uint4*)(buf + (u * VL_SCAN_THREADS + threadIdx.x) * 16);
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const uint32_t i = (u * VL_SCAN_THREADS + threadIdx.x) * 16;
-            nx[u] = __shfl_down_sync(0xffffffffu, v[u].x, 1);
-            if (lane_id() == 31) nx[u] = *(const uint32_t*)(buf + i + 16);
-            const uint32_t w[5] = {v[u].x, v[u].y, v[u].z, v[u].w, nx[u]};
-            mine |= i < len && scan_any_window<FULL4>(w, n4, m4);
-        }
-        uint32_t vote = __ballot_sync(0xffffffffu, mine);
-        if (vote) {                                           // rare: verify the candidates of one lane with the whole warp
-            const DevColumn& c = B.cols[(uint64_t)b * B.nfields + slot];
-            while (vote) {
-                const int src = __ffs(vote) - 1; vote &= vote - 1;
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const uint32_t i = (u * VL_SCAN_THREADS + (threadIdx.x & ~31u) + src) * 16;
-                    const uint32_t w[5] = {v[u].x, v[u].y, v[u].z, v[u].w, nx[u]};
-                    uint32_t cand = lane_id() == (uint32_t)src && i < len ? scan_window_mask(w, n4, m4) : 0;
-                    cand = __shfl_sync(0xffffffffu, cand, src);
-                    while (cand) {
-                        const int k = __ffs(cand) - 1; cand &= cand - 1;
-                        scan_verify_warp(P, B, c, sp, b, row_off64, off + i + k, leaf_bm);
-                    }
-                }
-            }
-        }
-        __syncwarp();
-        if (lane_id() == 0) mbar_arrive(bars + 8 * (VL_TMA_STAGES + stage));            // this warp is done with the stage
     }
 }
 
@@ -915,11 +759,11 @@ static __global__ void k_word_match(DevProgram P, BatchView B, uint32_t leaf_idx
 
 // ---- generic per-row matcher: one warp per bitmap word, lanes take rows l and l+32 ------------------------------------------------------------
 // exact / in() / regexp-without-literal-prefix on string columns; numeric columns that must be formatted to text first.
-// Persistent grid over the ACT_ROW work list: work item j = block work_blocks[j]; its bitmap words are dealt out to the CTA's warps.
+// Persistent grid over the ACT_ROW work list of k_plan_leaf: work item j = block work_blocks[j]; its bitmap words are dealt out to the CTA's warps.
 static __global__ void k_row_match(DevProgram P, BatchView B, uint32_t leaf_idx, int slot, const uint32_t* __restrict__ work_blocks,
                                    const uint32_t* __restrict__ work_count, const uint64_t* __restrict__ payload,
-                                   const uint32_t* __restrict__ row_off64, uint64_t* __restrict__ leaf_bm) {
-  const uint32_t nwork = work_count[0];
+                                   const uint32_t* __restrict__ row_off8, uint64_t* __restrict__ leaf_bm) {
+  const uint32_t nwork = work_count[WC_ROW];
   const DevLeaf& L = P.leaves[leaf_idx];
   for (uint32_t j = blockIdx.x; j < nwork; j += gridDim.x) {
     const uint32_t b = work_blocks[j];
@@ -939,7 +783,7 @@ static __global__ void k_row_match(DevProgram P, BatchView B, uint32_t leaf_idx,
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, ia, d), u = __shfl_up_sync(0xffffffffu, ib, d); if (lane_id() >= d) { ia += t; ib += u; } }
     uint32_t tot_a = __shfl_sync(0xffffffffu, ia, 31);
-    uint64_t base = c.lens_type >= 4 ? (uint64_t)r0 * c.lens_const : row_off64[gw];
+    uint64_t base = c.lens_type >= 4 ? (uint64_t)r0 * c.lens_const : row_off8[gw << 3];
     uint64_t oa = base + ia - la, ob = base + tot_a + ib - lb;
     if (c.data_const) { oa = ob = 0; la = lb = (uint32_t)c.data_len; }   // every row = data (encoding.go:113-120)
     bool ha = false, hb = false;

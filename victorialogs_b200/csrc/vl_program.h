@@ -145,6 +145,27 @@ inline bool parse_iso8601(const std::string& s, int64_t* out) {   // tryParseTim
 }
 inline uint64_t host_zigzag(int64_t v) { return ((uint64_t)v << 1) ^ (uint64_t)(v >> 63); }
 
+// ---- filter of the row-agnostic substring scan (k_substr_scan, vl_kernels.cuh) ----------------------------------------------------------
+// An occurrence of the needle that starts at byte r of an aligned 4-byte word leaves c0 = min(4 - r, L) needle bytes in that word and
+// c1 = min(4, L - (4 - r)) in the next one.  Per r the kernel tests ONE aligned word: the one that carries more needle bytes (the first on a tie).
+// pat / msk: its bytes and which of them count (little-endian word); delta: occurrence start - address of that word.  Every occurrence is found
+// by exactly the pattern of its r; everything a pattern finds is verified at (word address + delta[r]).  Returns whether some mask is partial
+// (needles of >= 7 bytes: never).  nd16 = the first 16 needle bytes as little-endian words, zero padded.
+inline bool fill_scan_patterns(const uint8_t* nd, uint32_t L, uint32_t pat[4], uint32_t msk[4], int32_t delta[4], uint32_t nd16[4]) {
+    bool masked = false;
+    for (uint32_t r = 0; r < 4; r++) {
+        const uint32_t c0 = std::min<uint32_t>(4 - r, L), c1 = L > 4 - r ? std::min<uint32_t>(4, L - (4 - r)) : 0;
+        uint32_t p = 0, m = 0;
+        if (c1 > c0) { for (uint32_t i = 0; i < c1; i++) { p |= (uint32_t)nd[4 - r + i] << (8 * i); m |= 0xFFu << (8 * i); } delta[r] = -(int32_t)(4 - r); }
+        else { for (uint32_t i = 0; i < c0; i++) { p |= (uint32_t)nd[i] << (8 * (r + i)); m |= 0xFFu << (8 * (r + i)); } delta[r] = (int32_t)r; }
+        pat[r] = p; msk[r] = m;
+        if (m != 0xFFFFFFFFu) masked = true;
+    }
+    for (int k = 0; k < 4; k++) nd16[k] = 0;
+    for (uint32_t i = 0; i < std::min<uint32_t>(L, 16); i++) nd16[i >> 2] |= (uint32_t)nd[i] << (8 * (i & 3));
+    return masked;
+}
+
 // ---- program ------------------------------------------------------------------------------------------------------
 struct PNode { int kind = F_NOOP; int leaf = -1; std::vector<int> kids; int prepass_begin = 0, prepass_count = 0; };
 
@@ -232,6 +253,9 @@ class ProgramBuilder {
             if (R.dot_star) scan(SCAN_CONTAINS, R.prefix_off, R.prefix_len);
             else if (R.dot_plus) scan(SCAN_RX_DOTPLUS, R.prefix_off, R.prefix_len);
             else if (R.sub_kind == 2) L.str_strategy = STR_ROW;   // substrDotPlus first-occurrence rule (regex.go:181-185)
+            // `PREFIX.*LITERAL` (dot-all): equivalent to "LITERAL occurs somewhere behind an occurrence of PREFIX".  Scan for the longer of the
+            // two literals (rarer in the data, and from 7 bytes on every occurrence covers a whole aligned word) and verify the other one.
+            else if (R.tail_len > R.prefix_len) scan(SCAN_RX_TAIL, R.tail_off, R.tail_len);
             else scan(SCAN_RX_SUFFIX, R.prefix_off, R.prefix_len);
         } else {
             if (R.dot_star) L.str_strategy = STR_ALL;

@@ -97,6 +97,6 @@ enum { STR_ROW = 0, STR_SCAN = 1, STR_ALL = 2 };
 // per (block, leaf) decision of the header dispatch
 enum { ACT_NONE = 0, ACT_ALL = 1, ACT_DICT = 2, ACT_SCAN = 3, ACT_FIXED_EQ = 4, ACT_FIXED_IN = 5, ACT_ROW = 6 };
 // scan verifier modes of the row-agnostic substring kernel
-enum { SCAN_PHRASE = 0, SCAN_PREFIX = 1, SCAN_CONTAINS = 2, SCAN_RX_DOTPLUS = 3, SCAN_RX_SUFFIX = 4 };
+enum { SCAN_PHRASE = 0, SCAN_PREFIX = 1, SCAN_CONTAINS = 2, SCAN_RX_DOTPLUS = 3, SCAN_RX_SUFFIX = 4, SCAN_RX_TAIL = 5 };
 
 }  // namespace vl
