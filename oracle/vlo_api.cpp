@@ -3,6 +3,8 @@
 #include "vlo_block.h"
 #include "vlo_gen.h"
 #include "vlo_part.h"
+#include <pthread.h>
+#include <sched.h>
 #include <thread>
 #include <atomic>
 #include <chrono>
@@ -356,14 +358,23 @@ int vlo_gen_rows(const vlo_gen_config* cfg, uint64_t block_id, int column, uint8
 // blocks ("with-zstd" variant of BASELINE.md); *secs covers all passes.
 // Returns seconds spent scanning in *secs; accumulates stats; out_counts (may be NULL) gets per-block match counts;
 // out_digest gets xor of xxh64(bitmap words) keyed by block id.
+// flags: bit 0 = "post-zstd" variant (values blocks decompressed before the timed region: the input stage of the device-resident scan),
+// bit 1 = pin worker t to CPU t % ncpu (steadier numbers on a shared host).
 int vlo_scan_generated(const vlo_gen_config* cfg, void* filter, uint64_t block_lo, uint64_t block_hi, int threads, int passes, double* secs,
-                       uint64_t* stats6, uint32_t* out_counts, uint64_t* out_digest, uint64_t* total_matches) {
+                       uint64_t* stats6, uint32_t* out_counts, uint64_t* out_digest, uint64_t* total_matches, int flags) {
     return guard([&] {
         uint64_t nb = block_hi - block_lo;
         std::vector<Block> blocks(nb);
+        const bool post_zstd = flags & 1, pin = flags & 2;
         {
             std::vector<std::thread> th; std::atomic<uint64_t> next{0};
-            for (int t = 0; t < threads; t++) th.emplace_back([&] { for (;;) { uint64_t i = next++; if (i >= nb) break; blocks[i] = gen_block(*cfg, block_lo + i); } });
+            for (int t = 0; t < threads; t++) th.emplace_back([&] {
+                for (;;) {
+                    uint64_t i = next++; if (i >= nb) break;
+                    blocks[i] = gen_block(*cfg, block_lo + i);
+                    if (post_zstd) for (Column& c : blocks[i].columns) c.predecoded = std::make_shared<const DecodedStringsBlock>(decode_values_block_stage(c.valuesBlock));
+                }
+            });
             for (auto& t : th) t.join();
         }
         std::vector<ScanStats> sts(threads); std::vector<uint64_t> digs(threads, 0), tots(threads, 0);
@@ -373,8 +384,10 @@ int vlo_scan_generated(const vlo_gen_config* cfg, void* filter, uint64_t block_l
         { BlockSearch bs; Bitmap bm; if (nb) block_search(bs, blocks[0], f, bm, nullptr); }   // warm lazily-initialised token caches
         auto t0 = std::chrono::steady_clock::now();
         std::vector<std::thread> th;
+        const unsigned ncpu = std::max(1u, std::thread::hardware_concurrency());
         for (int t = 0; t < threads; t++) th.emplace_back([&, t] {
             try {
+                if (pin) { cpu_set_t set; CPU_ZERO(&set); CPU_SET((unsigned)t % ncpu, &set); pthread_setaffinity_np(pthread_self(), sizeof set, &set); }
                 BlockSearch bs; Bitmap bm;
                 uint64_t lo = nb * t / threads, hi = nb * (t + 1) / threads;
                 for (int pass = 0; pass < passes; pass++)

@@ -30,6 +30,9 @@ struct Column {
     std::vector<std::string> dict;
     std::string valuesBlock;   // marshalStringsBlock(encoded values) == bytes at [valuesOffset, valuesOffset+valuesSize)
     std::string bloom;         // bytes at [bloomFilterOffset, +bloomFilterSize): big-endian u64 words
+    // bench only ("post-zstd" CPU baseline): the two bytes blocks of valuesBlock already decompressed, so that the timed scan
+    // starts at the same input stage as the device-resident scan.  Never set by the parity tests.
+    std::shared_ptr<const DecodedStringsBlock> predecoded;
 };
 struct ConstColumn { std::string name, value; };
 struct Block {
@@ -306,7 +309,7 @@ struct BlockSearch {
     const Block* b = nullptr;
     ScanStats* st = nullptr;
     std::map<std::string, BloomFilter> bloomCache;
-    struct Vals { DecodedStringsBlock dec; std::vector<sv> values; };
+    struct Vals { DecodedStringsBlock dec; const DecodedStringsBlock* d = nullptr; std::vector<sv> values; };
     std::map<std::string, std::unique_ptr<Vals>> valuesCache;
     std::vector<int64_t> timestampsCache; bool timestampsCached = false;
     const std::vector<int64_t>& timestamps() {   // getTimestamps block_search.go:479-506
@@ -336,9 +339,10 @@ struct BlockSearch {
         auto it = valuesCache.find(ch->name);
         if (it != valuesCache.end()) return it->second->values;
         auto v = std::make_unique<Vals>();
-        v->dec = decode_values_block_stage(ch->valuesBlock);
-        v->values = unmarshal_strings(v->dec, b->rows);
-        if (st) { st->values_bytes += v->dec.lens_items.size() + v->dec.data.size(); st->blocks_values_read++; }
+        if (ch->predecoded) v->d = ch->predecoded.get();
+        else { v->dec = decode_values_block_stage(ch->valuesBlock); v->d = &v->dec; }
+        v->values = unmarshal_strings(*v->d, b->rows);
+        if (st) { st->values_bytes += v->d->lens_items.size() + v->d->data.size(); st->blocks_values_read++; }
         auto& ref = *v;
         valuesCache.emplace(ch->name, std::move(v));
         return ref.values;

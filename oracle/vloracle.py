@@ -33,7 +33,11 @@ def build():
 def lib():
     global _LIB
     if _LIB is None:
-        path = os.path.join(_HERE, "liboracle.so")
+        # VLORACLE_LIB: bench.py's CPU arm points this at oracle/_ref/liboracle_zstd157.so (same code linked against the reference's own
+        # libzstd 1.5.7 static library) when that build exists; everything else uses the plain build
+        path = os.environ.get("VLORACLE_LIB") or os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            path = os.path.join(_HERE, "liboracle.so")
         if not os.path.exists(path):
             build()
         L = C.CDLL(path)
@@ -477,15 +481,16 @@ def gen_rows(cfg, block_id, column, cap=None):
     return [raw[int(offs[i]):int(offs[i + 1])] for i in range(rows)]
 
 
-def scan_generated(cfg, flt, block_lo, block_hi, threads, want_counts=False, passes=1):
-    """CPU baseline: multi-threaded blockSearch over generated blocks. -> dict(secs, stats, digest, matches, counts)"""
+def scan_generated(cfg, flt, block_lo, block_hi, threads, want_counts=False, passes=1, post_zstd=False, pin=False):
+    """CPU baseline: multi-threaded blockSearch over generated blocks. -> dict(secs, stats, digest, matches, counts).
+    post_zstd: values blocks are decompressed before the timed region (the input stage of the device-resident scan); pin: worker t -> CPU t."""
     secs = C.c_double()
     stats = np.zeros(6, dtype=np.uint64)
     dig, tot = C.c_uint64(), C.c_uint64()
     counts = np.zeros(block_hi - block_lo, dtype=np.uint32) if want_counts else None
     r = lib().vlo_scan_generated(C.byref(cfg), flt.h, C.c_uint64(block_lo), C.c_uint64(block_hi), C.c_int(threads), C.c_int(passes), C.byref(secs),
                                  stats.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p) if want_counts else None,
-                                 C.byref(dig), C.byref(tot))
+                                 C.byref(dig), C.byref(tot), C.c_int((1 if post_zstd else 0) | (2 if pin else 0)))
     if r:
         raise _err()
     return dict(secs=secs.value, passes=passes, stats=stats, digest=dig.value, matches=tot.value, counts=counts)

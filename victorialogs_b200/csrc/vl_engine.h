@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 #include "../../include/vlscan.h"
@@ -26,7 +27,7 @@ struct DevBuf {
         if (n <= cap) return;
         if (p) VL_CUDA(cudaFree(p));
         p = nullptr; cap = 0;
-        size_t want = n + n / 8 + 256;
+        size_t want = n + std::min<size_t>(n / 8, (size_t)256 << 20) + 256;   // growth slack, capped: a 150 GB arena must not ask for 170 GB
         VL_CUDA(cudaMalloc(&p, want)); cap = want;
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
