@@ -268,11 +268,16 @@ int vlscan_last_scan_stats(vlscan_ctx* ctx, vlscan_stats* stats);
  *   out_bitmap_words : packed per-block bitmaps, block b at word offset sum_{i<b} ceil(rows_i/64); bit i%64 of word i/64
  *                      = row i, tail bits zero (lib/logstorage/bitmap.go:28-31,62-72) so Go can alias it as bitmap.a
  *   out_match_counts : per block onesCount() (bitmap.go:185-191) == blockResult.rowsLen (block_result.go:403-414)
- * Either may be NULL. Synchronises the ctx stream. */
+ * Either may be NULL. Synchronises the ctx stream.  Bitmaps and counts live in the ctx: the scanned batch may already have been freed. */
 int vlscan_fetch_results(vlscan_ctx* ctx, uint64_t* out_bitmap_words, uint32_t* out_match_counts, vlscan_stats* stats /* may be NULL: d2h_bytes */);
 /* Ascending hit-row indexes (u32 per hit, row index within its block) of the last scan, block after block; for callers
  * that want to skip forEachSetBitReadonly (bitmap.go:156-183).  out_hit_offsets has nblocks+1 entries. */
 int vlscan_fetch_hits(vlscan_ctx* ctx, uint32_t* out_hit_rows, uint64_t cap, uint64_t* out_hit_offsets);
+/* Digest of the last scan's bitmaps of the blocks [block_lo, block_hi) of its batch, computed on the device: xor over the blocks of
+ * XXH64(the block's bitmap words as little-endian bytes) * (2 * (key_base + block index) + 1).  The oracle reports the same quantity for its own
+ * bitmaps, so a bench can check a billion-row scan against the CPU restatement on any block range without moving the bitmaps.  The batch of the
+ * last scan must still be alive (like for vlscan_fetch_hits: both read its block table on the device). */
+int vlscan_result_digest(vlscan_ctx* ctx, uint64_t block_lo, uint64_t block_hi, uint64_t key_base, uint64_t* out_digest);
 /* Device pointers of the last scan's results (bench / multi-GPU reduce): bitmap words, per-block counts,
  * and a 4 x u64 totals vector {rows, rows_matched, blocks_matched, values_bytes}. */
 int vlscan_result_device_ptrs(vlscan_ctx* ctx, void** bitmap_words, void** match_counts, void** totals4);

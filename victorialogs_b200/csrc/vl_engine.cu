@@ -556,6 +556,7 @@ static void do_scan(vlscan_ctx* ctx, const vlscan_program* prog, const vlscan_ba
     }
     VL_CUDA(cudaEventRecord(ctx->ev_end, ctx->stream));
     ctx->last_batch = batch; ctx->has_result = true; ctx->last_launches = ctx->launches - launches0;
+    ctx->last_nblocks = batch->nblocks; ctx->last_nwords = batch->nwords; ctx->last_rows = batch->rows;
     if (stats) {
         read_stats(ctx, stats, true);
         stats->blocks += batch->nblocks; stats->rows += batch->rows; stats->gpu_launches += ctx->launches - launches0;
@@ -993,7 +994,7 @@ int vlscan_last_scan_stats(vlscan_ctx* ctx, vlscan_stats* stats) {
         if (!ctx->has_result) throw BadInput("no scan on this ctx yet");
         VL_CUDA(cudaSetDevice(ctx->device));
         read_stats(ctx, stats, true);
-        stats->blocks += ctx->last_batch->nblocks; stats->rows += ctx->last_batch->rows; stats->gpu_launches += ctx->last_launches;
+        stats->blocks += ctx->last_nblocks; stats->rows += ctx->last_rows; stats->gpu_launches += ctx->last_launches;
     });
 }
 
@@ -1001,10 +1002,9 @@ int vlscan_fetch_results(vlscan_ctx* ctx, uint64_t* out_bitmap_words, uint32_t* 
     return guarded(ctx, [&] {
         if (!ctx->has_result) throw BadInput("no scan result to fetch on this ctx");
         VL_CUDA(cudaSetDevice(ctx->device));
-        const vlscan_batch* b = ctx->last_batch;
-        uint64_t d2h = 0;
-        if (out_bitmap_words && b->nwords) { VL_CUDA(cudaMemcpyAsync(out_bitmap_words, ctx->regs[0].p, b->nwords * 8, cudaMemcpyDeviceToHost, ctx->stream)); d2h += b->nwords * 8; }
-        if (out_match_counts && b->nblocks) { VL_CUDA(cudaMemcpyAsync(out_match_counts, ctx->counts.p, b->nblocks * 4, cudaMemcpyDeviceToHost, ctx->stream)); d2h += b->nblocks * 4; }
+        uint64_t d2h = 0;   // bitmaps and counts live in ctx scratch: no access to the batch here
+        if (out_bitmap_words && ctx->last_nwords) { VL_CUDA(cudaMemcpyAsync(out_bitmap_words, ctx->regs[0].p, ctx->last_nwords * 8, cudaMemcpyDeviceToHost, ctx->stream)); d2h += ctx->last_nwords * 8; }
+        if (out_match_counts && ctx->last_nblocks) { VL_CUDA(cudaMemcpyAsync(out_match_counts, ctx->counts.p, ctx->last_nblocks * 4, cudaMemcpyDeviceToHost, ctx->stream)); d2h += ctx->last_nblocks * 4; }
         read_stats(ctx, nullptr, true);
         if (stats) stats->d2h_bytes += d2h;
     });
@@ -1024,6 +1024,22 @@ int vlscan_fetch_hits(vlscan_ctx* ctx, uint32_t* out_hit_rows, uint64_t cap, uin
         uint64_t total = out_hit_offsets[b->nblocks];
         if (total > cap) throw BadInput("hit buffer too small");
         if (total) VL_CUDA(cudaMemcpyAsync(out_hit_rows, ctx->hits.p, total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        VL_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+int vlscan_result_digest(vlscan_ctx* ctx, uint64_t block_lo, uint64_t block_hi, uint64_t key_base, uint64_t* out_digest) {
+    return guarded(ctx, [&] {
+        if (!ctx->has_result) throw BadInput("no scan result on this ctx");
+        if (block_lo > block_hi || block_hi > ctx->last_nblocks) throw BadInput("block range outside the batch of the last scan");
+        VL_CUDA(cudaSetDevice(ctx->device));
+        ctx->hit_offs.ensure(16);
+        VL_CUDA(cudaMemsetAsync(ctx->hit_offs.p, 0, 8, ctx->stream));
+        if (block_hi > block_lo) {
+            k_bitmap_digest<<<cdiv(block_hi - block_lo, 128), 128, 0, ctx->stream>>>(ctx->last_batch->view(), ctx->regs[0].as<uint64_t>(), (uint32_t)block_lo, (uint32_t)block_hi, key_base, ctx->hit_offs.as<unsigned long long>());
+            launch_check(ctx);
+        }
+        VL_CUDA(cudaMemcpyAsync(out_digest, ctx->hit_offs.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
         VL_CUDA(cudaStreamSynchronize(ctx->stream));
     });
 }

@@ -88,7 +88,8 @@ struct vlscan_ctx {
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> scan_events; size_t scan_events_used = 0;
     // last scan
-    const vlscan_batch* last_batch = nullptr;
+    const vlscan_batch* last_batch = nullptr;   // the batch of the last scan: must stay alive until its results have been fetched
+    uint64_t last_nblocks = 0, last_nwords = 0, last_rows = 0;   // host-side facts about it, kept here so that counters never touch a freed batch
     vlscan_batch* recycle = nullptr;       // staging batch reused by vlscan_scan_batch
     bool has_result = false;
     uint64_t last_launches = 0;

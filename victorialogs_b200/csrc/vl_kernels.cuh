@@ -568,8 +568,13 @@ static __device__ __forceinline__ uint32_t ld_u32_unaligned(const uint8_t* p) { 
 // Verification of one candidate occurrence at byte `pos` of block b's data by a single lane.
 static __device__ __forceinline__ void scan_verify_lane(const DevProgram& P, const BatchView& B, const DevColumn& c, const ScanParams& sp, uint32_t b,
                                                      const uint32_t* __restrict__ row_off8, uint32_t pos, uint64_t* __restrict__ leaf_bm) {
+    // everything the chain below depends on is requested up front: column header fields, the block's row count and first bitmap word
     const uint8_t* data = B.arena + c.data_off;
     const uint32_t L = sp.needle_len, n = (uint32_t)c.data_len;
+    const uint32_t lens_type = c.lens_type, lens_const = c.lens_const;
+    const uint8_t* lens = B.arena + c.lens_off;
+    const uint32_t rows = B.blk_rows[b];
+    const uint64_t w0 = B.blk_word_off[b];
     if ((uint64_t)pos + L > n) return;
     // the filter only vouches for some of the L bytes.  Payloads keep >= 32 readable bytes past data_len, so whole words may be compared.
     {
@@ -584,16 +589,13 @@ static __device__ __forceinline__ void scan_verify_lane(const DevProgram& P, con
         for (uint32_t k = 16; k < L; k++) if (data[pos + k] != nd[k]) return;
     }
     // byte offset -> row
-    const uint32_t rows = B.blk_rows[b];
-    const uint64_t w0 = B.blk_word_off[b];
     uint32_t r, off, len;
-    if (c.lens_type >= 4) {
-        len = c.lens_const;
+    if (lens_type >= 4) {
+        len = lens_const;
         if (len == 0) return;
         r = pos / len; off = r * len;
         if (r >= rows) return;
     } else {
-        const uint8_t* lens = B.arena + c.lens_off;
         const uint32_t* ro = row_off8 + (w0 << 3);
         const uint32_t n8 = (rows + 7) >> 3;
         // last group of 8 rows that starts at or before pos.  Row lengths of one block are close to uniform, so pos * n8 / n is almost always
@@ -609,7 +611,7 @@ static __device__ __forceinline__ void scan_verify_lane(const DevProgram& P, con
         const uint32_t r0 = lo * 8, kmax = min(8u, rows - r0);
         uint32_t o = ro[lo];
         r = r0; off = o; len = 0;
-        if (c.lens_type == 0) {
+        if (lens_type == 0) {
             const uint2 lw = *(const uint2*)(lens + r0);   // r0 is a multiple of 8 and lens_off is 16-byte aligned
             const uint64_t l8 = ((uint64_t)lw.y << 32) | lw.x;
             for (uint32_t k = 0; k < kmax && o <= pos; k++) { const uint32_t l = (uint32_t)(l8 >> (8 * k)) & 0xFF; r = r0 + k; off = o; len = l; o += l; }
@@ -654,13 +656,22 @@ static __device__ __forceinline__ uint32_t scan_word_hits(uint32_t w, const Scan
     return (uint32_t)(w == sp.pat[0]) | (uint32_t)(w == sp.pat[1]) << 1 | (uint32_t)(w == sp.pat[2]) << 2 | (uint32_t)(w == sp.pat[3]) << 3;
 }
 
-// The slow path of the scan: enumerate the candidates of one lane's four vectors and verify each.  Kept out of line on purpose: behind a call
-// boundary the compiler cannot share sub-expressions with the filter of the hot loop (it spilled 16 masked words per round to do so), and the
-// registers the verification needs do not count against the 48 of the streaming loop.
+// Candidates are not verified where they are found: the lane that holds them appends (block, byte position) to a queue in shared memory and goes
+// on streaming.  Verifying in place costs a chain of ~6 dependent memory round trips (column header, row offsets, lens items, neighbouring bytes)
+// during which the other 31 lanes of the warp wait; out of the queue, the CTA's 256 threads verify 256 candidates at once, so the chain is paid
+// once per few hundred candidates and its loads overlap.  The queue is drained when a tile ends with at least VL_SCAN_QFLUSH entries, and when
+// the CTA has run out of tiles.  A candidate that finds the queue full is verified by its lane on the spot.
+#define VL_SCAN_QCAP 1024
+#define VL_SCAN_QFLUSH 192
+struct ScanCand { uint32_t block, pos; };
+
+// Enumerate the candidates of one lane's four vectors.  Kept out of line on purpose: behind a call boundary the compiler cannot share
+// sub-expressions with the filter of the hot loop (it spilled 16 masked words per round to do so), and the registers of this path do not
+// count against the 48 of the streaming loop.
 template <bool MASKED>
-static __device__ __noinline__ void scan_candidates(const DevProgram& P, const BatchView& B, const DevColumn& c, const ScanParams& sp, uint32_t b,
-                                                    const uint32_t* __restrict__ row_off8, uint64_t* __restrict__ leaf_bm, uint4 v0, uint4 v1, uint4 v2, uint4 v3,
-                                                    uint32_t base, uint32_t n) {
+static __device__ __noinline__ void scan_enqueue(const DevProgram& P, const BatchView& B, const DevColumn& c, const ScanParams& sp, uint32_t b,
+                                                 const uint32_t* __restrict__ row_off8, uint64_t* __restrict__ leaf_bm, ScanCand* s_q, uint32_t* s_cnt,
+                                                 uint4 v0, uint4 v1, uint4 v2, uint4 v3, uint32_t base, uint32_t n) {
     const uint32_t w[16] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
     unsigned long long cand = 0;             // bit 16 * u + 4 * i + r: word i of vector u matches pattern r
 #pragma unroll
@@ -670,7 +681,17 @@ static __device__ __noinline__ void scan_candidates(const DevProgram& P, const B
         const int u = bit >> 4, i = (bit >> 2) & 3, r = bit & 3;
         // vectors past the end of the data were not loaded (zeros); a zero word can only match a pattern of NUL bytes, rejected by the bounds below
         const int64_t q = (int64_t)base + u * (int64_t)VL_SCAN_QSTRIDE + 4 * i + sp.delta[r];
-        if (q >= 0 && q < (int64_t)n) scan_verify_lane(P, B, c, sp, b, row_off8, (uint32_t)q, leaf_bm);
+        if (q < 0 || q + (int64_t)sp.needle_len > (int64_t)n) continue;
+        const uint32_t at = atomicAdd(s_cnt, 1u);
+        if (at < VL_SCAN_QCAP) s_q[at] = ScanCand{b, (uint32_t)q};
+        else scan_verify_lane(P, B, c, sp, b, row_off8, (uint32_t)q, leaf_bm);
+    }
+}
+static __device__ __noinline__ void scan_drain(const DevProgram& P, const BatchView& B, int slot, const ScanParams& sp, const uint32_t* __restrict__ row_off8,
+                                               uint64_t* __restrict__ leaf_bm, const ScanCand* s_q, uint32_t count) {
+    for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) {
+        const ScanCand e = s_q[i];
+        scan_verify_lane(P, B, B.cols[(uint64_t)e.block * B.nfields + slot], sp, e.block, row_off8, e.pos, leaf_bm);
     }
 }
 
@@ -680,6 +701,10 @@ template <bool MASKED>
 static __global__ void __launch_bounds__(VL_SCAN_THREADS, 5) k_substr_scan(const __grid_constant__ DevProgram P, const __grid_constant__ BatchView B, int slot, const __grid_constant__ ScanParams sp, const uint32_t* __restrict__ tile_block,
                                                                            const uint32_t* __restrict__ tile_off, const uint32_t* __restrict__ work_count,
                                                                            const uint32_t* __restrict__ row_off8, uint64_t* __restrict__ leaf_bm) {
+    __shared__ ScanCand s_q[VL_SCAN_QCAP];
+    __shared__ uint32_t s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
     const uint32_t ntiles = work_count[WC_TILES];
     for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const uint32_t b = __ldg(tile_block + t), tile0 = __ldg(tile_off + t);
@@ -709,11 +734,18 @@ static __global__ void __launch_bounds__(VL_SCAN_THREADS, 5) k_substr_scan(const
                     else hit[u] |= w[i] == sp.pat[0] || w[i] == sp.pat[1] || w[i] == sp.pat[2] || w[i] == sp.pat[3];
                 }
             }
-            // (zero padding past n can only equal a pattern that fails verification: the occurrence would end past n)
-            // rare: this lane holds candidates and verifies them itself (the warp's other lanes wait, or do the same with theirs)
-            if (hit[0] | hit[1] | hit[2] | hit[3]) scan_candidates<MASKED>(P, B, c, sp, b, row_off8, leaf_bm, v[0], v[1], v[2], v[3], base, n);
+            if (hit[0] | hit[1] | hit[2] | hit[3]) scan_enqueue<MASKED>(P, B, c, sp, b, row_off8, leaf_bm, s_q, &s_cnt, v[0], v[1], v[2], v[3], base, n);   // rare
+        }
+        // end of the tile: drain the queue if it is worth a pass of the whole CTA (thread 0 decides; the barrier makes the decision uniform)
+        if (__syncthreads_or(threadIdx.x == 0 && s_cnt >= VL_SCAN_QFLUSH)) {
+            scan_drain(P, B, slot, sp, row_off8, leaf_bm, s_q, min(s_cnt, (uint32_t)VL_SCAN_QCAP));
+            __syncthreads();
+            if (threadIdx.x == 0) s_cnt = 0;
+            __syncthreads();
         }
     }
+    __syncthreads();
+    scan_drain(P, B, slot, sp, row_off8, leaf_bm, s_q, min(s_cnt, (uint32_t)VL_SCAN_QCAP));
 }
 
 // ---- dict LUT / fixed-width equality / typed in(): one thread per bitmap word ---------------------------------------------------------------
@@ -878,6 +910,20 @@ static __global__ void k_hits_compact(BatchView B, const uint64_t* __restrict__ 
         while (bits) { int k = __ffsll((long long)bits) - 1; bits &= bits - 1; if (pos < cap) hits[pos] = rbase + k; pos++; }
         out += __shfl_sync(0xffffffffu, incl, 31);
     }
+}
+
+// ---- digest of the result bitmaps (bench / tests; the oracle computes the same over its own bitmaps, oracle/vlo_api.cpp vlo_scan_generated) -------
+// xor over the blocks [block_lo, block_hi) of XXH64(the block's bitmap words as bytes) * (2 * key + 1), key = key_base + block index in the batch.
+static __global__ void k_bitmap_digest(BatchView B, const uint64_t* __restrict__ reg, uint32_t block_lo, uint32_t block_hi, uint64_t key_base, unsigned long long* __restrict__ out) {
+    const uint32_t b = block_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long d = 0;
+    if (b < block_hi) {
+        const uint64_t lo = B.blk_word_off[b], hi = B.blk_word_off[b + 1];
+        d = xxh64((const uint8_t*)(reg + lo), (uint32_t)((hi - lo) * 8)) * (2 * (key_base + b) + 1);
+    }
+#pragma unroll
+    for (int s = 16; s; s >>= 1) d ^= __shfl_xor_sync(0xffffffffu, d, s);
+    if (lane_id() == 0 && d) atomicXor(out, d);
 }
 
 }  // namespace vl

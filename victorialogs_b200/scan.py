@@ -69,7 +69,7 @@ EXPORTS = ["vlscan_device_count", "vlscan_ctx_create", "vlscan_ctx_free", "vlsca
            "vlscan_batch_upload", "vlscan_batch_free", "vlscan_batch_nblocks", "vlscan_batch_rows", "vlscan_batch_words", "vlscan_batch_device_bytes",
            "vlscan_batch_generate", "vlscan_batch_download", "vlscan_host_blocks_get", "vlscan_host_blocks_field", "vlscan_host_blocks_bytes",
            "vlscan_host_blocks_free", "vlscan_host_blocks_compress", "vlscan_zstd_decompress", "vlscan_zstd_inspect", "vlscan_zstd_walk_digest", "vlscan_part_open", "vlscan_part_free", "vlscan_part_header", "vlscan_part_nblocks", "vlscan_part_block_header", "vlscan_part_timestamps",
-           "vlscan_part_ncolumn_names", "vlscan_part_column_name", "vlscan_part_blocks", "vlscan_host_blocks_source", "vlscan_scan_resident", "vlscan_last_scan_stats", "vlscan_fetch_results", "vlscan_fetch_hits", "vlscan_result_device_ptrs", "vlscan_scan_batch"]
+           "vlscan_part_ncolumn_names", "vlscan_part_column_name", "vlscan_part_blocks", "vlscan_host_blocks_source", "vlscan_scan_resident", "vlscan_last_scan_stats", "vlscan_fetch_results", "vlscan_fetch_hits", "vlscan_result_digest", "vlscan_result_device_ptrs", "vlscan_scan_batch"]
 
 
 def lib_path():
@@ -627,6 +627,12 @@ class Ctx:
         offs = np.zeros(batch.nblocks + 1, dtype=np.uint64)
         self._check(lib().vlscan_fetch_hits(self.h, hits.ctypes.data_as(C.c_void_p), C.c_uint64(cap), offs.ctypes.data_as(C.c_void_p)))
         return hits[:int(offs[-1])], offs
+
+    def result_digest(self, block_lo, block_hi, key_base=0):
+        """xor over blocks of XXH64(bitmap words) * (2 * (key_base + block) + 1) of the last scan, computed on the device (vlscan_result_digest)"""
+        d = C.c_uint64()
+        self._check(lib().vlscan_result_digest(self.h, C.c_uint64(block_lo), C.c_uint64(block_hi), C.c_uint64(key_base), C.byref(d)))
+        return d.value
 
     def result_device_ptrs(self):
         a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
