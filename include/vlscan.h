@@ -131,11 +131,17 @@ int vlscan_ctx_sync(vlscan_ctx* ctx);                        /* cudaStreamSynchr
  *  11 STRING_RANGE (filter_string_range.go:12-20)   bytes(fieldName) bytes(minValue) bytes(maxValue)        `f:string_range(a, b)`, [min, max)
  *  12 IPV4_RANGE   (filter_ipv4_range.go:12-20)     bytes(fieldName) varuint(minValue) varuint(maxValue)    `f:ipv4_range(a, b)`, inclusive
  *  13 VALUE_TYPE   (filter_value_type.go:12-15)     bytes(fieldName) bytes(type name)                       `f:value_type(uint8)`
+ *  14 ANY_CASE_PHRASE (filter_any_case_phrase.go:14-24)   bytes(fieldName) bytes(phrase as written)            `f:i(phrase)`
+ *  15 ANY_CASE_PREFIX (filter_any_case_prefix.go:14-24)   bytes(fieldName) bytes(prefix as written)            `f:i(prefix*)`
+ *  16 SEQUENCE     (filter_sequence.go:12-22)       bytes(fieldName) varuint(n) n x bytes(phrase)           `f:seq(a, b, ...)`
+ *  17 CONTAINS_ALL (filter_contains_all.go:12-20)   bytes(fieldName) varuint(n) n x bytes(value)            `f:contains_all(a, b, ...)`
+ *  18 CONTAINS_ANY (filter_contains_any.go:12-20)   bytes(fieldName) varuint(n) n x bytes(value)            `f:contains_any(a, b, ...)`
  * Token hashes, merged AND/OR per-field tokens, typed needles and regex automata are derived here, like the
  * sync.Once initialisers of the Go filters do on first use.  Returns <0 with an error text for malformed trees,
  * regexps that do not compile and regexps outside the supported syntax. */
 enum { VLSCAN_F_NOOP = 0, VLSCAN_F_PHRASE, VLSCAN_F_PREFIX, VLSCAN_F_EXACT, VLSCAN_F_IN, VLSCAN_F_REGEXP, VLSCAN_F_AND, VLSCAN_F_OR, VLSCAN_F_NOT,
-       VLSCAN_F_EXACT_PREFIX = 9, VLSCAN_F_LEN_RANGE = 10, VLSCAN_F_STRING_RANGE = 11, VLSCAN_F_IPV4_RANGE = 12, VLSCAN_F_VALUE_TYPE = 13 };
+       VLSCAN_F_EXACT_PREFIX = 9, VLSCAN_F_LEN_RANGE = 10, VLSCAN_F_STRING_RANGE = 11, VLSCAN_F_IPV4_RANGE = 12, VLSCAN_F_VALUE_TYPE = 13,
+       VLSCAN_F_ANY_CASE_PHRASE = 14, VLSCAN_F_ANY_CASE_PREFIX = 15, VLSCAN_F_SEQUENCE = 16, VLSCAN_F_CONTAINS_ALL = 17, VLSCAN_F_CONTAINS_ANY = 18 };
 int vlscan_program_create(const void* tree, size_t tree_len, vlscan_program** out);
 void vlscan_program_free(vlscan_program* prog);
 /* canonical names of the fields the tree references (so the caller lists only those columns per block) */
@@ -167,8 +173,8 @@ int vlscan_parse_typed(int value_type, const void* s, size_t len, uint64_t* out)
  * bounds.  Returns 1 / 0, or -1 for other kinds.  For tests against the oracle.
  * kind 5 (REGEXP): arg1 = the expression; compiled like a regexp leaf and matched by the host mirror of the device automaton (the
  * form const and dict values are matched with); -2 when the expression does not compile.
- * Also answers for the predicates that are written (host+device, csrc/vl_anycase.cuh) but not yet wired into the row kernels, under
- * provisional numbers: 14 = matchAnyCasePhrase, 15 = matchAnyCasePrefix (arg1 = the phrase / prefix already lowercased by
+ * Also answers for the value predicates of kinds 14..18 (host builds of the host+device code in csrc/vl_anycase.cuh):
+ * 14 = matchAnyCasePhrase, 15 = matchAnyCasePrefix (arg1 = the phrase / prefix already lowercased by
  * strings.ToLower), 16 = matchSequence, 17 = matchAllPhrases, 18 = matchAnyPhrase (arg1 = phrase list, each as varuint length + bytes). */
 int vlscan_eval_predicate(int kind, const void* value, size_t value_len, const void* arg1, size_t arg1_len, const void* arg2,
                           size_t arg2_len, uint64_t aux0, uint64_t aux1);

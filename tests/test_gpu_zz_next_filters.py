@@ -1,6 +1,7 @@
 """GPU parity for the filter kinds of SURVEY §8(f) rank 3 that libvlscan compiles (exact_prefix, len_range, string_range, ipv4_range,
-value_type), through the C ABI against the CPU oracle and against the reference's own tables
-(filter_{exact_prefix,len_range,string_range,ipv4_range,value_type}_test.go, 199 cases in tests/golden/filter_cases_next.json).
+value_type, i(phrase), i(prefix*), seq(), contains_all(), contains_any()), through the C ABI against the CPU oracle and against the
+reference's own tables (filter_{exact_prefix,len_range,string_range,ipv4_range,value_type,any_case_phrase,any_case_prefix,sequence,
+contains_all,contains_any}_test.go, 715 cases in tests/golden/filter_cases_next.json).
 Bar: bit-exact bitmaps and counts.  (The file name sorts after the parity tests of the round-1 kinds on purpose.)"""
 import random
 
@@ -11,7 +12,7 @@ from golden_util import load_filter_cases, build_filter
 
 pytestmark = pytest.mark.gpu
 
-KINDS = ("exact_prefix", "len_range", "string_range", "ipv4_range", "value_type")
+KINDS = ("exact_prefix", "len_range", "string_range", "ipv4_range", "value_type", "any_case_phrase", "any_case_prefix", "sequence", "contains_all", "contains_any")
 CASES = [c for c in load_filter_cases("filter_cases_next.json") if c["filter"]["kind"] in KINDS]
 
 
@@ -36,7 +37,7 @@ def check(env, blocks, of, gf, stage="ondisk"):
 
 def test_reference_tables(env):
     oracle, vs, pu, ctx = env
-    assert len(CASES) == 199
+    assert len(CASES) == 199 + 107 + 114 + 103 + 104 + 88
     for c in CASES:
         b = oracle.Block.from_columns(c["columns"])
         gf = build_filter(vs.Filter, c["filter"])
@@ -85,6 +86,14 @@ def test_every_column_kind(env):
             probes.append(("ipv4_range", f, (lo, hi)))
         for t in ["string", "dict", "const", "uint8", "uint16", "uint32", "uint64", "int64", "float64", "ipv4", "iso8601", "unknown", ""]:
             probes.append(("value_type", f, (t,)))
+        for p in ["", "1", "10", "ROW", "Row 1", "SAME VALUE", "same", "ERROR", "Info", "10.0.0.7", "2024-03-05t12:04", "2024-03-05T12:04:28.004z", "t12", "ЙЦУК", "йц", "Zz", "ZZ TOP", "-", "e", "nan", "100.5", "-130"]:
+            probes.append(("any_case_phrase", f, (p,)))
+            probes.append(("any_case_prefix", f, (p,)))
+        for lst in [[], [""], ["", ""], ["1"], ["10"], ["row", "1"], ["1", "row"], ["same", "value"], ["value", "same"], ["10", "0", "7"], ["10.0.0.7"], ["2024-03-05T12:04:28.004Z"], ["2024", "03"],
+                    ["12", "04"], ["zz", "top"], ["", "top"], ["error"], ["info", "warn"], ["100"], ["100", "5"], ["-130"], ["7", "7"], ["1", "1", "1"], ["255"], ["йцук"], ["a", ""], ["no such"]]:
+            probes.append(("sequence", f, (lst,)))
+            probes.append(("contains_all", f, (lst,)))
+            probes.append(("contains_any", f, (lst,)))
     for kind, field, args in probes:
         check(env, [blk], getattr(F, kind)(field, *args), getattr(G, kind)(field, *args))
     # combinators mixing old and new kinds
@@ -112,9 +121,12 @@ def test_random_strings_many_blocks(env):
             vals.append(v)
         blocks.append(oracle.Block.from_columns([("m", vals), ("k", [b"k%d" % (i % 11) for i in range(rows)])]))
     F, G = oracle.Filter, vs.Filter
-    for _ in range(60):
-        kind = rng.choice(["exact_prefix", "len_range", "string_range", "ipv4_range"])
-        if kind == "exact_prefix": args = ("".join(rng.choice(alphabet) for _ in range(rng.randrange(0, 3))) if rng.random() < 0.7 else "prefix x",)
+    for _ in range(140):
+        kind = rng.choice(["exact_prefix", "len_range", "string_range", "ipv4_range", "any_case_phrase", "any_case_prefix", "sequence", "contains_all", "contains_any"])
+        word = lambda: "".join(rng.choice(alphabet + ["A", "B", "Й", "É", "z"]) for _ in range(rng.randrange(0, 4)))
+        if kind in ("any_case_phrase", "any_case_prefix"): args = (word() if rng.random() < 0.8 else "PREFIX X",)
+        elif kind in ("sequence", "contains_all", "contains_any"): args = ([word() if rng.random() < 0.8 else rng.choice(["prefix", "k1", "k10", "255", "x"]) for _ in range(rng.randrange(0, 4))],)
+        elif kind == "exact_prefix": args = ("".join(rng.choice(alphabet) for _ in range(rng.randrange(0, 3))) if rng.random() < 0.7 else "prefix x",)
         elif kind == "len_range": args = tuple(sorted([rng.randrange(0, 14), rng.randrange(0, 50)]))
         elif kind == "string_range": args = tuple(sorted(["".join(rng.choice(alphabet) for _ in range(rng.randrange(0, 3))) for _ in range(2)], key=lambda s: s.encode()))
         else: args = tuple(sorted([rng.getrandbits(32) >> rng.choice([0, 8, 24]), rng.getrandbits(32)]))

@@ -44,6 +44,14 @@ VLA_HD int32_t to_lower_rune(int32_t r) {
     }
     return r;
 }
+// unicode.ToUpper (host only: the program compiler upper-cases i(...) needles for iso8601 columns)
+static const unsigned int H_TOUPPER[VL_TOUPPER_COUNT][2] = { VL_TOUPPER_INIT };
+inline int32_t to_upper_rune_host(int32_t r) {
+    if (r < 0x80) return (uint32_t)(r - 'a') < 26u ? r - 32 : r;
+    int lo = 0, hi = VL_TOUPPER_COUNT - 1;
+    while (lo <= hi) { const int mid = (lo + hi) >> 1; const unsigned a = H_TOUPPER[mid][0]; if ((uint32_t)r < a) hi = mid - 1; else if ((uint32_t)r > a) lo = mid + 1; else return (int32_t)H_TOUPPER[mid][1]; }
+    return r;
+}
 // utf8.AppendRune into out[4]; returns the length (surrogates and values above U+10FFFF are written as U+FFFD)
 VLA_HD int encode_rune(uint8_t* out, int32_t r) {
     uint32_t c = (uint32_t)r;

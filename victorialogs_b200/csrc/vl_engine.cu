@@ -15,8 +15,6 @@
 #include "vl_engine.h"
 #include "vl_program.h"
 #include "vl_part.h"
-#define VL_ANYCASE_HOST_ONLY 1   // only vlscan_eval_predicate uses these so far
-#include "vl_anycase.cuh"
 
 using namespace vl;
 
@@ -469,7 +467,7 @@ struct ScanRun {
                 VL_CUDA(cudaEventRecord(evp.second, ctx->stream));
             }
             // per-row matcher (string exact / in / general regexp; numeric columns through text); persistent grid over the ACT_ROW work list
-            if (may_row) { k_row_match<<<persistent, 256, 0, ctx->stream>>>(P, B, (uint32_t)leaf_idx, slot, row_blocks, wc, payload, ro, leaf_bm); launch_check(ctx); }
+            if (may_row) { k_row_match<<<persistent, 256, 0, ctx->stream>>>(P, B, (uint32_t)leaf_idx, slot, row_blocks, wc, action, payload, ro, leaf_bm); launch_check(ctx); }
             if (has_dict || has_numeric) { k_word_match<<<cdiv(B.nwords, 128), 128, 0, ctx->stream>>>(P, B, (uint32_t)leaf_idx, slot, action, payload, leaf_bm, stats); launch_check(ctx); }
         }
         if (B.nwords) { k_apply_leaf<<<cdiv(B.nwords, 256), 256, 0, ctx->stream>>>(B, action, leaf_bm, reg); launch_check(ctx); }

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "vl_hd.cuh"
+#include "vl_anycase.cuh"
 #include "vl_types.h"
 
 namespace vl {
@@ -126,8 +127,22 @@ static __device__ bool leaf_match_string(const DevProgram& P, const DevLeaf& L, 
     case F_EXACT_PREFIX: case F_LEN_RANGE: case F_STRING_RANGE: case F_IPV4_RANGE:   // matchExactPrefix / matchLenRange / matchStringRange / matchIPv4Range
         return range_predicate(L.kind, s, n, nd, L.needle_len, P.blob + L.needle2_off, L.needle2_len, L.aux0, L.aux1);
     case F_VALUE_TYPE: return false;   // decided from the column header alone (k_plan_leaf)
+    case F_ANY_CASE_PHRASE: return any_case_match(s, n, nd, L.needle_len, false);   // matchAnyCasePhrase: needle = the lower-cased phrase
+    case F_ANY_CASE_PREFIX: return any_case_match(s, n, nd, L.needle_len, true);
+    case F_SEQUENCE: return match_sequence(s, n, PhraseList{P.blob + L.list_off, L.list_len});
+    case F_CONTAINS_ALL: return match_all_phrases(s, n, PhraseList{P.blob + L.list_off, L.list_len});
+    case F_CONTAINS_ANY: return match_any_phrase(s, n, PhraseList{P.blob + L.list_off, L.list_len});
     }
     return true;
+}
+// The text of a typed value (number, IPv4, timestamp) against the leaf.  i(...) leaves run the plain phrase / prefix matcher here, with the
+// lower-cased needle and, on iso8601 columns, the upper-cased one ("T", "Z"): filter_any_case_phrase.go:103-126, filter_any_case_prefix.go:106-129.
+static __device__ bool leaf_match_typed_text(const DevProgram& P, const DevLeaf& L, uint32_t vt, const uint8_t* s, uint32_t n) {
+    if (L.kind == F_ANY_CASE_PHRASE || L.kind == F_ANY_CASE_PREFIX) {
+        const uint8_t* nd = P.blob + (vt == VT_ISO8601 ? L.needle2_off : L.needle_off); const uint32_t nl = vt == VT_ISO8601 ? L.needle2_len : L.needle_len;
+        return L.kind == F_ANY_CASE_PHRASE ? match_phrase(s, n, nd, nl) : match_prefix(s, n, nd, nl);
+    }
+    return leaf_match_string(P, L, s, n);
 }
 
 // numeric value -> string (toUint8String .. toTimestampISO8601String, filter_prefix.go:365-408, filter_phrase.go:310-346)
@@ -147,7 +162,7 @@ static __device__ int encoded_to_string(uint32_t vt, uint64_t raw, uint8_t* buf)
 static __device__ __noinline__ bool leaf_match_f64(const DevProgram& P, const DevLeaf& L, uint64_t raw) {
     uint8_t buf[VL_FMT_F64_MAX];
     int n = fmt_f64(buf, raw);
-    return leaf_match_string(P, L, buf, (uint32_t)n);
+    return leaf_match_typed_text(P, L, VT_FLOAT64, buf, (uint32_t)n);
 }
 
 // ---- bloom probe, warp wide (bloomFilter.containsAll, lib/logstorage/bloomfilter.go:173-191) -----------------------------------
@@ -265,6 +280,9 @@ static __global__ void __launch_bounds__(VL_PLAN_WARPS * 32) k_plan_leaf(DevProg
         case F_LEN_RANGE: act = L.aux0 == 0 ? ACT_ALL : ACT_NONE; break;                                // matchLenRange("", min, max)
         case F_STRING_RANGE: act = (nl == 0 && L.needle2_len > 0) ? ACT_ALL : ACT_NONE; break;           // "" >= min && "" < max
         case F_IPV4_RANGE: case F_VALUE_TYPE: act = ACT_NONE; break;
+        case F_ANY_CASE_PHRASE: act = nl == 0 ? ACT_ALL : ACT_NONE; break;                               // filter_any_case_phrase.go:88-95
+        case F_ANY_CASE_PREFIX: act = ACT_NONE; break;                                                   // filter_any_case_prefix.go:92-97
+        case F_SEQUENCE: case F_CONTAINS_ALL: case F_CONTAINS_ANY: act = leaf_match_string(P, L, nullptr, 0) ? ACT_ALL : ACT_NONE; break;   // the predicate on ""
         }
     } else if (L.kind == F_VALUE_TYPE) {
         act = L.aux0 == c->vt ? ACT_ALL : ACT_NONE;   // valueType.String() == wanted name (filter_value_type.go:59-66); no payload is read
@@ -282,7 +300,7 @@ static __global__ void __launch_bounds__(VL_PLAN_WARPS * 32) k_plan_leaf(DevProg
             bloom_bytes += 8ull * nh;
             return bloom_contains_all_warp(bloom, c->bloom_words, h, nh);
         };
-        const uint64_t* H = P.u64s + L.hashes_off;
+        const uint64_t* H = P.u64s + L.hashes_off; uint32_t nH = L.nhashes;
         if (vt == VT_STRING) {
             bool ok = true;
             if (L.kind == F_IN) {
@@ -294,7 +312,18 @@ static __global__ void __launch_bounds__(VL_PLAN_WARPS * 32) k_plan_leaf(DevProg
                     for (uint32_t s = 0; s < L.in_nsets && !any; s++) { bloom_bytes += 8ull * sets[2 * s + 1]; any = bloom_contains_all_warp(bloom, c->bloom_words, P.u64s + sets[2 * s], sets[2 * s + 1]); }
                     ok = any;
                 }
-            } else ok = probe(H, L.nhashes);
+            } else if (L.kind == F_CONTAINS_ANY) {
+                // matchValuesAnyPhrase filter_contains_any.go:170-189: the common tokens, then EVERY phrase's own tokens (the reference keeps the
+                // phrases that pass; a phrase that does not pass cannot match a row, so trying all of them on the rows gives the same bits)
+                ok = probe(H, L.nhashes);
+                if (ok) {
+                    bool any = false;
+                    const uint32_t* sets = P.u32s + L.in_sets_off;
+                    for (uint32_t s = 0; s < L.in_nsets; s++) { bloom_bytes += 8ull * sets[2 * s + 1]; any |= bloom_contains_all_warp(bloom, c->bloom_words, P.u64s + sets[2 * s], sets[2 * s + 1]); }
+                    ok = any;
+                }
+            } else if (L.kind == F_ANY_CASE_PHRASE || L.kind == F_ANY_CASE_PREFIX) ok = true;   // tokens are case sensitive: no probe (filter_any_case_phrase.go:97-99)
+            else ok = probe(H, L.nhashes);
             if (!ok) act = ACT_NONE;
             else if (c->data_const) act = leaf_match_string(P, L, B.arena + c->data_off, (uint32_t)c->data_len) ? ACT_ALL : ACT_NONE, values_bytes = 1;
             else {
@@ -308,6 +337,13 @@ static __global__ void __launch_bounds__(VL_PLAN_WARPS * 32) k_plan_leaf(DevProg
             uint32_t w = width_of_vt(vt);
             bool fixed_ok = c->lens_type >= 4 && c->lens_const == w && c->data_len == (uint64_t)rows * w && !c->data_const;
             const TypedNeedle& tn = L.typed[vt];
+            // i(phrase) / i(prefix*) on typed columns: the phrase / prefix filter's path with the lower-cased needle and this filter's tokens; on
+            // iso8601 columns the upper-cased needle and tokens (filter_any_case_phrase.go:103-126)
+            uint32_t kind = L.kind;
+            if (kind == F_ANY_CASE_PHRASE || kind == F_ANY_CASE_PREFIX) {
+                kind = kind == F_ANY_CASE_PHRASE ? F_PHRASE : F_PREFIX;
+                if (vt == VT_ISO8601) { H = P.u64s + L.hashes2_off; nH = L.nhashes2; nd = P.blob + L.needle2_off; nl = L.needle2_len; }
+            }
             auto in_range = [&]() -> bool {
                 switch (vt) {
                 case VT_UINT8: case VT_UINT16: case VT_UINT32: case VT_UINT64: case VT_IPV4: return tn.val >= c->min_value && tn.val <= c->max_value;
@@ -318,14 +354,15 @@ static __global__ void __launch_bounds__(VL_PLAN_WARPS * 32) k_plan_leaf(DevProg
             };
             auto exact_path = [&]() {   // match*ByExactValue -> matchBinaryValue (filter_exact.go:237-364)
                 if (!tn.ok || !in_range()) { act = ACT_NONE; return; }
-                if (!probe(H, L.nhashes)) { act = ACT_NONE; return; }
-                act = fixed_ok ? ACT_FIXED_EQ : ACT_ROW; pay = tn.val;
+                if (!probe(H, nH)) { act = ACT_NONE; return; }
+                act = fixed_ok ? ACT_FIXED_EQ : ACT_ROW_EQ; pay = tn.val;
             };
             auto tostring_path = [&](bool use_bloom) {
-                if (use_bloom && !probe(H, L.nhashes)) { act = ACT_NONE; return; }
+                if (use_bloom && !probe(H, nH)) { act = ACT_NONE; return; }
                 act = ACT_ROW;
             };
-            switch (L.kind) {
+            const bool is_uintN = vt == VT_UINT8 || vt == VT_UINT16 || vt == VT_UINT32 || vt == VT_UINT64;
+            switch (kind) {
             case F_EXACT: exact_path(); break;
             case F_PHRASE:
                 if (vt == VT_FLOAT64) { if (!L.f64_phrase_gate) act = ACT_NONE; else if (L.f64_exact_form) exact_path(); else tostring_path(true); }
@@ -350,7 +387,46 @@ static __global__ void __launch_bounds__(VL_PLAN_WARPS * 32) k_plan_leaf(DevProg
                         for (uint32_t s = 0; s < L.in_nsets && !any; s++) { bloom_bytes += 8ull * sets[2 * s + 1]; any = bloom_contains_all_warp(bloom, c->bloom_words, P.u64s + sets[2 * s], sets[2 * s + 1]); }
                         ok = any;
                     }
-                    act = !ok ? ACT_NONE : fixed_ok ? ACT_FIXED_IN : ACT_ROW;
+                    act = !ok ? ACT_NONE : fixed_ok ? ACT_FIXED_IN : ACT_ROW_IN;
+                }
+                break;
+            case F_SEQUENCE:         // filter_sequence.go:139-258
+                if (is_uintN || vt == VT_INT64) { if (L.in_count > 1) act = ACT_NONE; else exact_path(); }          // one phrase: the exact value
+                else if (vt == VT_FLOAT64) tostring_path(true);
+                else if (L.in_count == 1 && tn.ok) exact_path();                                                  // ipv4 / iso8601, one phrase that is a whole value
+                else tostring_path(true);
+                break;
+            case F_CONTAINS_ALL:     // filter_contains_all.go:168-189 (matchAllValues), :191-300
+                if (is_uintN) {
+                    const uint32_t n_values = (uint32_t)L.aux0;   // distinct non-empty values
+                    if (n_values == 0) act = ACT_ALL;
+                    else if (n_values != 1 || L.in_typed_cnt[vt] != 1) act = ACT_NONE;
+                    else if (!probe(H, nH)) act = ACT_NONE;
+                    else { act = fixed_ok ? ACT_FIXED_EQ : ACT_ROW_EQ; pay = P.u64s[L.in_typed_off[vt]]; }
+                } else tostring_path(true);
+                break;
+            case F_CONTAINS_ANY:     // filter_contains_any.go:120-168: uintN like in(), the rest like the strings path over the value's text
+                if (is_uintN) {
+                    if (L.in_typed_cnt[vt] == 0) act = ACT_NONE;
+                    else {
+                        bool ok = probe(H, nH);
+                        if (ok && !(L.in_skip_sets || (uint64_t)L.in_nsets > 10ull * rows)) {
+                            bool any = false;
+                            const uint32_t* sets = P.u32s + L.in_sets_off;
+                            for (uint32_t s = 0; s < L.in_nsets && !any; s++) { bloom_bytes += 8ull * sets[2 * s + 1]; any = bloom_contains_all_warp(bloom, c->bloom_words, P.u64s + sets[2 * s], sets[2 * s + 1]); }
+                            ok = any;
+                        }
+                        act = !ok ? ACT_NONE : fixed_ok ? ACT_FIXED_IN : ACT_ROW_IN;
+                    }
+                } else {
+                    bool ok = probe(H, nH);
+                    if (ok) {
+                        bool any = false;
+                        const uint32_t* sets = P.u32s + L.in_sets_off;
+                        for (uint32_t s = 0; s < L.in_nsets; s++) { bloom_bytes += 8ull * sets[2 * s + 1]; any |= bloom_contains_all_warp(bloom, c->bloom_words, P.u64s + sets[2 * s], sets[2 * s + 1]); }
+                        ok = any;
+                    }
+                    act = ok ? ACT_ROW : ACT_NONE;
                 }
                 break;
             case F_EXACT_PREFIX: {   // match*ByExactPrefix filter_exact_prefix.go:105-273
@@ -398,7 +474,7 @@ static __global__ void __launch_bounds__(VL_PLAN_WARPS * 32) k_plan_leaf(DevProg
         if (act >= ACT_DICT || values_bytes) values_bytes = lens_stored_bytes(*c, rows) + c->data_len;   // getValuesForColumn was reached
     }
     if (c && c->kind == COL_VALUES && c->vt == VT_DICT && act == ACT_DICT) values_bytes = lens_stored_bytes(*c, rows) + c->data_len;
-    if (c && c->kind == COL_VALUES && (act == ACT_SCAN || act == ACT_ROW)) {
+    if (c && c->kind == COL_VALUES && (act == ACT_SCAN || act >= ACT_ROW)) {
         need_lens = 1;
         if (act == ACT_SCAN) { ntiles = (uint32_t)((c->data_len + VL_TILE_BYTES - 1) / VL_TILE_BYTES); scan_bytes = c->data_len; }
         else need_row = 1;
@@ -793,7 +869,7 @@ static __global__ void k_word_match(DevProgram P, BatchView B, uint32_t leaf_idx
 // exact / in() / regexp-without-literal-prefix on string columns; numeric columns that must be formatted to text first.
 // Persistent grid over the ACT_ROW work list of k_plan_leaf: work item j = block work_blocks[j]; its bitmap words are dealt out to the CTA's warps.
 static __global__ void k_row_match(DevProgram P, BatchView B, uint32_t leaf_idx, int slot, const uint32_t* __restrict__ work_blocks,
-                                   const uint32_t* __restrict__ work_count, const uint64_t* __restrict__ payload,
+                                   const uint32_t* __restrict__ work_count, const uint8_t* __restrict__ action, const uint64_t* __restrict__ payload,
                                    const uint32_t* __restrict__ row_off8, uint64_t* __restrict__ leaf_bm) {
   const uint32_t nwork = work_count[WC_ROW];
   const DevLeaf& L = P.leaves[leaf_idx];
@@ -801,6 +877,7 @@ static __global__ void k_row_match(DevProgram P, BatchView B, uint32_t leaf_idx,
     const uint32_t b = work_blocks[j];
     const DevColumn& c = B.cols[(uint64_t)b * B.nfields + slot];
     const uint32_t rows = B.blk_rows[b];
+    const uint8_t act = action[b]; const uint64_t pay = payload[b];
     const uint64_t w_lo = B.blk_word_off[b], w_hi = B.blk_word_off[b + 1];
    for (uint64_t gw = w_lo + (threadIdx.x >> 5); gw < w_hi; gw += blockDim.x >> 5) {
     uint32_t r0 = (uint32_t)(gw - w_lo) * 64;
@@ -827,15 +904,14 @@ static __global__ void k_row_match(DevProgram P, BatchView B, uint32_t leaf_idx,
         uint32_t w = width_of_vt(vt);
         if (len != w) return false;
         uint64_t raw = load_fixed_be(s, w);
-        if (L.kind == F_IN) return in_contains_typed(L, P.u64s, vt, raw);
-        if (L.kind == F_IPV4_RANGE) return raw >= L.aux0 && raw <= L.aux1;   // only ipv4 columns get here (k_plan_leaf)
-        if (L.kind == F_EXACT) return raw == payload[b];
-        if (L.kind == F_PHRASE && L.typed[vt].ok && !(vt == VT_FLOAT64 && !L.f64_exact_form)) return raw == payload[b];
+        if (act == ACT_ROW_EQ) return raw == pay;                              // matchBinaryValue filter_exact.go:356-364
+        if (act == ACT_ROW_IN) return in_contains_typed(L, P.u64s, vt, raw);   // matchAnyValue filter_in.go:187-200
+        if (L.kind == F_IPV4_RANGE) return raw >= L.aux0 && raw <= L.aux1;     // only ipv4 columns get here (k_plan_leaf)
         if (vt == VT_FLOAT64) return leaf_match_f64(P, L, raw);
         uint8_t buf[32];
         int n = encoded_to_string(vt, raw, buf);
         if (n < 0) return false;
-        return leaf_match_string(P, L, buf, (uint32_t)n);
+        return leaf_match_typed_text(P, L, vt, buf, (uint32_t)n);
     };
     if (ra < rows) ha = eval(oa, la);
     if (rb < rows) hb = eval(ob, lb);

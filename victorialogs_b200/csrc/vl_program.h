@@ -13,6 +13,7 @@
 #include <unordered_set>
 #include <vector>
 #include "vl_hd.cuh"
+#include "vl_anycase.cuh"
 #include "vl_regex.h"
 #include "vl_types.h"
 
@@ -55,6 +56,19 @@ inline std::string host_strip_first_last_token(std::string s) {   // skipFirstLa
 }
 inline void host_token_hashes(const std::vector<std::string>& toks, std::vector<uint64_t>& out) {   // appendTokensHashes bloomfilter.go:126-144
     for (auto& t : toks) { uint64_t h = xxh64((const uint8_t*)t.data(), (uint32_t)t.size()); for (int i = 0; i < 6; i++) out.push_back(xxh64_u64(h + i)); }
+}
+
+// strings.ToLower / strings.ToUpper (Go: rune by rune through unicode.ToLower / ToUpper; an invalid byte becomes U+FFFD)
+inline std::string host_map_case(const std::string& s, bool upper) {
+    std::string out;
+    const uint8_t* p = (const uint8_t*)s.data(); uint32_t n = (uint32_t)s.size();
+    for (uint32_t i = 0; i < n;) {
+        int w; int32_t r = decode_rune(p + i, n - i, &w); i += (uint32_t)w;
+        r = upper ? to_upper_rune_host(r) : to_lower_rune(r);
+        uint8_t enc[4]; int e = encode_rune(enc, r);
+        out.append((const char*)enc, (size_t)e);
+    }
+    return out;
 }
 
 // values_encoder.go:553-585
@@ -354,11 +368,70 @@ class ProgramBuilder {
             P.leaves[l].aux0 = code;
             P.nodes[id].leaf = l; break;
         }
+        case F_ANY_CASE_PHRASE: case F_ANY_CASE_PREFIX: {   // filter_any_case_phrase.go:14-53, filter_any_case_prefix.go:14-65
+            std::string f = bytes(), s = bytes();
+            const bool pre = kind == F_ANY_CASE_PREFIX;
+            const std::string lower = host_map_case(s, false), upper = host_map_case(s, true);
+            // initTokens: the tokens of the phrase AS WRITTEN (prefix: without its last token); they are probed on typed columns only
+            std::vector<std::string> tokens = host_tokenize({pre ? host_strip_last_token(s) : s});
+            int l = new_leaf(kind, f, lower, tokens);
+            DevLeaf& L = P.leaves[l];
+            L.starts_tok = needle_starts_with_token((const uint8_t*)lower.data(), (uint32_t)lower.size());
+            L.ends_tok = needle_ends_with_token((const uint8_t*)lower.data(), (uint32_t)lower.size());
+            typed_needles(L, lower);
+            { DevLeaf U; memset(&U, 0, sizeof U); typed_needles(U, upper); L.typed[VT_ISO8601] = U.typed[VT_ISO8601]; }   // iso8601 columns see the upper-cased phrase
+            L.needle2_off = P.put_bytes(upper.data(), upper.size()); L.needle2_len = (uint32_t)upper.size();
+            std::vector<std::string> up; for (auto& t : tokens) up.push_back(host_map_case(t, true));
+            std::vector<uint64_t> h2; host_token_hashes(up, h2);
+            L.hashes2_off = P.put_hashes(h2); L.nhashes2 = (uint32_t)h2.size();
+            if (pre) L.f64_prefix_gate = L.typed[VT_FLOAT64].ok || lower == "." || lower == "+" || lower == "-" || (!lower.empty() && (lower[0] == 'e' || lower[0] == 'E'));
+            else { L.f64_phrase_gate = L.typed[VT_FLOAT64].ok || lower == "." || lower == "+" || lower == "-"; size_t d = lower.find('.'); L.f64_exact_form = d != std::string::npos && d > 0 && d < lower.size() - 1; }
+            L.str_strategy = STR_ROW;   // case folding happens per value (any_case_match): no literal to scan for
+            P.leaf_tokens[l].clear();   // not among the kinds whose tokens feed the AND / OR pre-pass (filter_and.go:140-166)
+            P.nodes[id].leaf = l; break;
+        }
+        case F_SEQUENCE: case F_CONTAINS_ALL: case F_CONTAINS_ANY: {
+            std::string f = bytes(); uint64_t cnt = varuint();
+            if (cnt > (1u << 22)) throw ProgError("too many values");
+            std::vector<std::string> vals; for (uint64_t k = 0; k < cnt; k++) vals.push_back(bytes());
+            if (kind == F_SEQUENCE) {   // filter_sequence.go:12-67: empty phrases are dropped; no phrase left = matches everything
+                std::vector<std::string> ph; for (auto& v : vals) if (!v.empty()) ph.push_back(v);
+                if (ph.empty()) { P.field_id(f); P.nodes[id].kind = F_NOOP; break; }
+                int l = new_leaf(kind, f, ph[0], host_tokenize(ph));
+                DevLeaf& L = P.leaves[l];
+                typed_needles(L, ph[0]);   // typed columns: a single phrase is matched as an exact value (:213-258)
+                put_list(L, ph);
+                P.nodes[id].leaf = l; break;
+            }
+            // contains_all / contains_any share inValues with in(): string set, typed sets, common tokens + per-value token sets
+            bool has_empty = false; for (auto& v : vals) has_empty |= v.empty();
+            if (kind == F_CONTAINS_ALL && (vals.empty() || (vals.size() == 1 && vals[0].empty()))) { P.field_id(f); P.nodes[id].kind = F_NOOP; break; }   // filter_contains_all.go:92-96
+            if (kind == F_CONTAINS_ANY && has_empty) { P.field_id(f); P.nodes[id].kind = F_NOOP; break; }                                                  // filter_contains_any.go:84-92
+            int l = new_leaf(kind, f, "", {});
+            build_in(P.leaves[l], vals, kind == F_CONTAINS_ANY);
+            DevLeaf& L = P.leaves[l];
+            put_list(L, vals);
+            if (kind == F_CONTAINS_ANY) L.always_none = vals.empty();
+            else {
+                // getTokensHashesAll in_values.go:94-102: the tokens of all values together; aux0 = number of distinct non-empty values (:80-88)
+                std::vector<uint64_t> h; host_token_hashes(host_tokenize(vals), h);
+                L.hashes_off = P.put_hashes(h); L.nhashes = (uint32_t)h.size();
+                std::unordered_set<std::string> uniq; for (auto& v : vals) if (!v.empty()) uniq.insert(v);
+                L.aux0 = uniq.size();
+            }
+            P.leaf_tokens[l].clear();
+            P.nodes[id].leaf = l; break;
+        }
         case F_AND: case F_OR: { uint64_t c = varuint(); if (c > 100000) throw ProgError("too many children"); for (uint64_t k = 0; k < c; k++) { int ch = node(); P.nodes[id].kids.push_back(ch); } break; }
         case F_NOT: { int ch = node(); P.nodes[id].kids.push_back(ch); break; }
         default: throw ProgError("unknown filter kind " + std::to_string(kind));
         }
         return id;
+    }
+    void put_list(DevLeaf& L, const std::vector<std::string>& v) {   // (varuint length, bytes)*: the PhraseList the value predicates walk (vl_anycase.cuh)
+        std::string blob;
+        for (auto& s : v) { uint64_t n = s.size(); while (n >= 0x80) { blob.push_back((char)(n | 0x80)); n >>= 7; } blob.push_back((char)n); blob += s; }
+        L.list_off = P.put_bytes(blob.data(), blob.size()); L.list_len = (uint32_t)blob.size(); L.in_count = (uint32_t)v.size();
     }
     int put_regex(const CompiledRegex& cr) {
         DevRegex R; memset(&R, 0, sizeof R);
@@ -376,7 +449,7 @@ class ProgramBuilder {
         P.regexes.push_back(R); P.host_regexes.push_back(cr);
         return (int)P.regexes.size() - 1;
     }
-    void build_in(DevLeaf& L, const std::vector<std::string>& vals) {
+    void build_in(DevLeaf& L, const std::vector<std::string>& vals, bool keep_all_sets = false) {
         // string set (deduplicated; order irrelevant)
         std::vector<std::string> uniq; { std::unordered_set<std::string> seen; for (auto& v : vals) if (seen.insert(v).second) uniq.push_back(v); }
         L.in_count = (uint32_t)uniq.size();
@@ -417,12 +490,13 @@ class ProgramBuilder {
         L.in_nsets = (uint32_t)sets.size();
         L.in_skip_sets = sets.size() > 1000;   // maxTokenSetsToInit
         std::vector<uint32_t> desc;
-        if (!L.in_skip_sets) for (auto& s : sets) { std::vector<uint64_t> h; host_token_hashes(s, h); desc.push_back(P.put_hashes(h)); desc.push_back((uint32_t)h.size()); }
+        // (contains_any probes every value's own tokens on string columns whatever their number, filter_contains_any.go:170-189)
+        if (!L.in_skip_sets || keep_all_sets) for (auto& s : sets) { std::vector<uint64_t> h; host_token_hashes(s, h); desc.push_back(P.put_hashes(h)); desc.push_back((uint32_t)h.size()); }
         L.in_sets_off = (uint32_t)P.u32s.size(); P.u32s.insert(P.u32s.end(), desc.begin(), desc.end());
         P.leaf_tokens.back() = common;
     }
     // ---- AND / OR bloom pre-pass token merging -------------------------------------------------------------------------
-    bool leaf_has_tokens(int kind) const { return kind == F_PHRASE || kind == F_PREFIX || kind == F_EXACT || kind == F_REGEXP || kind == F_EXACT_PREFIX; }
+    bool leaf_has_tokens(int kind) const { return kind == F_PHRASE || kind == F_PREFIX || kind == F_EXACT || kind == F_REGEXP || kind == F_EXACT_PREFIX || kind == F_SEQUENCE; }
     const std::vector<FT>& by_field(int id) {
         if (node_ft_done_[id]) return node_ft_[id];
         node_ft_done_[id] = true;

@@ -6,7 +6,9 @@ namespace vl {
 
 enum { VT_STRING = 1, VT_DICT = 2, VT_UINT8 = 3, VT_UINT16 = 4, VT_UINT32 = 5, VT_UINT64 = 6, VT_FLOAT64 = 7, VT_IPV4 = 8, VT_ISO8601 = 9, VT_INT64 = 10, VT_MAX = 11 };
 enum { F_NOOP = 0, F_PHRASE, F_PREFIX, F_EXACT, F_IN, F_REGEXP, F_AND, F_OR, F_NOT,
-       F_EXACT_PREFIX = 9, F_LEN_RANGE = 10, F_STRING_RANGE = 11, F_IPV4_RANGE = 12, F_VALUE_TYPE = 13 };
+       F_EXACT_PREFIX = 9, F_LEN_RANGE = 10, F_STRING_RANGE = 11, F_IPV4_RANGE = 12, F_VALUE_TYPE = 13,
+       F_ANY_CASE_PHRASE = 14, F_ANY_CASE_PREFIX = 15, F_SEQUENCE = 16, F_CONTAINS_ALL = 17, F_CONTAINS_ANY = 18,
+       F_EQ_FIELD = 19, F_LE_FIELD = 20, F_RANGE = 21, F_TIME = 22 };
 enum { VTYPE_CONST = 0, VTYPE_NO_SUCH = 255 };   // F_VALUE_TYPE: DevLeaf.aux0 = VT_* code of the wanted type, or one of these
 enum { COL_MISSING = 0, COL_CONST = 1, COL_VALUES = 2 };
 
@@ -77,7 +79,11 @@ struct DevLeaf {
     uint32_t scan_needle_off, scan_needle_len;   // blob: the literal the scan searches for
     // exact_prefix / len_range / string_range / ipv4_range / value_type
     uint64_t aux0, aux1;               // len_range: minLen, maxLen; ipv4_range: minValue, maxValue; value_type: wanted type code
-    uint32_t needle2_off, needle2_len; // string_range: maxValue (needle = minValue)
+    uint32_t needle2_off, needle2_len; // string_range: maxValue (needle = minValue).  i(...): the UPPER-cased phrase (needle = the lower-cased one)
+    uint32_t hashes2_off, nhashes2;    // i(...): probe hashes of the upper-cased tokens (iso8601 columns, filter_any_case_phrase.go:119-126)
+    uint32_t list_off, list_len;       // seq() / contains_all() / contains_any(): the phrases as (varuint length, bytes)* in the blob; in_count = how many
+    int32_t field2;                    // eq_field / le_field: the other field (index into the program's field table)
+    uint32_t pad3;
 };
 // DevLeaf.gates
 enum { GATE_DIGIT_PREFIX = 1,          // exact_prefix: !(prefix < "0" || prefix > "9")
@@ -95,7 +101,10 @@ struct DevPrepass {                    // one fieldTokens entry of an AND / OR n
 
 enum { STR_ROW = 0, STR_SCAN = 1, STR_ALL = 2 };
 // per (block, leaf) decision of the header dispatch
-enum { ACT_NONE = 0, ACT_ALL = 1, ACT_DICT = 2, ACT_SCAN = 3, ACT_FIXED_EQ = 4, ACT_FIXED_IN = 5, ACT_ROW = 6 };
+enum { ACT_NONE = 0, ACT_ALL = 1, ACT_DICT = 2, ACT_SCAN = 3, ACT_FIXED_EQ = 4, ACT_FIXED_IN = 5,
+       ACT_ROW = 6,         // per-row matcher: the leaf's string predicate on the value (typed values through their text)
+       ACT_ROW_EQ = 7,      // per-row matcher: binary equality with the payload (typed column whose layout is not the fixed-width one)
+       ACT_ROW_IN = 8 };    // per-row matcher: membership in the leaf's typed value set
 // scan verifier modes of the row-agnostic substring kernel
 enum { SCAN_PHRASE = 0, SCAN_PREFIX = 1, SCAN_CONTAINS = 2, SCAN_RX_DOTPLUS = 3, SCAN_RX_SUFFIX = 4, SCAN_RX_TAIL = 5 };
 

@@ -24,6 +24,7 @@ _LIB = None
 
 F_NOOP, F_PHRASE, F_PREFIX, F_EXACT, F_IN, F_REGEXP, F_AND, F_OR, F_NOT = range(9)
 F_EXACT_PREFIX, F_LEN_RANGE, F_STRING_RANGE, F_IPV4_RANGE, F_VALUE_TYPE = 9, 10, 11, 12, 13
+F_ANY_CASE_PHRASE, F_ANY_CASE_PREFIX, F_SEQUENCE, F_CONTAINS_ALL, F_CONTAINS_ANY, F_EQ_FIELD, F_LE_FIELD, F_RANGE, F_TIME = 14, 15, 16, 17, 18, 19, 20, 21, 22
 VT_STRING, VT_DICT, VT_UINT8, VT_UINT16, VT_UINT32, VT_UINT64, VT_FLOAT64, VT_IPV4, VT_ISO8601, VT_INT64 = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
 COL_CONST, COL_VALUES = 1, 2
 STAGE_ONDISK, STAGE_DECODED = 0, 1
@@ -230,6 +231,29 @@ class Filter:
     @staticmethod
     def value_type(field, type_name):      # &filterValueType{fieldName, valueType}
         return Filter(bytes([F_VALUE_TYPE]) + _bytes(field) + _bytes(type_name), "%r:value_type(%r)" % (field, type_name))
+
+    @staticmethod
+    def any_case_phrase(field, phrase):    # &filterAnyCasePhrase{fieldName, phrase}        `f:i(phrase)`
+        return Filter(bytes([F_ANY_CASE_PHRASE]) + _bytes(field) + _bytes(phrase), "%r:i(%r)" % (field, phrase))
+
+    @staticmethod
+    def any_case_prefix(field, prefix):    # &filterAnyCasePrefix{fieldName, prefix}        `f:i(prefix*)`
+        return Filter(bytes([F_ANY_CASE_PREFIX]) + _bytes(field) + _bytes(prefix), "%r:i(%r*)" % (field, prefix))
+
+    @staticmethod
+    def sequence(field, phrases):          # &filterSequence{fieldName, phrases}            `f:seq(a, b, ...)`
+        phrases = list(phrases)
+        return Filter(bytes([F_SEQUENCE]) + _bytes(field) + _varuint(len(phrases)) + b"".join(_bytes(v) for v in phrases), "%r:seq(%r)" % (field, phrases))
+
+    @staticmethod
+    def contains_all(field, values):       # &filterContainsAll{fieldName, values}          `f:contains_all(a, b, ...)`
+        values = list(values)
+        return Filter(bytes([F_CONTAINS_ALL]) + _bytes(field) + _varuint(len(values)) + b"".join(_bytes(v) for v in values), "%r:contains_all(%r)" % (field, values))
+
+    @staticmethod
+    def contains_any(field, values):       # &filterContainsAny{fieldName, values}          `f:contains_any(a, b, ...)`
+        values = list(values)
+        return Filter(bytes([F_CONTAINS_ANY]) + _bytes(field) + _varuint(len(values)) + b"".join(_bytes(v) for v in values), "%r:contains_any(%r)" % (field, values))
 
     @staticmethod
     def and_(filters):
