@@ -69,12 +69,13 @@ def test_program_tokens_match_oracle(oracle):
     assert seen > 250
 
 
-PRODUCT_NEXT_KINDS = ("exact_prefix", "len_range", "string_range", "ipv4_range", "value_type")
+PRODUCT_NEXT_KINDS = ("exact_prefix", "len_range", "string_range", "ipv4_range", "value_type", "any_case_phrase", "any_case_prefix", "sequence", "contains_all", "contains_any")
 
 
 def test_next_filter_kinds_compile_and_tokens(oracle):
-    """The filters of SURVEY §8(f) rank 3 that libvlscan compiles so far: every reference-table filter builds; exact_prefix tokens
-    (getTokensSkipLast) equal the oracle's; the kinds not built yet are rejected, not guessed."""
+    """The filters of SURVEY §8(f) rank 3 that libvlscan compiles: every reference-table filter builds; the tokens of the kinds that feed the
+    AND / OR bloom pre-pass (exact_prefix: getTokensSkipLast, seq(): the tokens of all phrases) equal the oracle's; the kinds not built yet are
+    rejected, not guessed."""
     seen = {}
     for c in load_filter_cases("filter_cases_next.json"):
         spec = c["filter"]
@@ -83,15 +84,26 @@ def test_next_filter_kinds_compile_and_tokens(oracle):
             continue
         p = vs.Program(build_filter(vs.Filter, spec))
         assert p.fields() == [bytes.fromhex(spec["field"]) or b"_msg"]
-        if k == "exact_prefix":
-            assert p.leaf_tokens(0) == build_filter(oracle.Filter, spec).tokens(), spec
+        if k in ("exact_prefix", "sequence"):
+            want = build_filter(oracle.Filter, spec).tokens()
+            if k == "sequence" and not [v for v in spec["values"] if v]:
+                want = []   # a sequence without phrases compiles to a no-op node: there is no leaf to ask
+            try:
+                got = p.leaf_tokens(0)
+            except IndexError:
+                got = []
+            assert got == want, spec
         else:
-            assert p.leaf_tokens(0) == []
+            try:
+                assert p.leaf_tokens(0) == []
+            except IndexError:
+                pass        # compiled to a no-op (contains_all of nothing, contains_any with an empty value)
         seen[k] = seen.get(k, 0) + 1
-    assert seen == {"exact_prefix": 62, "len_range": 30, "string_range": 48, "ipv4_range": 24, "value_type": 35}
+    assert seen == {"exact_prefix": 62, "len_range": 30, "string_range": 48, "ipv4_range": 24, "value_type": 35, "any_case_phrase": 107, "any_case_prefix": 114, "sequence": 103,
+                    "contains_all": 104, "contains_any": 88}
     with pytest.raises(vs.VlscanError):
         vs.Program(vs.Filter(bytes([vs.F_IPV4_RANGE, 1, ord("f")]) + bytes([0x80, 0x80, 0x80, 0x80, 0x10, 0]), "ipv4 bound > 32 bits"))
-    for kind in (14, 15, 16, 17, 18, 19):
+    for kind in (19, 20, 21, 22, 23):
         with pytest.raises(vs.VlscanError):
             vs.Program(vs.Filter(bytes([kind, 1, ord("f"), 1, ord("x")]), "kind not built yet"))
     # AND: exact_prefix contributes its tokens to the per-field bloom pre-pass (filter_and.go:141-143)

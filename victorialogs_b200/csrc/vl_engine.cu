@@ -154,8 +154,11 @@ static int host_threads() {
     return (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
 }
 
+// need_bloom (may be NULL = all): per batch field, whether the program that will scan this batch ever probes that field's bloom filters.  A filter
+// nobody probes stays on the host (the reference reads a column's bloom filter lazily, only when a filter asks for it: getBloomFilterForColumn,
+// block_search.go:411-439); the column is staged with an empty filter, which no kernel touches.
 static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const size_t* field_name_lens, uint32_t nfields, const vlscan_block* blocks,
-                      uint64_t nblocks, vlscan_batch* out, vlscan_stats* stats) {
+                      uint64_t nblocks, vlscan_batch* out, vlscan_stats* stats, const std::vector<char>* need_bloom = nullptr) {
     VL_CUDA(cudaSetDevice(ctx->device));
     if (nblocks > 0xFFFFFFF0ull) throw BadInput("too many blocks in one batch");
     const bool dbg = getenv("VLSCAN_DEBUG_TIMING") != nullptr;
@@ -314,7 +317,8 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
                 d.data_const = (blk.rows >= 2 && lt >= 4 && data_len == d.lens_const) ? 1 : 0;
             } else throw BadInput("unknown values stage");
             if (c.bloom_len % 8) throw BadInput("cannot unmarshal bloomFilter from src with size not multiple by 8");   // bloomfilter.go:59-61
-            d.bloom_words = (uint32_t)(c.bloom_len / 8); d.bloom_off = add_piece(c.bloom, c.bloom_len);
+            if (need_bloom && !(*need_bloom)[c.field]) { d.bloom_words = 0; d.bloom_off = add_piece(c.bloom, 0); }
+            else { d.bloom_words = (uint32_t)(c.bloom_len / 8); d.bloom_off = add_piece(c.bloom, c.bloom_len); }
             if (c.value_type == VT_DICT) {
                 if (c.dict_len > 8) throw BadInput("valuesDict may contain max 8 items");
                 d.dict_len = c.dict_len;
@@ -1058,7 +1062,16 @@ int vlscan_scan_batch(vlscan_ctx* ctx, const vlscan_program* prog, const char* c
     ctx->recycle = nullptr;
     b->field_names.clear(); b->slot_vt_mask.clear();
     uint64_t launches0 = ctx->launches;
-    int rc = guarded(ctx, [&] { do_upload(ctx, field_names, field_name_lens, nfields, blocks, nblocks, b, stats); });
+    // which fields' bloom filters the program can ever probe: leaves with token hashes (or in() / contains_any() token sets) and the per-field
+    // tokens of the AND / OR pre-passes
+    std::vector<char> need_bloom(nfields, 0);
+    {
+        const Program& P = prog->p;
+        auto mark = [&](int field) { for (uint32_t s = 0; s < nfields; s++) if (std::string(field_names[s], field_name_lens[s]) == P.fields[field]) need_bloom[s] = 1; };
+        for (const DevLeaf& L : P.leaves) if (L.nhashes || L.nhashes2 || L.in_nsets) mark(L.field);
+        for (const DevPrepass& pp : P.prepass) if (pp.nhashes) mark(pp.field);
+    }
+    int rc = guarded(ctx, [&] { do_upload(ctx, field_names, field_name_lens, nfields, blocks, nblocks, b, stats, &need_bloom); });
     if (rc) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->stream); }   // nothing may still read the caller's buffers
     if (!rc) rc = vlscan_scan_resident(ctx, prog, b, nullptr);
     if (!rc) rc = vlscan_fetch_results(ctx, out_bitmap_words, out_match_counts, stats);

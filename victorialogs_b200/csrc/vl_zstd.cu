@@ -22,6 +22,12 @@ using namespace zs;
 struct ZstdDev {
     DevBuf frames, blocks, bstate, huf_tab, fse_tab, huf_state, fse_state, predef, lits, seqs, frame_err, status, lists;
     bool predef_ready = false;
+    cudaStream_t xstream = nullptr;          // second stream: k_seq_resolve + k_execute of group g run beside the entropy kernels of group g + 1
+    std::vector<cudaEvent_t> events;         // grow-only pool (two per launch group: entropy done, execute done)
+    cudaEvent_t event(size_t i) {
+        while (events.size() <= i) { cudaEvent_t e; VL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); events.push_back(e); }
+        return events[i];
+    }
     void* hpin = nullptr; size_t hpin_cap = 0;   // page-locked staging of the descriptor tables (read by k_pull_words over PCIe)
     void* ensure_hpin(size_t n) {
         if (n <= hpin_cap) return hpin;
@@ -33,6 +39,10 @@ struct ZstdDev {
     void release() {
         DevBuf* all[] = {&frames, &blocks, &bstate, &huf_tab, &fse_tab, &huf_state, &fse_state, &predef, &lits, &seqs, &frame_err, &status, &lists};
         for (DevBuf* b : all) b->release();
+        for (cudaEvent_t e : events) cudaEventDestroy(e);
+        events.clear();
+        if (xstream) cudaStreamDestroy(xstream);
+        xstream = nullptr;
         if (hpin) cudaFreeHost(hpin);
         hpin = nullptr; hpin_cap = 0;
     }
@@ -111,7 +121,11 @@ void ZstdJob::run(vlscan_ctx* ctx, const uint8_t* zsrc, uint8_t* arena) {
     D.frame_err.ensure(J.frames.size() * 4); D.status.ensure(16); D.lists.ensure(lists.size() * 4 + 16);
     D.huf_tab.ensure(std::max<size_t>((size_t)J.max_huf * Z_HUF_TABLE * 2, 16)); D.huf_state.ensure(std::max<size_t>((size_t)J.max_huf * sizeof(ZSlotState), 16));
     D.fse_tab.ensure(std::max<size_t>((size_t)J.max_fse * Z_FSE_SLOT_BYTES, 16)); D.fse_state.ensure(std::max<size_t>((size_t)J.max_fse * sizeof(ZSlotState), 16));
-    D.lits.ensure(J.max_lits + 64); D.seqs.ensure(std::max<size_t>(J.max_seqs * 16, 16));
+    // literals and sequence records are produced by the entropy kernels of a group and consumed by its execute kernel on the other stream:
+    // two copies, alternating by group, so that the entropy kernels of group g + 1 can run while group g is being executed
+    const size_t lits_stride = (J.max_lits + 64 + 255) / 256 * 256, seqs_stride = std::max<size_t>(J.max_seqs, 1);
+    D.lits.ensure(2 * lits_stride); D.seqs.ensure(2 * seqs_stride * 16);
+    if (!D.xstream) VL_CUDA(cudaStreamCreateWithFlags(&D.xstream, cudaStreamNonBlocking));
     if (!D.predef_ready) {
         D.predef.ensure(Z_FSE_SLOT_BYTES);
         k_zstd_predef<<<1, 32, 0, st>>>(D.predef.as<uint8_t>());
@@ -149,8 +163,13 @@ void ZstdJob::run(vlscan_ctx* ctx, const uint8_t* zsrc, uint8_t* arena) {
     static const char* phase_name[6] = {"huf_build", "huf_decode", "fse_build", "seq_decode", "seq_resolve", "execute"};
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> marks;
     int phase = 0;
-    auto begin = [&](int p) { phase = p; if (dbg) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); marks.push_back({p, {a, b}}); } };
-    auto launched = [&] { ctx->launches++; VL_CUDA(cudaGetLastError()); if (dbg) cudaEventRecord(marks.back().second.second, st); };
+    cudaStream_t xs = D.xstream;
+    cudaStream_t cur_stream = st;
+    auto begin = [&](int p) { phase = p; if (dbg) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, cur_stream); marks.push_back({p, {a, b}}); } };
+    auto launched = [&] { ctx->launches++; VL_CUDA(cudaGetLastError()); if (dbg) cudaEventRecord(marks.back().second.second, cur_stream); };
+    // everything enqueued so far on the ctx stream (tables, memsets) precedes the first execute
+    VL_CUDA(cudaEventRecord(D.event(0), st)); VL_CUDA(cudaStreamWaitEvent(xs, D.event(0), 0));
+    size_t gi = 0;
     for (const Group& g : J.groups) {
         uint32_t nh = g.huf_hi - g.huf_lo, nl = g.lit_hi - g.lit_lo, ns = g.seq_hi - g.seq_lo, nf = g.frame_hi - g.frame_lo;
         if (J.group_hook) {
@@ -158,17 +177,29 @@ void ZstdJob::run(vlscan_ctx* ctx, const uint8_t* zsrc, uint8_t* arena) {
             for (uint32_t i = J.frames[g.frame_lo].blk_lo; i < J.frames[g.frame_hi - 1].blk_hi; i++) need = std::max<uint64_t>(need, J.blocks[i].src + (J.blocks[i].type == ZB_RLE ? 1 : J.blocks[i].size));
             J.group_hook(need);
         }
-        if (nh) { begin(0); k_huf_build<<<cdiv_u(nh, 4), 128, 0, st>>>(V, L + g.huf_lo, nh); launched(); }
-        if (nl) { begin(1); k_huf_decode<<<cdiv_u(nl, Z_HUF_CTA_BLOCKS), Z_HUF_CTA_BLOCKS * 4, Z_HUF_CTA_BLOCKS * (Z_HUF_TABLE * 2 + 4 * Z_LINEBUF), st>>>(V, L + g.lit_lo, nl); launched(); }
+        ZView W = V;
+        W.lits = V.lits + (gi & 1) * lits_stride; W.seqs = V.seqs + (gi & 1) * seqs_stride;
+        cudaEvent_t ev_entropy = D.event(1 + 2 * gi), ev_exec = D.event(2 + 2 * gi);
+        cur_stream = st;
+        if (gi >= 2) VL_CUDA(cudaStreamWaitEvent(st, D.event(2 + 2 * (gi - 2)), 0));   // the scratch copy this group writes was read by group gi - 2
+        if (nh) { begin(0); k_huf_build<<<cdiv_u(nh, 4), 128, 0, st>>>(W, L + g.huf_lo, nh); launched(); }
+        if (nl) { begin(1); k_huf_decode<<<cdiv_u(nl, Z_HUF_CTA_BLOCKS), Z_HUF_CTA_BLOCKS * 4, Z_HUF_CTA_BLOCKS * (Z_HUF_TABLE * 2 + 4 * Z_LINEBUF), st>>>(W, L + g.lit_lo, nl); launched(); }
         if (ns) {
-            begin(2); k_fse_build<<<cdiv_u(ns, 64), 64, 0, st>>>(V, L + g.seq_lo, ns); launched();
-            begin(3); k_seq_decode<<<cdiv_u(ns, Z_SEQ_CTA_LANES), 64, Z_SEQ_CTA_LANES * (Z_FSE_SLOT_BYTES + Z_LINEBUF), st>>>(V, L + g.seq_lo, ns); launched();
+            begin(2); k_fse_build<<<cdiv_u(ns, 64), 64, 0, st>>>(W, L + g.seq_lo, ns); launched();
+            begin(3); k_seq_decode<<<cdiv_u(ns, Z_SEQ_CTA_LANES), 64, Z_SEQ_CTA_LANES * (Z_FSE_SLOT_BYTES + Z_LINEBUF), st>>>(W, L + g.seq_lo, ns); launched();
         }
-        begin(4); k_seq_resolve<<<cdiv_u(nf, 64), 64, 0, st>>>(V, g.frame_lo, nf); launched();
-        begin(5); k_execute<<<cdiv_u((uint64_t)nf * 32, 128), 128, 0, st>>>(V, L + g.ord_lo, nf); launched();
+        VL_CUDA(cudaEventRecord(ev_entropy, st));
+        VL_CUDA(cudaStreamWaitEvent(xs, ev_entropy, 0));
+        cur_stream = xs;
+        begin(4); k_seq_resolve<<<cdiv_u(nf, 64), 64, 0, xs>>>(W, g.frame_lo, nf); launched();
+        begin(5); k_execute<<<cdiv_u((uint64_t)nf * 32, Z_EXEC_WARPS * 32), Z_EXEC_WARPS * 32, 0, xs>>>(W, L + g.ord_lo, nf); launched();
+        VL_CUDA(cudaEventRecord(ev_exec, xs));
+        gi++;
     }
+    if (gi) VL_CUDA(cudaStreamWaitEvent(st, D.event(2 + 2 * (gi - 1)), 0));   // the ctx stream continues behind the last execute
+    cur_stream = st;
     if (dbg) {
-        VL_CUDA(cudaStreamSynchronize(st));
+        VL_CUDA(cudaStreamSynchronize(xs)); VL_CUDA(cudaStreamSynchronize(st));
         float tot[6] = {0, 0, 0, 0, 0, 0};
         for (auto& mk : marks) { float ms = 0; cudaEventElapsedTime(&ms, mk.second.first, mk.second.second); tot[mk.first] += ms; cudaEventDestroy(mk.second.first); cudaEventDestroy(mk.second.second); }
         fprintf(stderr, "[vlscan zstd] %zu groups:", J.groups.size());

@@ -566,14 +566,20 @@ static __global__ void __launch_bounds__(64) k_seq_resolve(ZView V, uint32_t fra
 }
 
 // ---- sequence execution; one warp per frame (RFC 8878 3.1.1.4) -------------------------------------------------------------------------------
-// Per group of 32 sequences: all literal runs go out first (they depend on nothing), then the matches.  A match must wait only for
-// the matches whose destination its source overlaps; `dep` is the index of the last such match inside the group, and a run of
-// consecutive matches with dep < (first match of the run) is copied as one flat, warp-wide copy.  The source of a match is mostly a
-// few hundred bytes back - data this warp stored moments ago - so every byte is mirrored in a per-warp ring in shared memory and
-// read from there when it is recent enough: the load that every run has to wait for then costs ~30 cycles instead of an L2 / HBM trip.
-static const uint32_t Z_RING = 4096;
-static __global__ void __launch_bounds__(128) k_execute(ZView V, const uint32_t* __restrict__ order, uint32_t nframes) {
-    __shared__ uint8_t s_ring[4][Z_RING];
+// The output of a frame is produced in groups of 32 sequences, one sequence per lane, inside a per-warp ring in shared memory that is indexed by
+// the low bits of the byte's address in the arena; a finished group is flushed to HBM with aligned 16-byte stores.  Log data compresses into
+// short sequences (a handful of literal bytes, a 4..40 byte match), so in the common case every lane simply copies its own literal run and its own
+// match - byte loops of a few iterations, all lanes at once - instead of the warp spreading each copy over its lanes (measured on the C2 batch:
+// 42 warp instructions per sequence, 46 % of the stall samples on the store behind the one-byte load of a match source that was not in the ring).
+// A match must wait only for the matches whose destination its source overlaps: `dep` is the index of the last such match inside the group;
+// the matches whose dep lies in front of the current position are copied together.  Sources within the last Z_RING bytes come from the ring,
+// older ones from HBM (8-byte loads; they lie in front of the group, hence flushed).  Groups with a long literal run or a long match take the
+// cooperative path instead: every copy is spread over the warp and goes to HBM directly (mirrored in the ring while it fits).
+static const uint32_t Z_RING = 8192;
+static const uint32_t Z_EXEC_WARPS = 4;
+static const uint32_t Z_FAST_LL = 32, Z_FAST_ML = 64;   // per-lane copy limits of the fast path: a group's output then stays below 3 KB
+static __global__ void __launch_bounds__(Z_EXEC_WARPS * 32) k_execute(ZView V, const uint32_t* __restrict__ order, uint32_t nframes) {
+    __shared__ __align__(16) uint8_t s_ring[Z_EXEC_WARPS][Z_RING];
     const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (wid >= nframes) return;
     const uint32_t f = order[wid];
@@ -581,13 +587,15 @@ static __global__ void __launch_bounds__(128) k_execute(ZView V, const uint32_t*
     const ZFrame& F = V.frames[f];
     uint8_t* dst = V.arena + F.dst;
     uint8_t* ring = s_ring[threadIdx.x >> 5];
+    const uint32_t abase = (uint32_t)(uintptr_t)dst;   // ring slot of frame position p = (address of dst + p) & (Z_RING - 1): same 16-byte alignment as in the arena
+#define VL_RING(p) ring[(abase + (p)) & (Z_RING - 1)]
     uint32_t ring_lo = 0;   // frame position from which the ring content can be trusted
     for (uint32_t bi = F.blk_lo; bi < F.blk_hi; bi++) {
         const ZBlock& B = V.blocks[bi];
         const uint32_t blk_base = V.bstate[bi].out_base;   // position of the block inside the frame
         const uint8_t* p = V.src + B.src;
-        if (B.type == ZB_RAW) { for (uint32_t k = lane; k < B.size; k += 32) { uint8_t v = p[k]; dst[blk_base + k] = v; ring[(blk_base + k) & (Z_RING - 1)] = v; } __syncwarp(); continue; }
-        if (B.type == ZB_RLE) { uint8_t v = p[0]; for (uint32_t k = lane; k < B.size; k += 32) { dst[blk_base + k] = v; ring[(blk_base + k) & (Z_RING - 1)] = v; } __syncwarp(); continue; }
+        if (B.type == ZB_RAW) { for (uint32_t k = lane; k < B.size; k += 32) { uint8_t v = p[k]; dst[blk_base + k] = v; VL_RING(blk_base + k) = v; } if (B.size >= Z_RING) ring_lo = blk_base + B.size - Z_RING; __syncwarp(); continue; }
+        if (B.type == ZB_RLE) { uint8_t v = p[0]; for (uint32_t k = lane; k < B.size; k += 32) { dst[blk_base + k] = v; VL_RING(blk_base + k) = v; } __syncwarp(); continue; }
         const uint8_t* lit = B.lit_type == ZL_RAW ? p + B.lit_hdr : V.lits + B.lit_off;
         const bool lit_rle = B.lit_type == ZL_RLE;
         const uint8_t rle_byte = lit_rle ? p[B.lit_hdr] : 0;
@@ -602,22 +610,8 @@ static __global__ void __launch_bounds__(128) k_execute(ZView V, const uint32_t*
             const uint32_t o_start = io - q.x - q.y;        // output offset of this lane's literals inside the group
             const uint32_t T = __shfl_sync(0xffffffffu, il, 31), O = __shfl_sync(0xffffffffu, io, 31);
             const uint32_t gend = out_run + O;              // frame position one past the group
-            // Inside a group stores are not in position order (all literals first), so two positions of one group must not share a ring
-            // slot: a group spanning Z_RING bytes or more reads from HBM only and leaves the ring untrusted below its end.
-            const bool ring_ok = O < Z_RING;
-            // literal runs of the whole group: byte k belongs to the sequence j with il[j-1] <= k < il[j]
-            for (uint32_t k0 = 0; k0 < T; k0 += 32) {
-                uint32_t k = k0 + lane;
-                uint32_t lo = 0;   // smallest j with il[j] > k, by 5 shuffle probes
-#pragma unroll
-                for (int s = 16; s; s >>= 1) { uint32_t v = __shfl_sync(0xffffffffu, il, (lo + s - 1) & 31); if (v <= k) lo += s; }
-                uint32_t js = __shfl_sync(0xffffffffu, lit_start, lo & 31), jo = __shfl_sync(0xffffffffu, o_start, lo & 31);
-                if (k < T) { uint8_t v = lit_rle ? rle_byte : lit[lit_run + k]; uint32_t at = out_run + jo + (k - js); dst[at] = v; ring[at & (Z_RING - 1)] = v; }
-            }
-            __syncwarp();
             const uint32_t cnt = min(32u, B.nseq - g);
             const uint32_t ml = q.y, off = q.z, amd = out_run + o_start + q.x;   // amd: frame position of the match destination
-            const uint32_t im = io - il;                                         // inclusive prefix sum of the match lengths
             if (__any_sync(0xffffffffu, lane < cnt && (off == 0 || off > amd))) { if (lane == 0) zfail(V, f, ZERR_OFFSET); return; }
             // dep: the last match of the group whose destination [amd_i, amd_i + ml_i) overlaps this match's source [s, e); destinations are
             // disjoint and ascending, so that is the last one starting below e, if it reaches beyond s
@@ -631,38 +625,109 @@ static __global__ void __launch_bounds__(128) k_execute(ZView V, const uint32_t*
                 const uint32_t ca = __shfl_sync(0xffffffffu, amd, ci), cm = __shfl_sync(0xffffffffu, ml, ci);
                 if (lo > 0 && ca + cm > s_src) dep = (int)lo - 1;
             }
-            uint32_t cur = 0;
-            while (cur < cnt) {
-                const uint32_t ready = __ballot_sync(0xffffffffu, lane >= cur && lane < cnt && dep < (int)cur) >> cur;   // bit 0 = match `cur`, always set
-                const uint32_t n = ready == 0xffffffffu ? 32u : max((uint32_t)__ffs((int)~ready) - 1u, 1u);
-                const uint32_t hi = cur + n;
-                const uint32_t im_lo = cur ? __shfl_sync(0xffffffffu, im, cur - 1) : 0u, M = __shfl_sync(0xffffffffu, im, hi - 1) - im_lo;
-                for (uint32_t k0 = 0; k0 < M; k0 += 32) {
-                    const uint32_t k = im_lo + k0 + lane;   // position in the group's concatenated match bytes
-                    uint32_t lo = 0;                         // smallest j with im[j] > k
-#pragma unroll
-                    for (int s = 16; s; s >>= 1) { uint32_t v = __shfl_sync(0xffffffffu, im, (lo + s - 1) & 31); if (v <= k) lo += s; }
-                    const uint32_t jm = __shfl_sync(0xffffffffu, ml, lo & 31), jo = __shfl_sync(0xffffffffu, off, lo & 31);
-                    const uint32_t jd = __shfl_sync(0xffffffffu, amd, lo & 31), je = __shfl_sync(0xffffffffu, im, lo & 31);
-                    if (k0 + lane < M) {
-                        const uint32_t kk = k - (je - jm);   // byte index inside match `lo`
-                        const uint32_t sa = jd - jo + (jo >= jm ? kk : kk % jo);   // frame position of the source byte
-                        // the ring holds position q as long as nothing was stored at q + Z_RING; stores so far reach up to gend
-                        const uint8_t v = (ring_ok && sa >= ring_lo && gend - sa < Z_RING) ? ring[sa & (Z_RING - 1)] : dst[sa];
-                        dst[jd + kk] = v; ring[(jd + kk) & (Z_RING - 1)] = v;
+            const bool fast = !__any_sync(0xffffffffu, q.x > Z_FAST_LL || q.y > Z_FAST_ML);
+            if (fast) {
+                // ---- every lane copies its own literal run and its own match into the ring ----
+                {
+                    const uint32_t at = out_run + o_start;
+                    if (lit_rle) { for (uint32_t k = 0; k < q.x; k++) VL_RING(at + k) = rle_byte; }
+                    else {
+                        const uint8_t* ls = lit + lit_run + lit_start;
+                        for (uint32_t k = 0; k < q.x; k += 8) {
+                            const uint64_t w = ldu64(ls + k);   // up to 15 bytes past the run: scratch and staging buffers keep that much slack
+                            const uint32_t m = min(8u, q.x - k);
+                            for (uint32_t t = 0; t < m; t++) VL_RING(at + k + t) = (uint8_t)(w >> (8 * t));
+                        }
                     }
                 }
                 __syncwarp();
-                cur = hi;
+                uint32_t cur = 0;
+                while (cur < cnt) {
+                    const uint32_t ready = __ballot_sync(0xffffffffu, lane >= cur && lane < cnt && dep < (int)cur) >> cur;   // bit 0 = match `cur`, always set
+                    const uint32_t n = ready == 0xffffffffu ? 32u : max((uint32_t)__ffs((int)~ready) - 1u, 1u);
+                    const uint32_t hi = cur + n;
+                    if (lane >= cur && lane < hi && ml) {
+                        // the ring holds position q as long as nothing was stored at q + Z_RING; stores so far stay below gend
+                        if (s_src >= ring_lo && gend - s_src <= Z_RING) {
+                            for (uint32_t k = 0; k < ml; k++) VL_RING(amd + k) = VL_RING(s_src + k);   // in order: an overlapping match repeats its own output
+                        } else if (gend - s_src > Z_RING || s_src + ml <= ring_lo) {
+                            // older than the ring (or than what the ring can be trusted for): more than 5 KB in front of the group's end, so
+                            // entirely in front of the group (flushed) and never overlapping its destination
+                            for (uint32_t k = 0; k < ml; k += 8) {
+                                const uint64_t w = ldu64(dst + s_src + k);
+                                const uint32_t m = min(8u, ml - k);
+                                for (uint32_t t = 0; t < m; t++) VL_RING(amd + k + t) = (uint8_t)(w >> (8 * t));
+                            }
+                        } else {
+                            // starts in front of the trusted part of the ring and runs into it: byte by byte (positions below ring_lo were
+                            // written to HBM directly by the cooperative path)
+                            for (uint32_t k = 0; k < ml; k++) { const uint32_t sp = s_src + k; VL_RING(amd + k) = sp >= ring_lo ? VL_RING(sp) : dst[sp]; }
+                        }
+                    }
+                    __syncwarp();
+                    cur = hi;
+                }
+                // ---- flush [out_run, gend): bytes up to the first 16-byte boundary of the arena, aligned 16-byte chunks, the bytes behind the last one ----
+                {
+                    const uintptr_t a0 = (uintptr_t)dst + out_run, a1 = (uintptr_t)dst + gend;
+                    const uintptr_t c0 = (a0 + 15) & ~(uintptr_t)15, c1 = a1 & ~(uintptr_t)15;
+                    if (c0 <= c1) {
+                        if (lane < c0 - a0) *(uint8_t*)(a0 + lane) = ring[(a0 + lane) & (Z_RING - 1)];
+                        for (uintptr_t c = c0 + 16 * lane; c < c1; c += 512) *(uint4*)c = *(const uint4*)(ring + (c & (Z_RING - 1)));
+                        if (lane < a1 - c1) *(uint8_t*)(c1 + lane) = ring[(c1 + lane) & (Z_RING - 1)];
+                    } else if (lane < O) *(uint8_t*)(a0 + lane) = ring[(a0 + lane) & (Z_RING - 1)];   // the group lies inside one 16-byte chunk
+                }
+                __syncwarp();
+            } else {
+                // ---- cooperative path: every copy spread over the warp, straight to HBM, mirrored in the ring ----
+                // Inside a group stores are not in position order (all literals first), so two positions of one group must not share a ring
+                // slot: a group spanning Z_RING bytes or more reads from HBM only and leaves the ring untrusted below its end.
+                const bool ring_ok = O < Z_RING;
+                // literal runs of the whole group: byte k belongs to the sequence j with il[j-1] <= k < il[j]
+                for (uint32_t k0 = 0; k0 < T; k0 += 32) {
+                    uint32_t k = k0 + lane;
+                    uint32_t lo = 0;   // smallest j with il[j] > k, by 5 shuffle probes
+#pragma unroll
+                    for (int s = 16; s; s >>= 1) { uint32_t v = __shfl_sync(0xffffffffu, il, (lo + s - 1) & 31); if (v <= k) lo += s; }
+                    uint32_t js = __shfl_sync(0xffffffffu, lit_start, lo & 31), jo = __shfl_sync(0xffffffffu, o_start, lo & 31);
+                    if (k < T) { uint8_t v = lit_rle ? rle_byte : lit[lit_run + k]; uint32_t at = out_run + jo + (k - js); dst[at] = v; VL_RING(at) = v; }
+                }
+                __syncwarp();
+                const uint32_t im = io - il;                                         // inclusive prefix sum of the match lengths
+                uint32_t cur = 0;
+                while (cur < cnt) {
+                    const uint32_t ready = __ballot_sync(0xffffffffu, lane >= cur && lane < cnt && dep < (int)cur) >> cur;
+                    const uint32_t n = ready == 0xffffffffu ? 32u : max((uint32_t)__ffs((int)~ready) - 1u, 1u);
+                    const uint32_t hi = cur + n;
+                    const uint32_t im_lo = cur ? __shfl_sync(0xffffffffu, im, cur - 1) : 0u, M = __shfl_sync(0xffffffffu, im, hi - 1) - im_lo;
+                    for (uint32_t k0 = 0; k0 < M; k0 += 32) {
+                        const uint32_t k = im_lo + k0 + lane;   // position in the group's concatenated match bytes
+                        uint32_t lo = 0;                         // smallest j with im[j] > k
+#pragma unroll
+                        for (int s = 16; s; s >>= 1) { uint32_t v = __shfl_sync(0xffffffffu, im, (lo + s - 1) & 31); if (v <= k) lo += s; }
+                        const uint32_t jm = __shfl_sync(0xffffffffu, ml, lo & 31), jo = __shfl_sync(0xffffffffu, off, lo & 31);
+                        const uint32_t jd = __shfl_sync(0xffffffffu, amd, lo & 31), je = __shfl_sync(0xffffffffu, im, lo & 31);
+                        if (k0 + lane < M) {
+                            const uint32_t kk = k - (je - jm);   // byte index inside match `lo`
+                            const uint32_t sa = jd - jo + (jo >= jm ? kk : kk % jo);   // frame position of the source byte
+                            const uint8_t v = (ring_ok && sa >= ring_lo && gend - sa < Z_RING) ? VL_RING(sa) : dst[sa];
+                            dst[jd + kk] = v; VL_RING(jd + kk) = v;
+                        }
+                    }
+                    __syncwarp();
+                    cur = hi;
+                }
+                if (!ring_ok) ring_lo = gend;
             }
             lit_run += T; out_run += O;
-            if (!ring_ok) ring_lo = gend;
         }
         // literals after the last sequence
         const uint32_t rest = B.lit_regen - lit_run;
-        for (uint32_t k = lane; k < rest; k += 32) { uint8_t v = lit_rle ? rle_byte : lit[lit_run + k]; dst[out_run + k] = v; ring[(out_run + k) & (Z_RING - 1)] = v; }
+        for (uint32_t k = lane; k < rest; k += 32) { uint8_t v = lit_rle ? rle_byte : lit[lit_run + k]; dst[out_run + k] = v; VL_RING(out_run + k) = v; }
+        if (rest >= Z_RING) ring_lo = out_run + rest - Z_RING;
         __syncwarp();
     }
+#undef VL_RING
 }
 
 }  // namespace zs

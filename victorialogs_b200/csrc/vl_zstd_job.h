@@ -25,8 +25,11 @@ using namespace zs;
 // scratch limits of one launch group (groups are cut at frame boundaries)
 // A group must hold enough blocks to fill the device for the lane-per-block phases (148 SMs x 56 sequence lanes = 8.3 k blocks per
 // wave); beyond a few waves, smaller groups are better: group g is decoded while the bytes of group g+1 are still being copied.
-const uint64_t kGroupLits = 2ull << 30, kGroupSeqs = 256ull << 20;
-const uint32_t kGroupSlots = 96u << 10;
+// Round 2: a quarter of the round-1 limits.  The C2 batch (667 M sequences) becomes 11 groups instead of 3: the first one is decoded after a
+// tenth of the compressed bytes has arrived, the execute kernel of group g runs beside the entropy kernels of group g + 1 (second stream,
+// vl_zstd.cu), and the scratch (two copies of literals + sequence records) shrinks from 6 GB to 3 GB.
+const uint64_t kGroupLits = 512ull << 20, kGroupSeqs = 64ull << 20;
+const uint32_t kGroupSlots = 32u << 10;
 
 struct Group { uint32_t frame_lo, frame_hi; uint32_t huf_lo, huf_hi, lit_lo, lit_hi, seq_lo, seq_hi, ord_lo, ord_hi; };
 
