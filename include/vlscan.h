@@ -66,12 +66,18 @@ typedef struct vlscan_column {
     const uint8_t* bloom;       uint64_t bloom_len;      /* big-endian u64 words as stored (bloomfilter.go:49-71)  */
 } vlscan_column;
 
-/* One block = blockSearchWork.bh.rowsCount + the columns the program references (block_search.go:64-77). */
+/* One block = blockSearchWork.bh.rowsCount + the columns the program references (block_search.go:64-77), and optionally its timestamps
+ * column: the bytes at [timestampsHeader.blockOffset, +blockSize) of timestamps.bin as stored (encoding.MarshalTimestamps with
+ * precisionBits = 64, lib/logstorage/block.go:674-690) plus the three header fields UnmarshalTimestamps needs (block_header.go:990-997).
+ * ZSTD marshal types are inflated on the device like values blocks.  Timestamps are needed by `_time` filters that only partly overlap
+ * the block (filter_time.go:114-137) and by vlscan_gather_timestamps; blocks handed over without them fail such a scan with an error. */
 typedef struct vlscan_block {
     uint64_t rows;
     uint32_t ncols;
-    uint32_t reserved;
+    uint32_t ts_marshal_type;         /* 0 = no timestamps given; else encoding.MarshalType 1..6 (vm/lib/encoding/encoding.go:20-43) */
     const vlscan_column* cols;
+    const uint8_t* timestamps; uint64_t timestamps_len;
+    int64_t min_timestamp, max_timestamp;   /* timestampsHeader.minTimestamp (= the first row's timestamp) and maxTimestamp */
 } vlscan_block;
 
 /* Counters of one scan (block_stats-like accounting, lib/logstorage/pipe_block_stats.go:90-105). Algorithmic bytes
@@ -136,12 +142,13 @@ int vlscan_ctx_sync(vlscan_ctx* ctx);                        /* cudaStreamSynchr
  *  16 SEQUENCE     (filter_sequence.go:12-22)       bytes(fieldName) varuint(n) n x bytes(phrase)           `f:seq(a, b, ...)`
  *  17 CONTAINS_ALL (filter_contains_all.go:12-20)   bytes(fieldName) varuint(n) n x bytes(value)            `f:contains_all(a, b, ...)`
  *  18 CONTAINS_ANY (filter_contains_any.go:12-20)   bytes(fieldName) varuint(n) n x bytes(value)            `f:contains_any(a, b, ...)`
+ *  22 TIME         (filter_time.go:14-23)           i64le(minTimestamp) i64le(maxTimestamp)                 `_time:[a, b]`, nanoseconds, inclusive
  * Token hashes, merged AND/OR per-field tokens, typed needles and regex automata are derived here, like the
  * sync.Once initialisers of the Go filters do on first use.  Returns <0 with an error text for malformed trees,
  * regexps that do not compile and regexps outside the supported syntax. */
 enum { VLSCAN_F_NOOP = 0, VLSCAN_F_PHRASE, VLSCAN_F_PREFIX, VLSCAN_F_EXACT, VLSCAN_F_IN, VLSCAN_F_REGEXP, VLSCAN_F_AND, VLSCAN_F_OR, VLSCAN_F_NOT,
        VLSCAN_F_EXACT_PREFIX = 9, VLSCAN_F_LEN_RANGE = 10, VLSCAN_F_STRING_RANGE = 11, VLSCAN_F_IPV4_RANGE = 12, VLSCAN_F_VALUE_TYPE = 13,
-       VLSCAN_F_ANY_CASE_PHRASE = 14, VLSCAN_F_ANY_CASE_PREFIX = 15, VLSCAN_F_SEQUENCE = 16, VLSCAN_F_CONTAINS_ALL = 17, VLSCAN_F_CONTAINS_ANY = 18 };
+       VLSCAN_F_ANY_CASE_PHRASE = 14, VLSCAN_F_ANY_CASE_PREFIX = 15, VLSCAN_F_SEQUENCE = 16, VLSCAN_F_CONTAINS_ALL = 17, VLSCAN_F_CONTAINS_ANY = 18, VLSCAN_F_TIME = 22 };
 int vlscan_program_create(const void* tree, size_t tree_len, vlscan_program** out);
 void vlscan_program_free(vlscan_program* prog);
 /* canonical names of the fields the tree references (so the caller lists only those columns per block) */
@@ -279,6 +286,20 @@ int vlscan_fetch_results(vlscan_ctx* ctx, uint64_t* out_bitmap_words, uint32_t* 
 /* Ascending hit-row indexes (u32 per hit, row index within its block) of the last scan, block after block; for callers
  * that want to skip forEachSetBitReadonly (bitmap.go:156-183).  out_hit_offsets has nblocks+1 entries. */
 int vlscan_fetch_hits(vlscan_ctx* ctx, uint32_t* out_hit_rows, uint64_t cap, uint64_t* out_hit_offsets);
+/* ---- hit materialisation: what blockResult reads for the selected rows (lib/logstorage/block_result.go:491-507, 529-591) -----------------------
+ * Both calls work on the result of the last vlscan_scan_resident of this ctx; its batch must still be alive.  Hits are ordered block after block,
+ * rows ascending (the order of vlscan_fetch_hits); out_hit_offsets (nblocks + 1 entries, may be NULL) receives the first hit of every block.
+ *
+ * vlscan_gather_timestamps: the `_time` of every selected row (blockResult.initTimestampsInternal): the timestamps blocks of the blocks with hits
+ *   are decoded on the device (encoding.UnmarshalTimestamps, all marshal types).  The batch must have been staged with timestamps.
+ * vlscan_gather_values: the value of `field` in every selected row as a string, the way blockResultColumn.getValues yields it: row bytes of a
+ *   strings column, the dictionary entry of a dict column, the text form of a typed value (marshalUint64String ... marshalTimestampISO8601String,
+ *   values_encoder.go:1367-1422), the value of a const column, "" for a field the block does not have.  out_value_offsets gets hits + 1 entries
+ *   (cap_values >= hits); the bytes of hit h are out_bytes[offsets[h], offsets[h + 1]).  *out_total_bytes = bytes needed, also when the call fails
+ *   because cap_bytes is too small (then nothing is written to out_bytes). */
+int vlscan_gather_timestamps(vlscan_ctx* ctx, int64_t* out_timestamps, uint64_t cap, uint64_t* out_hit_offsets);
+int vlscan_gather_values(vlscan_ctx* ctx, const char* field, size_t field_len, uint8_t* out_bytes, uint64_t cap_bytes, uint64_t* out_value_offsets, uint64_t cap_values,
+                         uint64_t* out_total_bytes, uint64_t* out_hit_offsets);
 /* Digest of the last scan's bitmaps of the blocks [block_lo, block_hi) of its batch, computed on the device: xor over the blocks of
  * XXH64(the block's bitmap words as little-endian bytes) * (2 * (key_base + block index) + 1).  The oracle reports the same quantity for its own
  * bitmaps, so a bench can check a billion-row scan against the CPU restatement on any block range without moving the bitmaps.  The batch of the

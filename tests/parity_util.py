@@ -17,7 +17,12 @@ def oracle_block_to_desc(blk, stage="ondisk"):
         else:
             d["lens_items"], d["data"] = vloracle.decode_values_block(c.values_block)
         cols.append(d)
-    return dict(rows=blk.rows, columns=cols)
+    d = dict(rows=blk.rows, columns=cols)
+    try:
+        d["timestamps"] = blk.timestamps_block()   # (encoded bytes, marshalType, minTimestamp, maxTimestamp)
+    except ValueError:
+        pass
+    return d
 
 
 def field_names_of(blocks):

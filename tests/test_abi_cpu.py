@@ -50,7 +50,7 @@ def test_header_is_plain_c_and_links(tmp_path):
 def test_struct_layouts_match_header():
     # sizes asserted against the C layout rules of include/vlscan.h (x86-64 SysV)
     assert C.sizeof(vs.CColumn) == 4 + 4 + 8 + 8 + 8 * 12
-    assert C.sizeof(vs.CBlock) == 24
+    assert C.sizeof(vs.CBlock) == 24 + 8 + 8 + 8 + 8   # + timestamps pointer, length, minTimestamp, maxTimestamp
     assert C.sizeof(vs.CStats) == 8 * 14
     assert C.sizeof(vs.GenConfig) == 32
 
@@ -103,7 +103,7 @@ def test_next_filter_kinds_compile_and_tokens(oracle):
                     "contains_all": 104, "contains_any": 88}
     with pytest.raises(vs.VlscanError):
         vs.Program(vs.Filter(bytes([vs.F_IPV4_RANGE, 1, ord("f")]) + bytes([0x80, 0x80, 0x80, 0x80, 0x10, 0]), "ipv4 bound > 32 bits"))
-    for kind in (19, 20, 21, 22, 23):
+    for kind in (19, 20, 21, 23):
         with pytest.raises(vs.VlscanError):
             vs.Program(vs.Filter(bytes([kind, 1, ord("f"), 1, ord("x")]), "kind not built yet"))
     # AND: exact_prefix contributes its tokens to the per-field bloom pre-pass (filter_and.go:141-143)

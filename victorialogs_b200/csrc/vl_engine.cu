@@ -258,10 +258,22 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
     };
     // Pre-pass: the compressed bytes of on-disk values blocks are shipped first (their place in the staging buffer is a running sum), so
     // that the DMA engine is busy while the host walks frame and block headers.
-    std::vector<ZValuesBlock> zv; std::vector<ZValuesInfo> zinfo; size_t zbad = SIZE_MAX, zo = 0; std::string zmsg;
+    std::vector<ZValuesBlock> zv, zts; std::vector<ZValuesInfo> zinfo; size_t zbad = SIZE_MAX, zo = 0, zt = 0; std::string zmsg;
+    std::vector<DevTimestamps> tsv; bool any_ts = false;
+    struct TsFrame { uint64_t block; uint32_t frame; uint64_t rel; };
+    std::vector<TsFrame> ts_frames;
     {
-        const uint64_t zc = collect_values_blocks(blocks, nblocks, zv);
+        uint64_t zc = collect_values_blocks(blocks, nblocks, zv);
         for (const ZValuesBlock& v : zv) if (v.n) zpieces.push_back({v.p, v.n, v.zoff});
+        // ZSTD-compressed timestamps blocks (marshal types 1 and 4) travel the same way, behind the values blocks
+        for (uint64_t b = 0; b < nblocks; b++) {
+            const vlscan_block& blk = blocks[b];
+            if (blk.ts_marshal_type != MT_ZSTD_NEAREST_DELTA2 && blk.ts_marshal_type != MT_ZSTD_NEAREST_DELTA) continue;
+            if (blk.timestamps_len > vl::part::kMaxTimestampsBlockSize) throw BadInput("timestamps block size cannot exceed 8 MiB");   // getTimestamps block_search.go:490-493
+            zts.push_back({blk.timestamps, (size_t)blk.timestamps_len, zc});
+            if (blk.timestamps_len) zpieces.push_back({blk.timestamps, blk.timestamps_len, zc});
+            zc += blk.timestamps_len;
+        }
         if (!zpieces.empty()) { ctx->zsrc.ensure(zc + 512); marking = true; copy_pieces(zpieces, ctx->zsrc.as<uint8_t>()); marking = false; }
         // frame, block and section headers of all of them, on several host threads; a malformed block is reported when the loop below gets to it
         zinfo.resize(zv.size());
@@ -274,6 +286,26 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
         const vlscan_block& blk = blocks[b];
         if (blk.rows > (8u << 20)) throw BadInput("block rows exceed maxRowsPerBlock (8Mi)");   // consts.go:24
         rows[b] = (uint32_t)blk.rows;
+        if (blk.ts_marshal_type) {   // the timestamps column: encoded deltas as stored + timestampsHeader (block_header.go:990-997)
+            if (blk.ts_marshal_type > MT_NEAREST_DELTA) throw BadInput("unknown MarshalType of a timestamps block");
+            if (blk.timestamps_len > vl::part::kMaxTimestampsBlockSize) throw BadInput("timestamps block size cannot exceed 8 MiB");
+            if (tsv.empty()) { tsv.resize(nblocks); memset(tsv.data(), 0, nblocks * sizeof(DevTimestamps)); }
+            any_ts = true;
+            DevTimestamps& t = tsv[b];
+            t.first = blk.min_timestamp; t.max = blk.max_timestamp;
+            if (blk.ts_marshal_type == MT_ZSTD_NEAREST_DELTA2 || blk.ts_marshal_type == MT_ZSTD_NEAREST_DELTA) {
+                uint64_t regen = 0; uint32_t id = 0;
+                zjob.add_frame(zts[zt].p, zts[zt].n, zts[zt].zoff, &regen, &id);   // throws on a malformed frame header
+                zt++;
+                if (regen > 10ull * blk.rows + 16) throw BadInput("cannot unmarshal timestamps: the decompressed block is larger than its varints can be");
+                t.mt = blk.ts_marshal_type == MT_ZSTD_NEAREST_DELTA2 ? MT_NEAREST_DELTA2 : MT_NEAREST_DELTA;
+                t.len = (uint32_t)regen;
+                ts_frames.push_back({b, id, arena_reserve(regen_cursor, regen)});
+            } else {
+                t.mt = (uint8_t)blk.ts_marshal_type; t.len = (uint32_t)blk.timestamps_len;
+                t.off = add_piece(blk.timestamps, blk.timestamps_len);
+            }
+        }
         for (uint32_t k = 0; k < blk.ncols; k++) {
             const vlscan_column& c = blk.cols[k];
             if (c.field >= nfields) throw BadInput("column refers to a field outside the batch field table");
@@ -344,7 +376,8 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
         d.lens_off += regen_base; d.data_off += regen_base;
         zjob.set_dst(o.lens_frame, regen_base + o.lens_rel); zjob.set_dst(o.data_frame, regen_base + o.data_rel);
     }
-    if (!ondisk.empty()) cursor = regen_base + regen_cursor;
+    for (const TsFrame& tf : ts_frames) { tsv[tf.block].off = regen_base + tf.rel; zjob.set_dst(tf.frame, regen_base + tf.rel); }
+    if (!ondisk.empty() || !ts_frames.empty()) cursor = regen_base + regen_cursor;
     out->arena_bytes = cursor + kArenaPad;
     t_desc = now();
     out->arena.ensure(out->arena_bytes);
@@ -359,11 +392,17 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
     for (int k = 0; k < 2; k++) if (evs[k]) cudaEventDestroy(evs[k]);
     out->cols.ensure(std::max<size_t>(cols.size() * sizeof(DevColumn), 16));
     if (!cols.empty()) VL_CUDA(cudaMemcpyAsync(out->cols.p, cols.data(), cols.size() * sizeof(DevColumn), cudaMemcpyHostToDevice, cs));
+    out->has_ts = any_ts;
+    if (any_ts) {
+        out->ts.ensure(nblocks * sizeof(DevTimestamps));
+        VL_CUDA(cudaMemcpyAsync(out->ts.p, tsv.data(), nblocks * sizeof(DevTimestamps), cudaMemcpyHostToDevice, cs));
+        h2d += nblocks * sizeof(DevTimestamps);
+    }
     VL_CUDA(cudaEventRecord(ev_copied, cs));
     h2d += cols.size() * sizeof(DevColumn);
     double t_h2d = 0, t_zrun = 0;
     if (dbg) t_h2d = now();
-    if (!ondisk.empty()) {
+    if (!ondisk.empty() || !ts_frames.empty()) {
         // regenerate the on-disk payloads in HBM (each launch group as soon as its compressed bytes have arrived), then derive
         // lens_type / lens_const / data_const from the regenerated lens blocks
         zjob.set_group_hook([&](uint64_t src_end) {
@@ -376,9 +415,11 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
         ctx->zcols.ensure(16 + ocols.size() * sizeof(OndiskCol));
         VL_CUDA(cudaMemsetAsync(ctx->zcols.p, 0, 16, ctx->stream));
         VL_CUDA(cudaMemcpyAsync(ctx->zcols.as<uint8_t>() + 16, ocols.data(), ocols.size() * sizeof(OndiskCol), cudaMemcpyHostToDevice, ctx->stream));
-        k_finish_ondisk_cols<<<cdiv(ocols.size(), 128), 128, 0, ctx->stream>>>(out->arena.as<uint8_t>(), out->cols.as<DevColumn>(), (const OndiskCol*)(ctx->zcols.as<uint8_t>() + 16),
-                                                                                 (uint32_t)ocols.size(), ctx->zcols.as<unsigned long long>());
-        launch_check(ctx);
+        if (!ocols.empty()) {
+            k_finish_ondisk_cols<<<cdiv(ocols.size(), 128), 128, 0, ctx->stream>>>(out->arena.as<uint8_t>(), out->cols.as<DevColumn>(), (const OndiskCol*)(ctx->zcols.as<uint8_t>() + 16),
+                                                                                     (uint32_t)ocols.size(), ctx->zcols.as<unsigned long long>());
+            launch_check(ctx);
+        }
         h2d += ocols.size() * sizeof(OndiskCol);
         zjob.check(ctx);   // synchronises the stream
         unsigned long long cst[2] = {0, 0};
@@ -435,7 +476,7 @@ struct ScanRun {
     void leaf(int leaf_idx, uint64_t* reg) {
         const DevLeaf& L = prog->p.leaves[leaf_idx];
         if (L.kind == F_NOOP) return;
-        int slot = field_slot[L.field];
+        int slot = L.field >= 0 ? field_slot[L.field] : -1;
         uint8_t* action = ctx->action.as<uint8_t>(); uint64_t* payload = ctx->payload.as<uint64_t>(); uint64_t* leaf_bm = ctx->leaf_bm.as<uint64_t>();
         uint32_t* lens_blocks = ctx->lens_blocks.as<uint32_t>(); uint32_t* row_blocks = ctx->row_blocks.as<uint32_t>(); uint32_t* wc = ctx->work_count.as<uint32_t>();
         uint32_t* tb = ctx->tile_block.as<uint32_t>(); uint32_t* to = ctx->tile_off.as<uint32_t>();
@@ -474,6 +515,11 @@ struct ScanRun {
             if (may_row) { k_row_match<<<persistent, 256, 0, ctx->stream>>>(P, B, (uint32_t)leaf_idx, slot, row_blocks, wc, action, payload, ro, leaf_bm); launch_check(ctx); }
             if (has_dict || has_numeric) { k_word_match<<<cdiv(B.nwords, 128), 128, 0, ctx->stream>>>(P, B, (uint32_t)leaf_idx, slot, action, payload, leaf_bm, stats); launch_check(ctx); }
         }
+        if (L.kind == F_TIME && B.nwords) {   // blocks the range only partly covers: decode their timestamps, compare per row
+            ctx->ts_vals.ensure(B.nwords * 64 * 8);
+            k_time_match<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(B, (long long)L.aux0, (long long)L.aux1, row_blocks, wc, ctx->ts_vals.as<unsigned long long>(), leaf_bm, stats);
+            launch_check(ctx);
+        }
         if (B.nwords) { k_apply_leaf<<<cdiv(B.nwords, 256), 256, 0, ctx->stream>>>(B, action, leaf_bm, reg); launch_check(ctx); }
     }
     std::pair<cudaEvent_t, cudaEvent_t>& next_scan_events() {
@@ -509,8 +555,8 @@ static void read_stats(vlscan_ctx* ctx, vlscan_stats* st, bool check_error) {
     if (check_error && h[ST_ERROR]) {
         static const char* const msg[] = {"", "cannot unmarshal strings: row lengths do not add up to the data length", "too big index for dict value",
                                           "unexpected length for binary representation of a number", "phrase/prefix/regexp over a float64 column needs float->string formatting, which the GPU engine does not implement",
-                                          "unexpected uint64 block type"};
-        throw BadInput(msg[std::min<unsigned long long>(h[ST_ERROR], 5)]);
+                                          "unexpected uint64 block type", "the filter needs the timestamps of a block that was handed over without them", "cannot unmarshal timestamps"};
+        throw BadInput(msg[std::min<unsigned long long>(h[ST_ERROR], 7)]);
     }
     if (!st) return;
     st->values_bytes += h[ST_VALUES_BYTES]; st->bloom_probe_bytes += h[ST_BLOOM_BYTES]; st->columns_read += h[ST_COLUMNS_READ];
@@ -553,7 +599,7 @@ static void do_scan(vlscan_ctx* ctx, const vlscan_program* prog, const vlscan_ba
     run.copy_reg(reg, batch->init_bitmap.as<uint64_t>());
     if (batch->nblocks) {
         run.node(pr.root, reg);
-        k_finalize<<<cdiv((uint64_t)batch->nblocks * 32, 256), 256, 0, ctx->stream>>>(run.B, reg, ctx->counts.as<uint32_t>(), run.stats, ctx->totals.as<unsigned long long>());
+        k_finalize<<<cdiv(batch->nblocks, 8), 256, 0, ctx->stream>>>(run.B, reg, ctx->counts.as<uint32_t>(), run.stats, ctx->totals.as<unsigned long long>());
         launch_check(ctx);
     }
     VL_CUDA(cudaEventRecord(ctx->ev_end, ctx->stream));
@@ -602,7 +648,8 @@ void vlscan_ctx_free(vlscan_ctx* ctx) {
     for (auto& r : ctx->regs) r.release();
     for (auto& r : ctx->row_off8) r.release();
     for (auto& r : ctx->ready) r.release();
-    ctx->zsrc.release(); ctx->zcols.release(); ctx->ztest.release();
+    ctx->zsrc.release(); ctx->zcols.release(); ctx->ztest.release(); ctx->ts_vals.release();
+    for (DevBuf* b : {&ctx->hit_block, &ctx->glens, &ctx->goffs, &ctx->gtiles, &ctx->gout, &ctx->gstat}) b->release();
     zstd_dev_free(ctx->zdev);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     delete ctx->recycle;
@@ -1026,6 +1073,100 @@ int vlscan_fetch_hits(vlscan_ctx* ctx, uint32_t* out_hit_rows, uint64_t cap, uin
         uint64_t total = out_hit_offsets[b->nblocks];
         if (total > cap) throw BadInput("hit buffer too small");
         if (total) VL_CUDA(cudaMemcpyAsync(out_hit_rows, ctx->hits.p, total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        VL_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+// ---- hit materialisation ----------------------------------------------------------------------------------------------------------------------
+// hits of the last scan on the device: ctx->hits (row inside its block), ctx->hit_block, ctx->hit_offs (first hit of every block); returns their number
+static uint64_t build_hit_list(vlscan_ctx* ctx, uint64_t* out_hit_offsets) {
+    if (!ctx->has_result) throw BadInput("no scan result on this ctx");
+    VL_CUDA(cudaSetDevice(ctx->device));
+    const vlscan_batch* b = ctx->last_batch;
+    BatchView B = b->view();
+    ctx->hit_offs.ensure((b->nblocks + 1) * 8);
+    k_scan_counts<<<1, 1024, 0, ctx->stream>>>(ctx->counts.as<uint32_t>(), (uint32_t)b->nblocks, ctx->hit_offs.as<uint64_t>()); launch_check(ctx);
+    uint64_t total = 0;
+    VL_CUDA(cudaMemcpyAsync(&total, ctx->hit_offs.as<uint64_t>() + b->nblocks, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_hit_offsets) VL_CUDA(cudaMemcpyAsync(out_hit_offsets, ctx->hit_offs.p, (b->nblocks + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    VL_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->hits.ensure(std::max<uint64_t>(total, 4) * 4); ctx->hit_block.ensure(std::max<uint64_t>(total, 4) * 4);
+    if (b->nblocks && total) {
+        k_hits_compact2<<<cdiv((uint64_t)b->nblocks * 32, 256), 256, 0, ctx->stream>>>(B, ctx->regs[0].as<uint64_t>(), ctx->hit_offs.as<uint64_t>(), ctx->hits.as<uint32_t>(), ctx->hit_block.as<uint32_t>(), total);
+        launch_check(ctx);
+    }
+    ctx->gstat.ensure(ST_COUNT * 8);
+    VL_CUDA(cudaMemsetAsync(ctx->gstat.p, 0, ST_COUNT * 8, ctx->stream));
+    return total;
+}
+static void check_gather_errors(vlscan_ctx* ctx) {
+    unsigned long long h[ST_COUNT];
+    VL_CUDA(cudaMemcpyAsync(h, ctx->gstat.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    VL_CUDA(cudaStreamSynchronize(ctx->stream));
+    static const char* const msg[] = {"", "cannot unmarshal strings: row lengths do not add up to the data length", "too big index for dict value", "unexpected length for binary representation of a number", "",
+                                      "unexpected uint64 block type", "the timestamps of a block with selected rows were not handed over", "cannot unmarshal timestamps"};
+    if (h[ST_ERROR]) throw BadInput(msg[std::min<unsigned long long>(h[ST_ERROR], 7)]);
+}
+
+int vlscan_gather_timestamps(vlscan_ctx* ctx, int64_t* out_timestamps, uint64_t cap, uint64_t* out_hit_offsets) {
+    return guarded(ctx, [&] {
+        const uint64_t n = build_hit_list(ctx, out_hit_offsets);
+        if (n > cap) throw BadInput("timestamps buffer too small");
+        if (!n) return;
+        const vlscan_batch* b = ctx->last_batch;
+        BatchView B = b->view();
+        uint32_t* wc = ctx->work_count.as<uint32_t>(); uint32_t* row_blocks = ctx->row_blocks.as<uint32_t>();
+        unsigned long long* gstat = ctx->gstat.as<unsigned long long>();
+        VL_CUDA(cudaMemsetAsync(wc, 0, WC_COUNT * 4, ctx->stream));
+        k_hit_blocks_list<<<cdiv(b->nblocks, 256), 256, 0, ctx->stream>>>(B, ctx->counts.as<uint32_t>(), -1, 1, row_blocks, wc); launch_check(ctx);
+        ctx->ts_vals.ensure(b->nwords * 64 * 8);
+        k_ts_decode_list<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(B, row_blocks, wc, ctx->ts_vals.as<unsigned long long>(), gstat); launch_check(ctx);
+        ctx->gout.ensure(n * 8);
+        k_gather_ts<<<cdiv(n, 256), 256, 0, ctx->stream>>>(B, ctx->hits.as<uint32_t>(), ctx->hit_block.as<uint32_t>(), n, ctx->ts_vals.as<unsigned long long>(), ctx->gout.as<long long>()); launch_check(ctx);
+        check_gather_errors(ctx);
+        VL_CUDA(cudaMemcpy(out_timestamps, ctx->gout.p, n * 8, cudaMemcpyDeviceToHost));
+    });
+}
+
+int vlscan_gather_values(vlscan_ctx* ctx, const char* field, size_t field_len, uint8_t* out_bytes, uint64_t cap_bytes, uint64_t* out_value_offsets, uint64_t cap_values,
+                         uint64_t* out_total_bytes, uint64_t* out_hit_offsets) {
+    if (out_total_bytes) *out_total_bytes = 0;
+    return guarded(ctx, [&] {
+        const uint64_t n = build_hit_list(ctx, out_hit_offsets);
+        if (n > cap_values) throw BadInput("value offsets buffer too small");
+        if (out_value_offsets) out_value_offsets[0] = 0;
+        if (!n) return;
+        const vlscan_batch* b = ctx->last_batch;
+        BatchView B = b->view();
+        std::string name(field, field_len); if (name.empty()) name = "_msg";   // getCanonicalColumnName
+        int slot = -1;
+        for (uint32_t s2 = 0; s2 < b->nfields; s2++) if (b->field_names[s2] == name) slot = (int)s2;
+        uint32_t* wc = ctx->work_count.as<uint32_t>(); uint32_t* lens_blocks = ctx->lens_blocks.as<uint32_t>();
+        unsigned long long* gstat = ctx->gstat.as<unsigned long long>();
+        const uint32_t* ro = nullptr;
+        if (slot >= 0) {   // row offsets of the strings blocks with hits (kept from the scan where it already computed them)
+            VL_CUDA(cudaMemsetAsync(wc, 0, WC_COUNT * 4, ctx->stream));
+            k_hit_blocks_list<<<cdiv(b->nblocks, 256), 256, 0, ctx->stream>>>(B, ctx->counts.as<uint32_t>(), slot, 0, lens_blocks, wc); launch_check(ctx);
+            uint8_t* ready = ctx->ready[slot].as<uint8_t>();
+            if (!ctx->ready_cleared[slot]) { VL_CUDA(cudaMemsetAsync(ready, 0, B.nblocks, ctx->stream)); ctx->ready_cleared[slot] = 1; }
+            k_lens_offsets<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(B, slot, lens_blocks, wc, ctx->row_off8[slot].as<uint32_t>(), ready, gstat); launch_check(ctx);
+            ro = ctx->row_off8[slot].as<uint32_t>();
+        }
+        const uint64_t ntiles = cdiv(n, VL_SCAN_TILE);
+        ctx->glens.ensure(n * 4); ctx->goffs.ensure((n + 1) * 8); ctx->gtiles.ensure((ntiles + 1) * 8);
+        k_gather_values<<<cdiv(n, 128), 128, 0, ctx->stream>>>(B, slot, ctx->hits.as<uint32_t>(), ctx->hit_block.as<uint32_t>(), n, ro, 0, ctx->glens.as<uint32_t>(), nullptr, nullptr, gstat); launch_check(ctx);
+        k_scan_tiles<<<(unsigned)ntiles, 256, 0, ctx->stream>>>(ctx->glens.as<uint32_t>(), n, ctx->gtiles.as<unsigned long long>(), nullptr, 0); launch_check(ctx);
+        k_scan_tile_sums<<<1, 1024, 0, ctx->stream>>>(ctx->gtiles.as<unsigned long long>(), ntiles, ctx->goffs.as<unsigned long long>() + n); launch_check(ctx);
+        k_scan_tiles<<<(unsigned)ntiles, 256, 0, ctx->stream>>>(ctx->glens.as<uint32_t>(), n, ctx->gtiles.as<unsigned long long>(), ctx->goffs.as<unsigned long long>(), 1); launch_check(ctx);
+        uint64_t total = 0;
+        VL_CUDA(cudaMemcpyAsync(&total, ctx->goffs.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        check_gather_errors(ctx);
+        if (out_total_bytes) *out_total_bytes = total;
+        if (total > cap_bytes) throw BadInput("values buffer too small (the needed size is reported)");
+        ctx->gout.ensure(std::max<uint64_t>(total, 16));
+        k_gather_values<<<cdiv(n, 128), 128, 0, ctx->stream>>>(B, slot, ctx->hits.as<uint32_t>(), ctx->hit_block.as<uint32_t>(), n, ro, 1, nullptr, ctx->goffs.as<uint64_t>(), ctx->gout.as<uint8_t>(), gstat); launch_check(ctx);
+        if (out_value_offsets) VL_CUDA(cudaMemcpyAsync(out_value_offsets, ctx->goffs.p, (n + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (total) VL_CUDA(cudaMemcpyAsync(out_bytes, ctx->gout.p, total, cudaMemcpyDeviceToHost, ctx->stream));
         VL_CUDA(cudaStreamSynchronize(ctx->stream));
     });
 }

@@ -51,7 +51,8 @@ struct vlscan_batch {
     std::vector<std::string> field_names;
     uint64_t nblocks = 0, nwords = 0, rows = 0;
     uint64_t arena_bytes = 0;
-    vl::DevBuf arena, cols, blk_rows, blk_word_off, word_block, init_bitmap;
+    vl::DevBuf arena, cols, blk_rows, blk_word_off, word_block, init_bitmap, ts;
+    bool has_ts = false;                  // some block came with its timestamps column
     std::vector<uint32_t> h_rows;
     std::vector<uint64_t> h_word_off;
     std::vector<uint32_t> slot_vt_mask;   // per field slot: bit vt set when some block stores the field with that valueType
@@ -63,11 +64,12 @@ struct vlscan_batch {
         vl::BatchView v;
         v.arena = arena.as<uint8_t>(); v.cols = cols.as<vl::DevColumn>(); v.blk_rows = blk_rows.as<uint32_t>();
         v.blk_word_off = blk_word_off.as<uint64_t>(); v.word_block = word_block.as<uint32_t>();
+        v.ts = has_ts ? ts.as<vl::DevTimestamps>() : nullptr;
         v.nblocks = (uint32_t)nblocks; v.nfields = nfields; v.nwords = nwords;
         return v;
     }
-    uint64_t device_bytes() const { return arena.cap + cols.cap + blk_rows.cap + blk_word_off.cap + word_block.cap + init_bitmap.cap; }
-    ~vlscan_batch() { cudaSetDevice(device); arena.release(); cols.release(); blk_rows.release(); blk_word_off.release(); word_block.release(); init_bitmap.release(); }
+    uint64_t device_bytes() const { return arena.cap + cols.cap + blk_rows.cap + blk_word_off.cap + word_block.cap + init_bitmap.cap + ts.cap; }
+    ~vlscan_batch() { cudaSetDevice(device); arena.release(); cols.release(); blk_rows.release(); blk_word_off.release(); word_block.release(); init_bitmap.release(); ts.release(); }
 };
 
 struct vlscan_ctx {
@@ -82,6 +84,8 @@ struct vlscan_ctx {
     std::vector<vl::DevBuf> row_off8;      // per batch field slot: byte offset of every 8th row (k_lens_offsets)
     std::vector<vl::DevBuf> ready;         // per batch field slot: row_off8 computed for block b in this scan
     std::vector<char> ready_cleared;
+    vl::DevBuf hit_block, glens, goffs, gtiles, gout, gstat;   // hit materialisation (vlscan_gather_*): block of each hit, value lengths / offsets, output staging, error slot
+    vl::DevBuf ts_vals;                    // decoded timestamps / running sums, 8 bytes per row of the batch (k_time_match, gather)
     vl::DevBuf zsrc, zcols, ztest;         // compressed staging of on-disk values blocks; their column list; test output
     vl::ZstdDev* zdev = nullptr;           // device ZSTD decoder scratch (vl_zstd.cu)
     void* pinned = nullptr; size_t pinned_cap = 0;

@@ -16,7 +16,7 @@ struct DevProgram {
 
 // stats slots (device u64 array)
 enum { ST_VALUES_BYTES = 0, ST_BLOOM_BYTES, ST_COLUMNS_READ, ST_BITMAP_BYTES, ST_ROWS_MATCHED, ST_BLOCKS_MATCHED, ST_ERROR, ST_SCAN_BYTES, ST_COUNT };
-enum { ERR_NONE = 0, ERR_LENS_MISMATCH = 1, ERR_DICT_INDEX = 2, ERR_BAD_WIDTH = 3, ERR_UNSUPPORTED_FLOAT_TOSTRING = 4, ERR_BAD_LENS_TYPE = 5 };
+enum { ERR_NONE = 0, ERR_LENS_MISMATCH = 1, ERR_DICT_INDEX = 2, ERR_BAD_WIDTH = 3, ERR_UNSUPPORTED_FLOAT_TOSTRING = 4, ERR_BAD_LENS_TYPE = 5, ERR_NO_TIMESTAMPS = 6, ERR_BAD_TIMESTAMPS = 7 };
 
 struct BatchView {
     const uint8_t* arena;
@@ -24,6 +24,7 @@ struct BatchView {
     const uint32_t* blk_rows;     // [nblocks]
     const uint64_t* blk_word_off; // [nblocks + 1]
     const uint32_t* word_block;   // [nwords] owning block of each bitmap word
+    const DevTimestamps* ts;      // [nblocks] or NULL when the batch was staged without timestamps
     uint32_t nblocks, nfields;
     uint64_t nwords;
 };
@@ -268,6 +269,13 @@ static __global__ void __launch_bounds__(VL_PLAN_WARPS * 32) k_plan_leaf(DevProg
     const DevColumn* c = slot >= 0 ? &B.cols[(uint64_t)b * B.nfields + slot] : nullptr;
     const uint8_t* nd = P.blob + L.needle_off; uint32_t nl = L.needle_len;
     if ((L.kind == F_IN && L.in_count == 0) || L.always_none) act = ACT_NONE;   // fi.values.isEmpty(); minLen > maxLen, minValue > maxValue
+    else if (L.kind == F_TIME) {   // filterTime.applyToBlockSearch filter_time.go:114-137: header-level decisions first
+        const int64_t mn = (int64_t)L.aux0, mx = (int64_t)L.aux1;
+        if (!B.ts || B.ts[b].mt == 0) { act = ACT_NONE; err = ERR_NO_TIMESTAMPS; }
+        else if (mn > B.ts[b].max || mx < B.ts[b].first) act = ACT_NONE;
+        else if (mn <= B.ts[b].first && mx >= B.ts[b].max) act = ACT_ALL;
+        else { act = ACT_TIME; need_row = 1; }
+    }
     else if (c && c->kind == COL_CONST) {
         if (L.kind == F_VALUE_TYPE) act = L.aux0 == VTYPE_CONST ? ACT_ALL : ACT_NONE;   // filter_value_type.go:46-52
         else act = leaf_match_string(P, L, B.arena + c->meta_off, c->meta_len) ? ACT_ALL : ACT_NONE;
@@ -537,35 +545,35 @@ static __global__ void k_finish_ondisk_cols(const uint8_t* __restrict__ arena, D
 
 // ---- lens decode -> byte offset of every 8th row (unmarshalUint64Items + the offsets implied by encoding.go:122-130) --------------------
 // row_off8[8 * w + g] = byte offset (within the block's data) of row 64 * (w - first word of the block) + 8 * g, for every bitmap word w of the
-// block.  One CTA per block of the lens work list, one thread per bitmap word.  Sums are taken in 64 bits: a lens block whose items do not add
+// block.  One warp per block of the lens work list, one lane per bitmap word.  Sums are taken in 64 bits: a lens block whose items do not add
 // up to the data length (encoding.go:124-126) is reported, never wrapped into agreement.
 static __global__ void k_lens_offsets(BatchView B, int slot, const uint32_t* __restrict__ lens_blocks, const uint32_t* __restrict__ work_count,
                                uint32_t* __restrict__ row_off8, uint8_t* __restrict__ ready, unsigned long long* __restrict__ stats) {
-    __shared__ unsigned long long warp_sums[32];
-    __shared__ unsigned long long carry_s;
+    // one WARP per block of the lens work list (a block of 2000..6400 rows has 32..100 bitmap words: a whole CTA per block left most of its
+    // threads idle between barriers); lane = bitmap word, 32 words per step, the running sum travels in a register
     const uint32_t nwork = work_count[WC_LENS];
-    for (uint32_t j = blockIdx.x; j < nwork; j += gridDim.x) {
-        uint32_t b = lens_blocks[j];
-        if (ready[b]) continue;   // uniform per CTA
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5, lane = lane_id();
+    for (uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < nwork; j += warps) {
+        const uint32_t b = lens_blocks[j];
+        if (ready[b]) continue;   // uniform per warp
         const DevColumn& c = B.cols[(uint64_t)b * B.nfields + slot];
-        uint32_t rows = B.blk_rows[b];
-        uint64_t w0 = B.blk_word_off[b]; uint32_t nw = (uint32_t)(B.blk_word_off[b + 1] - w0);
+        const uint32_t rows = B.blk_rows[b];
+        const uint64_t w0 = B.blk_word_off[b]; const uint32_t nw = (uint32_t)(B.blk_word_off[b + 1] - w0);
         const uint8_t* lens = B.arena + c.lens_off;
         if (c.lens_type >= 4) {   // one const item: nothing to decode, the consumers divide
-            if (threadIdx.x == 0) {
+            if (lane == 0) {
                 if ((unsigned long long)rows * c.lens_const != c.data_len) atomicMax(&stats[ST_ERROR], (unsigned long long)ERR_LENS_MISMATCH);
                 ready[b] = 1;
             }
             continue;
         }
-        if (threadIdx.x == 0) carry_s = 0;
-        __syncthreads();
-        for (uint32_t base = 0; base < nw; base += blockDim.x) {
-            uint32_t w = base + threadIdx.x;
+        unsigned long long carry = 0;
+        for (uint32_t base = 0; base < nw; base += 32) {
+            const uint32_t w = base + lane;
             uint32_t g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             unsigned long long sum = 0;
             if (w < nw) {
-                uint32_t r0 = w * 64, r1 = min(rows, r0 + 64);
+                const uint32_t r0 = w * 64, r1 = min(rows, r0 + 64);
                 if (c.lens_type == 0) {
                     if (r1 - r0 == 64) {   // 64 u8 lens = four 16-byte vectors (r0 is a multiple of 64; lens_off is 16-byte aligned)
                         const uint4* v = (const uint4*)(lens + r0);
@@ -579,18 +587,13 @@ static __global__ void k_lens_offsets(BatchView B, int slot, const uint32_t* __r
                     for (uint32_t r = r0; r < r1; r++) g64[(r - r0) >> 3] += c.lens_type == 3 ? ld_be64(lens + 8 * (uint64_t)r) : (unsigned long long)row_len(c, lens, r);
 #pragma unroll
                     for (int q = 0; q < 8; q++) { sum += g64[q]; g[q] = (uint32_t)min(g64[q], 0xFFFFFFFFull); }
-                    if (sum > 0xFFFFFFFFull) sum = 0x100000000ull;   // cannot equal a data length (< 4 GiB); keeps the CTA sum from wrapping
+                    if (sum > 0xFFFFFFFFull) sum = 0x100000000ull;   // cannot equal a data length (< 4 GiB); keeps the running sum from wrapping
                 }
             }
-            // CTA exclusive scan of `sum`
             unsigned long long incl = sum;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d); if (lane_id() >= d) incl += t; }
-            if (lane_id() == 31) warp_sums[threadIdx.x >> 5] = incl;
-            __syncthreads();
-            uint32_t wid = threadIdx.x >> 5; unsigned long long wpre = 0;
-            for (uint32_t k = 0; k < wid; k++) wpre += warp_sums[k];
-            unsigned long long excl = carry_s + wpre + incl - sum;
+            for (int d = 1; d < 32; d <<= 1) { unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+            const unsigned long long excl = carry + incl - sum;
             if (w < nw) {
                 uint32_t o = (uint32_t)min(excl, 0xFFFFFFFFull);
                 uint4 a, bq;
@@ -599,15 +602,12 @@ static __global__ void k_lens_offsets(BatchView B, int slot, const uint32_t* __r
                 uint4* dst = (uint4*)(row_off8 + ((w0 + w) << 3));
                 dst[0] = a; dst[1] = bq;
             }
-            __syncthreads();
-            if (threadIdx.x == blockDim.x - 1) carry_s = excl + sum;
-            __syncthreads();
+            carry += __shfl_sync(0xffffffffu, incl, 31);
         }
-        if (threadIdx.x == 0) {
-            if (carry_s != c.data_len) atomicMax(&stats[ST_ERROR], (unsigned long long)ERR_LENS_MISMATCH);   // encoding.go:124-126
+        if (lane == 0) {
+            if (carry != c.data_len) atomicMax(&stats[ST_ERROR], (unsigned long long)ERR_LENS_MISMATCH);   // encoding.go:124-126
             ready[b] = 1;
         }
-        __syncthreads();
     }
 }
 
@@ -931,22 +931,32 @@ static __global__ void k_apply_leaf(BatchView B, const uint8_t* __restrict__ act
 }
 
 // ---- finalize: per-block popcount (bitmap.onesCount bitmap.go:185-191 == blockResult.rowsLen) + totals -------------------------------------------
-static __global__ void k_finalize(BatchView B, const uint64_t* __restrict__ reg, uint32_t* __restrict__ counts, unsigned long long* __restrict__ stats,
+static __global__ void __launch_bounds__(256) k_finalize(BatchView B, const uint64_t* __restrict__ reg, uint32_t* __restrict__ counts, unsigned long long* __restrict__ stats,
                            unsigned long long* __restrict__ totals4) {
-    uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (b >= B.nblocks) return;
-    uint64_t lo = B.blk_word_off[b], hi = B.blk_word_off[b + 1];
-    uint32_t n = 0;
-    for (uint64_t w = lo + lane_id(); w < hi; w += 32) n += __popcll(reg[w]);
+    __shared__ unsigned long long s_acc[8][4];   // per warp: rows, rows matched, blocks matched, bitmap bytes
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t b = blockIdx.x * 8 + warp;
+    unsigned long long rows = 0, matched = 0, blocks = 0, bm_bytes = 0;
+    if (b < B.nblocks) {
+        uint64_t lo = B.blk_word_off[b], hi = B.blk_word_off[b + 1];
+        uint32_t n = 0;
+        for (uint64_t w = lo + lane_id(); w < hi; w += 32) n += __popcll(reg[w]);
 #pragma unroll
-    for (int d = 16; d; d >>= 1) n += __shfl_xor_sync(0xffffffffu, n, d);
-    if (lane_id() == 0) {
-        counts[b] = n;
-        atomicAdd(&totals4[0], (unsigned long long)B.blk_rows[b]);
-        if (n) {
-            atomicAdd(&stats[ST_ROWS_MATCHED], (unsigned long long)n); atomicAdd(&stats[ST_BLOCKS_MATCHED], 1ull);
-            atomicAdd(&stats[ST_BITMAP_BYTES], 8ull * (hi - lo));
-            atomicAdd(&totals4[1], (unsigned long long)n); atomicAdd(&totals4[2], 1ull);
+        for (int d = 16; d; d >>= 1) n += __shfl_xor_sync(0xffffffffu, n, d);
+        if (lane_id() == 0) counts[b] = n;
+        rows = B.blk_rows[b];
+        if (n) { matched = n; blocks = 1; bm_bytes = 8ull * (hi - lo); }
+    }
+    if (lane_id() == 0) { s_acc[warp][0] = rows; s_acc[warp][1] = matched; s_acc[warp][2] = blocks; s_acc[warp][3] = bm_bytes; }
+    __syncthreads();
+    if (threadIdx.x < 4) {   // one atomic per CTA and counter instead of six per block
+        unsigned long long t = 0;
+        for (int w = 0; w < 8; w++) t += s_acc[w][threadIdx.x];
+        if (t) {
+            if (threadIdx.x == 0) atomicAdd(&totals4[0], t);
+            else if (threadIdx.x == 1) { atomicAdd(&stats[ST_ROWS_MATCHED], t); atomicAdd(&totals4[1], t); }
+            else if (threadIdx.x == 2) { atomicAdd(&stats[ST_BLOCKS_MATCHED], t); atomicAdd(&totals4[2], t); }
+            else atomicAdd(&stats[ST_BITMAP_BYTES], t);
         }
     }
 }
@@ -986,6 +996,245 @@ static __global__ void k_hits_compact(BatchView B, const uint64_t* __restrict__ 
         while (bits) { int k = __ffsll((long long)bits) - 1; bits &= bits - 1; if (pos < cap) hits[pos] = rbase + k; pos++; }
         out += __shfl_sync(0xffffffffu, incl, 31);
     }
+}
+
+// ---- timestamps column: encoding.UnmarshalTimestamps on the device (vm/lib/encoding/encoding.go:173-250, nearest_delta2.go:57-90, ------------
+// nearest_delta.go, int.go:173-280) and filterTime (lib/logstorage/filter_time.go:114-137) ------------------------------------------------------
+// One CTA per block.  The sequential decoder becomes three data-parallel steps (tests/test_timestamps_model_cpu.py proves them equal to it,
+// malformed input included): (1) a byte ends a varint iff its continuation bit is clear, so the index of a varint is the number of such bytes in
+// front of it (ballot + popcount, CTA running sum) and every varint is assembled from its <= 10 bytes independently; (2) NearestDelta: values =
+// first + inclusive scan of the deltas; NearestDelta2: one more inclusive scan in front (deltas of deltas -> deltas), all sums mod 2^64 like Go's
+// int64; (3) DeltaConst / Const need no scan.  vals[0 .. rows) receives the timestamps.  Returns false (CTA-uniform) on malformed input:
+// a varint longer than 10 bytes or overflowing 64 bits, too few / too many varints, bytes left over.
+static __device__ unsigned long long cta_incl_scan_u64(unsigned long long v, unsigned long long* s_warp, unsigned long long* s_carry) {   // all threads of the CTA; carries across calls
+    unsigned long long incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d); if (lane_id() >= d) incl += t; }
+    const uint32_t wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (lane_id() == 31) s_warp[wid] = incl;
+    __syncthreads();
+    unsigned long long pre = *s_carry;
+    for (uint32_t k = 0; k < wid; k++) pre += s_warp[k];
+    unsigned long long tot = 0;
+    for (uint32_t k = 0; k < nw; k++) tot += s_warp[k];
+    __syncthreads();
+    if (threadIdx.x == 0) *s_carry += tot;
+    __syncthreads();
+    return pre + incl;
+}
+static __device__ bool ts_decode_block(const BatchView& B, uint32_t b, unsigned long long* __restrict__ vals) {
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_carry;
+    __shared__ uint32_t s_cnt[32];
+    __shared__ uint32_t s_ccarry;
+    __shared__ int s_bad;
+    const DevTimestamps t = B.ts[b];
+    const uint32_t R = B.blk_rows[b], len = t.len;
+    const uint8_t* raw = B.arena + t.off;
+    const unsigned long long first = (unsigned long long)t.first;
+    if (threadIdx.x == 0) { s_bad = 0; s_ccarry = 0; s_carry = 0; }
+    __syncthreads();
+    if (t.mt == MT_CONST) {
+        for (uint32_t r = threadIdx.x; r < R; r += blockDim.x) vals[r] = first;
+        return len == 0;
+    }
+    if (t.mt == MT_DELTA_CONST) {
+        unsigned long long u = 0; bool ok = len >= 1 && len <= 10;
+        if (ok) { for (uint32_t k = 0; k < len; k++) { const uint8_t c = raw[k]; if ((k + 1 < len) != (c >= 0x80)) ok = false; u |= (unsigned long long)(c & 0x7F) << (7 * k); } if (len == 10 && raw[9] > 1) ok = false; }
+        const unsigned long long d = (u >> 1) ^ (0ull - (u & 1));
+        for (uint32_t r = threadIdx.x; r < R; r += blockDim.x) vals[r] = first + (unsigned long long)r * d;
+        return ok;
+    }
+    if (t.mt != MT_NEAREST_DELTA && t.mt != MT_NEAREST_DELTA2) return false;
+    const uint32_t min_rows = t.mt == MT_NEAREST_DELTA2 ? 2u : 1u;
+    if (R < min_rows) return false;
+    const uint32_t need = R - 1;   // NearestDelta: one delta per row after the first; NearestDelta2: the first delta, then R - 2 deltas of deltas
+    // (1) varints
+    for (uint32_t base = 0; base < len; base += blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        const uint8_t c = i < len ? raw[i] : 0x80;
+        const bool is_end = i < len && c < 0x80;
+        const uint32_t m = __ballot_sync(0xffffffffu, is_end);
+        if (lane_id() == 0) s_cnt[threadIdx.x >> 5] = __popc(m);
+        __syncthreads();
+        uint32_t k = s_ccarry + __popc(m & ((1u << lane_id()) - 1));
+        for (uint32_t w = 0; w < (threadIdx.x >> 5); w++) k += s_cnt[w];
+        if (is_end) {
+            uint32_t s0 = i, n = 1;
+            while (s0 > 0 && raw[s0 - 1] >= 0x80 && n <= 10) { s0--; n++; }
+            unsigned long long u = 0;
+            for (uint32_t q = 0; q < n && q < 10; q++) u |= (unsigned long long)(raw[s0 + q] & 0x7F) << (7 * q);
+            if (n > 10 || (n == 10 && c > 1) || k >= need) s_bad = 1;
+            else vals[1 + k] = (u >> 1) ^ (0ull - (u & 1));
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { uint32_t tot = 0; for (uint32_t w = 0; w < (blockDim.x >> 5); w++) tot += s_cnt[w]; s_ccarry += tot; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && (s_ccarry != need || (len > 0 && raw[len - 1] >= 0x80))) s_bad = 1;
+    __syncthreads();
+    if (s_bad) return false;
+    // (2) prefix sums, in place
+    for (int pass = t.mt == MT_NEAREST_DELTA2 ? 0 : 1; pass < 2; pass++) {
+        if (threadIdx.x == 0) s_carry = pass == 1 ? first : 0;
+        __syncthreads();
+        for (uint32_t base = 0; base < need; base += blockDim.x) {
+            const uint32_t i = base + threadIdx.x;
+            const unsigned long long v = i < need ? vals[1 + i] : 0;
+            const unsigned long long sum = cta_incl_scan_u64(v, s_warp, &s_carry);
+            if (i < need) vals[1 + i] = sum;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) vals[0] = first;
+    __syncthreads();
+    return true;
+}
+
+// _time filter on the blocks it only partly covers (the ACT_TIME work list of k_plan_leaf): decode, compare, one 32-bit half of a bitmap word per warp
+static __global__ void __launch_bounds__(256) k_time_match(BatchView B, long long mn, long long mx, const uint32_t* __restrict__ row_blocks, const uint32_t* __restrict__ work_count,
+                                                            unsigned long long* __restrict__ ts_vals, uint64_t* __restrict__ leaf_bm, unsigned long long* __restrict__ stats) {
+    const uint32_t nwork = work_count[WC_ROW];
+    for (uint32_t j = blockIdx.x; j < nwork; j += gridDim.x) {
+        const uint32_t b = row_blocks[j], R = B.blk_rows[b];
+        const uint64_t w0 = B.blk_word_off[b];
+        unsigned long long* vals = ts_vals + w0 * 64;
+        const bool ok = ts_decode_block(B, b, vals);
+        if (!ok && threadIdx.x == 0) atomicMax(&stats[ST_ERROR], (unsigned long long)ERR_BAD_TIMESTAMPS);
+        const uint32_t rows_padded = (R + 63) / 64 * 64;
+        for (uint32_t base = 0; base < rows_padded; base += blockDim.x) {
+            const uint32_t r = base + threadIdx.x;
+            const long long v = r < R ? (long long)vals[r] : 0;
+            const uint32_t m = __ballot_sync(0xffffffffu, ok && r < R && v >= mn && v <= mx);
+            if (lane_id() == 0 && r < rows_padded) ((uint32_t*)(leaf_bm + w0))[r >> 5] = m;   // little-endian halves of the 64-bit words
+        }
+        __syncthreads();
+    }
+}
+
+// ---- hit materialisation: the selected rows' values and timestamps as blockResult would yield them -------------------------------------------
+// (lib/logstorage/block_result.go:491-507 initTimestampsInternal, :529-591 the per-type readers behind getValues; values_encoder.go:1367-1422)
+// hit h = (hit_block[h], hit_row[h]) in block order, rows ascending (k_hits_compact2).
+static __global__ void k_hits_compact2(BatchView B, const uint64_t* __restrict__ reg, const uint64_t* __restrict__ offs, uint32_t* __restrict__ hits, uint32_t* __restrict__ hit_block, uint64_t cap) {
+    uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (b >= B.nblocks) return;
+    uint64_t lo = B.blk_word_off[b], hi = B.blk_word_off[b + 1];
+    uint64_t out = offs[b];
+    for (uint64_t w0 = lo; w0 < hi; w0 += 32) {
+        uint64_t w = w0 + lane_id();
+        uint64_t bits = w < hi ? reg[w] : 0;
+        uint32_t n = __popcll(bits), incl = n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane_id() >= d) incl += t; }
+        uint64_t pos = out + incl - n;
+        uint32_t rbase = (uint32_t)(w - lo) * 64;
+        while (bits) { int k = __ffsll((long long)bits) - 1; bits &= bits - 1; if (pos < cap) { hits[pos] = rbase + k; hit_block[pos] = b; } pos++; }
+        out += __shfl_sync(0xffffffffu, incl, 31);
+    }
+}
+// blocks with hits -> work list: mode 0 = into the lens list those whose column `slot` is a strings column with per-row lens items, mode 1 = into
+// the row list every block with hits (timestamps decode)
+static __global__ void k_hit_blocks_list(BatchView B, const uint32_t* __restrict__ counts, int slot, int mode, uint32_t* __restrict__ list, uint32_t* __restrict__ work_count) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B.nblocks || counts[b] == 0) return;
+    if (mode == 0) {
+        if (slot < 0) return;
+        const DevColumn& c = B.cols[(uint64_t)b * B.nfields + slot];
+        if (c.kind != COL_VALUES || c.vt != VT_STRING || c.lens_type >= 4 || c.data_const) return;
+        list[atomicAdd(&work_count[WC_LENS], 1u)] = b;
+    } else list[atomicAdd(&work_count[WC_ROW], 1u)] = b;
+}
+static __global__ void __launch_bounds__(256) k_ts_decode_list(BatchView B, const uint32_t* __restrict__ row_blocks, const uint32_t* __restrict__ work_count,
+                                                                unsigned long long* __restrict__ ts_vals, unsigned long long* __restrict__ stats) {
+    const uint32_t nwork = work_count[WC_ROW];
+    for (uint32_t j = blockIdx.x; j < nwork; j += gridDim.x) {
+        const uint32_t b = row_blocks[j];
+        const bool ok = B.ts && B.ts[b].mt && ts_decode_block(B, b, ts_vals + B.blk_word_off[b] * 64);
+        if (!ok && threadIdx.x == 0) atomicMax(&stats[ST_ERROR], (unsigned long long)(B.ts && B.ts[b].mt ? ERR_BAD_TIMESTAMPS : ERR_NO_TIMESTAMPS));
+        __syncthreads();
+    }
+}
+static __global__ void k_gather_ts(BatchView B, const uint32_t* __restrict__ hits, const uint32_t* __restrict__ hit_block, uint64_t nhits, const unsigned long long* __restrict__ ts_vals,
+                                   long long* __restrict__ out) {
+    const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h < nhits) out[h] = (long long)ts_vals[B.blk_word_off[hit_block[h]] * 64 + hits[h]];
+}
+// The value of column `slot` in one row as a string.  pass 0: lens[h] = its length; pass 1: the bytes go to out + offs[h].
+static __global__ void k_gather_values(BatchView B, int slot, const uint32_t* __restrict__ hits, const uint32_t* __restrict__ hit_block, uint64_t nhits, const uint32_t* __restrict__ row_off8,
+                                       int pass, uint32_t* __restrict__ lens_out, const uint64_t* __restrict__ offs, uint8_t* __restrict__ out, unsigned long long* __restrict__ stats) {
+    const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= nhits) return;
+    const uint32_t b = hit_block[h], r = hits[h];
+    const uint8_t* src = nullptr; uint32_t len = 0;
+    uint8_t buf[VL_FMT_F64_MAX];
+    if (slot >= 0) {
+        const DevColumn& c = B.cols[(uint64_t)b * B.nfields + slot];
+        if (c.kind == COL_CONST) { src = B.arena + c.meta_off; len = c.meta_len; }
+        else if (c.kind == COL_VALUES) {
+            const uint8_t* data = B.arena + c.data_off;
+            if (c.vt == VT_STRING) {
+                if (c.data_const) { src = data; len = (uint32_t)c.data_len; }
+                else if (c.lens_type >= 4) { len = c.lens_const; src = data + (uint64_t)r * len; }
+                else {
+                    const uint8_t* lens = B.arena + c.lens_off;
+                    uint32_t o = row_off8[(B.blk_word_off[b] << 3) + (r >> 3)];
+                    for (uint32_t q = r & ~7u; q < r; q++) o += row_len(c, lens, q);
+                    len = row_len(c, lens, r); src = data + o;
+                }
+                if ((uint64_t)(src - data) + len > c.data_len) { len = 0; atomicMax(&stats[ST_ERROR], (unsigned long long)ERR_LENS_MISMATCH); }
+            } else if (c.vt == VT_DICT) {
+                const uint32_t id = data[r];
+                if (id >= c.dict_len) atomicMax(&stats[ST_ERROR], (unsigned long long)ERR_DICT_INDEX);
+                else { const uint32_t* dof = (const uint32_t*)(B.arena + c.meta_off); src = B.arena + c.meta_off + 4 * (c.dict_len + 1) + dof[id]; len = dof[id + 1] - dof[id]; }
+            } else {
+                const uint32_t w = width_of_vt(c.vt);
+                const uint64_t raw = load_fixed_be(data + (uint64_t)r * w, w);
+                const int n = c.vt == VT_FLOAT64 ? fmt_f64(buf, raw) : encoded_to_string(c.vt, raw, buf);
+                src = buf; len = n > 0 ? (uint32_t)n : 0;
+            }
+        }
+    }
+    if (pass == 0) { lens_out[h] = len; return; }
+    uint8_t* d = out + offs[h];
+    for (uint32_t k = 0; k < len; k++) d[k] = src[k];
+}
+// exclusive scan of u32 lengths into u64 offsets (offs[n] = total): tile sums, scan of the tile sums by one CTA, per-tile prefixes
+#define VL_SCAN_TILE 2048
+static __global__ void __launch_bounds__(256) k_scan_tiles(const uint32_t* __restrict__ v, uint64_t n, unsigned long long* __restrict__ tile_sums, unsigned long long* __restrict__ offs, int pass) {
+    __shared__ unsigned long long s_w[8];
+    const uint64_t base = (uint64_t)blockIdx.x * VL_SCAN_TILE + (uint64_t)threadIdx.x * 8;
+    unsigned long long x[8], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { x[k] = base + k < n ? v[base + k] : 0; sum += x[k]; }
+    unsigned long long incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d); if (lane_id() >= d) incl += t; }
+    if (lane_id() == 31) s_w[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    unsigned long long pre = 0, tot = 0;
+    for (uint32_t k = 0; k < 8; k++) { if (k < (threadIdx.x >> 5)) pre += s_w[k]; tot += s_w[k]; }
+    if (pass == 0) { if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot; return; }
+    unsigned long long o = tile_sums[blockIdx.x] + pre + incl - sum;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { if (base + k < n) offs[base + k] = o; o += x[k]; }
+}
+static __global__ void k_scan_tile_sums(unsigned long long* __restrict__ tile_sums, uint64_t ntiles, unsigned long long* __restrict__ total) {   // single CTA, exclusive, in place
+    __shared__ unsigned long long s[1024];
+    __shared__ unsigned long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint64_t base = 0; base < ntiles; base += blockDim.x) {
+        const uint64_t i = base + threadIdx.x;
+        const unsigned long long v = i < ntiles ? tile_sums[i] : 0;
+        s[threadIdx.x] = v;
+        __syncthreads();
+        for (uint32_t d = 1; d < blockDim.x; d <<= 1) { unsigned long long a = threadIdx.x >= d ? s[threadIdx.x - d] : 0; __syncthreads(); s[threadIdx.x] += a; __syncthreads(); }
+        if (i < ntiles) tile_sums[i] = carry + s[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry += s[threadIdx.x];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
 }
 
 // ---- digest of the result bitmaps (bench / tests; the oracle computes the same over its own bitmaps, oracle/vlo_api.cpp vlo_scan_generated) -------

@@ -229,6 +229,10 @@ public:
             }
             if (ix.n) throw BadInput("unexpected non-empty tail left after unmarshaling columnsHeaderIndex");
             vlscan_block blk; memset(&blk, 0, sizeof blk); blk.rows = bh.rowsCount; blk.ncols = (uint32_t)(out.cols.size() - first_col.back());
+            // the timestamps column travels with the block: `_time` filters that only partly cover it and vlscan_gather_timestamps need it
+            if (bh.tsSize > kMaxTimestampsBlockSize) throw BadInput("timestamps block size is too big");   // getTimestamps block_search.go:490-493
+            blk.ts_marshal_type = bh.tsMarshalType; blk.timestamps = timestamps_.at(bh.tsOffset, bh.tsSize, "a timestamps block"); blk.timestamps_len = bh.tsSize;
+            blk.min_timestamp = bh.minTimestamp; blk.max_timestamp = bh.maxTimestamp;
             out.blocks.push_back(blk); out.source.push_back(b);
         }
         for (size_t i = 0; i < out.blocks.size(); i++) out.blocks[i].cols = out.cols.data() + first_col[i];

@@ -422,6 +422,16 @@ class ProgramBuilder {
             P.leaf_tokens[l].clear();
             P.nodes[id].leaf = l; break;
         }
+        case F_TIME: {   // filter_time.go:14-23: [minTimestamp, maxTimestamp] in nanoseconds, both ends inclusive; no field (the block's timestamps column)
+            if (n_ - i_ < 16) throw ProgError("truncated filter tree");
+            uint64_t mn = 0, mx = 0;
+            for (int k = 0; k < 8; k++) { mn |= (uint64_t)p_[i_ + k] << (8 * k); mx |= (uint64_t)p_[i_ + 8 + k] << (8 * k); }
+            i_ += 16;
+            DevLeaf L; memset(&L, 0, sizeof L);
+            L.kind = F_TIME; L.field = -1; L.regex = -1; L.aux0 = mn; L.aux1 = mx; L.always_none = (int64_t)mn > (int64_t)mx; L.str_strategy = STR_ROW;
+            P.leaves.push_back(L); P.leaf_tokens.push_back({});
+            P.nodes[id].leaf = (int)P.leaves.size() - 1; break;
+        }
         case F_AND: case F_OR: { uint64_t c = varuint(); if (c > 100000) throw ProgError("too many children"); for (uint64_t k = 0; k < c; k++) { int ch = node(); P.nodes[id].kids.push_back(ch); } break; }
         case F_NOT: { int ch = node(); P.nodes[id].kids.push_back(ch); break; }
         default: throw ProgError("unknown filter kind " + std::to_string(kind));

@@ -32,6 +32,16 @@ struct DevColumn {
     uint32_t pad2;
 };
 
+// The timestamps column of one block of a resident batch: raw varint bytes in the arena (ZSTD types already inflated) + timestampsHeader
+struct DevTimestamps {
+    uint64_t off;          // arena offset of the encoded deltas
+    uint32_t len;
+    uint8_t mt;            // 0 none, else the plain marshal type: 2 delta const, 3 const, 5 nearest delta2, 6 nearest delta (encoding.go:20-43)
+    uint8_t pad[3];
+    int64_t first, max;    // minTimestamp (= first value), maxTimestamp
+};
+enum { MT_ZSTD_NEAREST_DELTA2 = 1, MT_DELTA_CONST = 2, MT_CONST = 3, MT_ZSTD_NEAREST_DELTA = 4, MT_NEAREST_DELTA2 = 5, MT_NEAREST_DELTA = 6 };
+
 struct TypedNeedle {       // result of parsing a needle for one valueType (filter_exact.go:237-354, in_values.go:141-315)
     uint64_t val;          // value in the column's comparison domain: uint / zig-zag int64 / float64 bits / ipv4 / iso8601 ns
     int64_t sval;          // signed view for the min/max range check of int64 / iso8601; float64: unused
@@ -104,7 +114,8 @@ enum { STR_ROW = 0, STR_SCAN = 1, STR_ALL = 2 };
 enum { ACT_NONE = 0, ACT_ALL = 1, ACT_DICT = 2, ACT_SCAN = 3, ACT_FIXED_EQ = 4, ACT_FIXED_IN = 5,
        ACT_ROW = 6,         // per-row matcher: the leaf's string predicate on the value (typed values through their text)
        ACT_ROW_EQ = 7,      // per-row matcher: binary equality with the payload (typed column whose layout is not the fixed-width one)
-       ACT_ROW_IN = 8 };    // per-row matcher: membership in the leaf's typed value set
+       ACT_ROW_IN = 8,      // per-row matcher: membership in the leaf's typed value set
+       ACT_TIME = 9 };      // _time filter that partly overlaps the block: decode the timestamps, compare per row
 // scan verifier modes of the row-agnostic substring kernel
 enum { SCAN_PHRASE = 0, SCAN_PREFIX = 1, SCAN_CONTAINS = 2, SCAN_RX_DOTPLUS = 3, SCAN_RX_SUFFIX = 4, SCAN_RX_TAIL = 5 };
 

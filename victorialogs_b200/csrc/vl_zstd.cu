@@ -163,7 +163,9 @@ void ZstdJob::run(vlscan_ctx* ctx, const uint8_t* zsrc, uint8_t* arena) {
     static const char* phase_name[6] = {"huf_build", "huf_decode", "fse_build", "seq_decode", "seq_resolve", "execute"};
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> marks;
     int phase = 0;
-    cudaStream_t xs = D.xstream;
+    // VLSCAN_ZSTD_OVERLAP=0 (tuning only) keeps resolve + execute on the ctx stream
+    static const bool overlap = [] { const char* e = getenv("VLSCAN_ZSTD_OVERLAP"); return !e || atoi(e) != 0; }();
+    cudaStream_t xs = overlap ? D.xstream : st;
     cudaStream_t cur_stream = st;
     auto begin = [&](int p) { phase = p; if (dbg) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, cur_stream); marks.push_back({p, {a, b}}); } };
     auto launched = [&] { ctx->launches++; VL_CUDA(cudaGetLastError()); if (dbg) cudaEventRecord(marks.back().second.second, cur_stream); };

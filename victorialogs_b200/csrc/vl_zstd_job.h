@@ -5,6 +5,7 @@
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <array>
@@ -28,8 +29,11 @@ using namespace zs;
 // Round 2: a quarter of the round-1 limits.  The C2 batch (667 M sequences) becomes 11 groups instead of 3: the first one is decoded after a
 // tenth of the compressed bytes has arrived, the execute kernel of group g runs beside the entropy kernels of group g + 1 (second stream,
 // vl_zstd.cu), and the scratch (two copies of literals + sequence records) shrinks from 6 GB to 3 GB.
-const uint64_t kGroupLits = 512ull << 20, kGroupSeqs = 64ull << 20;
-const uint32_t kGroupSlots = 32u << 10;
+// VLSCAN_ZSTD_GROUP_SCALE (tuning only): multiplies the three limits; 4 restores the round-1 ones.
+inline uint64_t group_scale() { static const uint64_t v = [] { const char* e = getenv("VLSCAN_ZSTD_GROUP_SCALE"); long x = e ? atol(e) : 1; return (uint64_t)(x < 1 ? 1 : x > 64 ? 64 : x); }(); return v; }
+#define kGroupLits ((512ull << 20) * group_scale())
+#define kGroupSeqs ((64ull << 20) * group_scale())
+#define kGroupSlots ((uint32_t)((32u << 10) * group_scale()))
 
 struct Group { uint32_t frame_lo, frame_hi; uint32_t huf_lo, huf_hi, lit_lo, lit_hi, seq_lo, seq_hi, ord_lo, ord_hi; };
 

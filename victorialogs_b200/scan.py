@@ -48,7 +48,8 @@ class CColumn(C.Structure):
 
 
 class CBlock(C.Structure):
-    _fields_ = [("rows", C.c_uint64), ("ncols", C.c_uint32), ("reserved", C.c_uint32), ("cols", C.POINTER(CColumn))]
+    _fields_ = [("rows", C.c_uint64), ("ncols", C.c_uint32), ("ts_marshal_type", C.c_uint32), ("cols", C.POINTER(CColumn)),
+                ("timestamps", C.c_void_p), ("timestamps_len", C.c_uint64), ("min_timestamp", C.c_int64), ("max_timestamp", C.c_int64)]
 
 
 class CStats(C.Structure):
@@ -70,7 +71,7 @@ EXPORTS = ["vlscan_device_count", "vlscan_ctx_create", "vlscan_ctx_free", "vlsca
            "vlscan_batch_upload", "vlscan_batch_free", "vlscan_batch_nblocks", "vlscan_batch_rows", "vlscan_batch_words", "vlscan_batch_device_bytes",
            "vlscan_batch_generate", "vlscan_batch_download", "vlscan_host_blocks_get", "vlscan_host_blocks_field", "vlscan_host_blocks_bytes",
            "vlscan_host_blocks_free", "vlscan_host_blocks_compress", "vlscan_zstd_decompress", "vlscan_zstd_inspect", "vlscan_zstd_walk_digest", "vlscan_part_open", "vlscan_part_free", "vlscan_part_header", "vlscan_part_nblocks", "vlscan_part_block_header", "vlscan_part_timestamps",
-           "vlscan_part_ncolumn_names", "vlscan_part_column_name", "vlscan_part_blocks", "vlscan_host_blocks_source", "vlscan_scan_resident", "vlscan_last_scan_stats", "vlscan_fetch_results", "vlscan_fetch_hits", "vlscan_result_digest", "vlscan_result_device_ptrs", "vlscan_scan_batch"]
+           "vlscan_part_ncolumn_names", "vlscan_part_column_name", "vlscan_part_blocks", "vlscan_host_blocks_source", "vlscan_scan_resident", "vlscan_last_scan_stats", "vlscan_fetch_results", "vlscan_fetch_hits", "vlscan_gather_timestamps", "vlscan_gather_values", "vlscan_result_digest", "vlscan_result_device_ptrs", "vlscan_scan_batch"]
 
 
 def lib_path():
@@ -256,6 +257,10 @@ class Filter:
         return Filter(bytes([F_CONTAINS_ANY]) + _bytes(field) + _varuint(len(values)) + b"".join(_bytes(v) for v in values), "%r:contains_any(%r)" % (field, values))
 
     @staticmethod
+    def time(min_timestamp, max_timestamp):   # &filterTime{minTimestamp, maxTimestamp}      `_time:[a, b]` (nanoseconds, inclusive)
+        return Filter(bytes([F_TIME]) + int(min_timestamp).to_bytes(8, "little", signed=True) + int(max_timestamp).to_bytes(8, "little", signed=True), "_time:[%d, %d]" % (min_timestamp, max_timestamp))
+
+    @staticmethod
     def and_(filters):
         return Filter(bytes([F_AND]) + _varuint(len(filters)) + b"".join(f.blob for f in filters), "(" + " AND ".join(f.desc for f in filters) + ")")
 
@@ -308,7 +313,8 @@ class HostBlocks:
         """blocks: list of dict(rows=int, columns=[dict(field=name, kind='const'|'values', ...)])
 
         values columns: value_type, min_value, max_value, dict (list of bytes), bloom (bytes) and either
-        values_block (bytes, on-disk stage) or lens_items + data (decoded stage)."""
+        values_block (bytes, on-disk stage) or lens_items + data (decoded stage).
+        A block may carry its timestamps column: timestamps=(encoded bytes, marshalType, minTimestamp, maxTimestamp)."""
         self.field_names = [_b(f) for f in field_names]
         fidx = {f: i for i, f in enumerate(self.field_names)}
         self._keep = []
@@ -360,6 +366,10 @@ class HostBlocks:
                     c.bloom, c.bloom_len = buf(col.get("bloom", b""))
                 k += 1
             self.blocks[bi].rows = blk["rows"]
+            if blk.get("timestamps") is not None:
+                data, mt, mn, mx = blk["timestamps"]
+                self.blocks[bi].timestamps, self.blocks[bi].timestamps_len = buf(data)
+                self.blocks[bi].ts_marshal_type, self.blocks[bi].min_timestamp, self.blocks[bi].max_timestamp = mt, mn, mx
             self.blocks[bi].ncols = k - first
             self.blocks[bi].cols = C.cast(C.byref(self.cols, first * C.sizeof(CColumn)), C.POINTER(CColumn))
         self.rows = [b["rows"] for b in blocks]
@@ -651,6 +661,37 @@ class Ctx:
         offs = np.zeros(batch.nblocks + 1, dtype=np.uint64)
         self._check(lib().vlscan_fetch_hits(self.h, hits.ctypes.data_as(C.c_void_p), C.c_uint64(cap), offs.ctypes.data_as(C.c_void_p)))
         return hits[:int(offs[-1])], offs
+
+    def gather_timestamps(self, batch=None):
+        """`_time` of the selected rows of the last scan, block after block (vlscan_gather_timestamps) -> (int64 array, hit offsets per block)"""
+        batch = batch or self._last
+        cap = max(int(batch.rows), 1)
+        ts = np.zeros(cap, dtype=np.int64)
+        offs = np.zeros(batch.nblocks + 1, dtype=np.uint64)
+        self._check(lib().vlscan_gather_timestamps(self.h, ts.ctypes.data_as(C.c_void_p), C.c_uint64(cap), offs.ctypes.data_as(C.c_void_p)))
+        return ts[:int(offs[-1])], offs
+
+    def gather_values(self, field, batch=None):
+        """the value of `field` in every selected row of the last scan as bytes (vlscan_gather_values) -> (list of bytes, hit offsets per block)"""
+        batch = batch or self._last
+        field = _b(field)
+        hoffs = np.zeros(batch.nblocks + 1, dtype=np.uint64)
+        nrows = max(int(batch.rows), 1)
+        voffs = np.zeros(nrows + 1, dtype=np.uint64)
+        total = C.c_uint64()
+        cap = 1 << 16
+        for _ in range(2):
+            out = np.zeros(cap, dtype=np.uint8)
+            rc = lib().vlscan_gather_values(self.h, field, C.c_size_t(len(field)), out.ctypes.data_as(C.c_void_p), C.c_uint64(cap), voffs.ctypes.data_as(C.c_void_p), C.c_uint64(nrows),
+                                            C.byref(total), hoffs.ctypes.data_as(C.c_void_p))
+            if rc and total.value > cap:
+                cap = total.value
+                continue
+            self._check(rc)
+            break
+        n = int(hoffs[-1])
+        raw = out.tobytes()
+        return [raw[int(voffs[i]):int(voffs[i + 1])] for i in range(n)], hoffs
 
     def result_digest(self, block_lo, block_hi, key_base=0):
         """xor over blocks of XXH64(bitmap words) * (2 * (key_base + block) + 1) of the last scan, computed on the device (vlscan_result_digest)"""
