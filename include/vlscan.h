@@ -305,6 +305,12 @@ int vlscan_gather_values(vlscan_ctx* ctx, const char* field, size_t field_len, u
  * bitmaps, so a bench can check a billion-row scan against the CPU restatement on any block range without moving the bitmaps.  The batch of the
  * last scan must still be alive (like for vlscan_fetch_hits: both read its block table on the device). */
 int vlscan_result_digest(vlscan_ctx* ctx, uint64_t block_lo, uint64_t block_hi, uint64_t key_base, uint64_t* out_digest);
+/* Multi-GPU hosts (one process, several devices): blocks are independent, so the Go side gives every GPU its own vlscan_ctx
+ * (vlscan_ctx_create(worker_id % vlscan_device_count())) and its own share of the block list; nothing is exchanged on the data path.  The only
+ * reduction of a query like `| stats count()` is this sum of the four match counters {rows, rows_matched, blocks_matched, values_bytes} of the
+ * last scan of every ctx (it synchronises each ctx's stream).  Multi-process jobs (bench.py: one rank per GPU) reduce the same vector with
+ * one NCCL all-reduce instead (vlscan_result_device_ptrs gives its device address). */
+int vlscan_totals_sum(vlscan_ctx* const* ctxs, int nctx, uint64_t out4[4]);
 /* Device pointers of the last scan's results (bench / multi-GPU reduce): bitmap words, per-block counts,
  * and a 4 x u64 totals vector {rows, rows_matched, blocks_matched, values_bytes}. */
 int vlscan_result_device_ptrs(vlscan_ctx* ctx, void** bitmap_words, void** match_counts, void** totals4);

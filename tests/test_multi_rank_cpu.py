@@ -73,3 +73,20 @@ def test_two_ranks_reduce_to_the_single_process_answer():
     assert red0 == red1 == whole
     assert [a + b for a, b in zip(loc0, loc1)] == whole
     assert (before0, before1) == (0, loc0[1]) and tot0 == tot1 == whole[1]
+
+
+def test_shard_ranges_by_bytes():
+    """Ranges are contiguous, cover every block once, and no rank carries more than its share plus one block."""
+    import random
+    from victorialogs_b200 import shard
+    rng = random.Random(4)
+    for trial in range(200):
+        n, world = rng.choice([0, 1, 7, 64, 1000]), rng.choice([1, 2, 4, 8])
+        sizes = [rng.choice([1, 10, 1000, 250000]) for _ in range(n)]
+        ranges = shard.shard_ranges_by_bytes(sizes, world)
+        assert len(ranges) == world and ranges[0][0] == 0 and ranges[-1][1] == n
+        assert all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
+        if n:
+            share = sum(sizes) / world
+            for lo, hi in ranges:
+                assert sum(sizes[lo:hi]) <= share + max(sizes) + 1e-9

@@ -192,9 +192,16 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
     // compressed staging buffer is being filled, `zmarks` records (end offset, event) pairs so that the decoder of a launch group can
     // start as soon as the bytes of that group have landed, while later bytes are still in flight.
     cudaStream_t cs = ctx->copy_stream;
+    // every event of this upload lives in `events`: destroyed when the function is left, by return or by exception (a worker that keeps
+    // hitting malformed parts must not leak one event per batch)
+    struct EventBag {
+        std::vector<cudaEvent_t> all;
+        cudaEvent_t make() { cudaEvent_t e; VL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); all.push_back(e); return e; }
+        ~EventBag() { for (cudaEvent_t e : all) cudaEventDestroy(e); }
+    } events;
     std::vector<std::pair<uint64_t, cudaEvent_t>> zmarks;
     bool marking = false;
-    auto mark = [&](uint64_t end_off) { cudaEvent_t e; VL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); VL_CUDA(cudaEventRecord(e, cs)); zmarks.push_back({end_off, e}); };
+    auto mark = [&](uint64_t end_off) { cudaEvent_t e = events.make(); VL_CUDA(cudaEventRecord(e, cs)); zmarks.push_back({end_off, e}); };
     auto flush = [&]() {
         if (!chunk_open || !fill) { chunk_open = false; fill = 0; return; }
         VL_CUDA(cudaMemcpyAsync(dev_base + chunk_dst, stage + (size_t)cur * CH, fill, cudaMemcpyHostToDevice, cs));
@@ -204,10 +211,21 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
         VL_CUDA(cudaEventSynchronize(evs[cur]));
     };
     auto is_pinned = [&](const void* p) { cudaPointerAttributes a; if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; } return a.type == cudaMemoryTypeHost; };
+    // Is [p, p + len) inside ONE page-locked allocation?  The runtime API only classifies single addresses; the driver knows the range of the
+    // allocation an address belongs to (cuPointerGetAttribute RANGE_START_ADDR / RANGE_SIZE).  libcuda is always there when a device is.
+    auto pinned_range_covers = [&](const uint8_t* p, uint64_t len) -> bool {
+        typedef int (*attr_fn)(void*, int, unsigned long long);
+        static const attr_fn fn = [] { void* h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL); return h ? (attr_fn)dlsym(h, "cuPointerGetAttribute") : (attr_fn) nullptr; }();
+        if (!is_pinned(p)) return false;
+        if (!fn) return len <= 1 || (len <= 4096 && is_pinned(p + len - 1));   // no driver entry point: only what single-address checks can vouch for
+        unsigned long long base = 0; size_t size = 0;
+        if (fn(&base, 11 /* CU_POINTER_ATTRIBUTE_RANGE_START_ADDR */, (unsigned long long)(uintptr_t)p) != 0 || fn(&size, 12 /* CU_POINTER_ATTRIBUTE_RANGE_SIZE */, (unsigned long long)(uintptr_t)p) != 0) return false;
+        return (unsigned long long)(uintptr_t)p >= base && (unsigned long long)(uintptr_t)p + len <= base + size;
+    };
     auto need_stage = [&]() {
         if (stage) return;
         stage = (uint8_t*)ctx->ensure_pinned(2 * CH);
-        for (int k = 0; k < 2; k++) { VL_CUDA(cudaEventCreateWithFlags(&evs[k], cudaEventDisableTiming)); VL_CUDA(cudaEventRecord(evs[k], cs)); }
+        for (int k = 0; k < 2; k++) { evs[k] = events.make(); VL_CUDA(cudaEventRecord(evs[k], cs)); }
     };
     bool all_pinned = true;
     auto copy_pieces = [&](const std::vector<Piece>& pieces, uint8_t* base) {
@@ -218,7 +236,9 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
         size_t j = i;
         while (j + 1 < pieces.size() && pieces[j + 1].src > pieces[j].src && pieces[j + 1].src - pieces[i].src == (ptrdiff_t)(pieces[j + 1].dst - pieces[i].dst)) j++;
         uint64_t run_len = (pieces[j].dst - pieces[i].dst) + pieces[j].len;
-        if (is_pinned(pieces[i].src) && is_pinned(pieces[j].src + pieces[j].len - 1)) {
+        // one DMA for the whole run (gaps included) only when the run lies inside a single page-locked allocation: two pinned buffers that
+        // merely line up could have pageable memory between them
+        if (pinned_range_covers(pieces[i].src, run_len)) {
             // page-locked caller memory: one DMA for the whole run, gaps (alignment slack) included
             flush();
             // (split at piece boundaries every ~128 MB so that consumers can be released chunk by chunk)
@@ -383,13 +403,11 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
     out->arena.ensure(out->arena_bytes);
     t_alloc = now();
     // the arena is cleared on the compute stream; the copy stream takes over from there
-    cudaEvent_t ev_cleared = nullptr, ev_copied = nullptr;
-    VL_CUDA(cudaEventCreateWithFlags(&ev_cleared, cudaEventDisableTiming)); VL_CUDA(cudaEventCreateWithFlags(&ev_copied, cudaEventDisableTiming));
+    cudaEvent_t ev_cleared = events.make(), ev_copied = events.make();
     VL_CUDA(cudaMemsetAsync(out->arena.p, 0, out->arena_bytes, ctx->stream));
     VL_CUDA(cudaEventRecord(ev_cleared, ctx->stream));
     VL_CUDA(cudaStreamWaitEvent(cs, ev_cleared, 0));
     copy_pieces(pieces, out->arena.as<uint8_t>());
-    for (int k = 0; k < 2; k++) if (evs[k]) cudaEventDestroy(evs[k]);
     out->cols.ensure(std::max<size_t>(cols.size() * sizeof(DevColumn), 16));
     if (!cols.empty()) VL_CUDA(cudaMemcpyAsync(out->cols.p, cols.data(), cols.size() * sizeof(DevColumn), cudaMemcpyHostToDevice, cs));
     out->has_ts = any_ts;
@@ -431,8 +449,6 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
     if (dbg) { VL_CUDA(cudaStreamSynchronize(ctx->stream)); t_copy = now(); }
     if (nfields) out->note_columns(cols);
     finish_batch_layout(ctx, out, rows);   // synchronises the stream => `owned`, `cols`, staging are safe to drop
-    for (auto& m : zmarks) cudaEventDestroy(m.second);
-    cudaEventDestroy(ev_cleared); cudaEventDestroy(ev_copied);
     if (dbg) fprintf(stderr, "[vlscan upload] blocks=%llu arena=%.1f MB h2d=%.1f MB pieces=%zu+%zu pinned=%d: describe %.1f ms, alloc %.1f ms, copy %.1f ms (%.1f GB/s), "
                              "zstd %llu frames / %llu blocks / %llu sequences: enqueue %.1f ms, decode %.1f ms; layout %.1f ms\n", (unsigned long long)nblocks,
                      out->arena_bytes / 1e6, h2d / 1e6, pieces.size(), zpieces.size(), (int)all_pinned, 1e3 * (t_desc - t_start), 1e3 * (t_alloc - t_desc), 1e3 * (t_h2d - t_alloc), h2d / 1e9 / std::max(t_h2d - t_alloc, 1e-9),
@@ -1185,6 +1201,23 @@ int vlscan_result_digest(vlscan_ctx* ctx, uint64_t block_lo, uint64_t block_hi, 
         VL_CUDA(cudaMemcpyAsync(out_digest, ctx->hit_offs.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
         VL_CUDA(cudaStreamSynchronize(ctx->stream));
     });
+}
+
+int vlscan_totals_sum(vlscan_ctx* const* ctxs, int nctx, uint64_t out4[4]) {
+    out4[0] = out4[1] = out4[2] = out4[3] = 0;
+    for (int i = 0; i < nctx; i++) {
+        vlscan_ctx* ctx = ctxs[i];
+        int rc = guarded(ctx, [&] {
+            if (!ctx->has_result) throw BadInput("no scan result on this ctx");
+            VL_CUDA(cudaSetDevice(ctx->device));
+            unsigned long long t[4];
+            VL_CUDA(cudaMemcpyAsync(t, ctx->totals.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
+            VL_CUDA(cudaStreamSynchronize(ctx->stream));
+            for (int k = 0; k < 4; k++) out4[k] += t[k];
+        });
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 int vlscan_result_device_ptrs(vlscan_ctx* ctx, void** bitmap_words, void** match_counts, void** totals4) {

@@ -71,7 +71,7 @@ EXPORTS = ["vlscan_device_count", "vlscan_ctx_create", "vlscan_ctx_free", "vlsca
            "vlscan_batch_upload", "vlscan_batch_free", "vlscan_batch_nblocks", "vlscan_batch_rows", "vlscan_batch_words", "vlscan_batch_device_bytes",
            "vlscan_batch_generate", "vlscan_batch_download", "vlscan_host_blocks_get", "vlscan_host_blocks_field", "vlscan_host_blocks_bytes",
            "vlscan_host_blocks_free", "vlscan_host_blocks_compress", "vlscan_zstd_decompress", "vlscan_zstd_inspect", "vlscan_zstd_walk_digest", "vlscan_part_open", "vlscan_part_free", "vlscan_part_header", "vlscan_part_nblocks", "vlscan_part_block_header", "vlscan_part_timestamps",
-           "vlscan_part_ncolumn_names", "vlscan_part_column_name", "vlscan_part_blocks", "vlscan_host_blocks_source", "vlscan_scan_resident", "vlscan_last_scan_stats", "vlscan_fetch_results", "vlscan_fetch_hits", "vlscan_gather_timestamps", "vlscan_gather_values", "vlscan_result_digest", "vlscan_result_device_ptrs", "vlscan_scan_batch"]
+           "vlscan_part_ncolumn_names", "vlscan_part_column_name", "vlscan_part_blocks", "vlscan_host_blocks_source", "vlscan_scan_resident", "vlscan_last_scan_stats", "vlscan_fetch_results", "vlscan_fetch_hits", "vlscan_gather_timestamps", "vlscan_gather_values", "vlscan_result_digest", "vlscan_totals_sum", "vlscan_result_device_ptrs", "vlscan_scan_batch"]
 
 
 def lib_path():
@@ -562,6 +562,16 @@ def search_part(ctx, part, flt, min_timestamp=-(1 << 63), max_timestamp=(1 << 63
                 bh = part.block_header(src)
                 hits.append((src, w.copy(), int(c), min_timestamp <= bh["min_timestamp"] and bh["max_timestamp"] <= max_timestamp))
     return hits
+
+
+def totals_sum(ctxs):
+    """{rows, rows_matched, blocks_matched, values_bytes} of the last scans of several contexts (one per GPU), summed: vlscan_totals_sum"""
+    arr = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+    out = (C.c_uint64 * 4)()
+    rc = lib().vlscan_totals_sum(arr, C.c_int(len(ctxs)), out)
+    if rc:
+        raise VlscanError(rc, lib().vlscan_last_error(None).decode("utf-8", "replace"))
+    return [int(x) for x in out]
 
 
 class Batch:

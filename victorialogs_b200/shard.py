@@ -13,6 +13,23 @@ def shard_range(nblocks, world, rank):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def shard_ranges_by_bytes(block_bytes, world):
+    """contiguous block ranges [lo, hi) for every rank, balanced by the decoded bytes of the blocks rather than by their number:
+    rank r ends at the first block where the running sum reaches (r + 1) / world of the total."""
+    total = float(sum(block_bytes))
+    out, lo, acc = [], 0, 0.0
+    n = len(block_bytes)
+    for r in range(world):
+        hi = lo
+        target = total * (r + 1) / world
+        while hi < n and (r == world - 1 or acc + block_bytes[hi] / 2.0 < target):
+            acc += block_bytes[hi]
+            hi += 1
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
 def reduce_counters(counters, group=None):
     """sum {rows, rows_matched, blocks_matched, values_bytes} over the ranks; `counters` is a 4-element int64 tensor (in place)"""
     assert counters.dtype == torch.int64 and counters.numel() == 4
