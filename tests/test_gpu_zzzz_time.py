@@ -97,7 +97,7 @@ def test_all_marshal_types_and_shapes(env):
 
 def test_malformed_timestamps_are_rejected(env):
     oracle, vs, pu, ctx = env
-    ts = [10 + 3 * i + (i % 5) for i in range(500)]
+    ts = [10 + 7 * i + (i % 5) for i in range(500)]
     blk = oracle.Block.from_columns([("x", [b"v%d" % i for i in range(500)])]).set_timestamps(ts)
     d = pu.oracle_block_to_desc(blk)
     data, mt, mn, mx = d["timestamps"]

@@ -188,6 +188,15 @@ static __device__ __forceinline__ bool block_alive_warp(const uint64_t* __restri
     for (uint64_t w = lo + lane_id(); w < hi; w += 32) any |= reg[w] != 0;
     return __any_sync(0xffffffffu, any);
 }
+// number of rows still selected in block b (bitmap.onesCount); uniform result
+static __device__ __forceinline__ uint32_t block_ones_warp(const uint64_t* __restrict__ reg, const BatchView& B, uint32_t b) {
+    const uint64_t lo = B.blk_word_off[b], hi = B.blk_word_off[b + 1];
+    uint32_t n = 0;
+    for (uint64_t w = lo + lane_id(); w < hi; w += 32) n += __popcll(reg[w]);
+#pragma unroll
+    for (int d = 16; d; d >>= 1) n += __shfl_xor_sync(0xffffffffu, n, d);
+    return n;
+}
 static __global__ void k_andnot(uint64_t* __restrict__ a, const uint64_t* __restrict__ b, uint64_t n) {   // bitmap.andNot bitmap.go:99-111
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) a[i] &= ~b[i];
@@ -261,7 +270,8 @@ static __global__ void __launch_bounds__(VL_PLAN_WARPS * 32) k_plan_leaf(DevProg
     unsigned long long bloom_bytes = 0, values_bytes = 0, scan_bytes = 0; int err = 0;
     uint32_t need_lens = 0, need_row = 0, ntiles = 0;
     const bool valid = b < B.nblocks;
-    const bool alive = valid && block_alive_warp(reg, B, b);
+    const uint32_t ones = valid ? block_ones_warp(reg, B, b) : 0;
+    const bool alive = ones != 0;
     if (alive && L.kind == F_NOOP) act = ACT_ALL;
     else if (alive) {
     act = ACT_ALL;
@@ -339,6 +349,9 @@ static __global__ void __launch_bounds__(VL_PLAN_WARPS * 32) k_plan_leaf(DevProg
                 // short rows (ids, paths, codes ...): candidates of the row-agnostic scan become dense relative to the bytes streamed and
                 // each costs a warp-wide verification, so such blocks take the per-row matcher instead (same predicate, same result)
                 if (act == ACT_SCAN && c->data_len < (uint64_t)VL_SHORT_ROW_BYTES * rows) act = ACT_ROW;
+                // few rows of the block are still selected (an earlier filter of an AND chain was selective): visit just those, like
+                // bm.forEachSetBit does, instead of streaming the whole block
+                if (act == ACT_SCAN && (uint64_t)ones * 16 < rows) act = ACT_ROW;
             }
         } else {
             // numeric / ipv4 / iso8601 columns
@@ -826,13 +839,14 @@ static __global__ void __launch_bounds__(VL_SCAN_THREADS, 5) k_substr_scan(const
 
 // ---- dict LUT / fixed-width equality / typed in(): one thread per bitmap word ---------------------------------------------------------------
 // matchEncodedValuesDict filter_phrase.go:272-289, matchBinaryValue filter_exact.go:356-364, matchAnyValue filter_in.go:187-200
-static __global__ void k_word_match(DevProgram P, BatchView B, uint32_t leaf_idx, int slot, const uint8_t* __restrict__ action, const uint64_t* __restrict__ payload,
+static __global__ void k_word_match(DevProgram P, BatchView B, uint32_t leaf_idx, int slot, const uint8_t* __restrict__ action, const uint64_t* __restrict__ payload, const uint64_t* __restrict__ reg,
                              uint64_t* __restrict__ leaf_bm, unsigned long long* __restrict__ stats) {
     uint64_t gw = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gw >= B.nwords) return;
     uint32_t b = B.word_block[gw];
     uint8_t act = action[b];
     if (act != ACT_DICT && act != ACT_FIXED_EQ && act != ACT_FIXED_IN) return;
+    if (!reg[gw]) { leaf_bm[gw] = 0; return; }   // no selected row left in these 64 (bm.forEachSetBit visits none)
     const DevColumn& c = B.cols[(uint64_t)b * B.nfields + slot];
     const DevLeaf& L = P.leaves[leaf_idx];
     uint32_t rows = B.blk_rows[b];
@@ -869,7 +883,7 @@ static __global__ void k_word_match(DevProgram P, BatchView B, uint32_t leaf_idx
 // exact / in() / regexp-without-literal-prefix on string columns; numeric columns that must be formatted to text first.
 // Persistent grid over the ACT_ROW work list of k_plan_leaf: work item j = block work_blocks[j]; its bitmap words are dealt out to the CTA's warps.
 static __global__ void k_row_match(DevProgram P, BatchView B, uint32_t leaf_idx, int slot, const uint32_t* __restrict__ work_blocks,
-                                   const uint32_t* __restrict__ work_count, const uint8_t* __restrict__ action, const uint64_t* __restrict__ payload,
+                                   const uint32_t* __restrict__ work_count, const uint8_t* __restrict__ action, const uint64_t* __restrict__ payload, const uint64_t* __restrict__ reg,
                                    const uint32_t* __restrict__ row_off8, uint64_t* __restrict__ leaf_bm) {
   const uint32_t nwork = work_count[WC_ROW];
   const DevLeaf& L = P.leaves[leaf_idx];
@@ -880,6 +894,10 @@ static __global__ void k_row_match(DevProgram P, BatchView B, uint32_t leaf_idx,
     const uint8_t act = action[b]; const uint64_t pay = payload[b];
     const uint64_t w_lo = B.blk_word_off[b], w_hi = B.blk_word_off[b + 1];
    for (uint64_t gw = w_lo + (threadIdx.x >> 5); gw < w_hi; gw += blockDim.x >> 5) {
+    // like bm.forEachSetBit (bitmap.go:128-153) only rows that are still selected are looked at: behind a selective filter of an AND chain
+    // that is a small fraction of the block
+    const uint64_t live = reg[gw];
+    if (!live) { if (lane_id() == 0) leaf_bm[gw] = 0; continue; }
     uint32_t r0 = (uint32_t)(gw - w_lo) * 64;
     const uint8_t* data = B.arena + c.data_off;
     const uint8_t* lens = B.arena + c.lens_off;
@@ -913,8 +931,8 @@ static __global__ void k_row_match(DevProgram P, BatchView B, uint32_t leaf_idx,
         if (n < 0) return false;
         return leaf_match_typed_text(P, L, vt, buf, (uint32_t)n);
     };
-    if (ra < rows) ha = eval(oa, la);
-    if (rb < rows) hb = eval(ob, lb);
+    if (ra < rows && (live >> lane_id() & 1)) ha = eval(oa, la);
+    if (rb < rows && (live >> (32 + lane_id()) & 1)) hb = eval(ob, lb);
     uint32_t lo = __ballot_sync(0xffffffffu, ha), hi = __ballot_sync(0xffffffffu, hb);
     if (lane_id() == 0) leaf_bm[gw] = ((uint64_t)hi << 32) | lo;
    }

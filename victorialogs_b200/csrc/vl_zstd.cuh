@@ -436,16 +436,65 @@ static __global__ void __launch_bounds__(64) k_fse_build(ZView V, const uint32_t
     V.bstate[bi].seq_bits_off = off;
 }
 
-// ---- sequence bitstream -> (literal length, match length, offset); one lane per block (RFC 8878 3.1.1.3.2.1.2 / 3.1.1.4) ------------------
-// Every sequence is three table lookups whose results decide where the next three happen: a chain of dependent loads per block.
-// With the tables in HBM (10 KB per block, far more than L2 over all blocks in flight) each link costs a DRAM round trip; so a CTA
-// stages the tables of Z_SEQ_CTA_LANES blocks (3840 bytes each) in shared memory and its lanes run their chains against those.
-static const uint32_t Z_SEQ_CTA_LANES = 56;
-static __global__ void __launch_bounds__(64) k_seq_decode(ZView V, const uint32_t* __restrict__ list, uint32_t n) {
+// ---- sequence bitstream -> (literal length, match length, offset); FOUR lanes per block (RFC 8878 3.1.1.3.2.1.2 / 3.1.1.4) ------------------
+// Every sequence is three table lookups whose results decide where the next three happen: a chain of dependent steps per block.  The tables
+// (3840 bytes per block) live in shared memory, which caps a CTA at Z_SEQ_CTA_BLOCKS blocks; round 1 ran that chain on ONE lane per block,
+// i.e. two warps per SM with ~220 dependent instructions per sequence (887 cycles per sequence, 3 % of the warp slots active).  Now the three
+// FSE states of a block sit on three lanes of a quad: lane 0 literal lengths, lane 1 match lengths, lane 2 offsets (lane 3 rides along).  Per
+// sequence each lane looks up ITS state, the three exchange their two bit widths with shuffles inside the quad, every lane cuts ITS two fields
+// (value bits, state-update bits) out of the shared bit window and steps its state; lane 2 resolves repeat offsets (it gets `literal length
+// == 0` from lane 0).  The window (identical in the four lanes) is read straight from the staging buffer, one aligned 8-byte word ahead, the
+// next 128-byte line prefetched into L1 - the quad's four loads coalesce into one.  7 warps per SM instead of 2, ~4x shorter chain.
+static const uint32_t Z_SEQ_CTA_BLOCKS = 56;
+static const uint32_t Z_SEQ_CTA_LANES = Z_SEQ_CTA_BLOCKS;   // (name kept for the host side: blocks per CTA)
+struct QuadBitReader {
+    uint64_t w0, w1, w2, w3;   // w0:w1:w2 = the 192-bit window, w3 = the next word, requested one word early
+    uint64_t wi;               // address >> 3 of the word held in w3
+    uint32_t off;              // bits of w0 already consumed (0..63 between calls)
+    int64_t pos;               // unread bits of the stream
+    static __device__ __forceinline__ uint64_t word(uint64_t w) { return *(const volatile uint64_t*)(uintptr_t)(w << 3); }
+    static __device__ __forceinline__ void prefetch_line(uint64_t w) { asm volatile("prefetch.global.L1 [%0];" ::"l"((uintptr_t)((w & ~(uint64_t)15) << 3))); }
+    __device__ __forceinline__ bool init(const uint8_t* p, uint32_t len) {
+        w0 = w1 = w2 = w3 = 0; off = 0; pos = 0; wi = 0;
+        if (!len) return false;
+        uint32_t last = p[len - 1];
+        if (!last) return false;
+        pos = (int64_t)len * 8 - (int64_t)(__clz(last) - 23);   // the end mark and the padding above it are not part of the stream
+        const uint64_t abits = (uint64_t)(uintptr_t)p * 8 + (uint64_t)pos;   // absolute bit address one past the first unread bit
+        const uint64_t wtop = (abits + 63) >> 6, whi = wtop - 1;
+        wi = whi - 3;
+        w0 = word(whi); w1 = word(whi - 1); w2 = word(whi - 2); w3 = word(wi);
+        prefetch_line(wi - 16);
+        off = (uint32_t)((wtop << 6) - abits);
+        return true;
+    }
+    // n bits (0..32) that start t bits below the top of w0 (t counts the consumed bits too); t + n <= 192
+    __device__ __forceinline__ uint32_t field(uint32_t t, uint32_t n) const {
+        uint32_t s = t + n;
+        s = s ? s : 1;
+        const bool low = s > 128;
+        const uint64_t a = low ? w1 : w0, b = low ? w2 : w1;
+        const uint32_t e = low ? s - 64 : s;
+        uint64_t v;
+        if (e <= 64) v = a >> (64 - e);
+        else { const uint32_t sh = e - 64; v = (sh < 64 ? a << sh : 0ull) | (b >> (64 - sh)); }
+        return (uint32_t)v & (uint32_t)((1ull << n) - 1);
+    }
+    __device__ __forceinline__ void consume(uint32_t n) {   // n <= 128
+        off += n; pos -= n;
+        while (off >= 64) {
+            w0 = w1; w1 = w2; w2 = w3; off -= 64; wi--;
+            w3 = word(wi);
+            if ((wi & 15) == 15) prefetch_line(wi - 16);   // entering a new line: ask for the one below it
+        }
+    }
+    __device__ __forceinline__ uint32_t read(uint32_t n) { uint32_t v = field(off, n); consume(n); return v; }
+};
+static __global__ void __launch_bounds__(Z_SEQ_CTA_BLOCKS * 4) k_seq_decode(ZView V, const uint32_t* __restrict__ list, uint32_t n) {
     extern __shared__ __align__(16) uint8_t s_fse[];
     __shared__ uint32_t s_llv[36], s_mlv[53];   // code -> value baseline | extra bits << 24
-    const uint32_t first = blockIdx.x * Z_SEQ_CTA_LANES;
-    const uint32_t here = min(Z_SEQ_CTA_LANES, n - first);
+    const uint32_t first = blockIdx.x * Z_SEQ_CTA_BLOCKS;
+    const uint32_t here = min(Z_SEQ_CTA_BLOCKS, n - first);
     if (threadIdx.x < 36) s_llv[threadIdx.x] = Z_LL_BASE[threadIdx.x] | ((uint32_t)Z_LL_BITS[threadIdx.x] << 24);
     if (threadIdx.x < 53) s_mlv[threadIdx.x] = Z_ML_BASE[threadIdx.x] | ((uint32_t)Z_ML_BITS[threadIdx.x] << 24);
     for (uint32_t it = 0; it < here; it++) {   // slot layout == shared layout: 240 chunks of 16 bytes, each from the slot its table lives in
@@ -461,67 +510,80 @@ static __global__ void __launch_bounds__(64) k_seq_decode(ZView V, const uint32_
         }
     }
     __syncthreads();
-    if (threadIdx.x >= here) return;
-    const uint32_t bi = list[first + threadIdx.x];
+    const uint32_t local = threadIdx.x >> 2, sub = threadIdx.x & 3;   // sub: 0 literal lengths, 1 match lengths, 2 offsets, 3 spare
+    if (local >= here) return;                                         // whole quads leave together
+    const uint32_t qbase = (threadIdx.x & 31) & ~3u;                   // first lane of this quad inside its warp
+    const uint32_t qmask = 0xFu << qbase;
+    const uint32_t bi = list[first + local];
     const ZBlock& B = V.blocks[bi];
     if (V.frame_err[B.frame]) return;
     const uint32_t off = V.bstate[bi].seq_bits_off;
-    const uint16_t* tr = (const uint16_t*)(s_fse + (size_t)threadIdx.x * Z_FSE_SLOT_BYTES);
-    const uint8_t* sy = s_fse + (size_t)threadIdx.x * Z_FSE_SLOT_BYTES + 2 * Z_FSE_ENTRIES;
+    const uint16_t* tr = (const uint16_t*)(s_fse + (size_t)local * Z_FSE_SLOT_BYTES);
+    const uint8_t* sy = s_fse + (size_t)local * Z_FSE_SLOT_BYTES + 2 * Z_FSE_ENTRIES;
     const int ll_al = B.ll_slot == Z_PREDEF ? 6 : V.fse_state[B.ll_slot].ll_al;
     const int of_al = B.of_slot == Z_PREDEF ? 5 : V.fse_state[B.of_slot].of_al;
     const int ml_al = B.ml_slot == Z_PREDEF ? 6 : V.fse_state[B.ml_slot].ml_al;
-    LineReader r;
-    if (off >= B.size || !r.init(V.src + B.src + off, B.size - off, s_fse + (size_t)Z_SEQ_CTA_LANES * Z_FSE_SLOT_BYTES + (size_t)threadIdx.x * Z_LINEBUF)) { zfail(V, B.frame, ZERR_SEQ_STREAM); return; }
-    uint32_t sl = Z_FSE_LL + r.read(ll_al), so = Z_FSE_OF + r.read(of_al), sm = Z_FSE_ML + r.read(ml_al);
-    uint4* __restrict__ out = V.seqs + B.seq_base;
-    uint64_t sum_ll = 0, sum_ml = 0;
+    QuadBitReader r;
+    if (off >= B.size || !r.init(V.src + B.src + off, B.size - off)) { if (sub == 0) zfail(V, B.frame, ZERR_SEQ_STREAM); return; }
+    // initial states, in stream order: literal lengths, offsets, match lengths
+    const uint32_t i_ll = r.read(ll_al), i_of = r.read(of_al), i_ml = r.read(ml_al);
+    uint32_t st = sub == 0 ? Z_FSE_LL + i_ll : sub == 1 ? Z_FSE_ML + i_ml : Z_FSE_OF + i_of;   // this lane's state (lane 3 shadows the offsets lane)
+    const uint32_t tbase = sub == 0 ? Z_FSE_LL : sub == 1 ? Z_FSE_ML : Z_FSE_OF;
+    uint32_t* __restrict__ out = (uint32_t*)(V.seqs + B.seq_base);
+    unsigned long long sum = 0;   // lane 0: literal lengths, lane 1: match lengths
     bool ok = true;
-    // Repeat offsets (RFC 8878 3.1.1.5) are resolved on the fly.  A block that follows other blocks with sequences does not know the
-    // three offsets it starts with: they are tracked as DIRTY until real offsets have pushed them out of the history, and
+    // Repeat offsets (RFC 8878 3.1.1.5) are resolved on the fly by the offsets lane.  A block that follows other blocks with sequences does
+    // not know the three offsets it starts with: they are tracked as DIRTY until real offsets have pushed them out of the history, and
     // k_seq_resolve redoes only that prefix of the block once the predecessor's final history is known.
     const uint32_t DIRTY = 0xFFFFFFFFu;
     uint32_t r1 = B.rep_known ? 1 : DIRTY, r2 = B.rep_known ? 4 : DIRTY, r3 = B.rep_known ? 8 : DIRTY;
     const uint32_t nseq = B.nseq;
     uint32_t clean_from = B.rep_known ? 0 : nseq + 1;
     for (uint32_t i = 0; i < nseq; i++) {
-        const uint32_t tl = tr[sl], to = tr[so], tm = tr[sm];
-        const uint32_t oc = sy[so], vl = s_llv[sy[sl]], vm = s_mlv[sy[sm]];
+        const uint32_t te = tr[st];        // baseline | nbits << 12 of this lane's state
+        const uint32_t code = sy[st];
+        const uint32_t vb = sub == 0 ? s_llv[code] : sub == 1 ? s_mlv[code] : 0;   // literal / match lengths: value baseline | extra bits << 24
         if (r.pos < 0) { ok = false; break; }
-        // Bit layout of one sequence, top down: offset extra bits, match-length extra bits, literal-length extra bits, then (unless it is
-        // the last sequence) the LL, ML, OF state updates.  All six widths are known now, so all six fields are cut out of the window
-        // independently.
         const bool more = i + 1 < nseq;
-        const uint32_t nM = vm >> 24, nL = vl >> 24, bL = more ? tl >> 12 : 0, bM = more ? tm >> 12 : 0, bO = more ? to >> 12 : 0;
-        const uint32_t t0 = r.off, t1 = t0 + oc, t2 = t1 + nM, t3 = t2 + nL, t4 = t3 + bL, t5 = t4 + bM, t6 = t5 + bO;
-        const uint32_t ov = (1u << oc) + r.field(t0, oc);
-        const uint32_t ml = (vm & 0xFFFFFF) + r.field(t1, nM);
-        const uint32_t ll = (vl & 0xFFFFFF) + r.field(t2, nL);
-        const uint32_t nsl = Z_FSE_LL + (tl & 0xFFF) + r.field(t3, bL);
-        const uint32_t nsm = Z_FSE_ML + (tm & 0xFFF) + r.field(t4, bM);
-        const uint32_t nso = Z_FSE_OF + (to & 0xFFF) + r.field(t5, bO);
+        // widths of this lane's two fields; the layout of one sequence, top down: offset bits, match-length bits, literal-length bits, then
+        // (unless it is the last sequence) the LL, ML, OF state updates
+        const uint32_t xb = sub < 2 ? vb >> 24 : code, sb = more ? te >> 12 : 0;   // an offset code IS its number of extra bits (baseline 1 << code)
+        const uint32_t vbase = sub < 2 ? (vb & 0xFFFFFF) : (1u << code);
+        const uint32_t pack = xb | (sb << 8);
+        const uint32_t p_ll = __shfl_sync(qmask, pack, qbase), p_ml = __shfl_sync(qmask, pack, qbase + 1), p_of = __shfl_sync(qmask, pack, qbase + 2);
+        const uint32_t t0 = r.off, t1 = t0 + (p_of & 0xFF), t2 = t1 + (p_ml & 0xFF), t3 = t2 + (p_ll & 0xFF), t4 = t3 + (p_ll >> 8), t5 = t4 + (p_ml >> 8), t6 = t5 + (p_of >> 8);
+        const uint32_t xt = sub == 0 ? t2 : sub == 1 ? t1 : t0;          // where this lane's value bits start
+        const uint32_t stt = sub == 0 ? t3 : sub == 1 ? t4 : t5;         // ... and its state-update bits
+        const uint32_t val = vbase + r.field(xt, xb);
+        const uint32_t nst = tbase + (te & 0xFFF) + r.field(stt, sb);
         r.consume(t6 - t0);
-        uint32_t o;
-        if (ov > 3) { o = ov - 3; r3 = r2; r2 = r1; r1 = o; }
-        else {
-            uint32_t idx = ov + (ll == 0 ? 1 : 0);
-            if (idx == 1) o = r1;
+        const uint32_t ll = __shfl_sync(qmask, val, qbase);               // the offsets lane needs "literal length == 0"
+        if (sub == 2) {
+            const uint32_t ov = val;
+            uint32_t o;
+            if (ov > 3) { o = ov - 3; r3 = r2; r2 = r1; r1 = o; }
             else {
-                o = idx == 2 ? r2 : idx == 3 ? r3 : (r1 == DIRTY ? DIRTY : r1 - 1);
-                if (idx != 2) r3 = r2;
-                r2 = r1; r1 = o;
+                uint32_t idx = ov + (ll == 0 ? 1 : 0);
+                if (idx == 1) o = r1;
+                else {
+                    o = idx == 2 ? r2 : idx == 3 ? r3 : (r1 == DIRTY ? DIRTY : r1 - 1);
+                    if (idx != 2) r3 = r2;
+                    r2 = r1; r1 = o;
+                }
             }
-        }
-        if (clean_from > nseq && r1 != DIRTY && r2 != DIRTY && r3 != DIRTY) clean_from = i + 1;
-        out[i] = make_uint4(ll, ml, o, ov);
-        sum_ll += ll; sum_ml += ml;
-        if (more) { sl = nsl; sm = nsm; so = nso; }
+            if (clean_from > nseq && r1 != DIRTY && r2 != DIRTY && r3 != DIRTY) clean_from = i + 1;
+            *(uint2*)(out + 4 * (size_t)i + 2) = make_uint2(o, ov);   // record = (literal length, match length, offset, raw offset value)
+        } else if (sub < 2) { out[4 * (size_t)i + sub] = val; sum += val; }
+        if (more) st = nst;
     }
-    r.finish();
-    if (!ok || r.pos != 0 || sum_ll > B.lit_regen || sum_ml + B.lit_regen > 0xFFFFFFFFull) { zfail(V, B.frame, ZERR_SEQ_STREAM); return; }
-    ZBlockState& S = V.bstate[bi];
-    S.out_len = (uint32_t)(B.lit_regen + sum_ml);
-    S.clean_from = clean_from; S.rep[0] = r1; S.rep[1] = r2; S.rep[2] = r3;
+    if (!__all_sync(qmask, ok) || r.pos != 0) { if (sub == 0) zfail(V, B.frame, ZERR_SEQ_STREAM); return; }
+    const unsigned long long sum_ll = __shfl_sync(qmask, sum, qbase), sum_ml = __shfl_sync(qmask, sum, qbase + 1);
+    if (sum_ll > B.lit_regen || sum_ml + B.lit_regen > 0xFFFFFFFFull) { if (sub == 0) zfail(V, B.frame, ZERR_SEQ_STREAM); return; }
+    if (sub == 2) {
+        ZBlockState& S = V.bstate[bi];
+        S.out_len = (uint32_t)(B.lit_regen + sum_ml);
+        S.clean_from = clean_from; S.rep[0] = r1; S.rep[1] = r2; S.rep[2] = r3;
+    }
 }
 
 // ---- block output bases + the repeat offsets k_seq_decode could not know; one lane per frame (RFC 8878 3.1.1.5) ---------------------------
@@ -566,20 +628,21 @@ static __global__ void __launch_bounds__(64) k_seq_resolve(ZView V, uint32_t fra
 }
 
 // ---- sequence execution; one warp per frame (RFC 8878 3.1.1.4) -------------------------------------------------------------------------------
-// The output of a frame is produced in groups of 32 sequences, one sequence per lane, inside a per-warp ring in shared memory that is indexed by
-// the low bits of the byte's address in the arena; a finished group is flushed to HBM with aligned 16-byte stores.  Log data compresses into
-// short sequences (a handful of literal bytes, a 4..40 byte match), so in the common case every lane simply copies its own literal run and its own
-// match - byte loops of a few iterations, all lanes at once - instead of the warp spreading each copy over its lanes (measured on the C2 batch:
-// 42 warp instructions per sequence, 46 % of the stall samples on the store behind the one-byte load of a match source that was not in the ring).
-// A match must wait only for the matches whose destination its source overlaps: `dep` is the index of the last such match inside the group;
-// the matches whose dep lies in front of the current position are copied together.  Sources within the last Z_RING bytes come from the ring,
-// older ones from HBM (8-byte loads; they lie in front of the group, hence flushed).  Groups with a long literal run or a long match take the
-// cooperative path instead: every copy is spread over the warp and goes to HBM directly (mirrored in the ring while it fits).
-static const uint32_t Z_RING = 8192;
+// Per group of 32 sequences: all literal runs go out first (they depend on nothing), then the matches.  A match must wait only for
+// the matches whose destination its source overlaps; `dep` is the index of the last such match inside the group, and a run of
+// consecutive matches with dep < (first match of the run) is copied as one flat, warp-wide copy.  The source of a match is mostly a
+// few hundred bytes back - data this warp stored moments ago - so every byte is mirrored in a per-warp ring in shared memory and
+// read from there when it is recent enough: the load that every run has to wait for then costs ~30 cycles instead of an L2 / HBM trip.
+// Round 2.  (a) Measured on the C2 batch (profiles/ncu_zstd_r02.md): 46 % of this kernel's stall samples sat on the store behind the one-byte
+// load of a match source that is not in the ring - zstd level 3 codes the random hex digits of log lines as 4..5 byte matches found anywhere in
+// the 385 KB frame, so most matches are far and every copy step paid a DRAM round trip.  Inside a run all copies are independent (that is what
+// makes it a run), so the loads of four steps are now issued before the first store.  (b) A variant in which every lane copies its own sequence
+// into the ring and the group is flushed with 16-byte stores was byte-exact too but slower (70 ms against 43 ms on that batch: the 43-byte
+// template match of every row keeps 31 lanes waiting); it is in the history of this file (commit "device ZSTD: per-lane sequence execution").
+static const uint32_t Z_RING = 4096;
 static const uint32_t Z_EXEC_WARPS = 4;
-static const uint32_t Z_FAST_LL = 32, Z_FAST_ML = 64;   // per-lane copy limits of the fast path: a group's output then stays below 3 KB
-static __global__ void __launch_bounds__(Z_EXEC_WARPS * 32) k_execute(ZView V, const uint32_t* __restrict__ order, uint32_t nframes) {
-    __shared__ __align__(16) uint8_t s_ring[Z_EXEC_WARPS][Z_RING];
+static __global__ void __launch_bounds__(128) k_execute(ZView V, const uint32_t* __restrict__ order, uint32_t nframes) {
+    __shared__ uint8_t s_ring[4][Z_RING];
     const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (wid >= nframes) return;
     const uint32_t f = order[wid];
@@ -587,15 +650,13 @@ static __global__ void __launch_bounds__(Z_EXEC_WARPS * 32) k_execute(ZView V, c
     const ZFrame& F = V.frames[f];
     uint8_t* dst = V.arena + F.dst;
     uint8_t* ring = s_ring[threadIdx.x >> 5];
-    const uint32_t abase = (uint32_t)(uintptr_t)dst;   // ring slot of frame position p = (address of dst + p) & (Z_RING - 1): same 16-byte alignment as in the arena
-#define VL_RING(p) ring[(abase + (p)) & (Z_RING - 1)]
     uint32_t ring_lo = 0;   // frame position from which the ring content can be trusted
     for (uint32_t bi = F.blk_lo; bi < F.blk_hi; bi++) {
         const ZBlock& B = V.blocks[bi];
         const uint32_t blk_base = V.bstate[bi].out_base;   // position of the block inside the frame
         const uint8_t* p = V.src + B.src;
-        if (B.type == ZB_RAW) { for (uint32_t k = lane; k < B.size; k += 32) { uint8_t v = p[k]; dst[blk_base + k] = v; VL_RING(blk_base + k) = v; } if (B.size >= Z_RING) ring_lo = blk_base + B.size - Z_RING; __syncwarp(); continue; }
-        if (B.type == ZB_RLE) { uint8_t v = p[0]; for (uint32_t k = lane; k < B.size; k += 32) { dst[blk_base + k] = v; VL_RING(blk_base + k) = v; } __syncwarp(); continue; }
+        if (B.type == ZB_RAW) { for (uint32_t k = lane; k < B.size; k += 32) { uint8_t v = p[k]; dst[blk_base + k] = v; ring[(blk_base + k) & (Z_RING - 1)] = v; } __syncwarp(); continue; }
+        if (B.type == ZB_RLE) { uint8_t v = p[0]; for (uint32_t k = lane; k < B.size; k += 32) { dst[blk_base + k] = v; ring[(blk_base + k) & (Z_RING - 1)] = v; } __syncwarp(); continue; }
         const uint8_t* lit = B.lit_type == ZL_RAW ? p + B.lit_hdr : V.lits + B.lit_off;
         const bool lit_rle = B.lit_type == ZL_RLE;
         const uint8_t rle_byte = lit_rle ? p[B.lit_hdr] : 0;
@@ -610,8 +671,22 @@ static __global__ void __launch_bounds__(Z_EXEC_WARPS * 32) k_execute(ZView V, c
             const uint32_t o_start = io - q.x - q.y;        // output offset of this lane's literals inside the group
             const uint32_t T = __shfl_sync(0xffffffffu, il, 31), O = __shfl_sync(0xffffffffu, io, 31);
             const uint32_t gend = out_run + O;              // frame position one past the group
+            // Inside a group stores are not in position order (all literals first), so two positions of one group must not share a ring
+            // slot: a group spanning Z_RING bytes or more reads from HBM only and leaves the ring untrusted below its end.
+            const bool ring_ok = O < Z_RING;
+            // literal runs of the whole group: byte k belongs to the sequence j with il[j-1] <= k < il[j]
+            for (uint32_t k0 = 0; k0 < T; k0 += 32) {
+                uint32_t k = k0 + lane;
+                uint32_t lo = 0;   // smallest j with il[j] > k, by 5 shuffle probes
+#pragma unroll
+                for (int s = 16; s; s >>= 1) { uint32_t v = __shfl_sync(0xffffffffu, il, (lo + s - 1) & 31); if (v <= k) lo += s; }
+                uint32_t js = __shfl_sync(0xffffffffu, lit_start, lo & 31), jo = __shfl_sync(0xffffffffu, o_start, lo & 31);
+                if (k < T) { uint8_t v = lit_rle ? rle_byte : lit[lit_run + k]; uint32_t at = out_run + jo + (k - js); dst[at] = v; ring[at & (Z_RING - 1)] = v; }
+            }
+            __syncwarp();
             const uint32_t cnt = min(32u, B.nseq - g);
             const uint32_t ml = q.y, off = q.z, amd = out_run + o_start + q.x;   // amd: frame position of the match destination
+            const uint32_t im = io - il;                                         // inclusive prefix sum of the match lengths
             if (__any_sync(0xffffffffu, lane < cnt && (off == 0 || off > amd))) { if (lane == 0) zfail(V, f, ZERR_OFFSET); return; }
             // dep: the last match of the group whose destination [amd_i, amd_i + ml_i) overlaps this match's source [s, e); destinations are
             // disjoint and ascending, so that is the last one starting below e, if it reaches beyond s
@@ -625,109 +700,46 @@ static __global__ void __launch_bounds__(Z_EXEC_WARPS * 32) k_execute(ZView V, c
                 const uint32_t ca = __shfl_sync(0xffffffffu, amd, ci), cm = __shfl_sync(0xffffffffu, ml, ci);
                 if (lo > 0 && ca + cm > s_src) dep = (int)lo - 1;
             }
-            const bool fast = !__any_sync(0xffffffffu, q.x > Z_FAST_LL || q.y > Z_FAST_ML);
-            if (fast) {
-                // ---- every lane copies its own literal run and its own match into the ring ----
-                {
-                    const uint32_t at = out_run + o_start;
-                    if (lit_rle) { for (uint32_t k = 0; k < q.x; k++) VL_RING(at + k) = rle_byte; }
-                    else {
-                        const uint8_t* ls = lit + lit_run + lit_start;
-                        for (uint32_t k = 0; k < q.x; k += 8) {
-                            const uint64_t w = ldu64(ls + k);   // up to 15 bytes past the run: scratch and staging buffers keep that much slack
-                            const uint32_t m = min(8u, q.x - k);
-                            for (uint32_t t = 0; t < m; t++) VL_RING(at + k + t) = (uint8_t)(w >> (8 * t));
-                        }
-                    }
-                }
-                __syncwarp();
-                uint32_t cur = 0;
-                while (cur < cnt) {
-                    const uint32_t ready = __ballot_sync(0xffffffffu, lane >= cur && lane < cnt && dep < (int)cur) >> cur;   // bit 0 = match `cur`, always set
-                    const uint32_t n = ready == 0xffffffffu ? 32u : max((uint32_t)__ffs((int)~ready) - 1u, 1u);
-                    const uint32_t hi = cur + n;
-                    if (lane >= cur && lane < hi && ml) {
-                        // the ring holds position q as long as nothing was stored at q + Z_RING; stores so far stay below gend
-                        if (s_src >= ring_lo && gend - s_src <= Z_RING) {
-                            for (uint32_t k = 0; k < ml; k++) VL_RING(amd + k) = VL_RING(s_src + k);   // in order: an overlapping match repeats its own output
-                        } else if (gend - s_src > Z_RING || s_src + ml <= ring_lo) {
-                            // older than the ring (or than what the ring can be trusted for): more than 5 KB in front of the group's end, so
-                            // entirely in front of the group (flushed) and never overlapping its destination
-                            for (uint32_t k = 0; k < ml; k += 8) {
-                                const uint64_t w = ldu64(dst + s_src + k);
-                                const uint32_t m = min(8u, ml - k);
-                                for (uint32_t t = 0; t < m; t++) VL_RING(amd + k + t) = (uint8_t)(w >> (8 * t));
-                            }
-                        } else {
-                            // starts in front of the trusted part of the ring and runs into it: byte by byte (positions below ring_lo were
-                            // written to HBM directly by the cooperative path)
-                            for (uint32_t k = 0; k < ml; k++) { const uint32_t sp = s_src + k; VL_RING(amd + k) = sp >= ring_lo ? VL_RING(sp) : dst[sp]; }
-                        }
-                    }
-                    __syncwarp();
-                    cur = hi;
-                }
-                // ---- flush [out_run, gend): bytes up to the first 16-byte boundary of the arena, aligned 16-byte chunks, the bytes behind the last one ----
-                {
-                    const uintptr_t a0 = (uintptr_t)dst + out_run, a1 = (uintptr_t)dst + gend;
-                    const uintptr_t c0 = (a0 + 15) & ~(uintptr_t)15, c1 = a1 & ~(uintptr_t)15;
-                    if (c0 <= c1) {
-                        if (lane < c0 - a0) *(uint8_t*)(a0 + lane) = ring[(a0 + lane) & (Z_RING - 1)];
-                        for (uintptr_t c = c0 + 16 * lane; c < c1; c += 512) *(uint4*)c = *(const uint4*)(ring + (c & (Z_RING - 1)));
-                        if (lane < a1 - c1) *(uint8_t*)(c1 + lane) = ring[(c1 + lane) & (Z_RING - 1)];
-                    } else if (lane < O) *(uint8_t*)(a0 + lane) = ring[(a0 + lane) & (Z_RING - 1)];   // the group lies inside one 16-byte chunk
-                }
-                __syncwarp();
-            } else {
-                // ---- cooperative path: every copy spread over the warp, straight to HBM, mirrored in the ring ----
-                // Inside a group stores are not in position order (all literals first), so two positions of one group must not share a ring
-                // slot: a group spanning Z_RING bytes or more reads from HBM only and leaves the ring untrusted below its end.
-                const bool ring_ok = O < Z_RING;
-                // literal runs of the whole group: byte k belongs to the sequence j with il[j-1] <= k < il[j]
-                for (uint32_t k0 = 0; k0 < T; k0 += 32) {
-                    uint32_t k = k0 + lane;
-                    uint32_t lo = 0;   // smallest j with il[j] > k, by 5 shuffle probes
+            uint32_t cur = 0;
+            while (cur < cnt) {
+                const uint32_t ready = __ballot_sync(0xffffffffu, lane >= cur && lane < cnt && dep < (int)cur) >> cur;   // bit 0 = match `cur`, always set
+                const uint32_t n = ready == 0xffffffffu ? 32u : max((uint32_t)__ffs((int)~ready) - 1u, 1u);
+                const uint32_t hi = cur + n;
+                const uint32_t im_lo = cur ? __shfl_sync(0xffffffffu, im, cur - 1) : 0u, M = __shfl_sync(0xffffffffu, im, hi - 1) - im_lo;
+                for (uint32_t k0 = 0; k0 < M; k0 += 128) {   // four steps of 32 bytes: all loads first, then all stores
+                    uint8_t v[4]; uint32_t at[4]; bool on[4];
 #pragma unroll
-                    for (int s = 16; s; s >>= 1) { uint32_t v = __shfl_sync(0xffffffffu, il, (lo + s - 1) & 31); if (v <= k) lo += s; }
-                    uint32_t js = __shfl_sync(0xffffffffu, lit_start, lo & 31), jo = __shfl_sync(0xffffffffu, o_start, lo & 31);
-                    if (k < T) { uint8_t v = lit_rle ? rle_byte : lit[lit_run + k]; uint32_t at = out_run + jo + (k - js); dst[at] = v; VL_RING(at) = v; }
-                }
-                __syncwarp();
-                const uint32_t im = io - il;                                         // inclusive prefix sum of the match lengths
-                uint32_t cur = 0;
-                while (cur < cnt) {
-                    const uint32_t ready = __ballot_sync(0xffffffffu, lane >= cur && lane < cnt && dep < (int)cur) >> cur;
-                    const uint32_t n = ready == 0xffffffffu ? 32u : max((uint32_t)__ffs((int)~ready) - 1u, 1u);
-                    const uint32_t hi = cur + n;
-                    const uint32_t im_lo = cur ? __shfl_sync(0xffffffffu, im, cur - 1) : 0u, M = __shfl_sync(0xffffffffu, im, hi - 1) - im_lo;
-                    for (uint32_t k0 = 0; k0 < M; k0 += 32) {
-                        const uint32_t k = im_lo + k0 + lane;   // position in the group's concatenated match bytes
-                        uint32_t lo = 0;                         // smallest j with im[j] > k
+                    for (int u = 0; u < 4; u++) {
+                        const uint32_t kq = k0 + 32 * u + lane;
+                        const uint32_t k = im_lo + kq;   // position in the group's concatenated match bytes
+                        uint32_t lo = 0;                 // smallest j with im[j] > k
 #pragma unroll
-                        for (int s = 16; s; s >>= 1) { uint32_t v = __shfl_sync(0xffffffffu, im, (lo + s - 1) & 31); if (v <= k) lo += s; }
+                        for (int s = 16; s; s >>= 1) { uint32_t x = __shfl_sync(0xffffffffu, im, (lo + s - 1) & 31); if (x <= k) lo += s; }
                         const uint32_t jm = __shfl_sync(0xffffffffu, ml, lo & 31), jo = __shfl_sync(0xffffffffu, off, lo & 31);
                         const uint32_t jd = __shfl_sync(0xffffffffu, amd, lo & 31), je = __shfl_sync(0xffffffffu, im, lo & 31);
-                        if (k0 + lane < M) {
+                        on[u] = kq < M; v[u] = 0; at[u] = 0;
+                        if (on[u]) {
                             const uint32_t kk = k - (je - jm);   // byte index inside match `lo`
                             const uint32_t sa = jd - jo + (jo >= jm ? kk : kk % jo);   // frame position of the source byte
-                            const uint8_t v = (ring_ok && sa >= ring_lo && gend - sa < Z_RING) ? VL_RING(sa) : dst[sa];
-                            dst[jd + kk] = v; VL_RING(jd + kk) = v;
+                            // the ring holds position q as long as nothing was stored at q + Z_RING; stores so far reach up to gend
+                            v[u] = (ring_ok && sa >= ring_lo && gend - sa < Z_RING) ? ring[sa & (Z_RING - 1)] : dst[sa];
+                            at[u] = jd + kk;
                         }
                     }
-                    __syncwarp();
-                    cur = hi;
+#pragma unroll
+                    for (int u = 0; u < 4; u++) if (on[u]) { dst[at[u]] = v[u]; ring[at[u] & (Z_RING - 1)] = v[u]; }
                 }
-                if (!ring_ok) ring_lo = gend;
+                __syncwarp();
+                cur = hi;
             }
             lit_run += T; out_run += O;
+            if (!ring_ok) ring_lo = gend;
         }
         // literals after the last sequence
         const uint32_t rest = B.lit_regen - lit_run;
-        for (uint32_t k = lane; k < rest; k += 32) { uint8_t v = lit_rle ? rle_byte : lit[lit_run + k]; dst[out_run + k] = v; VL_RING(out_run + k) = v; }
-        if (rest >= Z_RING) ring_lo = out_run + rest - Z_RING;
+        for (uint32_t k = lane; k < rest; k += 32) { uint8_t v = lit_rle ? rle_byte : lit[lit_run + k]; dst[out_run + k] = v; ring[(out_run + k) & (Z_RING - 1)] = v; }
         __syncwarp();
     }
-#undef VL_RING
 }
 
 }  // namespace zs
