@@ -7,8 +7,9 @@ is an argument rather than a format rule, in the exact form the kernels use:
   run happens against the state before the run - which is also why the kernel may issue the loads of several copy steps before the first
   store, as it does since round 2); the per-warp ring in shared memory with its validity rule (`gend - q < RING`, group span
   < RING, `ring_lo` after an oversized group).
-* LineReader: a 192-bit window over aligned 8-byte words; `field(t, n)` cuts n bits that start t bits below the top; `consume` slides
-  whole words.  Six fields of one sequence are cut at precomputed offsets from the same window."""
+* QuadBitReader (the sequence decoder's bit window; the model class below keeps its round-1 name): a 192-bit window over aligned 8-byte words;
+  `field(t, n)` cuts n bits that start t bits below the top; `consume` slides whole words.  The six fields of one sequence are cut at
+  precomputed offsets from the same window (since round 2 by three lanes, two fields each)."""
 import random
 
 RING = 4096

@@ -75,71 +75,6 @@ struct BackReader {
         return v;
     }
 };
-// The reader of the two long serial chains (Huffman streams, sequences): a 192-bit window w0:w1:w2 over ALIGNED 8-byte words of a backward
-// bitstream, fed from shared memory.  The stream is pulled in 128-byte lines with cp.async (global -> shared, no registers, no stall)
-// into a two-line buffer private to the lane, one line ahead of the reader, so the HBM latency of the stream is paid a full line
-// before the data is needed and a window word costs a shared-memory load.  With `off` < 64 consumed bits in w0 the window always holds
-// 128+ unread bits: every field of one sequence (<= 89 bits) is cut out of the SAME window at precomputed offsets - six independent
-// extractions instead of a read-after-read chain - and consumed with one `consume`.  `sbuf`: 256 bytes, 16-byte aligned.
-// Bits in front of the stream are whatever memory holds there (the staging buffer has headroom); callers detect overruns through `pos`.
-struct LineReader {
-    uint64_t w0, w1, w2;
-    uint64_t wi;          // address >> 3 of the word held in w2
-    uint8_t* sbuf;
-    uint32_t off;         // bits of w0 already consumed (0..63 between calls)
-    int64_t pos;          // unread bits of the stream
-    __device__ __forceinline__ void fetch_line(uint64_t line) const {   // line = address >> 7; lands in buffer half (line & 1)
-        const uint32_t sa = (uint32_t)__cvta_generic_to_shared(sbuf + ((line & 1) << 7));
-        const uint8_t* g = (const uint8_t*)(uintptr_t)(line << 7);
-#pragma unroll
-        for (int q = 0; q < 8; q++) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + 16 * q), "l"(g + 16 * q) : "memory");
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    }
-    __device__ __forceinline__ uint64_t word(uint64_t w) const { return *(const volatile uint64_t*)(sbuf + ((w & 31) << 3)); }
-    __device__ __forceinline__ bool init(const uint8_t* p, uint32_t len, uint8_t* lane_buf) {
-        sbuf = lane_buf; w0 = w1 = w2 = 0; off = 0; pos = 0; wi = 0;
-        if (!len) return false;
-        uint32_t last = p[len - 1];
-        if (!last) return false;
-        pos = (int64_t)len * 8 - (int64_t)(__clz(last) - 23);   // the end mark and the padding above it are not part of the stream
-        const uint64_t abits = (uint64_t)(uintptr_t)p * 8 + (uint64_t)pos;   // absolute bit address one past the first unread bit
-        const uint64_t wtop = (abits + 63) >> 6, whi = wtop - 1;
-        wi = whi - 2;
-        const uint64_t l0 = whi >> 4;
-        fetch_line(l0); fetch_line(l0 - 1);
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        w0 = word(whi); w1 = word(whi - 1); w2 = word(wi);
-        if ((wi >> 4) != l0) fetch_line(l0 - 2);   // w2 already sits in the lower line: keep the line below it in flight
-        off = (uint32_t)((wtop << 6) - abits);
-        return true;
-    }
-    // n bits (0..32) that start t bits below the top of w0 (t counts the consumed bits too); t + n <= 192
-    __device__ __forceinline__ uint32_t field(uint32_t t, uint32_t n) const {
-        uint32_t s = t + n;                       // end of the field, counted from the top of the window
-        s = s ? s : 1;
-        const bool low = s > 128;                 // field ends in w2: work on the pair w1:w2
-        const uint64_t a = low ? w1 : w0, b = low ? w2 : w1;
-        const uint32_t e = low ? s - 64 : s;      // 1..128: end of the field inside the pair a:b
-        uint64_t v;
-        if (e <= 64) v = a >> (64 - e);
-        else { const uint32_t sh = e - 64; v = (sh < 64 ? a << sh : 0ull) | (b >> (64 - sh)); }
-        return (uint32_t)v & (uint32_t)((1ull << n) - 1);
-    }
-    __device__ __forceinline__ void consume(uint32_t n) {   // n <= 128
-        off += n; pos -= n;
-        while (off >= 64) {
-            w0 = w1; w1 = w2; off -= 64; wi--;
-            if ((wi & 15) == 15) {   // w2 enters a new line: it was requested one line ago; request the next one into the half just left
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
-                fetch_line((wi >> 4) - 1);
-            }
-            w2 = word(wi);
-        }
-    }
-    __device__ __forceinline__ uint32_t read(uint32_t n) { uint32_t v = field(off, n); consume(n); return v; }
-    __device__ __forceinline__ void finish() const { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-};
-static const uint32_t Z_LINEBUF = 272;   // bytes of shared memory per lane for a LineReader (256 + a 16-byte skew against bank conflicts)
 struct FwdReader {
     const uint8_t* base; uint32_t len; uint32_t pos;
     __device__ __forceinline__ uint32_t read(int n) { uint32_t v = (uint32_t)(ldu64(base + (pos >> 3)) >> (pos & 7)) & ((1u << n) - 1); pos += n; return v; }
@@ -332,8 +267,12 @@ static __global__ void __launch_bounds__(128) k_huf_build(ZView V, const uint32_
 // ---- Huffman streams; one lane per stream (RFC 8878 4.2.2) --------------------------------------------------------------------------
 // A CTA takes Z_HUF_CTA_BLOCKS blocks (4 lanes each) and first copies their decoding tables into shared memory: with the tables in
 // HBM every symbol costs a 32-byte sector from L2 for a 2-byte entry and the kernel runs at the L2's sector rate; in shared memory
-// the per-symbol chain is one ~30-cycle lookup.  Dynamic shared memory: Z_HUF_CTA_BLOCKS * (2^11 entries * 2 bytes + 4 line buffers).
-static const uint32_t Z_HUF_CTA_BLOCKS = 40;
+// the per-symbol chain is one ~30-cycle lookup.  Dynamic shared memory: Z_HUF_CTA_BLOCKS * 2^11 entries * 2 bytes.
+// Round 2: the bitstream is no longer pulled through a per-lane line buffer in shared memory (22 instructions per symbol, all of them on the one
+// dependent chain a lane has).  A lane now reloads a 64-bit container straight from the staging buffer - the 8 bytes that end at its bit
+// cursor, >= 57 fresh bits - and cuts four symbols out of it: lookup, shift count += code length.  ~10 instructions per symbol, and the
+// shared memory the line buffers took holds the tables of 16 more blocks per CTA (56 instead of 40).
+static const uint32_t Z_HUF_CTA_BLOCKS = 56;
 static __global__ void __launch_bounds__(Z_HUF_CTA_BLOCKS * 4) k_huf_decode(ZView V, const uint32_t* __restrict__ list, uint32_t n) {
     extern __shared__ uint16_t s_tab[];
     const uint32_t local = threadIdx.x >> 2, k = threadIdx.x & 3;
@@ -371,33 +310,33 @@ static __global__ void __launch_bounds__(Z_HUF_CTA_BLOCKS * 4) k_huf_decode(ZVie
         len = k == 0 ? s1 : k == 1 ? s2 : k == 2 ? s3 : total - 6 - s1 - s2 - s3;
         s += off; out += (size_t)k * seg; nout = k < 3 ? seg : B.lit_regen - 3 * seg;
     }
-    LineReader r;
-    if (!r.init(s, len, (uint8_t*)(s_tab + (size_t)Z_HUF_CTA_BLOCKS * Z_HUF_TABLE) + (size_t)threadIdx.x * Z_LINEBUF)) { zfail(V, B.frame, ZERR_HUF_STREAM); return; }
-    // Decoding container: the next unread bits, top aligned, `avail` of them valid.  One symbol = one shared-memory lookup, two
-    // shifts and an add; 32 fresh bits are appended whenever at most 32 are left (so two symbols of <= 11 bits always fit).
+    // backward bitstream: `pos` unread bits; peek64(s, pos) = the 64 bits just below the cursor, top aligned (>= 57 of them real while pos >= 64,
+    // zeros in front of the stream)
+    if (!len || !s[len - 1]) { zfail(V, B.frame, ZERR_HUF_STREAM); return; }
+    int64_t pos = (int64_t)len * 8 - (int64_t)(__clz((uint32_t)s[len - 1]) - 23);   // the end mark and the padding above it are not part of the stream
     const int sh = 64 - (int)maxbits;
-    uint64_t w = 0; int avail = 0;
     uint32_t i = 0;
-#define VL_HUF_REFILL() if (avail <= 32) { w |= (uint64_t)r.read(32) << (32 - avail); avail += 32; }
-#define VL_HUF_SYM(dst_expr) { const uint32_t e = tab[w >> sh]; const int nb = (int)(e >> 8); w <<= nb; avail -= nb; dst_expr; }
     // head: byte stores until the output is 8-byte aligned
-    while (i < nout && (((uintptr_t)(out + i)) & 7) && r.pos + avail >= 0) { VL_HUF_REFILL(); VL_HUF_SYM(out[i++] = (uint8_t)e); }
-    // body: 8 symbols per 64-bit store
-    while (nout - i >= 8 && r.pos + avail >= 0) {
+    while (i < nout && (((uintptr_t)(out + i)) & 7) && pos >= 0) { const uint32_t e = tab[peek64(s, pos) >> sh]; pos -= (int64_t)(e >> 8); out[i++] = (uint8_t)e; }
+    // body: 8 symbols per 64-bit store, two container reloads (4 symbols of <= 11 bits each fit the >= 57 fresh bits of a reload)
+    while (nout - i >= 8 && pos >= 64) {
         uint64_t acc = 0;
 #pragma unroll
-        for (int q = 0; q < 8; q += 2) {
-            VL_HUF_REFILL();
-            VL_HUF_SYM(acc |= (uint64_t)(e & 0xFF) << (8 * q));
-            VL_HUF_SYM(acc |= (uint64_t)(e & 0xFF) << (8 * q + 8));
+        for (int half = 0; half < 2; half++) {
+            const uint64_t c = peek64(s, pos);
+            uint32_t used = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const uint32_t e = tab[(c << used) >> sh];
+                used += e >> 8;
+                acc |= (uint64_t)(e & 0xFF) << (8 * (4 * half + q));
+            }
+            pos -= (int64_t)used;
         }
         *(uint64_t*)(out + i) = acc; i += 8;
     }
-    while (i < nout && r.pos + avail >= 0) { VL_HUF_REFILL(); VL_HUF_SYM(out[i++] = (uint8_t)e); }
-#undef VL_HUF_REFILL
-#undef VL_HUF_SYM
-    r.finish();
-    if (i != nout || r.pos + avail != 0) zfail(V, B.frame, ZERR_HUF_STREAM);
+    while (i < nout && pos >= 0) { const uint32_t e = tab[peek64(s, pos) >> sh]; pos -= (int64_t)(e >> 8); out[i++] = (uint8_t)e; }
+    if (i != nout || pos != 0) zfail(V, B.frame, ZERR_HUF_STREAM);
 }
 
 // ---- sequence section: table descriptions; one lane per block (RFC 8878 3.1.1.3.2.1) ---------------------------------------------------
