@@ -171,6 +171,11 @@ int64_t vlscan_program_in_typed(const vlscan_program* prog, uint32_t leaf, int v
  * strconv.AppendFloat(f, 'f', -1, 64).  Host build of the routine the scan kernels run per row; returns the length
  * (<= 344) or -1 when cap is too small.  No NUL terminator is written. */
 int vlscan_format_float64(uint64_t ieee_bits, char* buf, size_t cap);
+/* parseMathNumber (lib/logstorage/pipe_math.go:1066-1080): the number a string value stands for in range(), le_field() and lt_field() - plain and
+ * `_`-separated decimals, durations ("1h5m"), byte sizes ("10KiB"), Go number literals (exponents, hexadecimal floats, base prefixes, inf), RFC 3339
+ * timestamps (nanoseconds; UTC where the text names no zone) and IPv4 addresses - or NaN.  Host build of the routine the row kernels run per
+ * value (csrc/vl_mathnum.cuh; decimal -> double is correctly rounded).  For tests against the oracle. */
+double vlscan_parse_math_number(const void* s, size_t len);
 /* how the program compiler reads a filter argument as a value of a typed column (tryParseUint64 / tryParseInt64 / tryParseFloat64Exact /
  * tryParseIPv4 / tryParseTimestampISO8601, values_encoder.go:428-850): 1 and *out = the value (int64 and float64 as their bits) when the text
  * is one, 0 when it is not, -1 for value types without a typed form.  For tests against the oracle. */

@@ -15,6 +15,7 @@
 #include "vl_engine.h"
 #include "vl_program.h"
 #include "vl_part.h"
+#include "vl_mathnum.cuh"
 
 using namespace vl;
 
@@ -776,6 +777,11 @@ int vlscan_parse_typed(int value_type, const void* s, size_t len, uint64_t* out)
     case VT_ISO8601: if (!vl::parse_iso8601(v, &i)) return 0; *out = (uint64_t)i; return 1;
     }
     return -1;
+}
+
+double vlscan_parse_math_number(const void* s, size_t len) {
+    if (len > 0xFFFFFFFFull) return NAN;
+    return vl::mn::parse_math_number((const uint8_t*)s, (uint32_t)len);
 }
 
 int vlscan_format_float64(uint64_t ieee_bits, char* buf, size_t cap) {

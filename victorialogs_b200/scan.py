@@ -67,7 +67,7 @@ class GenConfig(C.Structure):
 
 
 EXPORTS = ["vlscan_device_count", "vlscan_ctx_create", "vlscan_ctx_free", "vlscan_last_error", "vlscan_ctx_stream", "vlscan_ctx_sync",
-           "vlscan_program_create", "vlscan_program_free", "vlscan_program_nfields", "vlscan_program_field", "vlscan_program_leaf_tokens", "vlscan_program_prepass_tokens", "vlscan_program_in_hashes", "vlscan_program_in_typed", "vlscan_format_float64", "vlscan_parse_typed", "vlscan_eval_predicate",
+           "vlscan_program_create", "vlscan_program_free", "vlscan_program_nfields", "vlscan_program_field", "vlscan_program_leaf_tokens", "vlscan_program_prepass_tokens", "vlscan_program_in_hashes", "vlscan_program_in_typed", "vlscan_format_float64", "vlscan_parse_math_number", "vlscan_parse_typed", "vlscan_eval_predicate",
            "vlscan_batch_upload", "vlscan_batch_free", "vlscan_batch_nblocks", "vlscan_batch_rows", "vlscan_batch_words", "vlscan_batch_device_bytes",
            "vlscan_batch_generate", "vlscan_batch_download", "vlscan_host_blocks_get", "vlscan_host_blocks_field", "vlscan_host_blocks_bytes",
            "vlscan_host_blocks_free", "vlscan_host_blocks_compress", "vlscan_zstd_decompress", "vlscan_zstd_inspect", "vlscan_zstd_walk_digest", "vlscan_part_open", "vlscan_part_free", "vlscan_part_header", "vlscan_part_nblocks", "vlscan_part_block_header", "vlscan_part_timestamps",
@@ -154,6 +154,14 @@ def format_float64(bits):
     if n < 0:
         raise ValueError(bits)
     return buf.raw[:n]
+
+
+def parse_math_number(s):
+    """host build of the device's parseMathNumber (vlscan_parse_math_number) -> float (NaN when the value is no number)"""
+    L = lib()
+    L.vlscan_parse_math_number.restype = C.c_double
+    s = _b(s)
+    return L.vlscan_parse_math_number(s, C.c_size_t(len(s)))
 
 
 def device_count():
