@@ -142,13 +142,16 @@ int vlscan_ctx_sync(vlscan_ctx* ctx);                        /* cudaStreamSynchr
  *  16 SEQUENCE     (filter_sequence.go:12-22)       bytes(fieldName) varuint(n) n x bytes(phrase)           `f:seq(a, b, ...)`
  *  17 CONTAINS_ALL (filter_contains_all.go:12-20)   bytes(fieldName) varuint(n) n x bytes(value)            `f:contains_all(a, b, ...)`
  *  18 CONTAINS_ANY (filter_contains_any.go:12-20)   bytes(fieldName) varuint(n) n x bytes(value)            `f:contains_any(a, b, ...)`
+ *  19 EQ_FIELD     (filter_eq_field.go:14-22)       bytes(fieldName) bytes(otherFieldName)                  `f:eq_field(g)`
+ *  20 LE_FIELD     (filter_le_field.go:14-24)       bytes(fieldName) bytes(otherFieldName) u8(excludeEqualValues)   `f:le_field(g)`, `f:lt_field(g)`
+ *  21 RANGE        (filter_range.go:14-24)          bytes(fieldName) f64le(minValue) f64le(maxValue)        `f:range[a, b]`, `f:>a`, `f:<=b` ...
  *  22 TIME         (filter_time.go:14-23)           i64le(minTimestamp) i64le(maxTimestamp)                 `_time:[a, b]`, nanoseconds, inclusive
  * Token hashes, merged AND/OR per-field tokens, typed needles and regex automata are derived here, like the
  * sync.Once initialisers of the Go filters do on first use.  Returns <0 with an error text for malformed trees,
  * regexps that do not compile and regexps outside the supported syntax. */
 enum { VLSCAN_F_NOOP = 0, VLSCAN_F_PHRASE, VLSCAN_F_PREFIX, VLSCAN_F_EXACT, VLSCAN_F_IN, VLSCAN_F_REGEXP, VLSCAN_F_AND, VLSCAN_F_OR, VLSCAN_F_NOT,
        VLSCAN_F_EXACT_PREFIX = 9, VLSCAN_F_LEN_RANGE = 10, VLSCAN_F_STRING_RANGE = 11, VLSCAN_F_IPV4_RANGE = 12, VLSCAN_F_VALUE_TYPE = 13,
-       VLSCAN_F_ANY_CASE_PHRASE = 14, VLSCAN_F_ANY_CASE_PREFIX = 15, VLSCAN_F_SEQUENCE = 16, VLSCAN_F_CONTAINS_ALL = 17, VLSCAN_F_CONTAINS_ANY = 18, VLSCAN_F_TIME = 22 };
+       VLSCAN_F_ANY_CASE_PHRASE = 14, VLSCAN_F_ANY_CASE_PREFIX = 15, VLSCAN_F_SEQUENCE = 16, VLSCAN_F_CONTAINS_ALL = 17, VLSCAN_F_CONTAINS_ANY = 18, VLSCAN_F_EQ_FIELD = 19, VLSCAN_F_LE_FIELD = 20, VLSCAN_F_RANGE = 21, VLSCAN_F_TIME = 22 };
 int vlscan_program_create(const void* tree, size_t tree_len, vlscan_program** out);
 void vlscan_program_free(vlscan_program* prog);
 /* canonical names of the fields the tree references (so the caller lists only those columns per block) */

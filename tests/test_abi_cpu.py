@@ -69,7 +69,7 @@ def test_program_tokens_match_oracle(oracle):
     assert seen > 250
 
 
-PRODUCT_NEXT_KINDS = ("exact_prefix", "len_range", "string_range", "ipv4_range", "value_type", "any_case_phrase", "any_case_prefix", "sequence", "contains_all", "contains_any")
+PRODUCT_NEXT_KINDS = ("exact_prefix", "len_range", "string_range", "ipv4_range", "value_type", "any_case_phrase", "any_case_prefix", "sequence", "contains_all", "contains_any", "eq_field", "le_field", "range")
 
 
 def test_next_filter_kinds_compile_and_tokens(oracle):
@@ -83,7 +83,10 @@ def test_next_filter_kinds_compile_and_tokens(oracle):
         if k not in PRODUCT_NEXT_KINDS:
             continue
         p = vs.Program(build_filter(vs.Filter, spec))
-        assert p.fields() == [bytes.fromhex(spec["field"]) or b"_msg"]
+        want_fields = [bytes.fromhex(spec["field"]) or b"_msg"]
+        if k in ("eq_field", "le_field") and (bytes.fromhex(spec["arg"]) or b"_msg") not in want_fields:
+            want_fields.append(bytes.fromhex(spec["arg"]) or b"_msg")
+        assert p.fields() == want_fields
         if k in ("exact_prefix", "sequence"):
             want = build_filter(oracle.Filter, spec).tokens()
             if k == "sequence" and not [v for v in spec["values"] if v]:
@@ -100,10 +103,10 @@ def test_next_filter_kinds_compile_and_tokens(oracle):
                 pass        # compiled to a no-op (contains_all of nothing, contains_any with an empty value)
         seen[k] = seen.get(k, 0) + 1
     assert seen == {"exact_prefix": 62, "len_range": 30, "string_range": 48, "ipv4_range": 24, "value_type": 35, "any_case_phrase": 107, "any_case_prefix": 114, "sequence": 103,
-                    "contains_all": 104, "contains_any": 88}
+                    "contains_all": 104, "contains_any": 88, "eq_field": 78, "le_field": 139, "range": 62}
     with pytest.raises(vs.VlscanError):
         vs.Program(vs.Filter(bytes([vs.F_IPV4_RANGE, 1, ord("f")]) + bytes([0x80, 0x80, 0x80, 0x80, 0x10, 0]), "ipv4 bound > 32 bits"))
-    for kind in (19, 20, 21, 23):
+    for kind in (23, 24, 200):
         with pytest.raises(vs.VlscanError):
             vs.Program(vs.Filter(bytes([kind, 1, ord("f"), 1, ord("x")]), "kind not built yet"))
     # AND: exact_prefix contributes its tokens to the per-field bloom pre-pass (filter_and.go:141-143)

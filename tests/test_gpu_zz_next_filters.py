@@ -1,7 +1,8 @@
 """GPU parity for the filter kinds of SURVEY §8(f) rank 3 that libvlscan compiles (exact_prefix, len_range, string_range, ipv4_range,
-value_type, i(phrase), i(prefix*), seq(), contains_all(), contains_any()), through the C ABI against the CPU oracle and against the
-reference's own tables (filter_{exact_prefix,len_range,string_range,ipv4_range,value_type,any_case_phrase,any_case_prefix,sequence,
-contains_all,contains_any}_test.go, 715 cases in tests/golden/filter_cases_next.json).
+value_type, i(phrase), i(prefix*), seq(), contains_all(), contains_any(), eq_field(), le_field() / lt_field(), range()), through the C ABI
+against the CPU oracle and against the reference's own tables (filter_{exact_prefix,len_range,string_range,ipv4_range,value_type,
+any_case_phrase,any_case_prefix,sequence,contains_all,contains_any,eq_field,le_field,range}_test.go: all 994 cases of
+tests/golden/filter_cases_next.json).
 Bar: bit-exact bitmaps and counts.  (The file name sorts after the parity tests of the round-1 kinds on purpose.)"""
 import random
 
@@ -12,7 +13,7 @@ from golden_util import load_filter_cases, build_filter
 
 pytestmark = pytest.mark.gpu
 
-KINDS = ("exact_prefix", "len_range", "string_range", "ipv4_range", "value_type", "any_case_phrase", "any_case_prefix", "sequence", "contains_all", "contains_any")
+KINDS = ("exact_prefix", "len_range", "string_range", "ipv4_range", "value_type", "any_case_phrase", "any_case_prefix", "sequence", "contains_all", "contains_any", "eq_field", "le_field", "range")
 CASES = [c for c in load_filter_cases("filter_cases_next.json") if c["filter"]["kind"] in KINDS]
 
 
@@ -37,7 +38,7 @@ def check(env, blocks, of, gf, stage="ondisk"):
 
 def test_reference_tables(env):
     oracle, vs, pu, ctx = env
-    assert len(CASES) == 199 + 107 + 114 + 103 + 104 + 88
+    assert len(CASES) == 994   # every testFilterMatchForColumns case of the thirteen filters' test files
     for c in CASES:
         b = oracle.Block.from_columns(c["columns"])
         gf = build_filter(vs.Filter, c["filter"])
@@ -94,8 +95,28 @@ def test_every_column_kind(env):
             probes.append(("sequence", f, (lst,)))
             probes.append(("contains_all", f, (lst,)))
             probes.append(("contains_any", f, (lst,)))
+        for lo, hi in [(0, 0), (-1e9, 1e9), (1, 100), (100.5, 100.5), (10, 9), (-130 * 987654321, 0), (0.5, 2.5), (167772167, 167772167), (1.7e18, 1.8e18), (float("-inf"), float("inf")), (255, 1e30), (-0.0, 0.0),
+                       (1709640000e9, 1709647200e9), (37, 37)]:
+            probes.append(("range", f, (lo, hi)))
+        for g in fields:
+            probes.append(("eq_field", f, (g,)))
+            probes.append(("le_field", f, (g, False)))
+            probes.append(("le_field", f, (g, True)))
     for kind, field, args in probes:
         check(env, [blk], getattr(F, kind)(field, *args), getattr(G, kind)(field, *args))
+    # two-column filters on columns made to agree on some rows: same type on both sides (binary compare), dict against dict, typed against its text
+    n2 = 300
+    cols2 = [("a", [b"%d" % (i % 50) for i in range(n2)]), ("b", [b"%d" % ((i * 7) % 50) for i in range(n2)]), ("d1", [[b"x", b"y", b"10", b"9"][i % 4] for i in range(n2)]),
+             ("d2", [[b"x", b"10", b"y", b"100"][(i // 2) % 4] for i in range(n2)]), ("s", [b"%d" % (i % 50) if i % 3 else b"v%d" % i for i in range(n2)]),
+             ("f1", [b"%d.5" % (i % 20) for i in range(n2)]), ("f2", [b"%d.5" % ((i * 3) % 20) for i in range(n2)]), ("i1", [b"%d" % (i % 20 - 10) for i in range(n2)]), ("i2", [b"%d" % ((i * 3) % 20 - 10) for i in range(n2)]),
+             ("t1", [b"2024-03-%02dT00:00:00.000Z" % (1 + i % 9) for i in range(n2)]), ("t2", [b"2024-03-%02dT00:00:00.000Z" % (1 + (i * 5) % 9) for i in range(n2)]), ("c", [b"7"] * n2)]
+    blk2 = oracle.Block.from_columns(cols2)
+    names2 = [c[0] for c in cols2] + ["missing"]
+    for f in names2:
+        for g in names2:
+            check(env, [blk2], F.eq_field(f, g), G.eq_field(f, g))
+            check(env, [blk2], F.le_field(f, g, False), G.le_field(f, g, False))
+            check(env, [blk2], F.le_field(f, g, True), G.le_field(f, g, True))
     # combinators mixing old and new kinds
     of = F.and_([F.exact_prefix("msg", "row"), F.or_([F.len_range("lvl", 4, 4), F.ipv4_range("ip", 0x0A010000, 0x0A01FFFF)]), F.not_(F.string_range("u8", "1", "2")), F.value_type("ts", "iso8601")])
     gf = G.and_([G.exact_prefix("msg", "row"), G.or_([G.len_range("lvl", 4, 4), G.ipv4_range("ip", 0x0A010000, 0x0A01FFFF)]), G.not_(G.string_range("u8", "1", "2")), G.value_type("ts", "iso8601")])

@@ -497,8 +497,29 @@ struct ScanRun {
         uint8_t* action = ctx->action.as<uint8_t>(); uint64_t* payload = ctx->payload.as<uint64_t>(); uint64_t* leaf_bm = ctx->leaf_bm.as<uint64_t>();
         uint32_t* lens_blocks = ctx->lens_blocks.as<uint32_t>(); uint32_t* row_blocks = ctx->row_blocks.as<uint32_t>(); uint32_t* wc = ctx->work_count.as<uint32_t>();
         uint32_t* tb = ctx->tile_block.as<uint32_t>(); uint32_t* to = ctx->tile_off.as<uint32_t>();
-        // bm.isZero() per block, header dispatch + leaf bloom probe -> per-block action, and the work lists of the kernels below
         VL_CUDA(cudaMemsetAsync(wc, 0, WC_COUNT * 4, ctx->stream));
+        if (L.kind == F_EQ_FIELD || L.kind == F_LE_FIELD) {   // two columns, row by row (filter_eq_field.go, filter_le_field.go)
+            const int slot_b = field_slot[L.field2];
+            uint32_t* lens_b = tb;   // the tile table is idle for this leaf: it holds the second lens work list
+            k_plan_pair<<<cdiv((uint64_t)B.nblocks * 32, 256), 256, 0, ctx->stream>>>(P, B, (uint32_t)leaf_idx, slot, slot_b, reg, action, payload, lens_blocks, lens_b, row_blocks, wc, stats);
+            launch_check(ctx);
+            if (B.nwords) {
+                const int persistent = ctx->sm_count * 8;
+                const uint32_t *ro_a = nullptr, *ro_b = nullptr;
+                for (int side = 0; side < 2; side++) {
+                    const int sl = side ? slot_b : slot;
+                    if (sl < 0) continue;
+                    uint8_t* ready = ctx->ready[sl].as<uint8_t>();
+                    if (!ctx->ready_cleared[sl]) { VL_CUDA(cudaMemsetAsync(ready, 0, B.nblocks, ctx->stream)); ctx->ready_cleared[sl] = 1; }
+                    k_lens_offsets<<<persistent, 256, 0, ctx->stream>>>(B, sl, side ? lens_b : lens_blocks, wc, ctx->row_off8[sl].as<uint32_t>(), ready, stats, side ? WC_LENS2 : WC_LENS); launch_check(ctx);
+                    (side ? ro_b : ro_a) = ctx->row_off8[sl].as<uint32_t>();
+                }
+                k_row_pair<<<persistent, 256, 0, ctx->stream>>>(P, B, (uint32_t)leaf_idx, slot, slot_b, row_blocks, wc, payload, reg, ro_a, ro_b, leaf_bm, stats); launch_check(ctx);
+                k_apply_leaf<<<cdiv(B.nwords, 256), 256, 0, ctx->stream>>>(B, action, leaf_bm, reg); launch_check(ctx);
+            }
+            return;
+        }
+        // bm.isZero() per block, header dispatch + leaf bloom probe -> per-block action, and the work lists of the kernels below
         k_plan_leaf<<<cdiv(B.nblocks, VL_PLAN_WARPS), VL_PLAN_WARPS * 32, 0, ctx->stream>>>(P, B, (uint32_t)leaf_idx, slot, reg, action, payload, lens_blocks, row_blocks, tb, to, wc, stats);
         launch_check(ctx);
         if (slot >= 0 && B.nwords) {

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include "vl_hd.cuh"
 #include "vl_anycase.cuh"
+#include "vl_mathnum.cuh"
 #include "vl_types.h"
 
 namespace vl {
@@ -133,6 +134,10 @@ static __device__ bool leaf_match_string(const DevProgram& P, const DevLeaf& L, 
     case F_SEQUENCE: return match_sequence(s, n, PhraseList{P.blob + L.list_off, L.list_len});
     case F_CONTAINS_ALL: return match_all_phrases(s, n, PhraseList{P.blob + L.list_off, L.list_len});
     case F_CONTAINS_ANY: return match_any_phrase(s, n, PhraseList{P.blob + L.list_off, L.list_len});
+    case F_RANGE: {   // matchRange filter_range.go:352-355: the value as parseMathNumber reads it; NaN is outside every range
+        const double f = mn::parse_math_number(s, n);
+        return f >= __longlong_as_double((long long)L.rng_fmin) && f <= __longlong_as_double((long long)L.rng_fmax);
+    }
     }
     return true;
 }
@@ -255,7 +260,7 @@ static __global__ void k_prepass(DevProgram P, BatchView B, uint32_t pp_begin, u
 // items must be decoded, the 64 KiB tiles of the row-agnostic scan, blocks of the per-row matcher.  The lists are unordered (appended with
 // one atomic per CTA and list): every consumer only needs the set.
 #define VL_PLAN_WARPS 8
-enum { WC_LENS = 0, WC_TILES = 1, WC_ROW = 2, WC_COUNT = 4 };
+enum { WC_LENS = 0, WC_TILES = 1, WC_ROW = 2, WC_LENS2 = 3, WC_COUNT = 4 };   // WC_LENS2: the second column of a two-column leaf
 #define VL_TILE_BYTES 65536u                  /* row bytes per work item of the substring scan */
 static __global__ void __launch_bounds__(VL_PLAN_WARPS * 32) k_plan_leaf(DevProgram P, BatchView B, uint32_t leaf_idx, int slot, const uint64_t* __restrict__ reg,
                             uint8_t* __restrict__ action, uint64_t* __restrict__ payload, uint32_t* __restrict__ lens_blocks, uint32_t* __restrict__ row_blocks,
@@ -297,7 +302,7 @@ static __global__ void __launch_bounds__(VL_PLAN_WARPS * 32) k_plan_leaf(DevProg
         case F_REGEXP: act = regex_match(P.regexes[L.regex], P.blob, nullptr, 0) ? ACT_ALL : ACT_NONE; break;
         case F_LEN_RANGE: act = L.aux0 == 0 ? ACT_ALL : ACT_NONE; break;                                // matchLenRange("", min, max)
         case F_STRING_RANGE: act = (nl == 0 && L.needle2_len > 0) ? ACT_ALL : ACT_NONE; break;           // "" >= min && "" < max
-        case F_IPV4_RANGE: case F_VALUE_TYPE: act = ACT_NONE; break;
+        case F_IPV4_RANGE: case F_VALUE_TYPE: case F_RANGE: act = ACT_NONE; break;
         case F_ANY_CASE_PHRASE: act = nl == 0 ? ACT_ALL : ACT_NONE; break;                               // filter_any_case_phrase.go:88-95
         case F_ANY_CASE_PREFIX: act = ACT_NONE; break;                                                   // filter_any_case_prefix.go:92-97
         case F_SEQUENCE: case F_CONTAINS_ALL: case F_CONTAINS_ANY: act = leaf_match_string(P, L, nullptr, 0) ? ACT_ALL : ACT_NONE; break;   // the predicate on ""
@@ -340,7 +345,7 @@ static __global__ void __launch_bounds__(VL_PLAN_WARPS * 32) k_plan_leaf(DevProg
                     for (uint32_t s = 0; s < L.in_nsets; s++) { bloom_bytes += 8ull * sets[2 * s + 1]; any |= bloom_contains_all_warp(bloom, c->bloom_words, P.u64s + sets[2 * s], sets[2 * s + 1]); }
                     ok = any;
                 }
-            } else if (L.kind == F_ANY_CASE_PHRASE || L.kind == F_ANY_CASE_PREFIX) ok = true;   // tokens are case sensitive: no probe (filter_any_case_phrase.go:97-99)
+            } else if (L.kind == F_ANY_CASE_PHRASE || L.kind == F_ANY_CASE_PREFIX || L.kind == F_RANGE) ok = true;   // i(...): tokens are case sensitive, range(): no tokens - no probe
             else ok = probe(H, L.nhashes);
             if (!ok) act = ACT_NONE;
             else if (c->data_const) act = leaf_match_string(P, L, B.arena + c->data_off, (uint32_t)c->data_len) ? ACT_ALL : ACT_NONE, values_bytes = 1;
@@ -450,6 +455,15 @@ static __global__ void __launch_bounds__(VL_PLAN_WARPS * 32) k_plan_leaf(DevProg
                     act = ok ? ACT_ROW : ACT_NONE;
                 }
                 break;
+            case F_RANGE: {          // match*ByRange filter_range.go:216-347: header min / max first, then the encoded values themselves
+                const double fmn = __longlong_as_double((long long)L.rng_fmin), fmx = __longlong_as_double((long long)L.rng_fmax);
+                if (is_uintN) act = (fmx < 0 || L.rng_ulo > c->max_value || L.rng_uhi < c->min_value) ? ACT_NONE : ACT_ROW;
+                else if (vt == VT_INT64) act = (L.rng_ilo > (int64_t)c->max_value || L.rng_ihi < (int64_t)c->min_value) ? ACT_NONE : ACT_ROW;
+                else if (vt == VT_FLOAT64) act = (fmn > __longlong_as_double((long long)c->max_value) || fmx < __longlong_as_double((long long)c->min_value)) ? ACT_NONE : ACT_ROW;
+                else if (vt == VT_IPV4) act = (c->min_value > (uint64_t)L.rng_iphi || c->max_value < (uint64_t)L.rng_iplo) ? ACT_NONE : ACT_ROW;
+                else act = (fmx < 0 || L.rng_ilo > (int64_t)c->max_value || L.rng_ihi < (int64_t)c->min_value) ? ACT_NONE : ACT_ROW;   // iso8601: nanoseconds
+                break;
+            }
             case F_EXACT_PREFIX: {   // match*ByExactPrefix filter_exact_prefix.go:105-273
                 const bool is_uint = vt == VT_UINT8 || vt == VT_UINT16 || vt == VT_UINT32 || vt == VT_UINT64;
                 if (nl == 0) act = ACT_ALL;
@@ -561,10 +575,10 @@ static __global__ void k_finish_ondisk_cols(const uint8_t* __restrict__ arena, D
 // block.  One warp per block of the lens work list, one lane per bitmap word.  Sums are taken in 64 bits: a lens block whose items do not add
 // up to the data length (encoding.go:124-126) is reported, never wrapped into agreement.
 static __global__ void k_lens_offsets(BatchView B, int slot, const uint32_t* __restrict__ lens_blocks, const uint32_t* __restrict__ work_count,
-                               uint32_t* __restrict__ row_off8, uint8_t* __restrict__ ready, unsigned long long* __restrict__ stats) {
+                               uint32_t* __restrict__ row_off8, uint8_t* __restrict__ ready, unsigned long long* __restrict__ stats, int wc_idx = WC_LENS) {
     // one WARP per block of the lens work list (a block of 2000..6400 rows has 32..100 bitmap words: a whole CTA per block left most of its
     // threads idle between barriers); lane = bitmap word, 32 words per step, the running sum travels in a register
-    const uint32_t nwork = work_count[WC_LENS];
+    const uint32_t nwork = work_count[wc_idx];
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5, lane = lane_id();
     for (uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < nwork; j += warps) {
         const uint32_t b = lens_blocks[j];
@@ -925,6 +939,15 @@ static __global__ void k_row_match(DevProgram P, BatchView B, uint32_t leaf_idx,
         if (act == ACT_ROW_EQ) return raw == pay;                              // matchBinaryValue filter_exact.go:356-364
         if (act == ACT_ROW_IN) return in_contains_typed(L, P.u64s, vt, raw);   // matchAnyValue filter_in.go:187-200
         if (L.kind == F_IPV4_RANGE) return raw >= L.aux0 && raw <= L.aux1;     // only ipv4 columns get here (k_plan_leaf)
+        if (L.kind == F_RANGE) {
+            switch (vt) {
+            case VT_UINT8: case VT_UINT16: case VT_UINT32: case VT_UINT64: return raw >= L.rng_ulo && raw <= L.rng_uhi;
+            case VT_INT64: { const int64_t v = unzigzag64(raw); return v >= L.rng_ilo && v <= L.rng_ihi; }
+            case VT_FLOAT64: { const double f = __longlong_as_double((long long)raw); return f >= __longlong_as_double((long long)L.rng_fmin) && f <= __longlong_as_double((long long)L.rng_fmax); }
+            case VT_IPV4: return raw >= L.rng_iplo && raw <= L.rng_iphi;
+            default: return (int64_t)raw >= L.rng_ilo && (int64_t)raw <= L.rng_ihi;   // iso8601
+            }
+        }
         if (vt == VT_FLOAT64) return leaf_match_f64(P, L, raw);
         uint8_t buf[32];
         int n = encoded_to_string(vt, raw, buf);
@@ -1253,6 +1276,128 @@ static __global__ void k_scan_tile_sums(unsigned long long* __restrict__ tile_su
         __syncthreads();
     }
     if (threadIdx.x == 0) *total = carry;
+}
+
+// ---- two-column leaves: eq_field(), le_field() / lt_field() (filter_eq_field.go:60-237, filter_le_field.go:93-313) -------------------------------
+// the encoded bytes of row r of a values column (strings: the row; typed: the fixed-width value; dict: the id byte); false when the lens items are off
+static __device__ bool row_bytes(const BatchView& B, const DevColumn& c, uint32_t b, uint32_t r, const uint32_t* __restrict__ row_off8, const uint8_t** p, uint32_t* n) {
+    const uint8_t* data = B.arena + c.data_off;
+    if (c.data_const) { *p = data; *n = (uint32_t)c.data_len; return true; }
+    uint64_t off; uint32_t len;
+    if (c.lens_type >= 4) { len = c.lens_const; off = (uint64_t)r * len; }
+    else {
+        const uint8_t* lens = B.arena + c.lens_off;
+        uint32_t o = row_off8[(B.blk_word_off[b] << 3) + (r >> 3)];
+        for (uint32_t q = r & ~7u; q < r; q++) o += row_len(c, lens, q);
+        off = o; len = row_len(c, lens, r);
+    }
+    if (off + len > c.data_len) return false;
+    *p = data + off; *n = len;
+    return true;
+}
+// the string form of a row's value as blockResult.getValues yields it: const value, "" for a missing field, dict entry, row bytes, text of a typed value
+static __device__ bool row_string(const BatchView& B, const DevColumn* c, uint32_t b, uint32_t r, const uint32_t* __restrict__ row_off8, uint8_t* buf, const uint8_t** p, uint32_t* n) {
+    *p = buf; *n = 0;
+    if (!c || c->kind == COL_MISSING) return true;
+    if (c->kind == COL_CONST) { *p = B.arena + c->meta_off; *n = c->meta_len; return true; }
+    const uint8_t* v; uint32_t vn;
+    if (!row_bytes(B, *c, b, r, row_off8, &v, &vn)) return false;
+    if (c->vt == VT_STRING) { *p = v; *n = vn; return true; }
+    if (c->vt == VT_DICT) {
+        if (vn != 1 || v[0] >= c->dict_len) return false;
+        const uint32_t* dof = (const uint32_t*)(B.arena + c->meta_off);
+        *p = B.arena + c->meta_off + 4 * (c->dict_len + 1) + dof[v[0]]; *n = dof[v[0] + 1] - dof[v[0]];
+        return true;
+    }
+    if (vn != width_of_vt(c->vt)) return false;
+    const uint64_t raw = load_fixed_be(v, vn);
+    const int k = c->vt == VT_FLOAT64 ? fmt_f64(buf, raw) : encoded_to_string(c->vt, raw, buf);
+    *n = k > 0 ? (uint32_t)k : 0;
+    return true;
+}
+// leValuesString filter_le_field.go:283-297: numbers when both sides are numbers, else strings (bytewise, the shorter first on a tie)
+static __device__ bool le_values_string(const uint8_t* a, uint32_t an, const uint8_t* b2, uint32_t bn, bool excl) {
+    const double fa = mn::parse_math_number(a, an);
+    if (fa == fa) { const double fb = mn::parse_math_number(b2, bn); if (fb == fb) return excl ? fa < fb : fa <= fb; }
+    const uint32_t m = an < bn ? an : bn;
+    int cmp = 0;
+    for (uint32_t i = 0; i < m && !cmp; i++) cmp = (int)a[i] - (int)b2[i];
+    if (!cmp) cmp = an < bn ? -1 : an > bn ? 1 : 0;
+    return excl ? cmp < 0 : cmp <= 0;
+}
+// header-level decisions of a two-column leaf; one warp per block (lane 0 decides), work lists like k_plan_leaf
+static __global__ void __launch_bounds__(256) k_plan_pair(DevProgram P, BatchView B, uint32_t leaf_idx, int slot_a, int slot_b, const uint64_t* __restrict__ reg, uint8_t* __restrict__ action,
+                                                           uint64_t* __restrict__ payload, uint32_t* __restrict__ lens_a, uint32_t* __restrict__ lens_b, uint32_t* __restrict__ row_blocks,
+                                                           uint32_t* __restrict__ work_count, unsigned long long* __restrict__ stats) {
+    const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (b >= B.nblocks) return;
+    const DevLeaf& L = P.leaves[leaf_idx];
+    const bool alive = block_alive_warp(reg, B, b);
+    if (lane_id() != 0) return;
+    uint8_t act = ACT_NONE; uint64_t mode = PAIR_STRINGS;
+    if (alive && !L.always_none) {
+        const bool le = L.kind == F_LE_FIELD, excl = L.pair_excl != 0;
+        const DevColumn* ca = slot_a >= 0 ? &B.cols[(uint64_t)b * B.nfields + slot_a] : nullptr;
+        const DevColumn* cb = slot_b >= 0 ? &B.cols[(uint64_t)b * B.nfields + slot_b] : nullptr;
+        const int ka = ca ? ca->kind : COL_MISSING, kb = cb ? cb->kind : COL_MISSING;
+        // a const column with an empty value is no column at all for getConstColumnValue (block_search.go:232-276 returns "" for both)
+        const bool consta = ka == COL_CONST && ca->meta_len > 0, constb = kb == COL_CONST && cb->meta_len > 0;
+        const bool vala = ka == COL_VALUES, valb = kb == COL_VALUES;
+        if (consta && constb) {
+            const uint8_t* x = B.arena + ca->meta_off; const uint8_t* y = B.arena + cb->meta_off;
+            const bool m = le ? le_values_string(x, ca->meta_len, y, cb->meta_len, excl) : bytes_equal(x, ca->meta_len, y, cb->meta_len);
+            act = m ? ACT_ALL : ACT_NONE;
+        } else if (consta || constb) act = ACT_PAIR;                                      // one const: row strings
+        else if (!vala && !valb) act = (le && excl) ? ACT_NONE : ACT_ALL;                  // both fields missing: "" against ""
+        else if (!vala || !valb) act = ACT_PAIR;                                          // one missing: row strings
+        else if (ca->vt != cb->vt || ca->vt == VT_STRING) act = ACT_PAIR;
+        else { act = ACT_PAIR; mode = ca->vt == VT_DICT ? PAIR_DICT : PAIR_BINARY; }
+        if (act == ACT_PAIR) {
+            unsigned long long vb = 0, cols = 0;
+            if (vala) { vb += lens_stored_bytes(*ca, B.blk_rows[b]) + ca->data_len; cols++; if (ca->lens_type < 4 && !ca->data_const) lens_a[atomicAdd(&work_count[WC_LENS], 1u)] = b; }
+            if (valb) { vb += lens_stored_bytes(*cb, B.blk_rows[b]) + cb->data_len; cols++; if (cb->lens_type < 4 && !cb->data_const) lens_b[atomicAdd(&work_count[WC_LENS2], 1u)] = b; }
+            row_blocks[atomicAdd(&work_count[WC_ROW], 1u)] = b;
+            atomicAdd(&stats[ST_VALUES_BYTES], vb); atomicAdd(&stats[ST_COLUMNS_READ], cols);
+        }
+    }
+    action[b] = act; payload[b] = mode;
+}
+static __device__ __noinline__ bool pair_match_row(const DevProgram& P, const BatchView& B, const DevLeaf& L, const DevColumn* ca, const DevColumn* cb, uint32_t b, uint32_t r, uint32_t mode,
+                                                   const uint32_t* __restrict__ ro_a, const uint32_t* __restrict__ ro_b, unsigned long long* __restrict__ stats) {
+    const bool le = L.kind == F_LE_FIELD, excl = L.pair_excl != 0;
+    const uint8_t *x, *y; uint32_t xn, yn;
+    if (mode == PAIR_BINARY) {
+        if (!row_bytes(B, *ca, b, r, ro_a, &x, &xn) || !row_bytes(B, *cb, b, r, ro_b, &y, &yn)) { atomicMax(&stats[ST_ERROR], (unsigned long long)ERR_LENS_MISMATCH); return false; }
+        if (!le) return bytes_equal(x, xn, y, yn);                                        // applyFilterBinValue: same type, same binary form
+        if (ca->vt == VT_INT64 && xn == 8 && yn == 8) { const int64_t u = unzigzag64(ld_be64(x)), v = unzigzag64(ld_be64(y)); return excl ? u < v : u <= v; }
+        if (ca->vt == VT_FLOAT64 && xn == 8 && yn == 8) { const double u = __longlong_as_double((long long)ld_be64(x)), v = __longlong_as_double((long long)ld_be64(y)); return excl ? u < v : u <= v; }
+        return le_values_string(x, xn, y, yn, excl);   // uintN, ipv4, iso8601: their big-endian encodings go through leValuesString as they are (:246-252)
+    }
+    uint8_t bufa[VL_FMT_F64_MAX], bufb[VL_FMT_F64_MAX];
+    if (!row_string(B, ca, b, r, ro_a, bufa, &x, &xn) || !row_string(B, cb, b, r, ro_b, bufb, &y, &yn)) { atomicMax(&stats[ST_ERROR], (unsigned long long)ERR_DICT_INDEX); return false; }
+    return le ? le_values_string(x, xn, y, yn, excl) : bytes_equal(x, xn, y, yn);   // PAIR_DICT compares the entries, PAIR_STRINGS the string forms: same code
+}
+static __global__ void __launch_bounds__(256) k_row_pair(DevProgram P, BatchView B, uint32_t leaf_idx, int slot_a, int slot_b, const uint32_t* __restrict__ row_blocks, const uint32_t* __restrict__ work_count,
+                                                          const uint64_t* __restrict__ payload, const uint64_t* __restrict__ reg, const uint32_t* __restrict__ ro_a, const uint32_t* __restrict__ ro_b,
+                                                          uint64_t* __restrict__ leaf_bm, unsigned long long* __restrict__ stats) {
+    const uint32_t nwork = work_count[WC_ROW];
+    const DevLeaf& L = P.leaves[leaf_idx];
+    for (uint32_t j = blockIdx.x; j < nwork; j += gridDim.x) {
+        const uint32_t b = row_blocks[j], rows = B.blk_rows[b], mode = (uint32_t)payload[b];
+        const DevColumn* ca = slot_a >= 0 ? &B.cols[(uint64_t)b * B.nfields + slot_a] : nullptr;
+        const DevColumn* cb = slot_b >= 0 ? &B.cols[(uint64_t)b * B.nfields + slot_b] : nullptr;
+        const uint64_t w_lo = B.blk_word_off[b], w_hi = B.blk_word_off[b + 1];
+        for (uint64_t gw = w_lo + (threadIdx.x >> 5); gw < w_hi; gw += blockDim.x >> 5) {
+            const uint64_t live = reg[gw];   // only rows that are still selected (bm.forEachSetBit)
+            if (!live) { if (lane_id() == 0) leaf_bm[gw] = 0; continue; }
+            const uint32_t r0 = (uint32_t)(gw - w_lo) * 64, ra = r0 + lane_id(), rb = ra + 32;
+            bool ha = false, hb = false;
+            if (ra < rows && (live >> lane_id() & 1)) ha = pair_match_row(P, B, L, ca, cb, b, ra, mode, ro_a, ro_b, stats);
+            if (rb < rows && (live >> (32 + lane_id()) & 1)) hb = pair_match_row(P, B, L, ca, cb, b, rb, mode, ro_a, ro_b, stats);
+            const uint32_t lo = __ballot_sync(0xffffffffu, ha), hi = __ballot_sync(0xffffffffu, hb);
+            if (lane_id() == 0) leaf_bm[gw] = ((uint64_t)hi << 32) | lo;
+        }
+    }
 }
 
 // ---- digest of the result bitmaps (bench / tests; the oracle computes the same over its own bitmaps, oracle/vlo_api.cpp vlo_scan_generated) -------

@@ -422,6 +422,42 @@ class ProgramBuilder {
             P.leaf_tokens[l].clear();
             P.nodes[id].leaf = l; break;
         }
+        case F_RANGE: {   // filter_range.go:14-24: [minValue, maxValue] as float64, both ends inclusive
+            std::string f = bytes();
+            if (n_ - i_ < 16) throw ProgError("truncated filter tree");
+            uint64_t a = 0, b = 0;
+            for (int k = 0; k < 8; k++) { a |= (uint64_t)p_[i_ + k] << (8 * k); b |= (uint64_t)p_[i_ + 8 + k] << (8 * k); }
+            i_ += 16;
+            double mn, mx; memcpy(&mn, &a, 8); memcpy(&mx, &b, 8);
+            int l = new_leaf(kind, f, "", {});
+            DevLeaf& L = P.leaves[l];
+            L.always_none = mn > mx;
+            L.rng_fmin = a; L.rng_fmax = b;
+            const double c = std::ceil(mn), fl = std::floor(mx);
+            auto u64c = [](double v) -> uint64_t { return v < 0 ? 0 : v >= 18446744073709551616.0 ? UINT64_MAX : (uint64_t)v; };           // toUint64Clamp :380-388
+            auto i64c = [](double v) -> int64_t { return v < -9223372036854775808.0 ? INT64_MIN : v >= 9223372036854775808.0 ? INT64_MAX : (int64_t)v; };   // toInt64Clamp :396-404
+            auto u32c = [](double v) -> uint32_t { return v < 0 ? 0u : v > 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)v; };                    // toUint32Clamp :412-420
+            L.rng_ulo = u64c(c); L.rng_uhi = u64c(fl); L.rng_ilo = i64c(c); L.rng_ihi = i64c(fl); L.rng_iplo = u32c(c); L.rng_iphi = u32c(fl);
+            L.str_strategy = STR_ROW;
+            P.leaf_tokens[l].clear();
+            P.nodes[id].leaf = l; break;
+        }
+        case F_EQ_FIELD: case F_LE_FIELD: {   // filter_eq_field.go:14-22, filter_le_field.go:14-24
+            std::string f = bytes(), o = bytes();
+            uint32_t excl = 0;
+            if (kind == F_LE_FIELD) { if (i_ >= n_) throw ProgError("truncated filter tree"); excl = p_[i_++] ? 1 : 0; }
+            const int fa = P.field_id(f), fb = P.field_id(o);
+            if (fa == fb) {   // the same field on both sides: eq_field / le_field match every row, lt_field none
+                if (kind == F_LE_FIELD && excl) { int l = new_leaf(kind, f, "", {}); DevLeaf& L = P.leaves[l]; L.field2 = fb; L.pair_excl = 1; L.always_none = 1; P.leaf_tokens[l].clear(); P.nodes[id].leaf = l; }
+                else P.nodes[id].kind = F_NOOP;
+                break;
+            }
+            int l = new_leaf(kind, f, "", {});
+            DevLeaf& L = P.leaves[l];
+            L.field2 = fb; L.pair_excl = excl; L.str_strategy = STR_ROW;
+            P.leaf_tokens[l].clear();
+            P.nodes[id].leaf = l; break;
+        }
         case F_TIME: {   // filter_time.go:14-23: [minTimestamp, maxTimestamp] in nanoseconds, both ends inclusive; no field (the block's timestamps column)
             if (n_ - i_ < 16) throw ProgError("truncated filter tree");
             uint64_t mn = 0, mx = 0;

@@ -93,7 +93,9 @@ struct DevLeaf {
     uint32_t hashes2_off, nhashes2;    // i(...): probe hashes of the upper-cased tokens (iso8601 columns, filter_any_case_phrase.go:119-126)
     uint32_t list_off, list_len;       // seq() / contains_all() / contains_any(): the phrases as (varuint length, bytes)* in the blob; in_count = how many
     int32_t field2;                    // eq_field / le_field: the other field (index into the program's field table)
-    uint32_t pad3;
+    uint32_t pair_excl;                // le_field: 1 = lt_field (equal values excluded)
+    // range(): the bounds per column class (filter_range.go:246-347,362-420): u64 lo/hi, i64 lo/hi, f64 min/max (bits), u32 lo/hi
+    uint64_t rng_ulo, rng_uhi; int64_t rng_ilo, rng_ihi; uint64_t rng_fmin, rng_fmax; uint32_t rng_iplo, rng_iphi;
 };
 // DevLeaf.gates
 enum { GATE_DIGIT_PREFIX = 1,          // exact_prefix: !(prefix < "0" || prefix > "9")
@@ -115,7 +117,12 @@ enum { ACT_NONE = 0, ACT_ALL = 1, ACT_DICT = 2, ACT_SCAN = 3, ACT_FIXED_EQ = 4, 
        ACT_ROW = 6,         // per-row matcher: the leaf's string predicate on the value (typed values through their text)
        ACT_ROW_EQ = 7,      // per-row matcher: binary equality with the payload (typed column whose layout is not the fixed-width one)
        ACT_ROW_IN = 8,      // per-row matcher: membership in the leaf's typed value set
-       ACT_TIME = 9 };      // _time filter that partly overlaps the block: decode the timestamps, compare per row
+       ACT_TIME = 9,        // _time filter that partly overlaps the block: decode the timestamps, compare per row
+       ACT_PAIR = 10 };     // eq_field / le_field: two columns, row by row (payload: PAIR_* mode)
+// how a two-column leaf compares the rows of a block (filter_eq_field.go:60-121, filter_le_field.go:93-154)
+enum { PAIR_STRINGS = 0,   // the string forms of both values (const, missing = "", dict entry, text of a typed value)
+       PAIR_BINARY = 1,    // same typed valueType on both sides: the encoded values themselves
+       PAIR_DICT = 2 };    // both dict columns: the dictionary entries
 // scan verifier modes of the row-agnostic substring kernel
 enum { SCAN_PHRASE = 0, SCAN_PREFIX = 1, SCAN_CONTAINS = 2, SCAN_RX_DOTPLUS = 3, SCAN_RX_SUFFIX = 4, SCAN_RX_TAIL = 5 };
 

@@ -265,6 +265,19 @@ class Filter:
         return Filter(bytes([F_CONTAINS_ANY]) + _bytes(field) + _varuint(len(values)) + b"".join(_bytes(v) for v in values), "%r:contains_any(%r)" % (field, values))
 
     @staticmethod
+    def range(field, min_value, max_value):   # &filterRange{fieldName, minValue, maxValue}   `f:range[a, b]`, `f:>a` ... (float64 bounds, inclusive)
+        import struct
+        return Filter(bytes([F_RANGE]) + _bytes(field) + struct.pack("<dd", float(min_value), float(max_value)), "%r:range[%r, %r]" % (field, min_value, max_value))
+
+    @staticmethod
+    def eq_field(field, other_field):         # &filterEqField{fieldName, otherFieldName}    `f:eq_field(g)`
+        return Filter(bytes([F_EQ_FIELD]) + _bytes(field) + _bytes(other_field), "%r:eq_field(%r)" % (field, other_field))
+
+    @staticmethod
+    def le_field(field, other_field, exclude_equal=False):   # &filterLeField{...}            `f:le_field(g)` / `f:lt_field(g)`
+        return Filter(bytes([F_LE_FIELD]) + _bytes(field) + _bytes(other_field) + bytes([1 if exclude_equal else 0]), "%r:%s_field(%r)" % (field, "lt" if exclude_equal else "le", other_field))
+
+    @staticmethod
     def time(min_timestamp, max_timestamp):   # &filterTime{minTimestamp, maxTimestamp}      `_time:[a, b]` (nanoseconds, inclusive)
         return Filter(bytes([F_TIME]) + int(min_timestamp).to_bytes(8, "little", signed=True) + int(max_timestamp).to_bytes(8, "little", signed=True), "_time:[%d, %d]" % (min_timestamp, max_timestamp))
 
