@@ -408,6 +408,19 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
     VL_CUDA(cudaMemsetAsync(out->arena.p, 0, out->arena_bytes, ctx->stream));
     VL_CUDA(cudaEventRecord(ev_cleared, ctx->stream));
     VL_CUDA(cudaStreamWaitEvent(cs, ev_cleared, 0));
+    // The decoder is enqueued BEFORE anything below that can block this thread (packing pageable pieces through the staging ring, copies
+    // from pageable vectors): each launch group then runs as soon as its compressed bytes have landed, beside the DMA of the later ones.
+    const bool have_z = !ondisk.empty() || !ts_frames.empty();
+    double t_h2d = 0, t_zrun = 0;
+    if (dbg) t_h2d = now();
+    if (have_z) {
+        zjob.set_group_hook([&](uint64_t src_end) {
+            for (auto& m : zmarks) if (m.first >= src_end) { VL_CUDA(cudaStreamWaitEvent(ctx->stream, m.second, 0)); return; }
+            if (!zmarks.empty()) VL_CUDA(cudaStreamWaitEvent(ctx->stream, zmarks.back().second, 0));
+        });
+        zjob.run(ctx, ctx->zsrc.as<uint8_t>(), out->arena.as<uint8_t>());
+        if (dbg) t_zrun = now();
+    }
     copy_pieces(pieces, out->arena.as<uint8_t>());
     out->cols.ensure(std::max<size_t>(cols.size() * sizeof(DevColumn), 16));
     if (!cols.empty()) VL_CUDA(cudaMemcpyAsync(out->cols.p, cols.data(), cols.size() * sizeof(DevColumn), cudaMemcpyHostToDevice, cs));
@@ -419,18 +432,10 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
     }
     VL_CUDA(cudaEventRecord(ev_copied, cs));
     h2d += cols.size() * sizeof(DevColumn);
-    double t_h2d = 0, t_zrun = 0;
-    if (dbg) t_h2d = now();
-    if (!ondisk.empty() || !ts_frames.empty()) {
-        // regenerate the on-disk payloads in HBM (each launch group as soon as its compressed bytes have arrived), then derive
-        // lens_type / lens_const / data_const from the regenerated lens blocks
-        zjob.set_group_hook([&](uint64_t src_end) {
-            for (auto& m : zmarks) if (m.first >= src_end) { VL_CUDA(cudaStreamWaitEvent(ctx->stream, m.second, 0)); return; }
-            if (!zmarks.empty()) VL_CUDA(cudaStreamWaitEvent(ctx->stream, zmarks.back().second, 0));
-        });
-        zjob.run(ctx, ctx->zsrc.as<uint8_t>(), out->arena.as<uint8_t>());
+    const double t_enq = dbg ? now() : 0;
+    if (have_z) {
+        // the on-disk payloads are being regenerated in HBM; derive lens_type / lens_const / data_const from the regenerated lens blocks
         VL_CUDA(cudaStreamWaitEvent(ctx->stream, ev_copied, 0));
-        if (dbg) t_zrun = now();
         ctx->zcols.ensure(16 + ocols.size() * sizeof(OndiskCol));
         VL_CUDA(cudaMemsetAsync(ctx->zcols.p, 0, 16, ctx->stream));
         VL_CUDA(cudaMemcpyAsync(ctx->zcols.as<uint8_t>() + 16, ocols.data(), ocols.size() * sizeof(OndiskCol), cudaMemcpyHostToDevice, ctx->stream));
@@ -452,8 +457,8 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
     finish_batch_layout(ctx, out, rows);   // synchronises the stream => `owned`, `cols`, staging are safe to drop
     if (dbg) fprintf(stderr, "[vlscan upload] blocks=%llu arena=%.1f MB h2d=%.1f MB pieces=%zu+%zu pinned=%d: describe %.1f ms, alloc %.1f ms, copy %.1f ms (%.1f GB/s), "
                              "zstd %llu frames / %llu blocks / %llu sequences: enqueue %.1f ms, decode %.1f ms; layout %.1f ms\n", (unsigned long long)nblocks,
-                     out->arena_bytes / 1e6, h2d / 1e6, pieces.size(), zpieces.size(), (int)all_pinned, 1e3 * (t_desc - t_start), 1e3 * (t_alloc - t_desc), 1e3 * (t_h2d - t_alloc), h2d / 1e9 / std::max(t_h2d - t_alloc, 1e-9),
-                     (unsigned long long)zjob.frames(), (unsigned long long)zjob.compressed_blocks(), (unsigned long long)zjob.sequences(), 1e3 * (t_zrun > 0 ? t_zrun - t_h2d : 0), 1e3 * (t_copy - (t_zrun > 0 ? t_zrun : t_h2d)), 1e3 * (now() - t_copy));
+                     out->arena_bytes / 1e6, h2d / 1e6, pieces.size(), zpieces.size(), (int)all_pinned, 1e3 * (t_desc - t_start), 1e3 * (t_alloc - t_desc), 1e3 * (t_enq - (t_zrun > 0 ? t_zrun : t_h2d)), h2d / 1e9 / std::max(t_copy - t_start, 1e-9),
+                     (unsigned long long)zjob.frames(), (unsigned long long)zjob.compressed_blocks(), (unsigned long long)zjob.sequences(), 1e3 * (t_zrun > 0 ? t_zrun - t_h2d : 0), 1e3 * (t_copy - t_enq), 1e3 * (now() - t_copy));
     (void)all_pinned;
     h2d += out->nwords * 12 + nblocks * 12;
     if (stats) stats->h2d_bytes += h2d;

@@ -129,7 +129,7 @@ void ZstdJob::run(vlscan_ctx* ctx, const uint8_t* zsrc, uint8_t* arena) {
     if (!D.predef_ready) {
         D.predef.ensure(Z_FSE_SLOT_BYTES);
         k_zstd_predef<<<1, 32, 0, st>>>(D.predef.as<uint8_t>());
-        VL_CUDA(cudaFuncSetAttribute(k_seq_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Z_SEQ_CTA_BLOCKS * Z_FSE_SLOT_BYTES)));
+        VL_CUDA(cudaFuncSetAttribute(k_seq_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Z_SEQ_CTA_LANES * (Z_FSE_SLOT_BYTES + Z_LINEBUF))));
         VL_CUDA(cudaFuncSetAttribute(k_huf_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Z_HUF_CTA_BLOCKS * Z_HUF_TABLE * 2)));
         ctx->launches++; VL_CUDA(cudaGetLastError());
         D.predef_ready = true;
@@ -188,7 +188,7 @@ void ZstdJob::run(vlscan_ctx* ctx, const uint8_t* zsrc, uint8_t* arena) {
         if (nl) { begin(1); k_huf_decode<<<cdiv_u(nl, Z_HUF_CTA_BLOCKS), Z_HUF_CTA_BLOCKS * 4, Z_HUF_CTA_BLOCKS * Z_HUF_TABLE * 2, st>>>(W, L + g.lit_lo, nl); launched(); }
         if (ns) {
             begin(2); k_fse_build<<<cdiv_u(ns, 64), 64, 0, st>>>(W, L + g.seq_lo, ns); launched();
-            begin(3); k_seq_decode<<<cdiv_u(ns, Z_SEQ_CTA_BLOCKS), Z_SEQ_CTA_BLOCKS * 4, Z_SEQ_CTA_BLOCKS * Z_FSE_SLOT_BYTES, st>>>(W, L + g.seq_lo, ns); launched();
+            begin(3); k_seq_decode<<<cdiv_u(ns, Z_SEQ_CTA_LANES), 64, Z_SEQ_CTA_LANES * (Z_FSE_SLOT_BYTES + Z_LINEBUF), st>>>(W, L + g.seq_lo, ns); launched();
         }
         VL_CUDA(cudaEventRecord(ev_entropy, st));
         VL_CUDA(cudaStreamWaitEvent(xs, ev_entropy, 0));

@@ -375,65 +375,99 @@ static __global__ void __launch_bounds__(64) k_fse_build(ZView V, const uint32_t
     V.bstate[bi].seq_bits_off = off;
 }
 
-// ---- sequence bitstream -> (literal length, match length, offset); FOUR lanes per block (RFC 8878 3.1.1.3.2.1.2 / 3.1.1.4) ------------------
-// Every sequence is three table lookups whose results decide where the next three happen: a chain of dependent steps per block.  The tables
-// (3840 bytes per block) live in shared memory, which caps a CTA at Z_SEQ_CTA_BLOCKS blocks; round 1 ran that chain on ONE lane per block,
-// i.e. two warps per SM with ~220 dependent instructions per sequence (887 cycles per sequence, 3 % of the warp slots active).  Now the three
-// FSE states of a block sit on three lanes of a quad: lane 0 literal lengths, lane 1 match lengths, lane 2 offsets (lane 3 rides along).  Per
-// sequence each lane looks up ITS state, the three exchange their two bit widths with shuffles inside the quad, every lane cuts ITS two fields
-// (value bits, state-update bits) out of the shared bit window and steps its state; lane 2 resolves repeat offsets (it gets `literal length
-// == 0` from lane 0).  The window (identical in the four lanes) is read straight from the staging buffer, one aligned 8-byte word ahead, the
-// next 128-byte line prefetched into L1 - the quad's four loads coalesce into one.  7 warps per SM instead of 2, ~4x shorter chain.
-static const uint32_t Z_SEQ_CTA_BLOCKS = 56;
-static const uint32_t Z_SEQ_CTA_LANES = Z_SEQ_CTA_BLOCKS;   // (name kept for the host side: blocks per CTA)
-struct QuadBitReader {
-    uint64_t w0, w1, w2, w3;   // w0:w1:w2 = the 192-bit window, w3 = the next word, requested one word early
-    uint64_t wi;               // address >> 3 of the word held in w3
-    uint32_t off;              // bits of w0 already consumed (0..63 between calls)
-    int64_t pos;               // unread bits of the stream
-    static __device__ __forceinline__ uint64_t word(uint64_t w) { return *(const volatile uint64_t*)(uintptr_t)(w << 3); }
-    static __device__ __forceinline__ void prefetch_line(uint64_t w) { asm volatile("prefetch.global.L1 [%0];" ::"l"((uintptr_t)((w & ~(uint64_t)15) << 3))); }
-    __device__ __forceinline__ bool init(const uint8_t* p, uint32_t len) {
-        w0 = w1 = w2 = w3 = 0; off = 0; pos = 0; wi = 0;
-        if (!len) return false;
-        uint32_t last = p[len - 1];
-        if (!last) return false;
-        pos = (int64_t)len * 8 - (int64_t)(__clz(last) - 23);   // the end mark and the padding above it are not part of the stream
-        const uint64_t abits = (uint64_t)(uintptr_t)p * 8 + (uint64_t)pos;   // absolute bit address one past the first unread bit
-        const uint64_t wtop = (abits + 63) >> 6, whi = wtop - 1;
-        wi = whi - 3;
-        w0 = word(whi); w1 = word(whi - 1); w2 = word(whi - 2); w3 = word(wi);
-        prefetch_line(wi - 16);
-        off = (uint32_t)((wtop << 6) - abits);
-        return true;
+// ---- sequence bitstream -> (literal length, match length, offset); one lane per block (RFC 8878 3.1.1.3.2.1.2 / 3.1.1.4) ------------------
+// Every sequence is three table lookups whose results decide where the next three happen: a chain of dependent steps per block.  With the
+// tables in HBM (10 KB per block, far more than L2 over all blocks in flight) each link costs a DRAM round trip; so a CTA stages the tables
+// of Z_SEQ_CTA_LANES blocks (3840 bytes each) in shared memory and its lanes run their chains against those.  Shared memory caps an SM at 56
+// chains = two warps, so nothing hides latency and the kernel's time is (instructions per sequence) x (issue-to-issue latency): round 1's loop
+// was 277 SASS instructions per sequence (six independent field extractions out of a 192-bit register window, a refill loop with cp.async
+// line management inside it).  Round 2 rewrote the loop around a cheaper window:
+//   * the stream lives in a 256-byte ring per lane in shared memory, topped up by at most ONE predicated 16-byte cp.async per sequence (a
+//     sequence consumes at most 89 bits = 11.1 bytes, so one chunk per step always keeps up); `cp.async.wait_group 3` guarantees that what
+//     the reader touches (it stays 160 bytes ahead) has landed - no data-dependent branch, no loop;
+//   * per sequence FOUR aligned ring words are loaded and funnel-shifted into a 96-bit left-aligned window c2:c1:c0; the three value fields
+//     (offset bits | match-length bits + literal-length bits, <= 31 + 32) and the three state updates (<= 26 bits, cut as ONE field and split
+//     with bfe) come out of it with one funnel shift each; the position is a single 32-bit bit index relative to a 256-byte aligned origin;
+//   * errors are sticky bits checked once after the loop; the last sequence (no state update) is peeled off.
+// (Round 2 also tried FOUR lanes per block - one FSE state per lane of a quad, widths exchanged by shuffles, 7 warps per SM: byte-exact, but
+// 67 ms instead of 38 ms on 100 M rows of C2; the shuffles put ~90 instructions on every sequence of every quad.  profiles/zstd_history_r02.md)
+static const uint32_t Z_SEQ_CTA_LANES = 56;
+static const uint32_t Z_LINEBUF = 272;    // bytes of shared memory per lane: the 256-byte ring + a 16-byte skew against bank conflicts
+static const uint32_t Z_SEQ_LEAD = 160;   // the ring is kept filled this many bytes below the reader
+static __device__ __forceinline__ uint32_t lds_u32(uint32_t sa) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sa)); return v; }
+static __device__ __forceinline__ uint32_t bfe_u32(uint32_t a, uint32_t pos, uint32_t len) { uint32_t d; asm("bfe.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(pos), "r"(len)); return d; }
+static __device__ __forceinline__ uint32_t top_bits(uint32_t x, uint32_t n) { return __funnelshift_rc(x, 0u, 32u - n); }   // n = 0..32 highest bits of x
+struct SeqLane {
+    // stream
+    const uint8_t* gorg;      // 256-byte aligned origin in the staging buffer, below the stream
+    uint32_t ring;            // shared-memory address of the lane's ring; byte a of the origin space lives at ring + (a & 255)
+    uint32_t p;               // bit index (origin space) one past the first unread bit
+    uint32_t fc;              // 16-byte chunks >= fc have been requested
+    // tables
+    const uint16_t* tr; const uint8_t* sy; const uint32_t* llv; const uint32_t* mlv;
+    // chain state
+    uint32_t sl, so, sm, r1, r2, r3, ndirty, sum_ll, sum_ml, sticky;
+    uint4* out;
+    __device__ __forceinline__ void fetch_chunk() {
+        fc--;
+        const uint32_t sa = ring + ((fc & 15u) << 4);
+        const uint8_t* g = gorg + (size_t)fc * 16;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(g) : "memory");
     }
-    // n bits (0..32) that start t bits below the top of w0 (t counts the consumed bits too); t + n <= 192
-    __device__ __forceinline__ uint32_t field(uint32_t t, uint32_t n) const {
-        uint32_t s = t + n;
-        s = s ? s : 1;
-        const bool low = s > 128;
-        const uint64_t a = low ? w1 : w0, b = low ? w2 : w1;
-        const uint32_t e = low ? s - 64 : s;
-        uint64_t v;
-        if (e <= 64) v = a >> (64 - e);
-        else { const uint32_t sh = e - 64; v = (sh < 64 ? a << sh : 0ull) | (b >> (64 - sh)); }
-        return (uint32_t)v & (uint32_t)((1ull << n) - 1);
+    __device__ __forceinline__ void window(uint32_t& c2, uint32_t& c1, uint32_t& c0) const {
+        const uint32_t k = (p - 1u) >> 5, s = (0u - p) & 31u;
+        const uint32_t w3 = lds_u32(ring + ((k << 2) & 252u)), w2 = lds_u32(ring + (((k - 1u) << 2) & 252u));
+        const uint32_t w1 = lds_u32(ring + (((k - 2u) << 2) & 252u)), w0 = lds_u32(ring + (((k - 3u) << 2) & 252u));
+        c2 = __funnelshift_l(w2, w3, s); c1 = __funnelshift_l(w1, w2, s); c0 = __funnelshift_l(w0, w1, s);
     }
-    __device__ __forceinline__ void consume(uint32_t n) {   // n <= 128
-        off += n; pos -= n;
-        while (off >= 64) {
-            w0 = w1; w1 = w2; w2 = w3; off -= 64; wi--;
-            w3 = word(wi);
-            if ((wi & 15) == 15) prefetch_line(wi - 16);   // entering a new line: ask for the one below it
+    template <bool LAST>
+    __device__ __forceinline__ void step() {
+        const uint32_t tl = tr[sl], to = tr[so], tm = tr[sm];
+        const uint32_t oc = sy[so], vl = llv[sy[sl]], vm = mlv[sy[sm]];
+        // keep the ring ahead of the reader: one chunk per step is enough in the worst case
+        if (p < fc * 128u + Z_SEQ_LEAD * 8u && fc > 0) fetch_chunk();
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 3;" ::: "memory");
+        uint32_t c2, c1, c0;
+        window(c2, c1, c0);
+        // bit layout of one sequence, top down: offset bits, match-length bits, literal-length bits, then (unless it is the last sequence)
+        // the LL, ML, OF state updates
+        const uint32_t nL = vl >> 24, nM = vm >> 24, n2 = nM + nL;
+        const uint32_t ov = (1u << oc) + top_bits(c2, oc);
+        const uint32_t v2 = top_bits(__funnelshift_l(c1, c2, oc), n2);   // oc <= 31
+        const uint32_t ml = (vm & 0xFFFFFFu) + (v2 >> nL), ll = (vl & 0xFFFFFFu) + bfe_u32(v2, 0, nL);
+        const uint32_t o3 = oc + n2;                                     // <= 63
+        if (!LAST) {
+            const uint32_t bL = tl >> 12, bM = tm >> 12, bO = to >> 12, n3 = bL + bM + bO;   // <= 26
+            const bool up = o3 < 32;
+            const uint32_t v3 = top_bits(__funnelshift_l(up ? c1 : c0, up ? c2 : c1, o3), n3);
+            sl = Z_FSE_LL + (tl & 0xFFFu) + (v3 >> (bM + bO));
+            sm = Z_FSE_ML + (tm & 0xFFFu) + bfe_u32(v3, bO, bM);
+            so = Z_FSE_OF + (to & 0xFFFu) + bfe_u32(v3, 0, bO);
+            p -= o3 + n3;
+        } else p -= o3;
+        // repeat offsets (RFC 8878 3.1.1.5), resolved on the fly; unknown ones are DIRTY = 0xFFFFFFFF (real offsets stay below 2^31)
+        uint32_t o;
+        if (ov > 3) { o = ov - 3; r3 = r2; r2 = r1; r1 = o; }
+        else {
+            const uint32_t idx = ov + (ll == 0 ? 1 : 0);
+            if (idx == 1) o = r1;
+            else {
+                o = idx == 2 ? r2 : idx == 3 ? r3 : (r1 == 0xFFFFFFFFu ? r1 : r1 - 1);
+                if (idx != 2) r3 = r2;
+                r2 = r1; r1 = o;
+            }
         }
+        ndirty += (r1 | r2 | r3) >> 31;   // once the three are known they stay known: the dirty steps form a prefix
+        *out++ = make_uint4(ll, ml, o, ov);
+        sum_ll += ll; sum_ml += ml;       // each term < 2^18: a sum that passes 2^31 sets a sticky bit before it can wrap
+        sticky |= p | sum_ll | sum_ml;
     }
-    __device__ __forceinline__ uint32_t read(uint32_t n) { uint32_t v = field(off, n); consume(n); return v; }
 };
-static __global__ void __launch_bounds__(Z_SEQ_CTA_BLOCKS * 4) k_seq_decode(ZView V, const uint32_t* __restrict__ list, uint32_t n) {
+static __global__ void __launch_bounds__(64) k_seq_decode(ZView V, const uint32_t* __restrict__ list, uint32_t n) {
     extern __shared__ __align__(16) uint8_t s_fse[];
     __shared__ uint32_t s_llv[36], s_mlv[53];   // code -> value baseline | extra bits << 24
-    const uint32_t first = blockIdx.x * Z_SEQ_CTA_BLOCKS;
-    const uint32_t here = min(Z_SEQ_CTA_BLOCKS, n - first);
+    const uint32_t first = blockIdx.x * Z_SEQ_CTA_LANES;
+    const uint32_t here = min(Z_SEQ_CTA_LANES, n - first);
     if (threadIdx.x < 36) s_llv[threadIdx.x] = Z_LL_BASE[threadIdx.x] | ((uint32_t)Z_LL_BITS[threadIdx.x] << 24);
     if (threadIdx.x < 53) s_mlv[threadIdx.x] = Z_ML_BASE[threadIdx.x] | ((uint32_t)Z_ML_BITS[threadIdx.x] << 24);
     for (uint32_t it = 0; it < here; it++) {   // slot layout == shared layout: 240 chunks of 16 bytes, each from the slot its table lives in
@@ -449,80 +483,58 @@ static __global__ void __launch_bounds__(Z_SEQ_CTA_BLOCKS * 4) k_seq_decode(ZVie
         }
     }
     __syncthreads();
-    const uint32_t local = threadIdx.x >> 2, sub = threadIdx.x & 3;   // sub: 0 literal lengths, 1 match lengths, 2 offsets, 3 spare
-    if (local >= here) return;                                         // whole quads leave together
-    const uint32_t qbase = (threadIdx.x & 31) & ~3u;                   // first lane of this quad inside its warp
-    const uint32_t qmask = 0xFu << qbase;
-    const uint32_t bi = list[first + local];
+    if (threadIdx.x >= here) return;
+    const uint32_t bi = list[first + threadIdx.x];
     const ZBlock& B = V.blocks[bi];
     if (V.frame_err[B.frame]) return;
     const uint32_t off = V.bstate[bi].seq_bits_off;
-    const uint16_t* tr = (const uint16_t*)(s_fse + (size_t)local * Z_FSE_SLOT_BYTES);
-    const uint8_t* sy = s_fse + (size_t)local * Z_FSE_SLOT_BYTES + 2 * Z_FSE_ENTRIES;
     const int ll_al = B.ll_slot == Z_PREDEF ? 6 : V.fse_state[B.ll_slot].ll_al;
     const int of_al = B.of_slot == Z_PREDEF ? 5 : V.fse_state[B.of_slot].of_al;
     const int ml_al = B.ml_slot == Z_PREDEF ? 6 : V.fse_state[B.ml_slot].ml_al;
-    QuadBitReader r;
-    if (off >= B.size || !r.init(V.src + B.src + off, B.size - off)) { if (sub == 0) zfail(V, B.frame, ZERR_SEQ_STREAM); return; }
-    // initial states, in stream order: literal lengths, offsets, match lengths
-    const uint32_t i_ll = r.read(ll_al), i_of = r.read(of_al), i_ml = r.read(ml_al);
-    uint32_t st = sub == 0 ? Z_FSE_LL + i_ll : sub == 1 ? Z_FSE_ML + i_ml : Z_FSE_OF + i_of;   // this lane's state (lane 3 shadows the offsets lane)
-    const uint32_t tbase = sub == 0 ? Z_FSE_LL : sub == 1 ? Z_FSE_ML : Z_FSE_OF;
-    uint32_t* __restrict__ out = (uint32_t*)(V.seqs + B.seq_base);
-    unsigned long long sum = 0;   // lane 0: literal lengths, lane 1: match lengths
-    bool ok = true;
-    // Repeat offsets (RFC 8878 3.1.1.5) are resolved on the fly by the offsets lane.  A block that follows other blocks with sequences does
-    // not know the three offsets it starts with: they are tracked as DIRTY until real offsets have pushed them out of the history, and
-    // k_seq_resolve redoes only that prefix of the block once the predecessor's final history is known.
+    if (off >= B.size) { zfail(V, B.frame, ZERR_SEQ_STREAM); return; }
+    const uint64_t st = B.src + off;           // first byte of the bitstream; it ends with the block
+    const uint32_t len = B.size - off;
+    const uint32_t last = V.src[st + len - 1];
+    if (!last) { zfail(V, B.frame, ZERR_SEQ_STREAM); return; }   // the end mark is missing
+    SeqLane L;
+    const uint64_t org = (st & ~255ull) - 256;   // the staging buffer keeps 512 bytes of headroom in front of the first stream
+    const uint32_t s0 = (uint32_t)(st - org) * 8;
+    L.gorg = V.src + org;
+    L.ring = (uint32_t)__cvta_generic_to_shared(s_fse + (size_t)Z_SEQ_CTA_LANES * Z_FSE_SLOT_BYTES + (size_t)threadIdx.x * Z_LINEBUF);
+    L.p = s0 + len * 8 - (uint32_t)(__clz(last) - 23);   // the end mark and the padding above it are not part of the stream
+    L.fc = ((L.p - 1u) >> 7) + 1u;                       // p >= s0 >= 2048: at least 16 chunks lie below
+#pragma unroll
+    for (int q = 0; q < 12; q++) L.fetch_chunk();
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    L.tr = (const uint16_t*)(s_fse + (size_t)threadIdx.x * Z_FSE_SLOT_BYTES);
+    L.sy = s_fse + (size_t)threadIdx.x * Z_FSE_SLOT_BYTES + 2 * Z_FSE_ENTRIES;
+    L.llv = s_llv; L.mlv = s_mlv;
+    {   // initial states: LL, OF, ML (<= 9 + 8 + 9 bits)
+        uint32_t c2, c1, c0;
+        L.window(c2, c1, c0);
+        L.sl = Z_FSE_LL + top_bits(c2, ll_al);
+        L.so = Z_FSE_OF + top_bits(__funnelshift_l(c1, c2, ll_al), of_al);
+        L.sm = Z_FSE_ML + top_bits(__funnelshift_l(c1, c2, ll_al + of_al), ml_al);
+        L.p -= ll_al + of_al + ml_al;
+        (void)c0;
+    }
+    // Repeat offsets are resolved on the fly.  A block that follows other blocks with sequences does not know the three offsets it starts
+    // with: they are tracked as DIRTY until real offsets have pushed them out of the history, and k_seq_resolve redoes only that prefix of
+    // the block once the predecessor's final history is known.
     const uint32_t DIRTY = 0xFFFFFFFFu;
-    uint32_t r1 = B.rep_known ? 1 : DIRTY, r2 = B.rep_known ? 4 : DIRTY, r3 = B.rep_known ? 8 : DIRTY;
+    L.r1 = B.rep_known ? 1 : DIRTY; L.r2 = B.rep_known ? 4 : DIRTY; L.r3 = B.rep_known ? 8 : DIRTY;
+    L.ndirty = 0; L.sum_ll = 0; L.sum_ml = 0; L.sticky = L.p;
+    L.out = V.seqs + B.seq_base;
     const uint32_t nseq = B.nseq;
-    uint32_t clean_from = B.rep_known ? 0 : nseq + 1;
-    for (uint32_t i = 0; i < nseq; i++) {
-        const uint32_t te = tr[st];        // baseline | nbits << 12 of this lane's state
-        const uint32_t code = sy[st];
-        const uint32_t vb = sub == 0 ? s_llv[code] : sub == 1 ? s_mlv[code] : 0;   // literal / match lengths: value baseline | extra bits << 24
-        if (r.pos < 0) { ok = false; break; }
-        const bool more = i + 1 < nseq;
-        // widths of this lane's two fields; the layout of one sequence, top down: offset bits, match-length bits, literal-length bits, then
-        // (unless it is the last sequence) the LL, ML, OF state updates
-        const uint32_t xb = sub < 2 ? vb >> 24 : code, sb = more ? te >> 12 : 0;   // an offset code IS its number of extra bits (baseline 1 << code)
-        const uint32_t vbase = sub < 2 ? (vb & 0xFFFFFF) : (1u << code);
-        const uint32_t pack = xb | (sb << 8);
-        const uint32_t p_ll = __shfl_sync(qmask, pack, qbase), p_ml = __shfl_sync(qmask, pack, qbase + 1), p_of = __shfl_sync(qmask, pack, qbase + 2);
-        const uint32_t t0 = r.off, t1 = t0 + (p_of & 0xFF), t2 = t1 + (p_ml & 0xFF), t3 = t2 + (p_ll & 0xFF), t4 = t3 + (p_ll >> 8), t5 = t4 + (p_ml >> 8), t6 = t5 + (p_of >> 8);
-        const uint32_t xt = sub == 0 ? t2 : sub == 1 ? t1 : t0;          // where this lane's value bits start
-        const uint32_t stt = sub == 0 ? t3 : sub == 1 ? t4 : t5;         // ... and its state-update bits
-        const uint32_t val = vbase + r.field(xt, xb);
-        const uint32_t nst = tbase + (te & 0xFFF) + r.field(stt, sb);
-        r.consume(t6 - t0);
-        const uint32_t ll = __shfl_sync(qmask, val, qbase);               // the offsets lane needs "literal length == 0"
-        if (sub == 2) {
-            const uint32_t ov = val;
-            uint32_t o;
-            if (ov > 3) { o = ov - 3; r3 = r2; r2 = r1; r1 = o; }
-            else {
-                uint32_t idx = ov + (ll == 0 ? 1 : 0);
-                if (idx == 1) o = r1;
-                else {
-                    o = idx == 2 ? r2 : idx == 3 ? r3 : (r1 == DIRTY ? DIRTY : r1 - 1);
-                    if (idx != 2) r3 = r2;
-                    r2 = r1; r1 = o;
-                }
-            }
-            if (clean_from > nseq && r1 != DIRTY && r2 != DIRTY && r3 != DIRTY) clean_from = i + 1;
-            *(uint2*)(out + 4 * (size_t)i + 2) = make_uint2(o, ov);   // record = (literal length, match length, offset, raw offset value)
-        } else if (sub < 2) { out[4 * (size_t)i + sub] = val; sum += val; }
-        if (more) st = nst;
-    }
-    if (!__all_sync(qmask, ok) || r.pos != 0) { if (sub == 0) zfail(V, B.frame, ZERR_SEQ_STREAM); return; }
-    const unsigned long long sum_ll = __shfl_sync(qmask, sum, qbase), sum_ml = __shfl_sync(qmask, sum, qbase + 1);
-    if (sum_ll > B.lit_regen || sum_ml + B.lit_regen > 0xFFFFFFFFull) { if (sub == 0) zfail(V, B.frame, ZERR_SEQ_STREAM); return; }
-    if (sub == 2) {
-        ZBlockState& S = V.bstate[bi];
-        S.out_len = (uint32_t)(B.lit_regen + sum_ml);
-        S.clean_from = clean_from; S.rep[0] = r1; S.rep[1] = r2; S.rep[2] = r3;
-    }
+    for (uint32_t i = 0; i + 1 < nseq; i++) L.step<false>();
+    if (nseq) L.step<true>();
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    // sticky bit 31: the position ran below the origin (wrapped) or a sum left the range of any valid block
+    if ((L.sticky >> 31) || L.p != s0 || L.sum_ll > B.lit_regen) { zfail(V, B.frame, ZERR_SEQ_STREAM); return; }
+    ZBlockState& S = V.bstate[bi];
+    S.out_len = B.lit_regen + L.sum_ml;
+    S.clean_from = B.rep_known ? 0 : L.ndirty + 1;   // first step after which all three offsets were known; nseq + 1: never
+    S.rep[0] = L.r1; S.rep[1] = L.r2; S.rep[2] = L.r3;
 }
 
 // ---- block output bases + the repeat offsets k_seq_decode could not know; one lane per frame (RFC 8878 3.1.1.5) ---------------------------
