@@ -107,7 +107,8 @@ typedef struct vlscan_gen_config {
     uint32_t rows_per_block;
     uint32_t hot_block_permille;
     uint32_t hit_row_permille;
-    uint32_t columns_mask;       /* bit0 _msg, bit1 level, bit2 path, bit3 status */
+    uint32_t columns_mask;       /* bit0 _msg, bit1 level, bit2 path, bit3 status; bits 8..11: vocabulary focus for selectivity sweeps
+                                    (0 = a vocabulary row draws one of the 12 entries uniformly, k = always entry k - 1) */
 } vlscan_gen_config;
 
 /* ---- library / worker context ---------------------------------------------------------------------------------- */

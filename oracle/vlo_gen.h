@@ -17,7 +17,7 @@ struct vlo_gen_config {
     uint32_t rows_per_block;       // R (2 MB estimated-JSON rule evaluated by the caller for the field count)
     uint32_t hot_block_permille;   // block clustering: fraction of blocks that contain vocabulary rows
     uint32_t hit_row_permille;     // selectivity: in hot blocks, probability that a row draws a vocabulary template
-    uint32_t columns_mask;         // bit0 _msg, bit1 level, bit2 path, bit3 status
+    uint32_t columns_mask;         // bit0 _msg, bit1 level, bit2 path, bit3 status; bits 8..11: vocabulary focus (0 = uniform, k = always entry k - 1)
 };
 }
 
@@ -49,7 +49,8 @@ inline std::string gen_value(const vlo_gen_config& c, uint64_t b, uint64_t i, in
     case GEN_COL_MSG: {
         uint64_t r0 = gen_rnd(c.seed, b, i, 0);
         const char* tmpl = "message";
-        if (gen_block_hot(c, b) && (r0 % 1000) < c.hit_row_permille) tmpl = GEN_VOCAB[(r0 >> 32) % 12];
+        const uint32_t focus = (c.columns_mask >> 8) & 15;   // 1..12: every vocabulary row draws entry focus - 1; 0: uniform
+        if (gen_block_hot(c, b) && (r0 % 1000) < c.hit_row_permille) tmpl = GEN_VOCAB[focus ? focus - 1 : (r0 >> 32) % 12];
         uint32_t ip = (uint32_t)gen_rnd(c.seed, b, i, 1);
         uint64_t ua = gen_rnd(c.seed, b, i, 2), ub = gen_rnd(c.seed, b, i, 3), u64 = gen_rnd(c.seed, b, i, 4);
         char buf[256];

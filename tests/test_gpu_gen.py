@@ -29,13 +29,14 @@ def cfgs(oracle, vs, **kw):
 
 def test_generator_matches_reference_writer(env):
     oracle, vs, ctx = env
-    for kw in (dict(), dict(rows_per_block=64, total_rows=64 * 9), dict(rows_per_block=3000, total_rows=3000 * 3 + 64, hot_block_permille=1000, hit_row_permille=900)):
+    for kw in (dict(), dict(rows_per_block=64, total_rows=64 * 9), dict(rows_per_block=3000, total_rows=3000 * 3 + 64, hot_block_permille=1000, hit_row_permille=900),
+               dict(columns_mask=15 | (4 << 8), hit_row_permille=500), dict(columns_mask=1 | (12 << 8), hot_block_permille=1000, hit_row_permille=1000, rows_per_block=200, total_rows=900)):   # vocabulary focus
         ocfg, gcfg = cfgs(oracle, vs, **kw)
         nb = (ocfg.total_rows + ocfg.rows_per_block - 1) // ocfg.rows_per_block
         batch = ctx.generate(gcfg, 0, nb)
         assert batch.rows == ocfg.total_rows and batch.nblocks == nb
         dl = ctx.download(batch)
-        assert dl.field_names == [b"_msg", b"level", b"path", b"status"]
+        assert dl.field_names == [n for k, n in enumerate([b"_msg", b"level", b"path", b"status"]) if ocfg.columns_mask >> k & 1]
         for b in range(nb):
             ob = oracle.Block.generated(ocfg, b)
             assert dl.rows[b] == ob.rows and not ob.consts
@@ -49,6 +50,20 @@ def test_generator_matches_reference_writer(env):
                 assert gc["data"] == data, (b, oc.name)
                 assert gc["bloom"] == oc.bloom, (b, oc.name, len(gc["bloom"]), len(oc.bloom))
         batch.free()
+
+
+def test_vocabulary_focus_sets_the_selectivity(env):
+    """bits 8..11 of columns_mask: every vocabulary row carries ONE entry, so hit_row_permille is the selectivity of that entry's query"""
+    oracle, vs, ctx = env
+    ocfg, gcfg = cfgs(oracle, vs, columns_mask=1 | (4 << 8), hot_block_permille=1000, hit_row_permille=500, rows_per_block=2000, total_rows=40000)
+    batch = ctx.generate(gcfg, 0, 20)
+    st = ctx.scan_resident(vs.Program(vs.Filter.regexp("_msg", "conn.*refused")), batch)
+    want = sum(len(oracle.bitmap_rows(oracle.Block.generated(ocfg, b).search(oracle.Filter.regexp("_msg", "conn.*refused")), 2000)) for b in range(20))
+    assert st.rows_matched == want and 0.45 < want / 40000 < 0.55
+    batch.free()
+    for bad in (13 << 8, 1 << 12):
+        with pytest.raises(vs.VlscanError):
+            ctx.generate(vs.GenConfig(seed=SEED, total_rows=100, rows_per_block=100, hot_block_permille=0, hit_row_permille=0, columns_mask=1 | bad), 0, 1)
 
 
 def test_generator_block_ranges_are_consistent(env):

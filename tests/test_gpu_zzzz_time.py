@@ -159,9 +159,9 @@ def test_gather_timestamps_and_values(env):
             d[c.name] = [c.dict[it[0]] if c.value_type == 2 else oracle.encoded_to_string(c.value_type, it) for it in items]   # 2 = valueTypeDict
         for name, vals_in in rows_all[bi][1].items():
             if name != "f64":
-                assert d[name.encode()] == vals_in, name
+                assert d.get(name.encode(), [b""] * blk.rows) == vals_in, name   # a column of empty values is not stored at all
         stored.append(d)
-    assert any(a != b for bi in range(len(blocks)) for a, b in zip(stored[bi][b"f64"], rows_all[bi][1]["f64"]))   # the lossy case is covered
+    assert any(a != b for bi in range(len(blocks)) for a, b in zip(stored[bi].get(b"f64", []), rows_all[bi][1]["f64"]))   # the lossy case is covered
     F, G = oracle.Filter, vs.Filter
     for of, gf in [(F.phrase("lvl", "error"), G.phrase("lvl", "error")), (F.prefix("msg", "row 1"), G.prefix("msg", "row 1")), (F.noop(), G.noop()), (F.phrase("msg", "absent"), G.phrase("msg", "absent")),
                    (F.time(rows_all[2][0][0] + 1, rows_all[6][0][-1] - 1), G.time(rows_all[2][0][0] + 1, rows_all[6][0][-1] - 1))]:

@@ -7,9 +7,10 @@ is an argument rather than a format rule, in the exact form the kernels use:
   run happens against the state before the run - which is also why the kernel may issue the loads of several copy steps before the first
   store, as it does since round 2); the per-warp ring in shared memory with its validity rule (`gend - q < RING`, group span
   < RING, `ring_lo` after an oversized group).
-* QuadBitReader (the sequence decoder's bit window; the model class below keeps its round-1 name): a 192-bit window over aligned 8-byte words;
-  `field(t, n)` cuts n bits that start t bits below the top; `consume` slides whole words.  The six fields of one sequence are cut at
-  precomputed offsets from the same window (since round 2 by three lanes, two fields each)."""
+  Since round 2 the literal runs travel together with the FAR matches (sources wholly in front of the group) in chunks of 256 bytes, and
+  the dependency runs cover the NEAR matches only.
+* SeqLane (the sequence decoder's bit window): a 96-bit window funnel-shifted out of four aligned words of a 256-byte ring that is topped
+  up by one 16-byte chunk per sequence; three fields per sequence (offset bits | match + literal length bits | the three state updates)."""
 import random
 
 RING = 4096
@@ -48,16 +49,10 @@ def execute_model(lits, seqs, prefix):
         gend = out_run + O
         ring_ok = O < RING
         o_start = [io[j] - grp[j][0] - grp[j][1] for j in range(cnt)]
-        for j in range(cnt):                                   # literal runs of the whole group
-            for k in range(grp[j][0]):
-                v = lits[lit_run + il[j] - grp[j][0] + k]
-                at = out_run + o_start[j] + k
-                dst[at] = v
-                ring[at & (RING - 1)] = v
         amd = [out_run + o_start[j] + grp[j][0] for j in range(cnt)]
         ml = [q[1] for q in grp]
         off = [q[2] for q in grp]
-        dep = []
+        dep, far = [], []
         for j in range(cnt):
             s = amd[j] - off[j]
             e = s + min(ml[j], off[j])
@@ -67,15 +62,40 @@ def execute_model(lits, seqs, prefix):
                 if idx < cnt and amd[idx] < e:
                     lo += st
             dep.append(lo - 1 if lo > 0 and amd[lo - 1] + ml[lo - 1] > s else -1)
+            far.append(ml[j] > 0 and e <= out_run)             # reads only what lies in front of the group
+        for j in range(cnt):                                   # a far match is done before any near one starts: wait for the last near match in front of it
+            if dep[j] >= 0 and far[dep[j]]:
+                below = [i for i in range(dep[j]) if not far[i]]
+                dep[j] = below[-1] if below else -1
+        # phase 1: literal runs and far matches, chunks of 256 bytes of their concatenation; inside a chunk all loads precede all stores
+        jobs = []
+        for j in range(cnt):
+            for k in range(grp[j][0]):
+                jobs.append(("lit", lit_run + il[j] - grp[j][0] + k, out_run + o_start[j] + k))
+        for j in range(cnt):
+            if far[j]:
+                for kk in range(ml[j]):
+                    jobs.append(("dst", amd[j] - off[j] + (kk if off[j] >= ml[j] else kk % off[j]), amd[j] + kk))
+        for c0 in range(0, len(jobs), 256):
+            snap, rsnap = bytes(dst), bytes(ring)
+            for kind, src, at in jobs[c0:c0 + 256]:
+                if kind == "lit":
+                    v = lits[src]
+                else:
+                    v = rsnap[src & (RING - 1)] if (ring_ok and src >= ring_lo and gend - src < RING) else snap[src]
+                dst[at] = v
+                ring[at & (RING - 1)] = v
+        # phase 2: near matches in dependency order
         cur = 0
         while cur < cnt:
             n = 0
             while cur + n < cnt and dep[cur + n] < cur:
                 n += 1
             n = max(n, 1)
-            snap, rsnap = bytes(dst), bytes(ring)              # a run reads only what existed before the run
-            for j in range(cur, cur + n):
-                for kk in range(ml[j]):
+            run = [(j, kk) for j in range(cur, cur + n) if not far[j] for kk in range(ml[j])]
+            for c0 in range(0, len(run), 128):                 # four steps of 32 bytes: loads, then stores
+                snap, rsnap = bytes(dst), bytes(ring)
+                for j, kk in run[c0:c0 + 128]:
                     sa = amd[j] - off[j] + (kk if off[j] >= ml[j] else kk % off[j])
                     v = rsnap[sa & (RING - 1)] if (ring_ok and sa >= ring_lo and gend - sa < RING) else snap[sa]
                     dst[amd[j] + kk] = v
@@ -110,74 +130,88 @@ def test_executor_model_equals_sequential_lz():
         assert execute_model(lits, seqs, prefix) == lz_reference(lits, seqs, prefix), trial
 
 
-class LineReaderModel:
-    def __init__(self, mem, p_off, ln):
+M32 = 0xFFFFFFFF
+
+
+def funnelshift_l(lo, hi, sh):       # high 32 bits of (hi:lo) << (sh & 31)
+    return (((hi << 32 | lo) << (sh & 31)) >> 32) & M32
+
+
+def top_bits(x, n):                  # __funnelshift_rc(x, 0, 32 - n): the n = 0..32 highest bits of x
+    return x >> (32 - n) if n else 0
+
+
+class SeqWindowModel:
+    """SeqLane (k_seq_decode): a 32-bit bit index `p` relative to a 256-byte aligned origin below the stream; per sequence four aligned
+    ring words -> 96-bit left-aligned window c2:c1:c0; offset bits, (match + literal length) bits and the three state updates come out
+    with one funnel shift each.  The ring is modelled as the memory itself addressed mod 256 through a dict of fetched chunks, with the
+    kernel's top-up rule (one 16-byte chunk per step while the reader is closer than LEAD bytes) - reading a chunk that was never
+    requested, or one whose ring slot has been overwritten, fails the test."""
+    LEAD = 160
+
+    def __init__(self, mem, st, ln):
         self.mem = mem
-        last = mem[p_off + ln - 1]
+        last = mem[st + ln - 1]
         assert last
-        self.pos = ln * 8 - (8 - (last.bit_length() - 1))
-        abits = p_off * 8 + self.pos
-        wtop = (abits + 63) >> 6
-        whi = wtop - 1
-        self.wi = whi - 2
-        self.w0, self.w1, self.w2 = self.word(whi), self.word(whi - 1), self.word(self.wi)
-        self.off = (wtop << 6) - abits
+        self.org = (st & ~255) - 256
+        self.s0 = (st - self.org) * 8
+        self.p = self.s0 + ln * 8 - (8 - (last.bit_length() - 1))
+        self.fc = ((self.p - 1) >> 7) + 1
+        self.slot = {}                                         # ring slot (0..15) -> chunk index it holds
+        for _ in range(12):
+            self.fetch()
 
-    def word(self, w):
-        return int.from_bytes(self.mem[w * 8:w * 8 + 8], "little")
+    def fetch(self):
+        self.fc -= 1
+        self.slot[self.fc & 15] = self.fc
 
-    def field(self, t, n):
-        s = t + n or 1
-        low = s > 128
-        a, b = (self.w1, self.w2) if low else (self.w0, self.w1)
-        e = s - 64 if low else s
-        if e <= 64:
-            v = a >> (64 - e)
-        else:
-            sh = e - 64
-            v = (((a << sh) & M64) if sh < 64 else 0) | (b >> (64 - sh))
-        return v & ((1 << n) - 1) & 0xFFFFFFFF
+    def word(self, j):                                         # aligned 32-bit word j of the origin space, through the ring
+        assert self.slot.get((j >> 2) & 15) == j >> 2, "ring does not hold the chunk the reader needs"
+        a = self.org + 4 * j
+        return int.from_bytes(self.mem[a:a + 4], "little")
 
-    def consume(self, n):
-        self.off += n
-        self.pos -= n
-        while self.off >= 64:
-            self.w0, self.w1 = self.w1, self.w2
-            self.off -= 64
-            self.wi -= 1
-            self.w2 = self.word(self.wi)
+    def window(self):
+        k, s = (self.p - 1) >> 5, (-self.p) & 31
+        w3, w2, w1, w0 = self.word(k), self.word(k - 1), self.word(k - 2), self.word(k - 3)
+        return funnelshift_l(w2, w3, s), funnelshift_l(w1, w2, s), funnelshift_l(w0, w1, s)
+
+    def step(self, oc, nM, nL, bL, bM, bO):
+        if self.p < self.fc * 128 + self.LEAD * 8 and self.fc > 0:
+            self.fetch()
+        c2, c1, c0 = self.window()
+        n2 = nM + nL
+        x_of = top_bits(c2, oc)
+        v2 = top_bits(funnelshift_l(c1, c2, oc), n2)
+        x_ml, x_ll = v2 >> nL, v2 & ((1 << nL) - 1)
+        o3, n3 = oc + n2, bL + bM + bO
+        a, b = (c2, c1) if o3 < 32 else (c1, c0)
+        v3 = top_bits(funnelshift_l(b, a, o3), n3)
+        self.p -= o3 + n3
+        return [x_of, x_ml, x_ll, v3 >> (bM + bO), (v3 >> bO) & ((1 << bM) - 1), v3 & ((1 << bO) - 1)]
 
 
-def test_line_reader_model_equals_plain_bit_reader():
+def test_seq_window_model_equals_plain_bit_reader():
     rng = random.Random(3)
     for trial in range(300):
-        ln = rng.randint(1, 300)
-        p_off = 600 + rng.randint(0, 40)
-        mem = bytearray(rng.getrandbits(8) for _ in range(p_off + ln + 64))
-        if mem[p_off + ln - 1] == 0:
-            mem[p_off + ln - 1] = 1
+        ln = rng.choice([1, 2, 7, 40, 300, 3000])
+        st = 512 + rng.randint(0, 600)
+        mem = bytearray(rng.getrandbits(8) for _ in range(st + ln + 64))
+        if mem[st + ln - 1] == 0:
+            mem[st + ln - 1] = 1
         mem = bytes(mem)
-        lr = LineReaderModel(mem, p_off, ln)
-        value, pos = int.from_bytes(mem[p_off:p_off + ln], "little"), lr.pos
+        w = SeqWindowModel(mem, st, ln)
+        value, pos = int.from_bytes(mem[st:st + ln], "little"), w.p - w.s0
 
         def ref(n):
             nonlocal pos
             pos -= n
             return (value >> pos) & ((1 << n) - 1) if n else 0
 
+        heavy = trial % 3 == 0                                 # worst case: 89 bits per sequence, step after step
         while pos > 0:
-            if trial % 2 == 0:                                 # one field at a time
-                n = rng.randint(0, min(32, pos))
-                got = lr.field(lr.off, n)
-                lr.consume(n)
-                assert got == ref(n), (trial, n)
-            else:                                              # the six fields of a sequence from one window (<= 89 bits)
-                ws = [rng.randint(0, 31), rng.randint(0, 16), rng.randint(0, 16), rng.randint(0, 9), rng.randint(0, 9), rng.randint(0, 8)]
-                if sum(ws) > pos:
-                    ws = [min(pos, 5), 0, 0, 0, 0, 0]
-                t, got = lr.off, []
-                for w in ws:
-                    got.append(lr.field(t, w))
-                    t += w
-                lr.consume(t - lr.off)
-                assert got == [ref(w) for w in ws], (trial, ws)
+            ws = [31, 16, 16, 9, 9, 8] if heavy else [rng.randint(0, 31), rng.randint(0, 16), rng.randint(0, 16), rng.randint(0, 9), rng.randint(0, 9), rng.randint(0, 8)]
+            if sum(ws) > pos:
+                ws = [min(pos, 5), 0, 0, 0, 0, 0]
+            got = w.step(*ws)
+            assert got == [ref(x) for x in ws], (trial, ws)
+        assert w.p == w.s0

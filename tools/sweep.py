@@ -5,7 +5,11 @@ For every (workload, hot_block_permille, hit_row_permille) point: generate the d
 (CUDA events on the ctx stream), and report rows/s, ms/step, how many blocks the bloom pre-pass pruned ("bloom-only" blocks: their
 values are never read) versus fully decoded, algorithmic bytes and the achieved HBM GB/s of the step and of the dominant kernel.
 
-    python tools/sweep.py --rows 100000000 --out profiles/sweep_r01.json
+Vocabulary rows all carry the entry the workload's query looks for (`columns_mask` bits 8..11, the generator's focus knob), so
+hit_row_permille x hot_block_permille IS the row selectivity of the leading leaf: the sweep reaches 0.5 and 1.0, not just the 8 % a uniform
+draw over the 12 vocabulary entries allows.
+
+    python tools/sweep.py --rows 100000000 --out profiles/sweep_r02.json
 """
 import argparse
 import json
@@ -22,7 +26,8 @@ def main():
     ap.add_argument("--rows", type=int, default=100_000_000)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workloads", default="C2,C3,C4")
+    ap.add_argument("--workloads", default="C1,C2,C3,C4")
+    ap.add_argument("--no-focus", action="store_true", help="uniform vocabulary draw (the round-1 sweep)")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     import torch
@@ -37,9 +42,10 @@ def main():
         rows = args.rows - args.rows % wl["rows_per_block"]
         nb = rows // wl["rows_per_block"]
         prog = vs.Program(wl["tree"](vs.Filter))
+        focus = 0 if args.no_focus else {"C1": 1, "C2": 2, "C3": 4, "C4": 3}[name]   # error / timeout / conn 10.0.0.7 refused / GET /api/v1/items
         for hot in (1000, 300, 50):
-            for hit in (1, 10, 100, 500):
-                cfg = vs.GenConfig(seed=bench.SEED, total_rows=rows, rows_per_block=wl["rows_per_block"], hot_block_permille=hot, hit_row_permille=hit, columns_mask=wl["mask"])
+            for hit in (1, 10, 100, 500, 1000):
+                cfg = vs.GenConfig(seed=bench.SEED, total_rows=rows, rows_per_block=wl["rows_per_block"], hot_block_permille=hot, hit_row_permille=hit, columns_mask=wl["mask"] | (focus << 8))
                 batch = ctx.generate(cfg, 0, nb)
                 for _ in range(args.warmup):
                     ctx.scan_resident(prog, batch, want_stats=False)
@@ -54,7 +60,7 @@ def main():
                 ms = e0.elapsed_time(e1) / args.steps
                 st = ctx.last_scan_stats()
                 step_bytes = st.values_bytes + st.bloom_probe_bytes + st.bitmap_bytes
-                r = {"workload": name, "logsql": wl["logsql"], "rows": rows, "blocks": nb, "hot_block_permille": hot, "hit_row_permille": hit,
+                r = {"workload": name, "logsql": wl["logsql"], "rows": rows, "blocks": nb, "hot_block_permille": hot, "hit_row_permille": hit, "vocabulary_focus": focus,
                      "selectivity": st.rows_matched / rows, "rows_per_s": rows / (ms / 1e3), "ms_per_step": ms, "blocks_matched": int(st.blocks_matched),
                      "columns_read": int(st.columns_read), "values_bytes": int(st.values_bytes), "bloom_probe_bytes": int(st.bloom_probe_bytes),
                      "step_hbm_gbs": step_bytes / 1e9 / (ms / 1e3), "scan_kernel_gbs": (st.scan_kernel_bytes / 1e9) / (st.scan_kernel_ms / 1e3) if st.scan_kernel_ms > 0 else None,

@@ -38,7 +38,8 @@ __device__ __forceinline__ int put_hex(uint8_t* d, uint64_t v, int width) { for 
 __device__ int gen_msg(const vlscan_gen_config& c, bool hot, uint64_t b, uint64_t i, uint8_t* d) {
     uint64_t r0 = gen_rnd(c.seed, b, i, 0);
     int n = 0;
-    if (hot && (r0 % 1000) < c.hit_row_permille) n += put_str(d + n, D_VOCAB[(r0 >> 32) % 12]); else n += put_str(d + n, "message");
+    const uint32_t focus = (c.columns_mask >> 8) & 15;   // 1..12: every vocabulary row draws entry focus - 1 (selectivity sweeps); 0: uniform
+    if (hot && (r0 % 1000) < c.hit_row_permille) n += put_str(d + n, D_VOCAB[focus ? focus - 1 : (r0 >> 32) % 12]); else n += put_str(d + n, "message");
     n += put_str(d + n, " for the stream "); n += fmt_u64(d + n, b);
     n += put_str(d + n, " and worker "); n += fmt_u64(d + n, b % 7);
     n += put_str(d + n, "; ip="); n += fmt_ipv4(d + n, (uint32_t)gen_rnd(c.seed, b, i, 1));
@@ -244,6 +245,7 @@ extern "C" int vlscan_batch_generate(vlscan_ctx* ctx, const vlscan_gen_config* c
         int slot_of[4]; bt->nfields = 0;
         for (int k = 0; k < 4; k++) { slot_of[k] = -1; if (c.columns_mask >> k & 1) { slot_of[k] = (int)bt->nfields++; bt->field_names.push_back(names[k]); } }
         if (!bt->nfields) throw BadInput("generator: empty columns_mask");
+        if (((c.columns_mask >> 8) & 15) > 12 || (c.columns_mask >> 12)) throw BadInput("generator: bits 8..11 of columns_mask select a vocabulary entry 1..12, higher bits must be zero");
         // pass A
         uint32_t cap = 1; while (cap < c.rows_per_block * 40u) cap <<= 1;   // <= ~26 tokens per _msg row
         int grid = std::min<int>(std::max<uint32_t>(nb, 1), ctx->sm_count * 2);

@@ -613,8 +613,10 @@ static __global__ void __launch_bounds__(128) k_execute(ZView V, const uint32_t*
         const uint8_t rle_byte = lit_rle ? p[B.lit_hdr] : 0;
         const uint4* __restrict__ sq = V.seqs + B.seq_base;
         uint32_t lit_run = 0, out_run = blk_base;   // out_run: frame position where the group starts
+        uint4 qn = lane < B.nseq ? sq[lane] : make_uint4(0, 0, 0, 0);
         for (uint32_t g = 0; g < B.nseq; g += 32) {
-            uint4 q = g + lane < B.nseq ? sq[g + lane] : make_uint4(0, 0, 0, 0);
+            const uint4 q = qn;
+            qn = g + 32 + lane < B.nseq ? sq[g + 32 + lane] : make_uint4(0, 0, 0, 0);   // the next group's records travel while this group is executed
             uint32_t il = q.x, io = q.x + q.y;   // inclusive prefix sums over the 32 sequences of the group
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) { uint32_t a = __shfl_up_sync(0xffffffffu, il, d), b = __shfl_up_sync(0xffffffffu, io, d); if ((int)lane >= d) { il += a; io += b; } }
@@ -625,19 +627,8 @@ static __global__ void __launch_bounds__(128) k_execute(ZView V, const uint32_t*
             // Inside a group stores are not in position order (all literals first), so two positions of one group must not share a ring
             // slot: a group spanning Z_RING bytes or more reads from HBM only and leaves the ring untrusted below its end.
             const bool ring_ok = O < Z_RING;
-            // literal runs of the whole group: byte k belongs to the sequence j with il[j-1] <= k < il[j]
-            for (uint32_t k0 = 0; k0 < T; k0 += 32) {
-                uint32_t k = k0 + lane;
-                uint32_t lo = 0;   // smallest j with il[j] > k, by 5 shuffle probes
-#pragma unroll
-                for (int s = 16; s; s >>= 1) { uint32_t v = __shfl_sync(0xffffffffu, il, (lo + s - 1) & 31); if (v <= k) lo += s; }
-                uint32_t js = __shfl_sync(0xffffffffu, lit_start, lo & 31), jo = __shfl_sync(0xffffffffu, o_start, lo & 31);
-                if (k < T) { uint8_t v = lit_rle ? rle_byte : lit[lit_run + k]; uint32_t at = out_run + jo + (k - js); dst[at] = v; ring[at & (Z_RING - 1)] = v; }
-            }
-            __syncwarp();
             const uint32_t cnt = min(32u, B.nseq - g);
             const uint32_t ml = q.y, off = q.z, amd = out_run + o_start + q.x;   // amd: frame position of the match destination
-            const uint32_t im = io - il;                                         // inclusive prefix sum of the match lengths
             if (__any_sync(0xffffffffu, lane < cnt && (off == 0 || off > amd))) { if (lane == 0) zfail(V, f, ZERR_OFFSET); return; }
             // dep: the last match of the group whose destination [amd_i, amd_i + ml_i) overlaps this match's source [s, e); destinations are
             // disjoint and ascending, so that is the last one starting below e, if it reaches beyond s
@@ -651,29 +642,78 @@ static __global__ void __launch_bounds__(128) k_execute(ZView V, const uint32_t*
                 const uint32_t ca = __shfl_sync(0xffffffffu, amd, ci), cm = __shfl_sync(0xffffffffu, ml, ci);
                 if (lo > 0 && ca + cm > s_src) dep = (int)lo - 1;
             }
+            // FAR matches read only what lies in front of the group: they depend on nothing the group writes and go out together with the
+            // literal runs, all loads before all stores - one memory round trip for most of a group instead of one per literal step and one
+            // per dependency run.  (zstd level 3 finds most of its 4..5-byte matches far back in the frame.)  NEAR matches follow in
+            // dependency order; their sources are this group's own output, i.e. in the ring.
+            const bool is_far = lane < cnt && ml && e_src <= out_run;
+            uint32_t imf = is_far ? ml : 0u;   // inclusive prefix sum of the far match lengths
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t a = __shfl_up_sync(0xffffffffu, imf, d); if ((int)lane >= d) imf += a; }
+            const uint32_t MF = __shfl_sync(0xffffffffu, imf, 31), TF = T + MF;
+            const uint32_t imn = (io - il) - imf;   // inclusive prefix sum of the near match lengths
+            const uint32_t far_mask = __ballot_sync(0xffffffffu, is_far);
+            if (dep >= 0 && (far_mask >> dep & 1u)) {   // a far match is done before any near one starts: wait for the last NEAR match in front of it instead
+                const uint32_t below = ~far_mask & ((1u << dep) - 1u);
+                dep = below ? 31 - __clz((int)below) : -1;
+            }
+            for (uint32_t k0 = 0; k0 < TF; k0 += 256) {   // eight steps of 32 bytes: all loads first, then all stores
+                uint8_t v[8]; uint32_t at[8]; bool on[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const uint32_t base = k0 + 32 * u, kq = base + lane;   // base is warp-uniform
+                    on[u] = false; v[u] = 0; at[u] = 0;
+                    if (base >= TF) continue;
+                    if (base < T) {   // literal bytes: byte k belongs to the sequence j with il[j-1] <= k < il[j]
+                        uint32_t lo = 0;   // smallest j with il[j] > k, by 5 shuffle probes
+#pragma unroll
+                        for (int s = 16; s; s >>= 1) { uint32_t x = __shfl_sync(0xffffffffu, il, (lo + s - 1) & 31); if (x <= kq) lo += s; }
+                        const uint32_t js = __shfl_sync(0xffffffffu, lit_start, lo & 31), jo = __shfl_sync(0xffffffffu, o_start, lo & 31);
+                        if (kq < T) { on[u] = true; v[u] = lit_rle ? rle_byte : lit[lit_run + kq]; at[u] = out_run + jo + (kq - js); }
+                    }
+                    if (base + 32 > T) {   // bytes of far matches
+                        const uint32_t k = kq - T;   // position in the concatenated far match bytes (meaningless in lanes still on literals)
+                        uint32_t lo = 0;             // smallest j with imf[j] > k
+#pragma unroll
+                        for (int s = 16; s; s >>= 1) { uint32_t x = __shfl_sync(0xffffffffu, imf, (lo + s - 1) & 31); if (x <= k) lo += s; }
+                        const uint32_t jm = __shfl_sync(0xffffffffu, ml, lo & 31), jo = __shfl_sync(0xffffffffu, off, lo & 31);
+                        const uint32_t jd = __shfl_sync(0xffffffffu, amd, lo & 31), je = __shfl_sync(0xffffffffu, imf, lo & 31);
+                        if (kq >= T && kq < TF) {
+                            const uint32_t kk = k - (je - jm);   // byte index inside match `lo`
+                            const uint32_t sa = jd - jo + (jo >= jm ? kk : kk % jo);   // frame position of the source byte
+                            // the ring holds position q as long as nothing was stored at q + Z_RING; stores so far reach up to gend
+                            on[u] = true; v[u] = (ring_ok && sa >= ring_lo && gend - sa < Z_RING) ? ring[sa & (Z_RING - 1)] : dst[sa];
+                            at[u] = jd + kk;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) if (on[u]) { dst[at[u]] = v[u]; ring[at[u] & (Z_RING - 1)] = v[u]; }
+            }
+            __syncwarp();
             uint32_t cur = 0;
             while (cur < cnt) {
                 const uint32_t ready = __ballot_sync(0xffffffffu, lane >= cur && lane < cnt && dep < (int)cur) >> cur;   // bit 0 = match `cur`, always set
                 const uint32_t n = ready == 0xffffffffu ? 32u : max((uint32_t)__ffs((int)~ready) - 1u, 1u);
                 const uint32_t hi = cur + n;
-                const uint32_t im_lo = cur ? __shfl_sync(0xffffffffu, im, cur - 1) : 0u, M = __shfl_sync(0xffffffffu, im, hi - 1) - im_lo;
+                const uint32_t im_lo = cur ? __shfl_sync(0xffffffffu, imn, cur - 1) : 0u, M = __shfl_sync(0xffffffffu, imn, hi - 1) - im_lo;
                 for (uint32_t k0 = 0; k0 < M; k0 += 128) {   // four steps of 32 bytes: all loads first, then all stores
                     uint8_t v[4]; uint32_t at[4]; bool on[4];
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
                         const uint32_t kq = k0 + 32 * u + lane;
-                        const uint32_t k = im_lo + kq;   // position in the group's concatenated match bytes
-                        uint32_t lo = 0;                 // smallest j with im[j] > k
+                        on[u] = false; v[u] = 0; at[u] = 0;
+                        if (k0 + 32 * u >= M) continue;   // warp-uniform
+                        const uint32_t k = im_lo + kq;   // position in the group's concatenated near match bytes
+                        uint32_t lo = 0;                 // smallest j with imn[j] > k
 #pragma unroll
-                        for (int s = 16; s; s >>= 1) { uint32_t x = __shfl_sync(0xffffffffu, im, (lo + s - 1) & 31); if (x <= k) lo += s; }
+                        for (int s = 16; s; s >>= 1) { uint32_t x = __shfl_sync(0xffffffffu, imn, (lo + s - 1) & 31); if (x <= k) lo += s; }
                         const uint32_t jm = __shfl_sync(0xffffffffu, ml, lo & 31), jo = __shfl_sync(0xffffffffu, off, lo & 31);
-                        const uint32_t jd = __shfl_sync(0xffffffffu, amd, lo & 31), je = __shfl_sync(0xffffffffu, im, lo & 31);
-                        on[u] = kq < M; v[u] = 0; at[u] = 0;
-                        if (on[u]) {
+                        const uint32_t jd = __shfl_sync(0xffffffffu, amd, lo & 31), je = __shfl_sync(0xffffffffu, imn, lo & 31);
+                        if (kq < M) {
                             const uint32_t kk = k - (je - jm);   // byte index inside match `lo`
                             const uint32_t sa = jd - jo + (jo >= jm ? kk : kk % jo);   // frame position of the source byte
-                            // the ring holds position q as long as nothing was stored at q + Z_RING; stores so far reach up to gend
-                            v[u] = (ring_ok && sa >= ring_lo && gend - sa < Z_RING) ? ring[sa & (Z_RING - 1)] : dst[sa];
+                            on[u] = true; v[u] = (ring_ok && sa >= ring_lo && gend - sa < Z_RING) ? ring[sa & (Z_RING - 1)] : dst[sa];
                             at[u] = jd + kk;
                         }
                     }
