@@ -62,6 +62,7 @@ def parse_args():
     ap.add_argument("--rows", type=int, default=0, help="rows per rank (default: the workload's)")
     ap.add_argument("--hot-block-permille", type=int, default=1000, help="block clustering knob: fraction of blocks holding vocabulary rows")
     ap.add_argument("--hit-row-permille", type=int, default=60, help="selectivity knob: vocabulary rows inside hot blocks")
+    ap.add_argument("--vocab-focus", type=int, default=0, help="1..12: every vocabulary row carries that vocabulary entry (selectivity studies); 0: uniform draw, the headline setting")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-rows", type=int, default=100_000_000, help="rows per end-to-end step (the first rows of the rank's shard)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -217,7 +218,7 @@ def main():
         rows -= rows % w["rows_per_block"] if rows % w["rows_per_block"] and rows % w["rows_per_block"] < 64 else 0
         nb = (rows + w["rows_per_block"] - 1) // w["rows_per_block"]
         kw = dict(seed=SEED, total_rows=rows * world, rows_per_block=w["rows_per_block"], hot_block_permille=args.hot_block_permille,
-                  hit_row_permille=args.hit_row_permille, columns_mask=w["mask"])
+                  hit_row_permille=args.hit_row_permille, columns_mask=w["mask"] | (args.vocab_focus << 8))
         if rows % w["rows_per_block"]:
             kw["total_rows"] = nb * w["rows_per_block"] * (world - 1) + rows if world > 1 else rows
         return rows, nb, kw

@@ -7,8 +7,8 @@ is an argument rather than a format rule, in the exact form the kernels use:
   run happens against the state before the run - which is also why the kernel may issue the loads of several copy steps before the first
   store, as it does since round 2); the per-warp ring in shared memory with its validity rule (`gend - q < RING`, group span
   < RING, `ring_lo` after an oversized group).
-  Since round 2 the literal runs travel together with the FAR matches (sources wholly in front of the group) in chunks of 256 bytes, and
-  the dependency runs cover the NEAR matches only.
+  Since round 2 the unit of a copy is a chunk of up to 4 bytes, a group is assembled in the ring and flushed to HBM at its end (so HBM may
+  only be read in front of the group), and groups that span the ring keep the byte-per-lane path.
 * SeqLane (the sequence decoder's bit window): a 96-bit window funnel-shifted out of four aligned words of a 256-byte ring that is topped
   up by one 16-byte chunk per sequence; three fields per sequence (offset bits | match + literal length bits | the three state updates)."""
 import random
@@ -29,12 +29,16 @@ def lz_reference(lits, seqs, prefix):
     return bytes(out)
 
 
-def execute_model(lits, seqs, prefix):
+def execute_model(lits, seqs, prefix, ring_size=RING):
+    """k_execute, round 2.  `dst` is HBM, `ring` the per-warp ring.  Fast path (group output < ring): literal runs and matches are cut into
+    chunks of up to 4 bytes, assembled in the ring only, and [out_run, gend) is flushed to HBM at the end of the group - so a source byte
+    read from HBM must lie in front of the group.  Slow path: one byte per lane per step straight to HBM, mirrored in the ring."""
+    RS = ring_size
     total = len(prefix) + len(lits) + sum(m for _, m, _ in seqs)
-    dst = bytearray(prefix) + bytearray(total - len(prefix))
-    ring = bytearray(RING)
+    dst = bytearray(prefix) + bytearray(b"\xee" * (total - len(prefix)))      # 0xEE: never-written HBM
+    ring = bytearray(RS)
     for i, b in enumerate(prefix):
-        ring[i & (RING - 1)] = b
+        ring[i & (RS - 1)] = b
     lit_run, out_run, ring_lo = 0, len(prefix), 0
     for g in range(0, len(seqs), 32):
         grp = seqs[g:g + 32]
@@ -47,12 +51,11 @@ def execute_model(lits, seqs, prefix):
             io.append(b)
         T, O = il[-1], io[-1]
         gend = out_run + O
-        ring_ok = O < RING
         o_start = [io[j] - grp[j][0] - grp[j][1] for j in range(cnt)]
         amd = [out_run + o_start[j] + grp[j][0] for j in range(cnt)]
         ml = [q[1] for q in grp]
         off = [q[2] for q in grp]
-        dep, far = [], []
+        dep = []
         for j in range(cnt):
             s = amd[j] - off[j]
             e = s + min(ml[j], off[j])
@@ -62,51 +65,71 @@ def execute_model(lits, seqs, prefix):
                 if idx < cnt and amd[idx] < e:
                     lo += st
             dep.append(lo - 1 if lo > 0 and amd[lo - 1] + ml[lo - 1] > s else -1)
-            far.append(ml[j] > 0 and e <= out_run)             # reads only what lies in front of the group
-        for j in range(cnt):                                   # a far match is done before any near one starts: wait for the last near match in front of it
-            if dep[j] >= 0 and far[dep[j]]:
-                below = [i for i in range(dep[j]) if not far[i]]
-                dep[j] = below[-1] if below else -1
-        # phase 1: literal runs and far matches, chunks of 256 bytes of their concatenation; inside a chunk all loads precede all stores
-        jobs = []
-        for j in range(cnt):
-            for k in range(grp[j][0]):
-                jobs.append(("lit", lit_run + il[j] - grp[j][0] + k, out_run + o_start[j] + k))
-        for j in range(cnt):
-            if far[j]:
-                for kk in range(ml[j]):
-                    jobs.append(("dst", amd[j] - off[j] + (kk if off[j] >= ml[j] else kk % off[j]), amd[j] + kk))
-        for c0 in range(0, len(jobs), 256):
-            snap, rsnap = bytes(dst), bytes(ring)
-            for kind, src, at in jobs[c0:c0 + 256]:
-                if kind == "lit":
-                    v = lits[src]
-                else:
-                    v = rsnap[src & (RING - 1)] if (ring_ok and src >= ring_lo and gend - src < RING) else snap[src]
-                dst[at] = v
-                ring[at & (RING - 1)] = v
-        # phase 2: near matches in dependency order
-        cur = 0
-        while cur < cnt:
-            n = 0
-            while cur + n < cnt and dep[cur + n] < cur:
-                n += 1
-            n = max(n, 1)
-            run = [(j, kk) for j in range(cur, cur + n) if not far[j] for kk in range(ml[j])]
-            for c0 in range(0, len(run), 128):                 # four steps of 32 bytes: loads, then stores
-                snap, rsnap = bytes(dst), bytes(ring)
-                for j, kk in run[c0:c0 + 128]:
-                    sa = amd[j] - off[j] + (kk if off[j] >= ml[j] else kk % off[j])
-                    v = rsnap[sa & (RING - 1)] if (ring_ok and sa >= ring_lo and gend - sa < RING) else snap[sa]
-                    dst[amd[j] + kk] = v
-                    ring[(amd[j] + kk) & (RING - 1)] = v
-            cur += n
+
+        def in_ring(q):
+            return q >= ring_lo and gend - q <= RS
+
+        if O < RS:
+            for j in range(cnt):                               # literal chunks (no dependencies)
+                for k in range(grp[j][0]):
+                    ring[(out_run + o_start[j] + k) & (RS - 1)] = lits[lit_run + il[j] - grp[j][0] + k]
+            cur = 0
+            while cur < cnt:
+                n = 0
+                while cur + n < cnt and dep[cur + n] < cur:
+                    n += 1
+                n = max(n, 1)
+                chunks = [(j, b0) for j in range(cur, cur + n) for b0 in range(0, ml[j], 4)]
+                for c0 in range(0, len(chunks), 128):          # four steps of 32 chunks: loads, then stores
+                    snap, rsnap, stores = bytes(dst), bytes(ring), []
+                    for j, b0 in chunks[c0:c0 + 128]:
+                        nb = min(4, ml[j] - b0)
+                        sa = amd[j] - off[j] + b0
+                        if off[j] >= ml[j] and in_ring(sa):
+                            src = [rsnap[(sa + t) & (RS - 1)] for t in range(nb)]
+                        elif off[j] >= ml[j] and sa + nb <= out_run:
+                            src = [snap[sa + t] for t in range(nb)]
+                        else:
+                            src = []
+                            for t in range(nb):
+                                sb = amd[j] - off[j] + (b0 + t if off[j] >= ml[j] else (b0 + t) % off[j])
+                                assert in_ring(sb) or sb < out_run
+                                src.append(rsnap[sb & (RS - 1)] if in_ring(sb) else snap[sb])
+                        stores.append((amd[j] + b0, src))
+                    for at, src in stores:
+                        for t, v in enumerate(src):
+                            ring[(at + t) & (RS - 1)] = v
+                cur += n
+            for q in range(out_run, gend):                     # flush
+                dst[q] = ring[q & (RS - 1)]
+        else:
+            for j in range(cnt):
+                for k in range(grp[j][0]):
+                    v = lits[lit_run + il[j] - grp[j][0] + k]
+                    at = out_run + o_start[j] + k
+                    dst[at] = v
+                    ring[at & (RS - 1)] = v
+            cur = 0
+            while cur < cnt:
+                n = 0
+                while cur + n < cnt and dep[cur + n] < cur:
+                    n += 1
+                n = max(n, 1)
+                run = [(j, kk) for j in range(cur, cur + n) for kk in range(ml[j])]
+                for c0 in range(0, len(run), 32):
+                    snap = bytes(dst)
+                    for j, kk in run[c0:c0 + 32]:
+                        sa = amd[j] - off[j] + (kk if off[j] >= ml[j] else kk % off[j])
+                        v = snap[sa]
+                        dst[amd[j] + kk] = v
+                        ring[(amd[j] + kk) & (RS - 1)] = v
+                cur += n
+            ring_lo = gend
         lit_run += T
         out_run += O
-        if not ring_ok:
-            ring_lo = gend
     for k in range(len(lits) - lit_run):
         dst[out_run + k] = lits[lit_run + k]
+        ring[(out_run + k) & (RS - 1)] = lits[lit_run + k]
     return bytes(dst)
 
 
@@ -127,7 +150,9 @@ def test_executor_model_equals_sequential_lz():
             seqs.append((ll, ml, off))
             pos += ml
         lits = bytes(rng.getrandbits(8) for _ in range(nl + rng.randint(0, 10)))
-        assert execute_model(lits, seqs, prefix) == lz_reference(lits, seqs, prefix), trial
+        want = lz_reference(lits, seqs, prefix)
+        assert execute_model(lits, seqs, prefix) == want, trial
+        assert execute_model(lits, seqs, prefix, ring_size=256) == want, trial      # a small ring: sources straddle what the ring holds all the time
 
 
 M32 = 0xFFFFFFFF

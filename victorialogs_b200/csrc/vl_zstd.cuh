@@ -318,22 +318,42 @@ static __global__ void __launch_bounds__(Z_HUF_CTA_BLOCKS * 4) k_huf_decode(ZVie
     uint32_t i = 0;
     // head: byte stores until the output is 8-byte aligned
     while (i < nout && (((uintptr_t)(out + i)) & 7) && pos >= 0) { const uint32_t e = tab[peek64(s, pos) >> sh]; pos -= (int64_t)(e >> 8); out[i++] = (uint8_t)e; }
-    // body: 8 symbols per 64-bit store, two container reloads (4 symbols of <= 11 bits each fit the >= 57 fresh bits of a reload)
-    while (nout - i >= 8 && pos >= 64) {
-        uint64_t acc = 0;
+    // body: 8 symbols per 64-bit store, two containers of 4 symbols (<= 44 bits).  The container is cut out of a register window over
+    // ALIGNED 8-byte words of the stream - hi:lo hold the cursor, n1 and n2 are the two words below, requested 128+ bits (>= 12 symbols)
+    // before they are needed - so no load sits on the symbol chain (round 2; before, every container was an exposed L1/L2 round trip:
+    // 10.8 long-scoreboard stall cycles per issued instruction in ncu).
+    if (nout - i >= 8 && pos >= 128) {
+        const uint64_t* org = (const uint64_t*)((uintptr_t)s & ~(uintptr_t)7);
+        const uint32_t s0 = (uint32_t)((uintptr_t)s & 7) * 8;
+        uint32_t ab = s0 + (uint32_t)pos;            // bit index (relative to org) one past the first unread bit; streams are < 2^20 bytes
+        uint32_t k = (ab - 1) >> 6;
+        // words below the stream are staging-buffer headroom or the bytes in front of the stream: loaded, never used
+        uint64_t hi = org[k], lo = org[(int32_t)k - 1], n1 = org[(int32_t)k - 2], n2 = org[(int32_t)k - 3];
+        const uint32_t sh32 = 32 - maxbits;
+        while (nout - i >= 8 && ab - s0 >= 128) {   // 8 symbols consume <= 88 bits: the cursor never passes the start of the stream in here
+            uint64_t acc = 0;
 #pragma unroll
-        for (int half = 0; half < 2; half++) {
-            const uint64_t c = peek64(s, pos);
-            uint32_t used = 0;
+            for (int half = 0; half < 2; half++) {
+                const uint32_t sft = (0u - ab) & 63u;   // unused bits at the top of hi
+                const bool up = sft < 32;
+                const uint32_t a = up ? (uint32_t)(hi >> 32) : (uint32_t)hi, b = up ? (uint32_t)hi : (uint32_t)(lo >> 32), c = up ? (uint32_t)(lo >> 32) : (uint32_t)lo;
+                uint32_t ch = __funnelshift_l(b, a, sft), cl = __funnelshift_l(c, b, sft);   // the 64 bits below the cursor, top aligned
+                uint32_t used = 0;
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const uint32_t e = tab[(c << used) >> sh];
-                used += e >> 8;
-                acc |= (uint64_t)(e & 0xFF) << (8 * (4 * half + q));
+                for (int q = 0; q < 4; q++) {
+                    const uint32_t e = tab[ch >> sh32];
+                    const uint32_t nb = e >> 8;       // 1..11
+                    ch = __funnelshift_l(cl, ch, nb); cl <<= nb;
+                    used += nb;
+                    acc |= (uint64_t)(e & 0xFF) << (8 * (4 * half + q));
+                }
+                ab -= used;
+                const uint32_t k2 = (ab - 1) >> 6;
+                if (k2 != k) { hi = lo; lo = n1; n1 = n2; n2 = org[(int32_t)k2 - 3]; k = k2; }
             }
-            pos -= (int64_t)used;
+            *(uint64_t*)(out + i) = acc; i += 8;
         }
-        *(uint64_t*)(out + i) = acc; i += 8;
+        pos = (int64_t)ab - (int64_t)s0;
     }
     while (i < nout && pos >= 0) { const uint32_t e = tab[peek64(s, pos) >> sh]; pos -= (int64_t)(e >> 8); out[i++] = (uint8_t)e; }
     if (i != nout || pos != 0) zfail(V, B.frame, ZERR_HUF_STREAM);
@@ -579,21 +599,33 @@ static __global__ void __launch_bounds__(64) k_seq_resolve(ZView V, uint32_t fra
 }
 
 // ---- sequence execution; one warp per frame (RFC 8878 3.1.1.4) -------------------------------------------------------------------------------
-// Per group of 32 sequences: all literal runs go out first (they depend on nothing), then the matches.  A match must wait only for
-// the matches whose destination its source overlaps; `dep` is the index of the last such match inside the group, and a run of
-// consecutive matches with dep < (first match of the run) is copied as one flat, warp-wide copy.  The source of a match is mostly a
-// few hundred bytes back - data this warp stored moments ago - so every byte is mirrored in a per-warp ring in shared memory and
-// read from there when it is recent enough: the load that every run has to wait for then costs ~30 cycles instead of an L2 / HBM trip.
-// Round 2.  (a) Measured on the C2 batch (profiles/ncu_zstd_r02.md): 46 % of this kernel's stall samples sat on the store behind the one-byte
-// load of a match source that is not in the ring - zstd level 3 codes the random hex digits of log lines as 4..5 byte matches found anywhere in
-// the 385 KB frame, so most matches are far and every copy step paid a DRAM round trip.  Inside a run all copies are independent (that is what
-// makes it a run), so the loads of four steps are now issued before the first store.  (b) A variant in which every lane copies its own sequence
-// into the ring and the group is flushed with 16-byte stores was byte-exact too but slower (70 ms against 43 ms on that batch: the 43-byte
-// template match of every row keeps 31 lanes waiting); it is in the history of this file (commit "device ZSTD: per-lane sequence execution").
+// A frame is a serial chain of groups of 32 sequences (lane j holds sequence j).  Prefix sums give every literal run and every match its
+// place; a match must wait only for the matches whose destination its source overlaps: `dep` is the index of the last such match inside
+// the group (destinations are disjoint and ascending: 5 shuffle probes), and a run of consecutive matches with dep < (first match of the run)
+// is copied as one flat, warp-wide copy.
+//
+// Round 2.  ncu on the round-1 kernel (one BYTE per lane per step, straight to HBM, mirrored in a shared-memory ring) showed 34 warp
+// instructions per sequence: zstd level 3 turns log lines into ~13 sequences per row of 4 literal bytes + a 5-byte match, so the 5-probe
+// owner search, four shuffles and the address arithmetic (incl. an integer modulo for overlapping matches that almost never occur) were paid
+// per byte.  Now
+//   * the unit of work is a CHUNK of up to 4 bytes of one literal run or one match (prefix sums over chunk counts; one owner search per
+//     chunk): an unaligned 32-bit load (two aligned words + a funnel shift) instead of four byte loads, the modulo only in the branch that
+//     needs it;
+//   * the group is assembled in the ring only (byte stores to shared memory), then flushed to HBM with aligned 16-byte stores: the ring is
+//     indexed by the output ADDRESS modulo its size, so 16-byte chunks of the ring are 16-byte chunks of the arena;
+//   * the next group's sequence records are loaded while the current group is executed.
+// Groups that span the ring or more (a literal run of kilobytes) take the byte-per-lane path of round 1, which also stayed the reference for
+// tests/test_zstd_models_cpu.py.  (Two other round-2 variants were byte-exact but slower: every lane copying its own sequence - a memory
+// wavefront per lane per byte -, and far matches batched beside the literals - they were already in long runs.  profiles/zstd_history_r02.md)
 static const uint32_t Z_RING = 4096;
 static const uint32_t Z_EXEC_WARPS = 4;
+static __device__ __forceinline__ uint32_t ldu32(const uint8_t* p) {   // little-endian 4 bytes at any address: two aligned loads, up to 7 bytes of slack touched
+    const uintptr_t a = (uintptr_t)p & ~(uintptr_t)3;
+    const uint32_t lo = *(const uint32_t*)a, hi = *(const uint32_t*)(a + 4);
+    return __funnelshift_r(lo, hi, (uint32_t)((uintptr_t)p & 3) * 8);
+}
 static __global__ void __launch_bounds__(128) k_execute(ZView V, const uint32_t* __restrict__ order, uint32_t nframes) {
-    __shared__ uint8_t s_ring[4][Z_RING];
+    __shared__ __align__(16) uint8_t s_ring[Z_EXEC_WARPS][Z_RING];
     const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (wid >= nframes) return;
     const uint32_t f = order[wid];
@@ -601,13 +633,16 @@ static __global__ void __launch_bounds__(128) k_execute(ZView V, const uint32_t*
     const ZFrame& F = V.frames[f];
     uint8_t* dst = V.arena + F.dst;
     uint8_t* ring = s_ring[threadIdx.x >> 5];
+    const uint32_t abase = (uint32_t)(uintptr_t)dst;   // ring slot of frame position p = (address of dst + p) & (Z_RING - 1)
+#define VL_RIDX(p) ((abase + (p)) & (Z_RING - 1))
+#define VL_RING(p) ring[VL_RIDX(p)]
     uint32_t ring_lo = 0;   // frame position from which the ring content can be trusted
     for (uint32_t bi = F.blk_lo; bi < F.blk_hi; bi++) {
         const ZBlock& B = V.blocks[bi];
         const uint32_t blk_base = V.bstate[bi].out_base;   // position of the block inside the frame
         const uint8_t* p = V.src + B.src;
-        if (B.type == ZB_RAW) { for (uint32_t k = lane; k < B.size; k += 32) { uint8_t v = p[k]; dst[blk_base + k] = v; ring[(blk_base + k) & (Z_RING - 1)] = v; } __syncwarp(); continue; }
-        if (B.type == ZB_RLE) { uint8_t v = p[0]; for (uint32_t k = lane; k < B.size; k += 32) { dst[blk_base + k] = v; ring[(blk_base + k) & (Z_RING - 1)] = v; } __syncwarp(); continue; }
+        if (B.type == ZB_RAW) { for (uint32_t k = lane; k < B.size; k += 32) { uint8_t v = p[k]; dst[blk_base + k] = v; VL_RING(blk_base + k) = v; } __syncwarp(); continue; }
+        if (B.type == ZB_RLE) { uint8_t v = p[0]; for (uint32_t k = lane; k < B.size; k += 32) { dst[blk_base + k] = v; VL_RING(blk_base + k) = v; } __syncwarp(); continue; }
         const uint8_t* lit = B.lit_type == ZL_RAW ? p + B.lit_hdr : V.lits + B.lit_off;
         const bool lit_rle = B.lit_type == ZL_RLE;
         const uint8_t rle_byte = lit_rle ? p[B.lit_hdr] : 0;
@@ -624,9 +659,6 @@ static __global__ void __launch_bounds__(128) k_execute(ZView V, const uint32_t*
             const uint32_t o_start = io - q.x - q.y;        // output offset of this lane's literals inside the group
             const uint32_t T = __shfl_sync(0xffffffffu, il, 31), O = __shfl_sync(0xffffffffu, io, 31);
             const uint32_t gend = out_run + O;              // frame position one past the group
-            // Inside a group stores are not in position order (all literals first), so two positions of one group must not share a ring
-            // slot: a group spanning Z_RING bytes or more reads from HBM only and leaves the ring untrusted below its end.
-            const bool ring_ok = O < Z_RING;
             const uint32_t cnt = min(32u, B.nseq - g);
             const uint32_t ml = q.y, off = q.z, amd = out_run + o_start + q.x;   // amd: frame position of the match destination
             if (__any_sync(0xffffffffu, lane < cnt && (off == 0 || off > amd))) { if (lane == 0) zfail(V, f, ZERR_OFFSET); return; }
@@ -642,95 +674,148 @@ static __global__ void __launch_bounds__(128) k_execute(ZView V, const uint32_t*
                 const uint32_t ca = __shfl_sync(0xffffffffu, amd, ci), cm = __shfl_sync(0xffffffffu, ml, ci);
                 if (lo > 0 && ca + cm > s_src) dep = (int)lo - 1;
             }
-            // FAR matches read only what lies in front of the group: they depend on nothing the group writes and go out together with the
-            // literal runs, all loads before all stores - one memory round trip for most of a group instead of one per literal step and one
-            // per dependency run.  (zstd level 3 finds most of its 4..5-byte matches far back in the frame.)  NEAR matches follow in
-            // dependency order; their sources are this group's own output, i.e. in the ring.
-            const bool is_far = lane < cnt && ml && e_src <= out_run;
-            uint32_t imf = is_far ? ml : 0u;   // inclusive prefix sum of the far match lengths
+            if (O < Z_RING) {
+                // ---- chunks of up to 4 bytes, assembled in the ring, flushed with 16-byte stores --------------------------------------------
+                // Positions of one group never share a ring slot (O < Z_RING), and a source position sa with gend - sa <= Z_RING cannot have
+                // been overwritten by anything of this group; older sources are in front of the group, i.e. flushed, and come from HBM.
+                uint32_t cl = (q.x + 3) >> 2, cm = (ml + 3) >> 2;   // inclusive prefix sums of the chunk counts of literal runs / matches
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { uint32_t a = __shfl_up_sync(0xffffffffu, imf, d); if ((int)lane >= d) imf += a; }
-            const uint32_t MF = __shfl_sync(0xffffffffu, imf, 31), TF = T + MF;
-            const uint32_t imn = (io - il) - imf;   // inclusive prefix sum of the near match lengths
-            const uint32_t far_mask = __ballot_sync(0xffffffffu, is_far);
-            if (dep >= 0 && (far_mask >> dep & 1u)) {   // a far match is done before any near one starts: wait for the last NEAR match in front of it instead
-                const uint32_t below = ~far_mask & ((1u << dep) - 1u);
-                dep = below ? 31 - __clz((int)below) : -1;
-            }
-            for (uint32_t k0 = 0; k0 < TF; k0 += 256) {   // eight steps of 32 bytes: all loads first, then all stores
-                uint8_t v[8]; uint32_t at[8]; bool on[8];
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const uint32_t base = k0 + 32 * u, kq = base + lane;   // base is warp-uniform
-                    on[u] = false; v[u] = 0; at[u] = 0;
-                    if (base >= TF) continue;
-                    if (base < T) {   // literal bytes: byte k belongs to the sequence j with il[j-1] <= k < il[j]
-                        uint32_t lo = 0;   // smallest j with il[j] > k, by 5 shuffle probes
-#pragma unroll
-                        for (int s = 16; s; s >>= 1) { uint32_t x = __shfl_sync(0xffffffffu, il, (lo + s - 1) & 31); if (x <= kq) lo += s; }
-                        const uint32_t js = __shfl_sync(0xffffffffu, lit_start, lo & 31), jo = __shfl_sync(0xffffffffu, o_start, lo & 31);
-                        if (kq < T) { on[u] = true; v[u] = lit_rle ? rle_byte : lit[lit_run + kq]; at[u] = out_run + jo + (kq - js); }
-                    }
-                    if (base + 32 > T) {   // bytes of far matches
-                        const uint32_t k = kq - T;   // position in the concatenated far match bytes (meaningless in lanes still on literals)
-                        uint32_t lo = 0;             // smallest j with imf[j] > k
-#pragma unroll
-                        for (int s = 16; s; s >>= 1) { uint32_t x = __shfl_sync(0xffffffffu, imf, (lo + s - 1) & 31); if (x <= k) lo += s; }
-                        const uint32_t jm = __shfl_sync(0xffffffffu, ml, lo & 31), jo = __shfl_sync(0xffffffffu, off, lo & 31);
-                        const uint32_t jd = __shfl_sync(0xffffffffu, amd, lo & 31), je = __shfl_sync(0xffffffffu, imf, lo & 31);
-                        if (kq >= T && kq < TF) {
-                            const uint32_t kk = k - (je - jm);   // byte index inside match `lo`
-                            const uint32_t sa = jd - jo + (jo >= jm ? kk : kk % jo);   // frame position of the source byte
-                            // the ring holds position q as long as nothing was stored at q + Z_RING; stores so far reach up to gend
-                            on[u] = true; v[u] = (ring_ok && sa >= ring_lo && gend - sa < Z_RING) ? ring[sa & (Z_RING - 1)] : dst[sa];
-                            at[u] = jd + kk;
-                        }
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 8; u++) if (on[u]) { dst[at[u]] = v[u]; ring[at[u] & (Z_RING - 1)] = v[u]; }
-            }
-            __syncwarp();
-            uint32_t cur = 0;
-            while (cur < cnt) {
-                const uint32_t ready = __ballot_sync(0xffffffffu, lane >= cur && lane < cnt && dep < (int)cur) >> cur;   // bit 0 = match `cur`, always set
-                const uint32_t n = ready == 0xffffffffu ? 32u : max((uint32_t)__ffs((int)~ready) - 1u, 1u);
-                const uint32_t hi = cur + n;
-                const uint32_t im_lo = cur ? __shfl_sync(0xffffffffu, imn, cur - 1) : 0u, M = __shfl_sync(0xffffffffu, imn, hi - 1) - im_lo;
-                for (uint32_t k0 = 0; k0 < M; k0 += 128) {   // four steps of 32 bytes: all loads first, then all stores
-                    uint8_t v[4]; uint32_t at[4]; bool on[4];
+                for (int d = 1; d < 32; d <<= 1) { uint32_t a = __shfl_up_sync(0xffffffffu, cl, d), b = __shfl_up_sync(0xffffffffu, cm, d); if ((int)lane >= d) { cl += a; cm += b; } }
+                const uint32_t CL = __shfl_sync(0xffffffffu, cl, 31);
+                const uint32_t pk = lit_start | (o_start << 16);   // both < Z_RING = 2^12
+                const uint8_t* lsrc = lit + lit_run;
+                for (uint32_t c0 = 0; c0 < CL; c0 += 128) {   // four steps of 32 chunks: all loads first, then all stores
+                    uint32_t w[4], at[4], nb[4];
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
-                        const uint32_t kq = k0 + 32 * u + lane;
-                        on[u] = false; v[u] = 0; at[u] = 0;
-                        if (k0 + 32 * u >= M) continue;   // warp-uniform
-                        const uint32_t k = im_lo + kq;   // position in the group's concatenated near match bytes
-                        uint32_t lo = 0;                 // smallest j with imn[j] > k
+                        nb[u] = 0; w[u] = 0; at[u] = 0;
+                        if (c0 + 32 * u >= CL) continue;   // warp-uniform
+                        const uint32_t c = c0 + 32 * u + lane;
+                        uint32_t lo = 0;   // smallest j with cl[j] > c
 #pragma unroll
-                        for (int s = 16; s; s >>= 1) { uint32_t x = __shfl_sync(0xffffffffu, imn, (lo + s - 1) & 31); if (x <= k) lo += s; }
-                        const uint32_t jm = __shfl_sync(0xffffffffu, ml, lo & 31), jo = __shfl_sync(0xffffffffu, off, lo & 31);
-                        const uint32_t jd = __shfl_sync(0xffffffffu, amd, lo & 31), je = __shfl_sync(0xffffffffu, imn, lo & 31);
-                        if (kq < M) {
-                            const uint32_t kk = k - (je - jm);   // byte index inside match `lo`
-                            const uint32_t sa = jd - jo + (jo >= jm ? kk : kk % jo);   // frame position of the source byte
-                            on[u] = true; v[u] = (ring_ok && sa >= ring_lo && gend - sa < Z_RING) ? ring[sa & (Z_RING - 1)] : dst[sa];
-                            at[u] = jd + kk;
+                        for (int s = 16; s; s >>= 1) { uint32_t x = __shfl_sync(0xffffffffu, cl, (lo + s - 1) & 31); if (x <= c) lo += s; }
+                        const uint32_t jc = __shfl_sync(0xffffffffu, cl, lo & 31), jl = __shfl_sync(0xffffffffu, q.x, lo & 31), jp = __shfl_sync(0xffffffffu, pk, lo & 31);
+                        if (c < CL) {
+                            const uint32_t b0 = (c - (jc - ((jl + 3) >> 2))) * 4;   // first byte of the chunk inside its literal run
+                            nb[u] = min(4u, jl - b0);
+                            w[u] = lit_rle ? rle_byte * 0x01010101u : ldu32(lsrc + (jp & 0xFFFF) + b0);
+                            at[u] = out_run + (jp >> 16) + b0;
                         }
                     }
 #pragma unroll
-                    for (int u = 0; u < 4; u++) if (on[u]) { dst[at[u]] = v[u]; ring[at[u] & (Z_RING - 1)] = v[u]; }
+                    for (int u = 0; u < 4; u++) {
+#pragma unroll
+                        for (int t = 0; t < 4; t++) if ((uint32_t)t < nb[u]) VL_RING(at[u] + t) = (uint8_t)(w[u] >> (8 * t));
+                    }
                 }
                 __syncwarp();
-                cur = hi;
+                uint32_t cur = 0;
+                while (cur < cnt) {
+                    const uint32_t ready = __ballot_sync(0xffffffffu, lane >= cur && lane < cnt && dep < (int)cur) >> cur;   // bit 0 = match `cur`, always set
+                    const uint32_t n = ready == 0xffffffffu ? 32u : max((uint32_t)__ffs((int)~ready) - 1u, 1u);
+                    const uint32_t hi = cur + n;
+                    const uint32_t c_lo = cur ? __shfl_sync(0xffffffffu, cm, cur - 1) : 0u, C = __shfl_sync(0xffffffffu, cm, hi - 1) - c_lo;
+                    for (uint32_t c0 = 0; c0 < C; c0 += 128) {
+                        uint32_t w[4], at[4], nb[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            nb[u] = 0; w[u] = 0; at[u] = 0;
+                            if (c0 + 32 * u >= C) continue;   // warp-uniform
+                            const uint32_t c = c_lo + c0 + 32 * u + lane;
+                            uint32_t lo = 0;   // smallest j with cm[j] > c
+#pragma unroll
+                            for (int s = 16; s; s >>= 1) { uint32_t x = __shfl_sync(0xffffffffu, cm, (lo + s - 1) & 31); if (x <= c) lo += s; }
+                            const uint32_t jc = __shfl_sync(0xffffffffu, cm, lo & 31), jm = __shfl_sync(0xffffffffu, ml, lo & 31);
+                            const uint32_t jf = __shfl_sync(0xffffffffu, off, lo & 31), jd = __shfl_sync(0xffffffffu, amd, lo & 31);
+                            if (c0 + 32 * u + lane < C) {
+                                const uint32_t b0 = (c - (jc - ((jm + 3) >> 2))) * 4;   // first byte of the chunk inside its match
+                                nb[u] = min(4u, jm - b0);
+                                at[u] = jd + b0;
+                                const uint32_t sa = jd - jf + b0;
+                                if (jf >= jm && sa >= ring_lo && gend - sa <= Z_RING) {   // no overlap, first byte in the ring: so are the others
+                                    const uint32_t i0 = VL_RIDX(sa), a0 = i0 & ~3u;
+                                    w[u] = __funnelshift_r(*(const uint32_t*)(ring + a0), *(const uint32_t*)(ring + ((a0 + 4) & (Z_RING - 1))), (i0 & 3) * 8);
+                                } else if (jf >= jm && sa + nb[u] <= out_run) {           // no overlap, wholly in front of the group: flushed
+                                    w[u] = ldu32(dst + sa);
+                                } else {
+                                    // byte by byte: a match that repeats its own output (byte kk comes from the first `offset` bytes, all in front of
+                                    // it), or a source that starts in front of what the ring holds and runs into it
+                                    for (uint32_t t = 0; t < nb[u]; t++) {
+                                        const uint32_t sb = jd - jf + (jf >= jm ? b0 + t : (b0 + t) % jf);
+                                        const uint32_t v = (sb >= ring_lo && gend - sb <= Z_RING) ? VL_RING(sb) : dst[sb];
+                                        w[u] |= v << (8 * t);
+                                    }
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+#pragma unroll
+                            for (int t = 0; t < 4; t++) if ((uint32_t)t < nb[u]) VL_RING(at[u] + t) = (uint8_t)(w[u] >> (8 * t));
+                        }
+                    }
+                    __syncwarp();
+                    cur = hi;
+                }
+                // flush [out_run, gend): bytes up to the first 16-byte boundary of the arena, aligned 16-byte chunks, the bytes behind the last one
+                {
+                    const uintptr_t a0 = (uintptr_t)dst + out_run, a1 = (uintptr_t)dst + gend;
+                    const uintptr_t h0 = (a0 + 15) & ~(uintptr_t)15, h1 = a1 & ~(uintptr_t)15;
+                    if (h0 <= h1) {
+                        if (lane < h0 - a0) *(uint8_t*)(a0 + lane) = ring[(a0 + lane) & (Z_RING - 1)];
+                        for (uintptr_t c = h0 + 16 * lane; c < h1; c += 512) *(uint4*)c = *(const uint4*)(ring + (c & (Z_RING - 1)));
+                        if (lane < a1 - h1) *(uint8_t*)(h1 + lane) = ring[(h1 + lane) & (Z_RING - 1)];
+                    } else if (lane < O) *(uint8_t*)(a0 + lane) = ring[(a0 + lane) & (Z_RING - 1)];   // the group lies inside one 16-byte chunk
+                }
+                __syncwarp();
+            } else {
+                // ---- a group that spans the ring or more: one byte per lane per step, straight to HBM (round 1's path) ----------------------
+                // Stores are not in position order inside a group (all literals first), so the ring cannot be trusted below the end of
+                // such a group: sources come from HBM, and ring_lo moves to gend.
+                for (uint32_t k0 = 0; k0 < T; k0 += 32) {
+                    uint32_t k = k0 + lane;
+                    uint32_t lo = 0;   // smallest j with il[j] > k, by 5 shuffle probes
+#pragma unroll
+                    for (int s = 16; s; s >>= 1) { uint32_t v = __shfl_sync(0xffffffffu, il, (lo + s - 1) & 31); if (v <= k) lo += s; }
+                    uint32_t js = __shfl_sync(0xffffffffu, lit_start, lo & 31), jo = __shfl_sync(0xffffffffu, o_start, lo & 31);
+                    if (k < T) { uint8_t v = lit_rle ? rle_byte : lit[lit_run + k]; uint32_t at = out_run + jo + (k - js); dst[at] = v; VL_RING(at) = v; }
+                }
+                __syncwarp();
+                const uint32_t im = io - il;   // inclusive prefix sum of the match lengths
+                uint32_t cur = 0;
+                while (cur < cnt) {
+                    const uint32_t ready = __ballot_sync(0xffffffffu, lane >= cur && lane < cnt && dep < (int)cur) >> cur;
+                    const uint32_t n = ready == 0xffffffffu ? 32u : max((uint32_t)__ffs((int)~ready) - 1u, 1u);
+                    const uint32_t hi = cur + n;
+                    const uint32_t im_lo = cur ? __shfl_sync(0xffffffffu, im, cur - 1) : 0u, M = __shfl_sync(0xffffffffu, im, hi - 1) - im_lo;
+                    for (uint32_t k0 = 0; k0 < M; k0 += 32) {
+                        const uint32_t k = im_lo + k0 + lane;   // position in the group's concatenated match bytes
+                        uint32_t lo = 0;                         // smallest j with im[j] > k
+#pragma unroll
+                        for (int s = 16; s; s >>= 1) { uint32_t v = __shfl_sync(0xffffffffu, im, (lo + s - 1) & 31); if (v <= k) lo += s; }
+                        const uint32_t jm = __shfl_sync(0xffffffffu, ml, lo & 31), jo = __shfl_sync(0xffffffffu, off, lo & 31);
+                        const uint32_t jd = __shfl_sync(0xffffffffu, amd, lo & 31), je = __shfl_sync(0xffffffffu, im, lo & 31);
+                        if (k0 + lane < M) {
+                            const uint32_t kk = k - (je - jm);   // byte index inside match `lo`
+                            const uint32_t sa = jd - jo + (jo >= jm ? kk : kk % jo);   // frame position of the source byte
+                            const uint8_t v = dst[sa];
+                            dst[jd + kk] = v; VL_RING(jd + kk) = v;
+                        }
+                    }
+                    __syncwarp();
+                    cur = hi;
+                }
+                ring_lo = gend;
             }
             lit_run += T; out_run += O;
-            if (!ring_ok) ring_lo = gend;
         }
         // literals after the last sequence
         const uint32_t rest = B.lit_regen - lit_run;
-        for (uint32_t k = lane; k < rest; k += 32) { uint8_t v = lit_rle ? rle_byte : lit[lit_run + k]; dst[out_run + k] = v; ring[(out_run + k) & (Z_RING - 1)] = v; }
+        for (uint32_t k = lane; k < rest; k += 32) { uint8_t v = lit_rle ? rle_byte : lit[lit_run + k]; dst[out_run + k] = v; VL_RING(out_run + k) = v; }
         __syncwarp();
     }
+#undef VL_RING
+#undef VL_RIDX
 }
 
 }  // namespace zs
