@@ -186,7 +186,7 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
     // copy pieces: runs that are contiguous on both sides (src stride == dst stride) and live in pinned host memory go out as one
     // cudaMemcpyAsync; everything else is packed through a pinned staging ring.
     uint64_t h2d = 0;
-    const size_t CH = 32u << 20;
+    const size_t CH = 64u << 20;
     uint8_t* stage = nullptr; cudaEvent_t evs[2] = {nullptr, nullptr}; int cur = 0; size_t fill = 0; uint64_t chunk_dst = 0; bool chunk_open = false;
     uint8_t* dev_base = nullptr;   // destination buffer of the pieces being copied
     // All host->device payload copies run on the ctx's copy stream; the compute stream picks them up through events.  While the
@@ -203,8 +203,34 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
     std::vector<std::pair<uint64_t, cudaEvent_t>> zmarks;
     bool marking = false;
     auto mark = [&](uint64_t end_off) { cudaEvent_t e = events.make(); VL_CUDA(cudaEventRecord(e, cs)); zmarks.push_back({end_off, e}); };
+    // Packing pageable memory (a part's mmap()ed files) into the ring is a memcpy, ~10 GB/s on one core and page faults on cold files: the
+    // segments of a chunk are only recorded while the pieces are walked, and copied by all host threads when the chunk is flushed
+    // (each thread takes an equal byte range of the chunk).
+    struct Seg { const uint8_t* src; size_t at, len; };   // src == nullptr: zeros
+    std::vector<Seg> segs;
+    auto pack_chunk = [&](uint8_t* buf, size_t bytes) {
+        const int nt = (int)std::min<size_t>(std::max(1, host_threads()), bytes / (1u << 20) + 1);
+        auto work = [&](int t) {
+            const size_t lo = bytes * (size_t)t / nt, hi = bytes * (size_t)(t + 1) / nt;
+            size_t i = std::upper_bound(segs.begin(), segs.end(), lo, [](size_t v, const Seg& g) { return v < g.at; }) - segs.begin();
+            if (i) i--;
+            for (; i < segs.size() && segs[i].at < hi; i++) {
+                const Seg& g = segs[i];
+                const size_t a = std::max(g.at, lo), b = std::min(g.at + g.len, hi);
+                if (a >= b) continue;
+                if (g.src) memcpy(buf + a, g.src + (a - g.at), b - a); else memset(buf + a, 0, b - a);
+            }
+        };
+        if (nt <= 1) { work(0); return; }
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; t++) th.emplace_back(work, t);
+        work(0);
+        for (auto& x : th) x.join();
+    };
     auto flush = [&]() {
-        if (!chunk_open || !fill) { chunk_open = false; fill = 0; return; }
+        if (!chunk_open || !fill) { chunk_open = false; fill = 0; segs.clear(); return; }
+        pack_chunk(stage + (size_t)cur * CH, fill);
+        segs.clear();
         VL_CUDA(cudaMemcpyAsync(dev_base + chunk_dst, stage + (size_t)cur * CH, fill, cudaMemcpyHostToDevice, cs));
         VL_CUDA(cudaEventRecord(evs[cur], cs));
         if (marking) mark(chunk_dst + fill);
@@ -265,13 +291,13 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
                 if (chunk_open && (chunk_dst + fill != pc.dst + done || fill == CH)) flush();
                 if (!chunk_open) { chunk_open = true; chunk_dst = pc.dst + done; fill = 0; }
                 size_t take = (size_t)std::min<uint64_t>(pc.len - done, CH - fill);
-                memcpy(stage + (size_t)cur * CH + fill, pc.src + done, take);
+                segs.push_back({pc.src + done, fill, take});
                 fill += take; done += take;
             }
             // pack the inter-piece slack (zero in the arena already) when the next piece follows closely, so chunks stay large
             if (i + 1 < pieces.size()) {
                 uint64_t gap = pieces[i + 1].dst - (pc.dst + pc.len);
-                if (gap <= 64 && fill + gap < CH) { memset(stage + (size_t)cur * CH + fill, 0, gap); fill += gap; } else flush();
+                if (gap <= 64 && fill + gap < CH) { if (gap) segs.push_back({nullptr, fill, (size_t)gap}); fill += gap; } else flush();
             }
         }
     }

@@ -759,42 +759,70 @@ static __device__ __forceinline__ uint32_t scan_word_hits(uint32_t w, const Scan
     return (uint32_t)(w == sp.pat[0]) | (uint32_t)(w == sp.pat[1]) << 1 | (uint32_t)(w == sp.pat[2]) << 2 | (uint32_t)(w == sp.pat[3]) << 3;
 }
 
-// Candidates are not verified where they are found: the lane that holds them appends (block, byte position) to a queue in shared memory and goes
-// on streaming.  Verifying in place costs a chain of ~6 dependent memory round trips (column header, row offsets, lens items, neighbouring bytes)
-// during which the other 31 lanes of the warp wait; out of the queue, the CTA's 256 threads verify 256 candidates at once, so the chain is paid
-// once per few hundred candidates and its loads overlap.  The queue is drained when a tile ends with at least VL_SCAN_QFLUSH entries, and when
-// the CTA has run out of tiles.  A candidate that finds the queue full is verified by its lane on the spot.
+// Candidates are not verified where they are found.  A lane whose 16-byte vector holds a candidate word appends (block, byte position of the
+// VECTOR) to a queue in shared memory and goes on streaming; out of the queue, the CTA's 256 threads take one vector each, re-read it (it is
+// still in L2), enumerate its candidate words / alignments and verify them.  Verifying in place costs a chain of ~6 dependent memory round trips
+// (column header, row offsets, lens items, neighbouring bytes) during which the other 31 lanes of the warp wait; in the drain all lanes are
+// busy and the chains overlap.  Round 2, second step: the streaming side used to enumerate the candidates itself (4 compares on each of a
+// lane's 16 words, by every lane of a warp in which ANY lane had a hit): at selectivity 0.5 that enumeration was 43 % of all instructions of
+// the kernel (profiles/kernel_history_r02.md).  Now it only ballots which lanes have a hit in each of their four vectors and reserves queue
+// slots with one shared-memory atomic per vector index.  The queue is drained when a tile ends with at least VL_SCAN_QFLUSH entries, and when
+// the CTA has run out of tiles.  A vector that finds the queue full is handled by its lane on the spot.
 #define VL_SCAN_QCAP 1024
 #define VL_SCAN_QFLUSH 192
-struct ScanCand { uint32_t block, pos; };
+struct ScanCand { uint32_t block, pos; };   // pos: byte offset of a 16-byte vector inside the block's data
 
-// Enumerate the candidates of one lane's four vectors.  Kept out of line on purpose: behind a call boundary the compiler cannot share
-// sub-expressions with the filter of the hot loop (it spilled 16 masked words per round to do so), and the registers of this path do not
-// count against the 48 of the streaming loop.
+// all candidates of one vector: word i matches pattern r => an occurrence may start at pos + 4 i + delta[r]
+template <bool MASKED>
+static __device__ __forceinline__ void scan_vector(const DevProgram& P, const BatchView& B, const DevColumn& c, const ScanParams& sp, uint32_t b,
+                                                    const uint32_t* __restrict__ row_off8, uint32_t pos, uint64_t* __restrict__ leaf_bm) {
+    const uint32_t n = (uint32_t)c.data_len;
+    // vectors past the end of the data were streamed as zeros; a zero word can only match a pattern of NUL bytes, rejected by the bounds below
+    const uint4 v = pos < n ? __ldg((const uint4*)(B.arena + c.data_off + pos)) : make_uint4(0, 0, 0, 0);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        uint32_t m = scan_word_hits<MASKED>(w[i], sp);
+        while (m) {
+            const int r = __ffs((int)m) - 1; m &= m - 1;
+            const int64_t q = (int64_t)pos + 4 * i + sp.delta[r];
+            if (q < 0 || q + (int64_t)sp.needle_len > (int64_t)n) continue;
+            scan_verify_lane(P, B, c, sp, b, row_off8, (uint32_t)q, leaf_bm);
+        }
+    }
+}
+
+// Called by the WHOLE warp when some lane has a hit: `hits` bit u = this lane's vector u holds a candidate word.  Kept out of line on purpose:
+// behind a call boundary the compiler cannot share sub-expressions with the filter of the hot loop (it spilled 16 masked words per round to do
+// so), and the registers of this path do not count against the 48 of the streaming loop.
 template <bool MASKED>
 static __device__ __noinline__ void scan_enqueue(const DevProgram& P, const BatchView& B, const DevColumn& c, const ScanParams& sp, uint32_t b,
                                                  const uint32_t* __restrict__ row_off8, uint64_t* __restrict__ leaf_bm, ScanCand* s_q, uint32_t* s_cnt,
-                                                 uint4 v0, uint4 v1, uint4 v2, uint4 v3, uint32_t base, uint32_t n) {
-    const uint32_t w[16] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
-    unsigned long long cand = 0;             // bit 16 * u + 4 * i + r: word i of vector u matches pattern r
+                                                 uint32_t hits, uint32_t base) {
+    const uint32_t lane = threadIdx.x & 31;
 #pragma unroll
-    for (int k = 0; k < 16; k++) cand |= (unsigned long long)scan_word_hits<MASKED>(w[k], sp) << (4 * k);
-    while (cand) {
-        const int bit = __ffsll((long long)cand) - 1; cand &= cand - 1;
-        const int u = bit >> 4, i = (bit >> 2) & 3, r = bit & 3;
-        // vectors past the end of the data were not loaded (zeros); a zero word can only match a pattern of NUL bytes, rejected by the bounds below
-        const int64_t q = (int64_t)base + u * (int64_t)VL_SCAN_QSTRIDE + 4 * i + sp.delta[r];
-        if (q < 0 || q + (int64_t)sp.needle_len > (int64_t)n) continue;
-        const uint32_t at = atomicAdd(s_cnt, 1u);
-        if (at < VL_SCAN_QCAP) s_q[at] = ScanCand{b, (uint32_t)q};
-        else scan_verify_lane(P, B, c, sp, b, row_off8, (uint32_t)q, leaf_bm);
+    for (int u = 0; u < VL_SCAN_UNROLL; u++) {
+        const bool mine = hits >> u & 1;
+        const uint32_t m = __ballot_sync(0xffffffffu, mine);
+        if (!m) continue;
+        const int leader = __ffs((int)m) - 1;
+        uint32_t at0 = 0;
+        if ((int)lane == leader) at0 = atomicAdd(s_cnt, (uint32_t)__popc(m));
+        at0 = __shfl_sync(0xffffffffu, at0, leader);
+        if (mine) {
+            const uint32_t at = at0 + __popc(m & ((1u << lane) - 1u));
+            const uint32_t pos = base + u * VL_SCAN_QSTRIDE;
+            if (at < VL_SCAN_QCAP) s_q[at] = ScanCand{b, pos};
+            else scan_vector<MASKED>(P, B, c, sp, b, row_off8, pos, leaf_bm);
+        }
     }
 }
+template <bool MASKED>
 static __device__ __noinline__ void scan_drain(const DevProgram& P, const BatchView& B, int slot, const ScanParams& sp, const uint32_t* __restrict__ row_off8,
                                                uint64_t* __restrict__ leaf_bm, const ScanCand* s_q, uint32_t count) {
     for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) {
         const ScanCand e = s_q[i];
-        scan_verify_lane(P, B, B.cols[(uint64_t)e.block * B.nfields + slot], sp, e.block, row_off8, e.pos, leaf_bm);
+        scan_vector<MASKED>(P, B, B.cols[(uint64_t)e.block * B.nfields + slot], sp, e.block, row_off8, e.pos, leaf_bm);
     }
 }
 
@@ -837,18 +865,19 @@ static __global__ void __launch_bounds__(VL_SCAN_THREADS, 5) k_substr_scan(const
                     else hit[u] |= w[i] == sp.pat[0] || w[i] == sp.pat[1] || w[i] == sp.pat[2] || w[i] == sp.pat[3];
                 }
             }
-            if (hit[0] | hit[1] | hit[2] | hit[3]) scan_enqueue<MASKED>(P, B, c, sp, b, row_off8, leaf_bm, s_q, &s_cnt, v[0], v[1], v[2], v[3], base, n);   // rare
+            const uint32_t hits = (uint32_t)hit[0] | (uint32_t)hit[1] << 1 | (uint32_t)hit[2] << 2 | (uint32_t)hit[3] << 3;
+            if (__any_sync(0xffffffffu, hits != 0)) scan_enqueue<MASKED>(P, B, c, sp, b, row_off8, leaf_bm, s_q, &s_cnt, hits, base);   // the whole warp goes
         }
         // end of the tile: drain the queue if it is worth a pass of the whole CTA (thread 0 decides; the barrier makes the decision uniform)
         if (__syncthreads_or(threadIdx.x == 0 && s_cnt >= VL_SCAN_QFLUSH)) {
-            scan_drain(P, B, slot, sp, row_off8, leaf_bm, s_q, min(s_cnt, (uint32_t)VL_SCAN_QCAP));
+            scan_drain<MASKED>(P, B, slot, sp, row_off8, leaf_bm, s_q, min(s_cnt, (uint32_t)VL_SCAN_QCAP));
             __syncthreads();
             if (threadIdx.x == 0) s_cnt = 0;
             __syncthreads();
         }
     }
     __syncthreads();
-    scan_drain(P, B, slot, sp, row_off8, leaf_bm, s_q, min(s_cnt, (uint32_t)VL_SCAN_QCAP));
+    scan_drain<MASKED>(P, B, slot, sp, row_off8, leaf_bm, s_q, min(s_cnt, (uint32_t)VL_SCAN_QCAP));
 }
 
 // ---- dict LUT / fixed-width equality / typed in(): one thread per bitmap word ---------------------------------------------------------------

@@ -92,14 +92,33 @@ void ZstdJob::add_values_blocks(const ZValuesBlock* v, size_t n, int threads, ZV
     *bad = SIZE_MAX;
     if (!m->frames.empty()) throw BadInput("BUG: add_values_blocks needs an empty job");
     if (threads > 0) { m->walk_values_blocks(v, n, threads, info, bad, msg); return; }
+    // threads == 0: the block-by-block walk the device decoder was first verified with, kept as the reference the threaded walk is compared
+    // against (vlscan_zstd_walk_digest).  The tapered group limits need the batch's total number of sequences: a dry walk counts them.
+    uint64_t total_seqs = 0;
+    if (!group_scale_env()) {
+        ZstdJob dry;
+        dry.m->limit_scale = 1u << 20;
+        for (size_t i = 0; i < n; i++) {
+            try {
+                uint64_t r = 0; uint32_t id = 0;
+                const size_t c1 = dry.add_bytes_block(v[i].p, v[i].n, v[i].zoff, &r, &id);
+                dry.add_bytes_block(v[i].p + c1, v[i].n - c1, v[i].zoff + c1, &r, &id);
+            } catch (const BadInput&) { break; }   // reported by the walk below
+        }
+        total_seqs = dry.m->n_seqs;
+    }
+    auto taper = [&] { if (!group_scale_env()) m->limit_scale = (m->groups.empty() || m->n_seqs > total_seqs - total_seqs / 12) ? 1 : 4; };
     for (size_t i = 0; i < n; i++) {
         try {
             uint32_t f1 = 0, f2 = 0;
+            taper();
             const size_t c1 = add_bytes_block(v[i].p, v[i].n, v[i].zoff, &info[i].lens_len, &f1);
+            taper();
             const size_t c2 = add_bytes_block(v[i].p + c1, v[i].n - c1, v[i].zoff + c1, &info[i].data_len, &f2);
             if (c1 + c2 != v[i].n) throw BadInput("unexpected non-empty tail after reading bytes block with strings");
         } catch (const BadInput& e) { *bad = i; *msg = e.msg; return; }
     }
+    if (!group_scale_env()) m->limit_scale = 1;
 }
 
 void ZstdJob::prepare() { m->prepare(); }

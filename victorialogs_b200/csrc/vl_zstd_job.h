@@ -25,15 +25,15 @@ using namespace zs;
 
 // scratch limits of one launch group (groups are cut at frame boundaries)
 // A group must hold enough blocks to fill the device for the lane-per-block phases (148 SMs x 56 sequence lanes = 8.3 k blocks per
-// wave); beyond a few waves, smaller groups are better: group g is decoded while the bytes of group g+1 are still being copied.
-// Round 2: a quarter of the round-1 limits.  The C2 batch (667 M sequences) becomes 11 groups instead of 3: the first one is decoded after a
-// tenth of the compressed bytes has arrived, the execute kernel of group g runs beside the entropy kernels of group g + 1 (second stream,
-// vl_zstd.cu), and the scratch (two copies of literals + sequence records) shrinks from 6 GB to 3 GB.
-// VLSCAN_ZSTD_GROUP_SCALE (tuning only): multiplies the three limits; 4 restores the round-1 ones.
-inline uint64_t group_scale() { static const uint64_t v = [] { const char* e = getenv("VLSCAN_ZSTD_GROUP_SCALE"); long x = e ? atol(e) : 1; return (uint64_t)(x < 1 ? 1 : x > 64 ? 64 : x); }(); return v; }
-#define kGroupLits ((512ull << 20) * group_scale())
-#define kGroupSeqs ((64ull << 20) * group_scale())
-#define kGroupSlots ((uint32_t)((32u << 10) * group_scale()))
+// wave) and enough frames for the warp-per-frame executor (~9 k in flight): small groups decode less efficiently.  On the other hand
+// group g is decoded while the bytes of group g+1 are still being copied, so the FIRST group decides when the decoder starts and the LAST
+// one is the tail that nothing hides.  Measured on a B200 (profiles/zstd_history_r02.md): with uniform groups the C3 batch (decode bound)
+// wants the large limits, the C2 batch (DMA bound) half of them.  So the limits are tapered: a small first group, large ones in the middle,
+// small ones over the last twelfth of the sequences (walk_values_blocks knows every frame's needs before it cuts).
+// VLSCAN_ZSTD_GROUP_SCALE (tuning only): a fixed multiplier for all groups instead; 4 = the round-1 limits.
+inline uint64_t group_scale_env() { static const uint64_t v = [] { const char* e = getenv("VLSCAN_ZSTD_GROUP_SCALE"); long x = e ? atol(e) : 0; return (uint64_t)(x < 0 ? 0 : x > 64 ? 64 : x); }(); return v; }
+static const uint64_t kGroupLitsUnit = 512ull << 20, kGroupSeqsUnit = 64ull << 20;
+static const uint32_t kGroupSlotsUnit = 32u << 10;
 
 struct Group { uint32_t frame_lo, frame_hi; uint32_t huf_lo, huf_hi, lit_lo, lit_hi, seq_lo, seq_hi, ord_lo, ord_hi; };
 
@@ -47,6 +47,7 @@ struct ZstdJobImpl {
     std::vector<uint32_t> lists;   // work lists of all groups (prepare)
     // running scratch use of the open group
     uint64_t g_lits = 0, g_seqs = 0; uint32_t g_huf = 0, g_fse = 0; uint32_t g_frame_lo = 0;
+    uint64_t limit_scale = group_scale_env() ? group_scale_env() : 4;   // multiplier of the group limits for the frame being admitted
     uint64_t max_lits = 0, max_seqs = 0; uint32_t max_huf = 0, max_fse = 0;
     uint64_t n_compressed = 0, n_seqs = 0;
     int threads = 0;               // host threads for the table-sized passes (add_values_blocks sets it)
@@ -74,7 +75,8 @@ struct ZstdJobImpl {
     // Frame number f (the next one) needs `u`: cuts the launch group in front of it when the group's scratch would overflow, and returns the
     // scratch of the group used up in front of the frame.
     FrameUse admit_frame(uint32_t f, const FrameUse& u) {
-        if (g_frame_lo != f && (g_lits + u.lits > kGroupLits || g_seqs + u.seqs > kGroupSeqs || g_huf + u.huf > kGroupSlots || g_fse + u.fse > kGroupSlots)) close_group_at(f);
+        const uint64_t m = limit_scale;
+        if (g_frame_lo != f && (g_lits + u.lits > kGroupLitsUnit * m || g_seqs + u.seqs > kGroupSeqsUnit * m || g_huf + u.huf > kGroupSlotsUnit * m || g_fse + u.fse > kGroupSlotsUnit * m)) close_group_at(f);
         FrameUse base{g_lits, g_seqs, g_huf, g_fse};
         g_lits += u.lits; g_seqs += u.seqs; g_huf += u.huf; g_fse += u.fse;
         return base;
@@ -147,7 +149,15 @@ struct ZstdJobImpl {
             }
         });
         for (int t = 0; t < T; t++) if (sh[t].bad != SIZE_MAX) { *bad = sh[t].bad; *msg = sh[t].msg; frames.clear(); return; }
-        for (size_t f = 0; f < 2 * n; f++) use[f] = admit_frame((uint32_t)f, use[f]);   // scratch need -> scratch base
+        // scratch need -> scratch base; the group limits follow the position in the batch (see the top of this file)
+        uint64_t total_seqs = 0, seen = 0;
+        for (size_t f = 0; f < 2 * n; f++) total_seqs += use[f].seqs;
+        for (size_t f = 0; f < 2 * n; f++) {
+            if (!group_scale_env()) limit_scale = (groups.empty() || seen > total_seqs - total_seqs / 12) ? 1 : 4;
+            seen += use[f].seqs;
+            use[f] = admit_frame((uint32_t)f, use[f]);
+        }
+        if (!group_scale_env()) limit_scale = 1;   // frames added one by one after the walk (timestamps) join the last, small group
         std::vector<size_t> base((size_t)T + 1, 0);
         for (int t = 0; t < T; t++) base[t + 1] = base[t] + sh[t].blocks.size();
         if (base[T] > 0xFFFFFFF0ull) throw BadInput("too many ZSTD blocks in one batch");
