@@ -98,6 +98,8 @@ typedef struct vlscan_stats {
     double gpu_ms;                /* device time of the scan kernels (CUDA events on the ctx stream)               */
     double scan_kernel_ms;        /* device time of the dominant string-scan kernel launches only                  */
     uint64_t scan_kernel_bytes;   /* algorithmic bytes processed by those launches                                 */
+    uint64_t staged_columns;      /* vlscan_scan_batch, bloom-first staging: (block, column) values payloads uploaded ...          */
+    uint64_t pruned_columns;      /* ... and left on the host because no filter could reach them (0 / 0 when staged in one go)     */
 } vlscan_stats;
 
 /* Synthetic data set description (benchmark / test infrastructure; row shape of app/vlogsgenerator/main.go:240-281). */

@@ -51,7 +51,7 @@ def test_struct_layouts_match_header():
     # sizes asserted against the C layout rules of include/vlscan.h (x86-64 SysV)
     assert C.sizeof(vs.CColumn) == 4 + 4 + 8 + 8 + 8 * 12
     assert C.sizeof(vs.CBlock) == 24 + 8 + 8 + 8 + 8   # + timestamps pointer, length, minTimestamp, maxTimestamp
-    assert C.sizeof(vs.CStats) == 8 * 14
+    assert C.sizeof(vs.CStats) == 8 * 16   # + staged_columns, pruned_columns
     assert C.sizeof(vs.GenConfig) == 32
 
 

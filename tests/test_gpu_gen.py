@@ -125,6 +125,55 @@ def test_baseline_queries_on_generated_blocks(env):
     batch.free()
 
 
+def test_bloom_first_staging_leaves_pruned_values_on_the_host(env):
+    """Clustered data (3 of 10 blocks hold vocabulary rows): staged bloom-first, the values of blocks the bloom filters rule out never cross
+    PCIe - fewer bytes, same bits, same accounting - for on-disk and decoded stage; a query without tokens is staged in one go."""
+    import os
+    import parity_util as pu
+    oracle, vs, ctx = env
+    _, gcfg = cfgs(oracle, vs, total_rows=400_000, rows_per_block=2000, hot_block_permille=300, hit_row_permille=100)
+    nb = 200
+    batch = ctx.generate(gcfg, 0, nb)
+    decoded = ctx.download(batch)
+    batch.free()
+    ondisk = decoded.compress(threads=8)
+    F = vs.Filter
+    trees = {"phrase": F.phrase("_msg", "timeout"), "and": F.and_([F.phrase("_msg", "timeout"), F.phrase("level", "error")]),
+             "or": F.or_([F.phrase("_msg", "timeout"), F.phrase("_msg", "terror")]), "not": F.not_(F.phrase("_msg", "timeout")),
+             "and-not": F.and_([F.phrase("_msg", "GET"), F.not_(F.prefix("path", "static"))]),
+             "or of ands": F.or_([F.and_([F.phrase("_msg", "timeout"), F.exact("level", "error")]), F.and_([F.phrase("_msg", "refused"), F.in_("status", ["500", "503"])])])}
+    old = os.environ.get("VLSCAN_BLOOM_FIRST")
+    try:
+        for name, tree in trees.items():
+            prog = vs.Program(tree)
+            for host in (ondisk, decoded):
+                res = {}
+                for mode in ("0", "2"):
+                    os.environ["VLSCAN_BLOOM_FIRST"] = mode
+                    w, c, st = ctx.scan_batch(prog, host)
+                    res[mode] = (w.copy(), c.copy(), st)
+                (w0, c0, s0), (w2, c2, s2) = res["0"], res["2"]
+                assert np.array_equal(w0, w2) and np.array_equal(c0, c2), name
+                for k in pu.ACCOUNTING:
+                    assert getattr(s0, k) == getattr(s2, k), (name, k)
+                assert s2.staged_columns + s2.pruned_columns > 0, name
+                if name in ("phrase", "and", "or", "not"):   # cold blocks fail the bloom probe (under NOT: every row matches unread): most _msg values stay on the host
+                    assert s2.pruned_columns > s2.staged_columns and s2.h2d_bytes < 0.7 * s0.h2d_bytes, (name, s2.pruned_columns, s2.staged_columns, s2.h2d_bytes, s0.h2d_bytes)
+        # no tokens, no probe: the default (adaptive) mode stages in one go
+        os.environ.pop("VLSCAN_BLOOM_FIRST", None)
+        w, c, st = ctx.scan_batch(vs.Program(F.regexp("_msg", "conn.*refused")), ondisk)
+        assert st.staged_columns == 0 and st.pruned_columns == 0
+        # adaptive: a probe that prunes nothing switches the next calls of the same program to one-go staging
+        prog = vs.Program(F.phrase("_msg", "stream"))   # a token of every row
+        seen = [ctx.scan_batch(prog, ondisk)[2].staged_columns for _ in range(3)]
+        assert seen[0] > 0 and seen[1] == 0 and seen[2] == 0, seen
+    finally:
+        if old is None:
+            os.environ.pop("VLSCAN_BLOOM_FIRST", None)
+        else:
+            os.environ["VLSCAN_BLOOM_FIRST"] = old
+
+
 def test_full_size_properties(env):
     """Size-independent properties at a larger scale (2M rows): NOT(f) complements f, AND is an intersection, counts add up,
     hit offsets are sorted and agree with the bitmaps, repeated scans are idempotent."""

@@ -250,10 +250,13 @@ def test_dense_candidates_and_ragged_lens(env):
     wide = [row(150) for _ in range(3000)]
     assert max(len(v) for v in wide) > 255
     fixed = [(b"timeout " if i % 2 else b"timeouts") + b"%056d" % i for i in range(5000)]   # 64 bytes each: const lens item, scanned
+    # every 16-byte vector of a 64 KiB tile holds a candidate word: more candidate vectors than the scan's queue takes (the tile is re-scanned in place)
+    sat = [(b"timeout " * 8 if i % 3 else b"timeouts" * 8) + b"%d" % i for i in range(4000)]
     blocks = [oracle.Block.from_columns([("f", ragged), ("k", [b"%d" % i for i in range(len(ragged))])]),
               oracle.Block.from_columns([("f", ragged2), ("k", [b"%d" % i for i in range(len(ragged2))])]),
               oracle.Block.from_columns([("f", wide), ("k", [b"%d" % i for i in range(len(wide))])]),
-              oracle.Block.from_columns([("f", fixed), ("k", [b"%d" % i for i in range(len(fixed))])])]
+              oracle.Block.from_columns([("f", fixed), ("k", [b"%d" % i for i in range(len(fixed))])]),
+              oracle.Block.from_columns([("f", sat), ("k", [b"%d" % i for i in range(len(sat))])])]
     for kind, arg in [("phrase", "timeout"), ("phrase", "error"), ("prefix", "time"), ("phrase", "GET"), ("phrase", "t"), ("regexp", "conn.*refused"), ("regexp", "timeout.*error"),
                       ("regexp", "e.*timeouts"), ("regexp", "error [a-z]+ t")]:
         for stage in ("ondisk", "decoded"):

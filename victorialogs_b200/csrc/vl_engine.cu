@@ -137,12 +137,14 @@ void finish_batch_layout(vlscan_ctx* ctx, vlscan_batch* b, const std::vector<uin
 // ---- upload --------------------------------------------------------------------------------------------------------------
 // The on-disk values blocks of a batch in (block, column) order; each one's place in the compressed staging buffer is a running sum that
 // starts behind 512 bytes of headroom (the device bit readers load whole aligned words around a stream).  Returns the end of the last one.
-static uint64_t collect_values_blocks(const vlscan_block* blocks, uint64_t nblocks, std::vector<ZValuesBlock>& zv) {
+// need (may be NULL = all): need[block * nfields + field] != 0 for the columns whose values are staged (phase 2 of a bloom-first upload).
+static uint64_t collect_values_blocks(const vlscan_block* blocks, uint64_t nblocks, std::vector<ZValuesBlock>& zv, const uint8_t* need = nullptr, uint32_t nfields = 0) {
     uint64_t zc = 512;
     for (uint64_t b = 0; b < nblocks; b++)
         for (uint32_t k = 0; k < blocks[b].ncols; k++) {
             const vlscan_column& c = blocks[b].cols[k];
             if (c.kind != VLSCAN_COL_VALUES || c.stage != VLSCAN_STAGE_ONDISK) continue;
+            if (need && (c.field >= nfields || !need[b * nfields + c.field])) continue;
             zv.push_back({c.values, (size_t)c.values_len, zc});
             zc += c.values_len;
         }
@@ -158,17 +160,30 @@ static int host_threads() {
 // need_bloom (may be NULL = all): per batch field, whether the program that will scan this batch ever probes that field's bloom filters.  A filter
 // nobody probes stays on the host (the reference reads a column's bloom filter lazily, only when a filter asks for it: getBloomFilterForColumn,
 // block_search.go:411-439); the column is staged with an empty filter, which no kernel touches.
+//
+// mode: UP_FULL stages everything in one go.  A bloom-first upload (vlscan_scan_batch, the reference's lazy order: a column's values are read only
+// after its bloom filter let the block through, block_search.go:411-439 then :444-474) runs the function twice around the probe pass:
+// UP_HEADERS stages what the header dispatch and the bloom probes look at (const values, bloom filters, dict tables -> batch->harena) and
+// leaves every values payload on the host (VALUES_DEFERRED); UP_VALUES then stages the timestamps and the values of the columns the probe marked in
+// `need` (-> batch->arena) and flags the others VALUES_ABSENT.
+enum UploadMode { UP_FULL = 0, UP_HEADERS = 1, UP_VALUES = 2 };
 static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const size_t* field_name_lens, uint32_t nfields, const vlscan_block* blocks,
-                      uint64_t nblocks, vlscan_batch* out, vlscan_stats* stats, const std::vector<char>* need_bloom = nullptr) {
+                      uint64_t nblocks, vlscan_batch* out, vlscan_stats* stats, const std::vector<char>* need_bloom = nullptr, UploadMode mode = UP_FULL,
+                      const uint8_t* need = nullptr) {
     VL_CUDA(cudaSetDevice(ctx->device));
     if (nblocks > 0xFFFFFFF0ull) throw BadInput("too many blocks in one batch");
     const bool dbg = getenv("VLSCAN_DEBUG_TIMING") != nullptr;
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t_start = now(), t_desc = 0, t_alloc = 0, t_copy = 0;
     out->device = ctx->device; out->nfields = nfields;
-    for (uint32_t f = 0; f < nfields; f++) out->field_names.emplace_back(field_names[f], field_name_lens[f]);
-    std::vector<DevColumn> cols((size_t)nblocks * std::max<uint32_t>(nfields, 1));
-    memset(cols.data(), 0, cols.size() * sizeof(DevColumn));
+    std::vector<DevColumn>& cols = out->h_cols;   // UP_VALUES continues with the table UP_HEADERS left
+    if (mode != UP_VALUES) {
+        for (uint32_t f = 0; f < nfields; f++) out->field_names.emplace_back(field_names[f], field_name_lens[f]);
+        cols.assign((size_t)nblocks * std::max<uint32_t>(nfields, 1), DevColumn{});
+        memset(cols.data(), 0, cols.size() * sizeof(DevColumn));
+    } else if (cols.size() != (size_t)nblocks * std::max<uint32_t>(nfields, 1) || !need) throw BadInput("internal: values phase of a bloom-first upload without its header phase");
+    out->split_hdr = mode != UP_FULL;
+    DevBuf& arena_buf = mode == UP_HEADERS ? out->harena : out->arena;
     std::vector<uint32_t> rows(nblocks);
     struct Piece { const uint8_t* src; uint64_t len; uint64_t dst; };
     std::vector<Piece> pieces, zpieces;   // host -> arena, host -> compressed staging (on-disk values blocks)
@@ -309,8 +324,8 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
     std::vector<DevTimestamps> tsv; bool any_ts = false;
     struct TsFrame { uint64_t block; uint32_t frame; uint64_t rel; };
     std::vector<TsFrame> ts_frames;
-    {
-        uint64_t zc = collect_values_blocks(blocks, nblocks, zv);
+    if (mode != UP_HEADERS) {
+        uint64_t zc = collect_values_blocks(blocks, nblocks, zv, mode == UP_VALUES ? need : nullptr, nfields);
         for (const ZValuesBlock& v : zv) if (v.n) zpieces.push_back({v.p, v.n, v.zoff});
         // ZSTD-compressed timestamps blocks (marshal types 1 and 4) travel the same way, behind the values blocks
         for (uint64_t b = 0; b < nblocks; b++) {
@@ -329,42 +344,8 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
         if (dbg) fprintf(stderr, "[vlscan upload] header walk of %zu values blocks on %d host threads: %.1f ms (after %.1f ms of collecting and enqueueing the copies)\n",
                          zv.size(), host_threads(), 1e3 * (now() - t_w), 1e3 * (t_w - t_start));
     }
-    for (uint64_t b = 0; b < nblocks; b++) {
-        const vlscan_block& blk = blocks[b];
-        if (blk.rows > (8u << 20)) throw BadInput("block rows exceed maxRowsPerBlock (8Mi)");   // consts.go:24
-        rows[b] = (uint32_t)blk.rows;
-        if (blk.ts_marshal_type) {   // the timestamps column: encoded deltas as stored + timestampsHeader (block_header.go:990-997)
-            if (blk.ts_marshal_type > MT_NEAREST_DELTA) throw BadInput("unknown MarshalType of a timestamps block");
-            if (blk.timestamps_len > vl::part::kMaxTimestampsBlockSize) throw BadInput("timestamps block size cannot exceed 8 MiB");
-            if (tsv.empty()) { tsv.resize(nblocks); memset(tsv.data(), 0, nblocks * sizeof(DevTimestamps)); }
-            any_ts = true;
-            DevTimestamps& t = tsv[b];
-            t.first = blk.min_timestamp; t.max = blk.max_timestamp;
-            if (blk.ts_marshal_type == MT_ZSTD_NEAREST_DELTA2 || blk.ts_marshal_type == MT_ZSTD_NEAREST_DELTA) {
-                uint64_t regen = 0; uint32_t id = 0;
-                zjob.add_frame(zts[zt].p, zts[zt].n, zts[zt].zoff, &regen, &id);   // throws on a malformed frame header
-                zt++;
-                if (regen > 10ull * blk.rows + 16) throw BadInput("cannot unmarshal timestamps: the decompressed block is larger than its varints can be");
-                t.mt = blk.ts_marshal_type == MT_ZSTD_NEAREST_DELTA2 ? MT_NEAREST_DELTA2 : MT_NEAREST_DELTA;
-                t.len = (uint32_t)regen;
-                ts_frames.push_back({b, id, arena_reserve(regen_cursor, regen)});
-            } else {
-                t.mt = (uint8_t)blk.ts_marshal_type; t.len = (uint32_t)blk.timestamps_len;
-                t.off = add_piece(blk.timestamps, blk.timestamps_len);
-            }
-        }
-        for (uint32_t k = 0; k < blk.ncols; k++) {
-            const vlscan_column& c = blk.cols[k];
-            if (c.field >= nfields) throw BadInput("column refers to a field outside the batch field table");
-            DevColumn& d = cols[(size_t)b * nfields + c.field];
-            if (d.kind != COL_MISSING) throw BadInput("duplicate column for one field in a block");
-            if (c.kind == VLSCAN_COL_CONST) {
-                d.kind = COL_CONST; d.meta_len = (uint32_t)c.const_len; d.meta_off = add_piece(c.const_value, c.const_len);
-                continue;
-            }
-            if (c.kind != VLSCAN_COL_VALUES) throw BadInput("unknown column kind");
-            if (c.value_type < VT_STRING || c.value_type >= VT_MAX) throw BadInput("unknown valueType");
-            d.kind = COL_VALUES; d.vt = c.value_type; d.min_value = c.min_value; d.max_value = c.max_value;
+    // the values payload of one column: on-disk stage -> regenerated by the device decoder, decoded stage -> copied
+    auto stage_values = [&](const vlscan_block& blk, const vlscan_column& c, DevColumn& d, uint64_t b) {
             if (c.stage == VLSCAN_STAGE_ONDISK) {
                 // stringsBlockUnmarshaler.unmarshal: bytesBlock(lens) ++ bytesBlock(data) (encoding.go:83-108).  The host reads the
                 // containers, the frame header and the block headers; the payload is regenerated on the device.
@@ -395,6 +376,54 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
                 // decode rule of encoding.go:113-120: rows >= 2, all lens equal, len(data) == lens[0] => every row = data
                 d.data_const = (blk.rows >= 2 && lt >= 4 && data_len == d.lens_const) ? 1 : 0;
             } else throw BadInput("unknown values stage");
+    };
+    for (uint64_t b = 0; b < nblocks; b++) {
+        const vlscan_block& blk = blocks[b];
+        if (blk.rows > (8u << 20)) throw BadInput("block rows exceed maxRowsPerBlock (8Mi)");   // consts.go:24
+        rows[b] = (uint32_t)blk.rows;
+        if (blk.ts_marshal_type && mode != UP_HEADERS) {   // the timestamps column: encoded deltas as stored + timestampsHeader (block_header.go:990-997)
+            if (blk.ts_marshal_type > MT_NEAREST_DELTA) throw BadInput("unknown MarshalType of a timestamps block");
+            if (blk.timestamps_len > vl::part::kMaxTimestampsBlockSize) throw BadInput("timestamps block size cannot exceed 8 MiB");
+            if (tsv.empty()) { tsv.resize(nblocks); memset(tsv.data(), 0, nblocks * sizeof(DevTimestamps)); }
+            any_ts = true;
+            DevTimestamps& t = tsv[b];
+            t.first = blk.min_timestamp; t.max = blk.max_timestamp;
+            if (blk.ts_marshal_type == MT_ZSTD_NEAREST_DELTA2 || blk.ts_marshal_type == MT_ZSTD_NEAREST_DELTA) {
+                uint64_t regen = 0; uint32_t id = 0;
+                zjob.add_frame(zts[zt].p, zts[zt].n, zts[zt].zoff, &regen, &id);   // throws on a malformed frame header
+                zt++;
+                if (regen > 10ull * blk.rows + 16) throw BadInput("cannot unmarshal timestamps: the decompressed block is larger than its varints can be");
+                t.mt = blk.ts_marshal_type == MT_ZSTD_NEAREST_DELTA2 ? MT_NEAREST_DELTA2 : MT_NEAREST_DELTA;
+                t.len = (uint32_t)regen;
+                ts_frames.push_back({b, id, arena_reserve(regen_cursor, regen)});
+            } else {
+                t.mt = (uint8_t)blk.ts_marshal_type; t.len = (uint32_t)blk.timestamps_len;
+                t.off = add_piece(blk.timestamps, blk.timestamps_len);
+            }
+        }
+        for (uint32_t k = 0; k < blk.ncols; k++) {
+            const vlscan_column& c = blk.cols[k];
+            if (c.field >= nfields) throw BadInput("column refers to a field outside the batch field table");
+            DevColumn& d = cols[(size_t)b * nfields + c.field];
+            if (mode == UP_VALUES) {   // the headers are on the device since phase 1; now the values of the columns the probe pass marked
+                if (c.kind != VLSCAN_COL_VALUES) continue;
+                if (!need[b * nfields + c.field]) { d.values_state = VALUES_ABSENT; continue; }
+                d.values_state = VALUES_STAGED;
+                stage_values(blk, c, d, b);
+                continue;
+            }
+            if (d.kind != COL_MISSING) throw BadInput("duplicate column for one field in a block");
+            if (c.kind == VLSCAN_COL_CONST) {
+                d.kind = COL_CONST; d.meta_len = (uint32_t)c.const_len; d.meta_off = add_piece(c.const_value, c.const_len);
+                continue;
+            }
+            if (c.kind != VLSCAN_COL_VALUES) throw BadInput("unknown column kind");
+            if (c.value_type < VT_STRING || c.value_type >= VT_MAX) throw BadInput("unknown valueType");
+            d.kind = COL_VALUES; d.vt = c.value_type; d.min_value = c.min_value; d.max_value = c.max_value;
+            if (mode == UP_HEADERS) {
+                if (c.stage != VLSCAN_STAGE_ONDISK && c.stage != VLSCAN_STAGE_DECODED) throw BadInput("unknown values stage");
+                d.values_state = VALUES_DEFERRED;
+            } else stage_values(blk, c, d, b);
             if (c.bloom_len % 8) throw BadInput("cannot unmarshal bloomFilter from src with size not multiple by 8");   // bloomfilter.go:59-61
             if (need_bloom && !(*need_bloom)[c.field]) { d.bloom_words = 0; d.bloom_off = add_piece(c.bloom, 0); }
             else { d.bloom_words = (uint32_t)(c.bloom_len / 8); d.bloom_off = add_piece(c.bloom, c.bloom_len); }
@@ -425,13 +454,15 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
     }
     for (const TsFrame& tf : ts_frames) { tsv[tf.block].off = regen_base + tf.rel; zjob.set_dst(tf.frame, regen_base + tf.rel); }
     if (!ondisk.empty() || !ts_frames.empty()) cursor = regen_base + regen_cursor;
-    out->arena_bytes = cursor + kArenaPad;
+    const uint64_t arena_bytes = cursor + kArenaPad;
+    (mode == UP_HEADERS ? out->harena_bytes : out->arena_bytes) = arena_bytes;
+    if (mode == UP_FULL) out->harena_bytes = 0;
     t_desc = now();
-    out->arena.ensure(out->arena_bytes);
+    arena_buf.ensure(arena_bytes);
     t_alloc = now();
     // the arena is cleared on the compute stream; the copy stream takes over from there
     cudaEvent_t ev_cleared = events.make(), ev_copied = events.make();
-    VL_CUDA(cudaMemsetAsync(out->arena.p, 0, out->arena_bytes, ctx->stream));
+    VL_CUDA(cudaMemsetAsync(arena_buf.p, 0, arena_bytes, ctx->stream));
     VL_CUDA(cudaEventRecord(ev_cleared, ctx->stream));
     VL_CUDA(cudaStreamWaitEvent(cs, ev_cleared, 0));
     // The decoder is enqueued BEFORE anything below that can block this thread (packing pageable pieces through the staging ring, copies
@@ -444,13 +475,13 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
             for (auto& m : zmarks) if (m.first >= src_end) { VL_CUDA(cudaStreamWaitEvent(ctx->stream, m.second, 0)); return; }
             if (!zmarks.empty()) VL_CUDA(cudaStreamWaitEvent(ctx->stream, zmarks.back().second, 0));
         });
-        zjob.run(ctx, ctx->zsrc.as<uint8_t>(), out->arena.as<uint8_t>());
+        zjob.run(ctx, ctx->zsrc.as<uint8_t>(), arena_buf.as<uint8_t>());
         if (dbg) t_zrun = now();
     }
-    copy_pieces(pieces, out->arena.as<uint8_t>());
+    copy_pieces(pieces, arena_buf.as<uint8_t>());
     out->cols.ensure(std::max<size_t>(cols.size() * sizeof(DevColumn), 16));
     if (!cols.empty()) VL_CUDA(cudaMemcpyAsync(out->cols.p, cols.data(), cols.size() * sizeof(DevColumn), cudaMemcpyHostToDevice, cs));
-    out->has_ts = any_ts;
+    if (mode != UP_HEADERS) out->has_ts = any_ts; else out->has_ts = false;
     if (any_ts) {
         out->ts.ensure(nblocks * sizeof(DevTimestamps));
         VL_CUDA(cudaMemcpyAsync(out->ts.p, tsv.data(), nblocks * sizeof(DevTimestamps), cudaMemcpyHostToDevice, cs));
@@ -466,7 +497,7 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
         VL_CUDA(cudaMemsetAsync(ctx->zcols.p, 0, 16, ctx->stream));
         VL_CUDA(cudaMemcpyAsync(ctx->zcols.as<uint8_t>() + 16, ocols.data(), ocols.size() * sizeof(OndiskCol), cudaMemcpyHostToDevice, ctx->stream));
         if (!ocols.empty()) {
-            k_finish_ondisk_cols<<<cdiv(ocols.size(), 128), 128, 0, ctx->stream>>>(out->arena.as<uint8_t>(), out->cols.as<DevColumn>(), (const OndiskCol*)(ctx->zcols.as<uint8_t>() + 16),
+            k_finish_ondisk_cols<<<cdiv(ocols.size(), 128), 128, 0, ctx->stream>>>(arena_buf.as<uint8_t>(), out->cols.as<DevColumn>(), (const OndiskCol*)(ctx->zcols.as<uint8_t>() + 16),
                                                                                      (uint32_t)ocols.size(), ctx->zcols.as<unsigned long long>());
             launch_check(ctx);
         }
@@ -480,13 +511,15 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
     VL_CUDA(cudaStreamWaitEvent(ctx->stream, ev_copied, 0));
     if (dbg) { VL_CUDA(cudaStreamSynchronize(ctx->stream)); t_copy = now(); }
     if (nfields) out->note_columns(cols);
-    finish_batch_layout(ctx, out, rows);   // synchronises the stream => `owned`, `cols`, staging are safe to drop
+    if (mode != UP_VALUES) finish_batch_layout(ctx, out, rows);   // synchronises the stream => `owned`, `cols`, staging are safe to drop
+    else VL_CUDA(cudaStreamSynchronize(ctx->stream));             // the layout tables are there since the header phase
     if (dbg) fprintf(stderr, "[vlscan upload] blocks=%llu arena=%.1f MB h2d=%.1f MB pieces=%zu+%zu pinned=%d: describe %.1f ms, alloc %.1f ms, copy %.1f ms (%.1f GB/s), "
                              "zstd %llu frames / %llu blocks / %llu sequences: enqueue %.1f ms, decode %.1f ms; layout %.1f ms\n", (unsigned long long)nblocks,
-                     out->arena_bytes / 1e6, h2d / 1e6, pieces.size(), zpieces.size(), (int)all_pinned, 1e3 * (t_desc - t_start), 1e3 * (t_alloc - t_desc), 1e3 * (t_enq - (t_zrun > 0 ? t_zrun : t_h2d)), h2d / 1e9 / std::max(t_copy - t_start, 1e-9),
+                     arena_bytes / 1e6, h2d / 1e6, pieces.size(), zpieces.size(), (int)all_pinned, 1e3 * (t_desc - t_start), 1e3 * (t_alloc - t_desc), 1e3 * (t_enq - (t_zrun > 0 ? t_zrun : t_h2d)), h2d / 1e9 / std::max(t_copy - t_start, 1e-9),
                      (unsigned long long)zjob.frames(), (unsigned long long)zjob.compressed_blocks(), (unsigned long long)zjob.sequences(), 1e3 * (t_zrun > 0 ? t_zrun - t_h2d : 0), 1e3 * (t_copy - t_enq), 1e3 * (now() - t_copy));
     (void)all_pinned;
-    h2d += out->nwords * 12 + nblocks * 12;
+    if (mode != UP_VALUES) h2d += out->nwords * 12 + nblocks * 12;
+    if (mode == UP_FULL) std::vector<DevColumn>().swap(out->h_cols);   // only a bloom-first upload needs the table again
     if (stats) stats->h2d_bytes += h2d;
 }
 
@@ -595,6 +628,37 @@ struct ScanRun {
         if (ctx->scan_events_used == ctx->scan_events.size()) { cudaEvent_t a, b; VL_CUDA(cudaEventCreate(&a)); VL_CUDA(cudaEventCreate(&b)); ctx->scan_events.emplace_back(a, b); }
         return ctx->scan_events[ctx->scan_events_used++];
     }
+    // ---- probe pass of a bloom-first upload: which (block, column) values can the program reach? ------------------------------------------
+    // `reg` only says which blocks are still alive: the AND / OR bloom pre-passes of a leaf's ancestors zero the blocks they rule out
+    // (exactly what they do to the bitmaps of the real scan); leaves do not touch it.  The real scan hands a leaf a subset of these rows, so
+    // the blocks whose values it reads are a subset of the blocks marked here.
+    void probe_leaf(int leaf_idx, const uint64_t* reg, uint8_t* need) {
+        const DevLeaf& L = prog->p.leaves[leaf_idx];
+        if (L.kind == F_NOOP || L.kind == F_TIME) return;   // timestamps always travel with the block
+        const int slot = L.field >= 0 ? field_slot[L.field] : -1;
+        if (L.kind == F_EQ_FIELD || L.kind == F_LE_FIELD) {
+            k_plan_pair<<<cdiv((uint64_t)B.nblocks * 32, 256), 256, 0, ctx->stream>>>(P, B, (uint32_t)leaf_idx, slot, field_slot[L.field2], reg, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stats, need);
+        } else {
+            if (slot < 0) return;   // a field the batch does not have: nothing to stage
+            k_plan_leaf<<<cdiv(B.nblocks, VL_PLAN_WARPS), VL_PLAN_WARPS * 32, 0, ctx->stream>>>(P, B, (uint32_t)leaf_idx, slot, reg, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stats, need);
+        }
+        launch_check(ctx);
+    }
+    void probe_node(int id, uint64_t* reg, uint8_t* need) {
+        const PNode& nd = prog->p.nodes[id];
+        switch (nd.kind) {
+        case F_NOOP: break;
+        case F_AND: case F_OR: {
+            uint64_t* r = reg;
+            if (nd.prepass_count) { r = new_reg(); copy_reg(r, reg); prepass(nd, r); }
+            for (int k : nd.kids) probe_node(k, r, need);
+            if (nd.prepass_count) free_reg();
+            break;
+        }
+        case F_NOT: probe_node(nd.kids[0], reg, need); break;
+        default: probe_leaf(nd.leaf, reg, need);
+        }
+    }
     // applyToBlockSearch of the combinators: filter_and.go:58-74, filter_or.go:55-78, filter_not.go:38-46
     void node(int id, uint64_t* reg) {
         const PNode& nd = prog->p.nodes[id];
@@ -624,8 +688,9 @@ static void read_stats(vlscan_ctx* ctx, vlscan_stats* st, bool check_error) {
     if (check_error && h[ST_ERROR]) {
         static const char* const msg[] = {"", "cannot unmarshal strings: row lengths do not add up to the data length", "too big index for dict value",
                                           "unexpected length for binary representation of a number", "phrase/prefix/regexp over a float64 column needs float->string formatting, which the GPU engine does not implement",
-                                          "unexpected uint64 block type", "the filter needs the timestamps of a block that was handed over without them", "cannot unmarshal timestamps"};
-        throw BadInput(msg[std::min<unsigned long long>(h[ST_ERROR], 7)]);
+                                          "unexpected uint64 block type", "the filter needs the timestamps of a block that was handed over without them", "cannot unmarshal timestamps",
+                                          "internal: a filter reached the values of a column that the bloom-first probe pass had left on the host"};
+        throw BadInput(msg[std::min<unsigned long long>(h[ST_ERROR], 8)]);
     }
     if (!st) return;
     st->values_bytes += h[ST_VALUES_BYTES]; st->bloom_probe_bytes += h[ST_BLOOM_BYTES]; st->columns_read += h[ST_COLUMNS_READ];
@@ -678,6 +743,31 @@ static void do_scan(vlscan_ctx* ctx, const vlscan_program* prog, const vlscan_ba
         read_stats(ctx, stats, true);
         stats->blocks += batch->nblocks; stats->rows += batch->rows; stats->gpu_launches += ctx->launches - launches0;
     }
+}
+
+// The probe pass between the two phases of a bloom-first upload: runs the program's bloom pre-passes, header dispatch and leaf bloom probes on a
+// batch whose values are still on the host and returns need[block * nfields + field] = 1 for every values column some filter can reach.
+static void do_probe(vlscan_ctx* ctx, const vlscan_program* prog, const vlscan_batch* batch, std::vector<uint8_t>& need) {
+    VL_CUDA(cudaSetDevice(ctx->device));
+    ScanRun run{ctx, prog, batch};
+    run.P = const_cast<vlscan_program*>(prog)->image(ctx->device, ctx->stream);
+    run.B = batch->view();
+    const Program& pr = prog->p;
+    run.field_slot.assign(pr.fields.size(), -1);
+    for (size_t f = 0; f < pr.fields.size(); f++) for (uint32_t s = 0; s < batch->nfields; s++) if (batch->field_names[s] == pr.fields[f]) run.field_slot[f] = (int)s;
+    for (auto& nd : pr.nodes) run.slots_total += nd.prepass_count;
+    const size_t cells = (size_t)batch->nblocks * batch->nfields;
+    need.assign(cells, 0);
+    if (!cells || !batch->nwords) return;
+    ctx->need.ensure(std::max<size_t>(cells, 16)); ctx->stats.ensure(ST_COUNT * 8);
+    VL_CUDA(cudaMemsetAsync(ctx->need.p, 0, cells, ctx->stream));
+    VL_CUDA(cudaMemsetAsync(ctx->stats.p, 0, ST_COUNT * 8, ctx->stream));
+    run.stats = ctx->stats.as<unsigned long long>();
+    uint64_t* reg = run.new_reg();
+    run.copy_reg(reg, batch->init_bitmap.as<uint64_t>());
+    run.probe_node(pr.root, reg, ctx->need.as<uint8_t>());
+    VL_CUDA(cudaMemcpyAsync(need.data(), ctx->need.p, cells, cudaMemcpyDeviceToHost, ctx->stream));
+    VL_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
 // ---- C ABI -------------------------------------------------------------------------------------------------------------------
@@ -865,6 +955,7 @@ int vlscan_batch_download(vlscan_ctx* ctx, const vlscan_batch* batch, vlscan_hos
     auto* hb = new vlscan_host_blocks();
     int rc = guarded(ctx, [&] {
         VL_CUDA(cudaSetDevice(ctx->device));
+        if (batch->split_hdr) throw BadInput("a batch staged bloom-first cannot be downloaded");
         hb->bytes = batch->arena_bytes;
         VL_CUDA(cudaMallocHost(&hb->pinned, std::max<size_t>(hb->bytes, 16)));
         std::vector<DevColumn> cols((size_t)batch->nblocks * batch->nfields);
@@ -1303,7 +1394,38 @@ int vlscan_scan_batch(vlscan_ctx* ctx, const vlscan_program* prog, const char* c
         for (const DevLeaf& L : P.leaves) if (L.nhashes || L.nhashes2 || L.in_nsets) mark(L.field);
         for (const DevPrepass& pp : P.prepass) if (pp.nhashes) mark(pp.field);
     }
-    int rc = guarded(ctx, [&] { do_upload(ctx, field_names, field_name_lens, nfields, blocks, nblocks, b, stats, &need_bloom); });
+    // Bloom-first staging (the reference reads a column's values only after the block got past the bloom filters, block_search.go:411-474): when
+    // the program probes bloom filters at all, the headers and bloom filters go first, a probe pass marks the columns some filter can reach,
+    // and only their values cross PCIe and get decoded.  VLSCAN_BLOOM_FIRST = 0 never, 2 always, 1 (default) adaptive: after a probe that
+    // pruned less than 1/8 of the values bytes the next 7 calls with the same program stage everything at once (the probe serialises the
+    // bloom copy with the decode, which costs more than it saves when nearly every block is read anyway).
+    int bf = 1;
+    if (const char* e = getenv("VLSCAN_BLOOM_FIRST")) bf = atoi(e);
+    bool probes = false;
+    for (char c : need_bloom) probes |= c != 0;
+    if (ctx->bf_prog != (const void*)prog) { ctx->bf_prog = prog; ctx->bf_skip = 0; }
+    const bool two_phase = bf != 0 && probes && nblocks > 0 && (bf == 2 || ctx->bf_skip == 0);
+    if (!two_phase && ctx->bf_skip > 0) ctx->bf_skip--;
+    int rc;
+    if (two_phase) {
+        rc = guarded(ctx, [&] {
+            do_upload(ctx, field_names, field_name_lens, nfields, blocks, nblocks, b, stats, &need_bloom, UP_HEADERS);
+            std::vector<uint8_t> need;
+            do_probe(ctx, prog, b, need);
+            uint64_t vals_all = 0, vals_need = 0, cols_all = 0, cols_need = 0;
+            for (uint64_t i = 0; i < nblocks; i++)
+                for (uint32_t k = 0; k < blocks[i].ncols; k++) {
+                    const vlscan_column& c = blocks[i].cols[k];
+                    if (c.kind != VLSCAN_COL_VALUES || c.field >= nfields) continue;
+                    const uint64_t n = c.stage == VLSCAN_STAGE_ONDISK ? c.values_len : c.lens_items_len + c.data_len;
+                    vals_all += n; cols_all++;
+                    if (need[i * nfields + c.field]) { vals_need += n; cols_need++; }
+                }
+            if (stats) { stats->staged_columns += cols_need; stats->pruned_columns += cols_all - cols_need; }
+            if (vals_need * 8 > vals_all * 7) ctx->bf_skip = 7;
+            do_upload(ctx, field_names, field_name_lens, nfields, blocks, nblocks, b, stats, &need_bloom, UP_VALUES, need.data());
+        });
+    } else rc = guarded(ctx, [&] { do_upload(ctx, field_names, field_name_lens, nfields, blocks, nblocks, b, stats, &need_bloom); });
     if (rc) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->stream); }   // nothing may still read the caller's buffers
     if (!rc) rc = vlscan_scan_resident(ctx, prog, b, nullptr);
     if (!rc) rc = vlscan_fetch_results(ctx, out_bitmap_words, out_match_counts, stats);

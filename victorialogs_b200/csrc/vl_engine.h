@@ -50,8 +50,11 @@ struct vlscan_batch {
     uint32_t nfields = 0;
     std::vector<std::string> field_names;
     uint64_t nblocks = 0, nwords = 0, rows = 0;
-    uint64_t arena_bytes = 0;
+    uint64_t arena_bytes = 0, harena_bytes = 0;
     vl::DevBuf arena, cols, blk_rows, blk_word_off, word_block, init_bitmap, ts;
+    vl::DevBuf harena;                    // bloom-first staging only: header payloads (bloom filters, const values, dict tables) of phase 1
+    bool split_hdr = false;               // the columns' bloom_off / meta_off refer to `harena`, not to `arena`
+    std::vector<vl::DevColumn> h_cols;    // bloom-first staging: the column table between the two phases
     bool has_ts = false;                  // some block came with its timestamps column
     std::vector<uint32_t> h_rows;
     std::vector<uint64_t> h_word_off;
@@ -62,14 +65,14 @@ struct vlscan_batch {
     }
     vl::BatchView view() const {
         vl::BatchView v;
-        v.arena = arena.as<uint8_t>(); v.cols = cols.as<vl::DevColumn>(); v.blk_rows = blk_rows.as<uint32_t>();
+        v.arena = arena.as<uint8_t>(); v.hdr = split_hdr ? harena.as<uint8_t>() : arena.as<uint8_t>(); v.cols = cols.as<vl::DevColumn>(); v.blk_rows = blk_rows.as<uint32_t>();
         v.blk_word_off = blk_word_off.as<uint64_t>(); v.word_block = word_block.as<uint32_t>();
         v.ts = has_ts ? ts.as<vl::DevTimestamps>() : nullptr;
         v.nblocks = (uint32_t)nblocks; v.nfields = nfields; v.nwords = nwords;
         return v;
     }
-    uint64_t device_bytes() const { return arena.cap + cols.cap + blk_rows.cap + blk_word_off.cap + word_block.cap + init_bitmap.cap + ts.cap; }
-    ~vlscan_batch() { cudaSetDevice(device); arena.release(); cols.release(); blk_rows.release(); blk_word_off.release(); word_block.release(); init_bitmap.release(); ts.release(); }
+    uint64_t device_bytes() const { return arena.cap + harena.cap + cols.cap + blk_rows.cap + blk_word_off.cap + word_block.cap + init_bitmap.cap + ts.cap; }
+    ~vlscan_batch() { cudaSetDevice(device); arena.release(); harena.release(); cols.release(); blk_rows.release(); blk_word_off.release(); word_block.release(); init_bitmap.release(); ts.release(); }
 };
 
 struct vlscan_ctx {
@@ -86,6 +89,8 @@ struct vlscan_ctx {
     std::vector<char> ready_cleared;
     vl::DevBuf hit_block, glens, goffs, gtiles, gout, gstat;   // hit materialisation (vlscan_gather_*): block of each hit, value lengths / offsets, output staging, error slot
     vl::DevBuf ts_vals;                    // decoded timestamps / running sums, 8 bytes per row of the batch (k_time_match, gather)
+    vl::DevBuf need;                       // bloom-first probe pass: one byte per (block, field), set when the column's values must be staged
+    const void* bf_prog = nullptr; int bf_skip = 0;   // adaptive bloom-first: after a probe that pruned next to nothing, the next calls with the same program stage everything at once
     vl::DevBuf zsrc, zcols, ztest;         // compressed staging of on-disk values blocks; their column list; test output
     vl::ZstdDev* zdev = nullptr;           // device ZSTD decoder scratch (vl_zstd.cu)
     void* pinned = nullptr; size_t pinned_cap = 0;

@@ -17,10 +17,12 @@ struct DevProgram {
 
 // stats slots (device u64 array)
 enum { ST_VALUES_BYTES = 0, ST_BLOOM_BYTES, ST_COLUMNS_READ, ST_BITMAP_BYTES, ST_ROWS_MATCHED, ST_BLOCKS_MATCHED, ST_ERROR, ST_SCAN_BYTES, ST_COUNT };
-enum { ERR_NONE = 0, ERR_LENS_MISMATCH = 1, ERR_DICT_INDEX = 2, ERR_BAD_WIDTH = 3, ERR_UNSUPPORTED_FLOAT_TOSTRING = 4, ERR_BAD_LENS_TYPE = 5, ERR_NO_TIMESTAMPS = 6, ERR_BAD_TIMESTAMPS = 7 };
+enum { ERR_NONE = 0, ERR_LENS_MISMATCH = 1, ERR_DICT_INDEX = 2, ERR_BAD_WIDTH = 3, ERR_UNSUPPORTED_FLOAT_TOSTRING = 4, ERR_BAD_LENS_TYPE = 5, ERR_NO_TIMESTAMPS = 6, ERR_BAD_TIMESTAMPS = 7, ERR_VALUES_ABSENT = 8 };
 
 struct BatchView {
-    const uint8_t* arena;
+    const uint8_t* arena;         // values payloads: lens items, data, encoded timestamps (lens_off, data_off, DevTimestamps.off)
+    const uint8_t* hdr;           // header payloads: bloom filters, const values, dict tables (bloom_off, meta_off).  The same buffer as `arena`
+                                  // unless the batch was staged bloom-first (vlscan_scan_batch): then it is the phase-1 buffer
     const DevColumn* cols;        // [nblocks * nfields]
     const uint32_t* blk_rows;     // [nblocks]
     const uint64_t* blk_word_off; // [nblocks + 1]
@@ -224,7 +226,7 @@ static __global__ void k_prepass(DevProgram P, BatchView B, uint32_t pp_begin, u
         if (c && c->kind == COL_CONST) {
             // matchStringByAllTokens(v, tokens)
             const uint32_t* to = (const uint32_t*)(P.blob + pp.tok_offs_off);
-            const uint8_t* v = B.arena + c->meta_off;
+            const uint8_t* v = B.hdr + c->meta_off;
             ok = true;
             for (uint32_t t = 0; t < pp.ntokens && ok; t++) ok = match_phrase(v, c->meta_len, P.blob + pp.tok_blob_off + to[t], to[t + 1] - to[t]);
         } else if (!c || c->kind == COL_MISSING) {
@@ -232,8 +234,8 @@ static __global__ void k_prepass(DevProgram P, BatchView B, uint32_t pp_begin, u
         } else if (c->vt == VT_DICT) {
             // matchDictValuesByAllTokens: dict values joined with ',' (filter_and.go:198-208); a token never contains ','
             // so a phrase occurrence lies inside one value; value edges behave like the ',' separator (non-token char).
-            const uint32_t* dof = (const uint32_t*)(B.arena + c->meta_off);
-            const uint8_t* dv = B.arena + c->meta_off + 4 * (c->dict_len + 1);
+            const uint32_t* dof = (const uint32_t*)(B.hdr + c->meta_off);
+            const uint8_t* dv = B.hdr + c->meta_off + 4 * (c->dict_len + 1);
             const uint32_t* to = (const uint32_t*)(P.blob + pp.tok_offs_off);
             ok = true;
             for (uint32_t t = 0; t < pp.ntokens && ok; t++) {
@@ -243,7 +245,7 @@ static __global__ void k_prepass(DevProgram P, BatchView B, uint32_t pp_begin, u
             }
         } else {
             bloom_bytes += 8ull * pp.nhashes;
-            ok = bloom_contains_all_warp(B.arena + c->bloom_off, c->bloom_words, P.u64s + pp.hashes_off, pp.nhashes);
+            ok = bloom_contains_all_warp(B.hdr + c->bloom_off, c->bloom_words, P.u64s + pp.hashes_off, pp.nhashes);
         }
         if (is_or) { if (!skip && ok) { pass = true; break; } }
         else if (!ok) { pass = false; break; }
@@ -265,7 +267,12 @@ enum { WC_LENS = 0, WC_TILES = 1, WC_ROW = 2, WC_LENS2 = 3, WC_COUNT = 4 };   //
 static __global__ void __launch_bounds__(VL_PLAN_WARPS * 32) k_plan_leaf(DevProgram P, BatchView B, uint32_t leaf_idx, int slot, const uint64_t* __restrict__ reg,
                             uint8_t* __restrict__ action, uint64_t* __restrict__ payload, uint32_t* __restrict__ lens_blocks, uint32_t* __restrict__ row_blocks,
                             uint32_t* __restrict__ tile_block, uint32_t* __restrict__ tile_off, uint32_t* __restrict__ work_count,
-                            unsigned long long* __restrict__ stats) {
+                            unsigned long long* __restrict__ stats, uint8_t* __restrict__ need = nullptr) {
+    // need != NULL: PROBE pass of a bloom-first upload (phase 1: headers, bloom filters and dict tables are on the device, no values yet).
+    // `reg` then only carries which blocks are still alive behind the AND / OR bloom pre-passes of the leaf's ancestors; the kernel runs the
+    // same header dispatch and bloom probes and sets need[block * nfields + slot] when the leaf would go on to read the column's values.
+    // Nothing else is written.  Every block the real scan reads values of is marked: the real scan reaches a leaf with a subset of the rows
+    // (hence blocks) the probe reaches it with, and the gates below do not depend on the rows.
     __shared__ uint32_t s_cnt[VL_PLAN_WARPS][3], s_off[VL_PLAN_WARPS][3];
     __shared__ unsigned long long s_stat[VL_PLAN_WARPS][4];
     const uint32_t warp = threadIdx.x >> 5;
@@ -293,7 +300,7 @@ static __global__ void __launch_bounds__(VL_PLAN_WARPS * 32) k_plan_leaf(DevProg
     }
     else if (c && c->kind == COL_CONST) {
         if (L.kind == F_VALUE_TYPE) act = L.aux0 == VTYPE_CONST ? ACT_ALL : ACT_NONE;   // filter_value_type.go:46-52
-        else act = leaf_match_string(P, L, B.arena + c->meta_off, c->meta_len) ? ACT_ALL : ACT_NONE;
+        else act = leaf_match_string(P, L, B.hdr + c->meta_off, c->meta_len) ? ACT_ALL : ACT_NONE;
     } else if (!c || c->kind == COL_MISSING) {
         switch (L.kind) {
         case F_PHRASE: case F_EXACT: case F_EXACT_PREFIX: act = nl == 0 ? ACT_ALL : ACT_NONE; break;
@@ -310,14 +317,14 @@ static __global__ void __launch_bounds__(VL_PLAN_WARPS * 32) k_plan_leaf(DevProg
     } else if (L.kind == F_VALUE_TYPE) {
         act = L.aux0 == c->vt ? ACT_ALL : ACT_NONE;   // valueType.String() == wanted name (filter_value_type.go:59-66); no payload is read
     } else if (c->vt == VT_DICT) {
-        const uint32_t* dof = (const uint32_t*)(B.arena + c->meta_off);
-        const uint8_t* dv = B.arena + c->meta_off + 4 * (c->dict_len + 1);
+        const uint32_t* dof = (const uint32_t*)(B.hdr + c->meta_off);
+        const uint8_t* dv = B.hdr + c->meta_off + 4 * (c->dict_len + 1);
         uint32_t mask = 0;
         for (uint32_t d = 0; d < c->dict_len; d++) if (leaf_match_string(P, L, dv + dof[d], dof[d + 1] - dof[d])) mask |= 1u << d;
         if (mask == 0) act = ACT_NONE; else { act = ACT_DICT; pay = mask; }
     } else {
         uint32_t vt = c->vt;
-        const uint8_t* bloom = B.arena + c->bloom_off;
+        const uint8_t* bloom = B.hdr + c->bloom_off;
         auto probe = [&](const uint64_t* h, uint32_t nh) -> bool {
             if (nh == 0) return true;
             bloom_bytes += 8ull * nh;
@@ -348,6 +355,7 @@ static __global__ void __launch_bounds__(VL_PLAN_WARPS * 32) k_plan_leaf(DevProg
             } else if (L.kind == F_ANY_CASE_PHRASE || L.kind == F_ANY_CASE_PREFIX || L.kind == F_RANGE) ok = true;   // i(...): tokens are case sensitive, range(): no tokens - no probe
             else ok = probe(H, L.nhashes);
             if (!ok) act = ACT_NONE;
+            else if (need) { act = ACT_ROW; values_bytes = 1; }   // probe: the values would be read
             else if (c->data_const) act = leaf_match_string(P, L, B.arena + c->data_off, (uint32_t)c->data_len) ? ACT_ALL : ACT_NONE, values_bytes = 1;
             else {
                 act = L.str_strategy == STR_SCAN ? ACT_SCAN : L.str_strategy == STR_ALL ? ACT_ALL : ACT_ROW; values_bytes = 1;
@@ -509,12 +517,20 @@ static __global__ void __launch_bounds__(VL_PLAN_WARPS * 32) k_plan_leaf(DevProg
         if (act >= ACT_DICT || values_bytes) values_bytes = lens_stored_bytes(*c, rows) + c->data_len;   // getValuesForColumn was reached
     }
     if (c && c->kind == COL_VALUES && c->vt == VT_DICT && act == ACT_DICT) values_bytes = lens_stored_bytes(*c, rows) + c->data_len;
+    if (need) {
+        if (c && c->kind == COL_VALUES && (values_bytes || act >= ACT_DICT) && lane_id() == 0) need[(uint64_t)b * B.nfields + slot] = 1;
+        act = ACT_NONE; values_bytes = 0; bloom_bytes = 0; err = 0;
+    } else if (c && c->kind == COL_VALUES && c->values_state != VALUES_STAGED && (values_bytes || act >= ACT_DICT)) {
+        // cannot happen unless the probe pass and this dispatch disagree: fail loudly rather than read values that were never uploaded
+        act = ACT_NONE; values_bytes = 0; err = ERR_VALUES_ABSENT;
+    }
     if (c && c->kind == COL_VALUES && (act == ACT_SCAN || act >= ACT_ROW)) {
         need_lens = 1;
         if (act == ACT_SCAN) { ntiles = (uint32_t)((c->data_len + VL_TILE_BYTES - 1) / VL_TILE_BYTES); scan_bytes = c->data_len; }
         else need_row = 1;
     }
     }
+    if (need) return;   // probe pass: uniform for the whole grid
     if (lane_id() == 0) {
         if (valid) { action[b] = act; payload[b] = pay; }
         if (err) atomicMax(&stats[ST_ERROR], (unsigned long long)err);
@@ -759,6 +775,44 @@ static __device__ __forceinline__ uint32_t scan_word_hits(uint32_t w, const Scan
     return (uint32_t)(w == sp.pat[0]) | (uint32_t)(w == sp.pat[1]) << 1 | (uint32_t)(w == sp.pat[2]) << 2 | (uint32_t)(w == sp.pat[3]) << 3;
 }
 
+// does any of the four words of v match one of the four (mask, pattern) pairs?  -> 0 / 1
+template <bool MASKED>
+static __device__ __forceinline__ uint32_t scan_vector_hit(const uint4& v, const ScanParams& sp) {
+    uint32_t h;
+    if (MASKED) {
+        asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+            "lop3.b32 t, %1, %5, %9, 0x28;\n\tsetp.eq.u32 p, t, 0;\n\t"
+            "lop3.b32 t, %1, %6, %10, 0x28;\n\tsetp.eq.or.u32 p, t, 0, p;\n\t"
+            "lop3.b32 t, %1, %7, %11, 0x28;\n\tsetp.eq.or.u32 p, t, 0, p;\n\t"
+            "lop3.b32 t, %1, %8, %12, 0x28;\n\tsetp.eq.or.u32 p, t, 0, p;\n\t"
+            "lop3.b32 t, %2, %5, %9, 0x28;\n\tsetp.eq.or.u32 p, t, 0, p;\n\t"
+            "lop3.b32 t, %2, %6, %10, 0x28;\n\tsetp.eq.or.u32 p, t, 0, p;\n\t"
+            "lop3.b32 t, %2, %7, %11, 0x28;\n\tsetp.eq.or.u32 p, t, 0, p;\n\t"
+            "lop3.b32 t, %2, %8, %12, 0x28;\n\tsetp.eq.or.u32 p, t, 0, p;\n\t"
+            "lop3.b32 t, %3, %5, %9, 0x28;\n\tsetp.eq.or.u32 p, t, 0, p;\n\t"
+            "lop3.b32 t, %3, %6, %10, 0x28;\n\tsetp.eq.or.u32 p, t, 0, p;\n\t"
+            "lop3.b32 t, %3, %7, %11, 0x28;\n\tsetp.eq.or.u32 p, t, 0, p;\n\t"
+            "lop3.b32 t, %3, %8, %12, 0x28;\n\tsetp.eq.or.u32 p, t, 0, p;\n\t"
+            "lop3.b32 t, %4, %5, %9, 0x28;\n\tsetp.eq.or.u32 p, t, 0, p;\n\t"
+            "lop3.b32 t, %4, %6, %10, 0x28;\n\tsetp.eq.or.u32 p, t, 0, p;\n\t"
+            "lop3.b32 t, %4, %7, %11, 0x28;\n\tsetp.eq.or.u32 p, t, 0, p;\n\t"
+            "lop3.b32 t, %4, %8, %12, 0x28;\n\tsetp.eq.or.u32 p, t, 0, p;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(h)
+            : "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(sp.pat[0]), "r"(sp.pat[1]), "r"(sp.pat[2]), "r"(sp.pat[3]), "r"(sp.msk[0]), "r"(sp.msk[1]), "r"(sp.msk[2]), "r"(sp.msk[3]));
+    } else {
+        asm("{\n\t.reg .pred p;\n\t"
+            "setp.eq.u32 p, %1, %5;\n\tsetp.eq.or.u32 p, %1, %6, p;\n\tsetp.eq.or.u32 p, %1, %7, p;\n\tsetp.eq.or.u32 p, %1, %8, p;\n\t"
+            "setp.eq.or.u32 p, %2, %5, p;\n\tsetp.eq.or.u32 p, %2, %6, p;\n\tsetp.eq.or.u32 p, %2, %7, p;\n\tsetp.eq.or.u32 p, %2, %8, p;\n\t"
+            "setp.eq.or.u32 p, %3, %5, p;\n\tsetp.eq.or.u32 p, %3, %6, p;\n\tsetp.eq.or.u32 p, %3, %7, p;\n\tsetp.eq.or.u32 p, %3, %8, p;\n\t"
+            "setp.eq.or.u32 p, %4, %5, p;\n\tsetp.eq.or.u32 p, %4, %6, p;\n\tsetp.eq.or.u32 p, %4, %7, p;\n\tsetp.eq.or.u32 p, %4, %8, p;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(h)
+            : "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(sp.pat[0]), "r"(sp.pat[1]), "r"(sp.pat[2]), "r"(sp.pat[3]));
+    }
+    return h;
+}
+
 // Candidates are not verified where they are found.  A lane whose 16-byte vector holds a candidate word appends (block, byte position of the
 // VECTOR) to a queue in shared memory and goes on streaming; out of the queue, the CTA's 256 threads take one vector each, re-read it (it is
 // still in L2), enumerate its candidate words / alignments and verify them.  Verifying in place costs a chain of ~6 dependent memory round trips
@@ -768,7 +822,7 @@ static __device__ __forceinline__ uint32_t scan_word_hits(uint32_t w, const Scan
 // the kernel (profiles/kernel_history_r02.md).  Now it only ballots which lanes have a hit in each of their four vectors and reserves queue
 // slots with one shared-memory atomic per vector index.  The queue is drained when a tile ends with at least VL_SCAN_QFLUSH entries, and when
 // the CTA has run out of tiles.  A vector that finds the queue full is handled by its lane on the spot.
-#define VL_SCAN_QCAP 1024
+#define VL_SCAN_QCAP 2048
 #define VL_SCAN_QFLUSH 192
 struct ScanCand { uint32_t block, pos; };   // pos: byte offset of a 16-byte vector inside the block's data
 
@@ -792,30 +846,71 @@ static __device__ __forceinline__ void scan_vector(const DevProgram& P, const Ba
     }
 }
 
-// Called by the WHOLE warp when some lane has a hit: `hits` bit u = this lane's vector u holds a candidate word.  Kept out of line on purpose:
-// behind a call boundary the compiler cannot share sub-expressions with the filter of the hot loop (it spilled 16 masked words per round to do
-// so), and the registers of this path do not count against the 48 of the streaming loop.
-template <bool MASKED>
-static __device__ __noinline__ void scan_enqueue(const DevProgram& P, const BatchView& B, const DevColumn& c, const ScanParams& sp, uint32_t b,
-                                                 const uint32_t* __restrict__ row_off8, uint64_t* __restrict__ leaf_bm, ScanCand* s_q, uint32_t* s_cnt,
-                                                 uint32_t hits, uint32_t base) {
+// One tile of the streaming side.  FULL: the tile lies wholly inside the data, so the four loads of a round go out without bounds predicates at
+// immediate offsets from one pointer; otherwise (a block's last tile) every vector is checked against the end of the data and vectors past it
+// are streamed as zeros.  INPLACE: candidates are verified where they are found instead of being queued (the re-scan of a tile whose
+// candidates did not fit the queue).  Returns true when this lane had a candidate vector that found the queue full.
+// The queueing code is inline on purpose: with a call inside the round loop ptxas parks the loop state (pointer, round counter, block) in local
+// memory around every round (the call ABI pins most of the 48 registers), 6 local loads / stores per round.
+template <bool MASKED, bool FULL, bool INPLACE>
+static __device__ __forceinline__ bool scan_tile(const DevProgram& P, const BatchView& B, const DevColumn& c, const ScanParams& sp, uint32_t b,
+                                                 const uint32_t* __restrict__ row_off8, uint64_t* __restrict__ leaf_bm, ScanCand* s_q, uint32_t* s_cnt, uint32_t tile0) {
+    const uint32_t n = (uint32_t)c.data_len;           // < 4 GiB by construction (upload rejects larger payloads)
+    const uint8_t* __restrict__ data = B.arena + c.data_off;
     const uint32_t lane = threadIdx.x & 31;
+    bool overflow = false;
+#pragma unroll 1
+    for (int round = 0; round < VL_SCAN_ROUNDS; round++) {
+        const uint32_t round0 = tile0 + (uint32_t)round * (VL_SCAN_THREADS * 16);
+        if (!FULL && round0 >= n) break;                  // uniform: the whole round lies past the data
+        const uint32_t base = round0 + threadIdx.x * 16;
+        uint4 v[VL_SCAN_UNROLL];
+        if (FULL) {
+            const uint8_t* __restrict__ ptr = data + base;
 #pragma unroll
-    for (int u = 0; u < VL_SCAN_UNROLL; u++) {
-        const bool mine = hits >> u & 1;
-        const uint32_t m = __ballot_sync(0xffffffffu, mine);
-        if (!m) continue;
-        const int leader = __ffs((int)m) - 1;
-        uint32_t at0 = 0;
-        if ((int)lane == leader) at0 = atomicAdd(s_cnt, (uint32_t)__popc(m));
-        at0 = __shfl_sync(0xffffffffu, at0, leader);
-        if (mine) {
-            const uint32_t at = at0 + __popc(m & ((1u << lane) - 1u));
+            for (int u = 0; u < VL_SCAN_UNROLL; u++) v[u] = __ldg((const uint4*)(ptr + u * VL_SCAN_QSTRIDE));
+        } else {
+#pragma unroll
+            for (int u = 0; u < VL_SCAN_UNROLL; u++) {
+                const uint32_t p = base + u * VL_SCAN_QSTRIDE;
+                // payloads keep >= 32 readable bytes past data_len: a vector load that starts before n is always in bounds
+                v[u] = p < n ? __ldg((const uint4*)(data + p)) : make_uint4(0, 0, 0, 0);
+            }
+        }
+        // bit u of `hits`: vector u holds a word equal to one of the four patterns (one predicate chain of 16 x setp.eq.or per vector)
+        uint32_t hits = 0;
+#pragma unroll
+        for (int u = 0; u < VL_SCAN_UNROLL; u++) hits |= scan_vector_hit<MASKED>(v[u], sp) << u;
+        if (!__any_sync(0xffffffffu, hits != 0)) continue;
+        // some lane has a candidate: the whole warp reserves queue slots, one shared-memory atomic per vector index
+#pragma unroll
+        for (int u = 0; u < VL_SCAN_UNROLL; u++) {
+            const bool mine = hits >> u & 1;
             const uint32_t pos = base + u * VL_SCAN_QSTRIDE;
-            if (at < VL_SCAN_QCAP) s_q[at] = ScanCand{b, pos};
-            else scan_vector<MASKED>(P, B, c, sp, b, row_off8, pos, leaf_bm);
+            if (INPLACE) { if (mine) scan_vector<MASKED>(P, B, c, sp, b, row_off8, pos, leaf_bm); continue; }
+            const uint32_t m = __ballot_sync(0xffffffffu, mine);
+            if (!m) continue;
+            const int leader = __ffs((int)m) - 1;
+            uint32_t at0 = 0;
+            if ((int)lane == leader) at0 = atomicAdd(s_cnt, (uint32_t)__popc(m));
+            at0 = __shfl_sync(0xffffffffu, at0, leader);
+            if (mine) {
+                const uint32_t at = at0 + __popc(m & ((1u << lane) - 1u));
+                if (at < VL_SCAN_QCAP) s_q[at] = ScanCand{b, pos}; else overflow = true;
+            }
         }
     }
+    return overflow;
+}
+template <bool MASKED>
+static __device__ __noinline__ bool scan_tail_tile(const DevProgram& P, const BatchView& B, const DevColumn& c, const ScanParams& sp, uint32_t b,
+                                                   const uint32_t* __restrict__ row_off8, uint64_t* __restrict__ leaf_bm, ScanCand* s_q, uint32_t* s_cnt, uint32_t tile0) {
+    return scan_tile<MASKED, false, false>(P, B, c, sp, b, row_off8, leaf_bm, s_q, s_cnt, tile0);
+}
+template <bool MASKED>
+static __device__ __noinline__ void scan_tile_inplace(const DevProgram& P, const BatchView& B, const DevColumn& c, const ScanParams& sp, uint32_t b,
+                                                      const uint32_t* __restrict__ row_off8, uint64_t* __restrict__ leaf_bm, uint32_t tile0) {
+    scan_tile<MASKED, false, true>(P, B, c, sp, b, row_off8, leaf_bm, nullptr, nullptr, tile0);
 }
 template <bool MASKED>
 static __device__ __noinline__ void scan_drain(const DevProgram& P, const BatchView& B, int slot, const ScanParams& sp, const uint32_t* __restrict__ row_off8,
@@ -840,36 +935,15 @@ static __global__ void __launch_bounds__(VL_SCAN_THREADS, 5) k_substr_scan(const
     for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const uint32_t b = __ldg(tile_block + t), tile0 = __ldg(tile_off + t);
         const DevColumn& c = B.cols[(uint64_t)b * B.nfields + slot];
-        const uint32_t n = (uint32_t)c.data_len;           // < 4 GiB by construction (upload rejects larger payloads)
-        const uint8_t* __restrict__ data = B.arena + c.data_off;
-#pragma unroll 1
-        for (int round = 0; round < VL_SCAN_ROUNDS; round++) {
-            const uint32_t round0 = tile0 + (uint32_t)round * (VL_SCAN_THREADS * 16);
-            if (round0 >= n) break;                           // uniform: the whole round lies past the data
-            const uint32_t base = round0 + threadIdx.x * 16;
-            uint4 v[VL_SCAN_UNROLL];
-#pragma unroll
-            for (int u = 0; u < VL_SCAN_UNROLL; u++) {
-                uint32_t p = base + u * VL_SCAN_QSTRIDE;
-                // payloads keep >= 32 readable bytes past data_len: a vector load that starts before n is always in bounds
-                v[u] = p < n ? __ldg((const uint4*)(data + p)) : make_uint4(0, 0, 0, 0);
-            }
-            bool hit[VL_SCAN_UNROLL];
-#pragma unroll
-            for (int u = 0; u < VL_SCAN_UNROLL; u++) {
-                const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-                hit[u] = false;
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    if (MASKED) hit[u] |= (w[i] & sp.msk[0]) == sp.pat[0] || (w[i] & sp.msk[1]) == sp.pat[1] || (w[i] & sp.msk[2]) == sp.pat[2] || (w[i] & sp.msk[3]) == sp.pat[3];
-                    else hit[u] |= w[i] == sp.pat[0] || w[i] == sp.pat[1] || w[i] == sp.pat[2] || w[i] == sp.pat[3];
-                }
-            }
-            const uint32_t hits = (uint32_t)hit[0] | (uint32_t)hit[1] << 1 | (uint32_t)hit[2] << 2 | (uint32_t)hit[3] << 3;
-            if (__any_sync(0xffffffffu, hits != 0)) scan_enqueue<MASKED>(P, B, c, sp, b, row_off8, leaf_bm, s_q, &s_cnt, hits, base);   // the whole warp goes
-        }
-        // end of the tile: drain the queue if it is worth a pass of the whole CTA (thread 0 decides; the barrier makes the decision uniform)
-        if (__syncthreads_or(threadIdx.x == 0 && s_cnt >= VL_SCAN_QFLUSH)) {
+        bool overflow;
+        if (tile0 + VL_TILE_BYTES <= (uint32_t)c.data_len) overflow = scan_tile<MASKED, true, false>(P, B, c, sp, b, row_off8, leaf_bm, s_q, &s_cnt, tile0);
+        else overflow = scan_tail_tile<MASKED>(P, B, c, sp, b, row_off8, leaf_bm, s_q, &s_cnt, tile0);
+        // end of the tile: drain the queue if it is worth a pass of the whole CTA (thread 0 decides; the barrier makes the decision uniform),
+        // or if some candidate vector of this tile did not fit
+        if (__syncthreads_or((threadIdx.x == 0 && s_cnt >= VL_SCAN_QFLUSH) || overflow)) {
+            // candidates that did not fit were dropped: the tile is gone over again with verification in place (bits are OR-ed, so the
+            // candidates that did make it into the queue and are verified again below change nothing)
+            if (__syncthreads_or(overflow)) scan_tile_inplace<MASKED>(P, B, c, sp, b, row_off8, leaf_bm, tile0);
             scan_drain<MASKED>(P, B, slot, sp, row_off8, leaf_bm, s_q, min(s_cnt, (uint32_t)VL_SCAN_QCAP));
             __syncthreads();
             if (threadIdx.x == 0) s_cnt = 0;
@@ -1239,7 +1313,7 @@ static __global__ void k_gather_values(BatchView B, int slot, const uint32_t* __
     uint8_t buf[VL_FMT_F64_MAX];
     if (slot >= 0) {
         const DevColumn& c = B.cols[(uint64_t)b * B.nfields + slot];
-        if (c.kind == COL_CONST) { src = B.arena + c.meta_off; len = c.meta_len; }
+        if (c.kind == COL_CONST) { src = B.hdr + c.meta_off; len = c.meta_len; }
         else if (c.kind == COL_VALUES) {
             const uint8_t* data = B.arena + c.data_off;
             if (c.vt == VT_STRING) {
@@ -1255,7 +1329,7 @@ static __global__ void k_gather_values(BatchView B, int slot, const uint32_t* __
             } else if (c.vt == VT_DICT) {
                 const uint32_t id = data[r];
                 if (id >= c.dict_len) atomicMax(&stats[ST_ERROR], (unsigned long long)ERR_DICT_INDEX);
-                else { const uint32_t* dof = (const uint32_t*)(B.arena + c.meta_off); src = B.arena + c.meta_off + 4 * (c.dict_len + 1) + dof[id]; len = dof[id + 1] - dof[id]; }
+                else { const uint32_t* dof = (const uint32_t*)(B.hdr + c.meta_off); src = B.hdr + c.meta_off + 4 * (c.dict_len + 1) + dof[id]; len = dof[id + 1] - dof[id]; }
             } else {
                 const uint32_t w = width_of_vt(c.vt);
                 const uint64_t raw = load_fixed_be(data + (uint64_t)r * w, w);
@@ -1328,14 +1402,14 @@ static __device__ bool row_bytes(const BatchView& B, const DevColumn& c, uint32_
 static __device__ bool row_string(const BatchView& B, const DevColumn* c, uint32_t b, uint32_t r, const uint32_t* __restrict__ row_off8, uint8_t* buf, const uint8_t** p, uint32_t* n) {
     *p = buf; *n = 0;
     if (!c || c->kind == COL_MISSING) return true;
-    if (c->kind == COL_CONST) { *p = B.arena + c->meta_off; *n = c->meta_len; return true; }
+    if (c->kind == COL_CONST) { *p = B.hdr + c->meta_off; *n = c->meta_len; return true; }
     const uint8_t* v; uint32_t vn;
     if (!row_bytes(B, *c, b, r, row_off8, &v, &vn)) return false;
     if (c->vt == VT_STRING) { *p = v; *n = vn; return true; }
     if (c->vt == VT_DICT) {
         if (vn != 1 || v[0] >= c->dict_len) return false;
-        const uint32_t* dof = (const uint32_t*)(B.arena + c->meta_off);
-        *p = B.arena + c->meta_off + 4 * (c->dict_len + 1) + dof[v[0]]; *n = dof[v[0] + 1] - dof[v[0]];
+        const uint32_t* dof = (const uint32_t*)(B.hdr + c->meta_off);
+        *p = B.hdr + c->meta_off + 4 * (c->dict_len + 1) + dof[v[0]]; *n = dof[v[0] + 1] - dof[v[0]];
         return true;
     }
     if (vn != width_of_vt(c->vt)) return false;
@@ -1357,7 +1431,8 @@ static __device__ bool le_values_string(const uint8_t* a, uint32_t an, const uin
 // header-level decisions of a two-column leaf; one warp per block (lane 0 decides), work lists like k_plan_leaf
 static __global__ void __launch_bounds__(256) k_plan_pair(DevProgram P, BatchView B, uint32_t leaf_idx, int slot_a, int slot_b, const uint64_t* __restrict__ reg, uint8_t* __restrict__ action,
                                                            uint64_t* __restrict__ payload, uint32_t* __restrict__ lens_a, uint32_t* __restrict__ lens_b, uint32_t* __restrict__ row_blocks,
-                                                           uint32_t* __restrict__ work_count, unsigned long long* __restrict__ stats) {
+                                                           uint32_t* __restrict__ work_count, unsigned long long* __restrict__ stats, uint8_t* __restrict__ need = nullptr) {
+    // need != NULL: probe pass of a bloom-first upload (see k_plan_leaf): marks the values columns the row kernel would read, writes nothing else
     const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (b >= B.nblocks) return;
     const DevLeaf& L = P.leaves[leaf_idx];
@@ -1373,7 +1448,7 @@ static __global__ void __launch_bounds__(256) k_plan_pair(DevProgram P, BatchVie
         const bool consta = ka == COL_CONST && ca->meta_len > 0, constb = kb == COL_CONST && cb->meta_len > 0;
         const bool vala = ka == COL_VALUES, valb = kb == COL_VALUES;
         if (consta && constb) {
-            const uint8_t* x = B.arena + ca->meta_off; const uint8_t* y = B.arena + cb->meta_off;
+            const uint8_t* x = B.hdr + ca->meta_off; const uint8_t* y = B.hdr + cb->meta_off;
             const bool m = le ? le_values_string(x, ca->meta_len, y, cb->meta_len, excl) : bytes_equal(x, ca->meta_len, y, cb->meta_len);
             act = m ? ACT_ALL : ACT_NONE;
         } else if (consta || constb) act = ACT_PAIR;                                      // one const: row strings
@@ -1381,6 +1456,14 @@ static __global__ void __launch_bounds__(256) k_plan_pair(DevProgram P, BatchVie
         else if (!vala || !valb) act = ACT_PAIR;                                          // one missing: row strings
         else if (ca->vt != cb->vt || ca->vt == VT_STRING) act = ACT_PAIR;
         else { act = ACT_PAIR; mode = ca->vt == VT_DICT ? PAIR_DICT : PAIR_BINARY; }
+        if (act == ACT_PAIR && need) {
+            if (vala) need[(uint64_t)b * B.nfields + slot_a] = 1;
+            if (valb) need[(uint64_t)b * B.nfields + slot_b] = 1;
+            return;
+        }
+        if (act == ACT_PAIR && ((vala && ca->values_state != VALUES_STAGED) || (valb && cb->values_state != VALUES_STAGED))) {
+            atomicMax(&stats[ST_ERROR], (unsigned long long)ERR_VALUES_ABSENT); act = ACT_NONE;
+        }
         if (act == ACT_PAIR) {
             unsigned long long vb = 0, cols = 0;
             if (vala) { vb += lens_stored_bytes(*ca, B.blk_rows[b]) + ca->data_len; cols++; if (ca->lens_type < 4 && !ca->data_const) lens_a[atomicAdd(&work_count[WC_LENS], 1u)] = b; }
@@ -1389,6 +1472,7 @@ static __global__ void __launch_bounds__(256) k_plan_pair(DevProgram P, BatchVie
             atomicAdd(&stats[ST_VALUES_BYTES], vb); atomicAdd(&stats[ST_COLUMNS_READ], cols);
         }
     }
+    if (need) return;
     action[b] = act; payload[b] = mode;
 }
 static __device__ __noinline__ bool pair_match_row(const DevProgram& P, const BatchView& B, const DevLeaf& L, const DevColumn* ca, const DevColumn* cb, uint32_t b, uint32_t r, uint32_t mode,

@@ -11,6 +11,9 @@ enum { F_NOOP = 0, F_PHRASE, F_PREFIX, F_EXACT, F_IN, F_REGEXP, F_AND, F_OR, F_N
        F_EQ_FIELD = 19, F_LE_FIELD = 20, F_RANGE = 21, F_TIME = 22 };
 enum { VTYPE_CONST = 0, VTYPE_NO_SUCH = 255 };   // F_VALUE_TYPE: DevLeaf.aux0 = VT_* code of the wanted type, or one of these
 enum { COL_MISSING = 0, COL_CONST = 1, COL_VALUES = 2 };
+enum { VALUES_STAGED = 0,     // lens items and data are in the arena
+       VALUES_DEFERRED = 1,   // phase 1 of a bloom-first upload: only the header payloads (bloom filter, dict) are on the device yet
+       VALUES_ABSENT = 2 };   // the probe pass proved that no filter of the program reads this column's values in this block: they stayed on the host
 
 // One (block, field) cell of a resident batch: the columnHeader fields the scan needs + arena offsets of the payloads
 // (lib/logstorage/block_header.go:584-615).  Offsets are relative to the batch arena base.
@@ -20,7 +23,8 @@ struct DevColumn {
     uint8_t lens_type;     // uintBlockType 0..7 (lib/logstorage/encoding.go:177-187)
     uint8_t dict_len;
     uint8_t data_const;    // decode rule "every row = data" (encoding.go:113-120)
-    uint8_t pad[3];
+    uint8_t values_state;  // VALUES_*: bloom-first staging (vlscan_scan_batch) leaves the values of a column on the host while / when no filter can reach them
+    uint8_t pad[2];
     uint32_t lens_const;   // the single item of a const lens block
     uint32_t bloom_words;
     uint64_t min_value, max_value;

@@ -55,7 +55,7 @@ class CBlock(C.Structure):
 class CStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("blocks", "rows", "rows_matched", "blocks_matched", "values_bytes", "bloom_probe_bytes", "bitmap_bytes",
                                           "columns_read", "gpu_launches", "h2d_bytes", "d2h_bytes")] + \
-               [("gpu_ms", C.c_double), ("scan_kernel_ms", C.c_double), ("scan_kernel_bytes", C.c_uint64)]
+               [("gpu_ms", C.c_double), ("scan_kernel_ms", C.c_double), ("scan_kernel_bytes", C.c_uint64), ("staged_columns", C.c_uint64), ("pruned_columns", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
