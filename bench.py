@@ -408,22 +408,61 @@ def main():
 
     # ---- the other single-GPU configs of BASELINE.json, same run -------------------------------------------------------------------------
     extra = {}
-    if world == 1 and not args.no_extra:
-        for name in ("C2", "C4"):
+    if not args.no_extra:
+        # N > 1: C4 is BASELINE.json configs[3] - "1B rows block-sharded 8xB200" is 125 M rows per GPU, so at N = 8 this IS that configuration
+        for name in (("C2", "C4") if world == 1 else ("C4",)):
             if name == args.workload:
                 continue
             try:
                 w = WORKLOADS[name]
                 w_rows, w_nb, w_kw = gen_args(w, w["rows"])
                 x = measure(w, w_rows, w_nb, w_kw, 10, 3, False)
-                extra[name] = {"workload": "%s: %s over %d rows, %d fields" % (name, w["logsql"], w_rows, w["fields"]), "value": w_rows * x["steps"] / (x["ms"] / 1e3), "unit": "rows/s",
+                extra[name] = {"workload": "%s: %s over %d rows/GPU x %d GPU(s), %d fields" % (name, w["logsql"], w_rows, world, w["fields"]), "value": w_rows * world * x["steps"] / (x["ms"] / 1e3), "unit": "rows/s",
                                "ms_per_step": x["ms"] / x["steps"], "rows_matched": int(x["st"].rows_matched), "gpu_launches_per_step": int(x["st"].gpu_launches),
-                               "step_hbm_gbs": (x["step_bytes"] / 1e9) / (x["ms"] / x["steps"] / 1e3),
+                               "step_hbm_gbs_per_gpu": (x["step_bytes"] / 1e9) / (x["ms"] / x["steps"] / 1e3),
                                "roofline": {"kernel": "k_substr_scan", "achieved": x["achieved"], "peak": peak, "unit": "GB/s", "frac": x["achieved"] / peak, "kernel_ms_per_launch": x["k_avg"],
                                             "algorithmic_bytes_per_launch": int(x["kbytes"]), "kernel_share_of_step": x["share"]}}
                 x["batch"].free()
             except Exception as e:
                 extra[name] = {"error": str(e)[:200]}
+
+    # ---- bloom-first staging on clustered data: C2 with vocabulary rows in 1 block of 10 (the bloom filters rule the others out) ----------------
+    bloom_first = None
+    if world == 1 and not args.no_extra and not args.no_e2e:
+        try:
+            w = WORKLOADS["C2"]
+            b_rows, b_nb, b_kw = gen_args(w, min(w["rows"], args.e2e_rows))
+            b_kw["hot_block_permille"] = 100
+            sub = ctx.generate(vs.GenConfig(**b_kw), 0, b_nb)
+            host = ctx.download(sub)
+            sub.free()
+            disk = host.compress(threads=os.cpu_count() or 1)
+            del host
+            b_prog = vs.Program(w["tree"](vs.Filter))
+            nwords = sum((r + 63) // 64 for r in disk.rows)
+            words = np.zeros(max(nwords, 1), dtype=np.uint64)
+            counts = np.zeros(max(disk.nblocks, 1), dtype=np.uint32)
+            bloom_first = {"workload": "C2: %s over %d rows, vocabulary rows in 1 block of 10 (hot_block_permille 100), on-disk blocks on pinned host memory" % (w["logsql"], b_rows)}
+            keep = os.environ.get("VLSCAN_BLOOM_FIRST")
+            for key, mode in (("one_go", "0"), ("bloom_first", "2")):
+                os.environ["VLSCAN_BLOOM_FIRST"] = mode
+                ctx.scan_batch(b_prog, disk, words, counts)
+                sync_all()
+                t0 = time.perf_counter()
+                for _ in range(args.e2e_steps):
+                    _, _, est = ctx.scan_batch(b_prog, disk, words, counts)
+                sync_all()
+                dt = (time.perf_counter() - t0) / args.e2e_steps
+                bloom_first[key] = {"value": b_rows / dt, "unit": "rows/s", "ms_per_step": 1000 * dt, "h2d_bytes_per_step": int(est.h2d_bytes), "matched": int(counts.sum()),
+                                    "staged_columns": int(est.staged_columns), "pruned_columns": int(est.pruned_columns)}
+            if keep is None:
+                os.environ.pop("VLSCAN_BLOOM_FIRST", None)
+            else:
+                os.environ["VLSCAN_BLOOM_FIRST"] = keep
+            bloom_first["same_matches"] = bloom_first["one_go"]["matched"] == bloom_first["bloom_first"]["matched"]
+            del disk
+        except Exception as e:
+            bloom_first = {"error": str(e)[:200]}
 
     if rank == 0:
         ms, steps = m["ms"], m["steps"]
@@ -448,7 +487,7 @@ def main():
                          "traffic_source": (tr.get("source") if tr else "no ncu --set full capture of this exact launch size under profiles/ (profiles/ncu_traffic_r02.json lists the ones that exist)"),
                          "peak_source": peak_src, "kernel_ms_per_launch": m["k_avg"], "algorithmic_bytes_per_launch": int(m["kbytes"]),
                          "kernel_share_of_step": m["share"]},
-            "parity": parity, "e2e": e2e, "cpu_baseline": cpu, "cpu_baseline_post_zstd": cpu_post, "extra_workloads": extra or None,
+            "parity": parity, "e2e": e2e, "cpu_baseline": cpu, "cpu_baseline_post_zstd": cpu_post, "extra_workloads": extra or None, "e2e_bloom_first_staging": bloom_first,
         }
         if fallback_note:
             out["config"]["rows_note"] = "wanted %d rows/GPU: %s" % (want_rows, fallback_note)
