@@ -675,7 +675,8 @@ class PartWriter:
         for i in range(L.vlo_part_writer_nfiles(self.h)):
             n, nl, d, dl = C.c_void_p(), C.c_uint64(), C.c_void_p(), C.c_uint64()
             L.vlo_part_writer_file(self.h, C.c_uint64(i), C.byref(n), C.byref(nl), C.byref(d), C.byref(dl))
-            files[C.string_at(n, nl.value).decode()] = C.string_at(d, dl.value)
+            # ctypes.string_at takes a C int: a values file of a large part is longer than 2 GiB
+            files[C.string_at(n, nl.value).decode()] = (C.c_char * dl.value).from_address(d.value).raw if dl.value else b""
         return files
 
 

@@ -833,16 +833,15 @@ static __device__ __forceinline__ void scan_vector(const DevProgram& P, const Ba
     const uint32_t n = (uint32_t)c.data_len;
     // vectors past the end of the data were streamed as zeros; a zero word can only match a pattern of NUL bytes, rejected by the bounds below
     const uint4 v = pos < n ? __ldg((const uint4*)(B.arena + c.data_off + pos)) : make_uint4(0, 0, 0, 0);
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        uint32_t m = scan_word_hits<MASKED>(w[i], sp);
-        while (m) {
-            const int r = __ffs((int)m) - 1; m &= m - 1;
-            const int64_t q = (int64_t)pos + 4 * i + sp.delta[r];
-            if (q < 0 || q + (int64_t)sp.needle_len > (int64_t)n) continue;
-            scan_verify_lane(P, B, c, sp, b, row_off8, (uint32_t)q, leaf_bm);
-        }
+    // All candidates of the vector are collected first (bit 4 i + r: word i matches pattern r) and verified in ONE loop: with the verification
+    // nested inside the loop over the words, the lanes of a draining warp - each with its candidate in a different word - took turns through four
+    // copies of it, a quarter of the lanes at a time (ncu at 50 % candidate rows: 7.6 active lanes per instruction, 60 % of all instructions).
+    uint32_t m = scan_word_hits<MASKED>(v.x, sp) | scan_word_hits<MASKED>(v.y, sp) << 4 | scan_word_hits<MASKED>(v.z, sp) << 8 | scan_word_hits<MASKED>(v.w, sp) << 12;
+    while (m) {
+        const int j = __ffs((int)m) - 1; m &= m - 1;
+        const int64_t q = (int64_t)pos + (j & ~3) + sp.delta[j & 3];
+        if (q < 0 || q + (int64_t)sp.needle_len > (int64_t)n) continue;
+        scan_verify_lane(P, B, c, sp, b, row_off8, (uint32_t)q, leaf_bm);
     }
 }
 
@@ -882,22 +881,25 @@ static __device__ __forceinline__ bool scan_tile(const DevProgram& P, const Batc
 #pragma unroll
         for (int u = 0; u < VL_SCAN_UNROLL; u++) hits |= scan_vector_hit<MASKED>(v[u], sp) << u;
         if (!__any_sync(0xffffffffu, hits != 0)) continue;
-        // some lane has a candidate: the whole warp reserves queue slots, one shared-memory atomic per vector index
+        if (INPLACE) {
+#pragma unroll 1
+            for (int u = 0; u < VL_SCAN_UNROLL; u++) if (hits >> u & 1) scan_vector<MASKED>(P, B, c, sp, b, row_off8, base + u * VL_SCAN_QSTRIDE, leaf_bm);
+            continue;
+        }
+        // some lane has a candidate: the whole warp reserves queue slots with ONE shared-memory atomic per round (lane 0 adds the number of
+        // candidate vectors of all four vector indices); a lane's slot = the warp's base + the vectors of lower indices + those of lower lanes
+        const uint32_t b0 = __ballot_sync(0xffffffffu, hits & 1), b1 = __ballot_sync(0xffffffffu, hits & 2), b2 = __ballot_sync(0xffffffffu, hits & 4), b3 = __ballot_sync(0xffffffffu, hits & 8);
+        const uint32_t n0 = __popc(b0), n1 = n0 + __popc(b1), n2 = n1 + __popc(b2), n3 = n2 + __popc(b3);
+        uint32_t at0 = 0;
+        if (lane == 0) at0 = atomicAdd(s_cnt, n3);
+        at0 = __shfl_sync(0xffffffffu, at0, 0);
+        const uint32_t below = (1u << lane) - 1u;
+        const uint32_t bal[4] = {b0, b1, b2, b3}, first[4] = {at0, at0 + n0, at0 + n1, at0 + n2};
 #pragma unroll
         for (int u = 0; u < VL_SCAN_UNROLL; u++) {
-            const bool mine = hits >> u & 1;
-            const uint32_t pos = base + u * VL_SCAN_QSTRIDE;
-            if (INPLACE) { if (mine) scan_vector<MASKED>(P, B, c, sp, b, row_off8, pos, leaf_bm); continue; }
-            const uint32_t m = __ballot_sync(0xffffffffu, mine);
-            if (!m) continue;
-            const int leader = __ffs((int)m) - 1;
-            uint32_t at0 = 0;
-            if ((int)lane == leader) at0 = atomicAdd(s_cnt, (uint32_t)__popc(m));
-            at0 = __shfl_sync(0xffffffffu, at0, leader);
-            if (mine) {
-                const uint32_t at = at0 + __popc(m & ((1u << lane) - 1u));
-                if (at < VL_SCAN_QCAP) s_q[at] = ScanCand{b, pos}; else overflow = true;
-            }
+            if (!(hits >> u & 1)) continue;
+            const uint32_t at = first[u] + __popc(bal[u] & below);
+            if (at < VL_SCAN_QCAP) s_q[at] = ScanCand{b, base + u * VL_SCAN_QSTRIDE}; else overflow = true;
         }
     }
     return overflow;
