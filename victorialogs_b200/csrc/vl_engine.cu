@@ -237,10 +237,8 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
             }
         };
         if (nt <= 1) { work(0); return; }
-        std::vector<std::thread> th;
-        for (int t = 1; t < nt; t++) th.emplace_back(work, t);
-        work(0);
-        for (auto& x : th) x.join();
+        if (!ctx->pool) ctx->pool = new HostPool;
+        ctx->pool->run(nt, work);
     };
     auto flush = [&]() {
         if (!chunk_open || !fill) { chunk_open = false; fill = 0; segs.clear(); return; }
@@ -270,13 +268,15 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
         for (int k = 0; k < 2; k++) { evs[k] = events.make(); VL_CUDA(cudaEventRecord(evs[k], cs)); }
     };
     bool all_pinned = true;
-    auto copy_pieces = [&](const std::vector<Piece>& pieces, uint8_t* base) {
+    // pieces [i0, i1) of the list (all of it by default); the staging ring is flushed at the end of every call
+    auto copy_pieces = [&](const std::vector<Piece>& pieces, uint8_t* base, size_t i0 = 0, size_t i1 = SIZE_MAX) {
     dev_base = base;
-    size_t i = 0;
-    while (i < pieces.size()) {
+    size_t i = i0;
+    const size_t end = std::min(i1, pieces.size());
+    while (i < end) {
         // maximal run of pieces laid out identically on both sides (same stride between source and destination)
         size_t j = i;
-        while (j + 1 < pieces.size() && pieces[j + 1].src > pieces[j].src && pieces[j + 1].src - pieces[i].src == (ptrdiff_t)(pieces[j + 1].dst - pieces[i].dst)) j++;
+        while (j + 1 < end && pieces[j + 1].src > pieces[j].src && pieces[j + 1].src - pieces[i].src == (ptrdiff_t)(pieces[j + 1].dst - pieces[i].dst)) j++;
         uint64_t run_len = (pieces[j].dst - pieces[i].dst) + pieces[j].len;
         // one DMA for the whole run (gaps included) only when the run lies inside a single page-locked allocation: two pinned buffers that
         // merely line up could have pageable memory between them
@@ -310,7 +310,7 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
                 fill += take; done += take;
             }
             // pack the inter-piece slack (zero in the arena already) when the next piece follows closely, so chunks stay large
-            if (i + 1 < pieces.size()) {
+            if (i + 1 < end) {
                 uint64_t gap = pieces[i + 1].dst - (pc.dst + pc.len);
                 if (gap <= 64 && fill + gap < CH) { if (gap) segs.push_back({nullptr, fill, (size_t)gap}); fill += gap; } else flush();
             }
@@ -320,6 +320,14 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
     };
     // Pre-pass: the compressed bytes of on-disk values blocks are shipped first (their place in the staging buffer is a running sum), so
     // that the DMA engine is busy while the host walks frame and block headers.
+    bool zlazy = false; size_t zcopied = 0;   // zpieces[0, zcopied) are on their way to the compressed staging buffer
+    auto advance_z = [&](uint64_t limit) {      // enqueue every compressed piece that starts below `limit`
+        size_t hi = zcopied;
+        while (hi < zpieces.size() && zpieces[hi].dst < limit) hi++;
+        if (hi == zcopied) return;
+        marking = true; copy_pieces(zpieces, ctx->zsrc.as<uint8_t>(), zcopied, hi); marking = false;
+        zcopied = hi;
+    };
     std::vector<ZValuesBlock> zv, zts; std::vector<ZValuesInfo> zinfo; size_t zbad = SIZE_MAX, zo = 0, zt = 0; std::string zmsg;
     std::vector<DevTimestamps> tsv; bool any_ts = false;
     struct TsFrame { uint64_t block; uint32_t frame; uint64_t rel; };
@@ -336,7 +344,10 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
             if (blk.timestamps_len) zpieces.push_back({blk.timestamps, blk.timestamps_len, zc});
             zc += blk.timestamps_len;
         }
-        if (!zpieces.empty()) { ctx->zsrc.ensure(zc + 512); marking = true; copy_pieces(zpieces, ctx->zsrc.as<uint8_t>()); marking = false; }
+        // Page-locked sources: everything is enqueued right away (asynchronous DMA).  Pageable sources (a part's mmap()ed files) have to be packed
+        // through the staging ring by this thread: that is done lazily, launch group by launch group, from the decoder's group hook below, so
+        // that the device decodes group g while the host packs group g + 1 (packing it all here would finish before the first kernel starts).
+        if (!zpieces.empty()) { ctx->zsrc.ensure(zc + 512); zlazy = !pinned_range_covers(zpieces[0].src, zpieces[0].len); if (!zlazy) advance_z(UINT64_MAX); }
         // frame, block and section headers of all of them, on several host threads; a malformed block is reported when the loop below gets to it
         zinfo.resize(zv.size());
         const double t_w = now();
@@ -472,10 +483,12 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
     if (dbg) t_h2d = now();
     if (have_z) {
         zjob.set_group_hook([&](uint64_t src_end) {
+            if (zlazy) advance_z(src_end);
             for (auto& m : zmarks) if (m.first >= src_end) { VL_CUDA(cudaStreamWaitEvent(ctx->stream, m.second, 0)); return; }
             if (!zmarks.empty()) VL_CUDA(cudaStreamWaitEvent(ctx->stream, zmarks.back().second, 0));
         });
         zjob.run(ctx, ctx->zsrc.as<uint8_t>(), arena_buf.as<uint8_t>());
+        if (zlazy) advance_z(UINT64_MAX);
         if (dbg) t_zrun = now();
     }
     copy_pieces(pieces, arena_buf.as<uint8_t>());
@@ -810,6 +823,7 @@ void vlscan_ctx_free(vlscan_ctx* ctx) {
     ctx->zsrc.release(); ctx->zcols.release(); ctx->ztest.release(); ctx->ts_vals.release();
     for (DevBuf* b : {&ctx->hit_block, &ctx->glens, &ctx->goffs, &ctx->gtiles, &ctx->gout, &ctx->gstat}) b->release();
     zstd_dev_free(ctx->zdev);
+    delete ctx->pool;
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     delete ctx->recycle;
     for (auto& e : ctx->scan_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
