@@ -95,6 +95,22 @@ def test_threaded_header_walk_under_thread_sanitizer(tmp_path, oracle):
     assert "WARNING: ThreadSanitizer" not in r.stderr
 
 
+def test_host_pool_under_thread_sanitizer(tmp_path):
+    """tests/host_asan/pool_tsan.cpp: the persistent packing threads of a ctx (csrc/vl_hostpool.h), thousands of jobs of 1..33 indices back to back."""
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no g++")
+    exe = tmp_path / "pool_tsan"
+    r = subprocess.run([gxx, "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-fno-omit-frame-pointer", "-pthread", "-I", os.path.join(ROOT, "victorialogs_b200", "csrc"),
+                        os.path.join(ROOT, "tests", "host_asan", "pool_tsan.cpp"), "-o", str(exe)], capture_output=True, text=True, timeout=300)
+    if r.returncode != 0 and "tsan" in r.stderr and "cannot find" in r.stderr:
+        pytest.skip("ThreadSanitizer runtime not installed")
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run([str(exe), "3000"], capture_output=True, text=True, timeout=600, env=dict(os.environ, TSAN_OPTIONS="halt_on_error=1"))
+    assert r.returncode == 0, (r.returncode, r.stdout[-500:], r.stderr[-4000:])
+    assert r.stdout.startswith("ok total=") and "WARNING: ThreadSanitizer" not in r.stderr
+
+
 def test_next_predicates_build_as_device_code(tmp_path):
     """csrc/vl_anycase.cuh is host+device: its host builds are checked against the oracle (tests/test_abi_cpu.py); here nvcc has to accept
     the same functions inside a kernel for sm_100a - no stack frame, no spills."""
