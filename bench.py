@@ -141,6 +141,29 @@ def host_info():
     return info
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """N > 1: the ranks of a box share its host cores, its memory controllers and its PCIe roots.  Keep a rank's threads (and with them the
+    pinned staging memory they touch first) on the NUMA node its GPU hangs off, so that H2D copies do not cross the socket interconnect."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"], capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus)}
+    except Exception:
+        return None
+
+
 def oracle():
     ref = os.path.join(ROOT, "oracle", "_ref", "liboracle_zstd157.so")
     if os.path.exists(ref):
@@ -236,6 +259,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; libvlscan has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = vs.Ctx(local_rank)
@@ -491,6 +515,8 @@ def main():
         }
         if fallback_note:
             out["config"]["rows_note"] = "wanted %d rows/GPU: %s" % (want_rows, fallback_note)
+        if numa:
+            out["config"]["host_affinity"] = "each rank's threads bound to the NUMA node of its GPU (rank 0: node %d, %d CPUs)" % (numa["numa_node"], numa["cpus"])
         if m["totals"] is not None:
             out["allreduced_totals_over_timed_steps"] = {"rows": m["totals"][0], "rows_matched": m["totals"][1], "blocks_matched": m["totals"][2]}
         print(json.dumps(out), flush=True)

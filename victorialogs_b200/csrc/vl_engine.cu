@@ -253,13 +253,21 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
     auto is_pinned = [&](const void* p) { cudaPointerAttributes a; if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; } return a.type == cudaMemoryTypeHost; };
     // Is [p, p + len) inside ONE page-locked allocation?  The runtime API only classifies single addresses; the driver knows the range of the
     // allocation an address belongs to (cuPointerGetAttribute RANGE_START_ADDR / RANGE_SIZE).  libcuda is always there when a device is.
+    // Pointer queries cost microseconds each and a part's descriptors come as tens of thousands of small pieces (timestamps, const values) out of
+    // the same mmap()ed files: the last answers are remembered.  A 2 MiB-aligned region around a pageable address is taken as pageable as a whole
+    // (if a page-locked allocation begins inside it, its pieces merely take the staging ring), a page-locked allocation by its exact range.
+    uintptr_t pageable_lo = 1, pageable_hi = 0, locked_lo = 1, locked_hi = 0;
     auto pinned_range_covers = [&](const uint8_t* p, uint64_t len) -> bool {
         typedef int (*attr_fn)(void*, int, unsigned long long);
         static const attr_fn fn = [] { void* h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL); return h ? (attr_fn)dlsym(h, "cuPointerGetAttribute") : (attr_fn) nullptr; }();
-        if (!is_pinned(p)) return false;
+        const uintptr_t a = (uintptr_t)p;
+        if (a >= pageable_lo && a < pageable_hi) return false;
+        if (a >= locked_lo && a + len <= locked_hi) return true;
+        if (!is_pinned(p)) { pageable_lo = a & ~(uintptr_t)((2u << 20) - 1); pageable_hi = pageable_lo + (2u << 20); return false; }
         if (!fn) return len <= 1 || (len <= 4096 && is_pinned(p + len - 1));   // no driver entry point: only what single-address checks can vouch for
         unsigned long long base = 0; size_t size = 0;
         if (fn(&base, 11 /* CU_POINTER_ATTRIBUTE_RANGE_START_ADDR */, (unsigned long long)(uintptr_t)p) != 0 || fn(&size, 12 /* CU_POINTER_ATTRIBUTE_RANGE_SIZE */, (unsigned long long)(uintptr_t)p) != 0) return false;
+        if (size) { locked_lo = (uintptr_t)base; locked_hi = (uintptr_t)(base + size); }
         return (unsigned long long)(uintptr_t)p >= base && (unsigned long long)(uintptr_t)p + len <= base + size;
     };
     auto need_stage = [&]() {
