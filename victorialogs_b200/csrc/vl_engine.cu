@@ -317,10 +317,12 @@ static void do_upload(vlscan_ctx* ctx, const char* const* field_names, const siz
                 segs.push_back({pc.src + done, fill, take});
                 fill += take; done += take;
             }
-            // pack the inter-piece slack (zero in the arena already) when the next piece follows closely, so chunks stay large
+            // pack the space up to the next piece as zeros when it follows closely, so chunks stay large: between two pieces of the copied part
+            // there is nothing but alignment slack and empty reservations (a bloom filter left on the host is 48 bytes of them), zero in the
+            // arena already.  With a 64-byte limit every timestamps block of a part was a chunk, a DMA and an event of its own: 16 k per batch.
             if (i + 1 < end) {
                 uint64_t gap = pieces[i + 1].dst - (pc.dst + pc.len);
-                if (gap <= 64 && fill + gap < CH) { if (gap) segs.push_back({nullptr, fill, (size_t)gap}); fill += gap; } else flush();
+                if (gap <= 1024 && fill + gap < CH) { if (gap) segs.push_back({nullptr, fill, (size_t)gap}); fill += gap; } else flush();
             }
         }
     }
