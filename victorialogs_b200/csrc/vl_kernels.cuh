@@ -934,30 +934,23 @@ static __global__ void __launch_bounds__(VL_SCAN_THREADS, 5) k_substr_scan(const
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
     const uint32_t ntiles = work_count[WC_TILES];
-    // The CTA meets at a barrier after every SECOND tile (and after its last one): there the queue is drained if it is worth a pass of the
-    // whole CTA.  A barrier per tile made the warps wait for the slowest one every 64 KiB: 2.9 of 31 stall cycles per issued instruction.
-    bool overflow = false, have_prev = false;
-    uint32_t b_prev = 0, t_prev = 0;
     for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const uint32_t b = __ldg(tile_block + t), tile0 = __ldg(tile_off + t);
         const DevColumn& c = B.cols[(uint64_t)b * B.nfields + slot];
-        if (tile0 + VL_TILE_BYTES <= (uint32_t)c.data_len) overflow |= scan_tile<MASKED, true, false>(P, B, c, sp, b, row_off8, leaf_bm, s_q, &s_cnt, tile0);
-        else overflow |= scan_tail_tile<MASKED>(P, B, c, sp, b, row_off8, leaf_bm, s_q, &s_cnt, tile0);
-        if (!have_prev && t + gridDim.x < ntiles) { have_prev = true; b_prev = b; t_prev = tile0; continue; }   // uniform for the CTA
-        // drain if thread 0 sees enough entries (the barrier makes the decision uniform), or if some candidate vector of these tiles did not fit
+        bool overflow;
+        if (tile0 + VL_TILE_BYTES <= (uint32_t)c.data_len) overflow = scan_tile<MASKED, true, false>(P, B, c, sp, b, row_off8, leaf_bm, s_q, &s_cnt, tile0);
+        else overflow = scan_tail_tile<MASKED>(P, B, c, sp, b, row_off8, leaf_bm, s_q, &s_cnt, tile0);
+        // end of the tile: drain the queue if it is worth a pass of the whole CTA (thread 0 decides; the barrier makes the decision uniform),
+        // or if some candidate vector of this tile did not fit
         if (__syncthreads_or((threadIdx.x == 0 && s_cnt >= VL_SCAN_QFLUSH) || overflow)) {
-            // candidates that did not fit were dropped: the tiles are gone over again with verification in place (bits are OR-ed, so the
+            // candidates that did not fit were dropped: the tile is gone over again with verification in place (bits are OR-ed, so the
             // candidates that did make it into the queue and are verified again below change nothing)
-            if (__syncthreads_or(overflow)) {
-                if (have_prev) scan_tile_inplace<MASKED>(P, B, B.cols[(uint64_t)b_prev * B.nfields + slot], sp, b_prev, row_off8, leaf_bm, t_prev);
-                scan_tile_inplace<MASKED>(P, B, c, sp, b, row_off8, leaf_bm, tile0);
-            }
+            if (__syncthreads_or(overflow)) scan_tile_inplace<MASKED>(P, B, c, sp, b, row_off8, leaf_bm, tile0);
             scan_drain<MASKED>(P, B, slot, sp, row_off8, leaf_bm, s_q, min(s_cnt, (uint32_t)VL_SCAN_QCAP));
             __syncthreads();
             if (threadIdx.x == 0) s_cnt = 0;
             __syncthreads();
         }
-        overflow = false; have_prev = false;
     }
     __syncthreads();
     scan_drain<MASKED>(P, B, slot, sp, row_off8, leaf_bm, s_q, min(s_cnt, (uint32_t)VL_SCAN_QCAP));
