@@ -637,7 +637,7 @@ struct ScanRun {
                 VL_CUDA(cudaEventRecord(evp.second, ctx->stream));
             }
             // per-row matcher (string exact / in / general regexp; numeric columns through text); persistent grid over the ACT_ROW work list
-            if (may_row) { k_row_match<<<persistent, 256, 0, ctx->stream>>>(P, B, (uint32_t)leaf_idx, slot, row_blocks, wc, action, payload, reg, ro, leaf_bm); launch_check(ctx); }
+            if (may_row) { k_row_match<<<ctx->sm_count * ctx->row_occ, 256, 0, ctx->stream>>>(P, B, (uint32_t)leaf_idx, slot, row_blocks, wc, action, payload, reg, ro, leaf_bm); launch_check(ctx); }
             if (has_dict || has_numeric) { k_word_match<<<cdiv(B.nwords, 128), 128, 0, ctx->stream>>>(P, B, (uint32_t)leaf_idx, slot, action, payload, reg, leaf_bm, stats); launch_check(ctx); }
         }
         if (L.kind == F_TIME && B.nwords) {   // blocks the range only partly covers: decode their timestamps, compare per row
@@ -817,6 +817,8 @@ vlscan_ctx* vlscan_ctx_create(int device) {
         VL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->scan_occ[0], k_substr_scan<false>, VL_SCAN_THREADS, 0));
         VL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->scan_occ[1], k_substr_scan<true>, VL_SCAN_THREADS, 0));
         for (int& o : ctx->scan_occ) o = std::max(o, 1);
+        VL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->row_occ, k_row_match, 256, 0));
+        ctx->row_occ = std::max(ctx->row_occ, 1);
     });
     if (rc) { delete ctx; return nullptr; }
     return ctx;

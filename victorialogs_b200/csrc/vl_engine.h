@@ -108,6 +108,7 @@ struct vlscan_ctx {
     uint64_t last_launches = 0;
     int sm_count = 148;
     int scan_occ[2] = {1, 1};              // resident CTAs per SM of k_substr_scan<false> / <true> on this device
+    int row_occ = 1;                       // ... and of k_row_match (its persistent grid is exactly the resident set)
     void* ensure_pinned(size_t n);
 };
 

@@ -1001,7 +1001,10 @@ static __global__ void k_word_match(DevProgram P, BatchView B, uint32_t leaf_idx
 // ---- generic per-row matcher: one warp per bitmap word, lanes take rows l and l+32 ------------------------------------------------------------
 // exact / in() / regexp-without-literal-prefix on string columns; numeric columns that must be formatted to text first.
 // Persistent grid over the ACT_ROW work list of k_plan_leaf: work item j = block work_blocks[j]; its bitmap words are dealt out to the CTA's warps.
-static __global__ void k_row_match(DevProgram P, BatchView B, uint32_t leaf_idx, int slot, const uint32_t* __restrict__ work_blocks,
+// The kernel is a chain of dependent loads per block and per bitmap word (work list -> column header -> register word -> lens -> row bytes), so it
+// lives on resident warps: capped at 64 registers (4 CTAs per SM; the rarely taken predicates spill a little) it runs the `path:api*` leaf of C4
+// in a quarter of the time it took with the 153 registers (1 CTA per SM) the compiler picks on its own.
+static __global__ void __launch_bounds__(256, 4) k_row_match(DevProgram P, BatchView B, uint32_t leaf_idx, int slot, const uint32_t* __restrict__ work_blocks,
                                    const uint32_t* __restrict__ work_count, const uint8_t* __restrict__ action, const uint64_t* __restrict__ payload, const uint64_t* __restrict__ reg,
                                    const uint32_t* __restrict__ row_off8, uint64_t* __restrict__ leaf_bm) {
   const uint32_t nwork = work_count[WC_ROW];
