@@ -1007,19 +1007,29 @@ static __global__ void k_word_match(DevProgram P, BatchView B, uint32_t leaf_idx
 static __global__ void __launch_bounds__(256, 4) k_row_match(DevProgram P, BatchView B, uint32_t leaf_idx, int slot, const uint32_t* __restrict__ work_blocks,
                                    const uint32_t* __restrict__ work_count, const uint8_t* __restrict__ action, const uint64_t* __restrict__ payload, const uint64_t* __restrict__ reg,
                                    const uint32_t* __restrict__ row_off8, uint64_t* __restrict__ leaf_bm) {
-  const uint32_t nwork = work_count[WC_ROW];
+  if (work_count[WC_ROW] == 0) return;   // k_plan_leaf sent no block of the batch to the row matcher for this leaf
   const DevLeaf& L = P.leaves[leaf_idx];
-  for (uint32_t j = blockIdx.x; j < nwork; j += gridDim.x) {
-    const uint32_t b = work_blocks[j];
+  // Behind a selective filter of an AND chain most bitmap words are zero (like bm.forEachSetBit, bitmap.go:128-153, only rows that are still
+  // selected are looked at).  A warp therefore reads 32 consecutive register words at once - one word per lane, coalesced - and goes through
+  // the live ones among them one after the other; dead words cost 8 bytes of a coalesced load instead of a dependent round trip each.
+  // (work_blocks, the block list, is not walked any more: the words of blocks with another action are dropped by the action test below.)
+  const uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5), warp = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  for (uint64_t base = warp * 32; base < B.nwords; base += nwarps * 32) {
+    uint64_t live_l = 0; uint32_t b_l = 0;
+    if (base + lane_id() < B.nwords) {
+        live_l = reg[base + lane_id()];
+        if (live_l) { b_l = B.word_block[base + lane_id()]; const uint8_t a = action[b_l]; if (a < ACT_ROW || a > ACT_ROW_IN) live_l = 0; }
+    }
+    uint32_t todo = __ballot_sync(0xffffffffu, live_l != 0);
+   while (todo) {
+    const int src = __ffs((int)todo) - 1; todo &= todo - 1;
+    const uint64_t gw = base + (uint32_t)src;
+    const uint64_t live = __shfl_sync(0xffffffffu, live_l, src);
+    const uint32_t b = __shfl_sync(0xffffffffu, b_l, src);
     const DevColumn& c = B.cols[(uint64_t)b * B.nfields + slot];
     const uint32_t rows = B.blk_rows[b];
     const uint8_t act = action[b]; const uint64_t pay = payload[b];
-    const uint64_t w_lo = B.blk_word_off[b], w_hi = B.blk_word_off[b + 1];
-   for (uint64_t gw = w_lo + (threadIdx.x >> 5); gw < w_hi; gw += blockDim.x >> 5) {
-    // like bm.forEachSetBit (bitmap.go:128-153) only rows that are still selected are looked at: behind a selective filter of an AND chain
-    // that is a small fraction of the block
-    const uint64_t live = reg[gw];
-    if (!live) { if (lane_id() == 0) leaf_bm[gw] = 0; continue; }
+    const uint64_t w_lo = B.blk_word_off[b];
     uint32_t r0 = (uint32_t)(gw - w_lo) * 64;
     const uint8_t* data = B.arena + c.data_off;
     const uint8_t* lens = B.arena + c.lens_off;
