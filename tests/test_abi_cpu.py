@@ -592,3 +592,33 @@ def test_no_cpu_fallback():
     with pytest.raises(vs.VlscanError) as e:
         vs.Ctx(0)
     assert "no CUDA device" in str(e.value)
+
+
+def test_token_rune_table_against_an_independent_unicode_database():
+    """isTokenRune = unicode.IsLetter || unicode.IsDigit || '_' (tokenizer.go:142-148).  The product's and the oracle's range tables are both generated
+    from CPython's unicodedata, so comparing them with each other cannot catch a generation error.  The `regex` module carries its own
+    Unicode database (a newer version): on every code point assigned in Unicode 15.0 - Go 1.24's version - its \\p{L} / \\p{Nd} must agree
+    with what the product's tokenizer does to the code point, and everything it adds on top must be unassigned in 15.0."""
+    import unicodedata
+    regex = pytest.importorskip("regex")
+    if unicodedata.unidata_version != "15.0.0":
+        pytest.skip("needs a Python with Unicode 15.0 tables to know which code points Go 1.24 has assigned")
+    letter_or_digit = regex.compile(r"[\p{L}\p{Nd}]")
+    cps = [cp for cp in range(0x110000) if not 0xD800 <= cp <= 0xDFFF]
+    product = {}
+    for i in range(0, len(cps), 1000):
+        chunk = cps[i:i + 1000]
+        text = " ".join("a" + chr(cp) + "b" for cp in chunk).encode("utf-8")
+        tokens = set(vs.Program(vs.Filter.phrase("f", text)).leaf_tokens(0))
+        for cp in chunk:
+            product[cp] = ("a" + chr(cp) + "b").encode("utf-8") in tokens
+    newer_only = 0
+    for cp in cps:
+        ch = chr(cp)
+        independent = letter_or_digit.match(ch) is not None or ch == "_"
+        if unicodedata.category(ch) == "Cn":          # unassigned in Unicode 15.0: never a token character for Go 1.24
+            assert not product[cp], hex(cp)
+            newer_only += independent
+        else:
+            assert product[cp] == independent, (hex(cp), unicodedata.category(ch), product[cp], independent)
+    assert 1000 < newer_only < 20000                  # the other database really is a different (newer) one
