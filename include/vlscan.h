@@ -326,7 +326,18 @@ int vlscan_totals_sum(vlscan_ctx* const* ctxs, int nctx, uint64_t out4[4]);
  * and a 4 x u64 totals vector {rows, rows_matched, blocks_matched, values_bytes}. */
 int vlscan_result_device_ptrs(vlscan_ctx* ctx, void** bitmap_words, void** match_counts, void** totals4);
 
-/* End-to-end call on host buffers: upload + scan + fetch + free (what the cgo shim calls per work batch). */
+/* End-to-end call on host buffers: upload + scan + fetch + free (what the cgo shim calls per work batch; replaces the body of the worker loop,
+ * storage_search.go:1044-1062).  Only what the program can read crosses PCIe:
+ *  - bloom filters of fields no leaf / no AND-OR pre-pass ever probes stay on the host;
+ *  - when the program does probe bloom filters the call is staged bloom-first, in the reference's lazy order (getBloomFilterForColumn
+ *    block_search.go:411-439 before getValuesForColumn :444-474): headers + bloom filters, a probe pass on the device, then only the values of
+ *    the (block, column) cells some filter can reach (vlscan_stats.staged_columns / pruned_columns).  Results and accounting are identical to
+ *    staging in one go.  $VLSCAN_BLOOM_FIRST: 0 = never, 2 = always, 1 (default) = adaptive (skipped for 7 calls after a probe that left
+ *    less than 1/8 of the values bytes on the host);
+ *  - VLSCAN_STAGE_ONDISK payloads travel compressed and are regenerated in HBM.  Page-locked inputs go out as a few large DMA transfers;
+ *    pageable ones (a part's mmap()ed files) are packed through a pinned ring by $VLSCAN_HOST_THREADS threads of the ctx, launch group by
+ *    launch group, while the device decodes the previous group.
+ * The batch object is recycled inside the ctx; nothing of the call outlives it except out_bitmap_words / out_match_counts / stats. */
 int vlscan_scan_batch(vlscan_ctx* ctx, const vlscan_program* prog, const char* const* field_names, const size_t* field_name_lens,
                       uint32_t nfields, const vlscan_block* blocks, uint64_t nblocks, uint64_t* out_bitmap_words,
                       uint32_t* out_match_counts, vlscan_stats* stats);
