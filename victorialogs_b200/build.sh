@@ -11,5 +11,5 @@ for tu in vl_engine vl_gen vl_zstd; do
     pids+=($!)
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -shared -o libvlscan.so build/vl_engine.o build/vl_gen.o build/vl_zstd.o -ldl
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libvlscan.so build/vl_engine.o build/vl_gen.o build/vl_zstd.o -ldl
 echo built victorialogs_b200/libvlscan.so
