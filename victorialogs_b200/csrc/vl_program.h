@@ -236,7 +236,7 @@ class ProgramBuilder {
     std::string bytes() { uint64_t l = varuint(); if (l > n_ - i_) throw ProgError("truncated filter tree"); std::string s((const char*)p_ + i_, l); i_ += l; return s; }
 
     void typed_needles(DevLeaf& L, const std::string& s) {
-        uint64_t u; int64_t i; double f; uint32_t ip; int64_t ts;
+        uint64_t u = 0; int64_t i = 0; double f = 0; uint32_t ip = 0; int64_t ts = 0;
         bool uok = parse_u64(s, &u);
         for (int vt : {VT_UINT8, VT_UINT16, VT_UINT32, VT_UINT64}) { L.typed[vt].ok = uok; L.typed[vt].val = uok ? u : 0; }
         if (parse_i64(s, &i)) { L.typed[VT_INT64].ok = 1; L.typed[VT_INT64].val = host_zigzag(i); L.typed[VT_INT64].sval = i; }
